@@ -1,0 +1,107 @@
+// Shared helpers for the spittle_b200 CUDA engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <atomic>
+#include <cstring>
+
+#include "../../include/spittle_b200.h"
+
+namespace sb {
+
+// thread-local last error (sb_last_error)
+void set_error(const std::string& msg);
+const char* get_error();
+
+#define SB_CUDA_CHECK(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ::sb::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) +         \
+                            " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")");     \
+            return SB_ERR_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+#define SB_CHECK_ARG(cond, msg)                                                          \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            ::sb::set_error(std::string("invalid argument: ") + (msg));                  \
+            return SB_ERR_INVALID;                                                       \
+        }                                                                                \
+    } while (0)
+
+// 16-bit operand type traits: the engine runs either bf16 (north-star dtype) or f16
+// (the reference's own rounding points: ggml f16 weights x f16-rounded activations).
+template <typename T> struct Op16;
+template <> struct Op16<__nv_bfloat16> {
+    static constexpr int kUmmaFormat = 1;  // UMMA F16F32Format::BF16
+    __device__ __forceinline__ static __nv_bfloat16 from_f32(float x) { return __float2bfloat16_rn(x); }
+    __device__ __forceinline__ static float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
+    __device__ __forceinline__ static uint32_t pack2(float a, float b) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+    __device__ __forceinline__ static float2 unpack2(uint32_t u) {
+        __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+        return __bfloat1622float2(v);
+    }
+};
+template <> struct Op16<__half> {
+    static constexpr int kUmmaFormat = 0;  // UMMA F16F32Format::F16
+    __device__ __forceinline__ static __half from_f32(float x) { return __float2half_rn(x); }
+    __device__ __forceinline__ static float to_f32(__half x) { return __half2float(x); }
+    __device__ __forceinline__ static uint32_t pack2(float a, float b) {
+        __half2 v = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+    __device__ __forceinline__ static float2 unpack2(uint32_t u) {
+        __half2 v = *reinterpret_cast<__half2*>(&u);
+        return __half22float2(v);
+    }
+};
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+    // 0.5 x (1 + tanh(sqrt(2/pi) x (1 + 0.044715 x^2)))   (whisper.cpp / ggml GELU, App. C.2)
+    const float c = 0.79788456080286535588f;
+    float u = c * x * (1.0f + 0.044715f * x * x);
+    return 0.5f * x * (1.0f + tanhf(u));
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// monotone float <-> int key (for atomicMax on floats of either sign)
+__host__ __device__ __forceinline__ int float_key(float f) {
+#ifdef __CUDA_ARCH__
+    int i = __float_as_int(f);
+#else
+    int i; memcpy(&i, &f, 4);
+#endif
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__host__ __device__ __forceinline__ float key_float(int k) {
+    int i = k >= 0 ? k : k ^ 0x7fffffff;
+#ifdef __CUDA_ARCH__
+    return __int_as_float(i);
+#else
+    float f; memcpy(&f, &i, 4); return f;
+#endif
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+}  // namespace sb

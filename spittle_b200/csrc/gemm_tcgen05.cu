@@ -1,0 +1,377 @@
+// gemm_tcgen05: C[M,N] = epilogue(A[M,K] * W[N,K]^T) on the 5th-gen tensor cores (sm_100a).
+//
+// Replaces the ggml CPU mul_mat calls of the whisper.cpp encoder graph (SURVEY.md App. C.2,
+// rows a5/a6 of 8(a)): conv stem (implicit GEMM), QKV / out / MLP projections, cross-KV.
+// Reference rounding points are kept: 16-bit operands (bf16, or f16 exactly like ggml),
+// fp32 accumulation.
+//
+// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0      TMA producer : cp.async.bulk.tensor 2D loads of A (128x64) and W (256x64)
+//                              tiles, 128B-swizzled, into a 4-stage shared-memory ring
+//   warp 1      MMA issuer   : one thread issues tcgen05.mma.cta_group::1.kind::f16
+//                              (UMMA 128x256x16), accumulators in TMEM, double-buffered
+//                              (2 x 256 columns) so the epilogue of tile i overlaps tile i+1
+//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 -> registers -> (+bias, GELU,
+//                              +residual / positional embedding) -> global store
+// Synchronisation is mbarrier-only: full/empty per smem stage, tmem_full/tmem_empty per
+// accumulator stage; tcgen05.commit releases smem stages and publishes accumulators.
+// Tile order is n-fastest so the CTAs running together share each A tile through L2 and A
+// streams from HBM once; W (a few MB) stays L2-resident.
+#include "common.cuh"
+#include <cuda.h>
+#include <atomic>
+#include <mutex>
+
+namespace sb {
+extern std::atomic<uint64_t> g_launches;
+
+constexpr int kBM = 128;
+constexpr int kBN = 256;
+constexpr int kBK = 64;          // 64 x 2 B = 128 B = swizzle span
+constexpr int kStages = 4;
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kStageBytesA = kBM * kBK * 2;
+constexpr int kStageBytesB = kBN * kBK * 2;
+constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct GemmEpilogue {
+    void* out;            // [M, ldo] T or f32
+    int ldo;
+    int out_f32;          // 1: f32 output, 0: 16-bit output
+    const float* bias;    // [N] or null
+    int act;              // 0 none, 1 tanh-GELU
+    const float* residual;  // f32 [*, ldr] or null; added after activation
+    int ldr;
+    int res_row_mod;      // 0: residual row = row; >0: row % res_row_mod (positional embedding)
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address  [0,14)
+    d |= (uint64_t)1 << 16;                         // LBO (unused for swizzled K-major) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;               // SBO = 1024 B   [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    return d;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_gemm_tn(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+          GemmEpilogue ep, int M, int N, int K) {
+    extern __shared__ unsigned char smem_raw_g[];
+    const uint32_t raw = smem_u32(smem_raw_g);
+    const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024 B alignment
+    unsigned char* base_ptr = smem_raw_g + (base - raw);
+    const uint32_t bar_base = base + kStages * kStageBytes;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + kStages * kStageBytes + 128);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = (M + kBM - 1) / kBM, num_n = (N + kBN - 1) / kBN;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = (K + kBK - 1) / kBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(2 * kBN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int n_blk = tile % num_n, m_blk = tile / num_n;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+                    const uint32_t sa = base + stage * kStageBytes;
+                    tma_load_2d(sa, &tma_a, kb * kBK, m_blk * kBM, full_bar(stage));
+                    tma_load_2d(sa + kStageBytesA, &tma_b, kb * kBK, n_blk * kBN, full_bar(stage));
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=T, K-major both, N=256, M=128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)Op16<T>::kUmmaFormat << 7) |
+                                   ((uint32_t)Op16<T>::kUmmaFormat << 10) | ((uint32_t)(kBN >> 3) << 17) |
+                                   ((uint32_t)(kBM >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(as), aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * kBN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * kStageBytes;
+                    const uint64_t adesc = make_smem_desc(sa);
+                    const uint64_t bdesc = make_smem_desc(sa + kStageBytesA);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        // advance 16 elements = 32 B along K inside the swizzle atom: +2 in 16 B units
+                        tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    tc_commit(empty_bar(stage));
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar(as));
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;   // TMEM lane quarter this warp may access
+        int as = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n_blk = tile % num_n, m_blk = tile / num_n;
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            const int row = m_blk * kBM + q * 32 + lane;
+            const bool row_ok = row < M;
+            const int rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : row;
+#pragma unroll 1
+            for (int c = 0; c < kBN / 32; ++c) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kBN + c * 32);
+                tc_ld32(taddr, v);
+                tc_wait_ld();
+                const int col0 = n_blk * kBN + c * 32;
+                if (!row_ok || col0 >= N) continue;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                const bool full = col0 + 32 <= N;
+                if (full) {
+                    if (ep.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+                            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+                        }
+                    }
+                    if (ep.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(f[j]);
+                    }
+                    if (ep.residual) {
+                        const float* r = ep.residual + (int64_t)rrow * ep.ldr + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(r + j);
+                            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+                        }
+                    }
+                    if (ep.out_f32) {
+                        float* o = reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldo + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+                        T* o = reinterpret_cast<T*>(ep.out) + (int64_t)row * ep.ldo + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 u;
+                            u.x = Op16<T>::pack2(f[j], f[j + 1]);
+                            u.y = Op16<T>::pack2(f[j + 2], f[j + 3]);
+                            u.z = Op16<T>::pack2(f[j + 4], f[j + 5]);
+                            u.w = Op16<T>::pack2(f[j + 6], f[j + 7]);
+                            *reinterpret_cast<uint4*>(o + j) = u;
+                        }
+                    }
+                } else {
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = col0 + j;
+                        if (col >= N) break;
+                        float x = f[j];
+                        if (ep.bias) x += __ldg(ep.bias + col);
+                        if (ep.act == 1) x = gelu_tanh(x);
+                        if (ep.residual) x += ep.residual[(int64_t)rrow * ep.ldr + col];
+                        if (ep.out_f32) reinterpret_cast<float*>(ep.out)[(int64_t)row * ep.ldo + col] = x;
+                        else reinterpret_cast<T*>(ep.out)[(int64_t)row * ep.ldo + col] = Op16<T>::from_f32(x);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kBN));
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+// 2D row-major [rows, cols] 16-bit tensor, row stride ld elements; box = [box_rows, 64 cols], 128B swizzle
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int is_f16, int64_t rows, int64_t cols, int64_t ld,
+                 int box_rows) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return SB_ERR_CUDA; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) {
+        set_error("gemm operand must be 16-byte aligned with a 16-byte multiple row stride");
+        return SB_ERR_INVALID;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return SB_ERR_CUDA; }
+    return SB_OK;
+}
+
+static int g_num_sms = 0;
+
+int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+// A [M,K] (row stride lda), W [N,K] (row stride ldw); dtype 0 bf16 / 1 f16.
+int gemm_tn(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+            const GemmEpilogue& ep, cudaStream_t st) {
+    SB_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem");
+    SB_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm: K and N must be multiples of 8");
+    SB_CHECK_ARG(ep.out_f32 ? (ep.ldo % 4 == 0) : (ep.ldo % 8 == 0), "gemm: output row stride alignment");
+    CUtensorMap ta, tb;
+    int rc = make_tmap_2d(&ta, A, dtype, M, K, lda, kBM);
+    if (rc != SB_OK) return rc;
+    rc = make_tmap_2d(&tb, W, dtype, N, K, ldw, kBN);
+    if (rc != SB_OK) return rc;
+    const int num_tiles = ceil_div(M, kBM) * ceil_div(N, kBN);
+    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    static bool attr_done = false;
+    if (!attr_done) {
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        attr_done = true;
+    }
+    if (dtype == SB_DTYPE_F16)
+        k_gemm_tn<__half><<<grid, kGemmThreads, kGemmSmem, st>>>(ta, tb, ep, M, N, K);
+    else
+        k_gemm_tn<__nv_bfloat16><<<grid, kGemmThreads, kGemmSmem, st>>>(ta, tb, ep, M, N, K);
+    g_launches += 1;
+    SB_CUDA_CHECK(cudaGetLastError());
+    return SB_OK;
+}
+
+}  // namespace sb
+
+extern "C" int sb_gemm_tn_dev(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+                              void* out, int64_t ldo, int out_f32, const float* bias, int act,
+                              const float* residual, int64_t ldr, int res_row_mod, void* stream) {
+    SB_CHECK_ARG(A && W && out, "null pointer");
+    SB_CHECK_ARG(dtype == SB_DTYPE_BF16 || dtype == SB_DTYPE_F16, "dtype must be SB_DTYPE_BF16 or SB_DTYPE_F16");
+    sb::GemmEpilogue ep;
+    ep.out = out; ep.ldo = (int)ldo; ep.out_f32 = out_f32; ep.bias = bias; ep.act = act;
+    ep.residual = residual; ep.ldr = (int)ldr; ep.res_row_mod = res_row_mod;
+    return sb::gemm_tn(dtype, A, lda, W, ldw, M, N, K, ep, (cudaStream_t)stream);
+}

@@ -1,0 +1,212 @@
+"""GGML *legacy* Whisper model file (``ggml-*.bin``, magic 0x67676d6c) reader/writer.
+
+This is the on-disk format the reference loads through
+``WhisperEngine::load_model(&path)`` (src-tauri/src/managers/transcription.rs:262-263;
+custom ``*.bin`` discovery in src-tauri/src/managers/model.rs:267-382).  The format is
+defined by whisper.cpp (bundled by whisper-rs-sys 0.11.1, not vendored in the reference)
+and restated in SURVEY.md Appendix D:
+
+  u32 magic | 11 x i32 hparams | mel filters (i32 n_mel, i32 n_fft, f32 data) |
+  vocab (i32 n, n x (u32 len, bytes)) | tensors until EOF:
+      i32 n_dims, i32 name_len, i32 ttype, i32 ne[n_dims] (fastest-varying first),
+      name bytes, raw data
+
+The C++ loader in ``csrc/ggml_loader.cpp`` reads the same bytes; this module exists so the
+synthetic models of SURVEY.md 8(d) can be written once and loaded bit-identically by the
+oracle, the CPU baseline and the GPU engine.
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field, asdict
+from typing import Dict, List
+
+import numpy as np
+
+GGML_MAGIC = 0x67676D6C
+GGML_TYPE_F32 = 0
+GGML_TYPE_F16 = 1
+
+
+@dataclass
+class WhisperHParams:
+    n_vocab: int = 51865
+    n_audio_ctx: int = 1500
+    n_audio_state: int = 768
+    n_audio_head: int = 12
+    n_audio_layer: int = 12
+    n_text_ctx: int = 448
+    n_text_state: int = 768
+    n_text_head: int = 12
+    n_text_layer: int = 12
+    n_mels: int = 80
+    ftype: int = 1
+
+    def as_list(self) -> List[int]:
+        return [self.n_vocab, self.n_audio_ctx, self.n_audio_state, self.n_audio_head,
+                self.n_audio_layer, self.n_text_ctx, self.n_text_state, self.n_text_head,
+                self.n_text_layer, self.n_mels, self.ftype]
+
+
+# Named architectures (SURVEY.md 8(d) "Synthetic weights", Appendix E).
+ARCHS: Dict[str, WhisperHParams] = {
+    # fast CPU/GPU test shape: same structure, d_head = 64
+    "nano": WhisperHParams(n_audio_state=128, n_audio_head=2, n_audio_layer=2,
+                           n_text_state=128, n_text_head=2, n_text_layer=2, n_mels=80),
+    "micro": WhisperHParams(n_audio_state=256, n_audio_head=4, n_audio_layer=3,
+                            n_text_state=256, n_text_head=4, n_text_layer=3, n_mels=128,
+                            n_vocab=51866),
+    "small": WhisperHParams(),
+    "large-v3": WhisperHParams(n_vocab=51866, n_audio_state=1280, n_audio_head=20,
+                               n_audio_layer=32, n_text_state=1280, n_text_head=20,
+                               n_text_layer=32, n_mels=128),
+    "large-v3-turbo": WhisperHParams(n_vocab=51866, n_audio_state=1280, n_audio_head=20,
+                                     n_audio_layer=32, n_text_state=1280, n_text_head=20,
+                                     n_text_layer=4, n_mels=128),
+}
+
+
+@dataclass
+class SpecialTokens:
+    """Special token ids derived from n_vocab exactly as whisper.cpp does."""
+    eot: int
+    sot: int
+    translate: int
+    transcribe: int
+    solm: int
+    prev: int
+    nosp: int
+    not_: int
+    beg: int
+    lang_first: int
+    num_languages: int
+    blank: int  # id of the token whose text is " " (suppress_blank)
+
+    @staticmethod
+    def from_n_vocab(n_vocab: int, blank: int = 220) -> "SpecialTokens":
+        eot, sot, translate, transcribe, solm, prev, nosp, not_, beg = (
+            50256, 50257, 50357, 50358, 50359, 50360, 50361, 50362, 50363)
+        num_languages = 0
+        if n_vocab >= 51865:  # multilingual
+            num_languages = n_vocab - 51765 - 1
+            eot += 1
+            sot += 1
+            dt = num_languages - 98
+            translate += dt
+            transcribe += dt
+            solm += dt
+            prev += dt
+            nosp += dt
+            not_ += dt
+            beg += dt
+        return SpecialTokens(eot, sot, translate, transcribe, solm, prev, nosp, not_, beg,
+                             lang_first=sot + 1, num_languages=num_languages, blank=blank)
+
+
+@dataclass
+class GgmlModel:
+    hparams: WhisperHParams
+    mel_filters: np.ndarray                      # [n_mels, 201] f32
+    vocab: List[bytes]                           # id -> bytes (entries present in the file)
+    tensors: Dict[str, np.ndarray] = field(default_factory=dict)  # torch-shaped, f32 or f16
+
+    @property
+    def special(self) -> SpecialTokens:
+        blank = 220
+        for i, w in enumerate(self.vocab):
+            if w == b" ":
+                blank = i
+                break
+        return SpecialTokens.from_n_vocab(self.hparams.n_vocab, blank)
+
+    def token_bytes(self, tid: int) -> bytes:
+        """whisper_token_to_str: file vocab, else the synthesised special names."""
+        if tid < len(self.vocab):
+            return self.vocab[tid]
+        sp = self.special
+        names = {sp.eot: b"[_EOT_]", sp.sot: b"[_SOT_]", sp.translate: b"[_TRANSLATE_]",
+                 sp.transcribe: b"[_TRANSCRIBE_]", sp.solm: b"[_SOLM_]", sp.prev: b"[_PREV_]",
+                 sp.nosp: b"[_NOSP_]", sp.not_: b"[_NOT_]", sp.beg: b"[_BEG_]"}
+        if tid in names:
+            return names[tid]
+        if tid > sp.beg:
+            return b"[_TT_%d]" % (tid - sp.beg)
+        if sp.lang_first <= tid < sp.lang_first + sp.num_languages:
+            return b"[_LANG_%d]" % (tid - sp.lang_first)
+        return b"[_extra_token_%d]" % tid
+
+
+def write_ggml(path: str, model: GgmlModel) -> None:
+    hp = model.hparams
+    with open(path, "wb") as f:
+        f.write(struct.pack("<I", GGML_MAGIC))
+        f.write(struct.pack("<11i", *hp.as_list()))
+        mf = np.ascontiguousarray(model.mel_filters, dtype=np.float32)
+        assert mf.shape == (hp.n_mels, 201)
+        f.write(struct.pack("<ii", mf.shape[0], mf.shape[1]))
+        f.write(mf.tobytes())
+        f.write(struct.pack("<i", len(model.vocab)))
+        for w in model.vocab:
+            f.write(struct.pack("<I", len(w)))
+            f.write(w)
+        for name, arr in model.tensors.items():
+            if arr.dtype == np.float32:
+                ttype = GGML_TYPE_F32
+            elif arr.dtype == np.float16:
+                ttype = GGML_TYPE_F16
+            else:
+                raise ValueError(f"{name}: unsupported dtype {arr.dtype}")
+            nb = name.encode()
+            ne = list(reversed(arr.shape))  # fastest-varying first
+            f.write(struct.pack("<iii", len(ne), len(nb), ttype))
+            f.write(struct.pack("<%di" % len(ne), *ne))
+            f.write(nb)
+            f.write(np.ascontiguousarray(arr).tobytes())
+
+
+def read_ggml(path: str) -> GgmlModel:
+    with open(path, "rb") as f:
+        data = f.read()
+    off = 0
+
+    def take(fmt):
+        nonlocal off
+        v = struct.unpack_from(fmt, data, off)
+        off += struct.calcsize(fmt)
+        return v
+
+    (magic,) = take("<I")
+    if magic != GGML_MAGIC:
+        raise ValueError("bad magic 0x%08x (not a GGML legacy whisper file)" % magic)
+    hp = WhisperHParams(*take("<11i"))
+    n_mel, n_fft = take("<ii")
+    mel = np.frombuffer(data, dtype="<f4", count=n_mel * n_fft, offset=off).reshape(n_mel, n_fft).copy()
+    off += 4 * n_mel * n_fft
+    (nv,) = take("<i")
+    vocab = []
+    for _ in range(nv):
+        (ln,) = take("<I")
+        vocab.append(bytes(data[off:off + ln]))
+        off += ln
+    tensors: Dict[str, np.ndarray] = {}
+    while off < len(data):
+        n_dims, name_len, ttype = take("<iii")
+        ne = take("<%di" % n_dims)
+        name = data[off:off + name_len].decode()
+        off += name_len
+        shape = tuple(reversed(ne))
+        count = int(np.prod(shape))
+        if ttype == GGML_TYPE_F32:
+            arr = np.frombuffer(data, dtype="<f4", count=count, offset=off)
+            off += 4 * count
+        elif ttype == GGML_TYPE_F16:
+            arr = np.frombuffer(data, dtype="<f2", count=count, offset=off)
+            off += 2 * count
+        else:
+            raise ValueError(f"{name}: tensor type {ttype} (quantised) not supported yet")
+        tensors[name] = arr.reshape(shape).copy()
+    return GgmlModel(hp, mel, vocab, tensors)
+
+
+def hparams_dict(hp: WhisperHParams) -> dict:
+    return asdict(hp)
