@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Whisper transcription hot path on B200.
+
+Metric (BASELINE.json): RTFx = audio-seconds per wall-second.  Workload at N=1:
+BASELINE.json configs[1] "Whisper Small batch of 64 synthetic 30 s clips on 1xB200".
+A step = one pass of the whole hot path (log-mel -> encoder -> cross-KV -> greedy decode with
+the whisper.cpp seek loop -> text) over one batch of 64 clips through the C ABI
+(sb_transcribe_batch).  N > 1: one process per GPU (torchrun), every rank transcribes its own
+64 clips (weak scaling, no collective on the data path -- clips do not interact).
+
+  value  RTFx with the PCM already resident in HBM (device pointers handed to the C ABI)
+  e2e    RTFx with pinned HOST buffers: H2D of the PCM and D2H of tokens inside the timed region
+  roofline      tcgen05 GEMM launches (encoder + cross-KV): algorithmic FLOPs / CUDA-event time
+  cpu_baseline  the numpy oracle ("port" of whisper.cpp) on the host cores,
+                bounded sample
+  --impl reference   times that same CPU port as the reference arm (the reference itself cannot be
+                     built here: no Rust toolchain, crates not vendored -- DESIGN.md)
+
+Timing: W >= 3 warm-up steps; inputs (64 x 1.92 MB PCM plus ~4 GB of activations and 3.5 GB of
+cross-KV per step) are far larger than the 126 MB L2, so no explicit flush is needed; device
+timing with CUDA events bracketed by barrier + synchronize, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+ARCH = os.environ.get("SB_BENCH_ARCH", "small")
+CLIPS_PER_GPU = int(os.environ.get("SB_BENCH_CLIPS", "64"))
+CLIP_SECONDS = 30.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        pw = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.samples)}
+
+
+def make_clips(rank: int, n: int):
+    from spittle_b200 import synth
+    return [synth.make_clip(rank * n + i, seconds=CLIP_SECONDS) for i in range(n)]
+
+
+def model_path(arch: str) -> str:
+    from spittle_b200 import synth
+    d = os.environ.get("SB_MODEL_DIR", "/tmp/spittle_b200_models")
+    return synth.ensure_model_file(arch, d)
+
+
+def cpu_port_rtfx(arch: str, n_clips: int, threads_note: bool = True):
+    """Oracle (numpy port of the whisper.cpp path) timed on the host cores: bounded sample."""
+    from oracle import whisper_ref
+    from spittle_b200 import ggml_format
+    model = ggml_format.read_ggml(model_path(arch))
+    oracle = whisper_ref.WhisperOracle(model, act_f16=True)
+    clips = make_clips(0, n_clips)
+    t0 = time.perf_counter()
+    n_tok = 0
+    n_win = 0
+    for x in clips:
+        _, kept, wins = oracle.full(x, whisper_ref.DecodeConfig())
+        n_tok += sum(len(w.tokens) for w in wins)
+        n_win += len(wins)
+    dt = time.perf_counter() - t0
+    return (n_clips * CLIP_SECONDS) / dt, dt, n_tok, n_win
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference path, all host threads numpy/BLAS will use."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    vals = []
+    for i in range(args.warmup if args.warmup < 1 else 0):
+        pass
+    steps = max(1, min(args.steps, 3))
+    for _ in range(steps):
+        v, dt, n_tok, n_win = cpu_port_rtfx(ARCH, 1)
+        vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals])) * 1e3
+    line = {
+        "impl": "reference", "metric": "RTFx (audio-s per wall-s)", "value": value, "unit": "x real-time",
+        "n_gpus": args.gpus, "steps": steps, "warmup": 0, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16 (ggml rounding points) / f32 accumulate", "data": "synthetic",
+        "config": {"workload": f"Whisper {ARCH} greedy decode, bounded sample: 1 synthetic 30 s 16 kHz clip per step "
+                               f"of the {CLIPS_PER_GPU}-clip batch (clip 0)", "arch": ARCH},
+        "cpu_baseline": {"value": value, "unit": "x real-time", "cores": cores, "kind": "port",
+                         "sample": "1 clip x 30 s per step, numpy/OpenBLAS oracle restating whisper.cpp "
+                                   "(reference not buildable here: no cargo/rustc, crates not vendored)"},
+        "e2e": {"value": value, "unit": "x real-time", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default=os.environ.get("SB_BENCH_DTYPE", "f16"), choices=["f16", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from spittle_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: spittle_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    warmup = max(3, args.warmup)
+    peaks, peak_src = load_peaks()
+
+    # rank 0 writes the synthetic model file once; other ranks wait for it
+    if rank == 0:
+        path = model_path(ARCH)
+    if dist:
+        dist.barrier()
+    path = model_path(ARCH)
+    dtype = capi.SB_DTYPE_F16 if args.dtype == "f16" else capi.SB_DTYPE_BF16
+    eng = capi.Engine(path, device=local_rank, max_batch=CLIPS_PER_GPU, dtype=dtype)
+    clips = make_clips(rank, CLIPS_PER_GPU)
+    n = clips[0].shape[0]
+    host = torch.from_numpy(np.stack(clips)).pin_memory()
+    devbuf = host.to(torch.device("cuda", local_rank))
+    params = capi.default_params()
+    host_ptrs = [host.data_ptr() + i * n * 4 for i in range(CLIPS_PER_GPU)]
+    dev_ptrs = [devbuf.data_ptr() + i * n * 4 for i in range(CLIPS_PER_GPU)]
+    sizes = [n] * CLIPS_PER_GPU
+    audio_s = CLIPS_PER_GPU * CLIP_SECONDS
+
+    eng_stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(ptrs, k, profile):
+        eng.set_profile(profile)
+        eng.stats(reset=True)
+        l0 = capi.launch_count()
+        sync_all()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(eng_stream)          # CUDA events on the stream the engine launches on
+        res = None
+        for _ in range(k):
+            res = eng.transcribe_batch_ptrs(ptrs, sizes, params)     # returns host text: device work is complete
+        e1.record(eng_stream)
+        torch.cuda.synchronize()
+        ms_dev = e0.elapsed_time(e1)
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = max(ms_dev, wall)    # the call is synchronous: wall additionally covers host bookkeeping
+        if dist:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, res, eng.stats(reset=True), capi.launch_count() - l0
+
+    for _ in range(warmup):
+        eng.transcribe_batch_ptrs(dev_ptrs, sizes, params)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev, res, st_dev, launches = timed(dev_ptrs, args.steps, profile=True)
+    ms_e2e, res2, st_e2e, _ = timed(host_ptrs, args.steps, profile=False)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    value = world * audio_s * args.steps / (ms_dev / 1e3)
+    e2e = world * audio_s * args.steps / (ms_e2e / 1e3)
+    gemm_tflops = st_dev["gemm_flops"] / max(st_dev["gemm_ms"], 1e-9) / 1e9
+    attn_tflops = st_dev["attn_flops"] / max(st_dev["attn_ms"], 1e-9) / 1e9
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return 0
+
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt, n_tok, n_win = cpu_port_rtfx(ARCH, 1)
+        cpu_base = {"value": v, "unit": "x real-time", "cores": os.cpu_count() or 1, "kind": "port",
+                    "sample": f"1 clip x 30 s of the same batch (clip 0), {n_win} window(s), {n_tok} decoded tokens, "
+                              f"{dt:.1f} s CPU wall; numpy/OpenBLAS oracle"}
+    steps = args.steps
+    line = {
+        "metric": "RTFx (audio-s per wall-s)", "value": value, "unit": "x real-time", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"Whisper {ARCH} greedy decode, batch of {CLIPS_PER_GPU} synthetic 30 s 16 kHz clips per GPU "
+                               "(BASELINE.json configs[1]), random-init 'sharp' recipe seed 42, language en, timestamps on, "
+                               "no fallback", "arch": ARCH, "clips_per_gpu": CLIPS_PER_GPU,
+                   "l2": "inputs+activations per step >> 126 MB L2; no explicit flush",
+                   "windows_per_step": st_dev["windows"] / steps, "decoder_steps_per_step": st_dev["decoder_steps"] / steps,
+                   "tokens_per_step": st_dev["tokens_sampled"] / steps,
+                   "ms_mel": st_dev["mel_ms"] / steps, "ms_encode": st_dev["encode_ms"] / steps,
+                   "ms_decode": st_dev["decode_ms"] / steps},
+        "e2e": {"value": e2e, "unit": "x real-time", "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": (st_e2e["pcm_bytes"] + st_e2e["h2d_bytes"]) / steps,
+                "d2h_bytes_per_step": st_e2e["d2h_bytes"] / steps},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "k_gemm_tn (tcgen05, encoder + cross-KV projections)", "bound": "tensor",
+                     "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
+                     "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
+                     "launches": st_dev["gemm_launches"], "ms_per_step": st_dev["gemm_ms"] / steps, "traffic": None},
+        "roofline_extra": [
+            {"kernel": "k_attn_enc (mma.sync flash attention)", "bound": "tensor", "achieved": attn_tflops,
+             "peak": peak_tf, "unit": "TFLOP/s", "frac": attn_tflops / peak_tf, "ms_per_step": st_dev["attn_ms"] / steps},
+        ],
+        "clocks": sampler.summary(),
+    }
+    if cpu_base:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

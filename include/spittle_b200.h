@@ -97,6 +97,119 @@ SB_API int sb_gemm_tn_dev(int dtype, const void* A, int64_t lda, const void* W, 
                           const float* bias, int act, const float* residual, int64_t ldr,
                           int res_row_mod, void* stream);
 
+/* Stage entries used by the parity tests (device pointers). */
+SB_API int sb_layernorm_dev(int dtype, const float* x, const float* gamma, const float* beta,
+                            void* out16, float* out32, int rows, int d, void* stream);
+/* qkv [n_windows*n_ctx, 3*d_model] 16-bit (columns Q|K|V, heads of 64) -> out [n_windows*n_ctx, d_model] */
+SB_API int sb_attn_enc_dev(int dtype, const void* qkv, void* out, int n_windows, int n_ctx,
+                           int d_model, int n_head, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Engine: the native equivalent of transcribe-rs' WhisperEngine as the reference uses it
+ *   new() + load_model(&path)      managers/transcription.rs:262-263  -> sb_engine_create
+ *   unload_model()                 managers/transcription.rs:183-189  -> sb_engine_destroy
+ *   transcribe_samples(audio, Some(WhisperInferenceParams{language, translate,
+ *       initial_prompt, ..}))      managers/transcription.rs:494-503  -> sb_transcribe
+ * An engine may be created / used / destroyed from different threads; calls on one engine
+ * must be serialised by the caller (the reference holds its engine mutex across the whole
+ * inference, transcription.rs:437).  One engine drives one CUDA device; multi-GPU hosts
+ * create one engine per device (clips are independent, no collective).
+ * ---------------------------------------------------------------------------------- */
+typedef struct sb_engine sb_engine;
+
+typedef struct sb_config {
+    const char* model_path;   /* GGML legacy ggml-*.bin (f32 / f16 tensors) */
+    int device;               /* CUDA device ordinal */
+    int max_batch;            /* windows decoded together (0 -> 64) */
+    int dtype;                /* sb_dtype: operand type of the tensor-core GEMMs */
+    int use_cuda_graph;       /* 1: capture the decoder step into a CUDA graph (default), 0: plain launches */
+} sb_config;
+
+typedef struct sb_model_info {
+    int32_t n_vocab, n_audio_ctx, n_audio_state, n_audio_head, n_audio_layer;
+    int32_t n_text_ctx, n_text_state, n_text_head, n_text_layer, n_mels, ftype;
+    int32_t token_eot, token_sot, token_beg, token_blank;
+} sb_model_info;
+
+/* Decode policy.  sb_params_default() gives the configuration pinned for parity in
+ * language "en", transcribe, timestamps on, suppress_blank, no_context,
+ * max_initial_ts 1.0, greedy (temperature 0, no fallback), n_max = n_text_ctx/2 - 4. */
+typedef struct sb_params {
+    const char* language;        /* "en", ... ; NULL = reference's "auto" (NOT implemented yet: SB_ERR_UNSUPPORTED) */
+    int translate;               /* WhisperInferenceParams.translate */
+    const char* initial_prompt;  /* must be NULL for now (needs the BPE encoder; SB_ERR_UNSUPPORTED otherwise) */
+    int no_timestamps;
+    int suppress_blank;
+    int single_segment;
+    float max_initial_ts;
+    int n_max_tokens;            /* 0 -> n_text_ctx/2 - 4 (whisper.cpp); tests may cap it */
+    int max_windows;             /* 0 -> unlimited; safety cap on the seek loop */
+} sb_params;
+
+typedef struct sb_window_info {
+    int32_t seek;            /* window start, mel frames (10 ms) */
+    int32_t n_tokens;        /* tokens sampled in this window */
+    int32_t result_len;      /* tokens kept (whisper.cpp result_len) */
+    int32_t seek_delta;
+    int32_t failed;
+    int32_t token_offset;    /* offset of this window's sampled tokens in sb_result.sampled */
+} sb_window_info;
+
+typedef struct sb_result {
+    char* text;  size_t text_len;          /* UTF-8 bytes, trimmed like transcribe-rs; NUL-terminated */
+    int32_t* tokens; size_t n_tokens;      /* kept tokens (incl. timestamps / EOT), all windows */
+    int32_t* sampled; size_t n_sampled;    /* every sampled token, all windows */
+    float* margins;                        /* [n_sampled] top1-top2 of the filtered logits */
+    sb_window_info* windows; size_t n_windows;
+    float ms_mel, ms_encode, ms_decode;    /* device time of the batch this clip was part of */
+    int status;                            /* per-clip sb_status (batch API) */
+} sb_result;
+
+/* Cumulative engine counters (bench.py): device times are CUDA-event brackets on the engine's
+ * stream.  gemm_* / attn_* are only filled while profiling is enabled (one event pair per launch). */
+typedef struct sb_stats {
+    double clips, windows, rounds, decoder_steps, tokens_sampled;
+    double pcm_bytes;                 /* clip bytes copied to the device (H2D when the caller passes host memory) */
+    double h2d_bytes, d2h_bytes;      /* control traffic: decode state up, tokens / state down */
+    double mel_ms, encode_ms, decode_ms;
+    double gemm_ms, gemm_flops, gemm_launches;     /* tcgen05 GEMM launches of the encoder + cross-KV */
+    double attn_ms, attn_flops, attn_launches;     /* encoder attention launches */
+} sb_stats;
+
+SB_API void sb_params_default(sb_params* p);
+/* the CUDA stream (cudaStream_t) every kernel of this engine is launched on */
+SB_API void* sb_engine_stream(sb_engine* e);
+SB_API int sb_engine_set_profile(sb_engine* e, int enable);
+SB_API int sb_engine_stats(sb_engine* e, sb_stats* out, int reset);
+SB_API int sb_engine_create(const sb_config* cfg, sb_engine** out);
+SB_API int sb_engine_destroy(sb_engine* e);
+SB_API int sb_engine_info(const sb_engine* e, sb_model_info* info);
+/* id -> token bytes (whisper_token_to_str); returns length, copies at most cap bytes */
+SB_API int sb_token_text(const sb_engine* e, int32_t id, char* buf, int cap);
+
+/* One clip: 16 kHz mono f32 host samples -> text.  Empty input returns SB_OK with empty text
+ * (reference: transcription.rs:412-416); < 1 s of audio returns empty text like whisper.cpp
+ * (the reference pads such clips upstream, managers/audio.rs:466-475). */
+SB_API int sb_transcribe(sb_engine* e, const float* pcm16k, size_t n_samples, const sb_params* p,
+                         sb_result* out);
+/* Independent clips batched on this engine's GPU.  out: array of `count` results. */
+SB_API int sb_transcribe_batch(sb_engine* e, const float* const* pcm16k, const size_t* n_samples,
+                               size_t count, const sb_params* p, sb_result* out);
+SB_API void sb_result_free(sb_result* r);
+
+/* Parity hooks (host buffers).
+ * sb_encode: mel windows [n_windows][n_mel][3000] f32 -> encoder output [n_windows][1500][d] f32
+ *            (after ln_post; computed in the engine dtype, returned widened to f32). */
+SB_API int sb_encode(sb_engine* e, const float* mel_windows, int n_windows, float* enc_out);
+/* sb_decode_trace: encode + cross-KV + n_steps decoder steps with optional teacher forcing.
+ *   forced      [n_windows][n_steps] token ids, < 0 = use the sampled token; may be NULL
+ *   logits_out  [n_windows][n_steps][n_vocab] raw f32 logits before filtering; may be NULL
+ *   tokens_out  [n_windows][n_steps] sampled tokens;  margins_out same shape or NULL
+ * seek = 0 and seek_end = seek_end[w] for every window. */
+SB_API int sb_decode_trace(sb_engine* e, const float* mel_windows, int n_windows, const int32_t* seek_end,
+                           const sb_params* p, const int32_t* forced, int n_steps, float* logits_out,
+                           int32_t* tokens_out, float* margins_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,8 +49,7 @@ def _declare(l: C.CDLL) -> None:
     l.sb_logmel.argtypes = [vp, vp, sz, vp, C.POINTER(i32), C.POINTER(i32)]
     l.sb_logmel_batch_dev.argtypes = [vp, vp, i32, sz, vp, i32, vp, vp, vp]
     l.sb_gemm_tn_dev.argtypes = [i32, vp, i64, vp, i64, i32, i32, i32, vp, i64, i32, vp, i32, vp, i64, i32, vp]
-    for name in dir(l):
-        pass
+    _declare_engine(l)
 
 
 def check(rc: int) -> None:
@@ -118,3 +117,190 @@ def gemm_tn_dev(dtype: int, a_ptr: int, lda: int, w_ptr: int, ldw: int, M: int, 
                 res_row_mod: int = 0, stream: int = 0) -> None:
     check(lib().sb_gemm_tn_dev(dtype, a_ptr, lda, w_ptr, ldw, M, N, K, out_ptr, ldo, int(out_f32),
                                bias_ptr or None, act, res_ptr or None, ldr, res_row_mod, stream or None))
+
+
+# ---------------------------------------------------------------------------------------
+# engine
+# ---------------------------------------------------------------------------------------
+class SbConfig(C.Structure):
+    _fields_ = [("model_path", C.c_char_p), ("device", C.c_int), ("max_batch", C.c_int), ("dtype", C.c_int),
+                ("use_cuda_graph", C.c_int)]
+
+
+class SbModelInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_vocab", "n_audio_ctx", "n_audio_state", "n_audio_head", "n_audio_layer", "n_text_ctx", "n_text_state",
+        "n_text_head", "n_text_layer", "n_mels", "ftype", "token_eot", "token_sot", "token_beg", "token_blank")]
+
+
+class SbParams(C.Structure):
+    _fields_ = [("language", C.c_char_p), ("translate", C.c_int), ("initial_prompt", C.c_char_p),
+                ("no_timestamps", C.c_int), ("suppress_blank", C.c_int), ("single_segment", C.c_int),
+                ("max_initial_ts", C.c_float), ("n_max_tokens", C.c_int), ("max_windows", C.c_int)]
+
+
+class SbStats(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "clips", "windows", "rounds", "decoder_steps", "tokens_sampled", "pcm_bytes", "h2d_bytes", "d2h_bytes",
+        "mel_ms", "encode_ms", "decode_ms", "gemm_ms", "gemm_flops", "gemm_launches", "attn_ms", "attn_flops",
+        "attn_launches")]
+
+
+class SbWindowInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("seek", "n_tokens", "result_len", "seek_delta", "failed", "token_offset")]
+
+
+class SbResult(C.Structure):
+    _fields_ = [("text", C.POINTER(C.c_char)), ("text_len", C.c_size_t),
+                ("tokens", C.POINTER(C.c_int32)), ("n_tokens", C.c_size_t),
+                ("sampled", C.POINTER(C.c_int32)), ("n_sampled", C.c_size_t),
+                ("margins", C.POINTER(C.c_float)),
+                ("windows", C.POINTER(SbWindowInfo)), ("n_windows", C.c_size_t),
+                ("ms_mel", C.c_float), ("ms_encode", C.c_float), ("ms_decode", C.c_float),
+                ("status", C.c_int)]
+
+
+def _declare_engine(l: C.CDLL) -> None:
+    vp, i32 = C.c_void_p, C.c_int
+    l.sb_params_default.argtypes = [C.POINTER(SbParams)]
+    l.sb_params_default.restype = None
+    l.sb_engine_create.argtypes = [C.POINTER(SbConfig), C.POINTER(vp)]
+    l.sb_engine_destroy.argtypes = [vp]
+    l.sb_engine_info.argtypes = [vp, C.POINTER(SbModelInfo)]
+    l.sb_token_text.argtypes = [vp, C.c_int32, C.c_char_p, i32]
+    l.sb_engine_stream.argtypes = [vp]
+    l.sb_engine_stream.restype = vp
+    l.sb_engine_set_profile.argtypes = [vp, i32]
+    l.sb_engine_stats.argtypes = [vp, C.POINTER(SbStats), i32]
+    l.sb_transcribe.argtypes = [vp, vp, C.c_size_t, C.POINTER(SbParams), C.POINTER(SbResult)]
+    l.sb_transcribe_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(SbParams),
+                                      C.POINTER(SbResult)]
+    l.sb_result_free.argtypes = [C.POINTER(SbResult)]
+    l.sb_result_free.restype = None
+    l.sb_encode.argtypes = [vp, vp, i32, vp]
+    l.sb_decode_trace.argtypes = [vp, vp, i32, vp, C.POINTER(SbParams), vp, i32, vp, vp, vp]
+    l.sb_layernorm_dev.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, vp]
+    l.sb_attn_enc_dev.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
+
+
+class ClipResult:
+    """Python view of one sb_result (copied out; the C result is freed)."""
+
+    def __init__(self, r: SbResult):
+        self.text = C.string_at(r.text, r.text_len) if r.text else b""
+        self.tokens = [r.tokens[i] for i in range(r.n_tokens)]
+        self.sampled = [r.sampled[i] for i in range(r.n_sampled)]
+        self.margins = [r.margins[i] for i in range(r.n_sampled)]
+        self.windows = [dict(seek=w.seek, n_tokens=w.n_tokens, result_len=w.result_len, seek_delta=w.seek_delta,
+                             failed=w.failed, token_offset=w.token_offset)
+                        for w in (r.windows[i] for i in range(r.n_windows))]
+        self.ms_mel, self.ms_encode, self.ms_decode = r.ms_mel, r.ms_encode, r.ms_decode
+        self.status = r.status
+
+
+def default_params(**kw) -> SbParams:
+    l = lib()
+    p = SbParams()
+    l.sb_params_default(C.byref(p))
+    for k, v in kw.items():
+        if k in ("language", "initial_prompt") and isinstance(v, str):
+            v = v.encode()
+        setattr(p, k, v)
+    return p
+
+
+class Engine:
+    """sb_engine: one loaded model on one CUDA device."""
+
+    def __init__(self, model_path: str, device: int = 0, max_batch: int = 64, dtype: int = SB_DTYPE_BF16,
+                 use_cuda_graph: bool = True):
+        l = lib()
+        cfg = SbConfig(model_path.encode(), device, max_batch, dtype, int(use_cuda_graph))
+        self._h = C.c_void_p()
+        check(l.sb_engine_create(C.byref(cfg), C.byref(self._h)))
+        self.info = SbModelInfo()
+        check(l.sb_engine_info(self._h, C.byref(self.info)))
+        self.max_batch = max_batch
+        self.dtype = dtype
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().sb_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        """cudaStream_t of the engine (wrap with torch.cuda.ExternalStream to record events on it)."""
+        return int(lib().sb_engine_stream(self._h) or 0)
+
+    def set_profile(self, enable: bool) -> None:
+        check(lib().sb_engine_set_profile(self._h, int(enable)))
+
+    def stats(self, reset: bool = False) -> dict:
+        st = SbStats()
+        check(lib().sb_engine_stats(self._h, C.byref(st), int(reset)))
+        return {n: getattr(st, n) for n, _ in SbStats._fields_}
+
+    def token_text(self, tid: int) -> bytes:
+        buf = C.create_string_buffer(256)
+        n = lib().sb_token_text(self._h, tid, buf, 256)
+        return buf.raw[:min(n, 256)]
+
+    def transcribe_batch_ptrs(self, ptrs, sizes, params: Optional[SbParams] = None):
+        """ptrs: host addresses of f32 16 kHz clips (e.g. pinned torch tensors); sizes: samples per clip."""
+        n = len(ptrs)
+        arr_p = (C.c_void_p * n)(*ptrs)
+        arr_n = (C.c_size_t * n)(*sizes)
+        res = (SbResult * n)()
+        p = params if params is not None else default_params()
+        rc = lib().sb_transcribe_batch(self._h, arr_p, arr_n, n, C.byref(p), res)
+        try:
+            check(rc)
+            return [ClipResult(res[i]) for i in range(n)]
+        finally:
+            for i in range(n):
+                lib().sb_result_free(C.byref(res[i]))
+
+    def transcribe_batch(self, clips, params: Optional[SbParams] = None):
+        arrs = [np.ascontiguousarray(c, dtype=np.float32) for c in clips]
+        return self.transcribe_batch_ptrs([a.ctypes.data if a.size else 0 for a in arrs], [a.size for a in arrs], params)
+
+    def transcribe(self, pcm, params: Optional[SbParams] = None) -> "ClipResult":
+        a = np.ascontiguousarray(pcm, dtype=np.float32)
+        res = SbResult()
+        p = params if params is not None else default_params()
+        rc = lib().sb_transcribe(self._h, a.ctypes.data if a.size else None, a.size, C.byref(p), C.byref(res))
+        try:
+            check(rc)
+            return ClipResult(res)
+        finally:
+            lib().sb_result_free(C.byref(res))
+
+    def encode(self, mel_windows: np.ndarray) -> np.ndarray:
+        m = np.ascontiguousarray(mel_windows, dtype=np.float32)
+        W = m.shape[0]
+        out = np.empty((W, self.info.n_audio_ctx, self.info.n_audio_state), np.float32)
+        check(lib().sb_encode(self._h, m.ctypes.data, W, out.ctypes.data))
+        return out
+
+    def decode_trace(self, mel_windows: np.ndarray, seek_end, n_steps: int, forced=None, want_logits=True,
+                     params: Optional[SbParams] = None):
+        m = np.ascontiguousarray(mel_windows, dtype=np.float32)
+        W = m.shape[0]
+        se = np.ascontiguousarray(seek_end, dtype=np.int32)
+        f = None if forced is None else np.ascontiguousarray(forced, dtype=np.int32)
+        logits = np.empty((W, n_steps, self.info.n_vocab), np.float32) if want_logits else None
+        toks = np.empty((W, n_steps), np.int32)
+        marg = np.empty((W, n_steps), np.float32)
+        p = params if params is not None else default_params()
+        check(lib().sb_decode_trace(self._h, m.ctypes.data, W, se.ctypes.data, C.byref(p),
+                                    f.ctypes.data if f is not None else None, n_steps,
+                                    logits.ctypes.data if logits is not None else None, toks.ctypes.data,
+                                    marg.ctypes.data))
+        return logits, toks, marg

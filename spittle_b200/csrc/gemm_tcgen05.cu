@@ -18,6 +18,7 @@
 // Tile order is n-fastest so the CTAs running together share each A tile through L2 and A
 // streams from HBM once; W (a few MB) stays L2-resident.
 #include "common.cuh"
+#include "decoder.cuh"
 #include <cuda.h>
 #include <atomic>
 #include <mutex>
@@ -35,17 +36,6 @@ constexpr int kStageBytesA = kBM * kBK * 2;
 constexpr int kStageBytesB = kBN * kBK * 2;
 constexpr int kStageBytes = kStageBytesA + kStageBytesB;
 constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-
-struct GemmEpilogue {
-    void* out;            // [M, ldo] T or f32
-    int ldo;
-    int out_f32;          // 1: f32 output, 0: 16-bit output
-    const float* bias;    // [N] or null
-    int act;              // 0 none, 1 tanh-GELU
-    const float* residual;  // f32 [*, ldr] or null; added after activation
-    int ldr;
-    int res_row_mod;      // 0: residual row = row; >0: row % res_row_mod (positional embedding)
-};
 
 // ---- PTX wrappers ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

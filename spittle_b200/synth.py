@@ -177,11 +177,13 @@ RECIPES: Dict[str, dict] = {
     "hf": dict(kind="const", std=0.02, emb_std=0.02, ts_emb_scale=1.0, dec_pos_std=0.02),
     # Designed recipe: fan-in scaled projections (activations stay O(1) through depth),
     # sharper cross-attention so the audio actually steers the decoder, large tied token
-    # embedding so the softmax is peaked (text tokens win most steps) and a down-scaled
-    # timestamp block so timestamp pairs appear at a realistic rate.
+    # embedding so the softmax is peaked (text tokens win most steps), a slightly up-scaled
+    # timestamp block so timestamp pairs appear at a realistic rate, small decoder residual
+    # gains so the current token matters, and a random +-1 final-LayerNorm gain that removes the
+    # "repeat my own input token" attractor of a tied embedding (see make_synthetic_model).
     "sharp": dict(kind="fanin", gain=1.0, conv_gain=2.0, qk_gain=2.0, cross_qk_gain=4.0,
-                  cross_out_gain=2.0, emb_std=0.2, ts_emb_scale=0.86, dec_pos_std=0.1,
-                  bias_std=0.02),
+                  cross_out_gain=0.5, dec_res_gain=0.25, emb_std=0.2, ts_emb_scale=1.05,
+                  dec_pos_std=0.5, bias_std=0.02, final_ln_signs=True),
 }
 
 

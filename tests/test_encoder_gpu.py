@@ -1,0 +1,84 @@
+"""GPU parity: LayerNorm, encoder attention and the full encoder vs the oracle, via the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import logmel, whisper_ref
+from spittle_b200 import capi, synth, ggml_format
+
+pytestmark = pytest.mark.gpu
+
+# Stated tolerances for the encoder output (after ln_post, unit-variance rows):
+#   f16 engine vs the ggml-faithful oracle (same rounding points): differences come only from
+#       fp32 summation order, flash-style softmax and tanhf/exp2f implementations.
+#   bf16 engine vs the plain-f32 oracle: bf16 operands (8-bit mantissa) through L layers.
+TOL = {
+    capi.SB_DTYPE_F16: dict(rel_rms=2e-3, max_abs=3e-2),
+    capi.SB_DTYPE_BF16: dict(rel_rms=2e-2, max_abs=2.5e-1),
+}
+
+
+def test_layernorm_matches_numpy(cuda_dev):
+    import torch
+    rng = np.random.default_rng(0)
+    for d in (128, 768, 1280):
+        x = (rng.normal(0, 3, (77, d)) + rng.normal(0, 5, (77, 1))).astype(np.float32)
+        g = rng.normal(1, 0.2, d).astype(np.float32)
+        b = rng.normal(0, 0.2, d).astype(np.float32)
+        ref = whisper_ref.layer_norm(x, g, b)
+        xt, gt, bt = (torch.from_numpy(a).to(cuda_dev) for a in (x, g, b))
+        o32 = torch.empty_like(xt)
+        o16 = torch.empty(77, d, dtype=torch.float16, device=cuda_dev)
+        capi.check(capi.lib().sb_layernorm_dev(capi.SB_DTYPE_F16, xt.data_ptr(), gt.data_ptr(), bt.data_ptr(),
+                                               o16.data_ptr(), o32.data_ptr(), 77, d,
+                                               torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert np.abs(o32.cpu().numpy() - ref).max() < 2e-5
+        assert np.abs(o16.float().cpu().numpy() - ref).max() < 4e-3
+
+
+@pytest.mark.parametrize("dtype", [capi.SB_DTYPE_BF16, capi.SB_DTYPE_F16])
+def test_attention_matches_torch(cuda_dev, dtype):
+    import torch
+    tdt = torch.bfloat16 if dtype == capi.SB_DTYPE_BF16 else torch.float16
+    W, T, H = 3, 1500, 4
+    d = H * 64
+    g = torch.Generator(device="cpu").manual_seed(1)
+    qkv = (torch.randn(W * T, 3 * d, generator=g) * 1.5).to(tdt).to(cuda_dev)
+    out = torch.zeros(W * T, d, dtype=tdt, device=cuda_dev)
+    capi.check(capi.lib().sb_attn_enc_dev(dtype, qkv.data_ptr(), out.data_ptr(), W, T, d, H,
+                                          torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    q, k, v = (qkv.float().view(W, T, 3, H, 64)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(W * T, d)
+    err = (out.float() - ref).abs().max().item()
+    assert err < (2e-2 if dtype == capi.SB_DTYPE_BF16 else 3e-3), err
+
+
+def _windows(model, clip_ids, secs=30.0):
+    mels, ends = [], []
+    for i in clip_ids:
+        x = synth.make_clip(i, seconds=secs)
+        mel, n_len_org = logmel.logmel_f64(x, model.mel_filters)
+        mels.append(logmel.mel_window(mel, 0))
+        ends.append(n_len_org)
+    return np.stack(mels), ends
+
+
+@pytest.mark.parametrize("arch", ["nano", "micro"])
+@pytest.mark.parametrize("dtype", [capi.SB_DTYPE_F16, capi.SB_DTYPE_BF16])
+def test_encoder_matches_oracle(cuda_dev, model_dir, arch, dtype):
+    path = synth.ensure_model_file(arch, model_dir)
+    model = ggml_format.read_ggml(path)
+    eng = capi.Engine(path, dtype=dtype, max_batch=4)
+    mels, _ = _windows(model, [1, 3, 4])
+    got = eng.encode(mels)
+    oracle = whisper_ref.WhisperOracle(model, act_f16=(dtype == capi.SB_DTYPE_F16))
+    tol = TOL[dtype]
+    for w in range(mels.shape[0]):
+        ref = oracle.encode(mels[w])
+        err = got[w] - ref
+        rel_rms = float(np.sqrt((err ** 2).mean()) / np.sqrt((ref ** 2).mean()))
+        max_abs = float(np.abs(err).max())
+        print(f"{arch} dtype={dtype} window {w}: rel_rms={rel_rms:.3e} max_abs={max_abs:.3e}")
+        assert rel_rms <= tol["rel_rms"] and max_abs <= tol["max_abs"], (rel_rms, max_abs)
+    eng.close()

@@ -1,0 +1,86 @@
+"""Per-kernel micro-benchmarks (CUDA events, warm-up, L2 flush between iterations).
+Usage: python tools/kbench.py [gemm] [logmel]   -- prints one JSON line per case."""
+import json
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from spittle_b200 import capi, synth
+
+dev = torch.device("cuda:0")
+PEAKS = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) \
+    if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else \
+    {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=10, warmup=3, flush=True):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush:
+            flush_buf.zero_()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def bench_gemm():
+    st = torch.cuda.current_stream().cuda_stream
+    for dtype, tdt in ((capi.SB_DTYPE_BF16, torch.bfloat16),):
+        for (M, N, K, tag) in [(96000, 2304, 768, "small qkv B64"), (96000, 768, 768, "small out B64"),
+                               (96000, 3072, 768, "small mlp1 B64"), (96000, 768, 3072, "small mlp2 B64"),
+                               (48000, 3840, 1280, "v3 qkv B32"), (48000, 5120, 1280, "v3 mlp1 B32"),
+                               (48000, 1280, 5120, "v3 mlp2 B32"), (8192, 8192, 8192, "square 8192")]:
+            A = (torch.randn(M, K, device=dev) * 0.5).to(tdt)
+            W = (torch.randn(N, K, device=dev) * 0.05).to(tdt)
+            out = torch.empty(M, N, dtype=tdt, device=dev)
+            bias = torch.randn(N, device=dev)
+            f = lambda: capi.gemm_tn_dev(dtype, A.data_ptr(), K, W.data_ptr(), K, M, N, K, out.data_ptr(), N, False,
+                                         bias.data_ptr(), 0, 0, 0, 0, st)
+            med, mn = timeit(f, flush=False)
+            ref = lambda: torch.addmm(bias.to(tdt), A, W.T)
+            rmed, rmn = timeit(ref, flush=False)
+            fl = 2.0 * M * N * K
+            print(json.dumps({"kernel": "gemm_tcgen05", "case": tag, "M": M, "N": N, "K": K, "ms": med,
+                              "tflops": fl / med / 1e9, "frac_burst": fl / med / 1e9 / PEAKS["bf16_tflops"],
+                              "cublas_ms": rmed, "cublas_tflops": fl / rmed / 1e9}), flush=True)
+            del A, W, out
+
+
+def bench_logmel():
+    st = torch.cuda.current_stream().cuda_stream
+    for n_mel in (80, 128):
+        plan = capi.MelPlan(synth.mel_filterbank(n_mel))
+        for B in (64, 256, 1024):
+            n = 480000
+            n_len, n_len_org, n_calc = capi.logmel_geometry(n)
+            stride = (n_calc + 31) // 32 * 32
+            base = torch.from_numpy(np.stack([synth.make_clip(i) for i in range(8)])).to(dev)
+            pcm = base.repeat((B + 7) // 8, 1)[:B].contiguous()
+            mel = torch.empty((B, n_mel, stride), dtype=torch.float32, device=dev)
+            cmax = torch.empty(B, dtype=torch.int32, device=dev)
+            f = lambda: capi.logmel_batch_dev(plan, pcm.data_ptr(), B, n, mel.data_ptr(), stride, cmax.data_ptr(), 0, st)
+            med, mn = timeit(f, flush=True)
+            alg = B * (n * 4 + n_mel * 3000 * 4)
+            print(json.dumps({"kernel": "k_logmel(+norm)", "n_mel": n_mel, "clips": B, "ms": med,
+                              "GBps": alg / med / 1e6, "frac_hbm": alg / med / 1e6 / PEAKS["hbm_gbs"]}), flush=True)
+            del pcm, mel
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["gemm", "logmel"]
+    if "gemm" in what:
+        bench_gemm()
+    if "logmel" in what:
+        bench_logmel()
