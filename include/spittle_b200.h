@@ -104,6 +104,13 @@ SB_API int sb_layernorm_dev(int dtype, const float* x, const float* gamma, const
 SB_API int sb_attn_enc_dev(int dtype, const void* qkv, void* out, int n_windows, int n_ctx,
                            int d_model, int n_head, void* stream);
 
+/* Decoder-step weight-streaming GEMM: Y[Bn,N] = epi(X[Bn,K] W[N,K]^T), Bn small (HBM-bound on W).
+ * out32 (f32 [Bn, ldo32]) and/or out16 (16-bit [Bn, ldo16]); residual f32 may alias out32. */
+SB_API int sb_skinny_gemm_dev(int dtype, const void* X, int64_t ldx, const void* W, int64_t ldw,
+                              int Bn, int N, int K, const float* bias, int act, const float* residual,
+                              int64_t ldr, float* out32, int64_t ldo32, void* out16, int64_t ldo16,
+                              void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Engine: the native equivalent of transcribe-rs' WhisperEngine as the reference uses it
  *   new() + load_model(&path)      managers/transcription.rs:262-263  -> sb_engine_create

@@ -180,6 +180,8 @@ def _declare_engine(l: C.CDLL) -> None:
     l.sb_encode.argtypes = [vp, vp, i32, vp]
     l.sb_decode_trace.argtypes = [vp, vp, i32, vp, C.POINTER(SbParams), vp, i32, vp, vp, vp]
     l.sb_layernorm_dev.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, vp]
+    i64 = C.c_int64
+    l.sb_skinny_gemm_dev.argtypes = [i32, vp, i64, vp, i64, i32, i32, i32, vp, i32, vp, i64, vp, i64, vp, i64, vp]
     l.sb_attn_enc_dev.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
 
 

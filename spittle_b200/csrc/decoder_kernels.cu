@@ -75,17 +75,53 @@ __global__ void __launch_bounds__(256) k_skinny_gemm(const T* __restrict__ X, in
     const T* w_hi = W + (int64_t)r_hi * ldw + t * 8;
     const T* xb = X + (int64_t)b0 * ldx + t * 8;
     const int n_blk = K / 32;      // K % 32 == 0 enforced by the host
-    for (int kb = warp; kb < n_blk; kb += 8) {
-        const int k0 = kb * 32;
-        const uint4 alo = ldg_nc_v4(w_lo + k0);
-        const uint4 ahi = ldg_nc_v4(w_hi + k0);
+    // this warp's k-blocks: warp, warp + 8, ...  Weight loads are issued kWB blocks ahead of
+    // their use (the HBM stream must be in flight before anything waits on it); the activation
+    // rows come from L2 and are double-buffered one block ahead.
+    constexpr int kWB = 4;
+    const int n_it = (n_blk - warp + 7) / 8;       // iterations of this warp (may be 0)
+    uint4 wlo[kWB], whi[kWB];
+#pragma unroll
+    for (int i = 0; i < kWB; ++i)
+        if (i < n_it) { wlo[i] = ldg_nc_v4(w_lo + (warp + 8 * i) * 32); whi[i] = ldg_nc_v4(w_hi + (warp + 8 * i) * 32); }
+    uint4 xv[8];
+    if (n_it > 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int n = j * 8 + g;
-            uint4 bv = make_uint4(0, 0, 0, 0);
-            if (n < nb) bv = *reinterpret_cast<const uint4*>(xb + (int64_t)n * ldx + k0);
-            MmaOpD<T>::mma(acc[j], alo.x, ahi.x, alo.y, ahi.y, bv.x, bv.y);
-            MmaOpD<T>::mma(acc[j], alo.z, ahi.z, alo.w, ahi.w, bv.z, bv.w);
+            xv[j] = n < nb ? *reinterpret_cast<const uint4*>(xb + (int64_t)n * ldx + warp * 32) : make_uint4(0, 0, 0, 0);
+        }
+    }
+    for (int it0 = 0; it0 < n_it; it0 += kWB) {
+#pragma unroll
+        for (int i = 0; i < kWB; ++i) {
+            const int it = it0 + i;
+            if (it >= n_it) break;
+            const uint4 alo = wlo[i], ahi = whi[i];
+            // refill this slot with the block kWB iterations ahead
+            if (it + kWB < n_it) {
+                wlo[i] = ldg_nc_v4(w_lo + (warp + 8 * (it + kWB)) * 32);
+                whi[i] = ldg_nc_v4(w_hi + (warp + 8 * (it + kWB)) * 32);
+            }
+            uint4 xn[8];
+            const bool more = it + 1 < n_it;
+            if (more) {
+                const int k1 = (warp + 8 * (it + 1)) * 32;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int n = j * 8 + g;
+                    xn[j] = n < nb ? *reinterpret_cast<const uint4*>(xb + (int64_t)n * ldx + k1) : make_uint4(0, 0, 0, 0);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                MmaOpD<T>::mma(acc[j], alo.x, ahi.x, alo.y, ahi.y, xv[j].x, xv[j].y);
+                MmaOpD<T>::mma(acc[j], alo.z, ahi.z, alo.w, ahi.w, xv[j].z, xv[j].w);
+            }
+            if (more) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xv[j] = xn[j];
+            }
         }
     }
     // acc[j]: c0,c1 = (row g, batch j*8+2t, +1), c2,c3 = (row g+8, ...)
@@ -530,3 +566,17 @@ SB_INST_D(__nv_bfloat16)
 SB_INST_D(__half)
 
 }  // namespace sb
+
+// stage entry for parity tests / micro-benchmarks
+extern "C" int sb_skinny_gemm_dev(int dtype, const void* X, int64_t ldx, const void* W, int64_t ldw, int Bn, int N, int K,
+                                  const float* bias, int act, const float* residual, int64_t ldr, float* out32,
+                                  int64_t ldo32, void* out16, int64_t ldo16, void* stream) {
+    SB_CHECK_ARG(X && W && (out32 || out16), "null pointer");
+    sb::SkinnyEpilogue e;
+    e.bias = bias; e.act = act; e.residual = residual; e.ldr = (int)ldr; e.out32 = out32; e.ldo32 = (int)ldo32;
+    e.out16 = out16; e.ldo16 = (int)ldo16;
+    if (dtype == SB_DTYPE_F16)
+        return sb::skinny_gemm<__half>((const __half*)X, (int)ldx, (const __half*)W, (int)ldw, Bn, N, K, e, (cudaStream_t)stream);
+    return sb::skinny_gemm<__nv_bfloat16>((const __nv_bfloat16*)X, (int)ldx, (const __nv_bfloat16*)W, (int)ldw, Bn, N, K, e,
+                                          (cudaStream_t)stream);
+}
