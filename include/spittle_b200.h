@@ -83,6 +83,49 @@ SB_API int sb_logmel_batch_dev(const sb_melplan* plan, const float* pcm, int n_c
                                float* floor_val, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Capture front-end (batched over independent streams).
+ *
+ * Resampler: replaces rubato::FftFixedIn::<f32>::new(in_hz, out_hz, 1024, 1, 1) + process() as
+ * wrapped by FrameResampler (audio_toolkit/audio/resampler.rs:16-98).  Output semantics are those
+ * of push(everything) + finish(): the input is zero-padded to whole 1024-sample chunks, only whole
+ * rubato blocks (1026 -> 342 at 48 -> 16 kHz) are produced, the last 480-sample frame is zero padded.
+ * Only integer decimation ratios are implemented (48 kHz, 32 kHz, 16 kHz inputs).
+ * ---------------------------------------------------------------------------------- */
+typedef struct sb_resampler sb_resampler;
+SB_API int sb_resampler_create(int fs_in, int fs_out, sb_resampler** out);
+SB_API int sb_resampler_destroy(sb_resampler* r);
+/* n_fed: samples handed to rubato; n_out: resampled samples; n_frames: 480-sample frames emitted */
+SB_API int sb_resample_geometry(const sb_resampler* r, size_t n_in, size_t* n_fed, size_t* n_out,
+                                size_t* n_frames);
+/* in [n_streams][in_stride] (n_in valid), out [n_streams][out_stride >= n_frames*480], device, async */
+SB_API int sb_resample_dev(const sb_resampler* r, const float* in, int64_t in_stride, size_t n_in,
+                           int n_streams, float* out, int64_t out_stride, void* stream);
+
+/* Silero VAD v4 (16 kHz branch).  Replaces vad_rs::Vad::{new, compute} over onnxruntime
+ * (audio_toolkit/vad/silero.rs:25,41-44).  blob: the f32 tensors of the model in the order of
+ * spittle_b200/silero_weights.py BLOB_LAYOUT (read from the reference's silero_vad_v4.onnx).
+ * State h, c: [2][n_streams][64] f32, carried across calls like vad-rs carries h/c across frames. */
+typedef struct sb_vad sb_vad;
+SB_API int sb_vad_create(const float* blob, size_t n_floats, sb_vad** out);
+SB_API int sb_vad_destroy(sb_vad* v);
+SB_API size_t sb_vad_workspace_bytes(int n_streams, int n_frames);
+/* pcm16k [n_streams][pcm_stride] (n_frames*480 valid) -> probs [n_streams][n_frames]; device, async */
+SB_API int sb_vad_score_dev(const sb_vad* v, const float* pcm16k, int64_t pcm_stride, int n_streams,
+                            int n_frames, float* h_state, float* c_state, float* probs,
+                            void* workspace, void* stream);
+
+/* SmoothedVad gate + concatenation of kept frames.  Replaces SmoothedVad::push_frame
+ * (audio_toolkit/vad/smoothed.rs:41-96) and handle_frame's out_buf.extend (audio/recorder.rs:284-314).
+ * is_voice = prob > threshold (vad/silero.rs:46).  out [n_streams][out_stride]: kept samples,
+ * out_frames[s] = number of 480-sample frames written (may exceed n_frames: an onset re-emits the
+ * prefill ring exactly like the reference). */
+SB_API size_t sb_vad_gate_workspace_bytes(int n_streams, int n_frames);
+SB_API int sb_vad_gate_dev(const float* probs, const float* pcm16k, int64_t pcm_stride, int n_streams,
+                           int n_frames, float threshold, int prefill, int hangover, int onset,
+                           float* out, int64_t out_stride, int32_t* out_frames, void* workspace,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Tensor-core GEMM stage entry (parity tests / benchmarks).  C[M,N] = epi(A[M,K] * W[N,K]^T)
  * with tcgen05.mma, TMEM accumulators, TMA-fed.  Replaces ggml's CPU mul_mat (f16 x f16 ->
  * f32) inside the whisper.cpp encoder graph.

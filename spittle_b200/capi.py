@@ -50,6 +50,7 @@ def _declare(l: C.CDLL) -> None:
     l.sb_logmel_batch_dev.argtypes = [vp, vp, i32, sz, vp, i32, vp, vp, vp]
     l.sb_gemm_tn_dev.argtypes = [i32, vp, i64, vp, i64, i32, i32, i32, vp, i64, i32, vp, i32, vp, i64, i32, vp]
     _declare_engine(l)
+    _declare_frontend(l)
 
 
 def check(rc: int) -> None:
@@ -306,3 +307,84 @@ class Engine:
                                     logits.ctypes.data if logits is not None else None, toks.ctypes.data,
                                     marg.ctypes.data))
         return logits, toks, marg
+
+
+# ---------------------------------------------------------------------------------------
+# capture front-end
+# ---------------------------------------------------------------------------------------
+def _declare_frontend(l: C.CDLL) -> None:
+    vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+    l.sb_resampler_create.argtypes = [i32, i32, C.POINTER(vp)]
+    l.sb_resampler_destroy.argtypes = [vp]
+    l.sb_resample_geometry.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
+    l.sb_resample_dev.argtypes = [vp, vp, i64, sz, i32, vp, i64, vp]
+    l.sb_vad_create.argtypes = [vp, sz, C.POINTER(vp)]
+    l.sb_vad_destroy.argtypes = [vp]
+    l.sb_vad_workspace_bytes.argtypes = [i32, i32]
+    l.sb_vad_workspace_bytes.restype = sz
+    l.sb_vad_score_dev.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]
+    l.sb_vad_gate_workspace_bytes.argtypes = [i32, i32]
+    l.sb_vad_gate_workspace_bytes.restype = sz
+    l.sb_vad_gate_dev.argtypes = [vp, vp, i64, i32, i32, C.c_float, i32, i32, i32, vp, i64, vp, vp, vp]
+
+
+class Resampler:
+    def __init__(self, fs_in: int, fs_out: int = 16000):
+        self._h = C.c_void_p()
+        check(lib().sb_resampler_create(fs_in, fs_out, C.byref(self._h)))
+        self.fs_in, self.fs_out = fs_in, fs_out
+
+    def geometry(self, n_in: int):
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        check(lib().sb_resample_geometry(self._h, n_in, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def run_dev(self, in_ptr: int, in_stride: int, n_in: int, n_streams: int, out_ptr: int, out_stride: int, stream: int = 0):
+        check(lib().sb_resample_dev(self._h, in_ptr, in_stride, n_in, n_streams, out_ptr, out_stride, stream or None))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().sb_resampler_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Vad:
+    def __init__(self, blob: np.ndarray):
+        b = np.ascontiguousarray(blob, dtype=np.float32)
+        self._h = C.c_void_p()
+        check(lib().sb_vad_create(b.ctypes.data, b.size, C.byref(self._h)))
+
+    @staticmethod
+    def workspace_bytes(n_streams: int, n_frames: int) -> int:
+        return int(lib().sb_vad_workspace_bytes(n_streams, n_frames))
+
+    def score_dev(self, pcm_ptr, pcm_stride, n_streams, n_frames, h_ptr, c_ptr, probs_ptr, ws_ptr, stream=0):
+        check(lib().sb_vad_score_dev(self._h, pcm_ptr, pcm_stride, n_streams, n_frames, h_ptr, c_ptr, probs_ptr, ws_ptr,
+                                     stream or None))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().sb_vad_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def vad_gate_workspace_bytes(n_streams: int, n_frames: int) -> int:
+    return int(lib().sb_vad_gate_workspace_bytes(n_streams, n_frames))
+
+
+def vad_gate_dev(probs_ptr, pcm_ptr, pcm_stride, n_streams, n_frames, threshold, prefill, hangover, onset, out_ptr,
+                 out_stride, out_frames_ptr, ws_ptr, stream=0):
+    check(lib().sb_vad_gate_dev(probs_ptr, pcm_ptr, pcm_stride, n_streams, n_frames, threshold, prefill, hangover, onset,
+                                out_ptr, out_stride, out_frames_ptr, ws_ptr, stream or None))

@@ -1,0 +1,603 @@
+// Capture front-end on sm_100a (rows a9-a13 of SURVEY.md 8(a)):
+//   k_resample_fir     rubato FftFixedIn (48 -> 16 kHz) as a polyphase decimating FIR with the same
+//                      1026 Blackman-Harris^2 sinc taps (reference: audio_toolkit/audio/resampler.rs:24,
+//                      51-56; equivalence of the two forms: SURVEY.md App. B, ~1e-9)
+//   k_silero_features  Silero v4 per-frame front: reflect pad, STFT conv, magnitude, log, adaptive
+//                      normalisation, 4 separable conv blocks (reference: vad/silero.rs:41-44 ->
+//                      vad-rs -> onnxruntime; graph first-hand from silero_vad_v4.onnx, App. A)
+//   k_silero_lstm      the two LSTM(64) layers + decoder + sigmoid, state carried across frames,
+//                      gate weights resident in registers for the whole sequence
+//   k_vad_plan / k_vad_compact   SmoothedVad onset / hangover / prefill FSM and the capture consumer's
+//                      concatenation of kept frames (reference: vad/smoothed.rs:41-96,
+//                      audio/recorder.rs:284-314)
+// All fp32 (Silero decisions are thresholded: SURVEY 7.3 item 6); first, correctness-oriented
+// version on the CUDA cores -- the tensor-core (split-precision) formulation of the FIR and of the
+// STFT convolution is the next step.
+#include "common.cuh"
+#include <vector>
+#include <cmath>
+
+namespace sb {
+extern std::atomic<uint64_t> g_launches;
+
+// ------------------------------------------------------------------------------------------
+// polyphase decimating FIR:  y[m] = sum_k h[k] x[D m - k],  x = 0 outside [0, n_in)
+// ------------------------------------------------------------------------------------------
+constexpr int kFirTile = 1024;     // outputs per CTA
+constexpr int kFirR = 8;           // outputs per thread
+constexpr int kFirThreads = kFirTile / kFirR;
+
+__device__ __forceinline__ int fir_pad(int i) { return i + (i >> 3); }   // bank-conflict-free for stride-8 lanes
+
+template <int D>
+__global__ void __launch_bounds__(kFirThreads) k_resample_fir(const float* __restrict__ x, int64_t x_stride, int n_in,
+                                                              float* __restrict__ y, int64_t y_stride, int n_out,
+                                                              const float* __restrict__ h, int n_taps) {
+    extern __shared__ float s_fir[];
+    const int taps_p = n_taps / D;                        // taps per phase (342)
+    const int win = kFirTile + taps_p - 1;                // x_p samples needed per phase
+    const int win_pad = fir_pad(win) + 1;
+    float* hs = s_fir;                                    // [D][taps_p]
+    float* xs = s_fir + D * taps_p;                       // [D][win_pad]
+    const int stream = blockIdx.y;
+    const int m0 = blockIdx.x * kFirTile;
+    const float* xin = x + (int64_t)stream * x_stride;
+    for (int i = threadIdx.x; i < n_taps; i += blockDim.x) { const int p = i % D, j = i / D; hs[p * taps_p + j] = h[i]; }
+    // x_p[i] = x[D i - p],  i in [m0 - (taps_p - 1), m0 + kFirTile)
+    for (int i = threadIdx.x; i < D * win; i += blockDim.x) {
+        const int p = i / win, l = i - p * win;
+        const int64_t src = (int64_t)D * (m0 - (taps_p - 1) + l) - p;
+        xs[p * win_pad + fir_pad(l)] = (src >= 0 && src < n_in) ? __ldg(xin + src) : 0.0f;
+    }
+    __syncthreads();
+    float acc[kFirR];
+#pragma unroll
+    for (int r = 0; r < kFirR; ++r) acc[r] = 0.f;
+    const int base = threadIdx.x * kFirR + (taps_p - 1);  // local index of x_p[m] for r = 0, j = 0
+#pragma unroll 1
+    for (int p = 0; p < D; ++p) {
+        const float* xp = xs + p * win_pad;
+        const float* hp = hs + p * taps_p;
+        float w[kFirR];
+#pragma unroll
+        for (int r = 0; r < kFirR; ++r) w[r] = xp[fir_pad(base + r)];
+        for (int j = 0; j < taps_p; ++j) {
+            const float hv = hp[j];
+#pragma unroll
+            for (int r = 0; r < kFirR; ++r) acc[r] = fmaf(hv, w[r], acc[r]);
+            // slide the window one sample towards the past
+#pragma unroll
+            for (int r = kFirR - 1; r > 0; --r) w[r] = w[r - 1];
+            const int nxt = base - j - 1;
+            w[0] = nxt >= 0 ? xp[fir_pad(nxt)] : 0.0f;
+        }
+    }
+    float* yo = y + (int64_t)stream * y_stride;
+#pragma unroll
+    for (int r = 0; r < kFirR; ++r) {
+        const int m = m0 + threadIdx.x * kFirR + r;
+        if (m < n_out) yo[m] = acc[r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Silero v4 (16 kHz) weights, device resident
+// ------------------------------------------------------------------------------------------
+struct SileroDev {
+    const float* basis_t;      // [256][258]  (transposed STFT basis: coalesced over channels)
+    const float* norm_filter;  // [7]
+    const float *b1_dw_w, *b1_dw_b, *b1_pw_w, *b1_pw_b, *b1_proj_w, *b1_proj_b, *b1_down_w, *b1_down_b;
+    const float *b2_dw_w, *b2_dw_b, *b2_pw_w, *b2_pw_b, *b2_proj_w, *b2_proj_b, *b2_down_w, *b2_down_b;
+    const float *b3_dw_w, *b3_dw_b, *b3_pw_w, *b3_pw_b, *b3_down_w, *b3_down_b;
+    const float *b4_dw_w, *b4_dw_b, *b4_pw_w, *b4_pw_b, *b4_proj_w, *b4_proj_b, *b4_down_w, *b4_down_b;
+    const float *lstm_w[2], *lstm_r[2], *lstm_b[2];
+    const float *dec_w, *dec_b;
+};
+
+constexpr int kSfFrames = 8;                 // frames per CTA
+constexpr int kSfCols = kSfFrames * 7;       // 56 STFT columns
+constexpr int kSfThreads = 288;
+constexpr int kSfPadLen = 672;
+
+// generic small helpers operating on [C][kSfFrames][T] tiles in shared memory -------------------
+// depthwise conv k5 pad 2 (zero pad inside each frame), + bias, ReLU
+__device__ void dw5_relu(const float* in, float* out, const float* w, const float* b, int C, int T) {
+    const int total = C * kSfFrames * T;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int c = i / (kSfFrames * T), rem = i - c * kSfFrames * T;
+        const int f = rem / T, t = rem - f * T;
+        const float* row = in + (c * kSfFrames + f) * T;
+        float a = __ldg(b + c);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int tt = t + k - 2;
+            if (tt >= 0 && tt < T) a = fmaf(__ldg(w + c * 5 + k), row[tt], a);
+        }
+        out[i] = fmaxf(a, 0.f);
+    }
+}
+// pointwise: out[co][f][t] = relu( W1[co,:] . in1[:,f,t] + b1 (+ W2[co,:] . in2[:,f,t] + b2) (+ res[co][f][t]) )
+__device__ void pw_relu(const float* in1, const float* w1, const float* b1, const float* in2, const float* w2,
+                        const float* b2, const float* res, float* out, int Cin, int Cout, int T) {
+    const int FT = kSfFrames * T;
+    const int total = Cout * FT;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int co = i / FT, ft = i - co * FT;
+        float a = __ldg(b1 + co);
+        for (int ci = 0; ci < Cin; ++ci) a = fmaf(__ldg(w1 + co * Cin + ci), in1[ci * FT + ft], a);
+        if (in2) {
+            a += __ldg(b2 + co);
+            for (int ci = 0; ci < Cin; ++ci) a = fmaf(__ldg(w2 + co * Cin + ci), in2[ci * FT + ft], a);
+        }
+        if (res) a += res[i];
+        out[i] = fmaxf(a, 0.f);
+    }
+}
+// k1 conv with stride s over T: out[co][f][to] = relu(W[co,:] . in[:, f, s*to] + b)
+__device__ void down_relu(const float* in, const float* w, const float* b, float* out, int C_in, int C_out, int T_in,
+                          int T_out, int stride) {
+    const int total = C_out * kSfFrames * T_out;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int co = i / (kSfFrames * T_out), rem = i - co * kSfFrames * T_out;
+        const int f = rem / T_out, to = rem - f * T_out;
+        float a = __ldg(b + co);
+        for (int ci = 0; ci < C_in; ++ci) a = fmaf(__ldg(w + co * C_in + ci), in[(ci * kSfFrames + f) * T_in + to * stride], a);
+        out[i] = fmaxf(a, 0.f);
+    }
+}
+
+struct SileroSmem {
+    float xs[kSfFrames * kSfPadLen];      // reflect-padded frames
+    float x1[258 * kSfCols];              // [258][8][7]: magnitude (0..128) | norm (129..257)
+    float r1[258 * kSfCols];              // depthwise output / scratch
+    float y1[16 * kSfCols];               // block-1 pre-downsample
+    float y2[16 * kSfFrames * 4];         // T = 4
+    float r2[16 * kSfFrames * 4];
+    float z1[32 * kSfFrames * 4];
+    float z2[32 * kSfFrames * 2];         // T = 2
+    float r3[32 * kSfFrames * 2];
+    float u1[32 * kSfFrames * 2];
+    float u2[32 * kSfFrames];             // T = 1
+    float r4[32 * kSfFrames];
+    float v1[64 * kSfFrames];
+    float mean[kSfFrames * 7];
+    float mm[kSfFrames];
+};
+
+// pcm: [n_streams][n_frames*480]; out: [n_streams][n_frames][64]
+__global__ void __launch_bounds__(kSfThreads) k_silero_features(const float* __restrict__ pcm, int64_t pcm_stride, int n_frames,
+                                                                float* __restrict__ out, SileroDev wts) {
+    extern __shared__ __align__(16) unsigned char smem_raw_s[];
+    SileroSmem& s = *reinterpret_cast<SileroSmem*>(smem_raw_s);
+    const int stream = blockIdx.y;
+    const int f0 = blockIdx.x * kSfFrames;
+    const float* src = pcm + (int64_t)stream * pcm_stride;
+    // reflect pad 96 on both sides of every 480-sample frame
+    for (int i = threadIdx.x; i < kSfFrames * kSfPadLen; i += blockDim.x) {
+        const int f = i / kSfPadLen, j = i - f * kSfPadLen;
+        int k = j - 96;
+        if (k < 0) k = -k;
+        if (k >= 480) k = 2 * 479 - k;
+        s.xs[i] = (f0 + f < n_frames) ? __ldg(src + (int64_t)(f0 + f) * 480 + k) : 0.0f;
+    }
+    __syncthreads();
+    // STFT conv: item = (column half hh, channel pair i): re/im of 28 columns
+    {
+        const int item = threadIdx.x;
+        if (item < 258) {
+            const int hh = item / 129, i = item - hh * 129;
+            float re[28], im[28];
+#pragma unroll
+            for (int c = 0; c < 28; ++c) { re[c] = 0.f; im[c] = 0.f; }
+            const float* xb = s.xs + hh * 4 * kSfPadLen;
+            for (int k = 0; k < 256; ++k) {
+                const float br = __ldg(wts.basis_t + k * 258 + i);
+                const float bi = __ldg(wts.basis_t + k * 258 + 129 + i);
+#pragma unroll
+                for (int f = 0; f < 4; ++f)
+#pragma unroll
+                    for (int t = 0; t < 7; ++t) {
+                        const float xv = xb[f * kSfPadLen + 64 * t + k];
+                        re[f * 7 + t] = fmaf(br, xv, re[f * 7 + t]);
+                        im[f * 7 + t] = fmaf(bi, xv, im[f * 7 + t]);
+                    }
+            }
+#pragma unroll
+            for (int c = 0; c < 28; ++c) {
+                const float mag = sqrtf(re[c] * re[c] + im[c] * im[c]);
+                s.x1[i * kSfCols + hh * 28 + c] = mag;
+                s.r1[i * kSfCols + hh * 28 + c] = logf(1.0f + 1048576.0f * mag);   // spect (scratch)
+            }
+        }
+    }
+    __syncthreads();
+    // adaptive normalisation: mean over the 129 bins, reflect pad 3, 7-tap filter, mean over T
+    if (threadIdx.x < kSfCols) {
+        float a = 0.f;
+        for (int i = 0; i < 129; ++i) a += s.r1[i * kSfCols + threadIdx.x];
+        s.mean[threadIdx.x] = a / 129.0f;
+    }
+    __syncthreads();
+    if (threadIdx.x < kSfFrames) {
+        const float* m = s.mean + threadIdx.x * 7;
+        float p[13];
+        p[0] = m[3]; p[1] = m[2]; p[2] = m[1];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) p[3 + t] = m[t];
+        p[10] = m[5]; p[11] = m[4]; p[12] = m[3];
+        float acc = 0.f;
+        for (int t = 0; t < 7; ++t) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) a = fmaf(__ldg(wts.norm_filter + k), p[t + k], a);
+            acc += a;
+        }
+        s.mm[threadIdx.x] = acc / 7.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 129 * kSfCols; i += blockDim.x) {
+        const int col = i % kSfCols;
+        s.x1[129 * kSfCols + i] = s.r1[i] - s.mm[col / 7];
+    }
+    __syncthreads();
+    // block 1 (258 -> 16, T 7 -> 4)
+    dw5_relu(s.x1, s.r1, wts.b1_dw_w, wts.b1_dw_b, 258, 7);
+    __syncthreads();
+    pw_relu(s.r1, wts.b1_pw_w, wts.b1_pw_b, s.x1, wts.b1_proj_w, wts.b1_proj_b, nullptr, s.y1, 258, 16, 7);
+    __syncthreads();
+    down_relu(s.y1, wts.b1_down_w, wts.b1_down_b, s.y2, 16, 16, 7, 4, 2);
+    __syncthreads();
+    // block 2 (16 -> 32, T 4 -> 2)
+    dw5_relu(s.y2, s.r2, wts.b2_dw_w, wts.b2_dw_b, 16, 4);
+    __syncthreads();
+    pw_relu(s.r2, wts.b2_pw_w, wts.b2_pw_b, s.y2, wts.b2_proj_w, wts.b2_proj_b, nullptr, s.z1, 16, 32, 4);
+    __syncthreads();
+    down_relu(s.z1, wts.b2_down_w, wts.b2_down_b, s.z2, 32, 32, 4, 2, 2);
+    __syncthreads();
+    // block 3 (32 -> 32 with identity residual, T 2 -> 1)
+    dw5_relu(s.z2, s.r3, wts.b3_dw_w, wts.b3_dw_b, 32, 2);
+    __syncthreads();
+    pw_relu(s.r3, wts.b3_pw_w, wts.b3_pw_b, nullptr, nullptr, nullptr, s.z2, s.u1, 32, 32, 2);
+    __syncthreads();
+    down_relu(s.u1, wts.b3_down_w, wts.b3_down_b, s.u2, 32, 32, 2, 1, 2);
+    __syncthreads();
+    // block 4 (32 -> 64, T 1)
+    dw5_relu(s.u2, s.r4, wts.b4_dw_w, wts.b4_dw_b, 32, 1);
+    __syncthreads();
+    pw_relu(s.r4, wts.b4_pw_w, wts.b4_pw_b, s.u2, wts.b4_proj_w, wts.b4_proj_b, nullptr, s.v1, 32, 64, 1);
+    __syncthreads();
+    // final 64 -> 64 (stride 1), ReLU, write [frame][64]
+    for (int i = threadIdx.x; i < 64 * kSfFrames; i += blockDim.x) {
+        const int f = i / 64, co = i - f * 64;
+        if (f0 + f >= n_frames) continue;
+        float a = __ldg(wts.b4_down_b + co);
+        for (int ci = 0; ci < 64; ++ci) a = fmaf(__ldg(wts.b4_down_w + co * 64 + ci), s.v1[ci * kSfFrames + f], a);
+        out[((int64_t)stream * n_frames + f0 + f) * 64 + co] = fmaxf(a, 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// LSTM layer (ONNX gate order i, o, f, c).  CTA = 256 threads (one gate row each, its 128 weights
+// in registers for the whole sequence) x kLsStreams streams processed in lock step.
+//   xin  [n_streams][n_frames][64]   hout [n_streams][n_frames][64] (layer 1) or probs (layer 2)
+//   h, c [n_streams][64] in/out state of this layer
+// ------------------------------------------------------------------------------------------
+constexpr int kLsStreams = 8;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <bool LAST>
+__global__ void __launch_bounds__(256, 1) k_silero_lstm(const float* __restrict__ xin, int n_streams, int n_frames,
+                                                        const float* __restrict__ W, const float* __restrict__ R,
+                                                        const float* __restrict__ B, float* __restrict__ h_state,
+                                                        float* __restrict__ c_state, float* __restrict__ hout,
+                                                        const float* __restrict__ dec_w, const float* __restrict__ dec_b,
+                                                        float* __restrict__ probs) {
+    __shared__ __align__(16) float xh[kLsStreams][128];
+    __shared__ float gates[kLsStreams][256];
+    __shared__ float cst[kLsStreams][64];
+    const int g = threadIdx.x;
+    const int s0 = blockIdx.x * kLsStreams;
+    float w[128];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) { w[j] = __ldg(W + g * 64 + j); w[64 + j] = __ldg(R + g * 64 + j); }
+    const float bias = __ldg(B + g) + __ldg(B + 256 + g);
+    for (int i = threadIdx.x; i < kLsStreams * 64; i += 256) {
+        const int s = i >> 6, j = i & 63;
+        const bool ok = s0 + s < n_streams;
+        xh[s][64 + j] = ok ? h_state[(int64_t)(s0 + s) * 64 + j] : 0.f;
+        cst[s][j] = ok ? c_state[(int64_t)(s0 + s) * 64 + j] : 0.f;
+    }
+    for (int t = 0; t < n_frames; ++t) {
+        for (int i = threadIdx.x; i < kLsStreams * 64; i += 256) {
+            const int s = i >> 6, j = i & 63;
+            xh[s][j] = (s0 + s < n_streams) ? __ldg(xin + ((int64_t)(s0 + s) * n_frames + t) * 64 + j) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int s = 0; s < kLsStreams; ++s) {
+            float a = bias;
+            const float4* v = reinterpret_cast<const float4*>(xh[s]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float4 q = v[j];
+                a = fmaf(w[4 * j], q.x, a); a = fmaf(w[4 * j + 1], q.y, a);
+                a = fmaf(w[4 * j + 2], q.z, a); a = fmaf(w[4 * j + 3], q.w, a);
+            }
+            gates[s][g] = a;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kLsStreams * 64; i += 256) {
+            const int s = i >> 6, j = i & 63;
+            const float ig = sigmoidf_(gates[s][j]), og = sigmoidf_(gates[s][64 + j]);
+            const float fg = sigmoidf_(gates[s][128 + j]), cg = tanhf(gates[s][192 + j]);
+            const float c = fg * cst[s][j] + ig * cg;
+            const float h = og * tanhf(c);
+            cst[s][j] = c;
+            xh[s][64 + j] = h;
+            if (!LAST && s0 + s < n_streams) hout[((int64_t)(s0 + s) * n_frames + t) * 64 + j] = h;
+        }
+        __syncthreads();
+        if (LAST && threadIdx.x < kLsStreams && s0 + threadIdx.x < n_streams) {
+            const int s = threadIdx.x;
+            float a = __ldg(dec_b);
+            for (int j = 0; j < 64; ++j) a = fmaf(__ldg(dec_w + j), fmaxf(xh[s][64 + j], 0.f), a);
+            probs[(int64_t)(s0 + s) * n_frames + t] = sigmoidf_(a);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kLsStreams * 64; i += 256) {
+        const int s = i >> 6, j = i & 63;
+        if (s0 + s < n_streams) { h_state[(int64_t)(s0 + s) * 64 + j] = xh[s][64 + j]; c_state[(int64_t)(s0 + s) * 64 + j] = cst[s][j]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// SmoothedVad FSM (one thread per stream) and compaction.
+//   plan[stream][t] = {first source frame, n frames emitted, output frame offset}
+// ------------------------------------------------------------------------------------------
+struct GatePlan { int src, n, off; };
+
+__global__ void k_vad_plan(const float* __restrict__ probs, int n_streams, int n_frames, float threshold, int prefill,
+                           int hangover, int onset, GatePlan* __restrict__ plan, int* __restrict__ out_frames) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    bool in_speech = false;
+    int onset_c = 0, hang_c = 0, off = 0;
+    for (int t = 0; t < n_frames; ++t) {
+        const bool v = probs[(int64_t)s * n_frames + t] > threshold;
+        GatePlan p{t, 0, off};
+        if (!in_speech && v) {
+            if (++onset_c >= onset) {
+                in_speech = true; hang_c = hangover; onset_c = 0;
+                const int buffered = min(t + 1, prefill + 1);
+                p.src = t + 1 - buffered; p.n = buffered;
+            }
+        } else if (in_speech && v) {
+            hang_c = hangover; p.n = 1;
+        } else if (in_speech && !v) {
+            if (hang_c > 0) { --hang_c; p.n = 1; }
+            else in_speech = false;
+        } else {
+            onset_c = 0;
+        }
+        plan[(int64_t)s * n_frames + t] = p;
+        off += p.n;
+    }
+    out_frames[s] = off;
+}
+
+__global__ void __launch_bounds__(128) k_vad_compact(const float* __restrict__ pcm, int64_t pcm_stride, int n_frames,
+                                                     const GatePlan* __restrict__ plan, float* __restrict__ out,
+                                                     int64_t out_stride, int max_out_frames) {
+    const int s = blockIdx.y, t = blockIdx.x;
+    const GatePlan p = plan[(int64_t)s * n_frames + t];
+    if (p.n == 0) return;
+    const float* src = pcm + (int64_t)s * pcm_stride + (int64_t)p.src * 480;
+    float* dst = out + (int64_t)s * out_stride + (int64_t)p.off * 480;
+    const int n = min(p.n, max_out_frames - p.off) * 480;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+}  // namespace sb
+
+// ------------------------------------------------------------------------------------------
+// host side / C ABI
+// ------------------------------------------------------------------------------------------
+struct sb_resampler {
+    int fs_in = 0, fs_out = 0, decim = 1, n_taps = 0, fft_in = 0, fft_out = 0;
+    float* d_h = nullptr;
+};
+
+struct sb_vad {
+    float* d_blob = nullptr;
+    float* d_basis_t = nullptr;
+    sb::SileroDev dev{};
+};
+
+namespace {
+int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+}
+
+extern "C" {
+
+int sb_resampler_create(int fs_in, int fs_out, sb_resampler** out) {
+    SB_CHECK_ARG(out && fs_in > 0 && fs_out > 0, "bad arguments");
+    const int g = gcd_i(fs_in, fs_out);
+    const int a = fs_in / g, b = fs_out / g;
+    if (b != 1 || (a != 1 && a != 2 && a != 3 && a != 4 && a != 6)) {
+        sb::set_error("resampler: only integer decimation ratios (in/out in {1,2,3,4,6}) are implemented; "
+                      "rubato's rational ratios (e.g. 44100 -> 16000) are not yet");
+        return SB_ERR_UNSUPPORTED;
+    }
+    sb_resampler* r = new sb_resampler();
+    r->fs_in = fs_in; r->fs_out = fs_out; r->decim = a;
+    const int fft_chunks = (1024 + a - 1) / a;               // rubato: ceil(chunk_size_in / (fs_in / gcd))
+    r->fft_in = fft_chunks * a; r->fft_out = fft_chunks * b; r->n_taps = r->fft_in;
+    if (a > 1) {
+        // make_sincs(npoints = fft_in, factor 1, cutoff, BlackmanHarris2) -- SURVEY App. B; f32 cutoff like rubato
+        const float cutoff_f = powf(0.4f, 16.0f / (float)r->fft_out) * (float)r->fft_out / (float)r->fft_in;
+        const double cutoff = (double)cutoff_f;
+        std::vector<double> h(r->n_taps);
+        double sum = 0.0;
+        const int N = r->n_taps;
+        for (int x = 0; x < N; ++x) {
+            const double ph = (double)x / N;
+            double w = 0.35875 - 0.48829 * cos(2 * M_PI * ph) + 0.14128 * cos(4 * M_PI * ph) - 0.01168 * cos(6 * M_PI * ph);
+            w *= w;
+            const double t = ((double)x - (double)(N / 2)) * cutoff;
+            const double sc = t == 0.0 ? 1.0 : sin(M_PI * t) / (M_PI * t);
+            h[x] = w * sc; sum += h[x];
+        }
+        std::vector<float> hf(N);
+        for (int x = 0; x < N; ++x) hf[x] = (float)(h[x] / sum);
+        SB_CUDA_CHECK(cudaMalloc(&r->d_h, N * sizeof(float)));
+        SB_CUDA_CHECK(cudaMemcpy(r->d_h, hf.data(), N * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    *out = r;
+    return SB_OK;
+}
+
+int sb_resampler_destroy(sb_resampler* r) {
+    if (!r) return SB_OK;
+    cudaFree(r->d_h);
+    delete r;
+    return SB_OK;
+}
+
+int sb_resample_geometry(const sb_resampler* r, size_t n_in, size_t* n_fed, size_t* n_out, size_t* n_frames) {
+    SB_CHECK_ARG(r, "null resampler");
+    const size_t fed = (n_in + 1023) / 1024 * 1024;          // push() chunks + finish() zero pad
+    size_t out = fed;
+    if (r->decim > 1) out = fed / (size_t)r->fft_in * (size_t)r->fft_out;   // whole rubato blocks only
+    else out = n_in;                                          // pass-through (resampler.rs:38-41)
+    if (n_fed) *n_fed = fed;
+    if (n_out) *n_out = out;
+    if (n_frames) *n_frames = (out + 479) / 480;
+    return SB_OK;
+}
+
+int sb_resample_dev(const sb_resampler* r, const float* in, int64_t in_stride, size_t n_in, int n_streams, float* out,
+                    int64_t out_stride, void* stream) {
+    SB_CHECK_ARG(r && in && out && n_streams > 0 && n_streams <= 65535, "bad arguments");
+    size_t fed, n_out, n_frames;
+    sb_resample_geometry(r, n_in, &fed, &n_out, &n_frames);
+    SB_CHECK_ARG((size_t)out_stride >= n_frames * 480, "out_stride must hold n_frames * 480 samples");
+    cudaStream_t st = (cudaStream_t)stream;
+    // the last frame is zero padded by FrameResampler::finish
+    SB_CUDA_CHECK(cudaMemset2DAsync(out, out_stride * sizeof(float), 0, n_frames * 480 * sizeof(float), n_streams, st));
+    if (r->decim == 1) {
+        SB_CUDA_CHECK(cudaMemcpy2DAsync(out, out_stride * sizeof(float), in, in_stride * sizeof(float), n_in * sizeof(float),
+                                        n_streams, cudaMemcpyDeviceToDevice, st));
+        return SB_OK;
+    }
+    if (n_out == 0) return SB_OK;
+    const int D = r->decim, taps_p = r->n_taps / D;
+    const int win = sb::kFirTile + taps_p - 1;
+    const size_t smem = (size_t)(D * taps_p + D * (win + (win >> 3) + 2)) * sizeof(float);
+    dim3 grid((unsigned)((n_out + sb::kFirTile - 1) / sb::kFirTile), n_streams);
+#define SB_FIR(DD)                                                                                                   \
+    case DD:                                                                                                         \
+        SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_resample_fir<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        sb::k_resample_fir<DD><<<grid, sb::kFirThreads, smem, st>>>(in, in_stride, (int)n_in, out, out_stride, (int)n_out, r->d_h, r->n_taps); \
+        break;
+    switch (D) { SB_FIR(2) SB_FIR(3) SB_FIR(4) SB_FIR(6) default: sb::set_error("unsupported decimation"); return SB_ERR_UNSUPPORTED; }
+#undef SB_FIR
+    sb::g_launches += 1;
+    SB_CUDA_CHECK(cudaGetLastError());
+    return SB_OK;
+}
+
+// blob layout: spittle_b200/silero_weights.py BLOB_LAYOUT
+int sb_vad_create(const float* blob, size_t n_floats, sb_vad** out) {
+    SB_CHECK_ARG(blob && out, "null pointer");
+    static const int sizes[] = {258 * 256, 7, 258 * 5, 258, 16 * 258, 16, 16 * 258, 16, 16 * 16, 16,
+                                16 * 5, 16, 32 * 16, 32, 32 * 16, 32, 32 * 32, 32,
+                                32 * 5, 32, 32 * 32, 32, 32 * 32, 32,
+                                32 * 5, 32, 64 * 32, 64, 64 * 32, 64, 64 * 64, 64,
+                                256 * 64, 256 * 64, 512, 256 * 64, 256 * 64, 512, 64, 1};
+    size_t total = 0;
+    for (int s : sizes) total += s;
+    SB_CHECK_ARG(n_floats == total, "Silero weight blob has the wrong size");
+    sb_vad* v = new sb_vad();
+    SB_CUDA_CHECK(cudaMalloc(&v->d_blob, total * sizeof(float)));
+    SB_CUDA_CHECK(cudaMemcpy(v->d_blob, blob, total * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> bt(256 * 258);
+    for (int c = 0; c < 258; ++c) for (int k = 0; k < 256; ++k) bt[k * 258 + c] = blob[c * 256 + k];
+    SB_CUDA_CHECK(cudaMalloc(&v->d_basis_t, bt.size() * sizeof(float)));
+    SB_CUDA_CHECK(cudaMemcpy(v->d_basis_t, bt.data(), bt.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const float* p = v->d_blob;
+    const float* ptr[40];
+    for (int i = 0; i < 40; ++i) { ptr[i] = p; p += sizes[i]; }
+    sb::SileroDev& d = v->dev;
+    d.basis_t = v->d_basis_t; d.norm_filter = ptr[1];
+    d.b1_dw_w = ptr[2]; d.b1_dw_b = ptr[3]; d.b1_pw_w = ptr[4]; d.b1_pw_b = ptr[5]; d.b1_proj_w = ptr[6]; d.b1_proj_b = ptr[7];
+    d.b1_down_w = ptr[8]; d.b1_down_b = ptr[9];
+    d.b2_dw_w = ptr[10]; d.b2_dw_b = ptr[11]; d.b2_pw_w = ptr[12]; d.b2_pw_b = ptr[13]; d.b2_proj_w = ptr[14]; d.b2_proj_b = ptr[15];
+    d.b2_down_w = ptr[16]; d.b2_down_b = ptr[17];
+    d.b3_dw_w = ptr[18]; d.b3_dw_b = ptr[19]; d.b3_pw_w = ptr[20]; d.b3_pw_b = ptr[21]; d.b3_down_w = ptr[22]; d.b3_down_b = ptr[23];
+    d.b4_dw_w = ptr[24]; d.b4_dw_b = ptr[25]; d.b4_pw_w = ptr[26]; d.b4_pw_b = ptr[27]; d.b4_proj_w = ptr[28]; d.b4_proj_b = ptr[29];
+    d.b4_down_w = ptr[30]; d.b4_down_b = ptr[31];
+    d.lstm_w[0] = ptr[32]; d.lstm_r[0] = ptr[33]; d.lstm_b[0] = ptr[34];
+    d.lstm_w[1] = ptr[35]; d.lstm_r[1] = ptr[36]; d.lstm_b[1] = ptr[37];
+    d.dec_w = ptr[38]; d.dec_b = ptr[39];
+    *out = v;
+    return SB_OK;
+}
+
+int sb_vad_destroy(sb_vad* v) {
+    if (!v) return SB_OK;
+    cudaFree(v->d_blob); cudaFree(v->d_basis_t);
+    delete v;
+    return SB_OK;
+}
+
+size_t sb_vad_workspace_bytes(int n_streams, int n_frames) {
+    return (size_t)n_streams * n_frames * 64 * sizeof(float) * 2;
+}
+
+int sb_vad_score_dev(const sb_vad* v, const float* pcm16k, int64_t pcm_stride, int n_streams, int n_frames, float* h_state,
+                     float* c_state, float* probs, void* workspace, void* stream) {
+    SB_CHECK_ARG(v && pcm16k && h_state && c_state && probs && workspace, "null pointer");
+    SB_CHECK_ARG(n_streams > 0 && n_streams <= 65535 && n_frames > 0, "bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* feat = (float*)workspace;
+    float* h1 = feat + (size_t)n_streams * n_frames * 64;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_silero_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sb::SileroSmem)));
+        attr_done = true;
+    }
+    dim3 grid((n_frames + sb::kSfFrames - 1) / sb::kSfFrames, n_streams);
+    sb::k_silero_features<<<grid, sb::kSfThreads, sizeof(sb::SileroSmem), st>>>(pcm16k, pcm_stride, n_frames, feat, v->dev);
+    const int nb = (n_streams + sb::kLsStreams - 1) / sb::kLsStreams;
+    // state layout [2][n_streams][64]: layer-major like vad-rs' h,c [2,1,64] per stream
+    sb::k_silero_lstm<false><<<nb, 256, 0, st>>>(feat, n_streams, n_frames, v->dev.lstm_w[0], v->dev.lstm_r[0], v->dev.lstm_b[0],
+                                               h_state, c_state, h1, nullptr, nullptr, nullptr);
+    sb::k_silero_lstm<true><<<nb, 256, 0, st>>>(h1, n_streams, n_frames, v->dev.lstm_w[1], v->dev.lstm_r[1], v->dev.lstm_b[1],
+                                              h_state + (size_t)n_streams * 64, c_state + (size_t)n_streams * 64, nullptr,
+                                              v->dev.dec_w, v->dev.dec_b, probs);
+    sb::g_launches += 3;
+    SB_CUDA_CHECK(cudaGetLastError());
+    return SB_OK;
+}
+
+size_t sb_vad_gate_workspace_bytes(int n_streams, int n_frames) { return (size_t)n_streams * n_frames * sizeof(sb::GatePlan); }
+
+int sb_vad_gate_dev(const float* probs, const float* pcm16k, int64_t pcm_stride, int n_streams, int n_frames, float threshold,
+                    int prefill, int hangover, int onset, float* out, int64_t out_stride, int32_t* out_frames,
+                    void* workspace, void* stream) {
+    SB_CHECK_ARG(probs && pcm16k && out && out_frames && workspace, "null pointer");
+    SB_CHECK_ARG(n_streams > 0 && n_streams <= 65535 && n_frames > 0 && n_frames <= 65535 * 32, "bad shape");
+    SB_CHECK_ARG(prefill >= 0 && hangover >= 0 && onset >= 1, "bad gate parameters");
+    cudaStream_t st = (cudaStream_t)stream;
+    sb::GatePlan* plan = (sb::GatePlan*)workspace;
+    sb::k_vad_plan<<<(n_streams + 127) / 128, 128, 0, st>>>(probs, n_streams, n_frames, threshold, prefill, hangover, onset, plan, out_frames);
+    dim3 grid(n_frames, n_streams);
+    sb::k_vad_compact<<<grid, 128, 0, st>>>(pcm16k, pcm_stride, n_frames, plan, out, out_stride, (int)(out_stride / 480));
+    sb::g_launches += 2;
+    SB_CUDA_CHECK(cudaGetLastError());
+    return SB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+"""GPU parity: resampler, Silero VAD, SmoothedVad gate vs the oracles, through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import resample, silero, vad_gate
+from spittle_b200 import audio_toolkit, capi, silero_weights, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SILERO = os.path.join(GOLD, "silero_v4_16k.npz")
+
+RESAMPLE_TOL = 1e-5      # max abs error vs the f64 rubato restatement
+SILERO_TOL = 1e-4        # max abs error on the speech probability; decisions must be identical
+
+
+def test_resampler_matches_rubato_oracle(cuda_dev):
+    import torch
+    rs = audio_toolkit.FrameResampler(48000, 16000)
+    for ids, secs in [([0, 1, 2, 3, 4], 3.0), ([5], 30.0), ([3, 4], 0.04), ([1], 1025 / 48000.0)]:
+        x = np.stack([synth.make_clip(i, seconds=secs, sr=48000) for i in ids])
+        got = rs.process(x).cpu().numpy()
+        for s in range(len(ids)):
+            ref = resample.frame_resampler(x[s])
+            assert got[s].shape == ref.shape
+            err = np.abs(got[s] - ref).max() if ref.size else 0.0
+            assert err <= RESAMPLE_TOL, (ids[s], secs, err)
+    # golden vector (first 2000 samples of clip 3)
+    gold = np.load(os.path.join(GOLD, "oracle_golden.npz"))
+    got = rs.process(synth.make_clip(3, seconds=1.0, sr=48000)[None]).cpu().numpy().reshape(-1)[:2000]
+    assert np.abs(got - gold["resample_clip3_head"]).max() <= RESAMPLE_TOL
+    # pass-through when the device already delivers 16 kHz (resampler.rs:38-41)
+    x16 = synth.make_clip(2, seconds=1.0)
+    fr = audio_toolkit.FrameResampler(16000, 16000).process(x16[None]).cpu().numpy().reshape(-1)
+    assert np.array_equal(fr[:16000], x16) and np.all(fr[16000:] == 0) and fr.shape[0] == 34 * 480
+    with pytest.raises(capi.SbError):
+        audio_toolkit.FrameResampler(44100, 16000)
+
+
+def test_resampler_properties_full_size(cuda_dev):
+    """Size-independent properties at the C5 stream length (30 s @ 48 kHz): linearity, unity DC gain,
+    group delay of 171 output samples."""
+    rs = audio_toolkit.FrameResampler(48000, 16000)
+    n = 1440000
+    a = synth.make_clip(3, seconds=30.0, sr=48000)
+    b = synth.make_clip(4, seconds=30.0, sr=48000)
+    imp = np.zeros(n, np.float32); imp[30000] = 1.0
+    dc = np.full(n, 0.25, np.float32)
+    y = rs.process(np.stack([a, b, 2 * a - 3 * b, imp, dc])).cpu().numpy().reshape(5, -1)
+    assert np.abs(y[2] - (2 * y[0] - 3 * y[1])).max() < 5e-6
+    assert y[3].argmax() == (30000 + 513) // 3 and abs(y[3].sum() * 3 - 1.0) < 1e-5
+    assert np.abs(y[4][400:470000] - 0.25).max() < 1e-6
+
+
+def test_silero_probs_and_decisions_match_oracle(cuda_dev):
+    import torch
+    w = silero_weights.load_npz(SILERO)
+    vad = audio_toolkit.SileroVad(SILERO, 0.3)
+    kinds = ["vowel", "noise", "mix", "tone", "vowel", "mix"]
+    clips = np.stack([synth.make_clip(10 + i, seconds=4.5, kind=k) for i, k in enumerate(kinds)])
+    n_frames = clips.shape[1] // 480
+    frames = torch.from_numpy(clips[:, : n_frames * 480]).cuda().view(len(kinds), n_frames, 480)
+    probs = vad.score(frames).cpu().numpy()
+    borderline = 0
+    for s in range(len(kinds)):
+        o = silero.SileroOracle(w)
+        ref = o.score(clips[s])
+        err = np.abs(probs[s] - ref).max()
+        assert err <= SILERO_TOL, (kinds[s], err)
+        near = np.abs(ref - 0.3) < SILERO_TOL
+        borderline += int(near.sum())
+        assert np.array_equal((probs[s] > 0.3)[~near], (ref > 0.3)[~near])
+    print("frames within tolerance of the 0.3 threshold:", borderline)
+    # state carry: two half-length calls == one call (vad-rs keeps h/c between compute() calls)
+    vad.reset()
+    h = n_frames // 2
+    p2 = np.concatenate([vad.score(frames[:, :h].contiguous()).cpu().numpy(), vad.score(frames[:, h:].contiguous()).cpu().numpy()], axis=1)
+    assert np.abs(p2 - probs).max() < 1e-6
+    # golden vector
+    gold = np.load(os.path.join(GOLD, "oracle_golden.npz"))
+    vad.reset()
+    xg = synth.make_clip(4, seconds=3.0, kind="vowel")
+    pg = vad.score(torch.from_numpy(xg[: 100 * 480]).cuda().view(1, 100, 480)).cpu().numpy()[0]
+    assert np.abs(pg - gold["silero_vowel_probs"]).max() <= SILERO_TOL
+
+
+def test_gate_is_bit_exact(cuda_dev):
+    import torch
+    vad = audio_toolkit.SileroVad(SILERO, 0.3)
+    sm = audio_toolkit.SmoothedVad(vad, 15, 15, 2)
+    rng = np.random.default_rng(5)
+    n_streams, n_frames = 33, 257
+    frames = rng.uniform(-1, 1, (n_streams, n_frames, 480)).astype(np.float32)
+    probs = rng.uniform(0, 1, (n_streams, n_frames)).astype(np.float32)
+    # bursty voiced patterns so onset / hangover / prefill re-emission all occur
+    for s in range(n_streams):
+        run = rng.integers(1, 12)
+        t = 0
+        while t < n_frames:
+            v = rng.random() < 0.4
+            probs[s, t:t + run] = 0.9 if v else 0.05
+            t += run
+            run = rng.integers(1, 25)
+    probs[0, :] = 0.0
+    probs[1, :] = 1.0
+    probs[2, :] = 0.3                      # exactly at the threshold: prob > 0.3 is false
+    got = sm.gate(torch.from_numpy(frames).cuda(), torch.from_numpy(probs).cuda())
+    for s in range(n_streams):
+        ref = vad_gate.gate_audio(frames[s], probs[s], 0.3, 15, 15, 2)
+        assert got[s].shape == ref.shape and np.array_equal(got[s], ref), s
+    assert got[0].size == 0 and got[2].size == 0 and got[1].size == (n_frames - 1 + 2) * 480 - 480
+
+
+def test_capture_chain_matches_oracle(cuda_dev):
+    """48 kHz streams -> FrameResampler -> SileroVad -> SmoothedVad -> kept 16 kHz samples (run_consumer)."""
+    w = silero_weights.load_npz(SILERO)
+    vad = audio_toolkit.SmoothedVad(audio_toolkit.SileroVad(SILERO, 0.3), 15, 15, 2)
+    kinds = ["vowel", "mix", "tone", "mix"]
+    x48 = np.stack([synth.make_clip(20 + i, seconds=6.0, sr=48000, kind=k) for i, k in enumerate(kinds)])
+    got = audio_toolkit.run_consumer(x48, 48000, vad)
+    n_same = 0
+    for s in range(len(kinds)):
+        fr = resample.frame_resampler(x48[s])
+        o = silero.SileroOracle(w)
+        probs = np.array([o.compute(f) for f in fr])
+        ref = vad_gate.gate_audio(fr.astype(np.float32), probs, 0.3, 15, 15, 2)
+        near = (np.abs(probs - 0.3) < SILERO_TOL).any()
+        if got[s].shape == ref.shape:
+            assert np.abs(got[s] - ref).max() <= RESAMPLE_TOL
+            n_same += 1
+        else:
+            assert near, "kept-sample count differs without a borderline VAD frame"
+    assert n_same >= len(kinds) - 1
+    assert got[2].size == 0                       # a pure tone never opens the gate
+    assert audio_toolkit.stop_recording_pad(np.ones(10, np.float32)).shape == (20000,)
