@@ -181,32 +181,46 @@ __global__ void __launch_bounds__(kSfThreads) k_silero_features(const float* __r
         s.xs[i] = (f0 + f < n_frames) ? __ldg(src + (int64_t)(f0 + f) * 480 + k) : 0.0f;
     }
     __syncthreads();
-    // STFT conv: item = (column half hh, channel pair i): re/im of 28 columns
+    // STFT conv: item = (column half hh, channel pair i): re/im of 28 columns, two groups of 14.
+    // Blocked summation (8 blocks of 32 taps) keeps the fp32 round-off of the 256-term dot products
+    // well below the 2^-20 scale that log(1 + 2^20 |X|) magnifies on quiet bins.
     {
         const int item = threadIdx.x;
         if (item < 258) {
             const int hh = item / 129, i = item - hh * 129;
-            float re[28], im[28];
+#pragma unroll 1
+            for (int grp = 0; grp < 2; ++grp) {
+                float re[14], im[14];
 #pragma unroll
-            for (int c = 0; c < 28; ++c) { re[c] = 0.f; im[c] = 0.f; }
-            const float* xb = s.xs + hh * 4 * kSfPadLen;
-            for (int k = 0; k < 256; ++k) {
-                const float br = __ldg(wts.basis_t + k * 258 + i);
-                const float bi = __ldg(wts.basis_t + k * 258 + 129 + i);
+                for (int c = 0; c < 14; ++c) { re[c] = 0.f; im[c] = 0.f; }
+                const float* xb = s.xs + (hh * 4 + grp * 2) * kSfPadLen;
+#pragma unroll 1
+                for (int kb = 0; kb < 256; kb += 32) {
+                    float tr[14], ti[14];
 #pragma unroll
-                for (int f = 0; f < 4; ++f)
+                    for (int c = 0; c < 14; ++c) { tr[c] = 0.f; ti[c] = 0.f; }
+#pragma unroll 4
+                    for (int k = kb; k < kb + 32; ++k) {
+                        const float br = __ldg(wts.basis_t + k * 258 + i);
+                        const float bi = __ldg(wts.basis_t + k * 258 + 129 + i);
 #pragma unroll
-                    for (int t = 0; t < 7; ++t) {
-                        const float xv = xb[f * kSfPadLen + 64 * t + k];
-                        re[f * 7 + t] = fmaf(br, xv, re[f * 7 + t]);
-                        im[f * 7 + t] = fmaf(bi, xv, im[f * 7 + t]);
+                        for (int f = 0; f < 2; ++f)
+#pragma unroll
+                            for (int t = 0; t < 7; ++t) {
+                                const float xv = xb[f * kSfPadLen + 64 * t + k];
+                                tr[f * 7 + t] = fmaf(br, xv, tr[f * 7 + t]);
+                                ti[f * 7 + t] = fmaf(bi, xv, ti[f * 7 + t]);
+                            }
                     }
-            }
 #pragma unroll
-            for (int c = 0; c < 28; ++c) {
-                const float mag = sqrtf(re[c] * re[c] + im[c] * im[c]);
-                s.x1[i * kSfCols + hh * 28 + c] = mag;
-                s.r1[i * kSfCols + hh * 28 + c] = logf(1.0f + 1048576.0f * mag);   // spect (scratch)
+                    for (int c = 0; c < 14; ++c) { re[c] += tr[c]; im[c] += ti[c]; }
+                }
+#pragma unroll
+                for (int c = 0; c < 14; ++c) {
+                    const float mag = sqrtf(re[c] * re[c] + im[c] * im[c]);
+                    s.x1[i * kSfCols + hh * 28 + grp * 14 + c] = mag;
+                    s.r1[i * kSfCols + hh * 28 + grp * 14 + c] = log1pf(1048576.0f * mag);   // spect (scratch)
+                }
             }
         }
     }
