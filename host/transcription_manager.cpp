@@ -1,0 +1,189 @@
+// C++ mirror of the reference TranscriptionManager (see transcription_manager.hpp).
+#include "transcription_manager.hpp"
+
+#include <cstring>
+
+namespace sb {
+
+uint64_t TranscriptionManager::now_ms() {
+    using namespace std::chrono;
+    return (uint64_t)duration_cast<milliseconds>(system_clock::now().time_since_epoch()).count();
+}
+
+std::optional<uint64_t> TranscriptionManager::unload_limit_seconds(ModelUnloadTimeout t) {
+    switch (t) {   // settings.rs ModelUnloadTimeout -> seconds (transcription.rs:112-163)
+        case ModelUnloadTimeout::Never: return std::nullopt;
+        case ModelUnloadTimeout::Immediately: return 0;
+        case ModelUnloadTimeout::Sec5: return 5;
+        case ModelUnloadTimeout::Min2: return 120;
+        case ModelUnloadTimeout::Min5: return 300;
+        case ModelUnloadTimeout::Min10: return 600;
+        case ModelUnloadTimeout::Min15: return 900;
+        case ModelUnloadTimeout::Hour1: return 3600;
+    }
+    return std::nullopt;
+}
+
+TranscriptionManager::TranscriptionManager(ModelResolver resolver, SettingsFn get_settings)
+    : resolver_(std::move(resolver)), get_settings_(std::move(get_settings)), last_activity_(now_ms()) {
+    // idle watcher: checks every 10 s, unloads after the configured idle time (transcription.rs:112-163)
+    watcher_ = std::thread([this] {
+        while (!shutdown_.load()) {
+            for (int i = 0; i < 100 && !shutdown_.load(); ++i) std::this_thread::sleep_for(std::chrono::milliseconds(100));
+            if (shutdown_.load()) break;
+            const Settings s = get_settings_();
+            const auto limit = unload_limit_seconds(s.model_unload_timeout);
+            if (!limit || s.model_unload_timeout == ModelUnloadTimeout::Immediately) continue;
+            if (now_ms() - last_activity_.load() > *limit * 1000 && is_model_loaded()) unload_model();
+        }
+    });
+}
+
+TranscriptionManager::~TranscriptionManager() {
+    shutdown_.store(true);
+    if (watcher_.joinable()) watcher_.join();
+    for (auto& t : loaders_) if (t.joinable()) t.join();
+    std::lock_guard<std::mutex> g(engine_mu_);
+    if (engine_) { sb_engine_destroy(engine_); engine_ = nullptr; }
+}
+
+bool TranscriptionManager::is_model_loaded() {
+    std::lock_guard<std::mutex> g(engine_mu_);
+    return engine_ != nullptr;
+}
+
+Result<Unit> TranscriptionManager::unload_model() {
+    {
+        std::lock_guard<std::mutex> g(engine_mu_);
+        if (engine_) { sb_engine_destroy(engine_); engine_ = nullptr; }   // drop the engine to free memory
+    }
+    {
+        std::lock_guard<std::mutex> g(model_mu_);
+        current_model_id_.reset();
+    }
+    return Result<Unit>::Ok({});
+}
+
+void TranscriptionManager::maybe_unload_immediately(const std::string&) {
+    const Settings s = get_settings_();
+    if (s.model_unload_timeout == ModelUnloadTimeout::Immediately && is_model_loaded()) unload_model();
+}
+
+Result<Unit> TranscriptionManager::load_model(const std::string& model_id) {
+    const auto path = resolver_(model_id);
+    if (!path) return Result<Unit>::Err("Model not found: " + model_id);
+    const Settings s = get_settings_();
+    sb_config cfg{};
+    cfg.model_path = path->c_str();
+    cfg.device = s.device;
+    cfg.max_batch = s.max_batch;
+    cfg.dtype = s.dtype;
+    cfg.use_cuda_graph = 1;
+    sb_engine* e = nullptr;
+    if (sb_engine_create(&cfg, &e) != SB_OK)
+        return Result<Unit>::Err(std::string("Failed to load whisper model ") + model_id + ": " + sb_last_error());
+    {
+        std::lock_guard<std::mutex> g(engine_mu_);
+        if (engine_) sb_engine_destroy(engine_);
+        engine_ = e;
+    }
+    {
+        std::lock_guard<std::mutex> g(model_mu_);
+        current_model_id_ = model_id;
+    }
+    return Result<Unit>::Ok({});
+}
+
+void TranscriptionManager::initiate_model_load() {
+    {
+        std::lock_guard<std::mutex> g(loading_mu_);
+        if (is_loading_ || is_model_loaded()) return;       // transcription.rs:374-380
+        is_loading_ = true;
+    }
+    loaders_.emplace_back([this] {
+        const Settings s = get_settings_();
+        load_model(s.selected_model);                        // failure leaves the engine empty
+        {
+            std::lock_guard<std::mutex> g(loading_mu_);
+            is_loading_ = false;
+        }
+        loading_cv_.notify_all();
+    });
+}
+
+std::optional<std::string> TranscriptionManager::get_current_model() {
+    std::lock_guard<std::mutex> g(model_mu_);
+    return current_model_id_;
+}
+
+std::string TranscriptionManager::effective_language(const Settings& s) const {
+    // "auto" => None; zh-Hans / zh-Hant => "zh" (transcription.rs:448-459)
+    if (s.selected_language == "zh-Hans" || s.selected_language == "zh-Hant") return "zh";
+    return s.selected_language;
+}
+
+Result<std::string> TranscriptionManager::transcribe(std::vector<float> audio) {
+    last_activity_.store(now_ms());
+    if (audio.empty()) {                                      // transcription.rs:412-416
+        maybe_unload_immediately("empty audio");
+        return Result<std::string>::Ok("");
+    }
+    {
+        std::unique_lock<std::mutex> lk(loading_mu_);         // wait while the model is loading
+        loading_cv_.wait(lk, [this] { return !is_loading_; });
+    }
+    const Settings s = get_settings_();
+    std::string text;
+    {
+        std::lock_guard<std::mutex> g(engine_mu_);            // held for the whole inference (transcription.rs:437)
+        if (!engine_) return Result<std::string>::Err("Model is not loaded for transcription.");
+        sb_params p;
+        sb_params_default(&p);
+        const std::string lang = effective_language(s);
+        p.language = lang == "auto" ? nullptr : lang.c_str();
+        p.translate = s.translate_to_english ? 1 : 0;
+        sb_result r;
+        if (sb_transcribe(engine_, audio.data(), audio.size(), &p, &r) != SB_OK)
+            return Result<std::string>::Err(std::string("Whisper transcription failed: ") + sb_last_error());
+        text.assign(r.text ? r.text : "", r.text_len);
+        sb_result_free(&r);
+    }
+    // apply_custom_words / filter_transcription_output / jargon corrections (transcription.rs:538-580) are
+    // CPU string post-filters outside the replaced module; they run on `text` unchanged.
+    maybe_unload_immediately("transcription");
+    return Result<std::string>::Ok(std::move(text));
+}
+
+std::vector<Result<std::string>> TranscriptionManager::transcribe_batch(const std::vector<std::vector<float>>& clips) {
+    last_activity_.store(now_ms());
+    std::vector<Result<std::string>> out(clips.size());
+    {
+        std::unique_lock<std::mutex> lk(loading_mu_);
+        loading_cv_.wait(lk, [this] { return !is_loading_; });
+    }
+    const Settings s = get_settings_();
+    std::lock_guard<std::mutex> g(engine_mu_);
+    if (!engine_) {
+        for (auto& r : out) r = Result<std::string>::Err("Model is not loaded for transcription.");
+        return out;
+    }
+    std::vector<const float*> ptrs(clips.size());
+    std::vector<size_t> ns(clips.size());
+    for (size_t i = 0; i < clips.size(); ++i) { ptrs[i] = clips[i].data(); ns[i] = clips[i].size(); }
+    sb_params p;
+    sb_params_default(&p);
+    const std::string lang = effective_language(s);
+    p.language = lang == "auto" ? nullptr : lang.c_str();
+    p.translate = s.translate_to_english ? 1 : 0;
+    std::vector<sb_result> res(clips.size());
+    if (sb_transcribe_batch(engine_, ptrs.data(), ns.data(), clips.size(), &p, res.data()) != SB_OK) {
+        const std::string e = std::string("Whisper transcription failed: ") + sb_last_error();
+        for (auto& r : out) r = Result<std::string>::Err(e);
+    } else {
+        for (size_t i = 0; i < clips.size(); ++i) out[i] = Result<std::string>::Ok(std::string(res[i].text ? res[i].text : "", res[i].text_len));
+    }
+    for (auto& r : res) sb_result_free(&r);
+    return out;
+}
+
+}  // namespace sb

@@ -1,0 +1,102 @@
+// transcription_manager.hpp -- C++ host-side mirror of the reference's TranscriptionManager
+// (src-tauri/src/managers/transcription.rs) on top of the C ABI in include/spittle_b200.h.
+//
+// The reference is Rust; no Rust toolchain exists in this image, so the host side above the
+// C ABI is written in C++ (rust/transcription_b200.rs shows the same thing as the drop-in
+// Rust module a maintainer would add).  Same public surface, argument meaning and error
+// behaviour as the reference:
+//
+//   new(app_handle, model_manager)      transcription.rs:89    -> TranscriptionManager(ModelResolver, Settings)
+//   is_model_loaded()                   transcription.rs:170
+//   unload_model()                      transcription.rs:175
+//   maybe_unload_immediately(context)   transcription.rs:211
+//   load_model(model_id)                transcription.rs:223
+//   initiate_model_load()               transcription.rs:374
+//   get_current_model()                 transcription.rs:393
+//   transcribe(audio) -> Result<String> transcription.rs:398
+//   Drop joins the idle watcher         transcription.rs:608-624
+//
+// Result<T> is modelled as sb::Result<T>{ok, value, error}; the error strings are the reference's.
+#pragma once
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <optional>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../include/spittle_b200.h"
+
+namespace sb {
+
+template <typename T>
+struct Result {
+    bool ok = false;
+    T value{};
+    std::string error;
+    static Result Ok(T v) { Result r; r.ok = true; r.value = std::move(v); return r; }
+    static Result Err(std::string e) { Result r; r.ok = false; r.error = std::move(e); return r; }
+};
+struct Unit {};
+
+// settings.rs ModelUnloadTimeout
+enum class ModelUnloadTimeout { Never, Immediately, Min2, Min5, Min10, Min15, Hour1, Sec5 };
+
+// the hot-path-relevant subset of AppSettings (settings.rs:427-429,925): a plain struct replaces
+// the tauri store
+struct Settings {
+    std::string selected_model;
+    std::string selected_language = "auto";
+    bool translate_to_english = false;
+    ModelUnloadTimeout model_unload_timeout = ModelUnloadTimeout::Never;
+    int device = 0;
+    int max_batch = 64;
+    int dtype = SB_DTYPE_F16;
+};
+
+class TranscriptionManager {
+  public:
+    // model_id -> path of a GGML .bin (ModelManager::get_model_path, model.rs:804-847)
+    using ModelResolver = std::function<std::optional<std::string>(const std::string& model_id)>;
+    using SettingsFn = std::function<Settings()>;
+
+    TranscriptionManager(ModelResolver resolver, SettingsFn get_settings);
+    ~TranscriptionManager();
+    TranscriptionManager(const TranscriptionManager&) = delete;
+    TranscriptionManager& operator=(const TranscriptionManager&) = delete;
+
+    bool is_model_loaded();
+    Result<Unit> unload_model();
+    void maybe_unload_immediately(const std::string& context);
+    Result<Unit> load_model(const std::string& model_id);
+    void initiate_model_load();
+    std::optional<std::string> get_current_model();
+    Result<std::string> transcribe(std::vector<float> audio);
+    // additive (SURVEY 8(b) "Batch / multi-GPU surface"): independent clips on this manager's GPU
+    std::vector<Result<std::string>> transcribe_batch(const std::vector<std::vector<float>>& clips);
+
+  private:
+    static uint64_t now_ms();
+    static std::optional<uint64_t> unload_limit_seconds(ModelUnloadTimeout t);
+    std::string effective_language(const Settings& s) const;
+
+    ModelResolver resolver_;
+    SettingsFn get_settings_;
+    std::mutex engine_mu_;                 // engine: Arc<Mutex<Option<LoadedEngine>>>
+    sb_engine* engine_ = nullptr;
+    std::mutex model_mu_;
+    std::optional<std::string> current_model_id_;
+    std::atomic<uint64_t> last_activity_;
+    std::atomic<bool> shutdown_{false};
+    std::thread watcher_;
+    std::mutex loading_mu_;                // is_loading + loading_condvar
+    bool is_loading_ = false;
+    std::condition_variable loading_cv_;
+    std::vector<std::thread> loaders_;
+};
+
+}  // namespace sb

@@ -1,0 +1,58 @@
+//! Raw FFI bindings of include/spittle_b200.h (engine subset used by the drop-in manager).
+//! NOT COMPILED IN THIS IMAGE: there is no Rust toolchain; kept mechanical so a maintainer can
+//! `cargo build` it next to the prebuilt libspittle_b200.so.
+#![allow(non_camel_case_types)]
+use libc::{c_char, c_float, c_int, size_t};
+
+#[repr(C)]
+pub struct sb_engine { _private: [u8; 0] }
+
+#[repr(C)]
+pub struct sb_config {
+    pub model_path: *const c_char,
+    pub device: c_int,
+    pub max_batch: c_int,
+    pub dtype: c_int,          // 0 bf16, 1 f16
+    pub use_cuda_graph: c_int,
+}
+
+#[repr(C)]
+pub struct sb_params {
+    pub language: *const c_char,        // NULL = "auto"
+    pub translate: c_int,
+    pub initial_prompt: *const c_char,
+    pub no_timestamps: c_int,
+    pub suppress_blank: c_int,
+    pub single_segment: c_int,
+    pub max_initial_ts: c_float,
+    pub n_max_tokens: c_int,
+    pub max_windows: c_int,
+}
+
+#[repr(C)]
+pub struct sb_window_info {
+    pub seek: i32, pub n_tokens: i32, pub result_len: i32, pub seek_delta: i32, pub failed: i32, pub token_offset: i32,
+}
+
+#[repr(C)]
+pub struct sb_result {
+    pub text: *mut c_char, pub text_len: size_t,
+    pub tokens: *mut i32, pub n_tokens: size_t,
+    pub sampled: *mut i32, pub n_sampled: size_t,
+    pub margins: *mut c_float,
+    pub windows: *mut sb_window_info, pub n_windows: size_t,
+    pub ms_mel: c_float, pub ms_encode: c_float, pub ms_decode: c_float,
+    pub status: c_int,
+}
+
+extern "C" {
+    pub fn sb_last_error() -> *const c_char;
+    pub fn sb_params_default(p: *mut sb_params);
+    pub fn sb_engine_create(cfg: *const sb_config, out: *mut *mut sb_engine) -> c_int;
+    pub fn sb_engine_destroy(e: *mut sb_engine) -> c_int;
+    pub fn sb_transcribe(e: *mut sb_engine, pcm16k: *const c_float, n_samples: size_t, p: *const sb_params,
+                         out: *mut sb_result) -> c_int;
+    pub fn sb_transcribe_batch(e: *mut sb_engine, pcm16k: *const *const c_float, n_samples: *const size_t,
+                               count: size_t, p: *const sb_params, out: *mut sb_result) -> c_int;
+    pub fn sb_result_free(r: *mut sb_result);
+}

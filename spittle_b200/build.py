@@ -89,7 +89,24 @@ def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) 
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    build_host()
     return LIB
+
+
+def build_host() -> str:
+    """C++ host-side mirror of the reference TranscriptionManager + a small CLI over it."""
+    root = os.path.dirname(HERE)
+    out = os.path.join(root, "host", "sb_transcribe_cli")
+    srcs = [os.path.join(root, "host", f) for f in ("transcription_manager.cpp", "sb_transcribe_cli.cpp")]
+    newest = max(os.path.getmtime(p) for p in srcs + [os.path.join(root, "host", "transcription_manager.hpp"), LIB])
+    if os.path.exists(out) and os.path.getmtime(out) >= newest:
+        return out
+    cmd = ["g++", "-std=c++17", "-O2", "-I", INCLUDE] + srcs + ["-o", out, "-L", HERE, "-lspittle_b200",
+                                                              "-Wl,-rpath,$ORIGIN/../spittle_b200", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return out
 
 
 if __name__ == "__main__":

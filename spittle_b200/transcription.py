@@ -1,0 +1,138 @@
+"""Python mirror of the reference ``TranscriptionManager`` over the C ABI (test/bench convenience;
+the compiled host side is host/transcription_manager.{hpp,cpp}, the Rust drop-in is rust/).
+
+Reference surface (src-tauri/src/managers/transcription.rs): new :89, is_model_loaded :170,
+unload_model :175, maybe_unload_immediately :211, load_model :223, initiate_model_load :374,
+get_current_model :393, transcribe :398.  Error strings are the reference's.
+"""
+from __future__ import annotations
+
+import threading
+import time
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+
+from . import capi
+
+
+class TranscriptionError(RuntimeError):
+    """anyhow::Error analogue."""
+
+
+@dataclass
+class Settings:
+    """Hot-path subset of AppSettings (settings.rs:427-429, 925)."""
+    selected_model: str = ""
+    selected_language: str = "auto"
+    translate_to_english: bool = False
+    model_unload_timeout: str = "never"      # "never" | "immediately" | seconds as str
+    custom_words: List[str] = field(default_factory=list)
+    device: int = 0
+    max_batch: int = 64
+    dtype: int = capi.SB_DTYPE_F16
+
+
+class TranscriptionManager:
+    def __init__(self, model_paths: Dict[str, str], get_settings: Callable[[], Settings]):
+        self._paths = model_paths                  # ModelManager::get_model_path stand-in
+        self._get_settings = get_settings
+        self._engine: Optional[capi.Engine] = None
+        self._engine_lock = threading.Lock()
+        self._current_model_id: Optional[str] = None
+        self._last_activity = time.time()
+        self._loading = False
+        self._loading_cv = threading.Condition()
+
+    def is_model_loaded(self) -> bool:
+        with self._engine_lock:
+            return self._engine is not None
+
+    def unload_model(self) -> None:
+        with self._engine_lock:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = None
+        self._current_model_id = None
+
+    def maybe_unload_immediately(self, context: str) -> None:
+        if self._get_settings().model_unload_timeout == "immediately" and self.is_model_loaded():
+            self.unload_model()
+
+    def load_model(self, model_id: str) -> None:
+        path = self._paths.get(model_id)
+        if path is None:
+            raise TranscriptionError(f"Model not found: {model_id}")
+        s = self._get_settings()
+        try:
+            eng = capi.Engine(path, device=s.device, max_batch=s.max_batch, dtype=s.dtype)
+        except capi.SbError as e:
+            raise TranscriptionError(f"Failed to load whisper model {model_id}: {e}") from e
+        with self._engine_lock:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = eng
+        self._current_model_id = model_id
+
+    def initiate_model_load(self) -> None:
+        with self._loading_cv:
+            if self._loading or self.is_model_loaded():
+                return
+            self._loading = True
+
+        def work():
+            try:
+                self.load_model(self._get_settings().selected_model)
+            except TranscriptionError:
+                pass
+            finally:
+                with self._loading_cv:
+                    self._loading = False
+                    self._loading_cv.notify_all()
+
+        threading.Thread(target=work, daemon=True).start()
+
+    def get_current_model(self) -> Optional[str]:
+        return self._current_model_id
+
+    def _params(self, s: Settings):
+        lang = s.selected_language
+        if lang in ("zh-Hans", "zh-Hant"):
+            lang = "zh"
+        kw = dict(translate=int(s.translate_to_english))
+        p = capi.default_params(**kw)
+        p.language = None if lang == "auto" else lang.encode()
+        return p
+
+    def transcribe(self, audio) -> str:
+        self._last_activity = time.time()
+        a = np.ascontiguousarray(audio, dtype=np.float32)
+        if a.size == 0:                                      # transcription.rs:412-416
+            self.maybe_unload_immediately("empty audio")
+            return ""
+        with self._loading_cv:
+            while self._loading:
+                self._loading_cv.wait()
+        s = self._get_settings()
+        with self._engine_lock:
+            if self._engine is None:
+                raise TranscriptionError("Model is not loaded for transcription.")
+            try:
+                r = self._engine.transcribe(a, self._params(s))
+            except capi.SbError as e:
+                raise TranscriptionError(f"Whisper transcription failed: {e}") from e
+        self.maybe_unload_immediately("transcription")
+        return r.text.decode("utf-8", errors="replace")
+
+    def transcribe_batch(self, clips) -> List[str]:
+        self._last_activity = time.time()
+        with self._loading_cv:
+            while self._loading:
+                self._loading_cv.wait()
+        s = self._get_settings()
+        with self._engine_lock:
+            if self._engine is None:
+                raise TranscriptionError("Model is not loaded for transcription.")
+            res = self._engine.transcribe_batch(clips, self._params(s))
+        return [r.text.decode("utf-8", errors="replace") for r in res]
