@@ -67,9 +67,10 @@ template <> struct Op16<__half> {
 
 __device__ __forceinline__ float gelu_tanh(float x) {
     // 0.5 x (1 + tanh(sqrt(2/pi) x (1 + 0.044715 x^2)))   (whisper.cpp / ggml GELU, App. C.2)
+    // 0.5 (1 + tanh u) == 1 / (1 + exp(-2u)): two MUFU ops instead of tanhf's ~20 instructions
     const float c = 0.79788456080286535588f;
-    float u = c * x * (1.0f + 0.044715f * x * x);
-    return 0.5f * x * (1.0f + tanhf(u));
+    const float u = c * x * fmaf(0.044715f * x, x, 1.0f);
+    return x * __frcp_rn(1.0f + __expf(-2.0f * u));
 }
 
 __device__ __forceinline__ float warp_max(float v) {

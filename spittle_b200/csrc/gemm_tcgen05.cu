@@ -5,14 +5,15 @@
 // Reference rounding points are kept: 16-bit operands (bf16, or f16 exactly like ggml),
 // fp32 accumulation.
 //
-// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+// Structure (one CTA per SM, persistent over output tiles, 320 threads):
 //   warp 0      TMA producer : cp.async.bulk.tensor 2D loads of A (128x64) and W (256x64)
 //                              tiles, 128B-swizzled, into a 4-stage shared-memory ring
 //   warp 1      MMA issuer   : one thread issues tcgen05.mma.cta_group::1.kind::f16
 //                              (UMMA 128x256x16), accumulators in TMEM, double-buffered
 //                              (2 x 256 columns) so the epilogue of tile i overlaps tile i+1
-//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 -> registers -> (+bias, GELU,
-//                              +residual / positional embedding) -> global store
+//   warps 2..9  epilogue     : tcgen05.ld 32x32b.x32 -> registers -> XOR-swizzled smem transpose ->
+//                              (+bias, GELU, +residual / positional embedding) -> fully coalesced
+//                              128-bit global stores (each warp instruction writes whole lines)
 // Synchronisation is mbarrier-only: full/empty per smem stage, tmem_full/tmem_empty per
 // accumulator stage; tcgen05.commit releases smem stages and publishes accumulators.
 // Tile order is n-fastest so the CTAs running together share each A tile through L2 and A
@@ -31,11 +32,13 @@ constexpr int kBN = 256;
 constexpr int kBK = 64;          // 64 x 2 B = 128 B = swizzle span
 constexpr int kStages = 4;
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;           // two per TMEM lane quarter, each takes half of the 256 columns
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kStagingBytes = 32 * 32 * 4;          // per epilogue warp: one 32x32 f32 chunk, XOR-swizzled
 constexpr int kStageBytesA = kBM * kBK * 2;
 constexpr int kStageBytesB = kBN * kBK * 2;
 constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * kStagingBytes;
 
 // ---- PTX wrappers ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -128,7 +131,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
@@ -189,76 +192,60 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
             }
         }
     } else {
-        const int q = warp & 3;   // TMEM lane quarter this warp may access
+        const int ew = warp - 2;              // 0..7
+        const int q = warp & 3;               // TMEM lane quarter this warp may access
+        const int half = ew >> 2;             // which 128 columns of the 256-wide accumulator
+        float4* stg = reinterpret_cast<float4*>(base_ptr + kStages * kStageBytes + 256 + ew * kStagingBytes);
+        const int rsub = lane >> 3;           // read-back: 4 rows per instruction, 8 lanes x float4 per row
+        const int c4 = lane & 7;
         int as = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int n_blk = tile % num_n, m_blk = tile / num_n;
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
-            const int row = m_blk * kBM + q * 32 + lane;
-            const bool row_ok = row < M;
-            const int rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : row;
+            const int row_base = m_blk * kBM + q * 32;
 #pragma unroll 1
-            for (int c = 0; c < kBN / 32; ++c) {
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c = half * 4 + cc;
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kBN + c * 32);
                 tc_ld32(taddr, v);
                 tc_wait_ld();
                 const int col0 = n_blk * kBN + c * 32;
-                if (!row_ok || col0 >= N) continue;
-                float f[32];
+                if (col0 >= N || row_base >= M) continue;       // warp-uniform
+                // transpose through smem: lane = row writes its 32 values as 8 float4, chunk index XOR (row & 7)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                const bool full = col0 + 32 <= N;
-                if (full) {
-                    if (ep.bias) {
+                for (int j = 0; j < 8; ++j)
+                    stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                __syncwarp();
+                const int col = col0 + c4 * 4;
+                const bool col_ok = col < N;                     // N % 8 == 0: a 4-column group is all in or all out
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ep.bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
-                            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + rsub;
+                    const int row = row_base + rr;
+                    float4 f = stg[rr * 8 + (c4 ^ (rr & 7))];
+                    if (row < M && col_ok) {
+                        f.x += bias4.x; f.y += bias4.y; f.z += bias4.z; f.w += bias4.w;
+                        if (ep.act == 1) { f.x = gelu_tanh(f.x); f.y = gelu_tanh(f.y); f.z = gelu_tanh(f.z); f.w = gelu_tanh(f.w); }
+                        if (ep.residual) {
+                            const int rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : row;
+                            const float4 r4 = *reinterpret_cast<const float4*>(ep.residual + (int64_t)rrow * ep.ldr + col);
+                            f.x += r4.x; f.y += r4.y; f.z += r4.z; f.w += r4.w;
                         }
-                    }
-                    if (ep.act == 1) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(f[j]);
-                    }
-                    if (ep.residual) {
-                        const float* r = ep.residual + (int64_t)rrow * ep.ldr + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b = *reinterpret_cast<const float4*>(r + j);
-                            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+                        if (ep.out_f32) {
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldo + col) = f;
+                        } else {
+                            uint2 u;
+                            u.x = Op16<T>::pack2(f.x, f.y); u.y = Op16<T>::pack2(f.z, f.w);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<T*>(ep.out) + (int64_t)row * ep.ldo + col) = u;
                         }
-                    }
-                    if (ep.out_f32) {
-                        float* o = reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldo + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    } else {
-                        T* o = reinterpret_cast<T*>(ep.out) + (int64_t)row * ep.ldo + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 u;
-                            u.x = Op16<T>::pack2(f[j], f[j + 1]);
-                            u.y = Op16<T>::pack2(f[j + 2], f[j + 3]);
-                            u.z = Op16<T>::pack2(f[j + 4], f[j + 5]);
-                            u.w = Op16<T>::pack2(f[j + 6], f[j + 7]);
-                            *reinterpret_cast<uint4*>(o + j) = u;
-                        }
-                    }
-                } else {
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = col0 + j;
-                        if (col >= N) break;
-                        float x = f[j];
-                        if (ep.bias) x += __ldg(ep.bias + col);
-                        if (ep.act == 1) x = gelu_tanh(x);
-                        if (ep.residual) x += ep.residual[(int64_t)rrow * ep.ldr + col];
-                        if (ep.out_f32) reinterpret_cast<float*>(ep.out)[(int64_t)row * ep.ldo + col] = x;
-                        else reinterpret_cast<T*>(ep.out)[(int64_t)row * ep.ldo + col] = Op16<T>::from_f32(x);
                     }
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
