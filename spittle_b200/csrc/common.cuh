@@ -102,6 +102,30 @@ __host__ __device__ __forceinline__ float key_float(int k) {
 #endif
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// Decoder-step kernels are ~140 small dependent launches per token.  Each calls pdl_wait() before
+// touching anything a predecessor writes and pdl_trigger() once its main work is issued, so the next
+// kernel is scheduled and runs its independent prologue (weight prefetch, first K tile) under this
+// kernel's tail.  Triggering at the very top was measured slower: early-resident CTAs of the following
+// kernels steal registers/smem from the bandwidth-bound cross-attention.  Data produced by a
+// predecessor is always read through L2 (__ldcg): co-resident kernels can leave stale lines in L1,
+// which is only invalidated at launch.  Without the launch attribute both calls are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+extern bool g_pdl;   // core.cu; env SB_PDL=0 disables
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 

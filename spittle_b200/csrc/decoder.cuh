@@ -9,7 +9,7 @@ struct SpecialIds {
 };
 
 // per-sequence decode state, device resident (whisper_full's per-decoder bookkeeping, App. C.4)
-struct SeqState {
+struct __align__(16) SeqState {
     int n_tok;        // tokens sampled so far in this window (tokens_cur.size())
     int last, prev;   // last / penultimate sampled token
     int has_ts;
@@ -20,7 +20,7 @@ struct SeqState {
     int seek, seek_end;
     float sum_logprob;
     int pad_;
-};
+};   // 48 bytes, 16-byte aligned array elements (read with three 128-bit loads)
 
 struct SamplerArgs {
     SeqState* state;          // [B]
@@ -40,6 +40,14 @@ struct SamplerArgs {
     const int* pos_ptr;       // device: position of the token just fed to the decoder
     const int* prompt;        // device: prompt tokens
     int n_prompt;
+};
+
+// optional fused prologue of the cross-attention kernel: LayerNorm + query projection
+struct FusedQ {
+    const float* x = nullptr;      // residual stream [B, d] f32; nullptr -> q is read from memory instead
+    const float* ln_g = nullptr; const float* ln_b = nullptr;
+    const void* wq = nullptr;      // [d, d] 16-bit
+    const float* bq = nullptr;
 };
 
 struct SkinnyEpilogue {
@@ -89,7 +97,7 @@ template <typename T> int attn_enc(const T* qkv, T* out, int n_windows, int n_ct
 template <typename T> int dec_embed(const T* tok_emb, const float* pos_emb, const int* tokens, const int* pos_ptr, float* x, int Bn, int d, cudaStream_t st);
 template <typename T> int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, const SkinnyEpilogue& ep, cudaStream_t st);
 template <typename T> int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const int* pos_ptr, int Bn, int n_head, int d, int n_text_ctx, cudaStream_t st);
-template <typename T> int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t ld_kv, int64_t win_stride, T* out, int Bn, int n_head, int d, int n_ctx, cudaStream_t st);
+template <typename T> int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t ld_kv, int64_t win_stride, T* out, int Bn, int n_head, int d, int n_ctx, const FusedQ& fq, cudaStream_t st);
 int sample_step(const float* logits, int ld, const SamplerArgs& a, int Bn, cudaStream_t st);
 int dec_advance(int* pos_ptr, int* step_ptr, int n_prompt, cudaStream_t st);
 

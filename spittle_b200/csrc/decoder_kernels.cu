@@ -22,8 +22,10 @@ __global__ void __launch_bounds__(256) k_dec_embed(const T* __restrict__ tok_emb
                                                    const int* __restrict__ tokens, const int* __restrict__ pos_ptr,
                                                    float* __restrict__ x, int d) {
     const int b = blockIdx.x;
-    const int tok = tokens[b];
-    const int pos = *pos_ptr;
+    pdl_wait();
+    pdl_trigger();
+    const int tok = __ldcg(tokens + b);
+    const int pos = __ldcg(pos_ptr);
     for (int i = threadIdx.x; i < d; i += blockDim.x)
         x[(int64_t)b * d + i] = Op16<T>::to_f32(tok_emb[(int64_t)tok * d + i]) + pos_emb[(int64_t)pos * d + i];
 }
@@ -84,46 +86,61 @@ __global__ void __launch_bounds__(256) k_skinny_gemm(const T* __restrict__ X, in
 #pragma unroll
     for (int i = 0; i < kWB; ++i)
         if (i < n_it) { wlo[i] = ldg_nc_v4(w_lo + (warp + 8 * i) * 32); whi[i] = ldg_nc_v4(w_hi + (warp + 8 * i) * 32); }
-    uint4 xv[8];
-    if (n_it > 0) {
+    pdl_wait();      // weights are immutable: only the activations depend on the previous kernel
+    // epilogue operands do not depend on the main loop: fetch them now so their L2 round trip is hidden
+    const int e_n = tid >> 2, e_rq = (tid & 3) * 4;
+    float e_res[4] = {0.f, 0.f, 0.f, 0.f}, e_bias[4] = {0.f, 0.f, 0.f, 0.f};
+    if (e_n < nb) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int n = j * 8 + g;
-            xv[j] = n < nb ? *reinterpret_cast<const uint4*>(xb + (int64_t)n * ldx + warp * 32) : make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < 4; ++i) {
+            const int row = row0 + e_rq + i;
+            if (row < N) {
+                if (ep.bias) e_bias[i] = __ldg(ep.bias + row);
+                if (ep.residual) e_res[i] = __ldcg(ep.residual + (int64_t)(b0 + e_n) * ep.ldr + row);
+            }
         }
     }
-    for (int it0 = 0; it0 < n_it; it0 += kWB) {
+    // activation fragments: kXB k-blocks in flight (L2 latency ~ 0.4 us per round trip)
+    constexpr int kXB = 3;
+    uint4 xq[kXB][8];
 #pragma unroll
-        for (int i = 0; i < kWB; ++i) {
+    for (int i = 0; i < kXB; ++i)
+        if (i < n_it) {
+            const int k1 = (warp + 8 * i) * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = j * 8 + g;
+                xq[i][j] = n < nb ? __ldcg(reinterpret_cast<const uint4*>(xb + (int64_t)n * ldx + k1)) : make_uint4(0, 0, 0, 0);
+            }
+        }
+    // n_it is a multiple of nothing in particular: rotate the two register rings with fully unrolled
+    // bodies of lcm(kWB, kXB) = 12 iterations so every ring index is a compile-time constant
+    for (int it0 = 0; it0 < n_it; it0 += 12) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
             const int it = it0 + i;
             if (it >= n_it) break;
-            const uint4 alo = wlo[i], ahi = whi[i];
-            // refill this slot with the block kWB iterations ahead
+            const uint4 alo = wlo[i % kWB], ahi = whi[i % kWB];
             if (it + kWB < n_it) {
-                wlo[i] = ldg_nc_v4(w_lo + (warp + 8 * (it + kWB)) * 32);
-                whi[i] = ldg_nc_v4(w_hi + (warp + 8 * (it + kWB)) * 32);
-            }
-            uint4 xn[8];
-            const bool more = it + 1 < n_it;
-            if (more) {
-                const int k1 = (warp + 8 * (it + 1)) * 32;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int n = j * 8 + g;
-                    xn[j] = n < nb ? *reinterpret_cast<const uint4*>(xb + (int64_t)n * ldx + k1) : make_uint4(0, 0, 0, 0);
-                }
+                wlo[i % kWB] = ldg_nc_v4(w_lo + (warp + 8 * (it + kWB)) * 32);
+                whi[i % kWB] = ldg_nc_v4(w_hi + (warp + 8 * (it + kWB)) * 32);
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                MmaOpD<T>::mma(acc[j], alo.x, ahi.x, alo.y, ahi.y, xv[j].x, xv[j].y);
-                MmaOpD<T>::mma(acc[j], alo.z, ahi.z, alo.w, ahi.w, xv[j].z, xv[j].w);
+                MmaOpD<T>::mma(acc[j], alo.x, ahi.x, alo.y, ahi.y, xq[i % kXB][j].x, xq[i % kXB][j].y);
+                MmaOpD<T>::mma(acc[j], alo.z, ahi.z, alo.w, ahi.w, xq[i % kXB][j].z, xq[i % kXB][j].w);
             }
-            if (more) {
+            if (it + kXB < n_it) {     // refill this slot: kXB k-blocks of activations stay in flight
+                const int k1 = (warp + 8 * (it + kXB)) * 32;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) xv[j] = xn[j];
+                for (int j = 0; j < 8; ++j) {
+                    const int n = j * 8 + g;
+                    xq[i % kXB][j] = n < nb ? __ldcg(reinterpret_cast<const uint4*>(xb + (int64_t)n * ldx + k1)) : make_uint4(0, 0, 0, 0);
+                }
             }
         }
     }
+    pdl_trigger();   // main loop done: let the next kernel get scheduled and prefetch its weights
     // acc[j]: c0,c1 = (row g, batch j*8+2t, +1), c2,c3 = (row g+8, ...)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -134,7 +151,7 @@ __global__ void __launch_bounds__(256) k_skinny_gemm(const T* __restrict__ X, in
     }
     __syncthreads();
     // epilogue: thread -> (batch n = tid / 4, 4 consecutive rows r = (tid % 4) * 4)
-    const int n = tid >> 2, rq = (tid & 3) * 4;
+    const int n = e_n, rq = e_rq;
     if (n < nb) {
         const int b = b0 + n;
 #pragma unroll
@@ -144,9 +161,9 @@ __global__ void __launch_bounds__(256) k_skinny_gemm(const T* __restrict__ X, in
             float v = 0.f;
 #pragma unroll
             for (int w8 = 0; w8 < 8; ++w8) v += s_red[w8][r][n];
-            if (ep.bias) v += __ldg(ep.bias + row);
+            v += e_bias[i];
             if (ep.act == 1) v = gelu_tanh(v);
-            if (ep.residual) v += ep.residual[(int64_t)b * ep.ldr + row];
+            v += e_res[i];
             if (ep.out32) ep.out32[(int64_t)b * ep.ldo32 + row] = v;
             if (ep.out16) reinterpret_cast<T*>(ep.out16)[(int64_t)b * ep.ldo16 + row] = Op16<T>::from_f32(v);
         }
@@ -164,21 +181,23 @@ __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv
     __shared__ float s_p[4][448];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int idx = blockIdx.x * 4 + warp;
+    pdl_wait();
+    pdl_trigger();
     if (idx >= Bn * n_head) return;
     const int b = idx / n_head, h = idx - b * n_head;
-    const int pos = *pos_ptr;                 // index of the new token; attends to [0, pos]
+    const int pos = __ldcg(pos_ptr);          // index of the new token; attends to [0, pos]
     const T* q = qkv + (int64_t)b * 3 * d + h * 64;
     T* kb = kc + ((int64_t)b * n_text_ctx) * d + h * 64;
     T* vb = vc + ((int64_t)b * n_text_ctx) * d + h * 64;
     // append this step's K, V (each lane moves 2 elements)
-    reinterpret_cast<uint32_t*>(kb + (int64_t)pos * d)[lane] = reinterpret_cast<const uint32_t*>(q + d)[lane];
-    reinterpret_cast<uint32_t*>(vb + (int64_t)pos * d)[lane] = reinterpret_cast<const uint32_t*>(q + 2 * d)[lane];
+    reinterpret_cast<uint32_t*>(kb + (int64_t)pos * d)[lane] = __ldcg(reinterpret_cast<const uint32_t*>(q + d) + lane);
+    reinterpret_cast<uint32_t*>(vb + (int64_t)pos * d)[lane] = __ldcg(reinterpret_cast<const uint32_t*>(q + 2 * d) + lane);
     __syncwarp();
     // scores: lane <-> key
     float qf[64];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-        const float2 f = Op16<T>::unpack2(reinterpret_cast<const uint32_t*>(q)[i]);
+        const float2 f = Op16<T>::unpack2(__ldcg(reinterpret_cast<const uint32_t*>(q) + i));
         qf[2 * i] = f.x; qf[2 * i + 1] = f.y;
     }
     const int n_keys = pos + 1;
@@ -188,7 +207,7 @@ __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv
         float s = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const uint4 u = kr[c];
+            const uint4 u = __ldcg(kr + c);
             float2 f;
             f = Op16<T>::unpack2(u.x); s = fmaf(qf[c * 8 + 0], f.x, s); s = fmaf(qf[c * 8 + 1], f.y, s);
             f = Op16<T>::unpack2(u.y); s = fmaf(qf[c * 8 + 2], f.x, s); s = fmaf(qf[c * 8 + 3], f.y, s);
@@ -209,12 +228,25 @@ __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
     __syncwarp();
-    // PV: lane <-> 2 output dims; probabilities rounded to the operand type like ggml's mul_mat
+    // PV: lane <-> 2 output dims; probabilities rounded to the operand type like ggml's mul_mat.
+    // Keys are taken 16 at a time with all 16 value loads issued before the FMAs (the loop is
+    // otherwise a chain of exposed L2 latencies).
     float o0 = 0.f, o1 = 0.f;
-    for (int k = 0; k < n_keys; ++k) {
-        const float p = Op16<T>::to_f32(Op16<T>::from_f32(s_p[warp][k] * inv));
-        const float2 f = Op16<T>::unpack2(reinterpret_cast<const uint32_t*>(vb + (int64_t)k * d)[lane]);
-        o0 = fmaf(p, f.x, o0); o1 = fmaf(p, f.y, o1);
+    for (int k0 = 0; k0 < n_keys; k0 += 16) {
+        uint32_t vv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int k = min(k0 + i, n_keys - 1);
+            vv[i] = __ldcg(reinterpret_cast<const uint32_t*>(vb + (int64_t)k * d) + lane);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (k0 + i < n_keys) {
+                const float p = Op16<T>::to_f32(Op16<T>::from_f32(s_p[warp][k0 + i] * inv));
+                const float2 f = Op16<T>::unpack2(vv[i]);
+                o0 = fmaf(p, f.x, o0); o1 = fmaf(p, f.y, o1);
+            }
+        }
     }
     reinterpret_cast<uint32_t*>(out + (int64_t)b * d + h * 64)[lane] = Op16<T>::pack2(o0, o1);
 }
@@ -232,18 +264,20 @@ __device__ __forceinline__ void cp_async16_d(uint32_t dst, const void* src, bool
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz));
 }
 
+// With fq.x != nullptr the kernel also performs the cross-attention LayerNorm and the query
+// projection of its own (sequence, head): q_h = Wq[h*64 .. h*64+63, :] . round16(LN(x_b)) + bq
+// (two fewer launches per decoder layer; the extra prologue hides behind the K-tile stream).
 template <typename T>
 __global__ void __launch_bounds__(256) k_dec_cross_attn(const T* __restrict__ q, int ldq, const T* __restrict__ kbase,
                                                         const T* __restrict__ vbase, int64_t ld_kv, int64_t win_stride,
-                                                        T* __restrict__ out, int d, int n_ctx) {
+                                                        T* __restrict__ out, int d, int n_ctx, FusedQ fq) {
     __shared__ __align__(16) T s_tile[2][kXKeysPerTile * kXLd];
-    __shared__ float s_sc[1504];
+    __shared__ float s_sc[1504];      // scores; doubles as the normalised activation row in the fused prologue
     __shared__ float s_q[64];
     __shared__ float s_red[8];
     __shared__ float s_o[4][64];
     const int h = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid < 64) s_q[tid] = Op16<T>::to_f32(q[(int64_t)b * ldq + h * 64 + tid]) * 0.125f;
     const T* kp = kbase + (int64_t)b * win_stride + h * 64;
     const T* vp = vbase + (int64_t)b * win_stride + h * 64;
     const int n_tiles = (n_ctx + kXKeysPerTile - 1) / kXKeysPerTile;
@@ -262,7 +296,69 @@ __global__ void __launch_bounds__(256) k_dec_cross_attn(const T* __restrict__ q,
     };
 
     // ---- pass 1: scores ----
-    load_tile(0, kp, 0);
+    load_tile(0, kp, 0);          // the encoder wrote K/V long ago: start the stream before the dependency wait
+    pdl_wait();
+    if (fq.x == nullptr) {
+        if (tid < 32) {
+            const float2 f = Op16<T>::unpack2(__ldcg(reinterpret_cast<const uint32_t*>(q + (int64_t)b * ldq + h * 64) + tid));
+            s_q[2 * tid] = f.x * 0.125f; s_q[2 * tid + 1] = f.y * 0.125f;
+        }
+    } else {
+        // LayerNorm of row b (two-pass, values held in registers; d <= 1536)
+        float xv[6];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int k = tid + 256 * i;
+            xv[i] = k < d ? __ldcg(fq.x + (int64_t)b * d + k) : 0.f;
+            sum += xv[i];
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) s_red[warp] = sum;
+        __syncthreads();
+        float mean = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) mean += s_red[w];
+        mean /= (float)d;
+        __syncthreads();
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int k = tid + 256 * i;
+            if (k < d) { xv[i] -= mean; sq += xv[i] * xv[i]; }
+        }
+        sq = warp_sum(sq);
+        if (lane == 0) s_red[warp] = sq;
+        __syncthreads();
+        float var = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) var += s_red[w];
+        const float rstd = rsqrtf(var / (float)d + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int k = tid + 256 * i;
+            if (k < d) s_sc[k] = Op16<T>::to_f32(Op16<T>::from_f32(xv[i] * rstd * __ldg(fq.ln_g + k) + __ldg(fq.ln_b + k)));
+        }
+        __syncthreads();
+        // q_h[j] = Wq[h*64 + j, :] . h + bq : 4 threads per output row, each a contiguous quarter of K
+        const int j = tid >> 2, part = tid & 3;
+        const int kq = d >> 2;                       // d % 32 == 0
+        const T* wr = reinterpret_cast<const T*>(fq.wq) + (int64_t)(h * 64 + j) * d + part * kq;
+        const float* hr = s_sc + part * kq;
+        float acc = 0.f;
+        for (int k = 0; k < kq; k += 8) {
+            const uint4 u = ldg_nc_v4(wr + k);
+            float2 f;
+            f = Op16<T>::unpack2(u.x); acc = fmaf(f.x, hr[k + 0], acc); acc = fmaf(f.y, hr[k + 1], acc);
+            f = Op16<T>::unpack2(u.y); acc = fmaf(f.x, hr[k + 2], acc); acc = fmaf(f.y, hr[k + 3], acc);
+            f = Op16<T>::unpack2(u.z); acc = fmaf(f.x, hr[k + 4], acc); acc = fmaf(f.y, hr[k + 5], acc);
+            f = Op16<T>::unpack2(u.w); acc = fmaf(f.x, hr[k + 6], acc); acc = fmaf(f.y, hr[k + 7], acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        __syncthreads();                              // everyone is done reading the activation row in s_sc
+        if (part == 0) s_q[j] = Op16<T>::to_f32(Op16<T>::from_f32(acc + __ldg(fq.bq + h * 64 + j))) * 0.125f;
+    }
     for (int tI = 0; tI < n_tiles; ++tI) {
         const int buf = tI & 1;
         if (tI + 1 < n_tiles) { load_tile(buf ^ 1, kp, (tI + 1) * kXKeysPerTile); asm volatile("cp.async.wait_group 1;"); }
@@ -323,6 +419,7 @@ __global__ void __launch_bounds__(256) k_dec_cross_attn(const T* __restrict__ q,
         }
         __syncthreads();
     }
+    pdl_trigger();
     // reduce the 8 key groups
     if (warp >= 4) { s_o[warp - 4][2 * lane] = o0; s_o[warp - 4][2 * lane + 1] = o1; }
     __syncthreads();
@@ -401,15 +498,39 @@ struct LogitMask {
     }
 };
 
+// online log-sum-exp accumulator
+struct Lse {
+    float m, s;
+    __device__ __forceinline__ void add(float x) {
+        if (x > m) { s = s * __expf(m - x) + 1.0f; m = x; }
+        else s += __expf(x - m);
+    }
+    __device__ __forceinline__ void merge(float m2, float s2) {
+        const float M = fmaxf(m, m2);
+        if (M == -INFINITY) return;
+        s = s * __expf(m - M) + s2 * __expf(m2 - M);
+        m = M;
+    }
+};
+
 __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const float* __restrict__ logits, int ld,
                                                                        SamplerArgs a) {
     __shared__ float sf[32];
+    __shared__ float sg[32];
     __shared__ int si[32];
     BlockRed red{sf, si};
     const int b = blockIdx.x;
-    SeqState st = a.state[b];
-    const int step = *a.step_ptr;          // index of the token being sampled (i in whisper_full)
-    const int pos = *a.pos_ptr;
+    pdl_wait();
+    pdl_trigger();
+    SeqState st;
+    {
+        static_assert(sizeof(SeqState) == 48, "SeqState is read as three int4");
+        const int4* sp4 = reinterpret_cast<const int4*>(a.state + b);
+        int4* dp4 = reinterpret_cast<int4*>(&st);
+        dp4[0] = __ldcg(sp4); dp4[1] = __ldcg(sp4 + 1); dp4[2] = __ldcg(sp4 + 2);
+    }
+    const int step = __ldcg(a.step_ptr);   // index of the token being sampled (i in whisper_full)
+    const int pos = __ldcg(a.pos_ptr);
     if (pos < a.n_prompt - 1) {            // still feeding the prompt: queue its next token
         if (threadIdx.x == 0) a.next_tokens[b] = a.prompt[pos + 1];
         return;
@@ -429,38 +550,59 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
     mk.max_initial_tid = a.max_initial_tid;
     mk.init_lim = sp.beg + a.max_initial_tid + 1;     // tokens >= this are suppressed at step 0
     mk.mono_lim = sp.beg + st.seek_delta / 2;
-    // sweep 1: maxima
-    float mx_ts = -INFINITY, mx_text = -INFINITY;
-    for (int id = threadIdx.x; id < V; id += kSampThreads) {
-        if (mk.suppressed(id)) continue;
-        const float x = lg[id];
-        if (id >= sp.beg) mx_ts = fmaxf(mx_ts, x); else mx_text = fmaxf(mx_text, x);
-    }
-    mx_ts = red.max_f(mx_ts);
-    mx_text = red.max_f(mx_text);
-    const float mx = fmaxf(mx_ts, mx_text);
-    // sweep 2: exp sums (all, timestamps)
-    float se = 0.f, se_ts = 0.f;
-    for (int id = threadIdx.x; id < V; id += kSampThreads) {
-        if (mk.suppressed(id)) continue;
-        const float x = lg[id];
-        if (x > -INFINITY) {
-            se += __expf(x - mx);
-            if (id >= sp.beg) se_ts += __expf(x - mx_ts);
+    // plain text tokens [0, eot) only see two rules: the pairing rule and suppress_blank
+    const bool text_off = mk.last_ts && !mk.pen_ts;
+    const int blank_off = (mk.suppress_blank && mk.is_initial) ? sp.blank : -1;
+    // sweep 1: online log-sum-exp over all / timestamp tokens, text maximum
+    Lse all{-INFINITY, 0.f}, ts{-INFINITY, 0.f};
+    float mx_text = -INFINITY;
+    if (!text_off)
+        for (int id = threadIdx.x; id < sp.eot; id += kSampThreads) {
+            if (id == blank_off) continue;
+            const float x = __ldcg(lg + id);
+            all.add(x);
+            mx_text = fmaxf(mx_text, x);
         }
+    for (int id = sp.eot + threadIdx.x; id < V; id += kSampThreads) {
+        if (mk.suppressed(id)) continue;
+        const float x = __ldcg(lg + id);
+        all.add(x);
+        if (id >= sp.beg) ts.add(x); else mx_text = fmaxf(mx_text, x);
     }
-    se = red.sum_f(se);
-    se_ts = red.sum_f(se_ts);
-    const float lse = logf(se) + mx;
+    // block-combine the two accumulators and the text maximum
+    auto combine = [&](Lse& v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, v.m, o), s2 = __shfl_xor_sync(0xffffffffu, v.s, o);
+            v.merge(m2, s2);
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { sf[threadIdx.x >> 5] = v.m; sg[threadIdx.x >> 5] = v.s; }
+        __syncthreads();
+        Lse r{sf[0], sg[0]};
+        for (int i = 1; i < kSampThreads / 32; ++i) r.merge(sf[i], sg[i]);
+        v = r;
+    };
+    combine(all);
+    combine(ts);
+    mx_text = red.max_f(mx_text);
+    const float lse = logf(all.s) + all.m;
     // timestamp_logprob = logsumexp(logprobs[beg:]) ; max_text_token_logprob = max(logprobs[:beg])
-    const float ts_logprob = (mx_ts > -INFINITY && se_ts > 0.f) ? (logf(se_ts) + mx_ts - lse) : -INFINITY;
+    const float ts_logprob = (ts.m > -INFINITY && ts.s > 0.f) ? (logf(ts.s) + ts.m - lse) : -INFINITY;
     const float text_logprob = mx_text - lse;
     const bool force_ts = ts_logprob > text_logprob;
-    // sweep 3: arg-max (first maximum in ascending id) and the runner-up value
+    // sweep 2: arg-max (first maximum in ascending id) and the runner-up value
     float bv = -INFINITY, b2 = -INFINITY; int bi = 0x7fffffff;
-    for (int id = threadIdx.x; id < V; id += kSampThreads) {
+    if (!text_off && !force_ts)
+        for (int id = threadIdx.x; id < sp.eot; id += kSampThreads) {
+            if (id == blank_off) continue;
+            const float x = __ldcg(lg + id);
+            if (x > bv) { b2 = bv; bv = x; bi = id; }
+            else if (x > b2) b2 = x;
+        }
+    for (int id = sp.eot + threadIdx.x; id < V; id += kSampThreads) {
         if (mk.suppressed(id) || (force_ts && id < sp.beg)) continue;
-        const float x = lg[id];
+        const float x = __ldcg(lg + id);
         if (x > bv) { b2 = bv; bv = x; bi = id; }
         else if (x > b2) b2 = x;
     }
@@ -471,7 +613,7 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
 
     int tok = gi;
     if (a.forced) {
-        const int f = a.forced[(int64_t)b * a.n_max + step];
+        const int f = __ldcg(a.forced + (int64_t)b * a.n_max + step);
         if (f >= 0) tok = f;
     }
     a.tokens_out[(int64_t)b * a.n_max + step] = tok;
@@ -502,8 +644,10 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
 
 // advance the shared position / step counters (single thread) after a step
 __global__ void k_dec_advance(int* pos_ptr, int* step_ptr, int n_prompt) {
-    const int p = *pos_ptr;
-    if (p >= n_prompt - 1) *step_ptr += 1;
+    pdl_wait();
+    pdl_trigger();
+    const int p = __ldcg(pos_ptr);
+    if (p >= n_prompt - 1) *step_ptr = __ldcg(step_ptr) + 1;
     *pos_ptr = p + 1;
 }
 
@@ -511,7 +655,7 @@ __global__ void k_dec_advance(int* pos_ptr, int* step_ptr, int n_prompt) {
 template <typename T>
 int dec_embed(const T* tok_emb, const float* pos_emb, const int* tokens, const int* pos_ptr, float* x, int Bn, int d,
               cudaStream_t st) {
-    k_dec_embed<T><<<Bn, 256, 0, st>>>(tok_emb, pos_emb, tokens, pos_ptr, x, d);
+    launch_pdl(k_dec_embed<T>, dim3(Bn), dim3(256), 0, st, tok_emb, pos_emb, tokens, pos_ptr, x, d);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
@@ -520,7 +664,7 @@ template <typename T>
 int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, const SkinnyEpilogue& ep, cudaStream_t st) {
     SB_CHECK_ARG(K % 32 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "skinny gemm: K % 32 and 16-byte row alignment required");
     dim3 grid(ceil_div(N, 16), ceil_div(Bn, 64));
-    k_skinny_gemm<T><<<grid, 256, 0, st>>>(X, ldx, W, ldw, Bn, N, K, ep);
+    launch_pdl(k_skinny_gemm<T>, grid, dim3(256), 0, st, X, ldx, W, ldw, Bn, N, K, ep);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
@@ -529,29 +673,29 @@ template <typename T>
 int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const int* pos_ptr, int Bn, int n_head, int d, int n_text_ctx,
                   cudaStream_t st) {
     SB_CHECK_ARG(n_text_ctx <= 448 && d == n_head * 64, "self attention: n_text_ctx <= 448, d_head 64");
-    k_dec_self_attn<T><<<ceil_div(Bn * n_head, 4), 128, 0, st>>>(qkv, kc, vc, out, pos_ptr, Bn, n_head, d, n_text_ctx);
+    launch_pdl(k_dec_self_attn<T>, dim3(ceil_div(Bn * n_head, 4)), dim3(128), 0, st, qkv, kc, vc, out, pos_ptr, Bn, n_head, d, n_text_ctx);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
 }
 template <typename T>
 int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t ld_kv, int64_t win_stride, T* out, int Bn,
-                   int n_head, int d, int n_ctx, cudaStream_t st) {
-    SB_CHECK_ARG(n_ctx <= 1504 && d == n_head * 64, "cross attention: n_audio_ctx <= 1504, d_head 64");
+                   int n_head, int d, int n_ctx, const FusedQ& fq, cudaStream_t st) {
+    SB_CHECK_ARG(n_ctx <= 1504 && d == n_head * 64 && d <= 1504 && d % 32 == 0, "cross attention: n_audio_ctx, d <= 1504, d_head 64");
     dim3 grid(n_head, Bn);
-    k_dec_cross_attn<T><<<grid, 256, 0, st>>>(q, ldq, kbase, vbase, ld_kv, win_stride, out, d, n_ctx);
+    launch_pdl(k_dec_cross_attn<T>, grid, dim3(256), 0, st, q, ldq, kbase, vbase, ld_kv, win_stride, out, d, n_ctx, fq);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
 }
 int sample_step(const float* logits, int ld, const SamplerArgs& a, int Bn, cudaStream_t st) {
-        k_logits_filter_argmax<<<Bn, kSampThreads, 0, st>>>(logits, ld, a);
+        launch_pdl(k_logits_filter_argmax, dim3(Bn), dim3(kSampThreads), 0, st, logits, ld, a);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
 }
 int dec_advance(int* pos_ptr, int* step_ptr, int n_prompt, cudaStream_t st) {
-    k_dec_advance<<<1, 1, 0, st>>>(pos_ptr, step_ptr, n_prompt);
+    launch_pdl(k_dec_advance, dim3(1), dim3(1), 0, st, pos_ptr, step_ptr, n_prompt);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
@@ -561,7 +705,7 @@ int dec_advance(int* pos_ptr, int* step_ptr, int n_prompt, cudaStream_t st) {
     template int dec_embed<T>(const T*, const float*, const int*, const int*, float*, int, int, cudaStream_t);    \
     template int skinny_gemm<T>(const T*, int, const T*, int, int, int, int, const SkinnyEpilogue&, cudaStream_t); \
     template int dec_self_attn<T>(const T*, T*, T*, T*, const int*, int, int, int, int, cudaStream_t);             \
-    template int dec_cross_attn<T>(const T*, int, const T*, const T*, int64_t, int64_t, T*, int, int, int, int, cudaStream_t);
+    template int dec_cross_attn<T>(const T*, int, const T*, const T*, int64_t, int64_t, T*, int, int, int, int, const FusedQ&, cudaStream_t);
 SB_INST_D(__nv_bfloat16)
 SB_INST_D(__half)
 

@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(256) k_layernorm(const float* x, const float* 
                                                    float* out32, int rows, int d, float eps) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_wait();
+    pdl_trigger();
     if (warp >= rows) return;
     const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)warp * d);
     const int n4 = d >> 2;
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(256) k_layernorm(const float* x, const float* 
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
         const int idx = lane + 32 * i;
-        v[i] = idx < n4 ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = idx < n4 ? __ldcg(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);   // L2 path: safe under PDL overlap
         s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
     const float mean = warp_sum(s) / (float)d;
@@ -321,10 +323,10 @@ int layernorm(const float* x, const float* g, const float* b, T* out16, float* o
     SB_CHECK_ARG(d % 4 == 0 && d <= 32 * 4 * 12, "layernorm: d must be a multiple of 4 and <= 1536");
     const int blocks = ceil_div(rows, 8);
     const int n4 = d / 4;
-    if (n4 <= 32 * 2) k_layernorm<T, 2><<<blocks, 256, 0, st>>>(x, g, b, out16, out32, rows, d, 1e-5f);
-    else if (n4 <= 32 * 6) k_layernorm<T, 6><<<blocks, 256, 0, st>>>(x, g, b, out16, out32, rows, d, 1e-5f);
-    else if (n4 <= 32 * 10) k_layernorm<T, 10><<<blocks, 256, 0, st>>>(x, g, b, out16, out32, rows, d, 1e-5f);
-    else k_layernorm<T, 12><<<blocks, 256, 0, st>>>(x, g, b, out16, out32, rows, d, 1e-5f);
+    if (n4 <= 32 * 2) launch_pdl(k_layernorm<T, 2>, dim3(blocks), dim3(256), 0, st, x, g, b, out16, out32, rows, d, 1e-5f);
+    else if (n4 <= 32 * 6) launch_pdl(k_layernorm<T, 6>, dim3(blocks), dim3(256), 0, st, x, g, b, out16, out32, rows, d, 1e-5f);
+    else if (n4 <= 32 * 10) launch_pdl(k_layernorm<T, 10>, dim3(blocks), dim3(256), 0, st, x, g, b, out16, out32, rows, d, 1e-5f);
+    else launch_pdl(k_layernorm<T, 12>, dim3(blocks), dim3(256), 0, st, x, g, b, out16, out32, rows, d, 1e-5f);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;

@@ -170,19 +170,37 @@ struct Engine : EngineBase {
         return prof_end();
     }
 
-    int graph_nodes = 0;
+    // The decoder step is a chain of ~140 small, latency-bound launches plus one HBM-bound stream
+    // (cross-attention).  The batch is therefore cut into up to kMaxLanes independent sub-batches
+    // ("lanes"), each with its own CUDA stream, counters and captured step graph, so the chains of
+    // different lanes overlap and the cross-attention of one lane streams while the others wait on latency.
+    static constexpr int kMaxLanes = 4;
     struct GraphKey {
-        int W, n_max, flags, max_init, n_prompt, has_forced, gen;
+        int W, w0, Wl, n_max, flags, max_init, n_prompt, has_forced, gen;
         bool operator==(const GraphKey& o) const {
-            return W == o.W && n_max == o.n_max && flags == o.flags && max_init == o.max_init && n_prompt == o.n_prompt &&
-                   has_forced == o.has_forced && gen == o.gen;
+            return W == o.W && w0 == o.w0 && Wl == o.Wl && n_max == o.n_max && flags == o.flags && max_init == o.max_init &&
+                   n_prompt == o.n_prompt && has_forced == o.has_forced && gen == o.gen;
         }
     };
-    GraphKey gkey{0, 0, 0, 0, 0, 0, -1};
-    cudaGraphExec_t gexec = nullptr;
+    struct Lane {
+        cudaStream_t st = nullptr;
+        cudaEvent_t done = nullptr;
+        cudaGraphExec_t gexec = nullptr;
+        GraphKey key{0, 0, 0, 0, 0, 0, 0, 0, -1};
+        int graph_nodes = 0;
+    };
+    Lane lanes[kMaxLanes];
+    cudaEvent_t ev_fork = nullptr;
+    int n_lanes_cfg = 1;
+    bool fused_q = false;
 
     ~Engine() override {
-        if (gexec) cudaGraphExecDestroy(gexec);
+        for (auto& l : lanes) {
+            if (l.gexec) cudaGraphExecDestroy(l.gexec);
+            if (l.done) cudaEventDestroy(l.done);
+            if (l.st) cudaStreamDestroy(l.st);
+        }
+        if (ev_fork) cudaEventDestroy(ev_fork);
         for (auto& r : prof_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
         for (void* p : owned) cudaFree(p);
         DevBuf* bufs[] = {&b_pcm, &b_mel, &b_cmax, &b_floor, &b_clipmeta, &b_winmeta, &b_col1, &b_c1, &b_x, &b_h, &b_qkv,
@@ -293,7 +311,14 @@ struct Engine : EngineBase {
         SB_CHECK_ARG(hp.n_text_ctx <= 448, "n_text_ctx must be <= 448");
         SB_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         for (auto& e : ev) SB_CUDA_CHECK(cudaEventCreate(&e));
-        SB_CUDA_CHECK(cudaMallocHost(&h_ctr, 16 * sizeof(int)));
+        SB_CUDA_CHECK(cudaMallocHost(&h_ctr, 16 * kMaxLanes * sizeof(int)));
+        for (auto& l : lanes) {
+            SB_CUDA_CHECK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+            SB_CUDA_CHECK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        }
+        SB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        if (const char* e = getenv("SB_FUSED_Q")) fused_q = e[0] == '1';
+        if (const char* e = getenv("SB_DECODE_LANES")) { n_lanes_cfg = atoi(e); if (n_lanes_cfg < 1) n_lanes_cfg = 1; if (n_lanes_cfg > kMaxLanes) n_lanes_cfg = kMaxLanes; }
         int rc = sb_melplan_create(f.mel_filters.data(), hp.n_mels, &melplan);
         if (rc) return rc;
         rc = up_conv(f, "encoder.conv1", d, hp.n_mels, &conv1_w, &conv1_b); if (rc) return rc;
@@ -414,48 +439,60 @@ struct Engine : EngineBase {
         if ((rc = b_margins.ensure((size_t)W * n_max * 4))) return rc;
         if ((rc = b_forced.ensure((size_t)W * n_max * 4))) return rc;
         if ((rc = b_next.ensure(W * 4))) return rc;
-        if ((rc = b_ctr.ensure(64))) return rc;
+        if ((rc = b_ctr.ensure(64 * kMaxLanes))) return rc;
         if ((rc = b_prompt.ensure(64))) return rc;
         return SB_OK;
     }
 
-    // ---- one decoder step for W sequences (all launches on `st`) ------------------------------
-    int enqueue_step(int W, const SamplerArgs& sa) {
+    // ---- one decoder step for sequences [w0, w0 + Wl) of a W-sequence batch, all launches on `sl` ----
+    int enqueue_step(int W, int w0, int Wl, int* ctr, cudaStream_t sl, const SamplerArgs& sa) {
         const int d = hp.n_text_state, nctx = hp.n_audio_ctx;
         const int nkv = hp.n_text_layer * 2 * d;
-        int* pos_ptr = b_ctr.as<int>();
-        int* step_ptr = pos_ptr + 1;
+        int* pos_ptr = ctr;
+        int* step_ptr = ctr + 1;
+        float* dx = b_dx.as<float>() + (int64_t)w0 * d;
+        T* dh = b_dh.as<T>() + (int64_t)w0 * d;
+        T* dqkv = b_dqkv.as<T>() + (int64_t)w0 * 3 * d;
+        T* datt = b_datt.as<T>() + (int64_t)w0 * d;
+        T* dq = b_dq.as<T>() + (int64_t)w0 * d;
+        T* dmlp = b_dmlp.as<T>() + (int64_t)w0 * 4 * d;
+        float* logits = b_logits.as<float>() + (int64_t)w0 * hp.n_vocab;
         int rc;
-        if ((rc = dec_embed<T>(tok_emb, dec_pos, b_next.as<int>(), pos_ptr, b_dx.as<float>(), W, d, st))) return rc;
+        if ((rc = dec_embed<T>(tok_emb, dec_pos, b_next.as<int>() + w0, pos_ptr, dx, Wl, d, sl))) return rc;
         for (int l = 0; l < hp.n_text_layer; ++l) {
             const DecLayer<T>& L = dec[l];
-            T* kc = b_kself.as<T>() + (int64_t)l * W * hp.n_text_ctx * d;
-            T* vc = b_vself.as<T>() + (int64_t)l * W * hp.n_text_ctx * d;
+            T* kc = b_kself.as<T>() + ((int64_t)l * W + w0) * hp.n_text_ctx * d;
+            T* vc = b_vself.as<T>() + ((int64_t)l * W + w0) * hp.n_text_ctx * d;
             SkinnyEpilogue e{};
-            if ((rc = layernorm<T>(b_dx.as<float>(), L.ln1.g, L.ln1.b, b_dh.as<T>(), nullptr, W, d, st))) return rc;
-            e = SkinnyEpilogue{}; e.bias = L.qkv.b; e.out16 = b_dqkv.p; e.ldo16 = 3 * d;
-            if ((rc = skinny_gemm<T>(b_dh.as<T>(), d, L.qkv.w, d, W, 3 * d, d, e, st))) return rc;
-            if ((rc = dec_self_attn<T>(b_dqkv.as<T>(), kc, vc, b_datt.as<T>(), pos_ptr, W, hp.n_text_head, d, hp.n_text_ctx, st))) return rc;
-            e = SkinnyEpilogue{}; e.bias = L.o.b; e.residual = b_dx.as<float>(); e.ldr = d; e.out32 = b_dx.as<float>(); e.ldo32 = d;
-            if ((rc = skinny_gemm<T>(b_datt.as<T>(), d, L.o.w, d, W, d, d, e, st))) return rc;
-            if ((rc = layernorm<T>(b_dx.as<float>(), L.ln2.g, L.ln2.b, b_dh.as<T>(), nullptr, W, d, st))) return rc;
-            e = SkinnyEpilogue{}; e.bias = L.cq.b; e.out16 = b_dq.p; e.ldo16 = d;
-            if ((rc = skinny_gemm<T>(b_dh.as<T>(), d, L.cq.w, d, W, d, d, e, st))) return rc;
-            const T* kb = b_ckv.as<T>() + (int64_t)l * 2 * d;
-            if ((rc = dec_cross_attn<T>(b_dq.as<T>(), d, kb, kb + d, nkv, (int64_t)nctx * nkv, b_datt.as<T>(), W, hp.n_text_head, d, nctx, st))) return rc;
-            e = SkinnyEpilogue{}; e.bias = L.co.b; e.residual = b_dx.as<float>(); e.ldr = d; e.out32 = b_dx.as<float>(); e.ldo32 = d;
-            if ((rc = skinny_gemm<T>(b_datt.as<T>(), d, L.co.w, d, W, d, d, e, st))) return rc;
-            if ((rc = layernorm<T>(b_dx.as<float>(), L.ln3.g, L.ln3.b, b_dh.as<T>(), nullptr, W, d, st))) return rc;
-            e = SkinnyEpilogue{}; e.bias = L.fc1.b; e.act = 1; e.out16 = b_dmlp.p; e.ldo16 = 4 * d;
-            if ((rc = skinny_gemm<T>(b_dh.as<T>(), d, L.fc1.w, d, W, 4 * d, d, e, st))) return rc;
-            e = SkinnyEpilogue{}; e.bias = L.fc2.b; e.residual = b_dx.as<float>(); e.ldr = d; e.out32 = b_dx.as<float>(); e.ldo32 = d;
-            if ((rc = skinny_gemm<T>(b_dmlp.as<T>(), 4 * d, L.fc2.w, 4 * d, W, d, 4 * d, e, st))) return rc;
+            if ((rc = layernorm<T>(dx, L.ln1.g, L.ln1.b, dh, nullptr, Wl, d, sl))) return rc;
+            e = SkinnyEpilogue{}; e.bias = L.qkv.b; e.out16 = dqkv; e.ldo16 = 3 * d;
+            if ((rc = skinny_gemm<T>(dh, d, L.qkv.w, d, Wl, 3 * d, d, e, sl))) return rc;
+            if ((rc = dec_self_attn<T>(dqkv, kc, vc, datt, pos_ptr, Wl, hp.n_text_head, d, hp.n_text_ctx, sl))) return rc;
+            e = SkinnyEpilogue{}; e.bias = L.o.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
+            if ((rc = skinny_gemm<T>(datt, d, L.o.w, d, Wl, d, d, e, sl))) return rc;
+            // cross_attn_ln + query projection can be fused into the cross-attention kernel's prologue
+            FusedQ fq;
+            if (fused_q) { fq.x = dx; fq.ln_g = L.ln2.g; fq.ln_b = L.ln2.b; fq.wq = L.cq.w; fq.bq = L.cq.b; }
+            else {
+                if ((rc = layernorm<T>(dx, L.ln2.g, L.ln2.b, dh, nullptr, Wl, d, sl))) return rc;
+                e = SkinnyEpilogue{}; e.bias = L.cq.b; e.out16 = dq; e.ldo16 = d;
+                if ((rc = skinny_gemm<T>(dh, d, L.cq.w, d, Wl, d, d, e, sl))) return rc;
+            }
+            const T* kb = b_ckv.as<T>() + (int64_t)w0 * nctx * nkv + (int64_t)l * 2 * d;
+            if ((rc = dec_cross_attn<T>(dq, d, kb, kb + d, nkv, (int64_t)nctx * nkv, datt, Wl, hp.n_text_head, d, nctx, fq, sl))) return rc;
+            e = SkinnyEpilogue{}; e.bias = L.co.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
+            if ((rc = skinny_gemm<T>(datt, d, L.co.w, d, Wl, d, d, e, sl))) return rc;
+            if ((rc = layernorm<T>(dx, L.ln3.g, L.ln3.b, dh, nullptr, Wl, d, sl))) return rc;
+            e = SkinnyEpilogue{}; e.bias = L.fc1.b; e.act = 1; e.out16 = dmlp; e.ldo16 = 4 * d;
+            if ((rc = skinny_gemm<T>(dh, d, L.fc1.w, d, Wl, 4 * d, d, e, sl))) return rc;
+            e = SkinnyEpilogue{}; e.bias = L.fc2.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
+            if ((rc = skinny_gemm<T>(dmlp, 4 * d, L.fc2.w, 4 * d, Wl, d, 4 * d, e, sl))) return rc;
         }
-        if ((rc = layernorm<T>(b_dx.as<float>(), ln_f.g, ln_f.b, b_dh.as<T>(), nullptr, W, d, st))) return rc;
-        SkinnyEpilogue e{}; e.out32 = b_logits.as<float>(); e.ldo32 = hp.n_vocab;
-        if ((rc = skinny_gemm<T>(b_dh.as<T>(), d, tok_emb, d, W, hp.n_vocab, d, e, st))) return rc;
-        if ((rc = sample_step(b_logits.as<float>(), hp.n_vocab, sa, W, st))) return rc;
-        if ((rc = dec_advance(pos_ptr, step_ptr, sa.n_prompt, st))) return rc;
+        if ((rc = layernorm<T>(dx, ln_f.g, ln_f.b, dh, nullptr, Wl, d, sl))) return rc;
+        SkinnyEpilogue e{}; e.out32 = logits; e.ldo32 = hp.n_vocab;
+        if ((rc = skinny_gemm<T>(dh, d, tok_emb, d, Wl, hp.n_vocab, d, e, sl))) return rc;
+        if ((rc = sample_step(logits, hp.n_vocab, sa, Wl, sl))) return rc;
+        if ((rc = dec_advance(pos_ptr, step_ptr, sa.n_prompt, sl))) return rc;
         return SB_OK;
     }
 
@@ -481,66 +518,100 @@ struct Engine : EngineBase {
         }
         SB_CUDA_CHECK(cudaMemcpyAsync(b_state.p, hs.data(), W * sizeof(SeqState), cudaMemcpyHostToDevice, st));
         SB_CUDA_CHECK(cudaMemcpyAsync(b_prompt.p, prompt.data(), n_prompt * 4, cudaMemcpyHostToDevice, st));
-        SB_CUDA_CHECK(cudaMemsetAsync(b_ctr.p, 0, 64, st));
+        SB_CUDA_CHECK(cudaMemsetAsync(b_ctr.p, 0, 64 * kMaxLanes, st));
         SB_CUDA_CHECK(cudaMemsetAsync(b_tokens.p, 0xff, (size_t)W * n_max * 4, st));
         SB_CUDA_CHECK(cudaMemsetAsync(b_margins.p, 0, (size_t)W * n_max * 4, st));
         k_fill_i32<<<ceil_div(W, 256), 256, 0, st>>>(b_next.as<int>(), W, prompt[0]);
         g_launches += 1;
         if (forced_host) SB_CUDA_CHECK(cudaMemcpyAsync(b_forced.p, forced_host, (size_t)W * n_max * 4, cudaMemcpyHostToDevice, st));
-        SamplerArgs sa{};
-        sa.state = b_state.as<SeqState>();
-        sa.step_ptr = b_ctr.as<int>() + 1;
-        sa.tokens_out = b_tokens.as<int>();
-        sa.margins_out = b_margins.as<float>();
-        sa.next_tokens = b_next.as<int>();
-        sa.forced = forced_host ? b_forced.as<int>() : nullptr;
-        sa.n_done = b_ctr.as<int>() + 2;
-        sa.sp = sp; sa.n_vocab = hp.n_vocab; sa.n_max = n_max;
-        sa.suppress_blank = p.suppress_blank; sa.no_timestamps = p.no_timestamps; sa.single_segment = p.single_segment;
-        sa.max_initial_tid = p.max_initial_ts > 0.f ? (int)lroundf(p.max_initial_ts / (30.0f / hp.n_audio_ctx)) : -1;
-        sa.pos_ptr = b_ctr.as<int>(); sa.prompt = b_prompt.as<int>(); sa.n_prompt = n_prompt;
+        SamplerArgs sa0{};
+        sa0.forced = nullptr;
+        sa0.sp = sp; sa0.n_vocab = hp.n_vocab; sa0.n_max = n_max;
+        sa0.suppress_blank = p.suppress_blank; sa0.no_timestamps = p.no_timestamps; sa0.single_segment = p.single_segment;
+        sa0.max_initial_tid = p.max_initial_ts > 0.f ? (int)lroundf(p.max_initial_ts / (30.0f / hp.n_audio_ctx)) : -1;
+        sa0.prompt = b_prompt.as<int>(); sa0.n_prompt = n_prompt;
 
         const int total_steps = n_prompt - 1 + n_max;
         const bool graph = use_graph && !logits_out;
+        // lanes: independent sub-batches on their own streams (one lane when tracing logits)
+        int n_lanes = logits_out ? 1 : std::min(n_lanes_cfg, std::max(1, W / 8));
+        struct LaneRun { int w0, Wl; bool finished; int steps; };
+        std::vector<LaneRun> lr(n_lanes);
+        for (int i = 0; i < n_lanes; ++i) {
+            const int w0 = (int)((int64_t)W * i / n_lanes), w1 = (int)((int64_t)W * (i + 1) / n_lanes);
+            lr[i] = LaneRun{w0, w1 - w0, false, 0};
+        }
+        auto lane_args = [&](int i) {
+            SamplerArgs sa = sa0;
+            const int w0 = lr[i].w0;
+            int* ctr = b_ctr.as<int>() + 16 * i;
+            sa.state = b_state.as<SeqState>() + w0;
+            sa.step_ptr = ctr + 1;
+            sa.tokens_out = b_tokens.as<int>() + (size_t)w0 * n_max;
+            sa.margins_out = b_margins.as<float>() + (size_t)w0 * n_max;
+            sa.next_tokens = b_next.as<int>() + w0;
+            sa.forced = forced_host ? b_forced.as<int>() + (size_t)w0 * n_max : nullptr;
+            sa.n_done = ctr + 2;
+            sa.pos_ptr = ctr;
+            return sa;
+        };
+        // fork: every lane stream waits for the setup work queued on the main stream
+        SB_CUDA_CHECK(cudaEventRecord(ev_fork, st));
+        for (int i = 0; i < n_lanes; ++i) SB_CUDA_CHECK(cudaStreamWaitEvent(lanes[i].st, ev_fork, 0));
         if (graph) {
-            GraphKey k{W, n_max, (p.suppress_blank ? 1 : 0) | (p.no_timestamps ? 2 : 0) | (p.single_segment ? 4 : 0),
-                       sa.max_initial_tid, n_prompt, forced_host ? 1 : 0, g_ws_gen.load()};
-            if (!gexec || !(k == gkey)) {
-                if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+            for (int i = 0; i < n_lanes; ++i) {
+                Lane& L = lanes[i];
+                GraphKey k{W, lr[i].w0, lr[i].Wl, n_max,
+                           (p.suppress_blank ? 1 : 0) | (p.no_timestamps ? 2 : 0) | (p.single_segment ? 4 : 0),
+                           sa0.max_initial_tid, n_prompt, forced_host ? 1 : 0, g_ws_gen.load()};
+                if (L.gexec && k == L.key) continue;
+                if (L.gexec) { cudaGraphExecDestroy(L.gexec); L.gexec = nullptr; }
                 cudaGraph_t g = nullptr;
                 const uint64_t l0 = g_launches.load();
-                SB_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                rc = enqueue_step(W, sa);
-                cudaError_t ce = cudaStreamEndCapture(st, &g);
-                graph_nodes = (int)(g_launches.load() - l0);
-                g_launches -= (uint64_t)graph_nodes;      // captured, not executed
+                SB_CUDA_CHECK(cudaStreamBeginCapture(L.st, cudaStreamCaptureModeThreadLocal));
+                rc = enqueue_step(W, lr[i].w0, lr[i].Wl, b_ctr.as<int>() + 16 * i, L.st, lane_args(i));
+                cudaError_t ce = cudaStreamEndCapture(L.st, &g);
+                L.graph_nodes = (int)(g_launches.load() - l0);
+                g_launches -= (uint64_t)L.graph_nodes;      // captured, not executed
                 if (rc) { if (g) cudaGraphDestroy(g); return rc; }
                 if (ce != cudaSuccess) { set_error(std::string("graph capture: ") + cudaGetErrorString(ce)); return SB_ERR_CUDA; }
-                ce = cudaGraphInstantiate(&gexec, g, 0);
+                ce = cudaGraphInstantiate(&L.gexec, g, 0);
                 cudaGraphDestroy(g);
-                if (ce != cudaSuccess) { gexec = nullptr; set_error(std::string("graph instantiate: ") + cudaGetErrorString(ce)); return SB_ERR_CUDA; }
-                gkey = k;
+                if (ce != cudaSuccess) { L.gexec = nullptr; set_error(std::string("graph instantiate: ") + cudaGetErrorString(ce)); return SB_ERR_CUDA; }
+                L.key = k;
             }
         }
-        int done_steps = 0;
-        while (done_steps < total_steps) {
-            const int burst = logits_out ? 1 : std::min(8, total_steps - done_steps);
-            for (int i = 0; i < burst; ++i) {
-                if (graph) { SB_CUDA_CHECK(cudaGraphLaunch(gexec, st)); g_launches += (uint64_t)graph_nodes; }
-                else if ((rc = enqueue_step(W, sa))) return rc;
+        int active = n_lanes;
+        while (active > 0) {
+            for (int i = 0; i < n_lanes; ++i) {
+                if (lr[i].finished) continue;
+                Lane& L = lanes[i];
+                const int burst = logits_out ? 1 : std::min(8, total_steps - lr[i].steps);
+                for (int b = 0; b < burst; ++b) {
+                    if (graph) { SB_CUDA_CHECK(cudaGraphLaunch(L.gexec, L.st)); g_launches += (uint64_t)L.graph_nodes; }
+                    else if ((rc = enqueue_step(W, lr[i].w0, lr[i].Wl, b_ctr.as<int>() + 16 * i, L.st, lane_args(i)))) return rc;
+                }
+                if (logits_out && lr[i].steps >= n_prompt - 1) {
+                    const int sidx = lr[i].steps - (n_prompt - 1);
+                    for (int w = 0; w < W; ++w)
+                        SB_CUDA_CHECK(cudaMemcpyAsync(logits_out + ((size_t)w * n_max + sidx) * hp.n_vocab,
+                                                      b_logits.as<float>() + (size_t)w * hp.n_vocab, (size_t)hp.n_vocab * 4,
+                                                      cudaMemcpyDeviceToHost, L.st));
+                }
+                lr[i].steps += burst;
+                stats.decoder_steps += (double)burst * lr[i].Wl / W; stats.d2h_bytes += 16;
+                SB_CUDA_CHECK(cudaMemcpyAsync(h_ctr + 16 * i, b_ctr.as<int>() + 16 * i, 16, cudaMemcpyDeviceToHost, L.st));
             }
-            if (logits_out && done_steps >= n_prompt - 1) {
-                const int s = done_steps - (n_prompt - 1);
-                for (int w = 0; w < W; ++w)
-                    SB_CUDA_CHECK(cudaMemcpyAsync(logits_out + ((size_t)w * n_max + s) * hp.n_vocab,
-                                                  b_logits.as<float>() + (size_t)w * hp.n_vocab, (size_t)hp.n_vocab * 4,
-                                                  cudaMemcpyDeviceToHost, st));
+            for (int i = 0; i < n_lanes; ++i) {
+                if (lr[i].finished) continue;
+                SB_CUDA_CHECK(cudaStreamSynchronize(lanes[i].st));
+                if (h_ctr[16 * i + 2] >= lr[i].Wl || lr[i].steps >= total_steps) { lr[i].finished = true; --active; }
             }
-            done_steps += burst;
-            stats.decoder_steps += burst; stats.d2h_bytes += 16;
-            SB_CUDA_CHECK(cudaMemcpyAsync(h_ctr, b_ctr.p, 16, cudaMemcpyDeviceToHost, st));
-            SB_CUDA_CHECK(cudaStreamSynchronize(st));
-            if (h_ctr[2] >= W) break;
+        }
+        // join: the main stream continues after every lane
+        for (int i = 0; i < n_lanes; ++i) {
+            SB_CUDA_CHECK(cudaEventRecord(lanes[i].done, lanes[i].st));
+            SB_CUDA_CHECK(cudaStreamWaitEvent(st, lanes[i].done, 0));
         }
         out.state.resize(W); out.tokens.resize((size_t)W * n_max); out.margins.resize((size_t)W * n_max);
         SB_CUDA_CHECK(cudaMemcpyAsync(out.state.data(), b_state.p, W * sizeof(SeqState), cudaMemcpyDeviceToHost, st));
