@@ -341,7 +341,9 @@ struct Engine : EngineBase {
         if ((rc = up_ln(f, "encoder.ln_post", d, ln_post))) return rc;
         {
             SB_FIND(t, f, "decoder.token_embedding.weight", hp.n_vocab, dt);
-            std::vector<uint16_t> w; append16(*t, w); rc = up16(w, &tok_emb); if (rc) return rc;
+            std::vector<uint16_t> w; append16(*t, w);
+            w.resize((size_t)round_up(hp.n_vocab, 8) * dt, 0);      // zero rows: the logits GEMM runs on N rounded up to 8
+            rc = up16(w, &tok_emb); if (rc) return rc;
             SB_FIND(pe, f, "decoder.positional_embedding", hp.n_text_ctx, dt);
             std::vector<float> v; to_f32(*pe, v); rc = up32(v, &dec_pos); if (rc) return rc;
         }
@@ -433,7 +435,7 @@ struct Engine : EngineBase {
         if ((rc = b_datt.ensure(W * d * 2))) return rc;
         if ((rc = b_dq.ensure(W * d * 2))) return rc;
         if ((rc = b_dmlp.ensure(W * 4 * d * 2))) return rc;
-        if ((rc = b_logits.ensure((size_t)W * hp.n_vocab * 4))) return rc;
+        if ((rc = b_logits.ensure((size_t)W * round_up(hp.n_vocab, 8) * 4))) return rc;
         if ((rc = b_state.ensure(W * sizeof(SeqState)))) return rc;
         if ((rc = b_tokens.ensure((size_t)W * n_max * 4))) return rc;
         if ((rc = b_margins.ensure((size_t)W * n_max * 4))) return rc;
@@ -456,7 +458,8 @@ struct Engine : EngineBase {
         T* datt = b_datt.as<T>() + (int64_t)w0 * d;
         T* dq = b_dq.as<T>() + (int64_t)w0 * d;
         T* dmlp = b_dmlp.as<T>() + (int64_t)w0 * 4 * d;
-        float* logits = b_logits.as<float>() + (int64_t)w0 * hp.n_vocab;
+        const int vpad = (int)round_up(hp.n_vocab, 8);
+        float* logits = b_logits.as<float>() + (int64_t)w0 * vpad;
         int rc;
         if ((rc = dec_embed<T>(tok_emb, dec_pos, b_next.as<int>() + w0, pos_ptr, dx, Wl, d, sl))) return rc;
         for (int l = 0; l < hp.n_text_layer; ++l) {
@@ -489,9 +492,11 @@ struct Engine : EngineBase {
             if ((rc = skinny_gemm<T>(dmlp, 4 * d, L.fc2.w, 4 * d, Wl, d, 4 * d, e, sl))) return rc;
         }
         if ((rc = layernorm<T>(dx, ln_f.g, ln_f.b, dh, nullptr, Wl, d, sl))) return rc;
-        SkinnyEpilogue e{}; e.out32 = logits; e.ldo32 = hp.n_vocab;
-        if ((rc = skinny_gemm<T>(dh, d, tok_emb, d, Wl, hp.n_vocab, d, e, sl))) return rc;
-        if ((rc = sample_step(logits, hp.n_vocab, sa, Wl, sl))) return rc;
+        // tied-embedding logits: 80-130 MB of weights per step -> the TMA-fed tcgen05 GEMM streams them
+        // (one 128-row tile of sequences, ~200 column tiles) instead of the small-N weight-streaming kernel
+        GemmEpilogue ge{logits, vpad, 1, nullptr, 0, nullptr, 0, 0};
+        if ((rc = gemm_tn(dtype, dh, d, tok_emb, d, Wl, vpad, d, ge, sl))) return rc;
+        if ((rc = sample_step(logits, vpad, sa, Wl, sl))) return rc;
         if ((rc = dec_advance(pos_ptr, step_ptr, sa.n_prompt, sl))) return rc;
         return SB_OK;
     }
@@ -595,7 +600,7 @@ struct Engine : EngineBase {
                     const int sidx = lr[i].steps - (n_prompt - 1);
                     for (int w = 0; w < W; ++w)
                         SB_CUDA_CHECK(cudaMemcpyAsync(logits_out + ((size_t)w * n_max + sidx) * hp.n_vocab,
-                                                      b_logits.as<float>() + (size_t)w * hp.n_vocab, (size_t)hp.n_vocab * 4,
+                                                      b_logits.as<float>() + (size_t)w * round_up(hp.n_vocab, 8), (size_t)hp.n_vocab * 4,
                                                       cudaMemcpyDeviceToHost, L.st));
                 }
                 lr[i].steps += burst;
