@@ -33,9 +33,12 @@ constexpr int kTileSamples = (kFpb - 1) * kHop + kNFft;  // 5360
 constexpr int kZStride = 21;             // float2 row stride of the 20x20 scratch (bank-conflict-free)
 constexpr int kZPerFft = 20 * kZStride;  // 420 float2
 constexpr int kPStride = 201;            // odd -> conflict-free when lanes index frames
+constexpr int kMaxMel = 128;
+constexpr int kMaxBandW = 640;           // slaney triangles touch <= 2 rows per bin: 402 + slack
 
 struct MelPlanDev {
     int n_mel;
+    int n_w;                 // packed weights in w
     const int* band_start;   // [n_mel] first non-zero bin
     const int* band_len;     // [n_mel]
     const int* band_off;     // [n_mel] offset into w
@@ -130,6 +133,8 @@ struct __align__(16) LogmelSmem {
     float2 z[kFftPerCta * kZPerFft];
     float p[kFpb * kPStride];
     float red[16];
+    float bw[kMaxBandW];          // packed band weights (staged once per CTA)
+    int bstart[kMaxMel], blen[kMaxMel], boff[kMaxMel];
 };
 
 __global__ void __launch_bounds__(kThreads, 2)
@@ -144,20 +149,36 @@ k_logmel(LogmelArgs a, MelPlanDev plan) {
     const int n = a.n_samples;
 
     // ---- stage samples (padded coordinates p = frame*160 + j ; original index = p - 200) ----
+    // p0 - 200 is a multiple of 8, so the interior of the tile is read with aligned 128-bit loads
     const int p0 = frame0 * kHop;
-    for (int i = tid; i < kTileSamples; i += kThreads) {
-        int p = p0 + i;
-        int src = p - 200;
-        float v = 0.0f;
-        if (src < 0) src = -src;           // reflect: padded[p] = samples[200 - p]
-        if (src < n) v = __ldg(pcm + src);
-        s.x[i] = v;
+    const int src0 = p0 - 200;
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;   // clip bases need not be 16 B aligned
+    for (int i4 = tid; i4 < kTileSamples / 4; i4 += kThreads) {
+        const int src = src0 + 4 * i4;
+        float4 v;
+        if (base_aligned && src >= 0 && src + 3 < n) {
+            v = __ldg(reinterpret_cast<const float4*>(pcm + src));
+        } else {
+            float t[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int sidx = src + e;
+                if (sidx < 0) sidx = -sidx;          // reflect: padded[p] = samples[200 - p]
+                t[e] = sidx < n ? __ldg(pcm + sidx) : 0.0f;
+            }
+            v = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        *reinterpret_cast<float4*>(s.x + 4 * i4) = v;
     }
     for (int i = tid; i < kNFft; i += kThreads) {
         float sn, cs;
         sincospif(2.0f * (float)i / (float)kNFft, &sn, &cs);
         s.hann[i] = 0.5f * (1.0f - cs);
         s.tw[i] = make_float2(cs, sn);      // W400^i = cs - i sn
+    }
+    for (int i = tid; i < plan.n_w; i += kThreads) s.bw[i] = __ldg(plan.w + i);
+    for (int i = tid; i < plan.n_mel; i += kThreads) {
+        s.bstart[i] = __ldg(plan.band_start + i); s.blen[i] = __ldg(plan.band_len + i); s.boff[i] = __ldg(plan.band_off + i);
     }
     __syncthreads();
 
@@ -223,11 +244,12 @@ k_logmel(LogmelArgs a, MelPlanDev plan) {
     const float* prow = s.p + lane * kPStride;
     float vmax = -10.0f;
     for (int j = warp; j < plan.n_mel; j += kThreads / 32) {
-        const int b0 = __ldg(plan.band_start + j);
-        const int bl = __ldg(plan.band_len + j);
-        const float* w = plan.w + __ldg(plan.band_off + j);
+        const int b0 = s.bstart[j];
+        const int bl = s.blen[j];
+        const float* w = s.bw + s.boff[j];
         float acc = 0.0f;
-        for (int k = 0; k < bl; ++k) acc = fmaf(prow[b0 + k], __ldg(w + k), acc);
+#pragma unroll 4
+        for (int k = 0; k < bl; ++k) acc = fmaf(prow[b0 + k], w[k], acc);
         float v = log10f(fmaxf(acc, 1e-10f));
         if (valid) {
             out[(int64_t)j * a.mel_stride + frame] = v;
@@ -283,6 +305,7 @@ struct sb_melplan {
     int* d_len = nullptr;
     int* d_off = nullptr;
     float* d_w = nullptr;
+    int n_w = 0;
     bool consts_ready = false;
 };
 
@@ -318,7 +341,7 @@ int logmel_launch(const sb_melplan* plan, const float* pcm, int n_clips, size_t 
     a.pcm = pcm; a.mel = mel; a.clip_max = clip_max;
     a.pcm_clip_stride = pcm_clip_stride; a.n_samples = (int)n_samples; a.n_calc = n_calc;
     a.mel_clip_stride = mel_clip_stride; a.mel_stride = mel_stride;
-    MelPlanDev pd{plan->n_mel, plan->d_start, plan->d_len, plan->d_off, plan->d_w};
+    MelPlanDev pd{plan->n_mel, plan->n_w, plan->d_start, plan->d_len, plan->d_off, plan->d_w};
     k_logmel_init<<<ceil_div(n_clips, 256), 256, 0, st>>>(clip_max, n_clips);
     dim3 grid(ceil_div(n_calc, kFpb), n_clips);
     k_logmel<<<grid, kThreads, sizeof(LogmelSmem), st>>>(a, pd);
@@ -345,7 +368,7 @@ int sb_logmel_geometry(size_t n_samples, int* n_len, int* n_len_org, int* n_calc
 }
 
 int sb_melplan_create(const float* filters, int n_mel, sb_melplan** out) {
-    SB_CHECK_ARG(filters && out && n_mel > 0 && n_mel <= 512, "filters/out null or n_mel out of range");
+    SB_CHECK_ARG(filters && out && n_mel > 0 && n_mel <= 128, "filters/out null or n_mel out of range");
     std::vector<int> start(n_mel), len(n_mel), off(n_mel);
     std::vector<float> w;
     for (int j = 0; j < n_mel; ++j) {
@@ -357,8 +380,11 @@ int sb_melplan_create(const float* filters, int n_mel, sb_melplan** out) {
         for (int k = lo; k <= hi; ++k) w.push_back(filters[j * sb::kBins + k]);
     }
     if (w.empty()) w.push_back(0.0f);
+    SB_CHECK_ARG(n_mel <= sb::kMaxMel && (int)w.size() <= sb::kMaxBandW,
+                 "mel filterbank too dense for the shared-memory band table (n_mel <= 128, <= 640 non-zero taps)");
     sb_melplan* p = new sb_melplan();
     p->n_mel = n_mel;
+    p->n_w = (int)w.size();
     SB_CUDA_CHECK(cudaMalloc(&p->d_start, n_mel * sizeof(int)));
     SB_CUDA_CHECK(cudaMalloc(&p->d_len, n_mel * sizeof(int)));
     SB_CUDA_CHECK(cudaMalloc(&p->d_off, n_mel * sizeof(int)));
