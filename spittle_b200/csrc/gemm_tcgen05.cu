@@ -201,15 +201,37 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
         int as = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int n_blk = tile % num_n, m_blk = tile / num_n;
+            const int row_base = m_blk * kBM + q * 32;
+            // residual rows of this warp's 4 chunks are independent of the MMA: they are fetched one chunk
+            // ahead (the first one before waiting for the accumulator) so their HBM latency is not exposed
+            const int col_l = c4 * 4;
+            const bool has_res = ep.residual != nullptr;
+            float4 rnext[8];
+            auto load_res = [&](int cc, float4 (&dst)[8]) {
+                const int col = n_blk * kBN + (half * 4 + cc) * 32 + col_l;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int row = row_base + it * 4 + rsub;
+                    dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_res && row < M && col < N) {
+                        const int rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : row;
+                        dst[it] = *reinterpret_cast<const float4*>(ep.residual + (int64_t)rrow * ep.ldr + col);
+                    }
+                }
+            };
+            if (has_res) load_res(0, rnext);
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
-            const int row_base = m_blk * kBM + q * 32;
-#pragma unroll 1
+#pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
                 const int c = half * 4 + cc;
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kBN + c * 32);
                 tc_ld32(taddr, v);
+                float4 rcur[8];
+#pragma unroll
+                for (int it = 0; it < 8; ++it) rcur[it] = rnext[it];
+                if (has_res && cc + 1 < 4) load_res(cc + 1, rnext);
                 tc_wait_ld();
                 const int col0 = n_blk * kBN + c * 32;
                 if (col0 >= N || row_base >= M) continue;       // warp-uniform
@@ -219,28 +241,35 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                     stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                 __syncwarp();
-                const int col = col0 + c4 * 4;
+                const int col = col0 + col_l;
                 const bool col_ok = col < N;                     // N % 8 == 0: a 4-column group is all in or all out
                 float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ep.bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+                float4 f[8];
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
                     const int rr = it * 4 + rsub;
-                    const int row = row_base + rr;
-                    float4 f = stg[rr * 8 + (c4 ^ (rr & 7))];
+                    f[it] = stg[rr * 8 + (c4 ^ (rr & 7))];
+                    f[it].x += bias4.x; f[it].y += bias4.y; f[it].z += bias4.z; f[it].w += bias4.w;
+                }
+                if (ep.act == 1) {      // 32 independent GELUs: straight-line so the MUFU latencies overlap
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        f[it].x = gelu_tanh(f[it].x); f[it].y = gelu_tanh(f[it].y);
+                        f[it].z = gelu_tanh(f[it].z); f[it].w = gelu_tanh(f[it].w);
+                    }
+                }
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int row = row_base + it * 4 + rsub;
                     if (row < M && col_ok) {
-                        f.x += bias4.x; f.y += bias4.y; f.z += bias4.z; f.w += bias4.w;
-                        if (ep.act == 1) { f.x = gelu_tanh(f.x); f.y = gelu_tanh(f.y); f.z = gelu_tanh(f.z); f.w = gelu_tanh(f.w); }
-                        if (ep.residual) {
-                            const int rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : row;
-                            const float4 r4 = *reinterpret_cast<const float4*>(ep.residual + (int64_t)rrow * ep.ldr + col);
-                            f.x += r4.x; f.y += r4.y; f.z += r4.z; f.w += r4.w;
-                        }
+                        float4 o = f[it];
+                        if (has_res) { o.x += rcur[it].x; o.y += rcur[it].y; o.z += rcur[it].z; o.w += rcur[it].w; }
                         if (ep.out_f32) {
-                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldo + col) = f;
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldo + col) = o;
                         } else {
                             uint2 u;
-                            u.x = Op16<T>::pack2(f.x, f.y); u.y = Op16<T>::pack2(f.z, f.w);
+                            u.x = Op16<T>::pack2(o.x, o.y); u.y = Op16<T>::pack2(o.z, o.w);
                             *reinterpret_cast<uint2*>(reinterpret_cast<T*>(ep.out) + (int64_t)row * ep.ldo + col) = u;
                         }
                     }
