@@ -1,0 +1,362 @@
+// k_attn_enc_tc: encoder self-attention (non-causal, d_head 64, T = 1500) on tcgen05 / TMEM.
+//
+// Replaces the KQ / softmax / KQV part of the whisper.cpp encoder graph.
+// One CTA = one (window, head, 128-query tile).  S = Q K^T and O = P V are tcgen05.mma with the
+// accumulators in TMEM; the softmax runs on 128 threads, one per query row (a TMEM lane), so row
+// maxima and sums need no shuffles.
+//
+// Two passes over the 12 key tiles of 128 keys:
+//   pass 1  S_j = Q K_j^T (UMMA 128x128x16 x4)  ->  running row maximum only
+//   pass 2  S_j again, p = exp2((s - m) * scale) with the FINAL maximum, P_j (16-bit) written to shared
+//           memory in the 128B-swizzled K-major layout, O += P_j V_j (UMMA 128x64x16 x8, V is the
+//           MN-major B operand straight from its [key][64] rows)
+// Knowing the final maximum up front removes the accumulator rescaling of the one-pass online softmax
+// (TMEM round trips + an extra dependency between softmax and MMA); it costs the QK^T MMAs twice, which
+// is free here: the kernel is bound by the exp2 (MUFU) rate, not by the tensor pipe.
+// Rounding points of the reference are kept: Q, K, V are 16-bit, S is f32, probabilities are rounded to
+// 16 bits before P V, accumulation in f32; the normaliser is the f32 sum of the un-rounded probabilities.
+//
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 softmax + epilogue
+// (two warps per TMEM lane quarter, each owning 64 of the 128 key columns of a tile, so every SM
+// sub-partition has two warps to overlap the MUFU exp2 latency with the FMA/convert work).
+// TMEM: S double buffer 2 x 128 columns, O 64 columns (512 allocated).
+#include "common.cuh"
+#include "decoder.cuh"
+#include <cuda.h>
+
+namespace sb {
+extern std::atomic<uint64_t> g_launches;
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int is_f16, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
+constexpr int kAtBM = 128;            // queries per CTA
+constexpr int kAtBN = 128;            // keys per tile
+constexpr int kAtD = 64;
+constexpr int kAtKvStages = 4;        // 16 KB each (K or V tile)
+constexpr int kAtTileBytes = 128 * 64 * 2;
+constexpr int kAtPBytes = 128 * 128 * 2;       // one P tile = two 64-key swizzle atoms of 16 KB
+constexpr int kAtSmem = 1024 + kAtTileBytes /*Q*/ + kAtKvStages * kAtTileBytes + 2 * kAtPBytes + 256 + 2 * 128 * 4 /*row max / sum exchange*/;
+constexpr int kAtThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two per TMEM lane quarter)
+
+__device__ __forceinline__ uint32_t at_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void at_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void at_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void at_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void at_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "AT_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra AT_WAIT_DONE;\n"
+        "bra AT_WAIT_LOOP;\n"
+        "AT_WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void at_tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void at_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void at_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void at_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void at_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void at_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void at_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major SWIZZLE_128B operand (rows of 128 B, 8-row groups 1024 B apart); also valid for the MN-major
+// V tile whose 64-element rows are exactly one swizzle atom wide (K direction = consecutive 128 B rows).
+__device__ __forceinline__ uint64_t at_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                    // LBO (unused: the MN / K extent per instruction fits one atom)
+    d |= (uint64_t)(1024 >> 4) << 32;          // SBO: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                    // Blackwell descriptor version
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kAtThreads, 1)
+k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_qkv, T* __restrict__ out, int n_ctx, int d_model, float scale_log2e) {
+    extern __shared__ unsigned char at_smem_raw[];
+    const uint32_t raw = at_smem_u32(at_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* base_ptr = at_smem_raw + (base - raw);
+    const uint32_t sQ = base;
+    const uint32_t sKV = base + kAtTileBytes;
+    const uint32_t sP = sKV + kAtKvStages * kAtTileBytes;
+    const uint32_t bar0 = sP + 2 * kAtPBytes;
+    unsigned char* p_ptr = base_ptr + kAtTileBytes + kAtKvStages * kAtTileBytes;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + kAtTileBytes + kAtKvStages * kAtTileBytes + 2 * kAtPBytes + 192);
+    // barriers (8 B each)
+    const uint32_t q_full = bar0;
+    auto kv_full = [&](int s) { return bar0 + 8u * (1 + s); };
+    auto kv_empty = [&](int s) { return bar0 + 8u * (1 + kAtKvStages + s); };
+    auto s_full = [&](int b) { return bar0 + 8u * (1 + 2 * kAtKvStages + b); };
+    auto s_empty = [&](int b) { return bar0 + 8u * (3 + 2 * kAtKvStages + b); };
+    auto p_full = [&](int b) { return bar0 + 8u * (5 + 2 * kAtKvStages + b); };
+    auto p_empty = [&](int b) { return bar0 + 8u * (7 + 2 * kAtKvStages + b); };
+    const uint32_t o_full = bar0 + 8u * (9 + 2 * kAtKvStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, head = blockIdx.y, win = blockIdx.z;
+    const int n_kt = (n_ctx + kAtBN - 1) / kAtBN;
+    const int row_q0 = win * n_ctx + qt * kAtBM;         // first query row in the flattened [W*n_ctx] matrix
+    const int col_q = head * kAtD, col_k = d_model + head * kAtD, col_v = 2 * d_model + head * kAtD;
+
+    if (threadIdx.x == 0) {
+        at_mbar_init(q_full, 1);
+        for (int s = 0; s < kAtKvStages; ++s) { at_mbar_init(kv_full(s), 1); at_mbar_init(kv_empty(s), 1); }
+        for (int b = 0; b < 2; ++b) {
+            at_mbar_init(s_full(b), 1); at_mbar_init(s_empty(b), 8);
+            at_mbar_init(p_full(b), 8); at_mbar_init(p_empty(b), 1);
+        }
+        at_mbar_init(o_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_qkv) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(at_smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    at_fence_before();
+    __syncthreads();
+    at_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS0 = tmem, tO = tmem + 256;            // S buffers at columns [0,128) and [128,256); O at [256,320)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            at_mbar_expect_tx(q_full, kAtTileBytes);
+            at_tma_2d(sQ, &tm_qkv, col_q, row_q0, q_full);
+            int stage = 0; uint32_t phase = 0;
+            // pass 1: K tiles only; pass 2: K then V per tile
+            for (int pass = 0; pass < 2; ++pass)
+                for (int j = 0; j < n_kt; ++j)
+                    for (int which = 0; which <= pass; ++which) {
+                        at_mbar_wait(kv_empty(stage), phase ^ 1);
+                        at_mbar_expect_tx(kv_full(stage), kAtTileBytes);
+                        at_tma_2d(sKV + stage * kAtTileBytes, &tm_qkv, which == 0 ? col_k : col_v, win * n_ctx + j * kAtBN,
+                                  kv_full(stage));
+                        if (++stage == kAtKvStages) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t fmt = (uint32_t)Op16<T>::kUmmaFormat;
+            // S: D f32, A/B K-major, M 128, N 128.   PV: M 128, N 64, B (= V) MN-major
+            const uint32_t idesc_s = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kAtBN >> 3) << 17) | ((uint32_t)(kAtBM >> 4) << 24);
+            const uint32_t idesc_o = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) | ((uint32_t)(kAtD >> 3) << 17) | ((uint32_t)(kAtBM >> 4) << 24);
+            const uint64_t qdesc = at_desc(sQ);
+            int stage = 0; uint32_t phase = 0;
+            int sb = 0; uint32_t sphase = 0;      // S buffer ring (shared by both passes)
+            at_mbar_wait(q_full, 0);
+            at_fence_after();
+            auto issue_s = [&]() {
+                at_mbar_wait(s_empty(sb), sphase ^ 1);
+                at_mbar_wait(kv_full(stage), phase);
+                at_fence_after();
+                const uint64_t kdesc = at_desc(sKV + stage * kAtTileBytes);
+#pragma unroll
+                for (int k = 0; k < kAtD / 16; ++k) at_mma(tS0 + sb * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+                at_commit(kv_empty(stage));
+                at_commit(s_full(sb));
+                if (++stage == kAtKvStages) { stage = 0; phase ^= 1; }
+                if (++sb == 2) { sb = 0; sphase ^= 1; }
+            };
+            // pass 1
+            for (int j = 0; j < n_kt; ++j) issue_s();
+            // pass 2: S_0, then for each tile: S_{j+1} before PV_j so the tensor pipe always has work queued
+            int pb = 0; uint32_t pphase = 0;
+            issue_s();
+            for (int j = 0; j < n_kt; ++j) {
+                // V_j sits in the stage after K_j; K_{j+1} (if any) after that
+                const int v_stage = stage; const uint32_t v_phase = phase;
+                if (++stage == kAtKvStages) { stage = 0; phase ^= 1; }
+                if (j + 1 < n_kt) issue_s();
+                at_mbar_wait(p_full(pb), pphase);
+                at_mbar_wait(kv_full(v_stage), v_phase);
+                at_fence_after();
+                const uint64_t vdesc = at_desc(sKV + v_stage * kAtTileBytes);
+#pragma unroll
+                for (int k = 0; k < kAtBN / 16; ++k) {
+                    // P: two 64-key atoms of 16 KB, 32 B per k16 step inside an atom; V: 16 keys = 16 rows x 128 B
+                    const uint64_t pdesc = at_desc(sP + pb * kAtPBytes + (k >> 2) * 16384) + 2 * (k & 3);
+                    at_mma(tO, pdesc, vdesc + (uint64_t)(k * 2048 >> 4), idesc_o, (j | k) != 0);
+                }
+                at_commit(kv_empty(v_stage));
+                at_commit(p_empty(pb));
+                if (++pb == 2) { pb = 0; pphase ^= 1; }
+            }
+            at_commit(o_full);
+        }
+    } else {
+        // softmax warps: thread <-> (query row = TMEM lane, half of the key columns)
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        float* xch = reinterpret_cast<float*>(base_ptr + kAtTileBytes + kAtKvStages * kAtTileBytes + 2 * kAtPBytes + 256);
+        int sb = 0; uint32_t sphase = 0;
+        float m = -INFINITY;
+        // ---- pass 1: row maxima over this warp's 64 columns of every tile ----
+        for (int j = 0; j < n_kt; ++j) {
+            at_mbar_wait(s_full(sb), sphase);
+            at_fence_after();
+            uint32_t v0[32], v1[32];
+            at_ld32(tS0 + lane_addr + sb * 128 + half * 64, v0);
+            at_ld32(tS0 + lane_addr + sb * 128 + half * 64 + 32, v1);
+            at_wait_ld();
+            at_fence_before();
+            __syncwarp();
+            if (lane == 0) at_mbar_arrive(s_empty(sb));      // values are in registers: release the buffer early
+            const int k0 = j * kAtBN + half * 64;
+            if (k0 + 64 <= n_ctx) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (k0 + i < n_ctx) m = fmaxf(m, __uint_as_float(v0[i]));
+                    if (k0 + 32 + i < n_ctx) m = fmaxf(m, __uint_as_float(v1[i]));
+                }
+            }
+            if (++sb == 2) { sb = 0; sphase ^= 1; }
+        }
+        xch[half * 128 + row] = m;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        m = fmaxf(xch[row], xch[128 + row]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // ---- pass 2: probabilities with the final maximum ----
+        const float ms = m * scale_log2e;
+        float l = 0.f;
+        int pb = 0; uint32_t pphase = 0;
+        for (int j = 0; j < n_kt; ++j) {
+            at_mbar_wait(s_full(sb), sphase);
+            at_fence_after();
+            uint32_t v0[32], v1[32];
+            at_ld32(tS0 + lane_addr + sb * 128 + half * 64, v0);
+            at_ld32(tS0 + lane_addr + sb * 128 + half * 64 + 32, v1);
+            at_wait_ld();
+            at_fence_before();
+            __syncwarp();
+            if (lane == 0) at_mbar_arrive(s_empty(sb));
+            at_mbar_wait(p_empty(pb), pphase ^ 1);
+            // this warp's 64 keys are exactly swizzle atom `half` of the P tile
+            unsigned char* prow = p_ptr + pb * kAtPBytes + half * 16384 + row * 128;
+            const int k0 = j * kAtBN + half * 64;
+            const bool tail = k0 + 64 > n_ctx;
+            auto do_chunk = [&](const uint32_t (&v)[32], int cbase, int kk) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), scale_log2e, -ms));
+                    float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -ms));
+                    if (tail) {
+                        if (kk + 2 * i >= n_ctx) p0 = 0.f;
+                        if (kk + 2 * i + 1 >= n_ctx) p1 = 0.f;
+                    }
+                    l += p0 + p1;
+                    pk[i] = Op16<T>::pack2(p0, p1);
+                }
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    *reinterpret_cast<uint4*>(prow + (((cbase + ch) ^ (row & 7)) << 4)) =
+                        make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+            };
+            do_chunk(v0, 0, k0);
+            do_chunk(v1, 4, k0 + 32);
+            // P half-tile written through the generic proxy -> make it visible to the tensor core (async proxy)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) at_mbar_arrive(p_full(pb));
+            if (++sb == 2) { sb = 0; sphase ^= 1; }
+            if (++pb == 2) { pb = 0; pphase ^= 1; }
+        }
+        xch[half * 128 + row] = l;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        l = xch[row] + xch[128 + row];
+        // ---- epilogue: O / l, each warp stores 32 of the 64 head dims ----
+        at_mbar_wait(o_full, 0);
+        at_fence_after();
+        const float inv = 1.0f / l;
+        const int t = qt * kAtBM + row;
+        T* orow = out + ((int64_t)win * n_ctx + t) * d_model + head * kAtD + half * 32;
+        {
+            uint32_t v[32];
+            at_ld32(tO + lane_addr + half * 32, v);
+            at_wait_ld();
+            if (t < n_ctx) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 u;
+                    u.x = Op16<T>::pack2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+                    u.y = Op16<T>::pack2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+                    u.z = Op16<T>::pack2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+                    u.w = Op16<T>::pack2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+                    *reinterpret_cast<uint4*>(orow + i) = u;
+                }
+            }
+        }
+        at_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        at_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+
+template <typename T>
+int attn_enc_tc(const T* qkv, T* out, int n_windows, int n_ctx, int d_model, int n_head, cudaStream_t st) {
+    SB_CHECK_ARG(d_model == n_head * kAtD, "attention: d_head must be 64");
+    CUtensorMap tm;
+    const int is_f16 = std::is_same<T, __half>::value ? 1 : 0;
+    int rc = make_tmap_2d(&tm, qkv, is_f16, (int64_t)n_windows * n_ctx, 3 * (int64_t)d_model, 3 * (int64_t)d_model, 128);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_attn_enc_tc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_attn_enc_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+        attr_done = true;
+    }
+    dim3 grid(ceil_div(n_ctx, kAtBM), n_head, n_windows);
+    const float scale_log2e = (1.0f / 8.0f) * 1.4426950408889634f;
+    k_attn_enc_tc<T><<<grid, kAtThreads, kAtSmem, st>>>(tm, out, n_ctx, d_model, scale_log2e);
+    g_launches += 1;
+    SB_CUDA_CHECK(cudaGetLastError());
+    return SB_OK;
+}
+template int attn_enc_tc<__half>(const __half*, __half*, int, int, int, int, cudaStream_t);
+template int attn_enc_tc<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
+
+}  // namespace sb

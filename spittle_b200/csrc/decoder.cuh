@@ -91,7 +91,9 @@ int num_sms();
 template <typename T> int im2col_conv1(const Im2col1Args& a, T* out, int n_windows, cudaStream_t st);
 template <typename T> int im2col_conv2(const T* in, T* out, int n_windows, int n_in, int n_out, int d, cudaStream_t st);
 template <typename T> int layernorm(const float* x, const float* g, const float* b, T* out16, float* out32, int rows, int d, cudaStream_t st);
-template <typename T> int attn_enc(const T* qkv, T* out, int n_windows, int n_ctx, int d_model, int n_head, cudaStream_t st);
+template <typename T> int attn_enc(const T* qkv, T* out, int n_windows, int n_ctx, int d_model, int n_head, cudaStream_t st);   // mma.sync version
+template <typename T> int attn_enc_tc(const T* qkv, T* out, int n_windows, int n_ctx, int d_model, int n_head, cudaStream_t st);  // tcgen05 version
+bool use_tc_attention();   // env SB_ATTN=mma selects the legacy mma.sync kernel
 
 // decoder-side launchers (decoder_kernels.cu)
 template <typename T> int dec_embed(const T* tok_emb, const float* pos_emb, const int* tokens, const int* pos_ptr, float* x, int Bn, int d, cudaStream_t st);

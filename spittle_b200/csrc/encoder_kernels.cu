@@ -364,6 +364,12 @@ extern "C" int sb_layernorm_dev(int dtype, const float* x, const float* gamma, c
 extern "C" int sb_attn_enc_dev(int dtype, const void* qkv, void* out, int n_windows, int n_ctx, int d_model,
                                int n_head, void* stream) {
     SB_CHECK_ARG(qkv && out, "null pointer");
+    if (sb::use_tc_attention()) {
+        if (dtype == SB_DTYPE_F16)
+            return sb::attn_enc_tc<__half>((const __half*)qkv, (__half*)out, n_windows, n_ctx, d_model, n_head, (cudaStream_t)stream);
+        return sb::attn_enc_tc<__nv_bfloat16>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n_windows, n_ctx, d_model, n_head,
+                                              (cudaStream_t)stream);
+    }
     if (dtype == SB_DTYPE_F16)
         return sb::attn_enc<__half>((const __half*)qkv, (__half*)out, n_windows, n_ctx, d_model, n_head, (cudaStream_t)stream);
     return sb::attn_enc<__nv_bfloat16>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n_windows, n_ctx, d_model, n_head,

@@ -389,7 +389,8 @@ struct Engine : EngineBase {
             ep = GemmEpilogue{b_qkv.p, 3 * d, 0, L.qkv.b, 0, nullptr, 0, 0};
             if ((rc = gemm_p(b_h.p, d, L.qkv.w, d, M, 3 * d, d, ep))) return rc;
             if ((rc = prof_begin(1, 4.0 * W * (double)nctx * nctx * d))) return rc;
-            if ((rc = attn_enc<T>(b_qkv.as<T>(), b_att.as<T>(), W, nctx, d, hp.n_audio_head, st))) return rc;
+            if (use_tc_attention()) { if ((rc = attn_enc_tc<T>(b_qkv.as<T>(), b_att.as<T>(), W, nctx, d, hp.n_audio_head, st))) return rc; }
+            else if ((rc = attn_enc<T>(b_qkv.as<T>(), b_att.as<T>(), W, nctx, d, hp.n_audio_head, st))) return rc;
             if ((rc = prof_end())) return rc;
             ep = GemmEpilogue{b_x.p, d, 1, L.o.b, 0, b_x.as<float>(), d, 0};
             if ((rc = gemm_p(b_att.p, d, L.o.w, d, M, d, d, ep))) return rc;
