@@ -23,18 +23,25 @@
 #include "common.cuh"
 #include "decoder.cuh"
 #include <cuda.h>
+#include <type_traits>
+#include <cstdlib>
 
 namespace sb {
 extern std::atomic<uint64_t> g_launches;
 int make_tmap_2d(CUtensorMap* map, const void* ptr, int is_f16, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
 constexpr int kAtBM = 128;            // queries per CTA
-constexpr int kAtBN = 128;            // keys per tile
 constexpr int kAtD = 64;
-constexpr int kAtKvStages = 4;        // 16 KB each (K or V tile)
-constexpr int kAtTileBytes = 128 * 64 * 2;
-constexpr int kAtPBytes = 128 * 128 * 2;       // one P tile = two 64-key swizzle atoms of 16 KB
-constexpr int kAtSmem = 1024 + kAtTileBytes /*Q*/ + kAtKvStages * kAtTileBytes + 2 * kAtPBytes + 256 + 2 * 128 * 4 /*row max / sum exchange*/;
+constexpr int kAtKvStages = 4;
+constexpr int kAtQBytes = 128 * 64 * 2;
+// BN = keys per tile: 128 (512 TMEM columns, 1 CTA/SM) or 64 (256 columns, 2 CTAs/SM so one CTA's
+// pipeline bubbles -- prologue, pass switch, epilogue -- are covered by the other's work)
+template <int BN> struct AtCfg {
+    static constexpr int kTileBytes = BN * 64 * 2;            // K or V tile
+    static constexpr int kPBytes = 128 * BN * 2;              // P tile: BN/64 swizzle atoms of 16 KB
+    static constexpr int kSmem = 1024 + kAtQBytes + kAtKvStages * kTileBytes + 2 * kPBytes + 256 + 2 * 128 * 4;
+    static constexpr int kTmemCols = BN == 128 ? 512 : 256;   // 2 x BN (S double buffer) + 64 (O), power of two
+};
 constexpr int kAtThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two per TMEM lane quarter)
 
 __device__ __forceinline__ uint32_t at_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,6 +95,25 @@ __device__ __forceinline__ void at_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ float at_ex2(float x) {     // single MUFU.EX2 (exp2f adds denormal range fix-ups)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// back-off wait for the single-thread roles: a tight try_wait loop steals issue slots from the softmax warps
+__device__ __forceinline__ void at_mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
+}
 __device__ __forceinline__ void at_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void at_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void at_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -104,19 +130,23 @@ __device__ __forceinline__ uint64_t at_desc(uint32_t saddr) {
     return d;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kAtThreads, 1)
-k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_qkv, T* __restrict__ out, int n_ctx, int d_model, float scale_log2e) {
+template <typename T, int BN>
+__global__ void __launch_bounds__(kAtThreads, BN == 128 ? 1 : 2)
+k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, T* __restrict__ out,
+              int n_ctx, int d_model, float scale_log2e) {
+    constexpr int kAtBN = BN;
+    constexpr int kAtTileBytes = AtCfg<BN>::kTileBytes;
+    constexpr int kAtPBytes = AtCfg<BN>::kPBytes;
     extern __shared__ unsigned char at_smem_raw[];
     const uint32_t raw = at_smem_u32(at_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* base_ptr = at_smem_raw + (base - raw);
     const uint32_t sQ = base;
-    const uint32_t sKV = base + kAtTileBytes;
+    const uint32_t sKV = base + kAtQBytes;
     const uint32_t sP = sKV + kAtKvStages * kAtTileBytes;
     const uint32_t bar0 = sP + 2 * kAtPBytes;
-    unsigned char* p_ptr = base_ptr + kAtTileBytes + kAtKvStages * kAtTileBytes;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + kAtTileBytes + kAtKvStages * kAtTileBytes + 2 * kAtPBytes + 192);
+    unsigned char* p_ptr = base_ptr + kAtQBytes + kAtKvStages * kAtTileBytes;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + kAtQBytes + kAtKvStages * kAtTileBytes + 2 * kAtPBytes + 192);
     // barriers (8 B each)
     const uint32_t q_full = bar0;
     auto kv_full = [&](int s) { return bar0 + 8u * (1 + s); };
@@ -142,30 +172,31 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_qkv, T* __restrict__ out, i
         }
         at_mbar_init(o_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_qkv) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_kv) : "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(at_smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(at_smem_u32(tmem_slot)), "r"(AtCfg<BN>::kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     at_fence_before();
     __syncthreads();
     at_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tS0 = tmem, tO = tmem + 256;            // S buffers at columns [0,128) and [128,256); O at [256,320)
+    const uint32_t tS0 = tmem, tO = tmem + 2 * BN;         // S buffers at columns [0,BN) and [BN,2BN); O in the next 64
 
     if (warp == 0) {
         if (lane == 0) {
-            at_mbar_expect_tx(q_full, kAtTileBytes);
-            at_tma_2d(sQ, &tm_qkv, col_q, row_q0, q_full);
+            at_mbar_expect_tx(q_full, kAtQBytes);
+            at_tma_2d(sQ, &tm_q, col_q, row_q0, q_full);
             int stage = 0; uint32_t phase = 0;
             // pass 1: K tiles only; pass 2: K then V per tile
             for (int pass = 0; pass < 2; ++pass)
                 for (int j = 0; j < n_kt; ++j)
                     for (int which = 0; which <= pass; ++which) {
-                        at_mbar_wait(kv_empty(stage), phase ^ 1);
+                        at_mbar_wait_relaxed(kv_empty(stage), phase ^ 1);
                         at_mbar_expect_tx(kv_full(stage), kAtTileBytes);
-                        at_tma_2d(sKV + stage * kAtTileBytes, &tm_qkv, which == 0 ? col_k : col_v, win * n_ctx + j * kAtBN,
+                        at_tma_2d(sKV + stage * kAtTileBytes, &tm_kv, which == 0 ? col_k : col_v, win * n_ctx + j * kAtBN,
                                   kv_full(stage));
                         if (++stage == kAtKvStages) { stage = 0; phase ^= 1; }
                     }
@@ -182,12 +213,12 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_qkv, T* __restrict__ out, i
             at_mbar_wait(q_full, 0);
             at_fence_after();
             auto issue_s = [&]() {
-                at_mbar_wait(s_empty(sb), sphase ^ 1);
-                at_mbar_wait(kv_full(stage), phase);
+                at_mbar_wait_relaxed(s_empty(sb), sphase ^ 1);
+                at_mbar_wait_relaxed(kv_full(stage), phase);
                 at_fence_after();
                 const uint64_t kdesc = at_desc(sKV + stage * kAtTileBytes);
 #pragma unroll
-                for (int k = 0; k < kAtD / 16; ++k) at_mma(tS0 + sb * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+                for (int k = 0; k < kAtD / 16; ++k) at_mma(tS0 + sb * BN, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
                 at_commit(kv_empty(stage));
                 at_commit(s_full(sb));
                 if (++stage == kAtKvStages) { stage = 0; phase ^= 1; }
@@ -203,13 +234,13 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_qkv, T* __restrict__ out, i
                 const int v_stage = stage; const uint32_t v_phase = phase;
                 if (++stage == kAtKvStages) { stage = 0; phase ^= 1; }
                 if (j + 1 < n_kt) issue_s();
-                at_mbar_wait(p_full(pb), pphase);
-                at_mbar_wait(kv_full(v_stage), v_phase);
+                at_mbar_wait_relaxed(p_full(pb), pphase);
+                at_mbar_wait_relaxed(kv_full(v_stage), v_phase);
                 at_fence_after();
                 const uint64_t vdesc = at_desc(sKV + v_stage * kAtTileBytes);
 #pragma unroll
                 for (int k = 0; k < kAtBN / 16; ++k) {
-                    // P: two 64-key atoms of 16 KB, 32 B per k16 step inside an atom; V: 16 keys = 16 rows x 128 B
+                    // P: BN/64 atoms of 16 KB, 32 B per k16 step inside an atom; V: 16 keys = 16 rows x 128 B
                     const uint64_t pdesc = at_desc(sP + pb * kAtPBytes + (k >> 2) * 16384) + 2 * (k & 3);
                     at_mma(tO, pdesc, vdesc + (uint64_t)(k * 2048 >> 4), idesc_o, (j | k) != 0);
                 }
@@ -225,7 +256,8 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_qkv, T* __restrict__ out, i
         const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        float* xch = reinterpret_cast<float*>(base_ptr + kAtTileBytes + kAtKvStages * kAtTileBytes + 2 * kAtPBytes + 256);
+        float* xch = reinterpret_cast<float*>(base_ptr + kAtQBytes + kAtKvStages * kAtTileBytes + 2 * kAtPBytes + 256);
+        constexpr int HC = BN / 2;            // key columns per softmax warp (32 or 64)
         int sb = 0; uint32_t sphase = 0;
         float m = -INFINITY;
         // ---- pass 1: row maxima over this warp's 64 columns of every tile ----
@@ -233,21 +265,25 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_qkv, T* __restrict__ out, i
             at_mbar_wait(s_full(sb), sphase);
             at_fence_after();
             uint32_t v0[32], v1[32];
-            at_ld32(tS0 + lane_addr + sb * 128 + half * 64, v0);
-            at_ld32(tS0 + lane_addr + sb * 128 + half * 64 + 32, v1);
+            at_ld32(tS0 + lane_addr + sb * BN + half * HC, v0);
+            if (HC == 64) at_ld32(tS0 + lane_addr + sb * BN + half * HC + 32, v1);
             at_wait_ld();
             at_fence_before();
             __syncwarp();
             if (lane == 0) at_mbar_arrive(s_empty(sb));      // values are in registers: release the buffer early
-            const int k0 = j * kAtBN + half * 64;
-            if (k0 + 64 <= n_ctx) {
+            const int k0 = j * kAtBN + half * HC;
+            if (k0 + HC <= n_ctx) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+                for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v0[i]));
+                if (HC == 64) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v1[i]));
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     if (k0 + i < n_ctx) m = fmaxf(m, __uint_as_float(v0[i]));
-                    if (k0 + 32 + i < n_ctx) m = fmaxf(m, __uint_as_float(v1[i]));
+                    if (HC == 64 && k0 + 32 + i < n_ctx) m = fmaxf(m, __uint_as_float(v1[i]));
                 }
             }
             if (++sb == 2) { sb = 0; sphase ^= 1; }
@@ -264,24 +300,26 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_qkv, T* __restrict__ out, i
             at_mbar_wait(s_full(sb), sphase);
             at_fence_after();
             uint32_t v0[32], v1[32];
-            at_ld32(tS0 + lane_addr + sb * 128 + half * 64, v0);
-            at_ld32(tS0 + lane_addr + sb * 128 + half * 64 + 32, v1);
+            at_ld32(tS0 + lane_addr + sb * BN + half * HC, v0);
+            if (HC == 64) at_ld32(tS0 + lane_addr + sb * BN + half * HC + 32, v1);
             at_wait_ld();
             at_fence_before();
             __syncwarp();
             if (lane == 0) at_mbar_arrive(s_empty(sb));
             at_mbar_wait(p_empty(pb), pphase ^ 1);
-            // this warp's 64 keys are exactly swizzle atom `half` of the P tile
-            unsigned char* prow = p_ptr + pb * kAtPBytes + half * 16384 + row * 128;
-            const int k0 = j * kAtBN + half * 64;
-            const bool tail = k0 + 64 > n_ctx;
-            auto do_chunk = [&](const uint32_t (&v)[32], int cbase, int kk) {
+            // BN 128: this warp's 64 keys are swizzle atom `half`; BN 64: its 32 keys are chunks half*4.. of the only atom
+            unsigned char* prow = p_ptr + pb * kAtPBytes + (HC == 64 ? half * 16384 : 0) + row * 128;
+            const int cb = HC == 64 ? 0 : half * 4;
+            const int k0 = j * kAtBN + half * HC;
+            const bool tail = k0 + HC > n_ctx;
+            auto do_chunk = [&](const uint32_t (&v)[32], int cbase, int kk, auto tail_tag) {
+                constexpr bool kTail = decltype(tail_tag)::value;
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), scale_log2e, -ms));
-                    float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -ms));
-                    if (tail) {
+                    float p0 = at_ex2(fmaf(__uint_as_float(v[2 * i]), scale_log2e, -ms));
+                    float p1 = at_ex2(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -ms));
+                    if (kTail) {
                         if (kk + 2 * i >= n_ctx) p0 = 0.f;
                         if (kk + 2 * i + 1 >= n_ctx) p1 = 0.f;
                     }
@@ -293,8 +331,13 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_qkv, T* __restrict__ out, i
                     *reinterpret_cast<uint4*>(prow + (((cbase + ch) ^ (row & 7)) << 4)) =
                         make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
             };
-            do_chunk(v0, 0, k0);
-            do_chunk(v1, 4, k0 + 32);
+            if (tail) {
+                do_chunk(v0, cb, k0, std::true_type{});
+                if (HC == 64) do_chunk(v1, 4, k0 + 32, std::true_type{});
+            } else {
+                do_chunk(v0, cb, k0, std::false_type{});
+                if (HC == 64) do_chunk(v1, 4, k0 + 32, std::false_type{});
+            }
             // P half-tile written through the generic proxy -> make it visible to the tensor core (async proxy)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -332,29 +375,37 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_qkv, T* __restrict__ out, i
     __syncthreads();
     if (warp == 2) {
         at_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(AtCfg<BN>::kTmemCols));
     }
+}
+
+static int attn_bn() { const char* e = getenv("SB_ATTN_BN"); return (e && atoi(e) == 128) ? 128 : 64; }
+
+template <typename T, int BN>
+static int attn_enc_tc_launch(const T* qkv, T* out, int n_windows, int n_ctx, int d_model, int n_head, cudaStream_t st) {
+    CUtensorMap tq, tkv;
+    const int is_f16 = std::is_same<T, __half>::value ? 1 : 0;
+    int rc = make_tmap_2d(&tq, qkv, is_f16, (int64_t)n_windows * n_ctx, 3 * (int64_t)d_model, 3 * (int64_t)d_model, 128);
+    if (rc) return rc;
+    if ((rc = make_tmap_2d(&tkv, qkv, is_f16, (int64_t)n_windows * n_ctx, 3 * (int64_t)d_model, 3 * (int64_t)d_model, BN))) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_attn_enc_tc<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<BN>::kSmem));
+        attr_done = true;
+    }
+    dim3 grid(ceil_div(n_ctx, kAtBM), n_head, n_windows);
+    const float scale_log2e = (1.0f / 8.0f) * 1.4426950408889634f;
+    k_attn_enc_tc<T, BN><<<grid, kAtThreads, AtCfg<BN>::kSmem, st>>>(tq, tkv, out, n_ctx, d_model, scale_log2e);
+    g_launches += 1;
+    SB_CUDA_CHECK(cudaGetLastError());
+    return SB_OK;
 }
 
 template <typename T>
 int attn_enc_tc(const T* qkv, T* out, int n_windows, int n_ctx, int d_model, int n_head, cudaStream_t st) {
     SB_CHECK_ARG(d_model == n_head * kAtD, "attention: d_head must be 64");
-    CUtensorMap tm;
-    const int is_f16 = std::is_same<T, __half>::value ? 1 : 0;
-    int rc = make_tmap_2d(&tm, qkv, is_f16, (int64_t)n_windows * n_ctx, 3 * (int64_t)d_model, 3 * (int64_t)d_model, 128);
-    if (rc) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SB_CUDA_CHECK(cudaFuncSetAttribute(k_attn_enc_tc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
-        SB_CUDA_CHECK(cudaFuncSetAttribute(k_attn_enc_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
-        attr_done = true;
-    }
-    dim3 grid(ceil_div(n_ctx, kAtBM), n_head, n_windows);
-    const float scale_log2e = (1.0f / 8.0f) * 1.4426950408889634f;
-    k_attn_enc_tc<T><<<grid, kAtThreads, kAtSmem, st>>>(tm, out, n_ctx, d_model, scale_log2e);
-    g_launches += 1;
-    SB_CUDA_CHECK(cudaGetLastError());
-    return SB_OK;
+    if (attn_bn() == 128) return attn_enc_tc_launch<T, 128>(qkv, out, n_windows, n_ctx, d_model, n_head, st);
+    return attn_enc_tc_launch<T, 64>(qkv, out, n_windows, n_ctx, d_model, n_head, st);
 }
 template int attn_enc_tc<__half>(const __half*, __half*, int, int, int, int, cudaStream_t);
 template int attn_enc_tc<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
