@@ -123,6 +123,8 @@ bool use_tc_attention();   // env SB_ATTN=mma selects the legacy mma.sync kernel
 // decoder-side launchers (decoder_kernels.cu)
 template <typename T> int dec_embed(const T* tok_emb, const float* pos_emb, const int* tokens, const int* pos_ptr, float* x, int Bn, int d, cudaStream_t st);
 template <typename T> int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, const SkinnyEpilogue& ep, cudaStream_t st);
+template <typename T> int skinny_gemm_splitk(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, int ks, float* part, int64_t part_stride, cudaStream_t st);
+template <typename T> int dec_ln(float* x, const float* gamma, const float* beta, T* out16, int rows, int d, const T* tok_emb, const float* pos_emb, const int* next_tokens, const int* pos_ptr, const float* part, int nparts, int64_t part_stride, const float* pbias, cudaStream_t st);
 template <typename T> int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const int* pos_ptr, const SeqState* state, int Bn, int n_head, int d, int n_text_ctx, cudaStream_t st);
 template <typename T> int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t ld_kv, int64_t win_stride, T* out, const SeqState* state, int Bn, int n_head, int d, int n_ctx, const FusedQ& fq, cudaStream_t st);
 int sample_step(const float* logits, int ld, const SamplerArgs& a, int Bn, cudaStream_t st);

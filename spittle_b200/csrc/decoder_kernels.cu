@@ -43,6 +43,37 @@ __global__ void __launch_bounds__(256) k_skinny_gemm(const T* __restrict__ X, in
     skinny_body<T, 1>(X, ldx, W, ldw, Bn, N, 0, K / 32, ep, nullptr, 0, blockIdx.x, blockIdx.y, smem, sync);
 }
 
+// split-K variant: grid.x = tiles * ks; block (tile, slice) stores raw f32 sums of its K slice to part[slice]
+// (no epilogue); the consumer (k_dec_ln) adds bias + slices in slice order.  Less activation per block:
+// these launches are bound by each SM's L2 ingest of the shared [B, K] activation matrix, not by the weights.
+template <typename T>
+__global__ void __launch_bounds__(256) k_skinny_gemm_splitk(const T* __restrict__ X, int ldx, const T* __restrict__ W, int ldw,
+                                                            int Bn, int N, int K, int ks, float* __restrict__ part,
+                                                            int64_t part_stride) {
+    __shared__ __align__(16) unsigned char smem[kSkinnySmem / 2];
+    PdlSync sync;
+    const int tiles = (N + 15) / 16;
+    const int sI = blockIdx.x / tiles, tile = blockIdx.x - sI * tiles;
+    const int kb = K / 32;
+    const int kb0 = (int)((int64_t)kb * sI / ks), kb1 = (int)((int64_t)kb * (sI + 1) / ks);
+    SkinnyEpilogue ep{};
+    skinny_body<T, 1>(X, ldx, W, ldw, Bn, N, kb0, kb1, ep, part + sI * part_stride, N, tile, blockIdx.y, smem, sync);
+}
+
+// decoder LayerNorm, one warp (= one block) per row so the 64 rows spread over 64 SMs:
+// optional embedding (x = tok_emb[tok] + pos_emb[pos]) or split-K completion of the residual stream
+// (x += bias + sum_s part[s]) first, then LN -> 16-bit h.
+template <typename T, int VPL>
+__global__ void __launch_bounds__(32) k_dec_ln(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                               T* __restrict__ out16, int d, const T* __restrict__ tok_emb,
+                                               const float* __restrict__ pos_emb, const int* __restrict__ next_tokens,
+                                               const int* __restrict__ pos_ptr, const float* __restrict__ part, int nparts,
+                                               int64_t part_stride, const float* __restrict__ pbias) {
+    struct S { __device__ __forceinline__ void wait() { pdl_wait(); pdl_trigger(); } } sync;
+    ln_row_mega<T, VPL>(x, gamma, beta, out16, blockIdx.x, d, tok_emb, pos_emb, next_tokens, pos_ptr, part, nparts, part_stride,
+                        pbias, sync);
+}
+
 // self attention for one new token per sequence.  grid = B * n_head / 4, 128 threads (warp per (b, head)).
 template <typename T>
 __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc,
@@ -311,6 +342,29 @@ int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, 
     return SB_OK;
 }
 template <typename T>
+int skinny_gemm_splitk(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, int ks, float* part, int64_t part_stride,
+                       cudaStream_t st) {
+    SB_CHECK_ARG(K % 32 == 0 && ldx % 8 == 0 && ldw % 8 == 0 && ks >= 1 && ks <= kMegaMaxSplit && K / 32 >= ks,
+                 "split-K skinny gemm: K % 32, 16-byte row alignment, 1 <= ks <= 6");
+    dim3 grid(ceil_div(N, 16) * ks, ceil_div(Bn, 64));
+    launch_pdl(k_skinny_gemm_splitk<T>, grid, dim3(256), 0, st, X, ldx, W, ldw, Bn, N, K, ks, part, part_stride);
+    g_launches += 1;
+    SB_CUDA_CHECK(cudaGetLastError());
+    return SB_OK;
+}
+template <typename T>
+int dec_ln(float* x, const float* gamma, const float* beta, T* out16, int rows, int d, const T* tok_emb, const float* pos_emb,
+           const int* next_tokens, const int* pos_ptr, const float* part, int nparts, int64_t part_stride, const float* pbias,
+           cudaStream_t st) {
+    SB_CHECK_ARG(d % 4 == 0 && d <= 1536 && nparts >= 0 && nparts <= kMegaMaxSplit, "decoder layernorm: d % 4, d <= 1536");
+    if (d <= 768) launch_pdl(k_dec_ln<T, 6>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr, part, nparts, part_stride, pbias);
+    else if (d <= 1280) launch_pdl(k_dec_ln<T, 10>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr, part, nparts, part_stride, pbias);
+    else launch_pdl(k_dec_ln<T, 12>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr, part, nparts, part_stride, pbias);
+    g_launches += 1;
+    SB_CUDA_CHECK(cudaGetLastError());
+    return SB_OK;
+}
+template <typename T>
 int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const int* pos_ptr, const SeqState* state, int Bn, int n_head, int d,
                   int n_text_ctx, cudaStream_t st) {
     SB_CHECK_ARG(n_text_ctx <= 448 && d == n_head * 64, "self attention: n_text_ctx <= 448, d_head 64");
@@ -345,6 +399,8 @@ int dec_advance(int* pos_ptr, int* step_ptr, int n_prompt, unsigned* barrier, cu
 #define SB_INST_D(T)                                                                                              \
     template int dec_embed<T>(const T*, const float*, const int*, const int*, float*, int, int, cudaStream_t);    \
     template int skinny_gemm<T>(const T*, int, const T*, int, int, int, int, const SkinnyEpilogue&, cudaStream_t); \
+    template int skinny_gemm_splitk<T>(const T*, int, const T*, int, int, int, int, int, float*, int64_t, cudaStream_t); \
+    template int dec_ln<T>(float*, const float*, const float*, T*, int, int, const T*, const float*, const int*, const int*, const float*, int, int64_t, const float*, cudaStream_t); \
     template int dec_self_attn<T>(const T*, T*, T*, T*, const int*, const SeqState*, int, int, int, int, cudaStream_t);             \
     template int dec_cross_attn<T>(const T*, int, const T*, const T*, int64_t, int64_t, T*, const SeqState*, int, int, int, int, const FusedQ&, cudaStream_t);
 SB_INST_D(__nv_bfloat16)

@@ -68,88 +68,6 @@ constexpr int kMegaMaxB = 256;
 constexpr int kMegaWork = kCrossSmem > kSkinnySmem / 2 ? kCrossSmem : kSkinnySmem / 2;    // stage scratch (stages overlay each other)
 constexpr int kMegaSmem = 1040 + kMegaWork;
 
-// ---- LayerNorm of one row by one warp; optionally first completes the residual stream:
-//      x_row += bias + sum_s part[s][row]   (split-K slices of the producing projection, fixed order)
-template <typename T, int VPL>
-__device__ __forceinline__ void ln_row_mega(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                            T* __restrict__ out16, int row, int d, const T* __restrict__ tok_emb,
-                                            const float* __restrict__ pos_emb, const int* __restrict__ next_tokens, int pos,
-                                            const float* __restrict__ part, int nparts, int64_t part_stride,
-                                            const float* __restrict__ pbias, GridSync& sync) {
-    const int lane = threadIdx.x & 31;
-    const int n4 = d >> 2;
-    // immutable operands first: they are in flight while the barrier is still closing
-    float4 g[VPL], bt[VPL];
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int idx = lane + 32 * i;
-        if (idx < n4) { g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + idx); bt[i] = __ldg(reinterpret_cast<const float4*>(beta) + idx); }
-    }
-    sync.wait();
-    float4 v[VPL];
-    float4* xr = reinterpret_cast<float4*>(x + (int64_t)row * d);
-    if (tok_emb) {
-        const int tok = __ldcg(next_tokens + row);
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-            const int idx = lane + 32 * i;
-            if (idx < n4) {
-                const uint2 u = __ldg(reinterpret_cast<const uint2*>(tok_emb + (int64_t)tok * d) + idx);
-                const float4 p = __ldg(reinterpret_cast<const float4*>(pos_emb + (int64_t)pos * d) + idx);
-                const float2 a = Op16<T>::unpack2(u.x), b = Op16<T>::unpack2(u.y);
-                v[i] = make_float4(a.x + p.x, a.y + p.y, b.x + p.z, b.y + p.w);
-                xr[idx] = v[i];
-            } else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-            const int idx = lane + 32 * i;
-            v[i] = idx < n4 ? __ldcg(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (nparts > 0) {
-#pragma unroll
-            for (int i = 0; i < VPL; ++i) {
-                const int idx = lane + 32 * i;
-                if (idx < n4) {
-                    const float4 pb = __ldg(reinterpret_cast<const float4*>(pbias) + idx);
-                    float4 acc = pb;
-                    for (int sI = 0; sI < nparts; ++sI) {
-                        const float4 q = __ldcg(reinterpret_cast<const float4*>(part + sI * part_stride + (int64_t)row * d) + idx);
-                        acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
-                    }
-                    v[i].x += acc.x; v[i].y += acc.y; v[i].z += acc.z; v[i].w += acc.w;
-                    xr[idx] = v[i];
-                }
-            }
-        }
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
-    const float mean = warp_sum(s) / (float)d;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int idx = lane + 32 * i;
-        if (idx < n4) {
-            v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-            q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-        }
-    }
-    const float rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int idx = lane + 32 * i;
-        if (idx < n4) {
-            uint2 u;
-            u.x = Op16<T>::pack2(v[i].x * rstd * g[i].x + bt[i].x, v[i].y * rstd * g[i].y + bt[i].y);
-            u.y = Op16<T>::pack2(v[i].z * rstd * g[i].z + bt[i].z, v[i].w * rstd * g[i].w + bt[i].w);
-            reinterpret_cast<uint2*>(out16 + (int64_t)row * d)[idx] = u;
-        }
-    }
-}
-
 template <typename T, int VPL>
 __global__ void __launch_bounds__(256, 1) k_dec_step_mega(const DecLayerDev* __restrict__ layers, DecStepArgs a) {
     extern __shared__ __align__(128) unsigned char mega_smem[];
@@ -209,7 +127,7 @@ __global__ void __launch_bounds__(256, 1) k_dec_step_mega(const DecLayerDev* __r
             bool any = false;
             for (int row = cta + G * warp; row < Bn; row += G * 8) {
                 ln_row_mega<T, VPL>(a.x, g, bt, h16, row, d, embed ? reinterpret_cast<const T*>(a.tok_emb) : nullptr, a.pos_emb,
-                                    a.next_tokens, pos, a.part, np, a.part_stride, pbias, sync);
+                                    a.next_tokens, a.pos_ptr, a.part, np, a.part_stride, pbias, sync);
                 any = true;
             }
             (void)any;

@@ -196,6 +196,7 @@ struct Engine : EngineBase {
     bool use_mega = false;     // env SB_DEC_MEGA=1: persistent per-step megakernel instead of one PDL-chained launch per stage
                                // (measured SLOWER on B200: grid barriers cost ~2 us and one CTA/SM starves the cross-KV stream)
     DevBuf b_declayers, b_dpart;
+    bool chain_split = false;   // env SB_DEC_SPLITK=1: residual projections of the PDL chain split along K (measured slower: 722 vs 568 ms)
     bool mega_split = true;     // env SB_MEGA_SPLIT=0: no split-K / wide tiles in the megakernel projections
 
     ~Engine() override {
@@ -324,6 +325,7 @@ struct Engine : EngineBase {
         if (const char* e = getenv("SB_FUSED_Q")) fused_q = e[0] == '1';
         if (const char* e = getenv("SB_DEC_MEGA")) use_mega = e[0] != '0';
         if (const char* e = getenv("SB_MEGA_SPLIT")) mega_split = e[0] != '0';
+        if (const char* e = getenv("SB_DEC_SPLITK")) chain_split = e[0] != '0';
         if (const char* e = getenv("SB_DECODE_LANES")) { n_lanes_cfg = atoi(e); if (n_lanes_cfg < 1) n_lanes_cfg = 1; if (n_lanes_cfg > kMaxLanes) n_lanes_cfg = kMaxLanes; }
         int rc = sb_melplan_create(f.mel_filters.data(), hp.n_mels, &melplan);
         if (rc) return rc;
@@ -496,37 +498,61 @@ struct Engine : EngineBase {
             if ((rc = sample_step(logits, vpad, sa, Wl, sl))) return rc;
             return dec_advance(pos_ptr, step_ptr, sa.n_prompt, ma.barrier, sl);
         }
-        if ((rc = dec_embed<T>(tok_emb, dec_pos, b_next.as<int>() + w0, pos_ptr, dx, Wl, d, sl))) return rc;
+        // PDL chain, one launch per stage.  The residual projections (O, cross O, FC2) are split along K: each
+        // block then ingests a third (or less) of the [B, K] activation matrix -- per-SM L2 ingest of that shared
+        // matrix is what bounds these launches -- and the following LayerNorm launch adds bias + slices to x.
+        int ks_o = 1, ks_fc2 = 1, mt_unused = 1;
+        if (chain_split && !fused_q) {
+            mega_plan(d, d, true, num_sms(), &mt_unused, &ks_o);
+            mega_plan(d, 4 * d, true, num_sms(), &mt_unused, &ks_fc2);
+        }
+        float* part = b_dpart.as<float>() + (int64_t)w0 * d;
+        const int64_t pstride = (int64_t)W * d;
+        const int* next_tok = b_next.as<int>() + w0;
         for (int l = 0; l < hp.n_text_layer; ++l) {
             const DecLayer<T>& L = dec[l];
             T* kc = b_kself.as<T>() + ((int64_t)l * W + w0) * hp.n_text_ctx * d;
             T* vc = b_vself.as<T>() + ((int64_t)l * W + w0) * hp.n_text_ctx * d;
             SkinnyEpilogue e{};
-            if ((rc = layernorm<T>(dx, L.ln1.g, L.ln1.b, dh, nullptr, Wl, d, sl))) return rc;
+            // attn_ln; layer 0 forms x = token_embedding[tok] + positional_embedding[pos] first
+            if ((rc = dec_ln<T>(dx, L.ln1.g, L.ln1.b, dh, Wl, d, l == 0 ? tok_emb : nullptr, dec_pos, next_tok, pos_ptr, part,
+                                (l > 0 && ks_fc2 > 1) ? ks_fc2 : 0, pstride, l > 0 ? dec[l - 1].fc2.b : nullptr, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.qkv.b; e.out16 = dqkv; e.ldo16 = 3 * d;
             if ((rc = skinny_gemm<T>(dh, d, L.qkv.w, d, Wl, 3 * d, d, e, sl))) return rc;
             if ((rc = dec_self_attn<T>(dqkv, kc, vc, datt, pos_ptr, seq_state, Wl, hp.n_text_head, d, hp.n_text_ctx, sl))) return rc;
-            e = SkinnyEpilogue{}; e.bias = L.o.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
-            if ((rc = skinny_gemm<T>(datt, d, L.o.w, d, Wl, d, d, e, sl))) return rc;
+            if (ks_o > 1) { if ((rc = skinny_gemm_splitk<T>(datt, d, L.o.w, d, Wl, d, d, ks_o, part, pstride, sl))) return rc; }
+            else {
+                e = SkinnyEpilogue{}; e.bias = L.o.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
+                if ((rc = skinny_gemm<T>(datt, d, L.o.w, d, Wl, d, d, e, sl))) return rc;
+            }
             // cross_attn_ln + query projection can be fused into the cross-attention kernel's prologue
             FusedQ fq;
             if (fused_q) { fq.x = dx; fq.ln_g = L.ln2.g; fq.ln_b = L.ln2.b; fq.wq = L.cq.w; fq.bq = L.cq.b; }
             else {
-                if ((rc = layernorm<T>(dx, L.ln2.g, L.ln2.b, dh, nullptr, Wl, d, sl))) return rc;
+                if ((rc = dec_ln<T>(dx, L.ln2.g, L.ln2.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, part, ks_o > 1 ? ks_o : 0,
+                                    pstride, L.o.b, sl))) return rc;
                 e = SkinnyEpilogue{}; e.bias = L.cq.b; e.out16 = dq; e.ldo16 = d;
                 if ((rc = skinny_gemm<T>(dh, d, L.cq.w, d, Wl, d, d, e, sl))) return rc;
             }
             const T* kb = b_ckv.as<T>() + (int64_t)w0 * nctx * nkv + (int64_t)l * 2 * d;
             if ((rc = dec_cross_attn<T>(dq, d, kb, kb + d, nkv, (int64_t)nctx * nkv, datt, seq_state, Wl, hp.n_text_head, d, nctx, fq, sl))) return rc;
-            e = SkinnyEpilogue{}; e.bias = L.co.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
-            if ((rc = skinny_gemm<T>(datt, d, L.co.w, d, Wl, d, d, e, sl))) return rc;
-            if ((rc = layernorm<T>(dx, L.ln3.g, L.ln3.b, dh, nullptr, Wl, d, sl))) return rc;
+            if (ks_o > 1) { if ((rc = skinny_gemm_splitk<T>(datt, d, L.co.w, d, Wl, d, d, ks_o, part, pstride, sl))) return rc; }
+            else {
+                e = SkinnyEpilogue{}; e.bias = L.co.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
+                if ((rc = skinny_gemm<T>(datt, d, L.co.w, d, Wl, d, d, e, sl))) return rc;
+            }
+            if ((rc = dec_ln<T>(dx, L.ln3.g, L.ln3.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, part, ks_o > 1 ? ks_o : 0, pstride,
+                                L.co.b, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.fc1.b; e.act = 1; e.out16 = dmlp; e.ldo16 = 4 * d;
             if ((rc = skinny_gemm<T>(dh, d, L.fc1.w, d, Wl, 4 * d, d, e, sl))) return rc;
-            e = SkinnyEpilogue{}; e.bias = L.fc2.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
-            if ((rc = skinny_gemm<T>(dmlp, 4 * d, L.fc2.w, 4 * d, Wl, d, 4 * d, e, sl))) return rc;
+            if (ks_fc2 > 1) { if ((rc = skinny_gemm_splitk<T>(dmlp, 4 * d, L.fc2.w, 4 * d, Wl, d, 4 * d, ks_fc2, part, pstride, sl))) return rc; }
+            else {
+                e = SkinnyEpilogue{}; e.bias = L.fc2.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
+                if ((rc = skinny_gemm<T>(dmlp, 4 * d, L.fc2.w, 4 * d, Wl, d, 4 * d, e, sl))) return rc;
+            }
         }
-        if ((rc = layernorm<T>(dx, ln_f.g, ln_f.b, dh, nullptr, Wl, d, sl))) return rc;
+        if ((rc = dec_ln<T>(dx, ln_f.g, ln_f.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, part, ks_fc2 > 1 ? ks_fc2 : 0, pstride,
+                            dec.back().fc2.b, sl))) return rc;
         // tied-embedding logits: 80-130 MB of weights per step -> the TMA-fed tcgen05 GEMM streams them
         // (one 128-row tile of sequences, ~200 column tiles) instead of the small-N weight-streaming kernel
         GemmEpilogue ge{logits, vpad, 1, nullptr, 0, nullptr, 0, 0};
