@@ -101,7 +101,7 @@ __device__ __forceinline__ float at_ex2(float x) {     // single MUFU.EX2 (exp2f
     return y;
 }
 // back-off wait for the single-thread roles: a tight try_wait loop steals issue slots from the softmax warps
-__device__ __forceinline__ void at_mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void at_mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns = 64) {
     uint32_t done;
     for (;;) {
         asm volatile(
@@ -111,7 +111,7 @@ __device__ __forceinline__ void at_mbar_wait_relaxed(uint32_t bar, uint32_t pari
             "selp.u32 %0, 1, 0, p;\n"
             "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) break;
-        __nanosleep(64);
+        if (ns) __nanosleep(ns);
     }
 }
 __device__ __forceinline__ void at_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -133,7 +133,7 @@ __device__ __forceinline__ uint64_t at_desc(uint32_t saddr) {
 template <typename T, int BN>
 __global__ void __launch_bounds__(kAtThreads, BN == 128 ? 1 : 2)
 k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, T* __restrict__ out,
-              int n_ctx, int d_model, float scale_log2e) {
+              int n_ctx, int d_model, float scale_log2e, int mma_sleep) {
     constexpr int kAtBN = BN;
     constexpr int kAtTileBytes = AtCfg<BN>::kTileBytes;
     constexpr int kAtPBytes = AtCfg<BN>::kPBytes;
@@ -156,6 +156,11 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     auto p_full = [&](int b) { return bar0 + 8u * (5 + 2 * kAtKvStages + b); };
     auto p_empty = [&](int b) { return bar0 + 8u * (7 + 2 * kAtKvStages + b); };
     const uint32_t o_full = bar0 + 8u * (9 + 2 * kAtKvStages);
+    // pass 1 has no O accumulator yet: its S ring uses the whole TMEM allocation (4 buffers), so the MMAs run ahead
+    // of the row-maximum sweep instead of ping-ponging with it
+    constexpr int kS1 = AtCfg<BN>::kTmemCols / BN;
+    auto s1_full = [&](int b) { return bar0 + 8u * (10 + 2 * kAtKvStages + b); };
+    auto s1_empty = [&](int b) { return bar0 + 8u * (10 + 2 * kAtKvStages + kS1 + b); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, head = blockIdx.y, win = blockIdx.z;
@@ -171,6 +176,7 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             at_mbar_init(p_full(b), 8); at_mbar_init(p_empty(b), 1);
         }
         at_mbar_init(o_full, 1);
+        for (int b = 0; b < kS1; ++b) { at_mbar_init(s1_full(b), 1); at_mbar_init(s1_empty(b), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_kv) : "memory");
@@ -213,8 +219,8 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             at_mbar_wait(q_full, 0);
             at_fence_after();
             auto issue_s = [&]() {
-                at_mbar_wait_relaxed(s_empty(sb), sphase ^ 1);
-                at_mbar_wait_relaxed(kv_full(stage), phase);
+                at_mbar_wait_relaxed(s_empty(sb), sphase ^ 1, (unsigned)mma_sleep);
+                at_mbar_wait_relaxed(kv_full(stage), phase, (unsigned)mma_sleep);
                 at_fence_after();
                 const uint64_t kdesc = at_desc(sKV + stage * kAtTileBytes);
 #pragma unroll
@@ -224,8 +230,25 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 if (++stage == kAtKvStages) { stage = 0; phase ^= 1; }
                 if (++sb == 2) { sb = 0; sphase ^= 1; }
             };
-            // pass 1
-            for (int j = 0; j < n_kt; ++j) issue_s();
+            // pass 1: S_j into ring buffer j % kS1
+            for (int j = 0; j < n_kt; ++j) {
+                const int b1 = j % kS1; const uint32_t ph1 = (uint32_t)(j / kS1) & 1u;
+                at_mbar_wait_relaxed(s1_empty(b1), ph1 ^ 1, (unsigned)mma_sleep);
+                at_mbar_wait_relaxed(kv_full(stage), phase, (unsigned)mma_sleep);
+                at_fence_after();
+                const uint64_t kdesc = at_desc(sKV + stage * kAtTileBytes);
+#pragma unroll
+                for (int k = 0; k < kAtD / 16; ++k) at_mma(tS0 + b1 * BN, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+                at_commit(kv_empty(stage));
+                at_commit(s1_full(b1));
+                if (++stage == kAtKvStages) { stage = 0; phase ^= 1; }
+            }
+            // pass 2 reuses the TMEM columns: every pass-1 buffer must have been read out
+            for (int b1 = 0; b1 < kS1; ++b1) {
+                const int uses = b1 < n_kt ? (n_kt - b1 + kS1 - 1) / kS1 : 0;
+                if (uses > 0) at_mbar_wait_relaxed(s1_empty(b1), (uint32_t)(uses - 1) & 1u);
+            }
+            at_fence_after();
             // pass 2: S_0, then for each tile: S_{j+1} before PV_j so the tensor pipe always has work queued
             int pb = 0; uint32_t pphase = 0;
             issue_s();
@@ -234,8 +257,8 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 const int v_stage = stage; const uint32_t v_phase = phase;
                 if (++stage == kAtKvStages) { stage = 0; phase ^= 1; }
                 if (j + 1 < n_kt) issue_s();
-                at_mbar_wait_relaxed(p_full(pb), pphase);
-                at_mbar_wait_relaxed(kv_full(v_stage), v_phase);
+                at_mbar_wait_relaxed(p_full(pb), pphase, (unsigned)mma_sleep);
+                at_mbar_wait_relaxed(kv_full(v_stage), v_phase, (unsigned)mma_sleep);
                 at_fence_after();
                 const uint64_t vdesc = at_desc(sKV + v_stage * kAtTileBytes);
 #pragma unroll
@@ -262,15 +285,16 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         float m = -INFINITY;
         // ---- pass 1: row maxima over this warp's 64 columns of every tile ----
         for (int j = 0; j < n_kt; ++j) {
-            at_mbar_wait(s_full(sb), sphase);
+            const int b1 = j % kS1;
+            at_mbar_wait(s1_full(b1), (uint32_t)(j / kS1) & 1u);
             at_fence_after();
             uint32_t v0[32], v1[32];
-            at_ld32(tS0 + lane_addr + sb * BN + half * HC, v0);
-            if (HC == 64) at_ld32(tS0 + lane_addr + sb * BN + half * HC + 32, v1);
+            at_ld32(tS0 + lane_addr + b1 * BN + half * HC, v0);
+            if (HC == 64) at_ld32(tS0 + lane_addr + b1 * BN + half * HC + 32, v1);
             at_wait_ld();
             at_fence_before();
             __syncwarp();
-            if (lane == 0) at_mbar_arrive(s_empty(sb));      // values are in registers: release the buffer early
+            if (lane == 0) at_mbar_arrive(s1_empty(b1));     // values are in registers: release the buffer early
             const int k0 = j * kAtBN + half * HC;
             if (k0 + HC <= n_ctx) {
 #pragma unroll
@@ -286,7 +310,6 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     if (HC == 64 && k0 + 32 + i < n_ctx) m = fmaxf(m, __uint_as_float(v1[i]));
                 }
             }
-            if (++sb == 2) { sb = 0; sphase ^= 1; }
         }
         xch[half * 128 + row] = m;
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -379,6 +402,316 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     }
 }
 
+// ==========================================================================================
+// k_attn_enc_ts: same algorithm, but Q and P are tcgen05.mma A operands read from TMEM.
+//
+// ncu on k_attn_enc_tc (profiles/r1_full_attn_enc_tc_bn64.md): XU 43 %, tensor 33 %, issue 49 % -- nothing
+// saturated, yet no pipeline change moved the time.  What is saturated is shared-memory bandwidth: an
+// M128 x N64 x K16 UMMA reads 4 KB of A and 2 KB of B for 32 tensor-clocks of math (192 B/clk against the
+// SM's 128 B/clk), and per 64-key tile the CTA moved Q (16 KB, re-read for every tile), P (16 KB written by
+// the softmax warps, 16 KB read back), K and V (8 KB each, written by TMA and read by the MMA): ~88 KB.
+// Here Q is staged once into 32 TMEM columns and P is stored with tcgen05.st over the S columns it was
+// computed from, so per tile only K and V cross shared memory (32 KB incl. the TMA writes).
+//
+// TMEM (256 columns, 2 CTAs/SM): S0 [0,64) S1 [64,128) O [128,192) Q [192,224).  P_j lives inside S buffer
+// j%2: the warp that owns key columns [32h, 32h+32) of a row writes its 32 probabilities as 16 packed words
+// to columns [32h, 32h+16) -- over S values it has already loaded itself, so no cross-warp hazard.
+// The MMA thread issues S_0 S_1 | PV_0 S_2 | PV_1 S_3 | ...: the tensor pipe executes in issue order, so
+// S_{j+2} cannot overwrite buffer j%2 before PV_j has read P_j, and the softmax warps always find S_{j+1}
+// complete when they finish tile j.  Pass 1 (row maxima) rings over the three 64-column buffers below Q.
+// ==========================================================================================
+constexpr int kTsKvStages = 6;
+constexpr int kTsTileBytes = 64 * 64 * 2;
+constexpr int kTsSmem = 1024 + kTsKvStages * kTsTileBytes + 256 + 2 * 128 * 4;
+
+__device__ __forceinline__ void at_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void at_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void at_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <typename T>
+__global__ void __launch_bounds__(kAtThreads, 2)
+k_attn_enc_ts(const __grid_constant__ CUtensorMap tm_kv, const T* __restrict__ qkv, T* __restrict__ out, int n_ctx, int d_model,
+              float scale_log2e) {
+    constexpr int BN = 64;
+    extern __shared__ unsigned char at_smem_raw[];
+    const uint32_t raw = at_smem_u32(at_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* base_ptr = at_smem_raw + (base - raw);
+    const uint32_t sKV = base;
+    const uint32_t bar0 = sKV + kTsKvStages * kTsTileBytes;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + kTsKvStages * kTsTileBytes + 192);
+    float* xch = reinterpret_cast<float*>(base_ptr + kTsKvStages * kTsTileBytes + 256);
+    auto kv_full = [&](int s) { return bar0 + 8u * s; };
+    auto kv_empty = [&](int s) { return bar0 + 8u * (kTsKvStages + s); };
+    auto s_full = [&](int b) { return bar0 + 8u * (2 * kTsKvStages + b); };           // pass 2, 2 buffers
+    auto p_full = [&](int b) { return bar0 + 8u * (2 * kTsKvStages + 2 + b); };
+    auto s1_full = [&](int b) { return bar0 + 8u * (2 * kTsKvStages + 4 + b); };      // pass 1, 3 buffers
+    auto s1_empty = [&](int b) { return bar0 + 8u * (2 * kTsKvStages + 7 + b); };
+    const uint32_t q_full = bar0 + 8u * (2 * kTsKvStages + 10);
+    const uint32_t o_full = bar0 + 8u * (2 * kTsKvStages + 11);
+    constexpr int kS1 = 3;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, head = blockIdx.y, win = blockIdx.z;
+    const int n_kt = (n_ctx + BN - 1) / BN;
+    const int col_k = d_model + head * kAtD, col_v = 2 * d_model + head * kAtD;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTsKvStages; ++s) { at_mbar_init(kv_full(s), 1); at_mbar_init(kv_empty(s), 1); }
+        for (int b = 0; b < 2; ++b) { at_mbar_init(s_full(b), 1); at_mbar_init(p_full(b), 8); }
+        for (int b = 0; b < kS1; ++b) { at_mbar_init(s1_full(b), 1); at_mbar_init(s1_empty(b), 8); }
+        at_mbar_init(q_full, 8);
+        at_mbar_init(o_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_kv) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(at_smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    at_fence_before();
+    __syncthreads();
+    at_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS0 = tmem, tO = tmem + 128, tQ = tmem + 192;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int pass = 0; pass < 2; ++pass)
+                for (int j = 0; j < n_kt; ++j)
+                    for (int which = 0; which <= pass; ++which) {
+                        at_mbar_wait_relaxed(kv_empty(stage), phase ^ 1);
+                        at_mbar_expect_tx(kv_full(stage), kTsTileBytes);
+                        at_tma_2d(sKV + stage * kTsTileBytes, &tm_kv, which == 0 ? col_k : col_v, win * n_ctx + j * BN, kv_full(stage));
+                        if (++stage == kTsKvStages) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t fmt = (uint32_t)Op16<T>::kUmmaFormat;
+            const uint32_t idesc_s = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kAtBM >> 4) << 24);
+            const uint32_t idesc_o = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) | ((uint32_t)(kAtD >> 3) << 17) | ((uint32_t)(kAtBM >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            at_mbar_wait(q_full, 0);
+            at_fence_after();
+            auto mma_s = [&](uint32_t tdst) {
+                at_mbar_wait_relaxed(kv_full(stage), phase, 0);
+                at_fence_after();
+                const uint64_t kdesc = at_desc(sKV + stage * kTsTileBytes);
+#pragma unroll
+                for (int k = 0; k < kAtD / 16; ++k) at_mma_ts(tdst, tQ + 8 * k, kdesc + 2 * k, idesc_s, k != 0);
+                at_commit(kv_empty(stage));
+                if (++stage == kTsKvStages) { stage = 0; phase ^= 1; }
+            };
+            // pass 1: S_j into ring buffer j % 3
+            for (int j = 0; j < n_kt; ++j) {
+                const int b1 = j % kS1;
+                at_mbar_wait_relaxed(s1_empty(b1), ((uint32_t)(j / kS1) & 1u) ^ 1u, 0);
+                mma_s(tS0 + b1 * BN);
+                at_commit(s1_full(b1));
+            }
+            for (int b1 = 0; b1 < kS1; ++b1) {
+                const int uses = b1 < n_kt ? (n_kt - b1 + kS1 - 1) / kS1 : 0;
+                if (uses > 0) at_mbar_wait_relaxed(s1_empty(b1), (uint32_t)(uses - 1) & 1u, 0);
+            }
+            at_fence_after();
+            // pass 2.  Stage order produced by the TMA warp: K_0 V_0 K_1 V_1 ...; S_{j+2} needs K_{j+2}, two tiles ahead
+            // of V_j, so the K stages are consumed out of ring order: track the (stage, phase) of tile t's K explicitly.
+            const int st0 = stage; const uint32_t ph0 = phase;          // ring position of K_0
+            auto ring_at = [&](int idx, int& st, uint32_t& ph) {         // idx-th tile (K_0 = 0, V_0 = 1, K_1 = 2, ...)
+                const int lin = st0 + idx;
+                st = lin % kTsKvStages;
+                ph = ph0 ^ ((uint32_t)(lin / kTsKvStages) & 1u);
+            };
+            auto mma_s2 = [&](int t) {
+                int st; uint32_t ph;
+                ring_at(2 * t, st, ph);
+                at_mbar_wait_relaxed(kv_full(st), ph, 0);
+                at_fence_after();
+                const uint64_t kdesc = at_desc(sKV + st * kTsTileBytes);
+#pragma unroll
+                for (int k = 0; k < kAtD / 16; ++k) at_mma_ts(tS0 + (t & 1) * BN, tQ + 8 * k, kdesc + 2 * k, idesc_s, k != 0);
+                at_commit(kv_empty(st));
+                at_commit(s_full(t & 1));
+            };
+            mma_s2(0);
+            if (n_kt > 1) mma_s2(1);
+            for (int j = 0; j < n_kt; ++j) {
+                const int pb = j & 1; const uint32_t pphase = (uint32_t)(j >> 1) & 1u;
+                int st; uint32_t ph;
+                ring_at(2 * j + 1, st, ph);
+                at_mbar_wait_relaxed(p_full(pb), pphase, 0);
+                at_mbar_wait_relaxed(kv_full(st), ph, 0);
+                at_fence_after();
+                const uint64_t vdesc = at_desc(sKV + st * kTsTileBytes);
+#pragma unroll
+                for (int k = 0; k < BN / 16; ++k) {
+                    // keys 16k..16k+15: packed P columns [8k, 8k+8) of the owning warp's 16-column block (block h at column 32h)
+                    const uint32_t pa = tS0 + pb * BN + (k >> 1) * 32 + (k & 1) * 8;
+                    at_mma_ts(tO, pa, vdesc + (uint64_t)(k * 2048 >> 4), idesc_o, (j | k) != 0);
+                }
+                at_commit(kv_empty(st));
+                if (j + 2 < n_kt) mma_s2(j + 2);
+            }
+            at_commit(o_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const int t_q = qt * kAtBM + row;
+        // ---- Q row -> TMEM: this warp stores elements [32 half, 32 half + 32) of its rows as 16 packed words ----
+        {
+            uint32_t w[16];
+            if (t_q < n_ctx) {
+                const uint4* src = reinterpret_cast<const uint4*>(qkv + ((int64_t)win * n_ctx + t_q) * 3 * d_model + head * kAtD + half * 32);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 u = __ldg(src + i);
+                    w[4 * i] = u.x; w[4 * i + 1] = u.y; w[4 * i + 2] = u.z; w[4 * i + 3] = u.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i] = 0u;
+            }
+            at_st16(tQ + lane_addr + half * 16, w);
+            at_wait_st();
+            at_fence_before();
+            __syncwarp();
+            if (lane == 0) at_mbar_arrive(q_full);
+        }
+        float m = -INFINITY;
+        // ---- pass 1: row maxima over this warp's 32 columns of every tile ----
+        for (int j = 0; j < n_kt; ++j) {
+            const int b1 = j % kS1;
+            at_mbar_wait(s1_full(b1), (uint32_t)(j / kS1) & 1u);
+            at_fence_after();
+            uint32_t v0[32];
+            at_ld32(tS0 + lane_addr + b1 * BN + half * 32, v0);
+            at_wait_ld();
+            at_fence_before();
+            __syncwarp();
+            if (lane == 0) at_mbar_arrive(s1_empty(b1));
+            const int k0 = j * BN + half * 32;
+            if (k0 + 32 <= n_ctx) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v0[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (k0 + i < n_ctx) m = fmaxf(m, __uint_as_float(v0[i]));
+            }
+        }
+        xch[half * 128 + row] = m;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        m = fmaxf(xch[row], xch[128 + row]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // ---- pass 2 ----
+        const float ms = m * scale_log2e;
+        float l = 0.f;
+        for (int j = 0; j < n_kt; ++j) {
+            const int sb = j & 1;
+            at_mbar_wait(s_full(sb), (uint32_t)(j >> 1) & 1u);
+            at_fence_after();
+            uint32_t v[32];
+            at_ld32(tS0 + lane_addr + sb * BN + half * 32, v);
+            at_wait_ld();
+            const int k0 = j * BN + half * 32;
+            uint32_t pk[16];
+            if (k0 + 32 <= n_ctx) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float p0 = at_ex2(fmaf(__uint_as_float(v[2 * i]), scale_log2e, -ms));
+                    const float p1 = at_ex2(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -ms));
+                    l += p0 + p1;
+                    pk[i] = Op16<T>::pack2(p0, p1);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float p0 = at_ex2(fmaf(__uint_as_float(v[2 * i]), scale_log2e, -ms));
+                    float p1 = at_ex2(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -ms));
+                    if (k0 + 2 * i >= n_ctx) p0 = 0.f;
+                    if (k0 + 2 * i + 1 >= n_ctx) p1 = 0.f;
+                    l += p0 + p1;
+                    pk[i] = Op16<T>::pack2(p0, p1);
+                }
+            }
+            at_st16(tS0 + lane_addr + sb * BN + half * 32, pk);
+            at_wait_st();
+            at_fence_before();
+            __syncwarp();
+            if (lane == 0) at_mbar_arrive(p_full(sb));
+        }
+        xch[half * 128 + row] = l;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        l = xch[row] + xch[128 + row];
+        // ---- epilogue: O / l, each warp stores 32 of the 64 head dims ----
+        at_mbar_wait(o_full, 0);
+        at_fence_after();
+        const float inv = 1.0f / l;
+        T* orow = out + ((int64_t)win * n_ctx + t_q) * d_model + head * kAtD + half * 32;
+        {
+            uint32_t v[32];
+            at_ld32(tO + lane_addr + half * 32, v);
+            at_wait_ld();
+            if (t_q < n_ctx) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 u;
+                    u.x = Op16<T>::pack2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+                    u.y = Op16<T>::pack2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+                    u.z = Op16<T>::pack2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+                    u.w = Op16<T>::pack2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+                    *reinterpret_cast<uint4*>(orow + i) = u;
+                }
+            }
+        }
+        at_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        at_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+    }
+}
+
+template <typename T>
+static int attn_enc_ts_launch(const T* qkv, T* out, int n_windows, int n_ctx, int d_model, int n_head, cudaStream_t st) {
+    CUtensorMap tkv;
+    const int is_f16 = std::is_same<T, __half>::value ? 1 : 0;
+    int rc = make_tmap_2d(&tkv, qkv, is_f16, (int64_t)n_windows * n_ctx, 3 * (int64_t)d_model, 3 * (int64_t)d_model, 64);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_attn_enc_ts<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem));
+        attr_done = true;
+    }
+    dim3 grid(ceil_div(n_ctx, kAtBM), n_head, n_windows);
+    const float scale_log2e = (1.0f / 8.0f) * 1.4426950408889634f;
+    k_attn_enc_ts<T><<<grid, kAtThreads, kTsSmem, st>>>(tkv, qkv, out, n_ctx, d_model, scale_log2e);
+    g_launches += 1;
+    SB_CUDA_CHECK(cudaGetLastError());
+    return SB_OK;
+}
+
 static int attn_bn() { const char* e = getenv("SB_ATTN_BN"); return (e && atoi(e) == 128) ? 128 : 64; }
 
 template <typename T, int BN>
@@ -395,7 +728,8 @@ static int attn_enc_tc_launch(const T* qkv, T* out, int n_windows, int n_ctx, in
     }
     dim3 grid(ceil_div(n_ctx, kAtBM), n_head, n_windows);
     const float scale_log2e = (1.0f / 8.0f) * 1.4426950408889634f;
-    k_attn_enc_tc<T, BN><<<grid, kAtThreads, AtCfg<BN>::kSmem, st>>>(tq, tkv, out, n_ctx, d_model, scale_log2e);
+    static int mma_sleep = [] { const char* e = getenv("SB_ATTN_SLEEP"); return e ? atoi(e) : 64; }();
+    k_attn_enc_tc<T, BN><<<grid, kAtThreads, AtCfg<BN>::kSmem, st>>>(tq, tkv, out, n_ctx, d_model, scale_log2e, mma_sleep);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
@@ -404,6 +738,8 @@ static int attn_enc_tc_launch(const T* qkv, T* out, int n_windows, int n_ctx, in
 template <typename T>
 int attn_enc_tc(const T* qkv, T* out, int n_windows, int n_ctx, int d_model, int n_head, cudaStream_t st) {
     SB_CHECK_ARG(d_model == n_head * kAtD, "attention: d_head must be 64");
+    static const bool ts = [] { const char* e = getenv("SB_ATTN_TS"); return !(e && e[0] == '0'); }();    // SB_ATTN_TS=0: P/Q through shared memory
+    if (ts) return attn_enc_ts_launch<T>(qkv, out, n_windows, n_ctx, d_model, n_head, st);
     if (attn_bn() == 128) return attn_enc_tc_launch<T, 128>(qkv, out, n_windows, n_ctx, d_model, n_head, st);
     return attn_enc_tc_launch<T, 64>(qkv, out, n_windows, n_ctx, d_model, n_head, st);
 }
