@@ -101,6 +101,16 @@ SB_API int sb_resample_geometry(const sb_resampler* r, size_t n_in, size_t* n_fe
 SB_API int sb_resample_dev(const sb_resampler* r, const float* in, int64_t in_stride, size_t n_in,
                            int n_streams, float* out, int64_t out_stride, void* stream);
 
+/* Mono down-mix of interleaved capture frames.  Replaces the cpal input callback of
+ * AudioRecorder::build_stream (audio_toolkit/audio/recorder.rs:182-201): every sample goes through cpal's
+ * to_sample::<f32>() (i16: x / 32768, u16: (x - 32768) / 32768, f32: identity), a frame becomes the f32 sum
+ * of its channels in channel order divided by the channel count; channels == 1 is a plain conversion.
+ *   in  [n_streams][in_stride elements] interleaved, n_frames * channels valid per stream
+ *   out [n_streams][out_stride] f32, n_frames valid; device pointers, async on `stream` */
+typedef enum sb_sample_format { SB_SAMPLE_F32 = 0, SB_SAMPLE_I16 = 1, SB_SAMPLE_U16 = 2 } sb_sample_format;
+SB_API int sb_downmix_mono_dev(const void* in, int sample_format, int channels, int64_t in_stride, size_t n_frames,
+                               int n_streams, float* out, int64_t out_stride, void* stream);
+
 /* Silero VAD v4 (16 kHz branch).  Replaces vad_rs::Vad::{new, compute} over onnxruntime
  * (audio_toolkit/vad/silero.rs:25,41-44).  blob: the f32 tensors of the model in the order of
  * spittle_b200/silero_weights.py BLOB_LAYOUT (read from the reference's silero_vad_v4.onnx).
@@ -213,6 +223,8 @@ typedef struct sb_result {
     sb_window_info* windows; size_t n_windows;
     float ms_mel, ms_encode, ms_decode;    /* device time of the batch this clip was part of */
     int status;                            /* per-clip sb_status (batch API) */
+    int lang_id;                           /* whisper language id used for the prompt (detected when params.language is NULL /
+                                              "auto", like whisper_full); -1 for English-only models */
 } sb_result;
 
 /* Cumulative engine counters (bench.py): device times are CUDA-event brackets on the engine's

@@ -69,3 +69,23 @@ def stop_recording_pad(samples: np.ndarray, rate: int = 16000) -> np.ndarray:
         out[:n] = samples
         return out
     return samples
+
+
+def downmix_mono(interleaved: np.ndarray, channels: int) -> np.ndarray:
+    """cpal input callback of AudioRecorder::build_stream (audio/recorder.rs:182-201): to_sample::<f32>()
+    per sample (i16: x / 32768, u16: (x - 32768) / 32768, f32: identity), then per frame the f32 sum over the
+    channels in order, divided by the channel count.  Bit-exact f32 arithmetic."""
+    x = np.asarray(interleaved)
+    if x.dtype == np.int16:
+        f = x.astype(np.float32) / np.float32(32768.0)
+    elif x.dtype == np.uint16:
+        f = (x.astype(np.int32) - 32768).astype(np.float32) / np.float32(32768.0)
+    else:
+        f = x.astype(np.float32)
+    if channels == 1:
+        return f.copy()
+    fr = f[: (f.shape[0] // channels) * channels].reshape(-1, channels)
+    acc = np.zeros(fr.shape[0], np.float32)
+    for c in range(channels):
+        acc = (acc + fr[:, c]).astype(np.float32)
+    return (acc / np.float32(channels)).astype(np.float32)

@@ -22,6 +22,7 @@ model used as "truth" for stating the bf16 tolerance of the GPU path.
 """
 from __future__ import annotations
 
+import dataclasses
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -58,7 +59,7 @@ def softmax_rows(s: np.ndarray) -> np.ndarray:
 
 @dataclass
 class DecodeConfig:
-    language_id: int = 0          # "en" -> <|en|> = sot + 1 + 0
+    language_id: int = 0          # "en" -> <|en|> = sot + 1 + 0; -1 = auto-detect on the first window (reference default "auto")
     translate: bool = False
     no_timestamps: bool = False
     suppress_blank: bool = True
@@ -333,6 +334,18 @@ class WhisperOracle:
             n_past += 1
         return WindowResult(tokens, result_len, seek_delta, failed, tr if trace else None, margins)
 
+    def detect_language(self, enc: np.ndarray):
+        """whisper.cpp whisper_lang_auto_detect_with_state (App. C.4 / reference default selected_language
+        "auto", settings.rs:427-429): decode [sot] alone, softmax over the language tokens only, pick the
+        most probable (lowest id on ties).  Returns (language id, probabilities)."""
+        hp, sp = self.hp, self.sp
+        assert hp.n_vocab >= 51865, "English-only models have no language tokens"
+        logits = self.decode_step(sp.sot, 0, self.new_kv(), self.cross_kv(enc))
+        lg = logits[sp.lang_first: sp.lang_first + sp.num_languages].astype(np.float64)
+        p = np.exp(lg - lg.max())
+        p /= p.sum()
+        return int(np.argmax(lg)), p
+
     # -- whisper_full ------------------------------------------------------------------
     def full(self, samples: np.ndarray, cfg: Optional[DecodeConfig] = None, max_windows: int = 64):
         """Returns (text_bytes, all_tokens_kept, per_window WindowResult list)."""
@@ -352,6 +365,10 @@ class WhisperOracle:
             if seek + 100 >= seek_end:
                 break
             enc = self.encode(_logmel.mel_window(mel, seek, self.hp.n_audio_ctx))
+            if cfg.language_id < 0:                       # whisper_full detects once, at offset 0, before the seek loop
+                lang, _ = self.detect_language(enc) if self.hp.n_vocab >= 51865 else (0, None)
+                cfg = dataclasses.replace(cfg, language_id=lang)
+                self.last_detected_language = lang
             w = self.decode_window(enc, seek, seek_end, cfg)
             windows.append(w)
             toks = w.tokens[: w.result_len]

@@ -158,7 +158,7 @@ class SbResult(C.Structure):
                 ("margins", C.POINTER(C.c_float)),
                 ("windows", C.POINTER(SbWindowInfo)), ("n_windows", C.c_size_t),
                 ("ms_mel", C.c_float), ("ms_encode", C.c_float), ("ms_decode", C.c_float),
-                ("status", C.c_int)]
+                ("status", C.c_int), ("lang_id", C.c_int)]
 
 
 def _declare_engine(l: C.CDLL) -> None:
@@ -199,6 +199,7 @@ class ClipResult:
                         for w in (r.windows[i] for i in range(r.n_windows))]
         self.ms_mel, self.ms_encode, self.ms_decode = r.ms_mel, r.ms_encode, r.ms_decode
         self.status = r.status
+        self.lang_id = r.lang_id
 
 
 def default_params(**kw) -> SbParams:
@@ -314,6 +315,7 @@ class Engine:
 # ---------------------------------------------------------------------------------------
 def _declare_frontend(l: C.CDLL) -> None:
     vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+    l.sb_downmix_mono_dev.argtypes = [vp, i32, i32, i64, sz, i32, vp, i64, vp]
     l.sb_resampler_create.argtypes = [i32, i32, C.POINTER(vp)]
     l.sb_resampler_destroy.argtypes = [vp]
     l.sb_resample_geometry.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
@@ -378,6 +380,15 @@ class Vad:
             self.close()
         except Exception:
             pass
+
+
+SB_SAMPLE_F32, SB_SAMPLE_I16, SB_SAMPLE_U16 = 0, 1, 2
+
+
+def downmix_mono_dev(in_ptr, sample_format: int, channels: int, in_stride: int, n_frames: int, n_streams: int, out_ptr,
+                     out_stride: int, stream=None) -> None:
+    check(lib().sb_downmix_mono_dev(in_ptr, sample_format, channels, in_stride, n_frames, n_streams, out_ptr, out_stride,
+                                    stream or None))
 
 
 def vad_gate_workspace_bytes(n_streams: int, n_frames: int) -> int:

@@ -38,7 +38,7 @@ struct SamplerArgs {
     int single_segment;
     int max_initial_tid;      // round(max_initial_ts / 0.02), < 0 disables the rule
     const int* pos_ptr;       // device: position of the token just fed to the decoder
-    const int* prompt;        // device: prompt tokens
+    const int* prompt;        // device: prompt tokens [B][n_prompt] (per sequence: the language token may differ)
     int n_prompt;
 };
 
@@ -128,6 +128,9 @@ template <typename T> int dec_ln(float* x, const float* gamma, const float* beta
 template <typename T> int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const int* pos_ptr, const SeqState* state, int Bn, int n_head, int d, int n_text_ctx, cudaStream_t st);
 template <typename T> int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t ld_kv, int64_t win_stride, T* out, const SeqState* state, int Bn, int n_head, int d, int n_ctx, const FusedQ& fq, cudaStream_t st);
 int sample_step(const float* logits, int ld, const SamplerArgs& a, int Bn, cudaStream_t st);
+// whisper_lang_auto_detect: at decode position 0 ([sot] only) pick the language token with the largest logit and
+// write it into prompt slot 1 of every sequence whose slot holds the sentinel -1 (no-op at any other position)
+int lang_detect_step(const float* logits, int ld, int* prompt, int n_prompt, const int* pos_ptr, int* lang_out, SpecialIds sp, int Bn, cudaStream_t st);
 int dec_advance(int* pos_ptr, int* step_ptr, int n_prompt, unsigned* barrier, cudaStream_t st);
 
 }  // namespace sb

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
     const int step = __ldcg(a.step_ptr);   // index of the token being sampled (i in whisper_full)
     const int pos = __ldcg(a.pos_ptr);
     if (pos < a.n_prompt - 1) {            // still feeding the prompt: queue its next token
-        if (threadIdx.x == 0) a.next_tokens[b] = a.prompt[pos + 1];
+        if (threadIdx.x == 0) a.next_tokens[b] = __ldcg(a.prompt + (int64_t)b * a.n_prompt + pos + 1);
         return;
     }
     if (st.done) return;
@@ -313,6 +313,34 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
     a.state[b] = st;
 }
 
+// language auto-detect (whisper.cpp whisper_lang_auto_detect_with_state): the decoder has seen [sot] only;
+// among the language tokens the one with the largest raw logit (= largest softmax probability; lowest id on
+// ties) becomes prompt token 1 of the sequence.  One warp per sequence.
+__global__ void __launch_bounds__(32) k_lang_detect(const float* __restrict__ logits, int ld, int* __restrict__ prompt, int n_prompt,
+                                                    const int* __restrict__ pos_ptr, int* __restrict__ lang_out, SpecialIds sp) {
+    pdl_wait();
+    pdl_trigger();
+    if (__ldcg(pos_ptr) != 0) return;
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (__ldcg(prompt + (int64_t)b * n_prompt + 1) >= 0) return;       // language given (or detected on an earlier window)
+    const float* lg = logits + (int64_t)b * ld + sp.lang_first;
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int i = lane; i < sp.num_languages; i += 32) {
+        const float x = __ldcg(lg + i);
+        if (x > bv) { bv = x; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (v2 > bv || (v2 == bv && i2 < bi)) { bv = v2; bi = i2; }
+    }
+    if (lane == 0) {
+        prompt[(int64_t)b * n_prompt + 1] = sp.lang_first + bi;
+        if (lang_out) lang_out[b] = bi;
+    }
+}
+
 // advance the shared position / step counters (single thread) after a step
 __global__ void k_dec_advance(int* pos_ptr, int* step_ptr, int n_prompt, unsigned* barrier) {
     pdl_wait();
@@ -385,6 +413,14 @@ int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t 
 }
 int sample_step(const float* logits, int ld, const SamplerArgs& a, int Bn, cudaStream_t st) {
         launch_pdl(k_logits_filter_argmax, dim3(Bn), dim3(kSampThreads), 0, st, logits, ld, a);
+    g_launches += 1;
+    SB_CUDA_CHECK(cudaGetLastError());
+    return SB_OK;
+}
+int lang_detect_step(const float* logits, int ld, int* prompt, int n_prompt, const int* pos_ptr, int* lang_out, SpecialIds sp, int Bn,
+                     cudaStream_t st) {
+    SB_CHECK_ARG(n_prompt >= 2 && sp.num_languages > 0, "language auto-detect needs a multilingual model");
+    launch_pdl(k_lang_detect, dim3(Bn), dim3(32), 0, st, logits, ld, prompt, n_prompt, pos_ptr, lang_out, sp);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;

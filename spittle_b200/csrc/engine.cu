@@ -495,6 +495,7 @@ struct Engine : EngineBase {
             if ((rc = dec_step_mega<T>(b_declayers.as<DecLayerDev>(), ma, sl))) return rc;
             GemmEpilogue ge{logits, vpad, 1, nullptr, 0, nullptr, 0, 0};
             if ((rc = gemm_tn(dtype, dh, d, tok_emb, d, Wl, vpad, d, ge, sl))) return rc;
+            if (detect_lang && (rc = lang_detect_step(logits, vpad, const_cast<int*>(sa.prompt), sa.n_prompt, pos_ptr, detect_out + w0, sp, Wl, sl))) return rc;
             if ((rc = sample_step(logits, vpad, sa, Wl, sl))) return rc;
             return dec_advance(pos_ptr, step_ptr, sa.n_prompt, ma.barrier, sl);
         }
@@ -557,15 +558,19 @@ struct Engine : EngineBase {
         // (one 128-row tile of sequences, ~200 column tiles) instead of the small-N weight-streaming kernel
         GemmEpilogue ge{logits, vpad, 1, nullptr, 0, nullptr, 0, 0};
         if ((rc = gemm_tn(dtype, dh, d, tok_emb, d, Wl, vpad, d, ge, sl))) return rc;
+        if (detect_lang && (rc = lang_detect_step(logits, vpad, const_cast<int*>(sa.prompt), sa.n_prompt, pos_ptr, detect_out + w0, sp, Wl, sl))) return rc;
         if ((rc = sample_step(logits, vpad, sa, Wl, sl))) return rc;
         if ((rc = dec_advance(pos_ptr, step_ptr, sa.n_prompt, nullptr, sl))) return rc;
         return SB_OK;
     }
 
-    struct DecodeOut { std::vector<SeqState> state; std::vector<int> tokens; std::vector<float> margins; int n_max = 0; };
+    struct DecodeOut { std::vector<SeqState> state; std::vector<int> tokens; std::vector<float> margins; std::vector<int> langs; int n_max = 0; };
+    bool detect_lang = false; int* detect_out = nullptr;     // set by decode() for enqueue_step
+    bool auto_mode = false;                                  // current transcribe_batch call asked for language auto-detect
 
     // decode W windows whose cross-KV occupies rows [0, W*1500) of b_ckv
-    int decode(int W, const std::vector<int>& seek, const std::vector<int>& seek_end, const sb_params& p, int lang,
+    // langs[w]: language id of window w's prompt, or < 0: detect it at decode position 0 (reference default "auto")
+    int decode(int W, const std::vector<int>& seek, const std::vector<int>& seek_end, const sb_params& p, const std::vector<int>& langs,
                const int32_t* forced_host, int n_steps_cap, float* logits_out, DecodeOut& out) {
         int n_max = hp.n_text_ctx / 2 - 4;
         if (p.n_max_tokens > 0) n_max = std::min(n_max, p.n_max_tokens);
@@ -574,16 +579,28 @@ struct Engine : EngineBase {
         int rc = ensure_decoder_ws(W, n_max);
         if (rc) return rc;
         std::vector<int> prompt = {sp.sot};
-        if (hp.n_vocab >= 51865) { prompt.push_back(sp.lang_first + lang); prompt.push_back(p.translate ? sp.translate : sp.transcribe); }
+        if (hp.n_vocab >= 51865) { prompt.push_back(sp.lang_first); prompt.push_back(p.translate ? sp.translate : sp.transcribe); }
         if (p.no_timestamps) prompt.push_back(sp.not_);
         const int n_prompt = (int)prompt.size();
+        bool detect = false;
+        std::vector<int> prompts((size_t)W * n_prompt);
+        for (int w = 0; w < W; ++w) {
+            for (int i = 0; i < n_prompt; ++i) prompts[(size_t)w * n_prompt + i] = prompt[i];
+            if (n_prompt >= 2) {
+                if (langs[w] < 0) { detect = true; prompts[(size_t)w * n_prompt + 1] = -1; }     // sentinel: k_lang_detect fills it
+                else prompts[(size_t)w * n_prompt + 1] = sp.lang_first + langs[w];
+            }
+        }
+        if ((rc = b_prompt.ensure((size_t)W * n_prompt * 4 + (size_t)W * 4))) return rc;
+        int* d_lang = b_prompt.as<int>() + (size_t)W * n_prompt;      // detected language ids [W]
         std::vector<SeqState> hs(W);
         for (int w = 0; w < W; ++w) {
             SeqState s{}; s.seek_delta = 3000; s.seek = seek[w]; s.seek_end = seek_end[w];
             hs[w] = s;
         }
         SB_CUDA_CHECK(cudaMemcpyAsync(b_state.p, hs.data(), W * sizeof(SeqState), cudaMemcpyHostToDevice, st));
-        SB_CUDA_CHECK(cudaMemcpyAsync(b_prompt.p, prompt.data(), n_prompt * 4, cudaMemcpyHostToDevice, st));
+        SB_CUDA_CHECK(cudaMemcpyAsync(b_prompt.p, prompts.data(), prompts.size() * 4, cudaMemcpyHostToDevice, st));
+        SB_CUDA_CHECK(cudaMemsetAsync(d_lang, 0xff, (size_t)W * 4, st));
         SB_CUDA_CHECK(cudaMemsetAsync(b_ctr.p, 0, 64 * kMaxLanes, st));
         SB_CUDA_CHECK(cudaMemsetAsync(b_tokens.p, 0xff, (size_t)W * n_max * 4, st));
         SB_CUDA_CHECK(cudaMemsetAsync(b_margins.p, 0, (size_t)W * n_max * 4, st));
@@ -596,6 +613,11 @@ struct Engine : EngineBase {
         sa0.suppress_blank = p.suppress_blank; sa0.no_timestamps = p.no_timestamps; sa0.single_segment = p.single_segment;
         sa0.max_initial_tid = p.max_initial_ts > 0.f ? (int)lroundf(p.max_initial_ts / (30.0f / hp.n_audio_ctx)) : -1;
         sa0.prompt = b_prompt.as<int>(); sa0.n_prompt = n_prompt;
+        // the detect launch stays in the step graph for the whole call once auto-detect was requested (it is a no-op for
+        // sequences whose language is known), so later seek-loop rounds reuse the captured graph
+        if (detect) auto_mode = true;
+        detect = auto_mode && n_prompt >= 2;
+        detect_lang = detect; detect_out = d_lang;
 
         const int total_steps = n_prompt - 1 + n_max;
         const bool graph = use_graph && !logits_out;
@@ -639,6 +661,7 @@ struct Engine : EngineBase {
             sa.forced = forced_host ? b_forced.as<int>() + (size_t)w0 * n_max : nullptr;
             sa.n_done = ctr + 2;
             sa.pos_ptr = ctr;
+            sa.prompt = b_prompt.as<int>() + (size_t)w0 * n_prompt;
             return sa;
         };
         // fork: every lane stream waits for the setup work queued on the main stream
@@ -648,7 +671,7 @@ struct Engine : EngineBase {
             for (int i = 0; i < n_lanes; ++i) {
                 Lane& L = lanes[i];
                 GraphKey k{W, lr[i].w0, lr[i].Wl, n_max,
-                           (p.suppress_blank ? 1 : 0) | (p.no_timestamps ? 2 : 0) | (p.single_segment ? 4 : 0),
+                           (p.suppress_blank ? 1 : 0) | (p.no_timestamps ? 2 : 0) | (p.single_segment ? 4 : 0) | (detect ? 8 : 0),
                            sa0.max_initial_tid, n_prompt, forced_host ? 1 : 0, g_ws_gen.load()};
                 if (L.gexec && k == L.key) continue;
                 if (L.gexec) { cudaGraphExecDestroy(L.gexec); L.gexec = nullptr; }
@@ -700,6 +723,8 @@ struct Engine : EngineBase {
             SB_CUDA_CHECK(cudaStreamWaitEvent(st, lanes[i].done, 0));
         }
         out.state.resize(W); out.tokens.resize((size_t)W * n_max); out.margins.resize((size_t)W * n_max);
+        out.langs.assign(W, -1);
+        if (detect) SB_CUDA_CHECK(cudaMemcpyAsync(out.langs.data(), d_lang, (size_t)W * 4, cudaMemcpyDeviceToHost, st));     // -1 where nothing was detected
         SB_CUDA_CHECK(cudaMemcpyAsync(out.state.data(), b_state.p, W * sizeof(SeqState), cudaMemcpyDeviceToHost, st));
         SB_CUDA_CHECK(cudaMemcpyAsync(out.tokens.data(), b_tokens.p, (size_t)W * n_max * 4, cudaMemcpyDeviceToHost, st));
         SB_CUDA_CHECK(cudaMemcpyAsync(out.margins.data(), b_margins.p, (size_t)W * n_max * 4, cudaMemcpyDeviceToHost, st));
@@ -710,13 +735,15 @@ struct Engine : EngineBase {
     }
 
     int resolve_language(const sb_params& p, int* lang) {
-        if (!p.language) { set_error("language auto-detect (reference \"auto\") is not implemented yet; pass a language code"); return SB_ERR_UNSUPPORTED; }
+        if (p.initial_prompt && p.initial_prompt[0]) { set_error("initial_prompt is not implemented yet (needs the BPE encoder)"); return SB_ERR_UNSUPPORTED; }
+        // NULL / "" / "auto": whisper_full detects the language on the first window (multilingual models);
+        // English-only models have no language token at all
+        if (!p.language || !p.language[0] || std::string(p.language) == "auto") { *lang = hp.n_vocab >= 51865 ? -1 : 0; return SB_OK; }
         std::string l = p.language;
         if (l == "zh-Hans" || l == "zh-Hant") l = "zh";   // reference: transcription.rs:448-459
         const int id = lang_id(l.c_str());
         if (id < 0 || (hp.n_vocab >= 51865 && id >= sp.num_languages)) { set_error("unknown language code: " + l); return SB_ERR_INVALID; }
         *lang = id;
-        if (p.initial_prompt && p.initial_prompt[0]) { set_error("initial_prompt is not implemented yet (needs the BPE encoder)"); return SB_ERR_UNSUPPORTED; }
         return SB_OK;
     }
 
@@ -760,12 +787,13 @@ struct Engine : EngineBase {
         int lang = 0;
         int rc = resolve_language(p, &lang);
         if (rc) return rc;
+        auto_mode = lang < 0;
         if ((rc = ensure_encoder_ws(W, W, false))) return rc;
         if ((rc = stage_mel_windows(mel_windows, W))) return rc;
         if ((rc = encode_chunk(W, 0, nullptr))) return rc;
         std::vector<int> seek(W, 0), se(seek_end, seek_end + W);
         DecodeOut out;
-        if ((rc = decode(W, seek, se, p, lang, forced, n_steps, logits_out, out))) return rc;
+        if ((rc = decode(W, seek, se, p, std::vector<int>(W, lang), forced, n_steps, logits_out, out))) return rc;
         prof_collect();
         if (out.n_max != n_steps) { set_error("n_steps exceeds n_text_ctx/2 - 4"); return SB_ERR_INVALID; }
         memcpy(tokens_out, out.tokens.data(), (size_t)W * n_steps * 4);
@@ -776,7 +804,7 @@ struct Engine : EngineBase {
     // ---- whisper_full over a group of <= max_batch clips -------------------------------------
     struct ClipRun {
         size_t n = 0; int n_len = 0, n_len_org = 0, n_calc = 0;
-        int seek = 0; bool active = false;
+        int seek = 0; bool active = false; int lang = 0;
         std::vector<int32_t> kept, sampled; std::vector<float> margins; std::vector<sb_window_info> windows;
         std::string text;
     };
@@ -788,6 +816,7 @@ struct Engine : EngineBase {
         for (int c = 0; c < G; ++c) {
             ClipRun& r = clips[c];
             r.n = ns[c];
+            r.lang = lang;
             if (r.n == 0) continue;
             sb_logmel_geometry(r.n, &r.n_len, &r.n_len_org, &r.n_calc);
             // whisper.cpp: "input is too short" below 1 s -> no segments
@@ -836,12 +865,12 @@ struct Engine : EngineBase {
             // seek loop: every round encodes + decodes one window of every clip that still has audio
             const int max_windows = p.max_windows > 0 ? p.max_windows : 1 << 20;
             for (;;) {
-                std::vector<int> wclip, wseek, wend;
+                std::vector<int> wclip, wseek, wend, wlang;
                 for (int c = 0; c < G; ++c) {
                     ClipRun& r = clips[c];
                     if (!r.active) continue;
                     if (r.seek + 100 >= r.n_len_org || (int)r.windows.size() >= max_windows) { r.active = false; continue; }
-                    wclip.push_back(c); wseek.push_back(r.seek); wend.push_back(r.n_len_org);
+                    wclip.push_back(c); wseek.push_back(r.seek); wend.push_back(r.n_len_org); wlang.push_back(r.lang);
                 }
                 const int W = (int)wclip.size();
                 if (W == 0) break;
@@ -857,7 +886,7 @@ struct Engine : EngineBase {
                 if ((rc = encode_chunk(W, 0, nullptr))) return rc;
                 SB_CUDA_CHECK(cudaEventRecord(ev[1], st));
                 DecodeOut d;
-                if ((rc = decode(W, wseek, wend, p, lang, nullptr, 0, nullptr, d))) return rc;
+                if ((rc = decode(W, wseek, wend, p, wlang, nullptr, 0, nullptr, d))) return rc;
                 SB_CUDA_CHECK(cudaEventRecord(ev[2], st));
                 SB_CUDA_CHECK(cudaStreamSynchronize(st));
                 { float t; cudaEventElapsedTime(&t, ev[0], ev[1]); ms_enc += t; cudaEventElapsedTime(&t, ev[1], ev[2]); ms_dec += t; }
@@ -865,6 +894,7 @@ struct Engine : EngineBase {
                 stats.windows += W; stats.rounds += 1;
                 for (int w = 0; w < W; ++w) {
                     ClipRun& r = clips[wclip[w]];
+                    if (r.lang < 0) r.lang = d.langs[w] >= 0 ? d.langs[w] : 0;     // detected on the clip's first window
                     const SeqState& s = d.state[w];
                     sb_window_info wi{};
                     wi.seek = r.seek; wi.n_tokens = s.n_tok; wi.result_len = s.result_len; wi.seek_delta = s.seek_delta;
@@ -897,6 +927,7 @@ struct Engine : EngineBase {
             o.margins = (float*)dup(r.margins.data(), r.margins.size() * 4);
             o.n_windows = r.windows.size(); o.windows = (sb_window_info*)dup(r.windows.data(), r.windows.size() * sizeof(sb_window_info));
             o.ms_mel = ms_mel; o.ms_encode = ms_enc; o.ms_decode = ms_dec; o.status = SB_OK;
+            o.lang_id = hp.n_vocab >= 51865 ? r.lang : -1;
             stats.tokens_sampled += (double)r.sampled.size();
         }
         stats.mel_ms += ms_mel; stats.encode_ms += ms_enc; stats.decode_ms += ms_dec; stats.clips += G;
@@ -908,6 +939,7 @@ struct Engine : EngineBase {
         int lang = 0;
         int rc = resolve_language(p, &lang);
         if (rc) return rc;
+        auto_mode = lang < 0;
         for (size_t c0 = 0; c0 < count; c0 += max_batch) {
             const int G = (int)std::min<size_t>(max_batch, count - c0);
             if ((rc = run_group(pcm + c0, ns + c0, G, p, lang, out + c0))) return rc;

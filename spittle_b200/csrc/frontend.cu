@@ -21,6 +21,32 @@ namespace sb {
 extern std::atomic<uint64_t> g_launches;
 
 // ------------------------------------------------------------------------------------------
+// mono down-mix (row a14): out[f] = (sum_c to_f32(in[f * C + c])) / C, f32 sum in channel order like the
+// reference's iterator sum.  HBM-bound: C * sizeof(S) + 4 bytes per frame; consecutive threads take
+// consecutive frames, so a warp reads one contiguous span of 32 * C samples.
+// ------------------------------------------------------------------------------------------
+template <typename S> __device__ __forceinline__ float to_sample_f32(S v);
+template <> __device__ __forceinline__ float to_sample_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_sample_f32<int16_t>(int16_t v) { return (float)v * (1.0f / 32768.0f); }
+template <> __device__ __forceinline__ float to_sample_f32<uint16_t>(uint16_t v) { return (float)((int)v - 32768) * (1.0f / 32768.0f); }
+
+template <typename S>
+__global__ void __launch_bounds__(256) k_downmix_mono(const S* __restrict__ in, int channels, int64_t in_stride, int64_t n_frames,
+                                                      float* __restrict__ out, int64_t out_stride) {
+    const S* src = in + (int64_t)blockIdx.y * in_stride;
+    float* dst = out + (int64_t)blockIdx.y * out_stride;
+    const float inv = 1.0f / (float)channels;
+    for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_frames; f += (int64_t)gridDim.x * blockDim.x) {
+        const S* fr = src + f * channels;
+        if (channels == 1) { dst[f] = to_sample_f32<S>(__ldg(fr)); continue; }
+        float a = 0.f;
+        for (int c = 0; c < channels; ++c) a += to_sample_f32<S>(__ldg(fr + c));
+        dst[f] = a / (float)channels;
+        (void)inv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // polyphase decimating FIR:  y[m] = sum_k h[k] x[D m - k],  x = 0 outside [0, n_in)
 // ------------------------------------------------------------------------------------------
 constexpr int kFirTile = 1024;     // outputs per CTA
@@ -615,3 +641,23 @@ int sb_vad_gate_dev(const float* probs, const float* pcm16k, int64_t pcm_stride,
 }
 
 }  // extern "C"
+
+extern "C" int sb_downmix_mono_dev(const void* in, int sample_format, int channels, int64_t in_stride, size_t n_frames, int n_streams,
+                                   float* out, int64_t out_stride, void* stream) {
+    SB_CHECK_ARG(in && out, "null pointer");
+    SB_CHECK_ARG(channels >= 1 && channels <= 64 && n_streams >= 1 && n_streams <= 65535, "channels in [1, 64], n_streams in [1, 65535]");
+    SB_CHECK_ARG(in_stride >= (int64_t)n_frames * channels && out_stride >= (int64_t)n_frames, "strides too small");
+    if (n_frames == 0) return SB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int bx = (int)std::min<size_t>((n_frames + 255) / 256, 148 * 8);
+    dim3 grid(bx, n_streams);
+    switch (sample_format) {
+        case SB_SAMPLE_F32: sb::k_downmix_mono<float><<<grid, 256, 0, st>>>((const float*)in, channels, in_stride, (int64_t)n_frames, out, out_stride); break;
+        case SB_SAMPLE_I16: sb::k_downmix_mono<int16_t><<<grid, 256, 0, st>>>((const int16_t*)in, channels, in_stride, (int64_t)n_frames, out, out_stride); break;
+        case SB_SAMPLE_U16: sb::k_downmix_mono<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)in, channels, in_stride, (int64_t)n_frames, out, out_stride); break;
+        default: sb::set_error("invalid argument: sample_format"); return SB_ERR_INVALID;
+    }
+    sb::g_launches += 1;
+    SB_CUDA_CHECK(cudaGetLastError());
+    return SB_OK;
+}

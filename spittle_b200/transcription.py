@@ -14,7 +14,7 @@ from typing import Callable, Dict, List, Optional
 
 import numpy as np
 
-from . import capi
+from . import capi, text_filters
 
 
 class TranscriptionError(RuntimeError):
@@ -29,6 +29,7 @@ class Settings:
     translate_to_english: bool = False
     model_unload_timeout: str = "never"      # "never" | "immediately" | seconds as str
     custom_words: List[str] = field(default_factory=list)
+    word_correction_threshold: float = 0.18      # default_settings.json / settings.rs
     device: int = 0
     max_batch: int = 64
     dtype: int = capi.SB_DTYPE_F16
@@ -105,6 +106,15 @@ class TranscriptionManager:
         p.language = None if lang == "auto" else lang.encode()
         return p
 
+    @staticmethod
+    def _post_filter(text: str, s: Settings) -> str:
+        """transcription.rs:537-549: custom-word correction (only when configured), then the filler /
+        stutter / hallucination filter.  Jargon corrections (:552-580) are settings-driven string rules
+        outside this path's scope (off in the default settings)."""
+        if s.custom_words:
+            text = text_filters.apply_custom_words(text, s.custom_words, s.word_correction_threshold)
+        return text_filters.filter_transcription_output(text)
+
     def transcribe(self, audio) -> str:
         self._last_activity = time.time()
         a = np.ascontiguousarray(audio, dtype=np.float32)
@@ -122,8 +132,9 @@ class TranscriptionManager:
                 r = self._engine.transcribe(a, self._params(s))
             except capi.SbError as e:
                 raise TranscriptionError(f"Whisper transcription failed: {e}") from e
+        text = self._post_filter(r.text.decode("utf-8", errors="replace"), s)
         self.maybe_unload_immediately("transcription")
-        return r.text.decode("utf-8", errors="replace")
+        return text
 
     def transcribe_batch(self, clips) -> List[str]:
         self._last_activity = time.time()
@@ -135,4 +146,4 @@ class TranscriptionManager:
             if self._engine is None:
                 raise TranscriptionError("Model is not loaded for transcription.")
             res = self._engine.transcribe_batch(clips, self._params(s))
-        return [r.text.decode("utf-8", errors="replace") for r in res]
+        return [self._post_filter(r.text.decode("utf-8", errors="replace"), s) for r in res]

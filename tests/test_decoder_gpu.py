@@ -131,3 +131,41 @@ def test_step_megakernel_matches_stage_launches(cuda_dev, model_dir, monkeypatch
         assert a.sampled == b.sampled and a.tokens == b.tokens and a.text == b.text
         assert [w["n_tokens"] for w in a.windows] == [w["n_tokens"] for w in b.windows]
     assert any(len(set(w["n_tokens"] for w in r.windows)) > 0 for r in out["1"])
+
+
+def test_language_auto_detect_matches_oracle(cuda_dev, model_dir):
+    """params.language = NULL (the reference's default selected_language "auto", settings.rs:427-429):
+    whisper_full detects the language from the first window ([sot] step, arg-max over the language tokens)
+    and uses it for every window.  Detected ids and the resulting tokens must match the oracle."""
+    path = synth.ensure_model_file("nano", model_dir)
+    model = ggml_format.read_ggml(path)
+    oracle = whisper_ref.WhisperOracle(model, act_f16=True)
+    eng = capi.Engine(path, dtype=capi.SB_DTYPE_F16, max_batch=8)
+    clips = [synth.make_clip(i, s) for i, s in ((1, 30.0), (2, 9.0), (5, 30.0), (4, 12.0))]
+    params = capi.default_params(n_max_tokens=24, max_windows=2)
+    params.language = None
+    res = eng.transcribe_batch(clips, params)
+    n_exact = 0
+    for x, r in zip(clips, res):
+        mel, n_len_org = logmel.logmel_f32_faithful(x, model.mel_filters)
+        enc = oracle.encode(logmel.mel_window(mel, 0, oracle.hp.n_audio_ctx))
+        lang, probs = oracle.detect_language(enc)
+        top2 = np.sort(probs)[-2:]
+        if r.lang_id != lang:
+            assert top2[1] / top2[0] < 1.05, ("language mismatch at a decisive probability ratio", r.lang_id, lang, top2)
+            continue
+        text, kept, wins = oracle.full(x, whisper_ref.DecodeConfig(language_id=-1, n_max_override=24), max_windows=2)
+        got0 = r.sampled[: r.windows[0]["n_tokens"]]
+        if got0 == wins[0].tokens:
+            n_exact += 1
+        else:
+            first = next(k for k in range(min(len(got0), len(wins[0].tokens))) if got0[k] != wins[0].tokens[k])
+            assert wins[0].margins[first] < MARGIN_TOL[capi.SB_DTYPE_F16]
+    assert n_exact >= 2
+    # an explicit language still wins over detection, "auto" spelled out behaves like NULL
+    params.language = b"auto"
+    res2 = eng.transcribe_batch(clips[:2], params)
+    assert [r.lang_id for r in res2] == [r.lang_id for r in res[:2]] and res2[0].sampled == res[0].sampled
+    params.language = b"de"
+    assert eng.transcribe(clips[1], params).lang_id == 2          # whisper language table: en, zh, de, ...
+    eng.close()

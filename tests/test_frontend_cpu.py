@@ -95,3 +95,15 @@ def test_oracle_tokens_match_golden(gold):
     np.testing.assert_allclose(enc[::100, ::16], gold["nano_clip1_enc_grid"], atol=2e-3)
     w = oracle.decode_window(enc, 0, n_len_org, whisper_ref.DecodeConfig(n_max_override=16))
     assert w.tokens == list(gold["nano_clip1_tokens"])
+
+
+def test_downmix_oracle_known_answers():
+    """cpal to_sample conventions + channel mean (recorder.rs:182-201)."""
+    from oracle import vad_gate
+    x = np.array([32767, -32768, 0, 16384], np.int16)
+    assert np.array_equal(vad_gate.downmix_mono(x, 1), np.array([32767 / 32768, -1.0, 0.0, 0.5], np.float32))
+    assert np.array_equal(vad_gate.downmix_mono(x, 2), np.array([(32767 / 32768 - 1.0) / 2, 0.25], np.float32))
+    u = np.array([0, 32768, 65535], np.uint16)
+    assert np.array_equal(vad_gate.downmix_mono(u, 1), np.array([-1.0, 0.0, 32767 / 32768], np.float32))
+    f = np.array([0.1, 0.2, 0.3, 0.4, 0.5, 0.6], np.float32)
+    assert np.array_equal(vad_gate.downmix_mono(f, 3), ((f[0::3] + f[1::3]).astype(np.float32) + f[2::3]).astype(np.float32) / np.float32(3))

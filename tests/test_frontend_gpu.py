@@ -157,3 +157,29 @@ def test_capture_chain_matches_oracle(cuda_dev):
     assert n_same >= len(kinds) - 1
     assert got[2].size == 0                       # a pure tone never opens the gate
     assert audio_toolkit.stop_recording_pad(np.ones(10, np.float32)).shape == (20000,)
+
+
+@pytest.mark.parametrize("fmt,dtype", [(capi.SB_SAMPLE_F32, np.float32), (capi.SB_SAMPLE_I16, np.int16), (capi.SB_SAMPLE_U16, np.uint16)])
+@pytest.mark.parametrize("channels", [1, 2, 6])
+def test_downmix_mono_bit_exact(cuda_dev, fmt, dtype, channels):
+    """row a14: cpal callback down-mix (recorder.rs:182-201), bit-exact vs the oracle; ragged frame counts."""
+    import torch
+    from oracle import vad_gate
+    rng = np.random.default_rng(7 + channels)
+    n_streams, n_frames = 3, 4801
+    if dtype == np.float32:
+        host = rng.uniform(-1, 1, (n_streams, n_frames * channels + 5)).astype(np.float32)
+    else:
+        info = np.iinfo(dtype)
+        host = rng.integers(info.min, info.max + 1, (n_streams, n_frames * channels + 5)).astype(dtype)
+    tdt = {np.float32: torch.float32, np.int16: torch.int16, np.uint16: torch.uint16}[dtype]
+    dev_in = torch.from_numpy(host).to("cuda")
+    assert dev_in.dtype == tdt
+    dev_out = torch.zeros((n_streams, n_frames + 3), dtype=torch.float32, device="cuda")
+    capi.downmix_mono_dev(dev_in.data_ptr(), fmt, channels, host.shape[1], n_frames, n_streams, dev_out.data_ptr(), n_frames + 3)
+    torch.cuda.synchronize()
+    got = dev_out.cpu().numpy()
+    for s in range(n_streams):
+        ref = vad_gate.downmix_mono(host[s, : n_frames * channels], channels)
+        assert np.array_equal(got[s, :n_frames], ref)
+        assert np.all(got[s, n_frames:] == 0)

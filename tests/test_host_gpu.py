@@ -40,9 +40,11 @@ def test_python_transcription_manager(cuda_dev, model_dir):
     text = tm.transcribe(clip)                      # waits for the background load
     assert tm.is_model_loaded() and tm.get_current_model() == "nano"
     assert tm.transcribe_batch([clip, clip[:40000]])[0] == text
-    st.selected_language = "auto"
+    st.selected_language = "auto"                  # the reference default (settings.rs:427-429): detected per clip
+    assert isinstance(tm.transcribe(clip), str)
+    st.selected_language = "xx"
     with pytest.raises(transcription.TranscriptionError, match="Whisper transcription failed"):
-        tm.transcribe(clip)                         # language auto-detect not implemented yet: loud error
+        tm.transcribe(clip)                         # unknown language code: loud error
     st.selected_language = "en"
     st.model_unload_timeout = "immediately"
     tm.transcribe(clip)
