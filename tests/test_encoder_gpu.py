@@ -54,6 +54,46 @@ def test_attention_matches_torch(cuda_dev, dtype):
     assert err < (2e-2 if dtype == capi.SB_DTYPE_BF16 else 3e-3), err
 
 
+def _fallbacks():
+    import ctypes as C
+    n = C.c_ulonglong(0)
+    lib = capi.lib()
+    lib.sb_debug_attn_fallbacks.argtypes = [C.POINTER(C.c_ulonglong)]
+    capi.check(lib.sb_debug_attn_fallbacks(C.byref(n)))
+    return n.value
+
+
+@pytest.mark.parametrize("dtype", [capi.SB_DTYPE_F16, capi.SB_DTYPE_BF16])
+def test_attention_single_sweep_falls_back_exactly(cuda_dev, dtype):
+    """The single-sweep softmax takes its reference from the first 64 keys; rows whose later scores exceed it by
+    more than 2^14 must be recomputed by the exact two-pass sweep (no overflow of the 16-bit probabilities).
+    Head 0: scores grow along the keys (fallback), head 1: ordinary random scores (fast path), ragged last tile."""
+    import torch
+    tdt = torch.bfloat16 if dtype == capi.SB_DTYPE_BF16 else torch.float16
+    W, T, H = 2, 1500, 2
+    d = H * 64
+    g = torch.Generator(device="cpu").manual_seed(3)
+    qkv = torch.randn(W * T, 3, H, 64, generator=g)
+    ramp = torch.linspace(0.05, 1.2, T).repeat(W)                       # |k| grows 24x along the window
+    qkv[:, 0, 0, :] = 2.0 + 0.1 * qkv[:, 0, 0, :]                        # q ~ 2 * ones: q.k ~ 128 |k| -> 0.18 * 147 = 27 log2 units
+    qkv[:, 1, 0, :] = ramp[:, None] * (1.0 + 0.05 * qkv[:, 1, 0, :])
+    qkv = qkv.reshape(W * T, 3 * d).to(tdt).to(cuda_dev)
+    out = torch.zeros(W * T, d, dtype=tdt, device=cuda_dev)
+    n0 = _fallbacks()
+    capi.check(capi.lib().sb_attn_enc_dev(dtype, qkv.data_ptr(), out.data_ptr(), W, T, d, H,
+                                          torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    n1 = _fallbacks()
+    q, k, v = (qkv.float().view(W, T, 3, H, 64)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(W * T, d)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err < (3e-2 if dtype == capi.SB_DTYPE_BF16 else 5e-3), err
+    import os
+    if os.environ.get("SB_ATTN_TS", "1") != "0" and os.environ.get("SB_ATTN_TWO_PASS", "0") != "1":
+        assert 12 * W <= n1 - n0 < 2 * 12 * W, (n0, n1)              # the 12 q-tiles of head 0 in every window, none of head 1
+
+
 def _windows(model, clip_ids, secs=30.0):
     mels, ends = [], []
     for i in clip_ids:
