@@ -10,7 +10,9 @@ the whisper.cpp seek loop -> text) over one batch of 64 clips through the C ABI
 
   value  RTFx with the PCM already resident in HBM (device pointers handed to the C ABI)
   e2e    RTFx with pinned HOST buffers: H2D of the PCM and D2H of tokens inside the timed region
-  roofline      tcgen05 GEMM launches (encoder + cross-KV): algorithmic FLOPs / CUDA-event time
+  roofline      the kernel with the largest share of the step (decoder-step projections on Small, the tcgen05
+                GEMM on Large-v3 / Turbo): algorithmic bytes or FLOPs per launch / its CUDA-event duration, measured
+                live; the other hot kernels follow in roofline_extra
   cpu_baseline  the numpy oracle ("port" of whisper.cpp) on the host cores,
                 bounded sample
   --impl reference   times that same CPU port as the reference arm (the reference itself cannot be
@@ -230,11 +232,25 @@ def main():
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
+    # one more (untimed) batch with per-kernel CUDA-event brackets on the decoder step: projections + cross-attention.
+    # The brackets serialise the PDL chain and the step runs without its CUDA graph, so these are each kernel's own
+    # duration; they are related to the timed step only through the launch counts.
+    eng.set_profile(2)
+    eng.stats(reset=True)
+    eng.transcribe_batch_ptrs(dev_ptrs, sizes, params)
+    st_dec = eng.stats(reset=True)
+    eng.set_profile(0)
     value = world * audio_s * args.steps / (ms_dev / 1e3)
     e2e = world * audio_s * args.steps / (ms_e2e / 1e3)
     gemm_tflops = st_dev["gemm_flops"] / max(st_dev["gemm_ms"], 1e-9) / 1e9
     attn_tflops = st_dev["attn_flops"] / max(st_dev["attn_ms"], 1e-9) / 1e9
     peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    peak_hbm = peaks["hbm_gbs"]
+    skinny_gbps = st_dec["skinny_bytes"] / max(st_dec["skinny_ms"], 1e-9) / 1e6
+    xattn_gbps = st_dec["xattn_bytes"] / max(st_dec["xattn_ms"], 1e-9) / 1e6
+    # log-mel: algorithmic bytes (PCM in + n_mel x 3000 f32 out per 30 s clip) over the engine's mel time
+    mel_bytes = CLIPS_PER_GPU * (480000 * 4 + eng.info.n_mels * 3000 * 4)
+    mel_gbps = mel_bytes * args.steps / max(st_dev["mel_ms"], 1e-9) / 1e6
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -263,16 +279,47 @@ def main():
                 "h2d_bytes_per_step": (st_e2e["pcm_bytes"] + st_e2e["h2d_bytes"]) / steps,
                 "d2h_bytes_per_step": st_e2e["d2h_bytes"] / steps},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "k_gemm_tn (tcgen05, encoder + cross-KV projections)", "bound": "tensor",
-                     "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
-                     "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
-                     "launches": st_dev["gemm_launches"], "ms_per_step": st_dev["gemm_ms"] / steps, "traffic": None},
-        "roofline_extra": [
-            {"kernel": "k_attn_enc (mma.sync flash attention)", "bound": "tensor", "achieved": attn_tflops,
-             "peak": peak_tf, "unit": "TFLOP/s", "frac": attn_tflops / peak_tf, "ms_per_step": st_dev["attn_ms"] / steps},
-        ],
+        "roofline": None,
+        "roofline_extra": None,
         "clocks": sampler.summary(),
     }
+    # ---- rooflines: per-kernel entries, the one with the largest share of the timed step first ----
+    d_model, n_dec = eng.info.n_text_state, eng.info.n_text_layer
+    proj_per_step = 6 * n_dec                                    # QKV, O, Q, O, FC1, FC2 per decoder layer
+    skinny_avg_us = 1e3 * st_dec["skinny_ms"] / max(st_dec["skinny_launches"], 1)
+    xattn_avg_us = 1e3 * st_dec["xattn_ms"] / max(st_dec["xattn_launches"], 1)
+    dec_steps = st_dev["decoder_steps"] / steps
+    n_lanes = int(os.environ.get("SB_DECODE_LANES", "2"))
+    ms_step = ms_dev / steps
+    entries = [
+        {"kernel": "k_skinny_gemm (decoder-step projections, weight streaming, mma.sync)", "bound": "hbm",
+         "achieved": skinny_gbps, "peak": peak_hbm, "unit": "GB/s", "frac": skinny_gbps / peak_hbm,
+         "alg_bytes_per_launch": st_dec["skinny_bytes"] / max(st_dec["skinny_launches"], 1),
+         "avg_launch_us": skinny_avg_us, "launches_per_step": dec_steps * proj_per_step * n_lanes,
+         "share_of_step": dec_steps * proj_per_step * n_lanes * skinny_avg_us / 1e3 / n_lanes / ms_step,
+         "note": "latency-bound: 1-5 MB of weights per launch; share assumes the decode lanes overlap perfectly; ncu "
+                 "(profiles/r1_full_skinny_gemm.md, 768x768 launch): 1.31 MB DRAM read for 1.18 MB of weights",
+         "peak_source": f"{peak_src} hbm_gbs", "traffic": None},
+        {"kernel": "k_dec_cross_attn (decoder cross-attention over the cached 1500 encoder keys)", "bound": "hbm",
+         "achieved": xattn_gbps, "peak": peak_hbm, "unit": "GB/s", "frac": xattn_gbps / peak_hbm,
+         "avg_launch_us": xattn_avg_us, "launches_per_step": dec_steps * n_dec * n_lanes,
+         "share_of_step": dec_steps * n_dec * n_lanes * xattn_avg_us / 1e3 / ms_step,
+         "note": "bytes = K and V of the sequences still decoding (finished ones are skipped)", "traffic": None},
+        {"kernel": "k_gemm_tn (tcgen05 / TMEM / TMA, encoder + cross-KV projections)", "bound": "tensor",
+         "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
+         "launches_per_step": st_dev["gemm_launches"] / steps, "share_of_step": st_dev["gemm_ms"] / steps / ms_step,
+         "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)", "traffic": None},
+        {"kernel": "k_attn_enc_ts (tcgen05 encoder attention, Q/P as TMEM operands, single exp sweep)", "bound": "tensor",
+         "achieved": attn_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": attn_tflops / peak_tf,
+         "launches_per_step": st_dev["attn_launches"] / steps, "share_of_step": st_dev["attn_ms"] / steps / ms_step,
+         "note": "algorithmic 4 T^2 d FLOP; the kernel is bound by MUFU.EX2 (d_head 64), see profiles/", "traffic": None},
+        {"kernel": "k_logmel + k_logmel_norm", "bound": "hbm", "achieved": mel_gbps, "peak": peak_hbm, "unit": "GB/s",
+         "frac": mel_gbps / peak_hbm, "share_of_step": st_dev["mel_ms"] / steps / ms_step,
+         "note": "fp32 400-point FFT on the CUDA cores: instruction-bound (DESIGN.md 5)", "traffic": 1.59e8 / 64 * CLIPS_PER_GPU},
+    ]
+    entries.sort(key=lambda e: -e["share_of_step"])
+    line["roofline"] = entries[0]
+    line["roofline_extra"] = entries[1:]
     if cpu_base:
         line["cpu_baseline"] = cpu_base
     print(json.dumps(line), flush=True)

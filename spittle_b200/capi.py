@@ -144,7 +144,7 @@ class SbStats(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "clips", "windows", "rounds", "decoder_steps", "tokens_sampled", "pcm_bytes", "h2d_bytes", "d2h_bytes",
         "mel_ms", "encode_ms", "decode_ms", "gemm_ms", "gemm_flops", "gemm_launches", "attn_ms", "attn_flops",
-        "attn_launches")]
+        "attn_launches", "skinny_ms", "skinny_bytes", "skinny_launches", "xattn_ms", "xattn_bytes", "xattn_launches")]
 
 
 class SbWindowInfo(C.Structure):
@@ -243,7 +243,8 @@ class Engine:
         """cudaStream_t of the engine (wrap with torch.cuda.ExternalStream to record events on it)."""
         return int(lib().sb_engine_stream(self._h) or 0)
 
-    def set_profile(self, enable: bool) -> None:
+    def set_profile(self, enable) -> None:
+        """0 off, 1 encoder GEMM / attention brackets, 2 additionally decoder projections + cross-attention (no graph)."""
         check(lib().sb_engine_set_profile(self._h, int(enable)))
 
     def stats(self, reset: bool = False) -> dict:

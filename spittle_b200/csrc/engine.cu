@@ -137,7 +137,12 @@ struct Engine : EngineBase {
     // per-launch CUDA-event brackets (only when profile != 0): class 0 = tcgen05 GEMM, 1 = encoder attention
     struct ProfRec { cudaEvent_t a, b; int cls; double work; };
     std::vector<ProfRec> prof_pool; size_t prof_used = 0;
-    int prof_begin(int cls, double work) {
+    // profile == 2 additionally brackets the decoder-step projections (class 2, work = weight bytes) and the decoder
+    // cross-attention (class 3, work = K/V bytes of the live sequences): the step then runs without its CUDA graph
+    // and the brackets serialise the PDL chain, so these are each kernel's own duration, not the overlapped one
+    int prof_begin(int cls, double work) { return prof_begin_on(cls, work, st); }
+    int prof_end() { return prof_end_on(st); }
+    int prof_begin_on(int cls, double work, cudaStream_t s_) {
         if (!profile) return SB_OK;
         if (prof_used == prof_pool.size()) {
             ProfRec r{}; r.cls = cls;
@@ -145,12 +150,12 @@ struct Engine : EngineBase {
             prof_pool.push_back(r);
         }
         prof_pool[prof_used].cls = cls; prof_pool[prof_used].work = work;
-        SB_CUDA_CHECK(cudaEventRecord(prof_pool[prof_used].a, st));
+        SB_CUDA_CHECK(cudaEventRecord(prof_pool[prof_used].a, s_));
         return SB_OK;
     }
-    int prof_end() {
+    int prof_end_on(cudaStream_t s_) {
         if (!profile) return SB_OK;
-        SB_CUDA_CHECK(cudaEventRecord(prof_pool[prof_used].b, st));
+        SB_CUDA_CHECK(cudaEventRecord(prof_pool[prof_used].b, s_));
         ++prof_used;
         return SB_OK;
     }
@@ -159,7 +164,9 @@ struct Engine : EngineBase {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, prof_pool[i].a, prof_pool[i].b);
             if (prof_pool[i].cls == 0) { stats.gemm_ms += ms; stats.gemm_flops += prof_pool[i].work; stats.gemm_launches += 1; }
-            else { stats.attn_ms += ms; stats.attn_flops += prof_pool[i].work; stats.attn_launches += 1; }
+            else if (prof_pool[i].cls == 1) { stats.attn_ms += ms; stats.attn_flops += prof_pool[i].work; stats.attn_launches += 1; }
+            else if (prof_pool[i].cls == 2) { stats.skinny_ms += ms; stats.skinny_bytes += prof_pool[i].work; stats.skinny_launches += 1; }
+            else { stats.xattn_ms += ms; stats.xattn_bytes += prof_pool[i].work; stats.xattn_launches += 1; }
         }
         prof_used = 0;
     }
@@ -509,6 +516,13 @@ struct Engine : EngineBase {
         }
         float* part = b_dpart.as<float>() + (int64_t)w0 * d;
         const int64_t pstride = (int64_t)W * d;
+        const bool pd = profile == 2 && prof_sample;
+        auto sk = [&](const T* X, int ldx, const T* Wt, int ldw, int N, int K, const SkinnyEpilogue& ep) -> int {
+            int r;
+            if (pd && (r = prof_begin_on(2, 2.0 * N * K, sl))) return r;
+            if ((r = skinny_gemm<T>(X, ldx, Wt, ldw, Wl, N, K, ep, sl))) return r;
+            return pd ? prof_end_on(sl) : SB_OK;
+        };
         const int* next_tok = b_next.as<int>() + w0;
         for (int l = 0; l < hp.n_text_layer; ++l) {
             const DecLayer<T>& L = dec[l];
@@ -519,12 +533,12 @@ struct Engine : EngineBase {
             if ((rc = dec_ln<T>(dx, L.ln1.g, L.ln1.b, dh, Wl, d, l == 0 ? tok_emb : nullptr, dec_pos, next_tok, pos_ptr, part,
                                 (l > 0 && ks_fc2 > 1) ? ks_fc2 : 0, pstride, l > 0 ? dec[l - 1].fc2.b : nullptr, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.qkv.b; e.out16 = dqkv; e.ldo16 = 3 * d;
-            if ((rc = skinny_gemm<T>(dh, d, L.qkv.w, d, Wl, 3 * d, d, e, sl))) return rc;
+            if ((rc = sk(dh, d, L.qkv.w, d, 3 * d, d, e))) return rc;
             if ((rc = dec_self_attn<T>(dqkv, kc, vc, datt, pos_ptr, seq_state, Wl, hp.n_text_head, d, hp.n_text_ctx, sl))) return rc;
             if (ks_o > 1) { if ((rc = skinny_gemm_splitk<T>(datt, d, L.o.w, d, Wl, d, d, ks_o, part, pstride, sl))) return rc; }
             else {
                 e = SkinnyEpilogue{}; e.bias = L.o.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
-                if ((rc = skinny_gemm<T>(datt, d, L.o.w, d, Wl, d, d, e, sl))) return rc;
+                if ((rc = sk(datt, d, L.o.w, d, d, d, e))) return rc;
             }
             // cross_attn_ln + query projection can be fused into the cross-attention kernel's prologue
             FusedQ fq;
@@ -533,23 +547,25 @@ struct Engine : EngineBase {
                 if ((rc = dec_ln<T>(dx, L.ln2.g, L.ln2.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, part, ks_o > 1 ? ks_o : 0,
                                     pstride, L.o.b, sl))) return rc;
                 e = SkinnyEpilogue{}; e.bias = L.cq.b; e.out16 = dq; e.ldo16 = d;
-                if ((rc = skinny_gemm<T>(dh, d, L.cq.w, d, Wl, d, d, e, sl))) return rc;
+                if ((rc = sk(dh, d, L.cq.w, d, d, d, e))) return rc;
             }
             const T* kb = b_ckv.as<T>() + (int64_t)w0 * nctx * nkv + (int64_t)l * 2 * d;
+            if (pd && (rc = prof_begin_on(3, 4.0 * nctx * d * (double)live_hint, sl))) return rc;
             if ((rc = dec_cross_attn<T>(dq, d, kb, kb + d, nkv, (int64_t)nctx * nkv, datt, seq_state, Wl, hp.n_text_head, d, nctx, fq, sl))) return rc;
+            if (pd && (rc = prof_end_on(sl))) return rc;
             if (ks_o > 1) { if ((rc = skinny_gemm_splitk<T>(datt, d, L.co.w, d, Wl, d, d, ks_o, part, pstride, sl))) return rc; }
             else {
                 e = SkinnyEpilogue{}; e.bias = L.co.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
-                if ((rc = skinny_gemm<T>(datt, d, L.co.w, d, Wl, d, d, e, sl))) return rc;
+                if ((rc = sk(datt, d, L.co.w, d, d, d, e))) return rc;
             }
             if ((rc = dec_ln<T>(dx, L.ln3.g, L.ln3.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, part, ks_o > 1 ? ks_o : 0, pstride,
                                 L.co.b, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.fc1.b; e.act = 1; e.out16 = dmlp; e.ldo16 = 4 * d;
-            if ((rc = skinny_gemm<T>(dh, d, L.fc1.w, d, Wl, 4 * d, d, e, sl))) return rc;
+            if ((rc = sk(dh, d, L.fc1.w, d, 4 * d, d, e))) return rc;
             if (ks_fc2 > 1) { if ((rc = skinny_gemm_splitk<T>(dmlp, 4 * d, L.fc2.w, 4 * d, Wl, d, 4 * d, ks_fc2, part, pstride, sl))) return rc; }
             else {
                 e = SkinnyEpilogue{}; e.bias = L.fc2.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
-                if ((rc = skinny_gemm<T>(dmlp, 4 * d, L.fc2.w, 4 * d, Wl, d, 4 * d, e, sl))) return rc;
+                if ((rc = sk(dmlp, 4 * d, L.fc2.w, 4 * d, d, 4 * d, e))) return rc;
             }
         }
         if ((rc = dec_ln<T>(dx, ln_f.g, ln_f.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, part, ks_fc2 > 1 ? ks_fc2 : 0, pstride,
@@ -566,6 +582,8 @@ struct Engine : EngineBase {
 
     struct DecodeOut { std::vector<SeqState> state; std::vector<int> tokens; std::vector<float> margins; std::vector<int> langs; int n_max = 0; };
     bool detect_lang = false; int* detect_out = nullptr;     // set by decode() for enqueue_step
+    bool prof_sample = false;                                // profile == 2: bracket this step (every 8th)
+    int live_hint = 0;                                       // live sequences of the lane being enqueued (profile == 2 accounting)
     bool auto_mode = false;                                  // current transcribe_batch call asked for language auto-detect
 
     // decode W windows whose cross-KV occupies rows [0, W*1500) of b_ckv
@@ -620,7 +638,7 @@ struct Engine : EngineBase {
         detect_lang = detect; detect_out = d_lang;
 
         const int total_steps = n_prompt - 1 + n_max;
-        const bool graph = use_graph && !logits_out;
+        const bool graph = use_graph && !logits_out && profile != 2;
         // lanes: independent sub-batches on their own streams (one lane when tracing logits)
         int n_lanes = (logits_out || use_mega) ? 1 : std::min(n_lanes_cfg, std::max(1, W / 8));
         if (use_mega) {
@@ -695,7 +713,9 @@ struct Engine : EngineBase {
             for (int i = 0; i < n_lanes; ++i) {
                 if (lr[i].finished) continue;
                 Lane& L = lanes[i];
-                const int burst = logits_out ? 1 : std::min(8, total_steps - lr[i].steps);
+                const int burst = (logits_out || profile == 2) ? 1 : std::min(8, total_steps - lr[i].steps);
+                live_hint = std::max(0, lr[i].Wl - (lr[i].steps > 0 ? h_ctr[16 * i + 2] : 0));
+                prof_sample = (lr[i].steps % 8) == 0;
                 for (int b = 0; b < burst; ++b) {
                     if (graph) { SB_CUDA_CHECK(cudaGraphLaunch(L.gexec, L.st)); g_launches += (uint64_t)L.graph_nodes; }
                     else if ((rc = enqueue_step(W, lr[i].w0, lr[i].Wl, b_ctr.as<int>() + 16 * i, L.st, lane_args(i)))) return rc;
