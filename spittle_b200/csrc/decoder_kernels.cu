@@ -209,7 +209,20 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
     if (st.done) return;
     const SpecialIds sp = a.sp;
     const int V = a.n_vocab;
-    const float* lg = logits + (int64_t)b * ld;
+    // Stage the whole vocabulary row (207 KB, L2-resident: the logits GEMM just wrote it) in shared memory with one
+    // deep burst of 16-byte cp.async (13 in flight per thread).  The sweeps below then run out of shared memory; reading
+    // the row three times through L2 with one dependent 4-byte load per iteration cost 50-67 us per launch.
+    extern __shared__ __align__(16) float s_row[];
+    {
+        const float* src = logits + (int64_t)b * ld;
+        const int n16 = (V + 3) >> 2;                     // ld is a multiple of 8 floats: the padded tail is readable
+        for (int i = threadIdx.x; i < n16; i += kSampThreads)
+            cp_async16_d((uint32_t)__cvta_generic_to_shared(s_row + 4 * i), src + 4 * i, true);
+        asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group 0;");
+        __syncthreads();
+    }
+    const float* lg = s_row;
     LogitMask mk;
     mk.sp = sp;
     mk.is_initial = st.n_tok == 0;
@@ -230,13 +243,13 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
     if (!text_off)
         for (int id = threadIdx.x; id < sp.eot; id += kSampThreads) {
             if (id == blank_off) continue;
-            const float x = __ldcg(lg + id);
+            const float x = lg[id];
             all.add(x);
             mx_text = fmaxf(mx_text, x);
         }
     for (int id = sp.eot + threadIdx.x; id < V; id += kSampThreads) {
         if (mk.suppressed(id)) continue;
-        const float x = __ldcg(lg + id);
+        const float x = lg[id];
         all.add(x);
         if (id >= sp.beg) ts.add(x); else mx_text = fmaxf(mx_text, x);
     }
@@ -267,13 +280,13 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
     if (!text_off && !force_ts)
         for (int id = threadIdx.x; id < sp.eot; id += kSampThreads) {
             if (id == blank_off) continue;
-            const float x = __ldcg(lg + id);
+            const float x = lg[id];
             if (x > bv) { b2 = bv; bv = x; bi = id; }
             else if (x > b2) b2 = x;
         }
     for (int id = sp.eot + threadIdx.x; id < V; id += kSampThreads) {
         if (mk.suppressed(id) || (force_ts && id < sp.beg)) continue;
-        const float x = __ldcg(lg + id);
+        const float x = lg[id];
         if (x > bv) { b2 = bv; bv = x; bi = id; }
         else if (x > b2) b2 = x;
     }
@@ -412,7 +425,14 @@ int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t 
     return SB_OK;
 }
 int sample_step(const float* logits, int ld, const SamplerArgs& a, int Bn, cudaStream_t st) {
-        launch_pdl(k_logits_filter_argmax, dim3(Bn), dim3(kSampThreads), 0, st, logits, ld, a);
+    const size_t smem = (size_t)((a.n_vocab + 3) / 4) * 16;
+    SB_CHECK_ARG(smem <= 226 * 1024 && ld % 4 == 0, "sampler: vocabulary row must fit shared memory (<= 57856 tokens)");
+    static bool attr_done = false;
+    if (!attr_done) {
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_logits_filter_argmax, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        attr_done = true;
+    }
+    launch_pdl(k_logits_filter_argmax, dim3(Bn), dim3(kSampThreads), smem, st, logits, ld, a);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;

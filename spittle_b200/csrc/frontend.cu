@@ -120,7 +120,7 @@ struct SileroDev {
     const float *dec_w, *dec_b;
 };
 
-constexpr int kSfFrames = 8;                 // frames per CTA
+constexpr int kSfFrames = 4;                 // frames per CTA (72 KB of shared memory: three CTAs per SM)
 constexpr int kSfCols = kSfFrames * 7;       // 56 STFT columns
 constexpr int kSfThreads = 288;
 constexpr int kSfPadLen = 672;
@@ -191,7 +191,7 @@ struct SileroSmem {
 };
 
 // pcm: [n_streams][n_frames*480]; out: [n_streams][n_frames][64]
-__global__ void __launch_bounds__(kSfThreads) k_silero_features(const float* __restrict__ pcm, int64_t pcm_stride, int n_frames,
+__global__ void __launch_bounds__(kSfThreads, 3) k_silero_features(const float* __restrict__ pcm, int64_t pcm_stride, int n_frames,
                                                                 float* __restrict__ out, SileroDev wts) {
     extern __shared__ __align__(16) unsigned char smem_raw_s[];
     SileroSmem& s = *reinterpret_cast<SileroSmem*>(smem_raw_s);
@@ -207,46 +207,53 @@ __global__ void __launch_bounds__(kSfThreads) k_silero_features(const float* __r
         s.xs[i] = (f0 + f < n_frames) ? __ldg(src + (int64_t)(f0 + f) * 480 + k) : 0.0f;
     }
     __syncthreads();
-    // STFT conv: item = (column half hh, channel pair i): re/im of 28 columns, two groups of 14.
+    // STFT conv: item = (frame pair hh, channel pair i): re/im of the 2 x 7 columns of two frames.
     // Blocked summation (8 blocks of 32 taps) keeps the fp32 round-off of the 256-term dot products
     // well below the 2^-20 scale that log(1 + 2^20 |X|) magnifies on quiet bins.
+    // The window samples are read four taps at a time (one 128-bit shared-memory load feeds 8 FMAs): the loop is
+    // bound by the FMA pipe, not by the load/store unit.
     {
-        const int item = threadIdx.x;
-        if (item < 258) {
+        constexpr int kPairs = kSfFrames / 2;
+        for (int item = threadIdx.x; item < kPairs * 129; item += blockDim.x) {
             const int hh = item / 129, i = item - hh * 129;
+            float re[14], im[14];
+#pragma unroll
+            for (int c = 0; c < 14; ++c) { re[c] = 0.f; im[c] = 0.f; }
+            const float* xb = s.xs + (hh * 2) * kSfPadLen;
 #pragma unroll 1
-            for (int grp = 0; grp < 2; ++grp) {
-                float re[14], im[14];
+            for (int kb = 0; kb < 256; kb += 32) {
+                float tr[14], ti[14];
 #pragma unroll
-                for (int c = 0; c < 14; ++c) { re[c] = 0.f; im[c] = 0.f; }
-                const float* xb = s.xs + (hh * 4 + grp * 2) * kSfPadLen;
-#pragma unroll 1
-                for (int kb = 0; kb < 256; kb += 32) {
-                    float tr[14], ti[14];
+                for (int c = 0; c < 14; ++c) { tr[c] = 0.f; ti[c] = 0.f; }
+#pragma unroll 2
+                for (int k = kb; k < kb + 32; k += 4) {
+                    float br[4], bi[4];
 #pragma unroll
-                    for (int c = 0; c < 14; ++c) { tr[c] = 0.f; ti[c] = 0.f; }
-#pragma unroll 4
-                    for (int k = kb; k < kb + 32; ++k) {
-                        const float br = __ldg(wts.basis_t + k * 258 + i);
-                        const float bi = __ldg(wts.basis_t + k * 258 + 129 + i);
-#pragma unroll
-                        for (int f = 0; f < 2; ++f)
-#pragma unroll
-                            for (int t = 0; t < 7; ++t) {
-                                const float xv = xb[f * kSfPadLen + 64 * t + k];
-                                tr[f * 7 + t] = fmaf(br, xv, tr[f * 7 + t]);
-                                ti[f * 7 + t] = fmaf(bi, xv, ti[f * 7 + t]);
-                            }
+                    for (int e = 0; e < 4; ++e) {
+                        br[e] = __ldg(wts.basis_t + (k + e) * 258 + i);
+                        bi[e] = __ldg(wts.basis_t + (k + e) * 258 + 129 + i);
                     }
 #pragma unroll
-                    for (int c = 0; c < 14; ++c) { re[c] += tr[c]; im[c] += ti[c]; }
+                    for (int f = 0; f < 2; ++f)
+#pragma unroll
+                        for (int t = 0; t < 7; ++t) {
+                            const float4 xv = *reinterpret_cast<const float4*>(xb + f * kSfPadLen + 64 * t + k);
+                            float a = tr[f * 7 + t], b = ti[f * 7 + t];
+                            a = fmaf(br[0], xv.x, a); b = fmaf(bi[0], xv.x, b);
+                            a = fmaf(br[1], xv.y, a); b = fmaf(bi[1], xv.y, b);
+                            a = fmaf(br[2], xv.z, a); b = fmaf(bi[2], xv.z, b);
+                            a = fmaf(br[3], xv.w, a); b = fmaf(bi[3], xv.w, b);
+                            tr[f * 7 + t] = a; ti[f * 7 + t] = b;
+                        }
                 }
 #pragma unroll
-                for (int c = 0; c < 14; ++c) {
-                    const float mag = sqrtf(re[c] * re[c] + im[c] * im[c]);
-                    s.x1[i * kSfCols + hh * 28 + grp * 14 + c] = mag;
-                    s.r1[i * kSfCols + hh * 28 + grp * 14 + c] = log1pf(1048576.0f * mag);   // spect (scratch)
-                }
+                for (int c = 0; c < 14; ++c) { re[c] += tr[c]; im[c] += ti[c]; }
+            }
+#pragma unroll
+            for (int c = 0; c < 14; ++c) {
+                const float mag = sqrtf(re[c] * re[c] + im[c] * im[c]);
+                s.x1[i * kSfCols + hh * 14 + c] = mag;
+                s.r1[i * kSfCols + hh * 14 + c] = log1pf(1048576.0f * mag);   // spect (scratch)
             }
         }
     }
