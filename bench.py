@@ -134,8 +134,10 @@ def run_reference(args):
         "impl": "reference", "metric": "RTFx (audio-s per wall-s)", "value": value, "unit": "x real-time",
         "n_gpus": args.gpus, "steps": steps, "warmup": 0, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16 (ggml rounding points) / f32 accumulate", "data": "synthetic",
-        "config": {"workload": f"Whisper {ARCH} greedy decode, bounded sample: 1 synthetic 30 s 16 kHz clip per step "
-                               f"of the {CLIPS_PER_GPU}-clip batch (clip 0)", "arch": ARCH},
+        "config": {"workload": f"Whisper {ARCH} greedy decode, batch of {CLIPS_PER_GPU} synthetic 30 s 16 kHz clips per GPU "
+                               "(BASELINE.json configs[1]), random-init 'sharp' recipe seed 42, language en, timestamps on, "
+                               "no fallback", "arch": ARCH, "clips_per_gpu": CLIPS_PER_GPU,
+                   "sample": "each step = clip 0 of that batch (1 x 30 s), CPU only"},
         "cpu_baseline": {"value": value, "unit": "x real-time", "cores": cores, "kind": "port",
                          "sample": "1 clip x 30 s per step, numpy/OpenBLAS oracle restating whisper.cpp "
                                    "(reference not buildable here: no cargo/rustc, crates not vendored)"},
