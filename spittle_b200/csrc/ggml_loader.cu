@@ -29,6 +29,36 @@ float f16_bits_to_f32(uint16_t h) {
 }
 
 namespace {
+// ggml block-quantised types, 32 weights per block (layouts per ggml [MEM]):
+//   q4_0 {f16 d; u8 qs[16]}            x = (q - 8) d       q4_1 {f16 d, m; u8 qs[16]}            x = q d + m
+//   q5_0 {f16 d; u8 qh[4]; u8 qs[16]}  x = (q - 16) d      q5_1 {f16 d, m; u8 qh[4]; u8 qs[16]}  x = q d + m
+//   q8_0 {f16 d; i8 qs[32]}            x = q d
+// element j < 16 = low nibble of qs[j], element j + 16 = high nibble; q5's fifth bit is bit j / j + 16 of qh.
+// The weights are expanded to f32 here and then stored in the engine's 16-bit operand type; ggml's CPU kernels
+// instead quantise the ACTIVATIONS to 8 bits for these dot products -- that extra noise is not reproduced.
+int quant_block_bytes(int ttype) {
+    switch (ttype) { case 2: return 18; case 3: return 20; case 6: return 22; case 7: return 24; case 8: return 34; default: return 0; }
+}
+void dequantize(const uint8_t* src, int ttype, int64_t count, float* dst) {
+    const int bs = quant_block_bytes(ttype);
+    for (int64_t b = 0; b < count / 32; ++b, src += bs, dst += 32) {
+        uint16_t dh; memcpy(&dh, src, 2);
+        const float d = f16_bits_to_f32(dh);
+        const uint8_t* p = src + 2;
+        float m = 0.f;
+        if (ttype == 3 || ttype == 7) { uint16_t mh; memcpy(&mh, p, 2); m = f16_bits_to_f32(mh); p += 2; }
+        if (ttype == 8) { for (int j = 0; j < 32; ++j) dst[j] = (float)(int8_t)p[j] * d; continue; }
+        uint32_t qh = 0;
+        if (ttype == 6 || ttype == 7) { memcpy(&qh, p, 4); p += 4; }
+        for (int j = 0; j < 16; ++j) {
+            int lo = p[j] & 0x0F, hi = p[j] >> 4;
+            if (ttype == 6 || ttype == 7) { lo |= (int)((qh >> j) & 1u) << 4; hi |= (int)((qh >> (j + 16)) & 1u) << 4; }
+            if (ttype == 2) { dst[j] = (float)(lo - 8) * d; dst[j + 16] = (float)(hi - 8) * d; }
+            else if (ttype == 6) { dst[j] = (float)(lo - 16) * d; dst[j + 16] = (float)(hi - 16) * d; }
+            else { dst[j] = (float)lo * d + m; dst[j + 16] = (float)hi * d + m; }
+        }
+    }
+}
 struct Reader {
     const uint8_t* p; size_t n; size_t off = 0; bool ok = true;
     template <typename V> V get() {
@@ -103,17 +133,25 @@ int load_ggml_file(const char* path, GgmlFile& out) {
         HostTensor t;
         t.ttype = ttype;
         for (int i = n_dims - 1; i >= 0; --i) t.shape.push_back(ne[i]);   // fastest-first -> torch order
-        size_t esz;
-        if (ttype == 0) esz = 4;
-        else if (ttype == 1) esz = 2;
-        else {
-            set_error("tensor '" + name + "' has quantised type " + std::to_string(ttype) +
-                      " (only f32/f16 GGML files are supported so far)");
+        if (ttype == 0 || ttype == 1) {
+            t.nbytes = (size_t)t.numel() * (ttype == 0 ? 4 : 2);
+            t.data = r.take(t.nbytes);
+            if (!t.data) { set_error("truncated tensor data: " + name); return SB_ERR_FORMAT; }
+        } else if (quant_block_bytes(ttype) > 0) {
+            if (ne[0] % 32 != 0) { set_error("quantised tensor '" + name + "': row length is not a multiple of 32"); return SB_ERR_FORMAT; }
+            const size_t qbytes = (size_t)(t.numel() / 32) * quant_block_bytes(ttype);
+            const uint8_t* q = r.take(qbytes);
+            if (!q) { set_error("truncated tensor data: " + name); return SB_ERR_FORMAT; }
+            out.dequant.emplace_back((size_t)t.numel());
+            dequantize(q, ttype, t.numel(), out.dequant.back().data());
+            t.ttype = 0;
+            t.nbytes = (size_t)t.numel() * 4;
+            t.data = reinterpret_cast<const uint8_t*>(out.dequant.back().data());
+        } else {
+            set_error("tensor '" + name + "' has ggml type " + std::to_string(ttype) +
+                      " (supported: f32, f16, q4_0, q4_1, q5_0, q5_1, q8_0; k-quants are not)");
             return SB_ERR_FORMAT;
         }
-        t.nbytes = (size_t)t.numel() * esz;
-        t.data = r.take(t.nbytes);
-        if (!t.data) { set_error("truncated tensor data: " + name); return SB_ERR_FORMAT; }
         out.tensors[name] = t;
     }
     return SB_OK;

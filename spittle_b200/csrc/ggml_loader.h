@@ -11,7 +11,7 @@
 namespace sb {
 
 struct HostTensor {
-    int ttype = 0;                    // 0 f32, 1 f16
+    int ttype = 0;                    // 0 f32, 1 f16 (block-quantised tensors are dequantised to f32 on load)
     std::vector<int64_t> shape;       // torch order (slowest first)
     const uint8_t* data = nullptr;    // points into GgmlFile::blob
     size_t nbytes = 0;
@@ -30,6 +30,7 @@ struct GgmlFile {
     std::vector<std::string> vocab;             // id -> bytes, entries present in the file
     std::map<std::string, HostTensor> tensors;
     std::vector<uint8_t> blob;                  // whole file
+    std::vector<std::vector<float>> dequant;    // owned f32 copies of block-quantised tensors
 };
 
 // returns SB_OK / SB_ERR_IO / SB_ERR_FORMAT (message via sb::set_error)

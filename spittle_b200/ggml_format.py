@@ -26,6 +26,91 @@ import numpy as np
 GGML_MAGIC = 0x67676D6C
 GGML_TYPE_F32 = 0
 GGML_TYPE_F16 = 1
+# ggml block-quantised tensor types (32 weights per block; SURVEY 8(f) N2: the reference's catalog ships
+# Medium as q4_1 and Large-v3 as q5_0, resources/model_catalog.json:157,187).  Layouts per ggml [MEM]:
+#   q4_0 {f16 d; u8 qs[16]}               x = (q - 8) d        q4_1 {f16 d, m; u8 qs[16]}          x = q d + m
+#   q5_0 {f16 d; u8 qh[4]; u8 qs[16]}     x = (q - 16) d       q5_1 {f16 d, m; u8 qh[4]; u8 qs[16]} x = q d + m
+#   q8_0 {f16 d; i8 qs[32]}               x = q d
+# element j < 16 takes the low nibble of qs[j], element j + 16 the high nibble; the fifth bit of q5 comes from
+# bit j (low half) / bit j + 16 (high half) of the little-endian u32 qh.
+GGML_TYPE_Q4_0, GGML_TYPE_Q4_1, GGML_TYPE_Q5_0, GGML_TYPE_Q5_1, GGML_TYPE_Q8_0 = 2, 3, 6, 7, 8
+QUANT_BLOCK_BYTES = {GGML_TYPE_Q4_0: 18, GGML_TYPE_Q4_1: 20, GGML_TYPE_Q5_0: 22, GGML_TYPE_Q5_1: 24, GGML_TYPE_Q8_0: 34}
+GGML_FTYPE_OF_TYPE = {GGML_TYPE_Q4_0: 2, GGML_TYPE_Q4_1: 3, GGML_TYPE_Q8_0: 7, GGML_TYPE_Q5_0: 8, GGML_TYPE_Q5_1: 9}
+
+
+def quantize_blocks(x: np.ndarray, ttype: int) -> bytes:
+    """ggml reference quantisation (quantize_row_q*_reference) of a tensor whose last dim is a multiple of 32."""
+    v = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 32)
+    nb = v.shape[0]
+    if ttype == GGML_TYPE_Q8_0:
+        amax = np.abs(v).max(axis=1)
+        d = (amax / 127.0).astype(np.float32)
+        idv = np.where(d > 0, 1.0 / np.where(d > 0, d, 1), 0.0).astype(np.float32)
+        q = np.rint(v * idv[:, None]).astype(np.int8)
+        out = np.zeros((nb, 34), np.uint8)
+        out[:, 0:2] = d.astype("<f2").view(np.uint8).reshape(nb, 2)
+        out[:, 2:] = q.view(np.uint8)
+        return out.tobytes()
+    five = ttype in (GGML_TYPE_Q5_0, GGML_TYPE_Q5_1)
+    levels = 32 if five else 16
+    if ttype in (GGML_TYPE_Q4_0, GGML_TYPE_Q5_0):
+        idx = np.abs(v).argmax(axis=1)
+        mx = v[np.arange(nb), idx]                                   # signed value of largest magnitude
+        d = (mx / -(levels // 2)).astype(np.float32)
+        idv = np.where(d != 0, 1.0 / np.where(d != 0, d, 1), 0.0).astype(np.float32)
+        q = np.minimum(levels - 1, (v * idv[:, None] + (levels // 2 + 0.5)).astype(np.int32)).astype(np.uint8)
+        m = None
+    else:
+        mn, mxv = v.min(axis=1), v.max(axis=1)
+        d = ((mxv - mn) / (levels - 1)).astype(np.float32)
+        idv = np.where(d != 0, 1.0 / np.where(d != 0, d, 1), 0.0).astype(np.float32)
+        q = np.minimum(levels - 1, ((v - mn[:, None]) * idv[:, None] + 0.5).astype(np.int32)).astype(np.uint8)
+        m = mn.astype(np.float32)
+    lo, hi = q[:, :16], q[:, 16:]
+    qs = ((lo & 0x0F) | ((hi & 0x0F) << 4)).astype(np.uint8)
+    parts = [d.astype("<f2").view(np.uint8).reshape(nb, 2)]
+    if m is not None:
+        parts.append(m.astype("<f2").view(np.uint8).reshape(nb, 2))
+    if five:
+        qh = np.zeros(nb, np.uint32)
+        for j in range(16):
+            qh |= ((lo[:, j].astype(np.uint32) >> 4) & 1) << j
+            qh |= ((hi[:, j].astype(np.uint32) >> 4) & 1) << (j + 16)
+        parts.append(qh.astype("<u4").view(np.uint8).reshape(nb, 4))
+    parts.append(qs)
+    return np.concatenate(parts, axis=1).tobytes()
+
+
+def dequantize_blocks(raw: bytes, ttype: int, count: int) -> np.ndarray:
+    bs = QUANT_BLOCK_BYTES[ttype]
+    nb = count // 32
+    b = np.frombuffer(raw, np.uint8, nb * bs).reshape(nb, bs)
+    d = b[:, 0:2].copy().view("<f2").astype(np.float32)             # [nb, 1]
+    off = 2
+    m = None
+    if ttype in (GGML_TYPE_Q4_1, GGML_TYPE_Q5_1):
+        m = b[:, 2:4].copy().view("<f2").astype(np.float32)
+        off = 4
+    if ttype == GGML_TYPE_Q8_0:
+        q = b[:, 2:].copy().view(np.int8).astype(np.float32)
+        return (q * d).astype(np.float32).reshape(-1)
+    qh = None
+    if ttype in (GGML_TYPE_Q5_0, GGML_TYPE_Q5_1):
+        qh = b[:, off:off + 4].copy().view("<u4").reshape(nb)
+        off += 4
+    qs = b[:, off:off + 16]
+    lo = (qs & 0x0F).astype(np.int32)
+    hi = (qs >> 4).astype(np.int32)
+    if qh is not None:
+        j = np.arange(16)
+        lo |= (((qh[:, None] >> j) & 1) << 4).astype(np.int32)
+        hi |= (((qh[:, None] >> (j + 16)) & 1) << 4).astype(np.int32)
+    q = np.concatenate([lo, hi], axis=1).astype(np.float32)
+    if ttype == GGML_TYPE_Q4_0:
+        return ((q - 8.0) * d).astype(np.float32).reshape(-1)
+    if ttype == GGML_TYPE_Q5_0:
+        return ((q - 16.0) * d).astype(np.float32).reshape(-1)
+    return (q * d + m).astype(np.float32).reshape(-1)
 
 
 @dataclass
@@ -136,8 +221,12 @@ class GgmlModel:
         return b"[_extra_token_%d]" % tid
 
 
-def write_ggml(path: str, model: GgmlModel) -> None:
+def write_ggml(path: str, model: GgmlModel, quant_type: int = None) -> None:
+    """quant_type: store every 2-D f16 weight matrix in that ggml block type (what whisper.cpp's `quantize` tool does:
+    matrices are quantised, 1-D tensors, conv kernels and positional embeddings keep their float type)."""
     hp = model.hparams
+    if quant_type is not None:
+        hp = WhisperHParams(**{**asdict(hp), "ftype": GGML_FTYPE_OF_TYPE[quant_type]})
     with open(path, "wb") as f:
         f.write(struct.pack("<I", GGML_MAGIC))
         f.write(struct.pack("<11i", *hp.as_list()))
@@ -156,12 +245,17 @@ def write_ggml(path: str, model: GgmlModel) -> None:
                 ttype = GGML_TYPE_F16
             else:
                 raise ValueError(f"{name}: unsupported dtype {arr.dtype}")
+            payload = None
+            if (quant_type is not None and arr.ndim == 2 and arr.dtype == np.float16 and arr.shape[1] % 32 == 0
+                    and "positional_embedding" not in name):
+                ttype = quant_type
+                payload = quantize_blocks(arr.astype(np.float32), quant_type)
             nb = name.encode()
             ne = list(reversed(arr.shape))  # fastest-varying first
             f.write(struct.pack("<iii", len(ne), len(nb), ttype))
             f.write(struct.pack("<%di" % len(ne), *ne))
             f.write(nb)
-            f.write(np.ascontiguousarray(arr).tobytes())
+            f.write(payload if payload is not None else np.ascontiguousarray(arr).tobytes())
 
 
 def read_ggml(path: str) -> GgmlModel:
@@ -202,8 +296,12 @@ def read_ggml(path: str) -> GgmlModel:
         elif ttype == GGML_TYPE_F16:
             arr = np.frombuffer(data, dtype="<f2", count=count, offset=off)
             off += 2 * count
+        elif ttype in QUANT_BLOCK_BYTES:
+            nbytes = count // 32 * QUANT_BLOCK_BYTES[ttype]
+            arr = dequantize_blocks(data[off:off + nbytes], ttype, count)        # f32, like the engine's loader
+            off += nbytes
         else:
-            raise ValueError(f"{name}: tensor type {ttype} (quantised) not supported yet")
+            raise ValueError(f"{name}: tensor type {ttype} (k-quants) not supported")
         tensors[name] = arr.reshape(shape).copy()
     return GgmlModel(hp, mel, vocab, tensors)
 

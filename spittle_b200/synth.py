@@ -274,13 +274,15 @@ def make_synthetic_model(arch: str, seed: int = 42, recipe: str = "sharp",
                      tensors=T)
 
 
-def ensure_model_file(arch: str, directory: str, seed: int = 42, recipe: str = "sharp") -> str:
-    """Write (once) ``ggml-synth-<arch>-<recipe>-s<seed>.bin`` under ``directory``."""
+def ensure_model_file(arch: str, directory: str, seed: int = 42, recipe: str = "sharp", quant_type: int = None) -> str:
+    """Write (once) ``ggml-synth-<arch>-<recipe>-s<seed>[-q<type>].bin`` under ``directory``.
+    quant_type: a ggml block type (ggml_format.GGML_TYPE_Q*) for the weight matrices, like whisper.cpp's quantize tool."""
     os.makedirs(directory, exist_ok=True)
-    path = os.path.join(directory, f"ggml-synth-{arch}-{recipe}-s{seed}.bin")
+    suffix = "" if quant_type is None else f"-q{quant_type}"
+    path = os.path.join(directory, f"ggml-synth-{arch}-{recipe}-s{seed}{suffix}.bin")
     if not os.path.exists(path):
         tmp = path + ".tmp%d" % os.getpid()
-        write_ggml(tmp, make_synthetic_model(arch, seed, recipe))
+        write_ggml(tmp, make_synthetic_model(arch, seed, recipe), quant_type=quant_type)
         os.replace(tmp, path)
     return path
 

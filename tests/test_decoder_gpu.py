@@ -169,3 +169,27 @@ def test_language_auto_detect_matches_oracle(cuda_dev, model_dir):
     params.language = b"de"
     assert eng.transcribe(clips[1], params).lang_id == 2          # whisper language table: en, zh, de, ...
     eng.close()
+
+
+@pytest.mark.parametrize("qt", [3, 6])       # q4_1 (catalog: Medium), q5_0 (catalog: Large-v3)
+def test_quantised_model_file_matches_oracle(cuda_dev, model_dir, qt):
+    """block-quantised GGML files load (dequantised on load, then stored in the engine's 16-bit
+    operand type); the oracle runs on the same dequantised weights."""
+    path = synth.ensure_model_file("nano", model_dir, quant_type=qt)
+    model = ggml_format.read_ggml(path)
+    oracle = whisper_ref.WhisperOracle(model, act_f16=True)
+    eng = capi.Engine(path, dtype=capi.SB_DTYPE_F16, max_batch=4)
+    x = synth.make_clip(1, 30.0)
+    mel, n_len_org = logmel.logmel_f64(x, model.mel_filters)
+    win = logmel.mel_window(mel, 0)
+    enc = oracle.encode(win)
+    got = eng.encode(win[None])[0]
+    rel = float(np.sqrt(((got - enc) ** 2).mean()) / np.sqrt((enc ** 2).mean()))
+    assert rel < 2e-3, rel
+    tr = oracle.decode_window(enc, 0, n_len_org, whisper_ref.DecodeConfig(n_max_override=12), trace=True)
+    forced = np.full((1, 12), -1, np.int32)
+    forced[0, :len(tr.tokens)] = tr.tokens
+    logits, toks, _ = eng.decode_trace(win[None], [n_len_org], 12, forced=forced)
+    for s_ in range(len(tr.tokens)):
+        assert float(np.abs(logits[0, s_] - tr.logits_trace[s_]).max()) <= LOGIT_TOL[capi.SB_DTYPE_F16]
+    eng.close()

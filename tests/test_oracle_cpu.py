@@ -114,3 +114,39 @@ def test_oracle_window_runs_and_is_audio_dependent():
         assert 1 <= len(w.tokens) <= 12
         outs.append(tuple(w.tokens))
     assert outs[0] != outs[1]
+
+
+def test_ggml_block_quantisation_round_trip(tmp_path):
+    """q4_0 / q4_1 / q5_0 / q5_1 / q8_0 tensors (the reference catalog ships Medium as q4_1 and
+    Large-v3 as q5_0).  Known answers for the block layouts + write/read round trip of a quantised model file."""
+    from spittle_b200 import ggml_format as g, synth
+    # hand-built blocks: d = 0.5 (f16 0x3800), m = -1.0 (f16 0xBC00)
+    qs = bytes(((j & 0xF) | (((15 - j) & 0xF) << 4)) for j in range(16))
+    x = g.dequantize_blocks(b"\x00\x38" + qs, g.GGML_TYPE_Q4_0, 32)
+    assert np.array_equal(x[:16], (np.arange(16) - 8) * 0.5) and np.array_equal(x[16:], (15 - np.arange(16) - 8) * 0.5)
+    x = g.dequantize_blocks(b"\x00\x38\x00\xbc" + qs, g.GGML_TYPE_Q4_1, 32)
+    assert np.array_equal(x[:16], np.arange(16) * 0.5 - 1.0)
+    qh = (0x0000FFFF).to_bytes(4, "little")           # fifth bit set for the low half only
+    x = g.dequantize_blocks(b"\x00\x38" + qh + qs, g.GGML_TYPE_Q5_0, 32)
+    assert np.array_equal(x[:16], (np.arange(16) + 16 - 16) * 0.5) and np.array_equal(x[16:], (15 - np.arange(16) - 16) * 0.5)
+    x = g.dequantize_blocks(b"\x00\x38" + bytes(np.arange(-16, 16, dtype=np.int8).view(np.uint8)), g.GGML_TYPE_Q8_0, 32)
+    assert np.array_equal(x, np.arange(-16, 16) * 0.5)
+    # quantise -> dequantise stays within half a step of the block scale
+    rng = np.random.default_rng(1)
+    w = rng.normal(0, 0.1, (8, 64)).astype(np.float32)
+    for t, steps in ((g.GGML_TYPE_Q4_0, 8), (g.GGML_TYPE_Q4_1, 15), (g.GGML_TYPE_Q5_0, 16), (g.GGML_TYPE_Q5_1, 31), (g.GGML_TYPE_Q8_0, 127)):
+        y = g.dequantize_blocks(g.quantize_blocks(w, t), t, w.size).reshape(w.shape)
+        span = np.abs(w.reshape(-1, 32)).max(axis=1) * (2 if t in (g.GGML_TYPE_Q4_1, g.GGML_TYPE_Q5_1) else 1)
+        # the symmetric types anchor the scale on the largest-magnitude value: the other side clips by up to one step
+        k = 1.01 if t in (g.GGML_TYPE_Q4_0, g.GGML_TYPE_Q5_0) else 0.51
+        assert (np.abs(y - w).reshape(-1, 32).max(axis=1) <= k * span / steps + 1e-3).all(), t
+    # model file: matrices quantised, vectors / conv kernels / positional embeddings untouched
+    path = synth.ensure_model_file("nano", str(tmp_path), quant_type=g.GGML_TYPE_Q5_0)
+    ref = g.read_ggml(synth.ensure_model_file("nano", str(tmp_path)))
+    q = g.read_ggml(path)
+    assert q.hparams.ftype == 8
+    name = "decoder.blocks.0.mlp.0.weight"
+    assert q.tensors[name].dtype == np.float32 and q.tensors[name].shape == ref.tensors[name].shape
+    err = np.abs(q.tensors[name] - ref.tensors[name].astype(np.float32)).max()
+    assert 0 < err < 0.1 * np.abs(ref.tensors[name].astype(np.float32)).max()
+    assert np.array_equal(q.tensors["encoder.conv1.weight"], ref.tensors["encoder.conv1.weight"])
