@@ -51,3 +51,27 @@ def test_python_transcription_manager(cuda_dev, model_dir):
     assert not tm.is_model_loaded()
     with pytest.raises(transcription.TranscriptionError, match="Model not found"):
         tm.load_model("missing")
+
+
+def test_full_size_batch_invariance_and_determinism(cuda_dev, model_dir):
+    """Whisper Small (the BASELINE.json configs[1] architecture) at full size, where the numpy oracle is too slow to
+    be the checker: size-independent properties instead.  (1) the result of a clip does not depend on what else is
+    in the batch or on its position (clips do not interact: no_context, per-sequence state) -- except that lanes
+    regroup sequences, which must not change any token; (2) two runs are bit-identical; (3) the single-clip API
+    equals a batch of one; (4) empty and sub-second clips inside a large batch give "" without disturbing others."""
+    path = synth.ensure_model_file("small", model_dir)
+    eng = capi.Engine(path, dtype=capi.SB_DTYPE_F16, max_batch=16)
+    clips = [synth.make_clip(i, 30.0 if i % 3 else 17.5) for i in range(10)]
+    params = capi.default_params(n_max_tokens=40, max_windows=2)
+    full = eng.transcribe_batch(clips, params)
+    again = eng.transcribe_batch(clips, params)
+    assert [r.sampled for r in full] == [r.sampled for r in again] and [r.text for r in full] == [r.text for r in again]
+    mixed = [clips[7], np.zeros(0, np.float32), clips[2], synth.make_clip(3, 0.4), clips[0]]
+    part = eng.transcribe_batch(mixed, params)
+    assert part[1].text == b"" and part[3].text == b"" and part[1].windows == [] and part[3].windows == []
+    for got, idx in ((part[0], 7), (part[2], 2), (part[4], 0)):
+        assert got.sampled == full[idx].sampled and got.text == full[idx].text
+    one = eng.transcribe(clips[5], params)
+    assert one.sampled == full[5].sampled and one.text == full[5].text
+    assert len({tuple(r.sampled) for r in full}) >= 8          # the audio steers the tokens: clips differ
+    eng.close()
