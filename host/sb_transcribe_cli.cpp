@@ -2,14 +2,27 @@
 //   sb_transcribe_cli <model.bin> <clip.f32> [language]       raw little-endian f32, 16 kHz mono
 // Prints the transcription (exit 0) or the error (exit 1).  Used by tests/test_host_cpp_gpu.py.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iterator>
 #include <iostream>
 
+#include "text_filters.hpp"
 #include "transcription_manager.hpp"
 
 int main(int argc, char** argv) {
+    // text post-filter modes (no GPU needed): stdin -> stdout
+    //   sb_transcribe_cli --filter                         filter_transcription_output
+    //   sb_transcribe_cli --custom-words THRESH w1 w2 ..   apply_custom_words (words are separate argv entries)
+    if (argc >= 2 && (!std::strcmp(argv[1], "--filter") || !std::strcmp(argv[1], "--custom-words"))) {
+        std::string text((std::istreambuf_iterator<char>(std::cin)), std::istreambuf_iterator<char>());
+        if (!std::strcmp(argv[1], "--filter")) { std::fputs(sb::filter_transcription_output(text).c_str(), stdout); return 0; }
+        if (argc < 3) return 2;
+        std::vector<std::string> words(argv + 3, argv + argc);
+        std::fputs(sb::apply_custom_words(text, words, std::atof(argv[2])).c_str(), stdout);
+        return 0;
+    }
     if (argc < 3) { std::fprintf(stderr, "usage: %s model.bin clip.f32 [language]\n", argv[0]); return 2; }
     const std::string model = argv[1], clip = argv[2], lang = argc > 3 ? argv[3] : "en";
     sb::Settings st;

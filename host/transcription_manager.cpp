@@ -1,5 +1,6 @@
 // C++ mirror of the reference TranscriptionManager (see transcription_manager.hpp).
 #include "transcription_manager.hpp"
+#include "text_filters.hpp"
 
 #include <cstring>
 
@@ -148,8 +149,10 @@ Result<std::string> TranscriptionManager::transcribe(std::vector<float> audio) {
         text.assign(r.text ? r.text : "", r.text_len);
         sb_result_free(&r);
     }
-    // apply_custom_words / filter_transcription_output / jargon corrections (transcription.rs:538-580) are
-    // CPU string post-filters outside the replaced module; they run on `text` unchanged.
+    // transcription.rs:537-549: custom-word correction (only when configured), then the filler / stutter /
+    // hallucination filter.  Jargon corrections (:552-580) are settings-driven string rules outside this path.
+    if (!s.custom_words.empty()) text = apply_custom_words(text, s.custom_words, s.word_correction_threshold);
+    text = filter_transcription_output(text);
     maybe_unload_immediately("transcription");
     return Result<std::string>::Ok(std::move(text));
 }
@@ -180,7 +183,11 @@ std::vector<Result<std::string>> TranscriptionManager::transcribe_batch(const st
         const std::string e = std::string("Whisper transcription failed: ") + sb_last_error();
         for (auto& r : out) r = Result<std::string>::Err(e);
     } else {
-        for (size_t i = 0; i < clips.size(); ++i) out[i] = Result<std::string>::Ok(std::string(res[i].text ? res[i].text : "", res[i].text_len));
+        for (size_t i = 0; i < clips.size(); ++i) {
+            std::string text(res[i].text ? res[i].text : "", res[i].text_len);
+            if (!s.custom_words.empty()) text = apply_custom_words(text, s.custom_words, s.word_correction_threshold);
+            out[i] = Result<std::string>::Ok(filter_transcription_output(text));
+        }
     }
     for (auto& r : res) sb_result_free(&r);
     return out;

@@ -53,6 +53,8 @@ struct Settings {
     std::string selected_language = "auto";
     bool translate_to_english = false;
     ModelUnloadTimeout model_unload_timeout = ModelUnloadTimeout::Never;
+    std::vector<std::string> custom_words;            // settings.rs custom_words
+    double word_correction_threshold = 0.18;          // settings.rs:446-448
     int device = 0;
     int max_batch = 64;
     int dtype = SB_DTYPE_F16;

@@ -173,22 +173,27 @@ __device__ void down_relu(const float* in, const float* w, const float* b, float
 }
 
 struct SileroSmem {
-    float xs[kSfFrames * kSfPadLen];      // reflect-padded frames
-    float x1[258 * kSfCols];              // [258][8][7]: magnitude (0..128) | norm (129..257)
+    union {
+        float xs[kSfFrames * kSfPadLen];  // reflect-padded frames: dead once the STFT is done ...
+        struct {                          // ... so the small late-stage buffers live in the same bytes (3 CTAs per SM)
+            float y2[16 * kSfFrames * 4];         // T = 4
+            float r2[16 * kSfFrames * 4];
+            float z1[32 * kSfFrames * 4];
+            float z2[32 * kSfFrames * 2];         // T = 2
+            float r3[32 * kSfFrames * 2];
+            float u1[32 * kSfFrames * 2];
+            float u2[32 * kSfFrames];             // T = 1
+            float r4[32 * kSfFrames];
+            float v1[64 * kSfFrames];
+        };
+    };
+    float x1[258 * kSfCols];              // [258][frames][7]: magnitude (0..128) | norm (129..257)
     float r1[258 * kSfCols];              // depthwise output / scratch
     float y1[16 * kSfCols];               // block-1 pre-downsample
-    float y2[16 * kSfFrames * 4];         // T = 4
-    float r2[16 * kSfFrames * 4];
-    float z1[32 * kSfFrames * 4];
-    float z2[32 * kSfFrames * 2];         // T = 2
-    float r3[32 * kSfFrames * 2];
-    float u1[32 * kSfFrames * 2];
-    float u2[32 * kSfFrames];             // T = 1
-    float r4[32 * kSfFrames];
-    float v1[64 * kSfFrames];
     float mean[kSfFrames * 7];
     float mm[kSfFrames];
 };
+static_assert(sizeof(SileroSmem) * 3 <= 227 * 1024 - 3 * 1024, "three CTAs per SM");
 
 // pcm: [n_streams][n_frames*480]; out: [n_streams][n_frames][64]
 __global__ void __launch_bounds__(kSfThreads, 3) k_silero_features(const float* __restrict__ pcm, int64_t pcm_stride, int n_frames,

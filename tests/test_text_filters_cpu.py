@@ -56,3 +56,41 @@ def test_soundex_and_levenshtein_known_answers():
     assert tf.soundex_code("ashcraft") == "a261"
     assert tf.soundex_code("tymczak")[:1] == "t"
     assert tf.levenshtein("kitten", "sitting") == 3 and tf.levenshtein("", "abc") == 3 and tf.levenshtein("abc", "abc") == 0
+
+
+# ---- the same vectors through the compiled C++ host mirror (host/text_filters.cpp via host/sb_transcribe_cli) ----
+def _cli():
+    import subprocess
+    from spittle_b200 import build
+    exe = build.build_host()
+    def run(args, text):
+        r = subprocess.run([exe] + args, input=text.encode(), capture_output=True, timeout=30)
+        assert r.returncode == 0, r.stderr
+        return r.stdout.decode()
+    return run
+
+
+@pytest.fixture(scope="module")
+def cli():
+    if not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(__file__)), "spittle_b200", "libspittle_b200.so")):
+        pytest.skip("libspittle_b200.so not built")
+    return _cli()
+
+
+def test_cpp_filter_transcription_output(cli):
+    for v in G["filter_transcription_output"]:
+        assert cli(["--filter"], v["text"]) == v["expect"], v
+    for v in G["filter_transcription_output_nonempty"]:
+        assert cli(["--filter"], v["text"]) != ""
+
+
+def test_cpp_apply_custom_words(cli):
+    for v in G["apply_custom_words_eq"]:
+        if v["words"]:
+            assert cli(["--custom-words", str(v["threshold"])] + v["words"], v["text"]) == v["expect"], v
+    for v in G["apply_custom_words_contains"]:
+        got = cli(["--custom-words", str(v["threshold"])] + v["words"], v["text"])
+        for s_ in v["contains"]:
+            assert s_ in got, (v, got)
+        for s_ in v["not_contains"]:
+            assert s_ not in got, (v, got)
