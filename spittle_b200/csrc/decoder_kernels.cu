@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "decoder.cuh"
 #include "decoder_bodies.cuh"
+#include <cstdlib>
 
 namespace sb {
 extern std::atomic<uint64_t> g_launches;
@@ -41,6 +42,15 @@ __global__ void __launch_bounds__(256) k_skinny_gemm(const T* __restrict__ X, in
     __shared__ __align__(16) unsigned char smem[kSkinnySmem / 2];
     PdlSync sync;
     skinny_body<T, 1>(X, ldx, W, ldw, Bn, N, 0, K / 32, ep, nullptr, 0, blockIdx.x, blockIdx.y, smem, sync);
+}
+// 32 weight rows per block: half as many blocks each ingest the shared [B, K] activation matrix (the L2 -> SM traffic of
+// a launch is blocks x 98 KB), and a wide projection (QKV, FC1) leaves SMs free for the other decode lane
+template <typename T>
+__global__ void __launch_bounds__(256) k_skinny_gemm_w32(const T* __restrict__ X, int ldx, const T* __restrict__ W, int ldw,
+                                                         int Bn, int N, int K, SkinnyEpilogue ep) {
+    extern __shared__ __align__(16) unsigned char smem_w32[];
+    PdlSync sync;
+    skinny_body<T, 2>(X, ldx, W, ldw, Bn, N, 0, K / 32, ep, nullptr, 0, blockIdx.x, blockIdx.y, smem_w32, sync);
 }
 
 // split-K variant: grid.x = tiles * ks; block (tile, slice) stores raw f32 sums of its K slice to part[slice]
@@ -376,6 +386,18 @@ int dec_embed(const T* tok_emb, const float* pos_emb, const int* tokens, const i
 template <typename T>
 int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, const SkinnyEpilogue& ep, cudaStream_t st) {
     SB_CHECK_ARG(K % 32 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "skinny gemm: K % 32 and 16-byte row alignment required");
+    static const int w32_min_n = [] { const char* e = getenv("SB_DEC_W32_MIN_N"); return e ? atoi(e) : 2048; }();
+    if (N >= w32_min_n) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            SB_CUDA_CHECK(cudaFuncSetAttribute(k_skinny_gemm_w32<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkinnySmem));
+            attr_done = true;
+        }
+        launch_pdl(k_skinny_gemm_w32<T>, dim3(ceil_div(N, 32), ceil_div(Bn, 64)), dim3(256), (size_t)kSkinnySmem, st, X, ldx, W, ldw, Bn, N, K, ep);
+        g_launches += 1;
+        SB_CUDA_CHECK(cudaGetLastError());
+        return SB_OK;
+    }
     dim3 grid(ceil_div(N, 16), ceil_div(Bn, 64));
     launch_pdl(k_skinny_gemm<T>, grid, dim3(256), 0, st, X, ldx, W, ldw, Bn, N, K, ep);
     g_launches += 1;
