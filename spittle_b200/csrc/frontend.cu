@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include <vector>
 #include <cmath>
+#include <cstdlib>
 
 namespace sb {
 extern std::atomic<uint64_t> g_launches;
@@ -103,6 +104,100 @@ __global__ void __launch_bounds__(kFirThreads) k_resample_fir(const float* __res
     for (int r = 0; r < kFirR; ++r) {
         const int m = m0 + threadIdx.x * kFirR + r;
         if (m < n_out) yo[m] = acc[r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// The same FIR on the tensor cores.  16 consecutive outputs m0+16n .. m0+16n+15 are one GEMM column block:
+//   y[m0 + 16 n + i] = sum_j A[i][j] * B[j][n],   A[i][j] = h[(T-1) + D i - j]  (0 outside [0, T)),
+//                                                B[j][n] = x[D (m0 + 16 n) - (T-1) + j],   j in [0, T + 15 D)
+// A is a constant 16 x (T + 15 D) Toeplitz expansion of the taps (4 % more MACs than the direct form at D = 3), B is a
+// sliding window over ONE contiguous input segment (column n starts 16 D samples after column n-1), so both operands
+// are built from shared memory with index arithmetic only.  mma.sync.m16n8k8 TF32 with the 3-pass split
+// (a_hi b_hi + a_hi b_lo + a_lo b_hi, hi = cvt.rna.tf32, lo = the exact f32 remainder): products are exact to ~2^-21,
+// accumulation is f32 -- the result stays within the 1e-5 parity bound of the f64 rubato restatement.
+// CTA = 256 threads, 2048 outputs (128 column blocks = 16 n-tiles, two per warp) of one stream.
+// ------------------------------------------------------------------------------------------
+constexpr int kRmBlocks = 128;                    // 16-output column blocks per CTA
+constexpr int kRmTile = 16 * kRmBlocks;           // outputs per CTA
+
+__device__ __forceinline__ uint32_t tf32_hi(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = tf32_hi(x);
+    lo = tf32_hi(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256) k_resample_mma(const float* __restrict__ x, int64_t x_stride, int n_in,
+                                                      float* __restrict__ y, int64_t y_stride, int n_out,
+                                                      const float* __restrict__ h, int T, int D, int Kp) {
+    extern __shared__ float s_rm[];
+    const int hp_pad = Kp;                                  // hp[idx + hp_pad] = h[idx], zero outside [0, T)
+    const int hp_len = T + 15 * D + Kp + 8;
+    float* hp = s_rm;
+    float* xs = s_rm + ((hp_len + 3) & ~3);                 // input segment: Kp + 16 D (kRmBlocks - 1) samples
+    const int seg = Kp + 16 * D * (kRmBlocks - 1);
+    const int stream = blockIdx.y;
+    const int m0 = blockIdx.x * kRmTile;
+    const float* xin = x + (int64_t)stream * x_stride;
+    for (int i = threadIdx.x; i < hp_len; i += 256) {
+        const int idx = i - hp_pad;
+        hp[i] = (idx >= 0 && idx < T) ? __ldg(h + idx) : 0.0f;
+    }
+    const int64_t base0 = (int64_t)D * m0 - (T - 1);
+    for (int i = threadIdx.x; i < seg; i += 256) {
+        const int64_t src = base0 + i;
+        xs[i] = (src >= 0 && src < n_in) ? __ldg(xin + src) : 0.0f;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    float acc[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) { acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f; }
+    // A[i][j] = hp[hp_pad + (T-1) + D i - j]; rows g and g + 8, columns 8 s + t and 8 s + t + 4
+    const float* ha = hp + hp_pad + (T - 1) + D * g - t;
+    const float* hb = ha + 8 * D;
+    // B[j][n] = xs[j + 16 D n]; this warp's n-tiles: 2 warp and 2 warp + 1 (columns 8 nt + g)
+    const float* xb0 = xs + 16 * D * (8 * (2 * warp) + g) + t;
+    const float* xb1 = xb0 + 16 * D * 8;
+    const int n_steps = Kp >> 3;
+#pragma unroll 2
+    for (int sI = 0; sI < n_steps; ++sI) {
+        const int j = 8 * sI;
+        uint32_t ah[4], al[4];
+        split_tf32(ha[-j], ah[0], al[0]);
+        split_tf32(hb[-j], ah[1], al[1]);
+        split_tf32(ha[-j - 4], ah[2], al[2]);
+        split_tf32(hb[-j - 4], ah[3], al[3]);
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(xb0[j], bh0, bl0);
+        split_tf32(xb0[j + 4], bh1, bl1);
+        mma_tf32(acc[0], ah, bh0, bh1);
+        mma_tf32(acc[0], ah, bl0, bl1);
+        mma_tf32(acc[0], al, bh0, bh1);
+        split_tf32(xb1[j], bh0, bl0);
+        split_tf32(xb1[j + 4], bh1, bl1);
+        mma_tf32(acc[1], ah, bh0, bh1);
+        mma_tf32(acc[1], ah, bl0, bl1);
+        mma_tf32(acc[1], al, bh0, bh1);
+    }
+    // C[i][n]: c0 (g, 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)  ->  output m0 + 16 n + i
+    float* yo = y + (int64_t)stream * y_stride;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int nt = 2 * warp + u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int n = 8 * nt + 2 * t + (e & 1);
+            const int i = g + ((e >> 1) << 3);
+            const int m = m0 + 16 * n + i;
+            if (m < n_out) yo[m] = acc[u][e];
+        }
     }
 }
 
@@ -545,6 +640,20 @@ int sb_resample_dev(const sb_resampler* r, const float* in, int64_t in_stride, s
     }
     if (n_out == 0) return SB_OK;
     const int D = r->decim, taps_p = r->n_taps / D;
+    static const bool use_mma = [] { const char* e = getenv("SB_RESAMPLE_MMA"); return !(e && e[0] == '0'); }();
+    if (use_mma) {
+        // tensor-core Toeplitz form (k_resample_mma)
+        const int T = r->n_taps;
+        const int Kp = (T + 15 * D + 7) & ~7;
+        const size_t smem = (size_t)(((T + 15 * D + Kp + 8 + 3) & ~3) + Kp + 16 * D * (sb::kRmBlocks - 1)) * sizeof(float);
+        SB_CHECK_ARG(smem <= 200 * 1024, "resampler: filter too long for the shared-memory segment");
+        SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_resample_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)((n_out + sb::kRmTile - 1) / sb::kRmTile), n_streams);
+        sb::k_resample_mma<<<grid, 256, smem, st>>>(in, in_stride, (int)n_in, out, out_stride, (int)n_out, r->d_h, T, D, Kp);
+        sb::g_launches += 1;
+        SB_CUDA_CHECK(cudaGetLastError());
+        return SB_OK;
+    }
     const int win = sb::kFirTile + taps_p - 1;
     const size_t smem = (size_t)(D * taps_p + D * (win + (win >> 3) + 2)) * sizeof(float);
     dim3 grid((unsigned)((n_out + sb::kFirTile - 1) / sb::kFirTile), n_streams);
