@@ -793,9 +793,12 @@ struct Engine : EngineBase {
         int rc = ensure_encoder_ws(W, W, true);
         if (rc) return rc;
         if ((rc = stage_mel_windows(mel_windows, W))) return rc;
+        SB_CUDA_CHECK(cudaEventRecord(ev[0], st));
         if ((rc = encode_chunk(W, 0, b_enc32.as<float>()))) return rc;
+        SB_CUDA_CHECK(cudaEventRecord(ev[1], st));
         SB_CUDA_CHECK(cudaMemcpyAsync(enc_out, b_enc32.p, (size_t)W * hp.n_audio_ctx * hp.n_audio_state * 4, cudaMemcpyDeviceToHost, st));
         SB_CUDA_CHECK(cudaStreamSynchronize(st));
+        { float t = 0.f; cudaEventElapsedTime(&t, ev[0], ev[1]); stats.encode_ms += t; stats.windows += W; }   // conv stem .. ln_post + cross-KV
         prof_collect();
         return SB_OK;
     }

@@ -23,4 +23,7 @@ for r in range(reps):
     flops = W * (2 * 3000 * d * eng.info.n_mels * 3 + 2 * 1500 * d * d * 3 + L * (24 * 1500 * d * d + 4 * 1500 * 1500 * d))
     print(json.dumps({"arch": arch, "W": W, "wall_ms": dt * 1e3, "gemm_ms": st["gemm_ms"], "gemm_tflops": st["gemm_flops"] / max(st["gemm_ms"], 1e-9) / 1e9,
                       "attn_ms": st["attn_ms"], "attn_tflops": st["attn_flops"] / max(st["attn_ms"], 1e-9) / 1e9,
-                      "enc_flops_T": flops / 1e12}), flush=True)
+                      "enc_flops_T": flops / 1e12,
+                      # device time of conv stem + blocks + ln_post + the cross-KV GEMM (which is not in enc_flops_T):
+                      "encode_ms": st["encode_ms"],
+                      "encoder_tflops_lower_bound": flops / max(st["encode_ms"], 1e-9) / 1e9}), flush=True)
