@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from spittle_b200 import build, capi, synth, transcription
+from spittle_b200 import build, capi, ggml_format, synth, transcription
 
 pytestmark = pytest.mark.gpu
 
@@ -77,3 +77,40 @@ def test_full_size_batch_invariance_and_determinism(cuda_dev, model_dir):
     assert one.sampled == full[5].sampled and one.text == full[5].text
     assert len({tuple(r.sampled) for r in full}) >= 8          # the audio steers the tokens: clips differ
     eng.close()
+
+
+def test_long_audio_many_windows_and_batch_chunking(cuda_dev, model_dir):
+    """Edge sizes: a 3.5-minute clip (the seek loop runs many windows, whisper_full semantics), more clips than
+    max_batch (the engine cuts the call into groups), and a 128-sequence batch (two 64-row chunks per projection)."""
+    from oracle import whisper_ref
+    path = synth.ensure_model_file("nano", model_dir)
+    model = ggml_format.read_ggml(path)
+    params = capi.default_params(n_max_tokens=16)
+    eng = capi.Engine(path, dtype=capi.SB_DTYPE_F16, max_batch=4)
+    long_clip = np.concatenate([synth.make_clip(i, 30.0) for i in (1, 2, 3, 4, 5, 6, 7)])          # 210 s
+    r = eng.transcribe(long_clip, params)
+    assert len(r.windows) >= 7 and all(w["seek"] >= 0 for w in r.windows)
+    seeks = [w["seek"] for w in r.windows]
+    assert seeks == sorted(seeks) and seeks[0] == 0 and seeks[-1] + 100 < 21000 + 3000
+    # the oracle on the first 3 windows of the same long clip
+    oracle = whisper_ref.WhisperOracle(model, act_f16=True)
+    _, _, wins = oracle.full(long_clip, whisper_ref.DecodeConfig(n_max_override=16), max_windows=3)
+    for wi, w_ref in enumerate(wins):
+        got = r.sampled[r.windows[wi]["token_offset"]: r.windows[wi]["token_offset"] + r.windows[wi]["n_tokens"]]
+        if got != w_ref.tokens:
+            first = next(k for k in range(min(len(got), len(w_ref.tokens))) if got[k] != w_ref.tokens[k])
+            assert w_ref.margins[first] < 0.4, (wi, first)
+            break
+        assert r.windows[wi]["seek_delta"] == w_ref.seek_delta
+    # 10 clips through max_batch = 4 -> groups of 4, 4, 2; identical to one-at-a-time
+    clips = [synth.make_clip(i, 8.0 + i) for i in range(10)]
+    batch = eng.transcribe_batch(clips, params)
+    for i in (0, 3, 4, 9):
+        assert batch[i].sampled == eng.transcribe(clips[i], params).sampled
+    eng.close()
+    big = capi.Engine(path, dtype=capi.SB_DTYPE_F16, max_batch=128)
+    many = [synth.make_clip(i % 16, 6.0 + (i % 5)) for i in range(128)]
+    out = big.transcribe_batch(many, params)
+    for i in (0, 17, 64, 127):
+        assert out[i].sampled == big.transcribe(many[i], params).sampled
+    big.close()
