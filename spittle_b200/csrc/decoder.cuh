@@ -42,14 +42,6 @@ struct SamplerArgs {
     int n_prompt;
 };
 
-// optional fused prologue of the cross-attention kernel: LayerNorm + query projection
-struct FusedQ {
-    const float* x = nullptr;      // residual stream [B, d] f32; nullptr -> q is read from memory instead
-    const float* ln_g = nullptr; const float* ln_b = nullptr;
-    const void* wq = nullptr;      // [d, d] 16-bit
-    const float* bq = nullptr;
-};
-
 struct SkinnyEpilogue {
     const float* bias = nullptr;
     int act = 0;
@@ -57,31 +49,6 @@ struct SkinnyEpilogue {
     float* out32 = nullptr; int ldo32 = 0;
     void* out16 = nullptr; int ldo16 = 0;
 };
-
-// ---- persistent decoder-step megakernel (decoder_mega.cu) ----
-struct DecLayerDev {
-    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
-    const void *qkv_w, *o_w, *cq_w, *co_w, *fc1_w, *fc2_w;      // 16-bit [out][in]
-    const float *qkv_b, *o_b, *cq_b, *co_b, *fc1_b, *fc2_b;
-    void *kself, *vself;                  // this layer's self-KV cache of the batch: [Bn][n_text_ctx][d]
-    const void *cross_k, *cross_v;        // this layer's cross K / V of sequence 0 (rows strided by ld_kv)
-};
-constexpr int kMegaMaxSplit = 6;
-struct DecStepArgs {
-    int Bn, d, n_head, n_layer, n_ctx, n_text_ctx;
-    int64_t ld_kv, win_stride;
-    const void* tok_emb; const float* pos_emb;
-    const int* next_tokens; const int* pos_ptr;
-    const SeqState* state;                // null: treat every sequence as live (teacher-forced traces)
-    float* x; void* h; void* qkv; void* att; void* q; void* mlp;
-    const float *lnf_g, *lnf_b;
-    unsigned* barrier;                    // zero at launch; reset by k_dec_advance
-    int trace;                            // debug: CTA 0 records a per-stage timeline
-    float* part; int64_t part_stride;     // split-K slices [ks][Bn][d] f32 of the projections 3, 5, 7, 10
-    int mt[11], ks[11];                   // per stage kind: 16-row tiles per block (1|2), K splits (1..kMegaMaxSplit)
-};
-template <typename T> int dec_step_mega(const DecLayerDev* layers, const DecStepArgs& a, cudaStream_t st);
-void mega_plan(int N, int K, bool allow_split, int n_cta, int* mt, int* ks);   // stage decomposition that minimises per-SM ingest
 
 // conv1 im2col: window w reads clip clip_of[w] starting at mel frame seek[w]
 struct Im2col1Args {
@@ -121,16 +88,14 @@ template <typename T> int attn_enc_tc(const T* qkv, T* out, int n_windows, int n
 bool use_tc_attention();   // env SB_ATTN=mma selects the legacy mma.sync kernel
 
 // decoder-side launchers (decoder_kernels.cu)
-template <typename T> int dec_embed(const T* tok_emb, const float* pos_emb, const int* tokens, const int* pos_ptr, float* x, int Bn, int d, cudaStream_t st);
 template <typename T> int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, const SkinnyEpilogue& ep, cudaStream_t st);
-template <typename T> int skinny_gemm_splitk(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, int ks, float* part, int64_t part_stride, cudaStream_t st);
-template <typename T> int dec_ln(float* x, const float* gamma, const float* beta, T* out16, int rows, int d, const T* tok_emb, const float* pos_emb, const int* next_tokens, const int* pos_ptr, const float* part, int nparts, int64_t part_stride, const float* pbias, cudaStream_t st);
+template <typename T> int dec_ln(float* x, const float* gamma, const float* beta, T* out16, int rows, int d, const T* tok_emb, const float* pos_emb, const int* next_tokens, const int* pos_ptr, cudaStream_t st);
 template <typename T> int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const int* pos_ptr, const SeqState* state, int Bn, int n_head, int d, int n_text_ctx, cudaStream_t st);
-template <typename T> int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t ld_kv, int64_t win_stride, T* out, const SeqState* state, int Bn, int n_head, int d, int n_ctx, const FusedQ& fq, cudaStream_t st);
+template <typename T> int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t ld_kv, int64_t win_stride, T* out, const SeqState* state, int Bn, int n_head, int d, int n_ctx, cudaStream_t st);
 int sample_step(const float* logits, int ld, const SamplerArgs& a, int Bn, cudaStream_t st);
 // whisper_lang_auto_detect: at decode position 0 ([sot] only) pick the language token with the largest logit and
 // write it into prompt slot 1 of every sequence whose slot holds the sentinel -1 (no-op at any other position)
 int lang_detect_step(const float* logits, int ld, int* prompt, int n_prompt, const int* pos_ptr, int* lang_out, SpecialIds sp, int Bn, cudaStream_t st);
-int dec_advance(int* pos_ptr, int* step_ptr, int n_prompt, unsigned* barrier, cudaStream_t st);
+int dec_advance(int* pos_ptr, int* step_ptr, int n_prompt, cudaStream_t st);
 
 }  // namespace sb

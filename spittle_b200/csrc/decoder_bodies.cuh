@@ -1,12 +1,10 @@
-// Device bodies of the decoder-step stages, shared by two schedulers:
-//   * the stand-alone kernels of decoder_kernels.cu (one launch per stage, chained with PDL), and
-//   * the persistent per-step megakernel of decoder_mega.cu (one cooperative launch per token,
-//     stages separated by grid barriers).
-// Every body works on one "virtual block" (the blockIdx of the stand-alone launch) with 256
-// threads, takes its shared memory as a pointer, and calls sync.wait() exactly where the data of
-// the preceding stage is first needed: everything above that call only touches immutable
-// operands (weights, the cross-KV cache written by the encoder), so it overlaps the predecessor's
-// tail (PDL) or the grid barrier's latency (megakernel).
+// Device bodies of the decoder-step stages (the kernels of decoder_kernels.cu are thin wrappers).
+// Every body works on one block's share with its shared memory passed as a pointer, and calls
+// sync.wait() exactly where the data of the preceding stage is first needed: everything above that
+// call only touches immutable operands (weights, the cross-KV cache written by the encoder), so it
+// overlaps the predecessor's tail under programmatic dependent launch.  (A persistent per-step
+// megakernel driving the same bodies through grid barriers was measured slower and removed:
+// profiles/r1_mega_stage_trace.md.)
 #pragma once
 #include "common.cuh"
 #include "decoder.cuh"
@@ -52,15 +50,13 @@ __device__ __forceinline__ void cp_async16_d(uint32_t dst, const void* src, bool
 // Fragment trick: both operands are read with 16-byte vector loads of 8 consecutive k; the
 // k-permutation is the same for A and B so the products pair up correctly.
 // ------------------------------------------------------------------------------------------
-// MT = number of 16-row weight tiles per block (1 or 2).  The block covers k-blocks [kb0, kb1) of
-// 32 columns; with `partial` != null it stores its raw f32 sums to partial[b * ldp + row] (split-K:
-// the consumer stage adds the slices in a fixed order) instead of running the epilogue.
+// MT = number of 16-row weight tiles per block (1, or 2 for the wide projections).
 constexpr int kSkinnySmem = 8 * 32 * 65 * 4;       // MT = 2; MT = 1 needs half
 
 template <typename T, int MT, typename Sync>
 __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, const T* __restrict__ W, int ldw, int Bn, int N,
-                                            int kb0, int kb1, const SkinnyEpilogue& ep, float* __restrict__ partial, int ldp,
-                                            int tile, int chunk, unsigned char* smem, Sync& sync) {
+                                            int K, const SkinnyEpilogue& ep, int tile, int chunk, unsigned char* smem, Sync& sync) {
+    const int kb0 = 0, kb1 = K / 32;        // K % 32 == 0 enforced by the host
     float (*s_red)[16 * MT][65] = reinterpret_cast<float (*)[16 * MT][65]>(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -101,7 +97,7 @@ __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, co
     float e_res[4 * MT], e_bias[4 * MT];
 #pragma unroll
     for (int i = 0; i < 4 * MT; ++i) { e_res[i] = 0.f; e_bias[i] = 0.f; }
-    if (!partial && e_n < nb) {
+    if (e_n < nb) {
 #pragma unroll
         for (int i = 0; i < 4 * MT; ++i) {
             const int row = row0 + e_rq + i;
@@ -182,7 +178,6 @@ __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, co
             float v = 0.f;
 #pragma unroll
             for (int w8 = 0; w8 < 8; ++w8) v += s_red[w8][r][n];
-            if (partial) { partial[(int64_t)b * ldp + row] = v; continue; }
             v += e_bias[i];
             if (ep.act == 1) v = gelu_tanh(v);
             v += e_res[i];
@@ -192,70 +187,16 @@ __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, co
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// LayerNorm of one row by one warp (two-pass in registers), d <= 1536.  With tok_emb != null the
-// row is first formed as token_embedding[tok] + positional_embedding[pos] and stored to x.
-// ------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void ln_row_warp(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                            T* __restrict__ out16, int row, int d, const T* __restrict__ tok_emb,
-                                            const float* __restrict__ pos_emb, int tok, int pos) {
-    constexpr int VPL = 12;
-    const int lane = threadIdx.x & 31;
-    const int n4 = d >> 2;
-    float4 v[VPL];
-    float s = 0.f;
-    float4* xr = reinterpret_cast<float4*>(x + (int64_t)row * d);
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int idx = lane + 32 * i;
-        if (idx < n4) {
-            if (tok_emb) {
-                const uint2 u = __ldg(reinterpret_cast<const uint2*>(tok_emb + (int64_t)tok * d) + idx);
-                const float4 p = __ldg(reinterpret_cast<const float4*>(pos_emb + (int64_t)pos * d) + idx);
-                const float2 a = Op16<T>::unpack2(u.x), b = Op16<T>::unpack2(u.y);
-                v[i] = make_float4(a.x + p.x, a.y + p.y, b.x + p.z, b.y + p.w);
-                xr[idx] = v[i];
-            } else v[i] = __ldcg(xr + idx);
-        } else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        s += v[i].x + v[i].y + v[i].z + v[i].w;
-    }
-    const float mean = warp_sum(s) / (float)d;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int idx = lane + 32 * i;
-        if (idx < n4) {
-            v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-            q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-        }
-    }
-    const float rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int idx = lane + 32 * i;
-        if (idx < n4) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
-            const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + idx);
-            uint2 u;
-            u.x = Op16<T>::pack2(v[i].x * rstd * g.x + b.x, v[i].y * rstd * g.y + b.y);
-            u.y = Op16<T>::pack2(v[i].z * rstd * g.z + b.z, v[i].w * rstd * g.w + b.w);
-            reinterpret_cast<uint2*>(out16 + (int64_t)row * d)[idx] = u;
-        }
-    }
-}
-
-// ---- LayerNorm of one row by one warp; optionally first completes the residual stream:
-//      x_row += bias + sum_s part[s][row]   (split-K slices of the producing projection, fixed order)
+// ---- decoder LayerNorm of one row by one warp (two-pass in registers); with tok_emb != null the row is first formed
+//      as token_embedding[tok] + positional_embedding[pos] and stored to x
 template <typename T, int VPL, typename Sync>
-__device__ __forceinline__ void ln_row_mega(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                            T* __restrict__ out16, int row, int d, const T* __restrict__ tok_emb,
-                                            const float* __restrict__ pos_emb, const int* __restrict__ next_tokens,
-                                            const int* __restrict__ pos_ptr, const float* __restrict__ part, int nparts, int64_t part_stride,
-                                            const float* __restrict__ pbias, Sync& sync) {
+__device__ __forceinline__ void ln_row_dec(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                           T* __restrict__ out16, int row, int d, const T* __restrict__ tok_emb,
+                                           const float* __restrict__ pos_emb, const int* __restrict__ next_tokens,
+                                           const int* __restrict__ pos_ptr, Sync& sync) {
     const int lane = threadIdx.x & 31;
     const int n4 = d >> 2;
-    // immutable operands first: they are in flight while the barrier is still closing
+    // immutable operands first: they are in flight while the predecessor is still finishing
     float4 g[VPL], bt[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
@@ -285,25 +226,6 @@ __device__ __forceinline__ void ln_row_mega(float* __restrict__ x, const float* 
             const int idx = lane + 32 * i;
             v[i] = idx < n4 ? __ldcg(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (nparts > 0) {
-#pragma unroll
-            for (int i = 0; i < VPL; ++i) {
-                const int idx = lane + 32 * i;
-                if (idx < n4) {
-                    // all slice loads of this vector are independent: issue them together, add in slice order
-                    float4 q[kMegaMaxSplit];
-#pragma unroll
-                    for (int sI = 0; sI < kMegaMaxSplit; ++sI)
-                        if (sI < nparts) q[sI] = __ldcg(reinterpret_cast<const float4*>(part + sI * part_stride + (int64_t)row * d) + idx);
-                    float4 acc = __ldg(reinterpret_cast<const float4*>(pbias) + idx);
-#pragma unroll
-                    for (int sI = 0; sI < kMegaMaxSplit; ++sI)
-                        if (sI < nparts) { acc.x += q[sI].x; acc.y += q[sI].y; acc.z += q[sI].z; acc.w += q[sI].w; }
-                    v[i].x += acc.x; v[i].y += acc.y; v[i].z += acc.z; v[i].w += acc.w;
-                    xr[idx] = v[i];
-                }
-            }
-        }
     }
     float s = 0.f;
 #pragma unroll
@@ -331,87 +253,10 @@ __device__ __forceinline__ void ln_row_mega(float* __restrict__ x, const float* 
     }
 }
 
-
-// ------------------------------------------------------------------------------------------
-// self attention for one new token of one (sequence, head) by one warp.  qkv: [B, 3d] (this
-// step); cache K/V: [B][n_text_ctx][d].  s_p: 448 floats of this warp.
-// ------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void self_attn_warp(const T* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc,
-                                               T* __restrict__ out, int pos, int b, int h, int d, int n_text_ctx, float* s_p) {
-    const int lane = threadIdx.x & 31;
-    const T* q = qkv + (int64_t)b * 3 * d + h * 64;
-    T* kb = kc + ((int64_t)b * n_text_ctx) * d + h * 64;
-    T* vb = vc + ((int64_t)b * n_text_ctx) * d + h * 64;
-    // append this step's K, V (each lane moves 2 elements)
-    reinterpret_cast<uint32_t*>(kb + (int64_t)pos * d)[lane] = __ldcg(reinterpret_cast<const uint32_t*>(q + d) + lane);
-    reinterpret_cast<uint32_t*>(vb + (int64_t)pos * d)[lane] = __ldcg(reinterpret_cast<const uint32_t*>(q + 2 * d) + lane);
-    __syncwarp();
-    // scores: lane <-> key
-    float qf[64];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const float2 f = Op16<T>::unpack2(__ldcg(reinterpret_cast<const uint32_t*>(q) + i));
-        qf[2 * i] = f.x; qf[2 * i + 1] = f.y;
-    }
-    const int n_keys = pos + 1;
-    float mx = -INFINITY;
-    for (int k = lane; k < n_keys; k += 32) {
-        const uint4* kr = reinterpret_cast<const uint4*>(kb + (int64_t)k * d);
-        float s = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint4 u = __ldcg(kr + c);
-            float2 f;
-            f = Op16<T>::unpack2(u.x); s = fmaf(qf[c * 8 + 0], f.x, s); s = fmaf(qf[c * 8 + 1], f.y, s);
-            f = Op16<T>::unpack2(u.y); s = fmaf(qf[c * 8 + 2], f.x, s); s = fmaf(qf[c * 8 + 3], f.y, s);
-            f = Op16<T>::unpack2(u.z); s = fmaf(qf[c * 8 + 4], f.x, s); s = fmaf(qf[c * 8 + 5], f.y, s);
-            f = Op16<T>::unpack2(u.w); s = fmaf(qf[c * 8 + 6], f.x, s); s = fmaf(qf[c * 8 + 7], f.y, s);
-        }
-        s *= 0.125f;
-        s_p[k] = s;
-        mx = fmaxf(mx, s);
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int k = lane; k < n_keys; k += 32) {
-        const float p = __expf(s_p[k] - mx);
-        s_p[k] = p;
-        sum += p;
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    __syncwarp();
-    // PV: lane <-> 2 output dims; probabilities rounded to the operand type like ggml's mul_mat.
-    // Keys are taken 16 at a time with all 16 value loads issued before the FMAs (the loop is
-    // otherwise a chain of exposed L2 latencies).
-    float o0 = 0.f, o1 = 0.f;
-    for (int k0 = 0; k0 < n_keys; k0 += 16) {
-        uint32_t vv[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int k = min(k0 + i, n_keys - 1);
-            vv[i] = __ldcg(reinterpret_cast<const uint32_t*>(vb + (int64_t)k * d) + lane);
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if (k0 + i < n_keys) {
-                const float p = Op16<T>::to_f32(Op16<T>::from_f32(s_p[k0 + i] * inv));
-                const float2 f = Op16<T>::unpack2(vv[i]);
-                o0 = fmaf(p, f.x, o0); o1 = fmaf(p, f.y, o1);
-            }
-        }
-    }
-    reinterpret_cast<uint32_t*>(out + (int64_t)b * d + h * 64)[lane] = Op16<T>::pack2(o0, o1);
-    __syncwarp();
-}
-
 // ------------------------------------------------------------------------------------------
 // cross attention of one (sequence b, head h) by one 256-thread block.  Kc/Vc rows are strided
 // (ld_kv) inside the fused cross-KV buffer [W*1500, L*2*d]; K then V are each streamed exactly
 // once through a cp.async double-buffered shared-memory tile.
-// With fq.x != nullptr the body also performs the cross-attention LayerNorm and the query
-// projection of its own (sequence, head): q_h = Wq[h*64 .. h*64+63, :] . round16(LN(x_b)) + bq.
 // ------------------------------------------------------------------------------------------
 constexpr int kXKeysPerTile = 128;
 constexpr int kXLd = 72;   // padded row (elements)
@@ -420,10 +265,10 @@ constexpr int kCrossSmem = 2 * kXKeysPerTile * kXLd * 2 + 1504 * 4 + 64 * 4 + 8 
 template <typename T, typename Sync>
 __device__ __forceinline__ void cross_attn_body(const T* __restrict__ q, int ldq, const T* __restrict__ kbase,
                                                 const T* __restrict__ vbase, int64_t ld_kv, int64_t win_stride,
-                                                T* __restrict__ out, int d, int n_ctx, const FusedQ& fq, int h, int b,
+                                                T* __restrict__ out, int d, int n_ctx, int h, int b,
                                                 unsigned char* smem, Sync& sync) {
     T (*s_tile)[kXKeysPerTile * kXLd] = reinterpret_cast<T (*)[kXKeysPerTile * kXLd]>(smem);
-    float* s_sc = reinterpret_cast<float*>(smem + 2 * kXKeysPerTile * kXLd * 2);   // scores; also the LN row of the fused prologue
+    float* s_sc = reinterpret_cast<float*>(smem + 2 * kXKeysPerTile * kXLd * 2);   // scores
     float* s_q = s_sc + 1504;
     float* s_red = s_q + 64;
     float (*s_o)[64] = reinterpret_cast<float (*)[64]>(s_red + 8);
@@ -448,66 +293,9 @@ __device__ __forceinline__ void cross_attn_body(const T* __restrict__ q, int ldq
     // ---- pass 1: scores ----
     load_tile(0, kp, 0);          // the encoder wrote K/V long ago: start the stream before the dependency wait
     sync.wait();
-    if (fq.x == nullptr) {
-        if (tid < 32) {
-            const float2 f = Op16<T>::unpack2(__ldcg(reinterpret_cast<const uint32_t*>(q + (int64_t)b * ldq + h * 64) + tid));
-            s_q[2 * tid] = f.x * 0.125f; s_q[2 * tid + 1] = f.y * 0.125f;
-        }
-    } else {
-        // LayerNorm of row b (two-pass, values held in registers; d <= 1536)
-        float xv[6];
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const int k = tid + 256 * i;
-            xv[i] = k < d ? __ldcg(fq.x + (int64_t)b * d + k) : 0.f;
-            sum += xv[i];
-        }
-        sum = warp_sum(sum);
-        if (lane == 0) s_red[warp] = sum;
-        __syncthreads();
-        float mean = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) mean += s_red[w];
-        mean /= (float)d;
-        __syncthreads();
-        float sq = 0.f;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const int k = tid + 256 * i;
-            if (k < d) { xv[i] -= mean; sq += xv[i] * xv[i]; }
-        }
-        sq = warp_sum(sq);
-        if (lane == 0) s_red[warp] = sq;
-        __syncthreads();
-        float var = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) var += s_red[w];
-        const float rstd = rsqrtf(var / (float)d + 1e-5f);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const int k = tid + 256 * i;
-            if (k < d) s_sc[k] = Op16<T>::to_f32(Op16<T>::from_f32(xv[i] * rstd * __ldg(fq.ln_g + k) + __ldg(fq.ln_b + k)));
-        }
-        __syncthreads();
-        // q_h[j] = Wq[h*64 + j, :] . h + bq : 4 threads per output row, each a contiguous quarter of K
-        const int j = tid >> 2, part = tid & 3;
-        const int kq = d >> 2;                       // d % 32 == 0
-        const T* wr = reinterpret_cast<const T*>(fq.wq) + (int64_t)(h * 64 + j) * d + part * kq;
-        const float* hr = s_sc + part * kq;
-        float acc = 0.f;
-        for (int k = 0; k < kq; k += 8) {
-            const uint4 u = ldg_nc_v4(wr + k);
-            float2 f;
-            f = Op16<T>::unpack2(u.x); acc = fmaf(f.x, hr[k + 0], acc); acc = fmaf(f.y, hr[k + 1], acc);
-            f = Op16<T>::unpack2(u.y); acc = fmaf(f.x, hr[k + 2], acc); acc = fmaf(f.y, hr[k + 3], acc);
-            f = Op16<T>::unpack2(u.z); acc = fmaf(f.x, hr[k + 4], acc); acc = fmaf(f.y, hr[k + 5], acc);
-            f = Op16<T>::unpack2(u.w); acc = fmaf(f.x, hr[k + 6], acc); acc = fmaf(f.y, hr[k + 7], acc);
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        __syncthreads();                              // everyone is done reading the activation row in s_sc
-        if (part == 0) s_q[j] = Op16<T>::to_f32(Op16<T>::from_f32(acc + __ldg(fq.bq + h * 64 + j))) * 0.125f;
+    if (tid < 32) {
+        const float2 f = Op16<T>::unpack2(__ldcg(reinterpret_cast<const uint32_t*>(q + (int64_t)b * ldq + h * 64) + tid));
+        s_q[2 * tid] = f.x * 0.125f; s_q[2 * tid + 1] = f.y * 0.125f;
     }
     for (int tI = 0; tI < n_tiles; ++tI) {
         const int buf = tI & 1;

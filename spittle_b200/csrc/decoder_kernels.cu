@@ -2,7 +2,7 @@
 // a7 / a8 of 8(a)).  One "step" advances every live sequence of the batch by one token; all
 // sequences share the same position (prompt is identical), finished ones are masked.
 //
-//   k_dec_embed           x = token_embedding[tok] + positional_embedding[pos]
+//   k_dec_ln              LayerNorm of the residual stream (+ token / positional embedding at layer 0)
 //   k_skinny_gemm         Y[B,N] = X[B,K] W[N,K]^T (+bias, GELU, +residual); B <= 64 per pass,
 //                         HBM-bound weight streaming; tensor cores via mma.sync with the weight
 //                         rows as the M operand, 8 warps split K, smem reduction, fused epilogue
@@ -19,20 +19,6 @@ namespace sb {
 extern std::atomic<uint64_t> g_launches;
 
 // ------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) k_dec_embed(const T* __restrict__ tok_emb, const float* __restrict__ pos_emb,
-                                                   const int* __restrict__ tokens, const int* __restrict__ pos_ptr,
-                                                   float* __restrict__ x, int d) {
-    const int b = blockIdx.x;
-    pdl_wait();
-    pdl_trigger();
-    const int tok = __ldcg(tokens + b);
-    const int pos = __ldcg(pos_ptr);
-    for (int i = threadIdx.x; i < d; i += blockDim.x)
-        x[(int64_t)b * d + i] = Op16<T>::to_f32(tok_emb[(int64_t)tok * d + i]) + pos_emb[(int64_t)pos * d + i];
-}
-
-// ------------------------------------------------------------------------------------------
 // stand-alone launches of the shared stage bodies (decoder_bodies.cuh), chained with PDL
 // ------------------------------------------------------------------------------------------
 // skinny GEMM.  grid.x = ceil(N/16) row tiles, grid.y = batch chunks of 64.  256 threads.
@@ -41,7 +27,7 @@ __global__ void __launch_bounds__(256) k_skinny_gemm(const T* __restrict__ X, in
                                                      int Bn, int N, int K, SkinnyEpilogue ep) {
     __shared__ __align__(16) unsigned char smem[kSkinnySmem / 2];
     PdlSync sync;
-    skinny_body<T, 1>(X, ldx, W, ldw, Bn, N, 0, K / 32, ep, nullptr, 0, blockIdx.x, blockIdx.y, smem, sync);
+    skinny_body<T, 1>(X, ldx, W, ldw, Bn, N, K, ep, blockIdx.x, blockIdx.y, smem, sync);
 }
 // 32 weight rows per block: half as many blocks each ingest the shared [B, K] activation matrix (the L2 -> SM traffic of
 // a launch is blocks x 98 KB), and a wide projection (QKV, FC1) leaves SMs free for the other decode lane
@@ -50,55 +36,110 @@ __global__ void __launch_bounds__(256) k_skinny_gemm_w32(const T* __restrict__ X
                                                          int Bn, int N, int K, SkinnyEpilogue ep) {
     extern __shared__ __align__(16) unsigned char smem_w32[];
     PdlSync sync;
-    skinny_body<T, 2>(X, ldx, W, ldw, Bn, N, 0, K / 32, ep, nullptr, 0, blockIdx.x, blockIdx.y, smem_w32, sync);
+    skinny_body<T, 2>(X, ldx, W, ldw, Bn, N, K, ep, blockIdx.x, blockIdx.y, smem_w32, sync);
 }
 
-// split-K variant: grid.x = tiles * ks; block (tile, slice) stores raw f32 sums of its K slice to part[slice]
-// (no epilogue); the consumer (k_dec_ln) adds bias + slices in slice order.  Less activation per block:
-// these launches are bound by each SM's L2 ingest of the shared [B, K] activation matrix, not by the weights.
-template <typename T>
-__global__ void __launch_bounds__(256) k_skinny_gemm_splitk(const T* __restrict__ X, int ldx, const T* __restrict__ W, int ldw,
-                                                            int Bn, int N, int K, int ks, float* __restrict__ part,
-                                                            int64_t part_stride) {
-    __shared__ __align__(16) unsigned char smem[kSkinnySmem / 2];
-    PdlSync sync;
-    const int tiles = (N + 15) / 16;
-    const int sI = blockIdx.x / tiles, tile = blockIdx.x - sI * tiles;
-    const int kb = K / 32;
-    const int kb0 = (int)((int64_t)kb * sI / ks), kb1 = (int)((int64_t)kb * (sI + 1) / ks);
-    SkinnyEpilogue ep{};
-    skinny_body<T, 1>(X, ldx, W, ldw, Bn, N, kb0, kb1, ep, part + sI * part_stride, N, tile, blockIdx.y, smem, sync);
-}
-
-// decoder LayerNorm, one warp (= one block) per row so the 64 rows spread over 64 SMs:
-// optional embedding (x = tok_emb[tok] + pos_emb[pos]) or split-K completion of the residual stream
-// (x += bias + sum_s part[s]) first, then LN -> 16-bit h.
+// decoder LayerNorm, one warp (= one block) per row so the rows spread over as many SMs:
+// optional embedding (x = tok_emb[tok] + pos_emb[pos]) first, then LN -> 16-bit h.
 template <typename T, int VPL>
 __global__ void __launch_bounds__(32) k_dec_ln(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                T* __restrict__ out16, int d, const T* __restrict__ tok_emb,
                                                const float* __restrict__ pos_emb, const int* __restrict__ next_tokens,
-                                               const int* __restrict__ pos_ptr, const float* __restrict__ part, int nparts,
-                                               int64_t part_stride, const float* __restrict__ pbias) {
+                                               const int* __restrict__ pos_ptr) {
     struct S { __device__ __forceinline__ void wait() { pdl_wait(); pdl_trigger(); } } sync;
-    ln_row_mega<T, VPL>(x, gamma, beta, out16, blockIdx.x, d, tok_emb, pos_emb, next_tokens, pos_ptr, part, nparts, part_stride,
-                        pbias, sync);
+    ln_row_dec<T, VPL>(x, gamma, beta, out16, blockIdx.x, d, tok_emb, pos_emb, next_tokens, pos_ptr, sync);
 }
 
-// self attention for one new token per sequence.  grid = B * n_head / 4, 128 threads (warp per (b, head)).
+// self attention for one new token per sequence.  grid = (n_head, B), 128 threads: the four warps of a block split the
+// <= 448 cached keys of one (sequence, head) -- scores with lane <-> key, P V with lane <-> dim pair and the keys
+// interleaved over the warps -- so the two dependent sweeps over the cache are a quarter as long as with one warp.
 template <typename T>
 __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc,
                                                        T* __restrict__ out, const int* __restrict__ pos_ptr,
-                                                       const SeqState* __restrict__ state, int Bn, int n_head, int d,
-                                                       int n_text_ctx) {
-    __shared__ float s_p[4][448];
-    const int warp = threadIdx.x >> 5;
-    const int idx = blockIdx.x * 4 + warp;
+                                                       const SeqState* __restrict__ state, int n_head, int d, int n_text_ctx) {
+    __shared__ float s_p[448];
+    __shared__ float s_red[4];
+    __shared__ float s_o[4][64];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.x, b = blockIdx.y;
     pdl_wait();
     pdl_trigger();
-    if (idx >= Bn * n_head) return;
-    const int b = idx / n_head, h = idx - b * n_head;
     if (state && __ldcg(&state[b].done)) return;        // finished sequences are skipped
-    self_attn_warp<T>(qkv, kc, vc, out, __ldcg(pos_ptr), b, h, d, n_text_ctx, s_p[warp]);
+    const int pos = __ldcg(pos_ptr);                     // index of the new token; attends to [0, pos]
+    const T* q = qkv + (int64_t)b * 3 * d + h * 64;
+    T* kb = kc + ((int64_t)b * n_text_ctx) * d + h * 64;
+    T* vb = vc + ((int64_t)b * n_text_ctx) * d + h * 64;
+    if (warp == 0) {                                     // append this step's K, V (each lane moves 2 elements)
+        reinterpret_cast<uint32_t*>(kb + (int64_t)pos * d)[lane] = __ldcg(reinterpret_cast<const uint32_t*>(q + d) + lane);
+        reinterpret_cast<uint32_t*>(vb + (int64_t)pos * d)[lane] = __ldcg(reinterpret_cast<const uint32_t*>(q + 2 * d) + lane);
+    }
+    float qf[64];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const float2 f = Op16<T>::unpack2(__ldcg(reinterpret_cast<const uint32_t*>(q) + i));
+        qf[2 * i] = f.x; qf[2 * i + 1] = f.y;
+    }
+    __syncthreads();                                     // the appended row is visible to the whole block
+    const int n_keys = pos + 1;
+    float mx = -INFINITY;
+    for (int k = tid; k < n_keys; k += 128) {
+        const uint4* kr = reinterpret_cast<const uint4*>(kb + (int64_t)k * d);
+        float sc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 u = __ldcg(kr + c);
+            float2 f;
+            f = Op16<T>::unpack2(u.x); sc = fmaf(qf[c * 8 + 0], f.x, sc); sc = fmaf(qf[c * 8 + 1], f.y, sc);
+            f = Op16<T>::unpack2(u.y); sc = fmaf(qf[c * 8 + 2], f.x, sc); sc = fmaf(qf[c * 8 + 3], f.y, sc);
+            f = Op16<T>::unpack2(u.z); sc = fmaf(qf[c * 8 + 4], f.x, sc); sc = fmaf(qf[c * 8 + 5], f.y, sc);
+            f = Op16<T>::unpack2(u.w); sc = fmaf(qf[c * 8 + 6], f.x, sc); sc = fmaf(qf[c * 8 + 7], f.y, sc);
+        }
+        sc *= 0.125f;
+        s_p[k] = sc;
+        mx = fmaxf(mx, sc);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    __syncthreads();
+    float sum = 0.f;
+    for (int k = tid; k < n_keys; k += 128) {
+        const float p = __expf(s_p[k] - mx);
+        s_p[k] = p;
+        sum += p;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) s_red[warp] = sum;
+    __syncthreads();
+    const float inv = 1.0f / (((s_red[0] + s_red[1]) + s_red[2]) + s_red[3]);
+    // P V: warp w takes keys w, w + 4, ...; lane <-> 2 output dims; probabilities rounded to the operand type like
+    // ggml's mul_mat; 16 value loads are issued before their FMAs
+    float o0 = 0.f, o1 = 0.f;
+    for (int k0 = warp; k0 < n_keys; k0 += 64) {
+        uint32_t vv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int k = min(k0 + 4 * i, n_keys - 1);
+            vv[i] = __ldcg(reinterpret_cast<const uint32_t*>(vb + (int64_t)k * d) + lane);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int k = k0 + 4 * i;
+            if (k < n_keys) {
+                const float p = Op16<T>::to_f32(Op16<T>::from_f32(s_p[k] * inv));
+                const float2 f = Op16<T>::unpack2(vv[i]);
+                o0 = fmaf(p, f.x, o0); o1 = fmaf(p, f.y, o1);
+            }
+        }
+    }
+    s_o[warp][2 * lane] = o0; s_o[warp][2 * lane + 1] = o1;
+    __syncthreads();
+    if (warp == 0) {
+        const float a0 = ((s_o[0][2 * lane] + s_o[1][2 * lane]) + s_o[2][2 * lane]) + s_o[3][2 * lane];
+        const float a1 = ((s_o[0][2 * lane + 1] + s_o[1][2 * lane + 1]) + s_o[2][2 * lane + 1]) + s_o[3][2 * lane + 1];
+        reinterpret_cast<uint32_t*>(out + (int64_t)b * d + h * 64)[lane] = Op16<T>::pack2(a0, a1);
+    }
 }
 
 // cross attention.  grid = (n_head, B), 256 threads.
@@ -106,13 +147,13 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_dec_cross_attn(const T* __restrict__ q, int ldq, const T* __restrict__ kbase,
                                                         const T* __restrict__ vbase, int64_t ld_kv, int64_t win_stride,
                                                         T* __restrict__ out, const SeqState* __restrict__ state, int d,
-                                                        int n_ctx, FusedQ fq) {
+                                                        int n_ctx) {
     __shared__ __align__(16) unsigned char smem[kCrossSmem];
     // a finished sequence no longer needs its 2 x 1500 x 64 keys/values streamed: `done` was written by the
     // sampler of an earlier step (many launches ago), so it may be read before the dependency wait
     if (state && __ldcg(&state[blockIdx.y].done)) { pdl_wait(); pdl_trigger(); return; }
     PdlSync sync;
-    cross_attn_body<T>(q, ldq, kbase, vbase, ld_kv, win_stride, out, d, n_ctx, fq, blockIdx.x, blockIdx.y, smem, sync);
+    cross_attn_body<T>(q, ldq, kbase, vbase, ld_kv, win_stride, out, d, n_ctx, blockIdx.x, blockIdx.y, smem, sync);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -365,24 +406,15 @@ __global__ void __launch_bounds__(32) k_lang_detect(const float* __restrict__ lo
 }
 
 // advance the shared position / step counters (single thread) after a step
-__global__ void k_dec_advance(int* pos_ptr, int* step_ptr, int n_prompt, unsigned* barrier) {
+__global__ void k_dec_advance(int* pos_ptr, int* step_ptr, int n_prompt) {
     pdl_wait();
     pdl_trigger();
-    if (barrier) *barrier = 0u;      // grid-barrier counter of the step megakernel
     const int p = __ldcg(pos_ptr);
     if (p >= n_prompt - 1) *step_ptr = __ldcg(step_ptr) + 1;
     *pos_ptr = p + 1;
 }
 
 // ---- launchers -------------------------------------------------------------------------
-template <typename T>
-int dec_embed(const T* tok_emb, const float* pos_emb, const int* tokens, const int* pos_ptr, float* x, int Bn, int d,
-              cudaStream_t st) {
-    launch_pdl(k_dec_embed<T>, dim3(Bn), dim3(256), 0, st, tok_emb, pos_emb, tokens, pos_ptr, x, d);
-    g_launches += 1;
-    SB_CUDA_CHECK(cudaGetLastError());
-    return SB_OK;
-}
 template <typename T>
 int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, const SkinnyEpilogue& ep, cudaStream_t st) {
     SB_CHECK_ARG(K % 32 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "skinny gemm: K % 32 and 16-byte row alignment required");
@@ -405,24 +437,12 @@ int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, 
     return SB_OK;
 }
 template <typename T>
-int skinny_gemm_splitk(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, int ks, float* part, int64_t part_stride,
-                       cudaStream_t st) {
-    SB_CHECK_ARG(K % 32 == 0 && ldx % 8 == 0 && ldw % 8 == 0 && ks >= 1 && ks <= kMegaMaxSplit && K / 32 >= ks,
-                 "split-K skinny gemm: K % 32, 16-byte row alignment, 1 <= ks <= 6");
-    dim3 grid(ceil_div(N, 16) * ks, ceil_div(Bn, 64));
-    launch_pdl(k_skinny_gemm_splitk<T>, grid, dim3(256), 0, st, X, ldx, W, ldw, Bn, N, K, ks, part, part_stride);
-    g_launches += 1;
-    SB_CUDA_CHECK(cudaGetLastError());
-    return SB_OK;
-}
-template <typename T>
 int dec_ln(float* x, const float* gamma, const float* beta, T* out16, int rows, int d, const T* tok_emb, const float* pos_emb,
-           const int* next_tokens, const int* pos_ptr, const float* part, int nparts, int64_t part_stride, const float* pbias,
-           cudaStream_t st) {
-    SB_CHECK_ARG(d % 4 == 0 && d <= 1536 && nparts >= 0 && nparts <= kMegaMaxSplit, "decoder layernorm: d % 4, d <= 1536");
-    if (d <= 768) launch_pdl(k_dec_ln<T, 6>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr, part, nparts, part_stride, pbias);
-    else if (d <= 1280) launch_pdl(k_dec_ln<T, 10>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr, part, nparts, part_stride, pbias);
-    else launch_pdl(k_dec_ln<T, 12>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr, part, nparts, part_stride, pbias);
+           const int* next_tokens, const int* pos_ptr, cudaStream_t st) {
+    SB_CHECK_ARG(d % 4 == 0 && d <= 1536, "decoder layernorm: d % 4, d <= 1536");
+    if (d <= 768) launch_pdl(k_dec_ln<T, 6>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr);
+    else if (d <= 1280) launch_pdl(k_dec_ln<T, 10>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr);
+    else launch_pdl(k_dec_ln<T, 12>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
@@ -431,17 +451,17 @@ template <typename T>
 int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const int* pos_ptr, const SeqState* state, int Bn, int n_head, int d,
                   int n_text_ctx, cudaStream_t st) {
     SB_CHECK_ARG(n_text_ctx <= 448 && d == n_head * 64, "self attention: n_text_ctx <= 448, d_head 64");
-    launch_pdl(k_dec_self_attn<T>, dim3(ceil_div(Bn * n_head, 4)), dim3(128), 0, st, qkv, kc, vc, out, pos_ptr, state, Bn, n_head, d, n_text_ctx);
+    launch_pdl(k_dec_self_attn<T>, dim3(n_head, Bn), dim3(128), 0, st, qkv, kc, vc, out, pos_ptr, state, n_head, d, n_text_ctx);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
 }
 template <typename T>
 int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t ld_kv, int64_t win_stride, T* out,
-                   const SeqState* state, int Bn, int n_head, int d, int n_ctx, const FusedQ& fq, cudaStream_t st) {
+                   const SeqState* state, int Bn, int n_head, int d, int n_ctx, cudaStream_t st) {
     SB_CHECK_ARG(n_ctx <= 1504 && d == n_head * 64 && d <= 1504 && d % 32 == 0, "cross attention: n_audio_ctx, d <= 1504, d_head 64");
     dim3 grid(n_head, Bn);
-    launch_pdl(k_dec_cross_attn<T>, grid, dim3(256), 0, st, q, ldq, kbase, vbase, ld_kv, win_stride, out, state, d, n_ctx, fq);
+    launch_pdl(k_dec_cross_attn<T>, grid, dim3(256), 0, st, q, ldq, kbase, vbase, ld_kv, win_stride, out, state, d, n_ctx);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
@@ -467,20 +487,18 @@ int lang_detect_step(const float* logits, int ld, int* prompt, int n_prompt, con
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
 }
-int dec_advance(int* pos_ptr, int* step_ptr, int n_prompt, unsigned* barrier, cudaStream_t st) {
-    launch_pdl(k_dec_advance, dim3(1), dim3(1), 0, st, pos_ptr, step_ptr, n_prompt, barrier);
+int dec_advance(int* pos_ptr, int* step_ptr, int n_prompt, cudaStream_t st) {
+    launch_pdl(k_dec_advance, dim3(1), dim3(1), 0, st, pos_ptr, step_ptr, n_prompt);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
 }
 
 #define SB_INST_D(T)                                                                                              \
-    template int dec_embed<T>(const T*, const float*, const int*, const int*, float*, int, int, cudaStream_t);    \
     template int skinny_gemm<T>(const T*, int, const T*, int, int, int, int, const SkinnyEpilogue&, cudaStream_t); \
-    template int skinny_gemm_splitk<T>(const T*, int, const T*, int, int, int, int, int, float*, int64_t, cudaStream_t); \
-    template int dec_ln<T>(float*, const float*, const float*, T*, int, int, const T*, const float*, const int*, const int*, const float*, int, int64_t, const float*, cudaStream_t); \
+    template int dec_ln<T>(float*, const float*, const float*, T*, int, int, const T*, const float*, const int*, const int*, cudaStream_t); \
     template int dec_self_attn<T>(const T*, T*, T*, T*, const int*, const SeqState*, int, int, int, int, cudaStream_t);             \
-    template int dec_cross_attn<T>(const T*, int, const T*, const T*, int64_t, int64_t, T*, const SeqState*, int, int, int, int, const FusedQ&, cudaStream_t);
+    template int dec_cross_attn<T>(const T*, int, const T*, const T*, int64_t, int64_t, T*, const SeqState*, int, int, int, int, cudaStream_t);
 SB_INST_D(__nv_bfloat16)
 SB_INST_D(__half)
 

@@ -199,12 +199,6 @@ struct Engine : EngineBase {
     Lane lanes[kMaxLanes];
     cudaEvent_t ev_fork = nullptr;
     int n_lanes_cfg = 2;
-    bool fused_q = false;
-    bool use_mega = false;     // env SB_DEC_MEGA=1: persistent per-step megakernel instead of one PDL-chained launch per stage
-                               // (measured SLOWER on B200: grid barriers cost ~2 us and one CTA/SM starves the cross-KV stream)
-    DevBuf b_declayers, b_dpart;
-    bool chain_split = false;   // env SB_DEC_SPLITK=1: residual projections of the PDL chain split along K (measured slower: 722 vs 568 ms)
-    bool mega_split = true;     // env SB_MEGA_SPLIT=0: no split-K / wide tiles in the megakernel projections
 
     ~Engine() override {
         for (auto& l : lanes) {
@@ -217,7 +211,7 @@ struct Engine : EngineBase {
         for (void* p : owned) cudaFree(p);
         DevBuf* bufs[] = {&b_pcm, &b_mel, &b_cmax, &b_floor, &b_clipmeta, &b_winmeta, &b_col1, &b_c1, &b_x, &b_h, &b_qkv,
                           &b_att, &b_mlp, &b_enc32, &b_ckv, &b_kself, &b_vself, &b_dx, &b_dh, &b_dqkv, &b_datt, &b_dq,
-                          &b_dmlp, &b_logits, &b_state, &b_tokens, &b_margins, &b_next, &b_forced, &b_ctr, &b_prompt, &b_declayers, &b_dpart};
+                          &b_dmlp, &b_logits, &b_state, &b_tokens, &b_margins, &b_next, &b_forced, &b_ctr, &b_prompt};
         for (DevBuf* b : bufs) b->release();
         if (melplan) sb_melplan_destroy(melplan);
         if (h_ctr) cudaFreeHost(h_ctr);
@@ -329,10 +323,6 @@ struct Engine : EngineBase {
             SB_CUDA_CHECK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
         }
         SB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-        if (const char* e = getenv("SB_FUSED_Q")) fused_q = e[0] == '1';
-        if (const char* e = getenv("SB_DEC_MEGA")) use_mega = e[0] != '0';
-        if (const char* e = getenv("SB_MEGA_SPLIT")) mega_split = e[0] != '0';
-        if (const char* e = getenv("SB_DEC_SPLITK")) chain_split = e[0] != '0';
         if (const char* e = getenv("SB_DECODE_LANES")) { n_lanes_cfg = atoi(e); if (n_lanes_cfg < 1) n_lanes_cfg = 1; if (n_lanes_cfg > kMaxLanes) n_lanes_cfg = kMaxLanes; }
         int rc = sb_melplan_create(f.mel_filters.data(), hp.n_mels, &melplan);
         if (rc) return rc;
@@ -459,7 +449,6 @@ struct Engine : EngineBase {
         if ((rc = b_next.ensure(W * 4))) return rc;
         if ((rc = b_ctr.ensure(64 * kMaxLanes))) return rc;
         if ((rc = b_prompt.ensure(64))) return rc;
-        if ((rc = b_dpart.ensure((size_t)kMegaMaxSplit * W * d * 4))) return rc;
         return SB_OK;
     }
 
@@ -480,42 +469,8 @@ struct Engine : EngineBase {
         // teacher-forced traces keep every sequence alive (their `done` flag only marks where free-running would stop)
         const SeqState* seq_state = sa.forced ? nullptr : sa.state;
         int rc;
-        if (use_mega) {
-            // one persistent cooperative kernel for embedding + all layers + final LayerNorm (decoder_mega.cu)
-            DecStepArgs ma{};
-            ma.Bn = Wl; ma.d = d; ma.n_head = hp.n_text_head; ma.n_layer = hp.n_text_layer; ma.n_ctx = nctx; ma.n_text_ctx = hp.n_text_ctx;
-            ma.ld_kv = nkv; ma.win_stride = (int64_t)nctx * nkv;
-            ma.tok_emb = tok_emb; ma.pos_emb = dec_pos; ma.next_tokens = b_next.as<int>() + w0; ma.pos_ptr = pos_ptr;
-            ma.state = seq_state; ma.x = dx; ma.h = dh; ma.qkv = dqkv; ma.att = datt; ma.q = dq; ma.mlp = dmlp;
-            ma.lnf_g = ln_f.g; ma.lnf_b = ln_f.b; ma.barrier = reinterpret_cast<unsigned*>(ctr + 8);
-            { const char* e = getenv("SB_MEGA_TRACE"); ma.trace = (e && e[0] == '1') ? 1 : 0; }
-            ma.part = b_dpart.as<float>(); ma.part_stride = (int64_t)Wl * d;
-            for (int k = 0; k < 11; ++k) { ma.mt[k] = 1; ma.ks[k] = 1; }
-            if (mega_split) {
-                const int G = num_sms();
-                mega_plan(3 * d, d, false, G, &ma.mt[1], &ma.ks[1]);
-                mega_plan(d, d, true, G, &ma.mt[3], &ma.ks[3]);
-                ma.mt[7] = ma.mt[3]; ma.ks[7] = ma.ks[3];
-                mega_plan(4 * d, d, false, G, &ma.mt[9], &ma.ks[9]);
-                mega_plan(d, 4 * d, true, G, &ma.mt[10], &ma.ks[10]);
-            }
-            if ((rc = dec_step_mega<T>(b_declayers.as<DecLayerDev>(), ma, sl))) return rc;
-            GemmEpilogue ge{logits, vpad, 1, nullptr, 0, nullptr, 0, 0};
-            if ((rc = gemm_tn(dtype, dh, d, tok_emb, d, Wl, vpad, d, ge, sl))) return rc;
-            if (detect_lang && (rc = lang_detect_step(logits, vpad, const_cast<int*>(sa.prompt), sa.n_prompt, pos_ptr, detect_out + w0, sp, Wl, sl))) return rc;
-            if ((rc = sample_step(logits, vpad, sa, Wl, sl))) return rc;
-            return dec_advance(pos_ptr, step_ptr, sa.n_prompt, ma.barrier, sl);
-        }
-        // PDL chain, one launch per stage.  The residual projections (O, cross O, FC2) are split along K: each
-        // block then ingests a third (or less) of the [B, K] activation matrix -- per-SM L2 ingest of that shared
-        // matrix is what bounds these launches -- and the following LayerNorm launch adds bias + slices to x.
-        int ks_o = 1, ks_fc2 = 1, mt_unused = 1;
-        if (chain_split && !fused_q) {
-            mega_plan(d, d, true, num_sms(), &mt_unused, &ks_o);
-            mega_plan(d, 4 * d, true, num_sms(), &mt_unused, &ks_fc2);
-        }
-        float* part = b_dpart.as<float>() + (int64_t)w0 * d;
-        const int64_t pstride = (int64_t)W * d;
+        // PDL chain, one launch per stage (what was measured against it and lost -- a persistent per-step megakernel,
+        // split-K / cluster projections, LayerNorm fused into the projections -- is in profiles/r1_mega_stage_trace.md)
         const bool pd = profile == 2 && prof_sample;
         auto sk = [&](const T* X, int ldx, const T* Wt, int ldw, int N, int K, const SkinnyEpilogue& ep) -> int {
             int r;
@@ -530,53 +485,35 @@ struct Engine : EngineBase {
             T* vc = b_vself.as<T>() + ((int64_t)l * W + w0) * hp.n_text_ctx * d;
             SkinnyEpilogue e{};
             // attn_ln; layer 0 forms x = token_embedding[tok] + positional_embedding[pos] first
-            if ((rc = dec_ln<T>(dx, L.ln1.g, L.ln1.b, dh, Wl, d, l == 0 ? tok_emb : nullptr, dec_pos, next_tok, pos_ptr, part,
-                                (l > 0 && ks_fc2 > 1) ? ks_fc2 : 0, pstride, l > 0 ? dec[l - 1].fc2.b : nullptr, sl))) return rc;
+            if ((rc = dec_ln<T>(dx, L.ln1.g, L.ln1.b, dh, Wl, d, l == 0 ? tok_emb : nullptr, dec_pos, next_tok, pos_ptr, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.qkv.b; e.out16 = dqkv; e.ldo16 = 3 * d;
             if ((rc = sk(dh, d, L.qkv.w, d, 3 * d, d, e))) return rc;
             if ((rc = dec_self_attn<T>(dqkv, kc, vc, datt, pos_ptr, seq_state, Wl, hp.n_text_head, d, hp.n_text_ctx, sl))) return rc;
-            if (ks_o > 1) { if ((rc = skinny_gemm_splitk<T>(datt, d, L.o.w, d, Wl, d, d, ks_o, part, pstride, sl))) return rc; }
-            else {
-                e = SkinnyEpilogue{}; e.bias = L.o.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
-                if ((rc = sk(datt, d, L.o.w, d, d, d, e))) return rc;
-            }
-            // cross_attn_ln + query projection can be fused into the cross-attention kernel's prologue
-            FusedQ fq;
-            if (fused_q) { fq.x = dx; fq.ln_g = L.ln2.g; fq.ln_b = L.ln2.b; fq.wq = L.cq.w; fq.bq = L.cq.b; }
-            else {
-                if ((rc = dec_ln<T>(dx, L.ln2.g, L.ln2.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, part, ks_o > 1 ? ks_o : 0,
-                                    pstride, L.o.b, sl))) return rc;
-                e = SkinnyEpilogue{}; e.bias = L.cq.b; e.out16 = dq; e.ldo16 = d;
-                if ((rc = sk(dh, d, L.cq.w, d, d, d, e))) return rc;
-            }
+            e = SkinnyEpilogue{}; e.bias = L.o.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
+            if ((rc = sk(datt, d, L.o.w, d, d, d, e))) return rc;
+            if ((rc = dec_ln<T>(dx, L.ln2.g, L.ln2.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, sl))) return rc;
+            e = SkinnyEpilogue{}; e.bias = L.cq.b; e.out16 = dq; e.ldo16 = d;
+            if ((rc = sk(dh, d, L.cq.w, d, d, d, e))) return rc;
             const T* kb = b_ckv.as<T>() + (int64_t)w0 * nctx * nkv + (int64_t)l * 2 * d;
             if (pd && (rc = prof_begin_on(3, 4.0 * nctx * d * (double)live_hint, sl))) return rc;
-            if ((rc = dec_cross_attn<T>(dq, d, kb, kb + d, nkv, (int64_t)nctx * nkv, datt, seq_state, Wl, hp.n_text_head, d, nctx, fq, sl))) return rc;
+            if ((rc = dec_cross_attn<T>(dq, d, kb, kb + d, nkv, (int64_t)nctx * nkv, datt, seq_state, Wl, hp.n_text_head, d, nctx, sl))) return rc;
             if (pd && (rc = prof_end_on(sl))) return rc;
-            if (ks_o > 1) { if ((rc = skinny_gemm_splitk<T>(datt, d, L.co.w, d, Wl, d, d, ks_o, part, pstride, sl))) return rc; }
-            else {
-                e = SkinnyEpilogue{}; e.bias = L.co.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
-                if ((rc = sk(datt, d, L.co.w, d, d, d, e))) return rc;
-            }
-            if ((rc = dec_ln<T>(dx, L.ln3.g, L.ln3.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, part, ks_o > 1 ? ks_o : 0, pstride,
-                                L.co.b, sl))) return rc;
+            e = SkinnyEpilogue{}; e.bias = L.co.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
+            if ((rc = sk(datt, d, L.co.w, d, d, d, e))) return rc;
+            if ((rc = dec_ln<T>(dx, L.ln3.g, L.ln3.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.fc1.b; e.act = 1; e.out16 = dmlp; e.ldo16 = 4 * d;
             if ((rc = sk(dh, d, L.fc1.w, d, 4 * d, d, e))) return rc;
-            if (ks_fc2 > 1) { if ((rc = skinny_gemm_splitk<T>(dmlp, 4 * d, L.fc2.w, 4 * d, Wl, d, 4 * d, ks_fc2, part, pstride, sl))) return rc; }
-            else {
-                e = SkinnyEpilogue{}; e.bias = L.fc2.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
-                if ((rc = sk(dmlp, 4 * d, L.fc2.w, 4 * d, d, 4 * d, e))) return rc;
-            }
+            e = SkinnyEpilogue{}; e.bias = L.fc2.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
+            if ((rc = sk(dmlp, 4 * d, L.fc2.w, 4 * d, d, 4 * d, e))) return rc;
         }
-        if ((rc = dec_ln<T>(dx, ln_f.g, ln_f.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, part, ks_fc2 > 1 ? ks_fc2 : 0, pstride,
-                            dec.back().fc2.b, sl))) return rc;
+        if ((rc = dec_ln<T>(dx, ln_f.g, ln_f.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, sl))) return rc;
         // tied-embedding logits: 80-130 MB of weights per step -> the TMA-fed tcgen05 GEMM streams them
         // (one 128-row tile of sequences, ~200 column tiles) instead of the small-N weight-streaming kernel
         GemmEpilogue ge{logits, vpad, 1, nullptr, 0, nullptr, 0, 0};
         if ((rc = gemm_tn(dtype, dh, d, tok_emb, d, Wl, vpad, d, ge, sl))) return rc;
         if (detect_lang && (rc = lang_detect_step(logits, vpad, const_cast<int*>(sa.prompt), sa.n_prompt, pos_ptr, detect_out + w0, sp, Wl, sl))) return rc;
         if ((rc = sample_step(logits, vpad, sa, Wl, sl))) return rc;
-        if ((rc = dec_advance(pos_ptr, step_ptr, sa.n_prompt, nullptr, sl))) return rc;
+        if ((rc = dec_advance(pos_ptr, step_ptr, sa.n_prompt, sl))) return rc;
         return SB_OK;
     }
 
@@ -640,27 +577,7 @@ struct Engine : EngineBase {
         const int total_steps = n_prompt - 1 + n_max;
         const bool graph = use_graph && !logits_out && profile != 2;
         // lanes: independent sub-batches on their own streams (one lane when tracing logits)
-        int n_lanes = (logits_out || use_mega) ? 1 : std::min(n_lanes_cfg, std::max(1, W / 8));
-        if (use_mega) {
-            // per-layer operand table of the step megakernel: the self-KV / cross-KV bases depend on W
-            const int d = hp.n_text_state, nkv = hp.n_text_layer * 2 * d;
-            std::vector<DecLayerDev> tab(hp.n_text_layer);
-            for (int l = 0; l < hp.n_text_layer; ++l) {
-                const DecLayer<T>& L = dec[l];
-                DecLayerDev& t = tab[l];
-                t.ln1_g = L.ln1.g; t.ln1_b = L.ln1.b; t.ln2_g = L.ln2.g; t.ln2_b = L.ln2.b; t.ln3_g = L.ln3.g; t.ln3_b = L.ln3.b;
-                t.qkv_w = L.qkv.w; t.o_w = L.o.w; t.cq_w = L.cq.w; t.co_w = L.co.w; t.fc1_w = L.fc1.w; t.fc2_w = L.fc2.w;
-                t.qkv_b = L.qkv.b; t.o_b = L.o.b; t.cq_b = L.cq.b; t.co_b = L.co.b; t.fc1_b = L.fc1.b; t.fc2_b = L.fc2.b;
-                t.kself = b_kself.as<T>() + (int64_t)l * W * hp.n_text_ctx * d;
-                t.vself = b_vself.as<T>() + (int64_t)l * W * hp.n_text_ctx * d;
-                t.cross_k = b_ckv.as<T>() + (int64_t)l * 2 * d;
-                t.cross_v = b_ckv.as<T>() + (int64_t)l * 2 * d + d;
-            }
-            (void)nkv;
-            if ((rc = b_declayers.ensure(tab.size() * sizeof(DecLayerDev)))) return rc;
-            SB_CUDA_CHECK(cudaMemcpyAsync(b_declayers.p, tab.data(), tab.size() * sizeof(DecLayerDev), cudaMemcpyHostToDevice, st));
-            SB_CUDA_CHECK(cudaStreamSynchronize(st));     // tab is a stack vector
-        }
+        int n_lanes = logits_out ? 1 : std::min(n_lanes_cfg, std::max(1, W / 8));
         struct LaneRun { int w0, Wl; bool finished; int steps; };
         std::vector<LaneRun> lr(n_lanes);
         for (int i = 0; i < n_lanes; ++i) {

@@ -114,25 +114,6 @@ def test_transcribe_matches_oracle_full(cuda_dev, model_dir, dtype):
     eng.close()
 
 
-def test_step_megakernel_matches_stage_launches(cuda_dev, model_dir, monkeypatch):
-    """The persistent per-step megakernel (decoder_mega.cu) and the one-launch-per-stage PDL chain
-    run the same stage bodies: tokens, margins and text must be bit-identical, including batches
-    where sequences finish at different steps (finished ones are skipped by the attention stages)."""
-    path = synth.ensure_model_file("nano", model_dir)
-    clips = [synth.make_clip(i, s) for i, s in ((1, 30.0), (2, 7.3), (5, 30.0), (4, 12.0), (6, 21.0), (7, 30.0))]
-    params = capi.default_params(n_max_tokens=48, max_windows=3)
-    out = {}
-    for mega in ("1", "0"):
-        monkeypatch.setenv("SB_DEC_MEGA", mega)
-        eng = capi.Engine(path, dtype=capi.SB_DTYPE_F16, max_batch=8)
-        out[mega] = eng.transcribe_batch(clips, params)
-        eng.close()
-    for a, b in zip(out["1"], out["0"]):
-        assert a.sampled == b.sampled and a.tokens == b.tokens and a.text == b.text
-        assert [w["n_tokens"] for w in a.windows] == [w["n_tokens"] for w in b.windows]
-    assert any(len(set(w["n_tokens"] for w in r.windows)) > 0 for r in out["1"])
-
-
 def test_language_auto_detect_matches_oracle(cuda_dev, model_dir):
     """params.language = NULL (the reference's default selected_language "auto", settings.rs:427-429):
     whisper_full detects the language from the first window ([sot] step, arg-max over the language tokens)
