@@ -43,6 +43,14 @@ def gelu_tanh(x: np.ndarray) -> np.ndarray:
     return (F32(0.5) * x * (F32(1.0) + np.tanh(c * x * (F32(1.0) + F32(0.044715) * x * x)))).astype(F32)
 
 
+def gelu_erf(x: np.ndarray) -> np.ndarray:
+    """Exact GELU (x/2)(1 + erf(x/sqrt 2)): what OpenAI/HF Whisper use; only for the HF cross-check
+    (tests/test_oracle_hf_cpu.py) -- whisper.cpp/ggml uses the tanh form above."""
+    from scipy.special import erf
+    x = x.astype(np.float64)
+    return (0.5 * x * (1.0 + erf(x / np.sqrt(2.0)))).astype(F32)
+
+
 def layer_norm(x: np.ndarray, w: np.ndarray, b: np.ndarray, eps: float = 1e-5) -> np.ndarray:
     x = x.astype(F32)
     mu = x.mean(axis=-1, keepdims=True, dtype=np.float64).astype(F32)
@@ -79,7 +87,9 @@ class WindowResult:
 
 
 class WhisperOracle:
-    def __init__(self, model, act_f16: bool = True):
+    def __init__(self, model, act_f16: bool = True, gelu: str = "tanh"):
+        assert gelu in ("tanh", "erf") and not (act_f16 and gelu == "erf")
+        self.gelu_kind = gelu
         self.m = model
         self.hp = model.hparams
         self.sp = model.special
@@ -99,7 +109,7 @@ class WhisperOracle:
             y = _h(gelu_tanh(_h(x)))
             y = np.where(x <= -10.0, F32(0), np.where(x >= 10.0, x, y))
             return y.astype(F32)
-        return gelu_tanh(x)
+        return gelu_erf(x) if self.gelu_kind == "erf" else gelu_tanh(x)
 
     def _heads(self, k, v, n_head):
         """K, V [Tk,d] -> f16-rounded per-head views (K^T [H,dh,Tk], V [H,Tk,dh])."""
