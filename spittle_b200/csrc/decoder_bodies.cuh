@@ -254,73 +254,102 @@ __device__ __forceinline__ void ln_row_dec(float* __restrict__ x, const float* _
 }
 
 // ------------------------------------------------------------------------------------------
-// cross attention of one (sequence b, head h) by one 256-thread block.  Kc/Vc rows are strided
-// (ld_kv) inside the fused cross-KV buffer [W*1500, L*2*d]; K then V are each streamed exactly
-// once through a cp.async double-buffered shared-memory tile.
+// cross attention of one (sequence b, head h) by one 256-thread block.  Kc/Vc rows are strided (ld_kv) inside the
+// fused cross-KV buffer [W*1500, L*2*d]; K then V are each streamed exactly once, straight into registers: the
+// streaming loops contain no shared-memory staging and no block barrier, and every warp keeps 4 KB of independent
+// 16-byte loads in flight (32 KB per block, 96 KB per SM at 3 blocks).  The K stream starts before the dependency
+// wait.  History (profiles/r1_cross_attn_stream.md): the first version staged 128-key cp.async tiles through shared
+// memory between two __syncthreads (one 16 KB tile in flight per block): 80 us per launch at 64 live sequences
+// (3.7 TB/s) in the decode chain; this form 49.6 us (5.95 TB/s = 91 % of the measured HBM peak).  A fused
+// "cross_attn_ln + query projection" prologue (two launches fewer per layer) was measured slower: streaming the
+// 98 KB weight slice through one block costs more than the two launches.
 // ------------------------------------------------------------------------------------------
-constexpr int kXKeysPerTile = 128;
-constexpr int kXLd = 72;   // padded row (elements)
-constexpr int kCrossSmem = 2 * kXKeysPerTile * kXLd * 2 + 1504 * 4 + 64 * 4 + 8 * 4 + 4 * 64 * 4;
+constexpr int kXU = 8;
+constexpr int kCrossSmem = 1504 * 4 + 8 * 4 + 8 * 64 * 4;
 
 template <typename T, typename Sync>
 __device__ __forceinline__ void cross_attn_body(const T* __restrict__ q, int ldq, const T* __restrict__ kbase,
-                                                const T* __restrict__ vbase, int64_t ld_kv, int64_t win_stride,
-                                                T* __restrict__ out, int d, int n_ctx, int h, int b,
-                                                unsigned char* smem, Sync& sync) {
-    T (*s_tile)[kXKeysPerTile * kXLd] = reinterpret_cast<T (*)[kXKeysPerTile * kXLd]>(smem);
-    float* s_sc = reinterpret_cast<float*>(smem + 2 * kXKeysPerTile * kXLd * 2);   // scores
-    float* s_q = s_sc + 1504;
-    float* s_red = s_q + 64;
+                                                       const T* __restrict__ vbase, int64_t ld_kv, int64_t win_stride,
+                                                       T* __restrict__ out, int d, int n_ctx, int h, int b,
+                                                       unsigned char* smem, Sync& sync) {
+    float* s_sc = reinterpret_cast<float*>(smem);        // scores / probabilities
+    float* s_red = s_sc + 1504;
     float (*s_o)[64] = reinterpret_cast<float (*)[64]>(s_red + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const T* kp = kbase + (int64_t)b * win_stride + h * 64;
-    const T* vp = vbase + (int64_t)b * win_stride + h * 64;
-    const int n_tiles = (n_ctx + kXKeysPerTile - 1) / kXKeysPerTile;
-
-    auto load_tile = [&](int buf, const T* src, int key0) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int idx = tid + 256 * i;      // 128 rows x 8 chunks
-            const int r = idx >> 3, c = idx & 7;
-            const int key = key0 + r;
-            const bool ok = key < n_ctx;
-            cp_async16_d((uint32_t)__cvta_generic_to_shared(&s_tile[buf][r * kXLd + c * 8]),
-                         src + (int64_t)(ok ? key : 0) * ld_kv + c * 8, ok);
-        }
-        asm volatile("cp.async.commit_group;");
+    const int sub = lane >> 3, ch = lane & 7;
+    // this lane's keys: key(it, u) = it * 256 + u * 32 + warp * 4 + sub
+    const int key_l = warp * 4 + sub;
+    const T* vp = vbase + (int64_t)b * win_stride + h * 64 + ch * 8 + (int64_t)key_l * ld_kv;
+    const int64_t u_stride = 32 * ld_kv;
+    // ---- pass 1: scores on the tensor cores.  A 16-key x 64-dim slab is the A operand of four m16n8k16 MMAs whose
+    // B operand carries q in column 0 (the other seven columns are zero): lane (g = lane / 4, t = lane % 4) loads
+    // 16 bytes = dims [32 hf + 8 t, +8) of rows g and g + 8; q is laid out with the same k permutation, so the
+    // products pair up (the skinny GEMM's fragment trick).  Per 2 KB of keys a warp issues 4 loads + 4 MMAs instead
+    // of ~200 unpack / FFMA / shuffle instructions: the CUDA-core form of this pass was issue-bound (59 % of the SM's
+    // issue slots at HBM speed).  Warp w takes slabs w, w + 8, ...; the ring keeps two slabs (4 KB per warp) in flight.
+    const int g = lane >> 2, t = lane & 3;
+    const int n_slab = (n_ctx + 15) >> 4;
+    // load cursor: rows g / g + 8 of the next slab to request; slabs are requested in the order they are consumed
+    // (warp, warp + 8, warp + 16, ...), so the cursor only ever advances by 128 rows
+    const T* kcur = kbase + (int64_t)b * win_stride + h * 64 + t * 8 + (int64_t)(warp * 16 + g) * ld_kv;
+    const int64_t row8 = 8 * ld_kv, slab_step = 128 * ld_kv;
+    int krow = warp * 16 + g;
+    auto slab_load = [&](uint4 (&dst)[4]) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        const bool v0 = krow < n_ctx, v1 = krow + 8 < n_ctx;
+        dst[0] = v0 ? ldg_nc_v4(kcur) : z;
+        dst[1] = v0 ? ldg_nc_v4(kcur + 32) : z;
+        dst[2] = v1 ? ldg_nc_v4(kcur + row8) : z;
+        dst[3] = v1 ? ldg_nc_v4(kcur + row8 + 32) : z;
+        kcur += slab_step; krow += 128;
     };
-
-    // ---- pass 1: scores ----
-    load_tile(0, kp, 0);          // the encoder wrote K/V long ago: start the stream before the dependency wait
-    sync.wait();
-    if (tid < 32) {
-        const float2 f = Op16<T>::unpack2(__ldcg(reinterpret_cast<const uint32_t*>(q + (int64_t)b * ldq + h * 64) + tid));
-        s_q[2 * tid] = f.x * 0.125f; s_q[2 * tid + 1] = f.y * 0.125f;
+    uint4 ka[4], kb2[4];
+    {
+        slab_load(ka);          // slab warp (rows past n_ctx load zeros)
+        slab_load(kb2);         // slab warp + 8
     }
-    for (int tI = 0; tI < n_tiles; ++tI) {
-        const int buf = tI & 1;
-        if (tI + 1 < n_tiles) { load_tile(buf ^ 1, kp, (tI + 1) * kXKeysPerTile); asm volatile("cp.async.wait_group 1;"); }
-        else asm volatile("cp.async.wait_group 0;");
-        __syncthreads();
-        if (tid < kXKeysPerTile) {
-            const int key = tI * kXKeysPerTile + tid;
-            const uint4* kr = reinterpret_cast<const uint4*>(&s_tile[buf][tid * kXLd]);
-            float s = 0.f;
+    sync.wait();           // (the K stream has started before the dependency wait: the encoder wrote K/V long ago)
+    // q fragment, read straight from the query projection's output: only column 0 (g == 0) is non-zero
+    uint32_t qb[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint4 u = kr[c];
-                float2 f;
-                f = Op16<T>::unpack2(u.x); s = fmaf(s_q[c * 8 + 0], f.x, s); s = fmaf(s_q[c * 8 + 1], f.y, s);
-                f = Op16<T>::unpack2(u.y); s = fmaf(s_q[c * 8 + 2], f.x, s); s = fmaf(s_q[c * 8 + 3], f.y, s);
-                f = Op16<T>::unpack2(u.z); s = fmaf(s_q[c * 8 + 4], f.x, s); s = fmaf(s_q[c * 8 + 5], f.y, s);
-                f = Op16<T>::unpack2(u.w); s = fmaf(s_q[c * 8 + 6], f.x, s); s = fmaf(s_q[c * 8 + 7], f.y, s);
-            }
-            if (key < n_ctx) s_sc[key] = s;
-        }
-        __syncthreads();
+    for (int i = 0; i < 8; ++i) qb[i] = 0u;
+    if (g == 0) {
+        const uint4* qg = reinterpret_cast<const uint4*>(q + (int64_t)b * ldq + h * 64 + t * 8);
+        const uint4 q0 = __ldcg(qg), q1 = __ldcg(qg + 4);        // dims [8 t, +8) and [32 + 8 t, +8)
+        qb[0] = q0.x; qb[1] = q0.y; qb[2] = q0.z; qb[3] = q0.w;
+        qb[4] = q1.x; qb[5] = q1.y; qb[6] = q1.z; qb[7] = q1.w;
     }
-    // prefetch the first V tile while the softmax statistics are reduced
-    load_tile(0, vp, 0);
+    auto slab_scores = [&](const uint4 (&a)[4], int slab) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        MmaOpD<T>::mma(c, a[0].x, a[2].x, a[0].y, a[2].y, qb[0], qb[1]);
+        MmaOpD<T>::mma(c, a[0].z, a[2].z, a[0].w, a[2].w, qb[2], qb[3]);
+        MmaOpD<T>::mma(c, a[1].x, a[3].x, a[1].y, a[3].y, qb[4], qb[5]);
+        MmaOpD<T>::mma(c, a[1].z, a[3].z, a[1].w, a[3].w, qb[6], qb[7]);
+        if (t == 0) {
+            const int r0 = slab * 16 + g;
+            if (r0 < n_ctx) s_sc[r0] = c[0] * 0.125f;
+            if (r0 + 8 < n_ctx) s_sc[r0 + 8] = c[2] * 0.125f;
+        }
+    };
+#pragma unroll 1
+    for (int slab = warp; slab < n_slab; slab += 16) {
+        uint4 cur[4] = {ka[0], ka[1], ka[2], ka[3]};
+        slab_load(ka);                                            // slab + 16
+        slab_scores(cur, slab);
+        if (slab + 8 < n_slab) {
+            uint4 cur2[4] = {kb2[0], kb2[1], kb2[2], kb2[3]};
+            slab_load(kb2);                                       // slab + 24
+            slab_scores(cur2, slab + 8);
+        }
+    }
+    uint4 ring[kXU];
+    const T* ld_p;
+    const int n_steps = ((n_ctx + 255) >> 8) * kXU;
+    // the first V rows do not depend on the softmax: request them before the block-wide reductions
+    ld_p = vp;
+#pragma unroll
+    for (int u = 0; u < kXU; ++u) { ring[u] = u * 32 + key_l < n_ctx ? ldg_nc_v4(ld_p) : make_uint4(0, 0, 0, 0); ld_p += u_stride; }
+    __syncthreads();
     float mx = -INFINITY;
     for (int k = tid; k < n_ctx; k += 256) mx = fmaxf(mx, s_sc[k]);
     mx = warp_max(mx);
@@ -339,36 +368,45 @@ __device__ __forceinline__ void cross_attn_body(const T* __restrict__ q, int ldq
 #pragma unroll
     for (int w = 0; w < 8; ++w) sum += s_red[w];
     const float inv = 1.0f / sum;
-    // ---- pass 2: O = P V ; thread -> (dim pair dp = tid % 32, key group kg = tid / 32) ----
-    float o0 = 0.f, o1 = 0.f;
-    for (int tI = 0; tI < n_tiles; ++tI) {
-        const int buf = tI & 1;
-        if (tI + 1 < n_tiles) { load_tile(buf ^ 1, vp, (tI + 1) * kXKeysPerTile); asm volatile("cp.async.wait_group 1;"); }
-        else asm volatile("cp.async.wait_group 0;");
-        __syncthreads();
-        const int key0 = tI * kXKeysPerTile;
-#pragma unroll 4
-        for (int r = warp; r < kXKeysPerTile; r += 8) {
-            const int key = key0 + r;
-            if (key >= n_ctx) break;
-            const float p = Op16<T>::to_f32(Op16<T>::from_f32(s_sc[key] * inv));
-            const float2 f = Op16<T>::unpack2(reinterpret_cast<const uint32_t*>(&s_tile[buf][r * kXLd])[lane]);
-            o0 = fmaf(p, f.x, o0); o1 = fmaf(p, f.y, o1);
+    // ---- pass 2: O = P V; lane accumulates its 8 dims over its keys ----
+    float oacc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) oacc[i] = 0.f;
+#pragma unroll 1
+    for (int s0 = 0; s0 < n_steps; s0 += kXU) {
+#pragma unroll
+        for (int u = 0; u < kXU; ++u) {
+            const uint4 vv = ring[u];
+            const int key = (s0 + u) * 32 + key_l;
+            if (key + 256 < n_ctx) ring[u] = ldg_nc_v4(ld_p);
+            ld_p += u_stride;
+            if (key < n_ctx) {
+                const float p = Op16<T>::to_f32(Op16<T>::from_f32(s_sc[key] * inv));
+                float2 f;
+                f = Op16<T>::unpack2(vv.x); oacc[0] = fmaf(p, f.x, oacc[0]); oacc[1] = fmaf(p, f.y, oacc[1]);
+                f = Op16<T>::unpack2(vv.y); oacc[2] = fmaf(p, f.x, oacc[2]); oacc[3] = fmaf(p, f.y, oacc[3]);
+                f = Op16<T>::unpack2(vv.z); oacc[4] = fmaf(p, f.x, oacc[4]); oacc[5] = fmaf(p, f.y, oacc[5]);
+                f = Op16<T>::unpack2(vv.w); oacc[6] = fmaf(p, f.x, oacc[6]); oacc[7] = fmaf(p, f.y, oacc[7]);
+            }
         }
-        __syncthreads();
     }
     sync.trigger();
-    // reduce the 8 key groups
-    if (warp >= 4) { s_o[warp - 4][2 * lane] = o0; s_o[warp - 4][2 * lane + 1] = o1; }
+    // reduce the four key sub-lanes of the warp, then the eight warps
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        oacc[i] += __shfl_xor_sync(0xffffffffu, oacc[i], 8);
+        oacc[i] += __shfl_xor_sync(0xffffffffu, oacc[i], 16);
+    }
+    if (sub == 0) {
+        *reinterpret_cast<float4*>(&s_o[warp][ch * 8]) = make_float4(oacc[0], oacc[1], oacc[2], oacc[3]);
+        *reinterpret_cast<float4*>(&s_o[warp][ch * 8 + 4]) = make_float4(oacc[4], oacc[5], oacc[6], oacc[7]);
+    }
     __syncthreads();
-    if (warp < 4) { o0 += s_o[warp][2 * lane]; o1 += s_o[warp][2 * lane + 1]; }
-    __syncthreads();
-    if (warp >= 1 && warp < 4) { s_o[warp][2 * lane] = o0; s_o[warp][2 * lane + 1] = o1; }
-    __syncthreads();
-    if (warp == 0) {
-        o0 += s_o[1][2 * lane] + s_o[2][2 * lane] + s_o[3][2 * lane];
-        o1 += s_o[1][2 * lane + 1] + s_o[2][2 * lane + 1] + s_o[3][2 * lane + 1];
-        reinterpret_cast<uint32_t*>(out + (int64_t)b * d + h * 64)[lane] = Op16<T>::pack2(o0, o1);
+    if (tid < 32) {
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { o0 += s_o[w][2 * tid]; o1 += s_o[w][2 * tid + 1]; }
+        reinterpret_cast<uint32_t*>(out + (int64_t)b * d + h * 64)[tid] = Op16<T>::pack2(o0, o1);
     }
 }
 

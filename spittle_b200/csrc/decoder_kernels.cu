@@ -14,9 +14,13 @@
 #include "decoder.cuh"
 #include "decoder_bodies.cuh"
 #include <cstdlib>
+#include <string>
 
 namespace sb {
 extern std::atomic<uint64_t> g_launches;
+// profiling knob (tools/ab_decode.sh): SB_DBG_SKIP bit mask drops whole stage classes from the step (1 cross-attention,
+// 2 projections, 4 LayerNorm, 8 self-attention) -- results are garbage, the point is the time of what is left
+static int dbg_skip() { static int v = getenv("SB_DBG_SKIP") ? atoi(getenv("SB_DBG_SKIP")) : 0; return v; }
 
 // ------------------------------------------------------------------------------------------
 // stand-alone launches of the shared stage bodies (decoder_bodies.cuh), chained with PDL
@@ -62,13 +66,25 @@ __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv
     __shared__ float s_o[4][64];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int h = blockIdx.x, b = blockIdx.y;
-    pdl_wait();
-    pdl_trigger();
-    if (state && __ldcg(&state[b].done)) return;        // finished sequences are skipped
+    // `done` and `pos` were written by the sampler / k_dec_advance of the previous step (many launches ago) and the cache
+    // rows [0, pos) by earlier steps: all of it may be touched before the dependency wait, so the rows this block is
+    // about to sweep are requested into L2 while the QKV projection in front of it is still finishing
+    const bool skip = state && __ldcg(&state[b].done);   // finished sequences are skipped
     const int pos = __ldcg(pos_ptr);                     // index of the new token; attends to [0, pos]
     const T* q = qkv + (int64_t)b * 3 * d + h * 64;
     T* kb = kc + ((int64_t)b * n_text_ctx) * d + h * 64;
     T* vb = vc + ((int64_t)b * n_text_ctx) * d + h * 64;
+    if (!skip) {
+        for (int k = tid; k < pos; k += 128) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + (int64_t)k * d));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + (int64_t)k * d + 32));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + (int64_t)k * d));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + (int64_t)k * d + 32));
+        }
+    }
+    pdl_wait();
+    pdl_trigger();
+    if (skip) return;
     if (warp == 0) {                                     // append this step's K, V (each lane moves 2 elements)
         reinterpret_cast<uint32_t*>(kb + (int64_t)pos * d)[lane] = __ldcg(reinterpret_cast<const uint32_t*>(q + d) + lane);
         reinterpret_cast<uint32_t*>(vb + (int64_t)pos * d)[lane] = __ldcg(reinterpret_cast<const uint32_t*>(q + 2 * d) + lane);
@@ -142,12 +158,12 @@ __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv
     }
 }
 
-// cross attention.  grid = (n_head, B), 256 threads.
+// cross attention.  grid = (n_head, B), 256 threads, 3 blocks per SM (80 registers: the K / V register rings).
 template <typename T>
-__global__ void __launch_bounds__(256) k_dec_cross_attn(const T* __restrict__ q, int ldq, const T* __restrict__ kbase,
-                                                        const T* __restrict__ vbase, int64_t ld_kv, int64_t win_stride,
-                                                        T* __restrict__ out, const SeqState* __restrict__ state, int d,
-                                                        int n_ctx) {
+__global__ void __launch_bounds__(256, 3) k_dec_cross_attn(const T* __restrict__ q, int ldq, const T* __restrict__ kbase,
+                                                           const T* __restrict__ vbase, int64_t ld_kv, int64_t win_stride,
+                                                           T* __restrict__ out, const SeqState* __restrict__ state, int d,
+                                                           int n_ctx) {
     __shared__ __align__(16) unsigned char smem[kCrossSmem];
     // a finished sequence no longer needs its 2 x 1500 x 64 keys/values streamed: `done` was written by the
     // sampler of an earlier step (many launches ago), so it may be read before the dependency wait
@@ -418,6 +434,7 @@ __global__ void k_dec_advance(int* pos_ptr, int* step_ptr, int n_prompt) {
 template <typename T>
 int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, const SkinnyEpilogue& ep, cudaStream_t st) {
     SB_CHECK_ARG(K % 32 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "skinny gemm: K % 32 and 16-byte row alignment required");
+    if (dbg_skip() & 2) return SB_OK;
     static const int w32_min_n = [] { const char* e = getenv("SB_DEC_W32_MIN_N"); return e ? atoi(e) : 2048; }();
     if (N >= w32_min_n) {
         static bool attr_done = false;
@@ -440,6 +457,7 @@ template <typename T>
 int dec_ln(float* x, const float* gamma, const float* beta, T* out16, int rows, int d, const T* tok_emb, const float* pos_emb,
            const int* next_tokens, const int* pos_ptr, cudaStream_t st) {
     SB_CHECK_ARG(d % 4 == 0 && d <= 1536, "decoder layernorm: d % 4, d <= 1536");
+    if (dbg_skip() & 4) return SB_OK;
     if (d <= 768) launch_pdl(k_dec_ln<T, 6>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr);
     else if (d <= 1280) launch_pdl(k_dec_ln<T, 10>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr);
     else launch_pdl(k_dec_ln<T, 12>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr);
@@ -451,6 +469,7 @@ template <typename T>
 int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const int* pos_ptr, const SeqState* state, int Bn, int n_head, int d,
                   int n_text_ctx, cudaStream_t st) {
     SB_CHECK_ARG(n_text_ctx <= 448 && d == n_head * 64, "self attention: n_text_ctx <= 448, d_head 64");
+    if (dbg_skip() & 8) return SB_OK;
     launch_pdl(k_dec_self_attn<T>, dim3(n_head, Bn), dim3(128), 0, st, qkv, kc, vc, out, pos_ptr, state, n_head, d, n_text_ctx);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
@@ -459,7 +478,9 @@ int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const int* pos_ptr, const 
 template <typename T>
 int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t ld_kv, int64_t win_stride, T* out,
                    const SeqState* state, int Bn, int n_head, int d, int n_ctx, cudaStream_t st) {
-    SB_CHECK_ARG(n_ctx <= 1504 && d == n_head * 64 && d <= 1504 && d % 32 == 0, "cross attention: n_audio_ctx, d <= 1504, d_head 64");
+    SB_CHECK_ARG(n_ctx <= 1504 && d == n_head * 64 && d <= 1504 && d % 32 == 0 && ldq % 8 == 0 && ld_kv % 8 == 0,
+                 "cross attention: n_audio_ctx, d <= 1504, d_head 64, 16-byte aligned rows");
+    if (dbg_skip() & 1) return SB_OK;
     dim3 grid(n_head, Bn);
     launch_pdl(k_dec_cross_attn<T>, grid, dim3(256), 0, st, q, ldq, kbase, vbase, ld_kv, win_stride, out, state, d, n_ctx);
     g_launches += 1;

@@ -491,10 +491,10 @@ struct Engine : EngineBase {
             if ((rc = dec_self_attn<T>(dqkv, kc, vc, datt, pos_ptr, seq_state, Wl, hp.n_text_head, d, hp.n_text_ctx, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.o.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
             if ((rc = sk(datt, d, L.o.w, d, d, d, e))) return rc;
+            const T* kb = b_ckv.as<T>() + (int64_t)w0 * nctx * nkv + (int64_t)l * 2 * d;
             if ((rc = dec_ln<T>(dx, L.ln2.g, L.ln2.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.cq.b; e.out16 = dq; e.ldo16 = d;
             if ((rc = sk(dh, d, L.cq.w, d, d, d, e))) return rc;
-            const T* kb = b_ckv.as<T>() + (int64_t)w0 * nctx * nkv + (int64_t)l * 2 * d;
             if (pd && (rc = prof_begin_on(3, 4.0 * nctx * d * (double)live_hint, sl))) return rc;
             if ((rc = dec_cross_attn<T>(dq, d, kb, kb + d, nkv, (int64_t)nctx * nkv, datt, seq_state, Wl, hp.n_text_head, d, nctx, sl))) return rc;
             if (pd && (rc = prof_end_on(sl))) return rc;
