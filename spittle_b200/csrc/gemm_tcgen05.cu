@@ -18,10 +18,21 @@
 // accumulator stage; tcgen05.commit releases smem stages and publishes accumulators.
 // Tile order is n-fastest so the CTAs running together share each A tile through L2 and A
 // streams from HBM once; W (a few MB) stays L2-resident.
+//
+// kCtas = 2 (large M): the two CTAs of a cluster (one TPC) work on one 256x256 tile with
+// tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and HALF of the W tile (128 of the 256 columns),
+// the leader CTA's MMA thread issues UMMA 256x256x16 for the pair, and each CTA's TMEM holds the accumulator rows
+// of its own A half.  Per k-block a CTA moves 32 KB through shared memory instead of 48 KB (the 1-CTA tile was
+// bound by shared-memory bandwidth: profiles/r1_full_gemm_tn.md), and the ring is 6 stages deep instead of 4.
+// Both producers signal the LEADER's full barrier (the peer through its cluster address), tcgen05.commit multicasts
+// the "stage free" / "accumulator ready" arrivals to both CTAs, and the peer's epilogue warps release the
+// accumulator stage on the leader's barrier.
 #include "common.cuh"
 #include "decoder.cuh"
 #include <cuda.h>
+#include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace sb {
@@ -30,15 +41,18 @@ extern std::atomic<uint64_t> g_launches;
 constexpr int kBM = 128;
 constexpr int kBN = 256;
 constexpr int kBK = 64;          // 64 x 2 B = 128 B = swizzle span
-constexpr int kStages = 4;
 constexpr int kUmmaK = 16;
 constexpr int kEpiWarps = 8;           // two per TMEM lane quarter, each takes half of the 256 columns
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kStagingBytes = 32 * 32 * 4;          // per epilogue warp: one 32x32 f32 chunk, XOR-swizzled
 constexpr int kStageBytesA = kBM * kBK * 2;
-constexpr int kStageBytesB = kBN * kBK * 2;
-constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * kStagingBytes;
+template <int kCtas> struct GemmCfg {
+    static constexpr int kStages = kCtas == 1 ? 4 : 6;
+    static constexpr int kRowsB = kBN / kCtas;                      // W rows (output columns) staged by one CTA
+    static constexpr int kStageBytesB = kRowsB * kBK * 2;
+    static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+    static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * kStagingBytes;
+};
 
 // ---- PTX wrappers ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,6 +82,40 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+// 2-CTA form: the data lands in this CTA's shared memory, the transaction bytes are counted on `bar`, a
+// shared::cluster address that may belong to the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {      // arrives on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -109,67 +157,90 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return d;
 }
 
-template <typename T>
+template <typename T, int kCtas>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tn(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
           GemmEpilogue ep, int M, int N, int K) {
+    using Cfg = GemmCfg<kCtas>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int kStageBytes = Cfg::kStageBytes;
+    constexpr int kTileM = kBM * kCtas;                    // rows of one output tile (of the CTA pair)
     extern __shared__ unsigned char smem_raw_g[];
     const uint32_t raw = smem_u32(smem_raw_g);
     const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024 B alignment
     unsigned char* base_ptr = smem_raw_g + (base - raw);
     const uint32_t bar_base = base + kStages * kStageBytes;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + kStages * kStageBytes + 128);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + kStages * kStageBytes + 192);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_m = (M + kBM - 1) / kBM, num_n = (N + kBN - 1) / kBN;
+    const uint32_t cta_rank = kCtas == 1 ? 0u : cluster_ctarank();
+    const int tile0 = blockIdx.x / kCtas, tile_step = gridDim.x / kCtas;    // tiles are dealt to clusters
+    const int num_m = (M + kTileM - 1) / kTileM, num_n = (N + kBN - 1) / kBN;
     const int num_tiles = num_m * num_n;
     const int num_kb = (K + kBK - 1) / kBK;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps * kCtas); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(2 * kBN));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if constexpr (kCtas == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(2 * kBN));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(2 * kBN));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kCtas == 1) __syncthreads(); else cluster_sync_all();    // the peer's barriers are initialised too
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 const int n_blk = tile % num_n, m_blk = tile / num_n;
+                const int row_a = m_blk * kTileM + (int)cta_rank * kBM;
+                const int row_b = n_blk * kBN + (int)cta_rank * Cfg::kRowsB;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
-                    mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
                     const uint32_t sa = base + stage * kStageBytes;
-                    tma_load_2d(sa, &tma_a, kb * kBK, m_blk * kBM, full_bar(stage));
-                    tma_load_2d(sa + kStageBytesA, &tma_b, kb * kBK, n_blk * kBN, full_bar(stage));
+                    if constexpr (kCtas == 1) {
+                        mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+                        tma_load_2d(sa, &tma_a, kb * kBK, row_a, full_bar(stage));
+                        tma_load_2d(sa + kStageBytesA, &tma_b, kb * kBK, row_b, full_bar(stage));
+                    } else {
+                        // the leader's barrier counts the bytes of both CTAs; a peer load that completes before the
+                        // leader's expect_tx only drives the transaction count negative for a moment
+                        if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * kStageBytes);
+                        const uint32_t fb = mapa_u32(full_bar(stage), 0);
+                        tma_load_2d_pair(sa, &tma_a, kb * kBK, row_a, fb);
+                        tma_load_2d_pair(sa + kStageBytesA, &tma_b, kb * kBK, row_b, fb);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=T, K-major both, N=256, M=128
+        if (lane == 0 && cta_rank == 0) {
+            // instruction descriptor: D=f32, A=B=T, K-major both, N=256, M=128 (256 for the CTA pair)
             const uint32_t idesc = (1u << 4) | ((uint32_t)Op16<T>::kUmmaFormat << 7) |
                                    ((uint32_t)Op16<T>::kUmmaFormat << 10) | ((uint32_t)(kBN >> 3) << 17) |
-                                   ((uint32_t)(kBM >> 4) << 24);
+                                   ((uint32_t)(kTileM >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 mbar_wait(tempty_bar(as), aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * kBN;
@@ -182,12 +253,13 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
                         // advance 16 elements = 32 B along K inside the swizzle atom: +2 in 16 B units
-                        tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        if constexpr (kCtas == 1) tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        else tc_mma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     }
-                    tc_commit(empty_bar(stage));
+                    if constexpr (kCtas == 1) tc_commit(empty_bar(stage)); else tc_commit_pair(empty_bar(stage));
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(tfull_bar(as));
+                if constexpr (kCtas == 1) tc_commit(tfull_bar(as)); else tc_commit_pair(tfull_bar(as));
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
@@ -199,9 +271,9 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
         const int rsub = lane >> 3;           // read-back: 4 rows per instruction, 8 lanes x float4 per row
         const int c4 = lane & 7;
         int as = 0; uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             const int n_blk = tile % num_n, m_blk = tile / num_n;
-            const int row_base = m_blk * kBM + q * 32;
+            const int row_base = m_blk * kTileM + (int)cta_rank * kBM + q * 32;
             // residual rows of this warp's 4 chunks are independent of the MMA: they are fetched one chunk
             // ahead (the first one before waiting for the accumulator) so their HBM latency is not exposed
             const int col_l = c4 * 4;
@@ -278,15 +350,19 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (lane == 0) {      // the accumulator stage is released on the barrier the MMA thread waits on: the leader's
+                if (kCtas == 1 || cta_rank == 0) mbar_arrive(tempty_bar(as));
+                else mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0));
+            }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kCtas == 1) __syncthreads(); else cluster_sync_all();    // neither CTA of a pair leaves while the other works
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kBN));
+        if constexpr (kCtas == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kBN));
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kBN));
     }
 }
 
@@ -347,23 +423,41 @@ int gemm_tn(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, i
     SB_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem");
     SB_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm: K and N must be multiples of 8");
     SB_CHECK_ARG(ep.out_f32 ? (ep.ldo % 4 == 0) : (ep.ldo % 8 == 0), "gemm: output row stride alignment");
+    // CTA pairs (cta_group::2, 256x256 tiles) when there are enough rows to fill the machine with them
+    static const int pair_min_m = [] { const char* e = getenv("SB_GEMM_PAIR_MIN_M"); return e ? atoi(e) : 4096; }();
+    const bool pair = M >= pair_min_m;
     CUtensorMap ta, tb;
     int rc = make_tmap_2d(&ta, A, dtype, M, K, lda, kBM);
     if (rc != SB_OK) return rc;
-    rc = make_tmap_2d(&tb, W, dtype, N, K, ldw, kBN);
+    rc = make_tmap_2d(&tb, W, dtype, N, K, ldw, pair ? GemmCfg<2>::kRowsB : GemmCfg<1>::kRowsB);
     if (rc != SB_OK) return rc;
-    const int num_tiles = ceil_div(M, kBM) * ceil_div(N, kBN);
-    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
     static bool attr_done = false;
     if (!attr_done) {
-        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::kSmem));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__half, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::kSmem));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__nv_bfloat16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::kSmem));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__half, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::kSmem));
         attr_done = true;
     }
-    if (dtype == SB_DTYPE_F16)
-        k_gemm_tn<__half><<<grid, kGemmThreads, kGemmSmem, st>>>(ta, tb, ep, M, N, K);
-    else
-        k_gemm_tn<__nv_bfloat16><<<grid, kGemmThreads, kGemmSmem, st>>>(ta, tb, ep, M, N, K);
+    if (pair) {
+        const int num_tiles = ceil_div(M, 2 * kBM) * ceil_div(N, kBN);
+        const int clusters = std::min(num_tiles, num_sms() / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = GemmCfg<2>::kSmem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (dtype == SB_DTYPE_F16) SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tn<__half, 2>, ta, tb, ep, M, N, K));
+        else SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tn<__nv_bfloat16, 2>, ta, tb, ep, M, N, K));
+    } else {
+        const int num_tiles = ceil_div(M, kBM) * ceil_div(N, kBN);
+        const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+        if (dtype == SB_DTYPE_F16)
+            k_gemm_tn<__half, 1><<<grid, kGemmThreads, GemmCfg<1>::kSmem, st>>>(ta, tb, ep, M, N, K);
+        else
+            k_gemm_tn<__nv_bfloat16, 1><<<grid, kGemmThreads, GemmCfg<1>::kSmem, st>>>(ta, tb, ep, M, N, K);
+    }
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
