@@ -53,7 +53,9 @@ __device__ __forceinline__ void cp_async16_d(uint32_t dst, const void* src, bool
 // MT = number of 16-row weight tiles per block (1, or 2 for the wide projections).
 constexpr int kSkinnySmem = 8 * 32 * 65 * 4;       // MT = 2; MT = 1 needs half
 
-template <typename T, int MT, typename Sync>
+// NJ = 8-sequence column tiles per block (8: 64 sequences; 4: 32 sequences -- half the accumulators and activation
+// ring, 96 registers, so a block can share an SM with two resident cross-attention blocks of the other decode lane).
+template <typename T, int MT, int NJ, typename Sync>
 __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, const T* __restrict__ W, int ldw, int Bn, int N,
                                             int K, const SkinnyEpilogue& ep, int tile, int chunk, unsigned char* smem, Sync& sync) {
     const int kb0 = 0, kb1 = K / 32;        // K % 32 == 0 enforced by the host
@@ -61,13 +63,13 @@ __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, co
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int row0 = tile * 16 * MT;
-    const int b0 = chunk * 64;
-    const int nb = min(64, Bn - b0);
-    float acc[MT][8][4];
+    const int b0 = chunk * (NJ * 8);
+    const int nb = min(NJ * 8, Bn - b0);
+    float acc[MT][NJ][4];
 #pragma unroll
     for (int m = 0; m < MT; ++m)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { acc[m][j][0] = acc[m][j][1] = acc[m][j][2] = acc[m][j][3] = 0.f; }
+        for (int j = 0; j < NJ; ++j) { acc[m][j][0] = acc[m][j][1] = acc[m][j][2] = acc[m][j][3] = 0.f; }
     const T* w_lo[MT];
     const T* w_hi[MT];
 #pragma unroll
@@ -79,7 +81,7 @@ __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, co
     // this warp's k-blocks: kb0 + warp, kb0 + warp + 8, ...  Weight loads are issued kWB blocks ahead of
     // their use (the HBM stream must be in flight before anything waits on it); the activation
     // rows come from L2 and are kept kXB blocks ahead.
-    constexpr int kWB = MT == 1 ? 4 : 2;
+    constexpr int kWB = (MT == 1 && NJ == 8) ? 4 : 2;
     const int n_it = (kb1 - kb0 - warp + 7) / 8;       // iterations of this warp (may be <= 0)
     uint4 wlo[MT][kWB], whi[MT][kWB];
 #pragma unroll
@@ -93,13 +95,15 @@ __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, co
         }
     sync.wait();     // weights are immutable: only the activations depend on the previous stage
     // epilogue operands do not depend on the main loop: fetch them now so their L2 round trip is hidden
-    const int e_n = tid >> 2, e_rq = (tid & 3) * 4 * MT;
-    float e_res[4 * MT], e_bias[4 * MT];
+    constexpr int kTpb = 256 / (NJ * 8);            // threads per sequence in the epilogue
+    constexpr int kRpt = 16 * MT / kTpb;            // output rows per thread
+    const int e_n = tid / kTpb, e_rq = (tid % kTpb) * kRpt;
+    float e_res[kRpt], e_bias[kRpt];
 #pragma unroll
-    for (int i = 0; i < 4 * MT; ++i) { e_res[i] = 0.f; e_bias[i] = 0.f; }
+    for (int i = 0; i < kRpt; ++i) { e_res[i] = 0.f; e_bias[i] = 0.f; }
     if (e_n < nb) {
 #pragma unroll
-        for (int i = 0; i < 4 * MT; ++i) {
+        for (int i = 0; i < kRpt; ++i) {
             const int row = row0 + e_rq + i;
             if (row < N) {
                 if (ep.bias) e_bias[i] = __ldg(ep.bias + row);
@@ -107,21 +111,21 @@ __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, co
             }
         }
     }
-    constexpr int kXB = MT == 1 ? 3 : 2;
-    uint4 xq[kXB][8];
+    constexpr int kXB = (MT == 1 && NJ == 8) ? 3 : 2;
+    uint4 xq[kXB][NJ];
 #pragma unroll
     for (int i = 0; i < kXB; ++i)
         if (i < n_it) {
             const int k1 = (kb0 + warp + 8 * i) * 32;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 const int n = j * 8 + g;
                 xq[i][j] = n < nb ? __ldcg(reinterpret_cast<const uint4*>(xb + (int64_t)n * ldx + k1)) : make_uint4(0, 0, 0, 0);
             }
         }
     // rotate the two register rings with fully unrolled bodies of lcm(kWB, kXB) iterations so
     // every ring index is a compile-time constant
-    constexpr int kRot = MT == 1 ? 12 : 2;
+    constexpr int kRot = (MT == 1 && NJ == 8) ? 12 : 2;
     for (int it0 = 0; it0 < n_it; it0 += kRot) {
 #pragma unroll
         for (int i = 0; i < kRot; ++i) {
@@ -138,7 +142,7 @@ __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, co
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < NJ; ++j) {
 #pragma unroll
                 for (int m = 0; m < MT; ++m) {
                     MmaOpD<T>::mma(acc[m][j], alo[m].x, ahi[m].x, alo[m].y, ahi[m].y, xq[i % kXB][j].x, xq[i % kXB][j].y);
@@ -148,7 +152,7 @@ __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, co
             if (it + kXB < n_it) {
                 const int k1 = (kb0 + warp + 8 * (it + kXB)) * 32;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < NJ; ++j) {
                     const int n = j * 8 + g;
                     xq[i % kXB][j] = n < nb ? __ldcg(reinterpret_cast<const uint4*>(xb + (int64_t)n * ldx + k1)) : make_uint4(0, 0, 0, 0);
                 }
@@ -160,7 +164,7 @@ __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, co
 #pragma unroll
     for (int m = 0; m < MT; ++m)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < NJ; ++j) {
             s_red[warp][16 * m + g][j * 8 + 2 * t] = acc[m][j][0];
             s_red[warp][16 * m + g][j * 8 + 2 * t + 1] = acc[m][j][1];
             s_red[warp][16 * m + g + 8][j * 8 + 2 * t] = acc[m][j][2];
@@ -172,7 +176,7 @@ __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, co
     if (n < nb) {
         const int b = b0 + n;
 #pragma unroll
-        for (int i = 0; i < 4 * MT; ++i) {
+        for (int i = 0; i < kRpt; ++i) {
             const int r = rq + i, row = row0 + r;
             if (row >= N) break;
             float v = 0.f;

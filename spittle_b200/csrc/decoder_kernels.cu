@@ -25,13 +25,13 @@ static int dbg_skip() { static int v = getenv("SB_DBG_SKIP") ? atoi(getenv("SB_D
 // ------------------------------------------------------------------------------------------
 // stand-alone launches of the shared stage bodies (decoder_bodies.cuh), chained with PDL
 // ------------------------------------------------------------------------------------------
-// skinny GEMM.  grid.x = ceil(N/16) row tiles, grid.y = batch chunks of 64.  256 threads.
-template <typename T>
-__global__ void __launch_bounds__(256) k_skinny_gemm(const T* __restrict__ X, int ldx, const T* __restrict__ W, int ldw,
+// skinny GEMM.  grid.x = ceil(N/16) row tiles, grid.y = batch chunks of 8 NJ sequences.  256 threads.
+template <typename T, int NJ>
+__global__ void __launch_bounds__(256) __maxnreg__(NJ == 4 ? 96 : 232) k_skinny_gemm(const T* __restrict__ X, int ldx, const T* __restrict__ W, int ldw,
                                                      int Bn, int N, int K, SkinnyEpilogue ep) {
     __shared__ __align__(16) unsigned char smem[kSkinnySmem / 2];
     PdlSync sync;
-    skinny_body<T, 1>(X, ldx, W, ldw, Bn, N, K, ep, blockIdx.x, blockIdx.y, smem, sync);
+    skinny_body<T, 1, NJ>(X, ldx, W, ldw, Bn, N, K, ep, blockIdx.x, blockIdx.y, smem, sync);
 }
 // 32 weight rows per block: half as many blocks each ingest the shared [B, K] activation matrix (the L2 -> SM traffic of
 // a launch is blocks x 98 KB), and a wide projection (QKV, FC1) leaves SMs free for the other decode lane
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_skinny_gemm_w32(const T* __restrict__ X
                                                          int Bn, int N, int K, SkinnyEpilogue ep) {
     extern __shared__ __align__(16) unsigned char smem_w32[];
     PdlSync sync;
-    skinny_body<T, 2>(X, ldx, W, ldw, Bn, N, K, ep, blockIdx.x, blockIdx.y, smem_w32, sync);
+    skinny_body<T, 2, 8>(X, ldx, W, ldw, Bn, N, K, ep, blockIdx.x, blockIdx.y, smem_w32, sync);
 }
 
 // decoder LayerNorm, one warp (= one block) per row so the rows spread over as many SMs:
@@ -436,19 +436,23 @@ int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, 
     SB_CHECK_ARG(K % 32 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "skinny gemm: K % 32 and 16-byte row alignment required");
     if (dbg_skip() & 2) return SB_OK;
     static const int w32_min_n = [] { const char* e = getenv("SB_DEC_W32_MIN_N"); return e ? atoi(e) : 2048; }();
-    if (N >= w32_min_n) {
+    static const bool narrow_ok = [] { const char* e = getenv("SB_DEC_NARROW"); return e ? atoi(e) != 0 : true; }();
+    const bool narrow = narrow_ok && Bn <= 32;      // 32-sequence blocks (half the registers) for a decode lane of <= 32
+    const int chunks = ceil_div(Bn, narrow ? 32 : 64);
+    if (N >= w32_min_n && !narrow) {
         static bool attr_done = false;
         if (!attr_done) {
             SB_CUDA_CHECK(cudaFuncSetAttribute(k_skinny_gemm_w32<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkinnySmem));
             attr_done = true;
         }
-        launch_pdl(k_skinny_gemm_w32<T>, dim3(ceil_div(N, 32), ceil_div(Bn, 64)), dim3(256), (size_t)kSkinnySmem, st, X, ldx, W, ldw, Bn, N, K, ep);
+        launch_pdl(k_skinny_gemm_w32<T>, dim3(ceil_div(N, 32), chunks), dim3(256), (size_t)kSkinnySmem, st, X, ldx, W, ldw, Bn, N, K, ep);
         g_launches += 1;
         SB_CUDA_CHECK(cudaGetLastError());
         return SB_OK;
     }
-    dim3 grid(ceil_div(N, 16), ceil_div(Bn, 64));
-    launch_pdl(k_skinny_gemm<T>, grid, dim3(256), 0, st, X, ldx, W, ldw, Bn, N, K, ep);
+    dim3 grid(ceil_div(N, 16), chunks);
+    if (narrow) launch_pdl(k_skinny_gemm<T, 4>, grid, dim3(256), 0, st, X, ldx, W, ldw, Bn, N, K, ep);
+    else launch_pdl(k_skinny_gemm<T, 8>, grid, dim3(256), 0, st, X, ldx, W, ldw, Bn, N, K, ep);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
