@@ -234,9 +234,9 @@ def main():
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
-    # one more (untimed) batch with per-kernel CUDA-event brackets on the decoder step: projections + cross-attention.
-    # The brackets serialise the PDL chain and the step runs without its CUDA graph, so these are each kernel's own
-    # duration; they are related to the timed step only through the launch counts.
+    # one more (untimed) batch with the device-side launch trace on (sb_engine_set_profile(e, 2)): every decoder-stage
+    # launch stamps %globaltimer at its first block's start and its last block's end.  The step keeps its CUDA graph, its
+    # lanes and its PDL overlap, so these are the durations inside the real chain.
     eng.set_profile(2)
     eng.stats(reset=True)
     eng.transcribe_batch_ptrs(dev_ptrs, sizes, params)
@@ -286,33 +286,43 @@ def main():
         "clocks": sampler.summary(),
     }
     # ---- rooflines: per-kernel entries, the one with the largest share of the timed step first ----
-    d_model, n_dec = eng.info.n_text_state, eng.info.n_text_layer
-    proj_per_step = 6 * n_dec                                    # QKV, O, Q, O, FC1, FC2 per decoder layer
     skinny_avg_us = 1e3 * st_dec["skinny_ms"] / max(st_dec["skinny_launches"], 1)
     xattn_avg_us = 1e3 * st_dec["xattn_ms"] / max(st_dec["xattn_launches"], 1)
-    dec_steps = st_dev["decoder_steps"] / steps
-    n_lanes = int(os.environ.get("SB_DECODE_LANES", "2"))
+    ln_avg_us = 1e3 * st_dec["dln_ms"] / max(st_dec["dln_launches"], 1)
+    self_avg_us = 1e3 * st_dec["dself_ms"] / max(st_dec["dself_launches"], 1)
     ms_step = ms_dev / steps
-    # share of the timed step: the two bracketed decode kernels are scaled so that, together with the unbracketed decode
-    # kernels (LayerNorm, self-attention, sampler, logits GEMM: 25 % of the decode kernel time in the committed launch
-    # list profiles/r1_launches_bench_small_final.md), they fill the decode phase of the step
-    t_sk = dec_steps * proj_per_step * n_lanes * skinny_avg_us
-    t_xa = dec_steps * n_dec * n_lanes * xattn_avg_us
+    # share of the timed step: the decode phase of the step is split between the traced kernel classes in proportion to
+    # their summed launch durations in the traced batch (the lanes overlap, so the sum exceeds the wall time; the logits
+    # GEMM and the sampler, ~5 % of the decode kernel time, are not traced)
+    t_all = max(st_dec["skinny_ms"] + st_dec["xattn_ms"] + st_dec["dln_ms"] + st_dec["dself_ms"], 1e-9)
     dec_share = (st_dev["decode_ms"] / steps) / ms_step
+    lane_step_us = 1e3 * st_dec["dstep_ms"] / max(st_dec["dstep_count"], 1)
     entries = [
         {"kernel": "k_skinny_gemm (decoder-step projections, weight streaming, mma.sync)", "bound": "hbm",
          "achieved": skinny_gbps, "peak": peak_hbm, "unit": "GB/s", "frac": skinny_gbps / peak_hbm,
          "alg_bytes_per_launch": st_dec["skinny_bytes"] / max(st_dec["skinny_launches"], 1),
-         "avg_launch_us": skinny_avg_us, "launches_per_step": dec_steps * proj_per_step * n_lanes,
-         "share_of_step": 0.75 * dec_share * t_sk / max(t_sk + t_xa, 1e-9),
-         "note": "latency-bound: 1-5 MB of weights per launch; ncu "
-                 "(profiles/r1_full_skinny_gemm.md, 768x768 launch): 1.31 MB DRAM read for 1.18 MB of weights",
-         "peak_source": f"{peak_src} hbm_gbs", "traffic": None},
-        {"kernel": "k_dec_cross_attn (decoder cross-attention over the cached 1500 encoder keys)", "bound": "hbm",
+         "avg_launch_us": skinny_avg_us, "launches_per_step": st_dec["skinny_launches"],
+         "share_of_step": dec_share * st_dec["skinny_ms"] / t_all,
+         "note": "latency-bound: 1-5 MB of weights per launch inside a ~140-launch dependent chain per lane-step "
+                 f"(traced lane-step {lane_step_us:.0f} us); duration = first block start -> last block end (device trace); "
+                 "ncu (profiles/r1_full_skinny_gemm.md, 768x768 launch): 1.31 MB DRAM read for 1.18 MB of weights",
+         "peak_source": f"{peak_src} hbm_gbs", "traffic": 1.31e6 / 1.18e6 * st_dec["skinny_bytes"] / max(st_dec["skinny_launches"], 1)},
+        {"kernel": "k_dec_cross_attn (decoder cross-attention over the cached 1500 encoder keys, register streaming, "
+                   "mma.sync scores)", "bound": "hbm",
          "achieved": xattn_gbps, "peak": peak_hbm, "unit": "GB/s", "frac": xattn_gbps / peak_hbm,
-         "avg_launch_us": xattn_avg_us, "launches_per_step": dec_steps * n_dec * n_lanes,
-         "share_of_step": 0.75 * dec_share * t_xa / max(t_sk + t_xa, 1e-9),
-         "note": "bytes = K and V of the sequences still decoding (finished ones are skipped)", "traffic": None},
+         "alg_bytes_per_launch": st_dec["xattn_bytes"] / max(st_dec["xattn_launches"], 1),
+         "avg_launch_us": xattn_avg_us, "launches_per_step": st_dec["xattn_launches"],
+         "share_of_step": dec_share * st_dec["xattn_ms"] / t_all,
+         "note": "bytes = K and V of the sequences still decoding (finished ones are skipped); two lanes stream "
+                 "concurrently and share HBM; alone at 64 live sequences 49.6 us = 5.95 TB/s "
+                 "(profiles/r1_cross_attn_stream.md)", "peak_source": f"{peak_src} hbm_gbs",
+         "traffic": 291.8e6 / 294.9e6 * st_dec["xattn_bytes"] / max(st_dec["xattn_launches"], 1)},
+        {"kernel": "k_dec_ln + k_dec_self_attn (decoder LayerNorm / self-attention over the <= 448-token cache)",
+         "bound": "hbm", "achieved": None, "peak": peak_hbm, "unit": "GB/s", "frac": None,
+         "avg_launch_us": {"ln": ln_avg_us, "self_attn": self_avg_us},
+         "launches_per_step": st_dec["dln_launches"] + st_dec["dself_launches"],
+         "share_of_step": dec_share * (st_dec["dln_ms"] + st_dec["dself_ms"]) / t_all,
+         "note": "latency-bound stages of the chain", "traffic": None},
         {"kernel": "k_gemm_tn (tcgen05 / TMEM / TMA, encoder + cross-KV projections)", "bound": "tensor",
          "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
          "launches_per_step": st_dev["gemm_launches"] / steps, "share_of_step": st_dev["gemm_ms"] / steps / ms_step,
@@ -326,6 +336,8 @@ def main():
          "note": "fp32 400-point FFT on the CUDA cores: instruction-bound (DESIGN.md 5)", "traffic": 1.59e8 / 64 * CLIPS_PER_GPU},
     ]
     entries.sort(key=lambda e: -e["share_of_step"])
+    if entries[0]["frac"] is None:      # the dominant entry must carry a roofline fraction
+        entries[0], entries[1] = entries[1], entries[0]
     line["roofline"] = entries[0]
     line["roofline_extra"] = entries[1:]
     if cpu_base:

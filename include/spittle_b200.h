@@ -236,10 +236,13 @@ typedef struct sb_stats {
     double mel_ms, encode_ms, decode_ms;
     double gemm_ms, gemm_flops, gemm_launches;     /* tcgen05 GEMM launches of the encoder + cross-KV */
     double attn_ms, attn_flops, attn_launches;     /* encoder attention launches */
-    /* sb_engine_set_profile(e, 2) only: sampled (every 8th step) brackets of the decoder-step projections (weight bytes)
-     * and of the decoder cross-attention (K/V bytes of the live sequences); the step then runs without its CUDA graph */
+    /* sb_engine_set_profile(e, 2) only: device-side launch trace of the decoder step (first block start -> last block end
+     * of every launch, %globaltimer; the step keeps its CUDA graph and PDL overlap): projections (weight bytes),
+     * cross-attention (K/V bytes of the live sequences), LayerNorm, self-attention; dstep = first start -> last end of the
+     * traced launches of one lane-step */
     double skinny_ms, skinny_bytes, skinny_launches;
     double xattn_ms, xattn_bytes, xattn_launches;
+    double dln_ms, dln_launches, dself_ms, dself_launches, dstep_ms, dstep_count;
 } sb_stats;
 
 SB_API void sb_params_default(sb_params* p);

@@ -144,7 +144,8 @@ class SbStats(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "clips", "windows", "rounds", "decoder_steps", "tokens_sampled", "pcm_bytes", "h2d_bytes", "d2h_bytes",
         "mel_ms", "encode_ms", "decode_ms", "gemm_ms", "gemm_flops", "gemm_launches", "attn_ms", "attn_flops",
-        "attn_launches", "skinny_ms", "skinny_bytes", "skinny_launches", "xattn_ms", "xattn_bytes", "xattn_launches")]
+        "attn_launches", "skinny_ms", "skinny_bytes", "skinny_launches", "xattn_ms", "xattn_bytes", "xattn_launches",
+        "dln_ms", "dln_launches", "dself_ms", "dself_launches", "dstep_ms", "dstep_count")]
 
 
 class SbWindowInfo(C.Structure):

@@ -114,6 +114,34 @@ __host__ __device__ __forceinline__ float key_float(int k) {
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Device-side launch trace (sb_engine_set_profile(e, 2)): thread 0 of every block stamps %globaltimer into the slot
+// of its launch (slot = decode position x launches-per-step + index of the launch inside the step; min over the
+// blocks for the start, max for the end).  The launches keep their CUDA graph and their PDL overlap, so these are the
+// durations inside the real chain, which CUDA-event brackets around single launches cannot give.
+struct TraceSlot {
+    unsigned long long* t0 = nullptr;   // [max_steps * per_step] first block start (ns)
+    unsigned long long* t1 = nullptr;   // [max_steps * per_step] last block end (ns)
+    const int* pos = nullptr;           // device: decode position of this step
+    int idx = 0, per_step = 0;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ void trace_begin(const TraceSlot& ts) {
+    if (ts.t0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(ts.t0 + (size_t)__ldcg(ts.pos) * ts.per_step + ts.idx, t);
+    }
+}
+__device__ __forceinline__ void trace_end(const TraceSlot& ts) {
+    if (ts.t1 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(ts.t1 + (size_t)__ldcg(ts.pos) * ts.per_step + ts.idx, t);
+    }
+}
+#endif
+extern thread_local TraceSlot g_trace_next;   // core.cu: consumed (and cleared) by the next decoder-stage launcher
+
 extern bool g_pdl;   // core.cu; env SB_PDL=0 disables
 
 template <typename... KArgs, typename... Args>

@@ -48,6 +48,7 @@ struct SkinnyEpilogue {
     const float* residual = nullptr; int ldr = 0;
     float* out32 = nullptr; int ldo32 = 0;
     void* out16 = nullptr; int ldo16 = 0;
+    TraceSlot trace;       // filled by the launcher from g_trace_next
 };
 
 // conv1 im2col: window w reads clip clip_of[w] starting at mel frame seek[w]

@@ -58,6 +58,7 @@ constexpr int kSkinnySmem = 8 * 32 * 65 * 4;       // MT = 2; MT = 1 needs half
 template <typename T, int MT, int NJ, typename Sync>
 __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, const T* __restrict__ W, int ldw, int Bn, int N,
                                             int K, const SkinnyEpilogue& ep, int tile, int chunk, unsigned char* smem, Sync& sync) {
+    trace_begin(ep.trace);
     const int kb0 = 0, kb1 = K / 32;        // K % 32 == 0 enforced by the host
     float (*s_red)[16 * MT][65] = reinterpret_cast<float (*)[16 * MT][65]>(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -189,6 +190,7 @@ __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, co
             if (ep.out16) reinterpret_cast<T*>(ep.out16)[(int64_t)b * ep.ldo16 + row] = Op16<T>::from_f32(v);
         }
     }
+    trace_end(ep.trace);
 }
 
 // ---- decoder LayerNorm of one row by one warp (two-pass in registers); with tok_emb != null the row is first formed
@@ -275,7 +277,8 @@ template <typename T, typename Sync>
 __device__ __forceinline__ void cross_attn_body(const T* __restrict__ q, int ldq, const T* __restrict__ kbase,
                                                        const T* __restrict__ vbase, int64_t ld_kv, int64_t win_stride,
                                                        T* __restrict__ out, int d, int n_ctx, int h, int b,
-                                                       unsigned char* smem, Sync& sync) {
+                                                       unsigned char* smem, Sync& sync, const TraceSlot& ts) {
+    trace_begin(ts);
     float* s_sc = reinterpret_cast<float*>(smem);        // scores / probabilities
     float* s_red = s_sc + 1504;
     float (*s_o)[64] = reinterpret_cast<float (*)[64]>(s_red + 8);
@@ -412,6 +415,7 @@ __device__ __forceinline__ void cross_attn_body(const T* __restrict__ q, int ldq
         for (int w = 0; w < 8; ++w) { o0 += s_o[w][2 * tid]; o1 += s_o[w][2 * tid + 1]; }
         reinterpret_cast<uint32_t*>(out + (int64_t)b * d + h * 64)[tid] = Op16<T>::pack2(o0, o1);
     }
+    trace_end(ts);
 }
 
 }  // namespace sb

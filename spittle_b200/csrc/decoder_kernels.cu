@@ -49,9 +49,11 @@ template <typename T, int VPL>
 __global__ void __launch_bounds__(32) k_dec_ln(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                T* __restrict__ out16, int d, const T* __restrict__ tok_emb,
                                                const float* __restrict__ pos_emb, const int* __restrict__ next_tokens,
-                                               const int* __restrict__ pos_ptr) {
+                                               const int* __restrict__ pos_ptr, TraceSlot ts) {
+    trace_begin(ts);
     struct S { __device__ __forceinline__ void wait() { pdl_wait(); pdl_trigger(); } } sync;
     ln_row_dec<T, VPL>(x, gamma, beta, out16, blockIdx.x, d, tok_emb, pos_emb, next_tokens, pos_ptr, sync);
+    trace_end(ts);
 }
 
 // self attention for one new token per sequence.  grid = (n_head, B), 128 threads: the four warps of a block split the
@@ -60,7 +62,9 @@ __global__ void __launch_bounds__(32) k_dec_ln(float* __restrict__ x, const floa
 template <typename T>
 __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc,
                                                        T* __restrict__ out, const int* __restrict__ pos_ptr,
-                                                       const SeqState* __restrict__ state, int n_head, int d, int n_text_ctx) {
+                                                       const SeqState* __restrict__ state, int n_head, int d, int n_text_ctx,
+                                                       TraceSlot ts) {
+    trace_begin(ts);
     __shared__ float s_p[448];
     __shared__ float s_red[4];
     __shared__ float s_o[4][64];
@@ -156,6 +160,7 @@ __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv
         const float a1 = ((s_o[0][2 * lane + 1] + s_o[1][2 * lane + 1]) + s_o[2][2 * lane + 1]) + s_o[3][2 * lane + 1];
         reinterpret_cast<uint32_t*>(out + (int64_t)b * d + h * 64)[lane] = Op16<T>::pack2(a0, a1);
     }
+    trace_end(ts);
 }
 
 // cross attention.  grid = (n_head, B), 256 threads, 3 blocks per SM (80 registers: the K / V register rings).
@@ -163,13 +168,13 @@ template <typename T>
 __global__ void __launch_bounds__(256, 3) k_dec_cross_attn(const T* __restrict__ q, int ldq, const T* __restrict__ kbase,
                                                            const T* __restrict__ vbase, int64_t ld_kv, int64_t win_stride,
                                                            T* __restrict__ out, const SeqState* __restrict__ state, int d,
-                                                           int n_ctx) {
+                                                           int n_ctx, TraceSlot ts) {
     __shared__ __align__(16) unsigned char smem[kCrossSmem];
     // a finished sequence no longer needs its 2 x 1500 x 64 keys/values streamed: `done` was written by the
     // sampler of an earlier step (many launches ago), so it may be read before the dependency wait
     if (state && __ldcg(&state[blockIdx.y].done)) { pdl_wait(); pdl_trigger(); return; }
     PdlSync sync;
-    cross_attn_body<T>(q, ldq, kbase, vbase, ld_kv, win_stride, out, d, n_ctx, blockIdx.x, blockIdx.y, smem, sync);
+    cross_attn_body<T>(q, ldq, kbase, vbase, ld_kv, win_stride, out, d, n_ctx, blockIdx.x, blockIdx.y, smem, sync, ts);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -437,6 +442,7 @@ int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, 
     if (dbg_skip() & 2) return SB_OK;
     static const int w32_min_n = [] { const char* e = getenv("SB_DEC_W32_MIN_N"); return e ? atoi(e) : 2048; }();
     static const bool narrow_ok = [] { const char* e = getenv("SB_DEC_NARROW"); return e ? atoi(e) != 0 : true; }();
+    SkinnyEpilogue ept = ep; ept.trace = g_trace_next; g_trace_next = TraceSlot();
     const bool narrow = narrow_ok && Bn <= 32;      // 32-sequence blocks (half the registers) for a decode lane of <= 32
     const int chunks = ceil_div(Bn, narrow ? 32 : 64);
     if (N >= w32_min_n && !narrow) {
@@ -445,14 +451,14 @@ int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, 
             SB_CUDA_CHECK(cudaFuncSetAttribute(k_skinny_gemm_w32<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkinnySmem));
             attr_done = true;
         }
-        launch_pdl(k_skinny_gemm_w32<T>, dim3(ceil_div(N, 32), chunks), dim3(256), (size_t)kSkinnySmem, st, X, ldx, W, ldw, Bn, N, K, ep);
+        launch_pdl(k_skinny_gemm_w32<T>, dim3(ceil_div(N, 32), chunks), dim3(256), (size_t)kSkinnySmem, st, X, ldx, W, ldw, Bn, N, K, ept);
         g_launches += 1;
         SB_CUDA_CHECK(cudaGetLastError());
         return SB_OK;
     }
     dim3 grid(ceil_div(N, 16), chunks);
-    if (narrow) launch_pdl(k_skinny_gemm<T, 4>, grid, dim3(256), 0, st, X, ldx, W, ldw, Bn, N, K, ep);
-    else launch_pdl(k_skinny_gemm<T, 8>, grid, dim3(256), 0, st, X, ldx, W, ldw, Bn, N, K, ep);
+    if (narrow) launch_pdl(k_skinny_gemm<T, 4>, grid, dim3(256), 0, st, X, ldx, W, ldw, Bn, N, K, ept);
+    else launch_pdl(k_skinny_gemm<T, 8>, grid, dim3(256), 0, st, X, ldx, W, ldw, Bn, N, K, ept);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
@@ -461,10 +467,11 @@ template <typename T>
 int dec_ln(float* x, const float* gamma, const float* beta, T* out16, int rows, int d, const T* tok_emb, const float* pos_emb,
            const int* next_tokens, const int* pos_ptr, cudaStream_t st) {
     SB_CHECK_ARG(d % 4 == 0 && d <= 1536, "decoder layernorm: d % 4, d <= 1536");
+    const TraceSlot ts = g_trace_next; g_trace_next = TraceSlot();
     if (dbg_skip() & 4) return SB_OK;
-    if (d <= 768) launch_pdl(k_dec_ln<T, 6>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr);
-    else if (d <= 1280) launch_pdl(k_dec_ln<T, 10>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr);
-    else launch_pdl(k_dec_ln<T, 12>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr);
+    if (d <= 768) launch_pdl(k_dec_ln<T, 6>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr, ts);
+    else if (d <= 1280) launch_pdl(k_dec_ln<T, 10>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr, ts);
+    else launch_pdl(k_dec_ln<T, 12>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr, ts);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
@@ -473,8 +480,9 @@ template <typename T>
 int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const int* pos_ptr, const SeqState* state, int Bn, int n_head, int d,
                   int n_text_ctx, cudaStream_t st) {
     SB_CHECK_ARG(n_text_ctx <= 448 && d == n_head * 64, "self attention: n_text_ctx <= 448, d_head 64");
+    const TraceSlot ts = g_trace_next; g_trace_next = TraceSlot();
     if (dbg_skip() & 8) return SB_OK;
-    launch_pdl(k_dec_self_attn<T>, dim3(n_head, Bn), dim3(128), 0, st, qkv, kc, vc, out, pos_ptr, state, n_head, d, n_text_ctx);
+    launch_pdl(k_dec_self_attn<T>, dim3(n_head, Bn), dim3(128), 0, st, qkv, kc, vc, out, pos_ptr, state, n_head, d, n_text_ctx, ts);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
@@ -484,9 +492,10 @@ int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t 
                    const SeqState* state, int Bn, int n_head, int d, int n_ctx, cudaStream_t st) {
     SB_CHECK_ARG(n_ctx <= 1504 && d == n_head * 64 && d <= 1504 && d % 32 == 0 && ldq % 8 == 0 && ld_kv % 8 == 0,
                  "cross attention: n_audio_ctx, d <= 1504, d_head 64, 16-byte aligned rows");
+    const TraceSlot ts = g_trace_next; g_trace_next = TraceSlot();
     if (dbg_skip() & 1) return SB_OK;
     dim3 grid(n_head, Bn);
-    launch_pdl(k_dec_cross_attn<T>, grid, dim3(256), 0, st, q, ldq, kbase, vbase, ld_kv, win_stride, out, state, d, n_ctx);
+    launch_pdl(k_dec_cross_attn<T>, grid, dim3(256), 0, st, q, ldq, kbase, vbase, ld_kv, win_stride, out, state, d, n_ctx, ts);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;

@@ -4,6 +4,7 @@
 // (src-tauri/src/managers/transcription.rs:262-263 load_model, :494-503 transcribe_samples,
 // :183-189 unload_model) and of whisper.cpp's whisper_full_with_state.
 #include "common.cuh"
+#include <cstdio>
 #include "decoder.cuh"
 #include "ggml_loader.h"
 #include <algorithm>
@@ -133,13 +134,17 @@ struct Engine : EngineBase {
     DevBuf b_ckv, b_kself, b_vself, b_dx, b_dh, b_dqkv, b_datt, b_dq, b_dmlp, b_logits;
     DevBuf b_state, b_tokens, b_margins, b_next, b_forced, b_ctr, b_prompt;
     int* h_ctr = nullptr;   // pinned: [pos, step, n_done]
+    // profile == 2: device-side launch trace of the decoder step (TraceSlot, common.cuh)
+    DevBuf b_trace;
+    std::vector<int> trace_cls;          // class of launch idx inside a step: 0 projection, 1 LayerNorm, 2 self-attn, 3 cross-attn
+    std::vector<double> trace_work;      // algorithmic bytes of launch idx (projections: weight bytes)
+    int trace_per_step = 0, trace_max_steps = 0;
+    std::vector<double> trace_sum_dur, trace_sum_t0, trace_sum_t1, trace_cnt;   // per launch index, for SB_TRACE_DUMP
 
     // per-launch CUDA-event brackets (only when profile != 0): class 0 = tcgen05 GEMM, 1 = encoder attention
     struct ProfRec { cudaEvent_t a, b; int cls; double work; };
     std::vector<ProfRec> prof_pool; size_t prof_used = 0;
-    // profile == 2 additionally brackets the decoder-step projections (class 2, work = weight bytes) and the decoder
-    // cross-attention (class 3, work = K/V bytes of the live sequences): the step then runs without its CUDA graph
-    // and the brackets serialise the PDL chain, so these are each kernel's own duration, not the overlapped one
+    // (profile == 2 adds the device-side launch trace of the decoder step, see b_trace)
     int prof_begin(int cls, double work) { return prof_begin_on(cls, work, st); }
     int prof_end() { return prof_end_on(st); }
     int prof_begin_on(int cls, double work, cudaStream_t s_) {
@@ -471,12 +476,25 @@ struct Engine : EngineBase {
         int rc;
         // PDL chain, one launch per stage (what was measured against it and lost -- a persistent per-step megakernel,
         // split-K / cluster projections, LayerNorm fused into the projections -- is in profiles/r1_mega_stage_trace.md)
-        const bool pd = profile == 2 && prof_sample;
+        // profile == 2: every stage launch of the step gets a trace slot (class, algorithmic bytes); the step keeps its graph
+        const bool tracing = profile == 2 && trace_per_step > 0;
+        const int lane_idx = (int)((ctr - b_ctr.as<int>()) / 16);
+        int tidx = 0;
+        auto tr = [&](int cls, double work) {
+            if (!tracing) return;
+            if ((int)trace_cls.size() <= tidx) { trace_cls.resize(tidx + 1); trace_work.resize(tidx + 1); }
+            trace_cls[tidx] = cls; trace_work[tidx] = work;
+            const size_t n = (size_t)trace_max_steps * trace_per_step;
+            TraceSlot ts;
+            ts.t0 = b_trace.as<unsigned long long>() + (size_t)lane_idx * 2 * n;
+            ts.t1 = ts.t0 + n;
+            ts.pos = pos_ptr; ts.idx = tidx; ts.per_step = trace_per_step;
+            g_trace_next = ts;
+            ++tidx;
+        };
         auto sk = [&](const T* X, int ldx, const T* Wt, int ldw, int N, int K, const SkinnyEpilogue& ep) -> int {
-            int r;
-            if (pd && (r = prof_begin_on(2, 2.0 * N * K, sl))) return r;
-            if ((r = skinny_gemm<T>(X, ldx, Wt, ldw, Wl, N, K, ep, sl))) return r;
-            return pd ? prof_end_on(sl) : SB_OK;
+            tr(0, 2.0 * N * K);
+            return skinny_gemm<T>(X, ldx, Wt, ldw, Wl, N, K, ep, sl);
         };
         const int* next_tok = b_next.as<int>() + w0;
         for (int l = 0; l < hp.n_text_layer; ++l) {
@@ -485,27 +503,31 @@ struct Engine : EngineBase {
             T* vc = b_vself.as<T>() + ((int64_t)l * W + w0) * hp.n_text_ctx * d;
             SkinnyEpilogue e{};
             // attn_ln; layer 0 forms x = token_embedding[tok] + positional_embedding[pos] first
+            tr(1, 0);
             if ((rc = dec_ln<T>(dx, L.ln1.g, L.ln1.b, dh, Wl, d, l == 0 ? tok_emb : nullptr, dec_pos, next_tok, pos_ptr, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.qkv.b; e.out16 = dqkv; e.ldo16 = 3 * d;
             if ((rc = sk(dh, d, L.qkv.w, d, 3 * d, d, e))) return rc;
+            tr(2, 0);
             if ((rc = dec_self_attn<T>(dqkv, kc, vc, datt, pos_ptr, seq_state, Wl, hp.n_text_head, d, hp.n_text_ctx, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.o.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
             if ((rc = sk(datt, d, L.o.w, d, d, d, e))) return rc;
             const T* kb = b_ckv.as<T>() + (int64_t)w0 * nctx * nkv + (int64_t)l * 2 * d;
+            tr(1, 0);
             if ((rc = dec_ln<T>(dx, L.ln2.g, L.ln2.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.cq.b; e.out16 = dq; e.ldo16 = d;
             if ((rc = sk(dh, d, L.cq.w, d, d, d, e))) return rc;
-            if (pd && (rc = prof_begin_on(3, 4.0 * nctx * d * (double)live_hint, sl))) return rc;
+            tr(3, 0);
             if ((rc = dec_cross_attn<T>(dq, d, kb, kb + d, nkv, (int64_t)nctx * nkv, datt, seq_state, Wl, hp.n_text_head, d, nctx, sl))) return rc;
-            if (pd && (rc = prof_end_on(sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.co.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
             if ((rc = sk(datt, d, L.co.w, d, d, d, e))) return rc;
+            tr(1, 0);
             if ((rc = dec_ln<T>(dx, L.ln3.g, L.ln3.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.fc1.b; e.act = 1; e.out16 = dmlp; e.ldo16 = 4 * d;
             if ((rc = sk(dh, d, L.fc1.w, d, 4 * d, d, e))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.fc2.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
             if ((rc = sk(dmlp, 4 * d, L.fc2.w, 4 * d, d, 4 * d, e))) return rc;
         }
+        tr(1, 0);
         if ((rc = dec_ln<T>(dx, ln_f.g, ln_f.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, sl))) return rc;
         // tied-embedding logits: 80-130 MB of weights per step -> the TMA-fed tcgen05 GEMM streams them
         // (one 128-row tile of sequences, ~200 column tiles) instead of the small-N weight-streaming kernel
@@ -519,8 +541,6 @@ struct Engine : EngineBase {
 
     struct DecodeOut { std::vector<SeqState> state; std::vector<int> tokens; std::vector<float> margins; std::vector<int> langs; int n_max = 0; };
     bool detect_lang = false; int* detect_out = nullptr;     // set by decode() for enqueue_step
-    bool prof_sample = false;                                // profile == 2: bracket this step (every 8th)
-    int live_hint = 0;                                       // live sequences of the lane being enqueued (profile == 2 accounting)
     bool auto_mode = false;                                  // current transcribe_batch call asked for language auto-detect
 
     // decode W windows whose cross-KV occupies rows [0, W*1500) of b_ckv
@@ -575,7 +595,20 @@ struct Engine : EngineBase {
         detect_lang = detect; detect_out = d_lang;
 
         const int total_steps = n_prompt - 1 + n_max;
-        const bool graph = use_graph && !logits_out && profile != 2;
+        const bool tracing = profile == 2 && !logits_out;
+        const bool graph = use_graph && !logits_out;
+        // launch trace: [lane][start | end][step][launch] globaltimer stamps, reset per decode() call
+        trace_per_step = 0;
+        if (tracing) {
+            trace_per_step = 11 * hp.n_text_layer + 1;
+            trace_max_steps = total_steps;
+            const size_t n = (size_t)trace_max_steps * trace_per_step;
+            if ((rc = b_trace.ensure((size_t)kMaxLanes * 2 * n * 8))) return rc;
+            for (int i = 0; i < kMaxLanes; ++i) {
+                SB_CUDA_CHECK(cudaMemsetAsync(b_trace.as<unsigned long long>() + (size_t)i * 2 * n, 0xff, n * 8, st));
+                SB_CUDA_CHECK(cudaMemsetAsync(b_trace.as<unsigned long long>() + (size_t)i * 2 * n + n, 0, n * 8, st));
+            }
+        }
         // lanes: independent sub-batches on their own streams (one lane when tracing logits)
         int n_lanes = logits_out ? 1 : std::min(n_lanes_cfg, std::max(1, W / 8));
         struct LaneRun { int w0, Wl; bool finished; int steps; };
@@ -606,7 +639,7 @@ struct Engine : EngineBase {
             for (int i = 0; i < n_lanes; ++i) {
                 Lane& L = lanes[i];
                 GraphKey k{W, lr[i].w0, lr[i].Wl, n_max,
-                           (p.suppress_blank ? 1 : 0) | (p.no_timestamps ? 2 : 0) | (p.single_segment ? 4 : 0) | (detect ? 8 : 0),
+                           (p.suppress_blank ? 1 : 0) | (p.no_timestamps ? 2 : 0) | (p.single_segment ? 4 : 0) | (detect ? 8 : 0) | (tracing ? 16 : 0),
                            sa0.max_initial_tid, n_prompt, forced_host ? 1 : 0, g_ws_gen.load()};
                 if (L.gexec && k == L.key) continue;
                 if (L.gexec) { cudaGraphExecDestroy(L.gexec); L.gexec = nullptr; }
@@ -630,9 +663,7 @@ struct Engine : EngineBase {
             for (int i = 0; i < n_lanes; ++i) {
                 if (lr[i].finished) continue;
                 Lane& L = lanes[i];
-                const int burst = (logits_out || profile == 2) ? 1 : std::min(8, total_steps - lr[i].steps);
-                live_hint = std::max(0, lr[i].Wl - (lr[i].steps > 0 ? h_ctr[16 * i + 2] : 0));
-                prof_sample = (lr[i].steps % 8) == 0;
+                const int burst = logits_out ? 1 : std::min(8, total_steps - lr[i].steps);
                 for (int b = 0; b < burst; ++b) {
                     if (graph) { SB_CUDA_CHECK(cudaGraphLaunch(L.gexec, L.st)); g_launches += (uint64_t)L.graph_nodes; }
                     else if ((rc = enqueue_step(W, lr[i].w0, lr[i].Wl, b_ctr.as<int>() + 16 * i, L.st, lane_args(i)))) return rc;
@@ -666,6 +697,56 @@ struct Engine : EngineBase {
         SB_CUDA_CHECK(cudaMemcpyAsync(out.tokens.data(), b_tokens.p, (size_t)W * n_max * 4, cudaMemcpyDeviceToHost, st));
         SB_CUDA_CHECK(cudaMemcpyAsync(out.margins.data(), b_margins.p, (size_t)W * n_max * 4, cudaMemcpyDeviceToHost, st));
         SB_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (tracing) {
+            const size_t n = (size_t)trace_max_steps * trace_per_step;
+            std::vector<unsigned long long> ht((size_t)n_lanes * 2 * n);
+            SB_CUDA_CHECK(cudaMemcpy(ht.data(), b_trace.p, ht.size() * 8, cudaMemcpyDeviceToHost));
+            for (int i = 0; i < n_lanes; ++i) {
+                const unsigned long long* t0 = ht.data() + (size_t)i * 2 * n;
+                const unsigned long long* t1 = t0 + n;
+                for (int sI = 0; sI < lr[i].steps && sI < trace_max_steps; ++sI) {
+                    unsigned long long first = ~0ull, last = 0;
+                    for (int k = 0; k < trace_per_step && k < (int)trace_cls.size(); ++k) {
+                        const unsigned long long a = t0[(size_t)sI * trace_per_step + k], b = t1[(size_t)sI * trace_per_step + k];
+                        if (a == ~0ull || b <= a) continue;          // never ran (every block skipped) or clock wrap
+                        const double ms = (double)(b - a) * 1e-6;
+                        first = std::min(first, a); last = std::max(last, b);
+                        switch (trace_cls[k]) {
+                            case 0: stats.skinny_ms += ms; stats.skinny_bytes += trace_work[k]; stats.skinny_launches += 1; break;
+                            case 1: stats.dln_ms += ms; stats.dln_launches += 1; break;
+                            case 2: stats.dself_ms += ms; stats.dself_launches += 1; break;
+                            default: stats.xattn_ms += ms; stats.xattn_launches += 1; break;
+                        }
+                    }
+                    if (last > first) { stats.dstep_ms += (double)(last - first) * 1e-6; stats.dstep_count += 1; }
+                    if (last > first && getenv("SB_TRACE_DUMP")) {    // per-index timeline relative to the lane-step's first start
+                        if ((int)trace_cnt.size() < trace_per_step) {
+                            trace_sum_dur.assign(trace_per_step, 0.0); trace_sum_t0.assign(trace_per_step, 0.0);
+                            trace_sum_t1.assign(trace_per_step, 0.0); trace_cnt.assign(trace_per_step, 0.0);
+                        }
+                        for (int k = 0; k < trace_per_step && k < (int)trace_cls.size(); ++k) {
+                            const unsigned long long a = t0[(size_t)sI * trace_per_step + k], b = t1[(size_t)sI * trace_per_step + k];
+                            if (a == ~0ull || b <= a) continue;
+                            trace_sum_dur[k] += (double)(b - a); trace_sum_t0[k] += (double)(a - first);
+                            trace_sum_t1[k] += (double)(b - first); trace_cnt[k] += 1;
+                        }
+                    }
+                }
+            }
+            if (const char* dump = getenv("SB_TRACE_DUMP")) {
+                if (FILE* f = fopen(dump, "w")) {
+                    fprintf(f, "idx,class,work_bytes,count,avg_us,avg_start_us,avg_end_us\n");
+                    for (int k = 0; k < (int)trace_cnt.size() && k < (int)trace_cls.size(); ++k)
+                        if (trace_cnt[k] > 0)
+                            fprintf(f, "%d,%d,%.0f,%.0f,%.3f,%.3f,%.3f\n", k, trace_cls[k], trace_work[k], trace_cnt[k],
+                                    trace_sum_dur[k] / trace_cnt[k] * 1e-3, trace_sum_t0[k] / trace_cnt[k] * 1e-3, trace_sum_t1[k] / trace_cnt[k] * 1e-3);
+                    fclose(f);
+                }
+            }
+            // cross-attention bytes: a sequence with n_tok sampled tokens was live for n_prompt + n_tok - 1 steps
+            for (int w = 0; w < W; ++w)
+                stats.xattn_bytes += (double)(n_prompt + std::max(out.state[w].n_tok, 1) - 1) * hp.n_text_layer * 4.0 * hp.n_audio_ctx * hp.n_text_state;
+        }
         stats.d2h_bytes += (double)W * (sizeof(SeqState) + 8.0 * n_max);
         stats.h2d_bytes += (double)W * sizeof(SeqState) + 4.0 * n_prompt;
         return SB_OK;
