@@ -316,7 +316,7 @@ def main():
          "note": "bytes = K and V of the sequences still decoding (finished ones are skipped); two lanes stream "
                  "concurrently and share HBM; alone at 64 live sequences 49.6 us = 5.95 TB/s "
                  "(profiles/r1_cross_attn_stream.md)", "peak_source": f"{peak_src} hbm_gbs",
-         "traffic": 291.8e6 / 294.9e6 * st_dec["xattn_bytes"] / max(st_dec["xattn_launches"], 1)},
+         "traffic": 290.4e6 / 294.9e6 * st_dec["xattn_bytes"] / max(st_dec["xattn_launches"], 1)},   # ncu: profiles/r1_full_dec_cross_attn.md
         {"kernel": "k_dec_ln + k_dec_self_attn (decoder LayerNorm / self-attention over the <= 448-token cache)",
          "bound": "hbm", "achieved": None, "peak": peak_hbm, "unit": "GB/s", "frac": None,
          "avg_launch_us": {"ln": ln_avg_us, "self_attn": self_avg_us},
