@@ -111,6 +111,19 @@ typedef enum sb_sample_format { SB_SAMPLE_F32 = 0, SB_SAMPLE_I16 = 1, SB_SAMPLE_
 SB_API int sb_downmix_mono_dev(const void* in, int sample_format, int channels, int64_t in_stride, size_t n_frames,
                                int n_streams, float* out, int64_t out_stride, void* stream);
 
+/* History WAV payload.  Replaces the sample loop of save_wav_file (audio_toolkit/audio/utils.rs:17-20):
+ * out[i] = (in[i] * 32767) as i16 with Rust's cast semantics (truncate toward zero, saturate, NaN -> 0).
+ * Device pointers, 16-byte aligned, async on `stream`. */
+SB_API int sb_pcm_f32_to_i16_dev(const float* in, int16_t* out, size_t n, void* stream);
+
+/* Mic-level visualiser, batched.  Replaces AudioVisualiser::{new, feed} (audio_toolkit/audio/visualizer.rs:20-149,
+ * constructed at audio/recorder.rs:276-282 with window 512, 16 buckets, 400-4000 Hz; fed once per captured chunk,
+ * recorder.rs:323): for every chunk the first 512 samples are analysed (DC removal, Hann, power per bucket, dB, range
+ * map, gain / curve, left-to-right smoothing).  pcm [n_streams][stream_stride] with n_chunks * chunk_len valid samples,
+ * chunk_len >= 512; out [n_streams][n_chunks][16] f32.  Device pointers, async on `stream`. */
+SB_API int sb_visualiser_levels_dev(const float* pcm, int64_t stream_stride, int n_streams, int n_chunks, int chunk_len,
+                                    int sample_rate, float* out, void* stream);
+
 /* Silero VAD v4 (16 kHz branch).  Replaces vad_rs::Vad::{new, compute} over onnxruntime
  * (audio_toolkit/vad/silero.rs:25,41-44).  blob: the f32 tensors of the model in the order of
  * spittle_b200/silero_weights.py BLOB_LAYOUT (read from the reference's silero_vad_v4.onnx).

@@ -7,6 +7,8 @@ Same names and argument meaning as the reference (src-tauri/src/audio_toolkit):
   SmoothedVad(inner, prefill, hangover, onset)  vad/smoothed.rs:20-96
   run_consumer(...)                           audio/recorder.rs:255-373  (resample -> VAD -> append)
   stop_recording_pad(samples)                 managers/audio.rs:466-475
+  save_wav_file(path, samples)                audio/utils.rs:7-26        (hound: 16 kHz mono i16)
+  AudioVisualiser(rate, 512, 16, 400, 4000)   audio/visualizer.rs:20-149 (mic-level buckets per captured chunk)
 
 The reference is a streaming, single-microphone loop; here a whole recording per stream is pushed
 at once (push(all) + finish()), many streams per call.  torch is used only for device memory.
@@ -139,3 +141,45 @@ def run_consumer(streams, in_sample_rate: int, vad: Optional[SmoothedVad]) -> Li
         host = frames.cpu().numpy()
         return [host[s].reshape(-1).copy() for s in range(host.shape[0])]
     return vad.gate(frames)
+
+
+def save_wav_file(file_path: str, samples) -> None:
+    """16 kHz mono 16-bit PCM WAV of one recording (audio/utils.rs:7-26; called by managers/history.rs:180-214).
+    The f32 -> i16 conversion `(s * 32767) as i16` runs on the GPU; the 44-byte header is written here."""
+    import struct
+    torch = _torch()
+    x = samples if hasattr(samples, "is_cuda") else torch.from_numpy(np.ascontiguousarray(samples, np.float32))
+    x = x.cuda().contiguous().view(-1)
+    out = torch.empty(x.numel(), dtype=torch.int16, device=x.device)
+    if x.numel():
+        capi.pcm_f32_to_i16_dev(x.data_ptr(), out.data_ptr(), x.numel(), torch.cuda.current_stream().cuda_stream)
+    data = out.cpu().numpy().tobytes()
+    with open(file_path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE")
+        f.write(b"fmt " + struct.pack("<IHHIIHH", 16, 1, 1, WHISPER_SAMPLE_RATE, WHISPER_SAMPLE_RATE * 2, 2, 16))
+        f.write(b"data" + struct.pack("<I", len(data)))
+        f.write(data)
+
+
+class AudioVisualiser:
+    """Batched mirror of AudioVisualiser::feed: levels(streams, chunk_len) returns what the reference's visualiser
+    would have emitted for every chunk of every stream ([n_streams, n_chunks, 16]); the reference analyses the first
+    512 samples of each fed chunk."""
+
+    def __init__(self, sample_rate: int, window_size: int = 512, buckets: int = 16, freq_min: float = 400.0,
+                 freq_max: float = 4000.0):
+        if (window_size, buckets, freq_min, freq_max) != (512, 16, 400.0, 4000.0):
+            raise capi.SbError(-7, "only the reference's visualiser geometry (512, 16, 400 Hz, 4000 Hz) is implemented")
+        self.sample_rate = sample_rate
+
+    def levels(self, streams, chunk_len: int):
+        torch = _torch()
+        x = streams if hasattr(streams, "is_cuda") else torch.from_numpy(np.ascontiguousarray(streams, np.float32))
+        x = x.cuda().contiguous()
+        n_streams, n_in = x.shape
+        n_chunks = n_in // chunk_len
+        out = torch.empty((n_streams, n_chunks, 16), dtype=torch.float32, device=x.device)
+        if n_chunks:
+            capi.visualiser_levels_dev(x.data_ptr(), x.stride(0), n_streams, n_chunks, chunk_len, self.sample_rate,
+                                       out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return out

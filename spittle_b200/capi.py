@@ -318,6 +318,8 @@ class Engine:
 def _declare_frontend(l: C.CDLL) -> None:
     vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
     l.sb_downmix_mono_dev.argtypes = [vp, i32, i32, i64, sz, i32, vp, i64, vp]
+    l.sb_pcm_f32_to_i16_dev.argtypes = [vp, vp, sz, vp]
+    l.sb_visualiser_levels_dev.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp]
     l.sb_resampler_create.argtypes = [i32, i32, C.POINTER(vp)]
     l.sb_resampler_destroy.argtypes = [vp]
     l.sb_resample_geometry.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
@@ -391,6 +393,16 @@ def downmix_mono_dev(in_ptr, sample_format: int, channels: int, in_stride: int, 
                      out_stride: int, stream=None) -> None:
     check(lib().sb_downmix_mono_dev(in_ptr, sample_format, channels, in_stride, n_frames, n_streams, out_ptr, out_stride,
                                     stream or None))
+
+
+def pcm_f32_to_i16_dev(in_ptr, out_ptr, n: int, stream=None) -> None:
+    check(lib().sb_pcm_f32_to_i16_dev(in_ptr, out_ptr, n, stream or None))
+
+
+def visualiser_levels_dev(pcm_ptr, stream_stride: int, n_streams: int, n_chunks: int, chunk_len: int, sample_rate: int,
+                          out_ptr, stream=None) -> None:
+    check(lib().sb_visualiser_levels_dev(pcm_ptr, stream_stride, n_streams, n_chunks, chunk_len, sample_rate, out_ptr,
+                                         stream or None))
 
 
 def vad_gate_workspace_bytes(n_streams: int, n_frames: int) -> int:
