@@ -59,6 +59,32 @@ void dequantize(const uint8_t* src, int ttype, int64_t count, float* dst) {
         }
     }
 }
+// k-quant q5_K (the catalog's breeze-asr-q5_k.bin): super-blocks of 256 weights, 176 bytes
+//   {f16 d, dmin; u8 scales[12]; u8 qh[32]; u8 qs[128]}, x = d sc_j q - dmin mn_j per 32-weight sub-block j
+// (ggml dequantize_row_q5_K / get_scale_min_k4 [MEM])
+constexpr int kQkK = 256, kQ5KBytes = 176;
+void dequantize_q5_k(const uint8_t* src, int64_t count, float* dst) {
+    for (int64_t b = 0; b < count / kQkK; ++b, src += kQ5KBytes, dst += kQkK) {
+        uint16_t h; memcpy(&h, src, 2);
+        const float d = f16_bits_to_f32(h);
+        memcpy(&h, src + 2, 2);
+        const float dmin = f16_bits_to_f32(h);
+        const uint8_t* sc = src + 4;
+        const uint8_t* qh = src + 16;
+        const uint8_t* ql = src + 48;
+        for (int j = 0; j < 8; ++j) {
+            int s, m;
+            if (j < 4) { s = sc[j] & 63; m = sc[j + 4] & 63; }
+            else { s = (sc[j + 4] & 0xF) | ((sc[j - 4] >> 6) << 4); m = (sc[j + 4] >> 4) | ((sc[j] >> 6) << 4); }
+            const float dj = d * (float)s, mj = dmin * (float)m;
+            const uint8_t* q = ql + 32 * (j / 2);
+            for (int l = 0; l < 32; ++l) {
+                const int nib = (j & 1) ? (q[l] >> 4) : (q[l] & 0xF);
+                dst[32 * j + l] = dj * (float)(nib + (((qh[l] >> j) & 1) << 4)) - mj;
+            }
+        }
+    }
+}
 struct Reader {
     const uint8_t* p; size_t n; size_t off = 0; bool ok = true;
     template <typename V> V get() {
@@ -147,9 +173,19 @@ int load_ggml_file(const char* path, GgmlFile& out) {
             t.ttype = 0;
             t.nbytes = (size_t)t.numel() * 4;
             t.data = reinterpret_cast<const uint8_t*>(out.dequant.back().data());
+        } else if (ttype == 13) {
+            if (ne[0] % kQkK != 0) { set_error("q5_K tensor '" + name + "': row length is not a multiple of 256"); return SB_ERR_FORMAT; }
+            const size_t qbytes = (size_t)(t.numel() / kQkK) * kQ5KBytes;
+            const uint8_t* q = r.take(qbytes);
+            if (!q) { set_error("truncated tensor data: " + name); return SB_ERR_FORMAT; }
+            out.dequant.emplace_back((size_t)t.numel());
+            dequantize_q5_k(q, t.numel(), out.dequant.back().data());
+            t.ttype = 0;
+            t.nbytes = (size_t)t.numel() * 4;
+            t.data = reinterpret_cast<const uint8_t*>(out.dequant.back().data());
         } else {
             set_error("tensor '" + name + "' has ggml type " + std::to_string(ttype) +
-                      " (supported: f32, f16, q4_0, q4_1, q5_0, q5_1, q8_0; k-quants are not)");
+                      " (supported: f32, f16, q4_0, q4_1, q5_0, q5_1, q8_0, q5_K; the other k-quants are not)");
             return SB_ERR_FORMAT;
         }
         out.tensors[name] = t;

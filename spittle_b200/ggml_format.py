@@ -34,12 +34,74 @@ GGML_TYPE_F16 = 1
 # element j < 16 takes the low nibble of qs[j], element j + 16 the high nibble; the fifth bit of q5 comes from
 # bit j (low half) / bit j + 16 (high half) of the little-endian u32 qh.
 GGML_TYPE_Q4_0, GGML_TYPE_Q4_1, GGML_TYPE_Q5_0, GGML_TYPE_Q5_1, GGML_TYPE_Q8_0 = 2, 3, 6, 7, 8
+# k-quant q5_K (catalog: breeze-asr-q5_k.bin, resources/model_catalog.json:202): super-blocks of 256 weights, 176 bytes
+#   {f16 d, dmin; u8 scales[12]; u8 qh[32]; u8 qs[128]}: eight sub-blocks of 32 with 6-bit scale sc_j and minimum mn_j
+#   (packed by get_scale_min_k4), x = d sc_j q - dmin mn_j, q in [0, 32): low four bits in the nibbles of qs (64 weights per
+#   32 bytes: sub-block 2g in the low nibbles, 2g + 1 in the high ones), fifth bit in bit 2g / 2g + 1 of qh[l].  [MEM]
+GGML_TYPE_Q5_K = 13
+QK_K, Q5_K_BYTES = 256, 176
 QUANT_BLOCK_BYTES = {GGML_TYPE_Q4_0: 18, GGML_TYPE_Q4_1: 20, GGML_TYPE_Q5_0: 22, GGML_TYPE_Q5_1: 24, GGML_TYPE_Q8_0: 34}
-GGML_FTYPE_OF_TYPE = {GGML_TYPE_Q4_0: 2, GGML_TYPE_Q4_1: 3, GGML_TYPE_Q8_0: 7, GGML_TYPE_Q5_0: 8, GGML_TYPE_Q5_1: 9}
+GGML_FTYPE_OF_TYPE = {GGML_TYPE_Q4_0: 2, GGML_TYPE_Q4_1: 3, GGML_TYPE_Q8_0: 7, GGML_TYPE_Q5_0: 8, GGML_TYPE_Q5_1: 9, GGML_TYPE_Q5_K: 13}
+
+
+def quantize_q5_k(x: np.ndarray) -> bytes:
+    """A valid q5_K encoding of a tensor whose last dim is a multiple of 256 (per sub-block min / max fit; ggml's own
+    quantiser searches for better scales, the FORMAT is what matters to the loader)."""
+    v = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 8, 32)
+    nb = v.shape[0]
+    mn = np.minimum(v.min(axis=2), 0.0)
+    scale = (v.max(axis=2) - mn) / 31.0
+    d = (scale.max(axis=1) / 63.0).astype("<f2")
+    dmin = ((-mn).max(axis=1) / 63.0).astype("<f2")
+    df, dminf = d.astype(np.float32), dmin.astype(np.float32)
+    sc = np.where(df[:, None] > 0, np.rint(scale / np.where(df[:, None] > 0, df[:, None], 1)), 0).clip(0, 63).astype(np.uint8)
+    mq = np.where(dminf[:, None] > 0, np.rint(-mn / np.where(dminf[:, None] > 0, dminf[:, None], 1)), 0).clip(0, 63).astype(np.uint8)
+    eff = df[:, None] * sc
+    q = np.where(eff[:, :, None] > 0, np.rint((v + (dminf[:, None] * mq)[:, :, None]) / np.where(eff[:, :, None] > 0, eff[:, :, None], 1)), 0)
+    q = q.clip(0, 31).astype(np.uint8)
+    scales = np.zeros((nb, 12), np.uint8)
+    for j in range(4):
+        scales[:, j] = sc[:, j] & 63
+        scales[:, j + 4] = mq[:, j] & 63
+    for j in range(4, 8):
+        scales[:, j + 4] = (sc[:, j] & 0xF) | ((mq[:, j] & 0xF) << 4)
+        scales[:, j - 4] |= (sc[:, j] >> 4) << 6
+        scales[:, j] |= (mq[:, j] >> 4) << 6
+    qs = np.zeros((nb, 128), np.uint8)
+    qh = np.zeros((nb, 32), np.uint8)
+    for g in range(4):
+        lo, hi = q[:, 2 * g], q[:, 2 * g + 1]
+        qs[:, 32 * g: 32 * g + 32] = (lo & 0xF) | ((hi & 0xF) << 4)
+        qh |= ((lo >> 4) & 1) << (2 * g)
+        qh |= ((hi >> 4) & 1) << (2 * g + 1)
+    return np.concatenate([d.view(np.uint8).reshape(nb, 2), dmin.view(np.uint8).reshape(nb, 2), scales, qh, qs], axis=1).tobytes()
+
+
+def dequantize_q5_k(raw: bytes, count: int) -> np.ndarray:
+    """ggml dequantize_row_q5_K."""
+    nb = count // QK_K
+    b = np.frombuffer(raw, np.uint8, nb * Q5_K_BYTES).reshape(nb, Q5_K_BYTES)
+    d = b[:, 0:2].copy().view("<f2").astype(np.float32).reshape(nb)
+    dmin = b[:, 2:4].copy().view("<f2").astype(np.float32).reshape(nb)
+    scales, qh, qs = b[:, 4:16].astype(np.int32), b[:, 16:48].astype(np.int32), b[:, 48:176].astype(np.int32)
+    out = np.zeros((nb, 8, 32), np.float32)
+    for j in range(8):
+        if j < 4:
+            sc, m = scales[:, j] & 63, scales[:, j + 4] & 63
+        else:
+            sc = (scales[:, j + 4] & 0xF) | ((scales[:, j - 4] >> 6) << 4)
+            m = (scales[:, j + 4] >> 4) | ((scales[:, j] >> 6) << 4)
+        g = j // 2
+        nib = (qs[:, 32 * g: 32 * g + 32] & 0xF) if j % 2 == 0 else (qs[:, 32 * g: 32 * g + 32] >> 4)
+        q = nib + (((qh >> j) & 1) << 4)
+        out[:, j] = ((d * sc.astype(np.float32))[:, None] * q.astype(np.float32) - (dmin * m.astype(np.float32))[:, None]).astype(np.float32)
+    return out.reshape(-1)
 
 
 def quantize_blocks(x: np.ndarray, ttype: int) -> bytes:
     """ggml reference quantisation (quantize_row_q*_reference) of a tensor whose last dim is a multiple of 32."""
+    if ttype == GGML_TYPE_Q5_K:
+        return quantize_q5_k(x)
     v = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 32)
     nb = v.shape[0]
     if ttype == GGML_TYPE_Q8_0:
@@ -82,6 +144,8 @@ def quantize_blocks(x: np.ndarray, ttype: int) -> bytes:
 
 
 def dequantize_blocks(raw: bytes, ttype: int, count: int) -> np.ndarray:
+    if ttype == GGML_TYPE_Q5_K:
+        return dequantize_q5_k(raw, count)
     bs = QUANT_BLOCK_BYTES[ttype]
     nb = count // 32
     b = np.frombuffer(raw, np.uint8, nb * bs).reshape(nb, bs)
@@ -246,8 +310,8 @@ def write_ggml(path: str, model: GgmlModel, quant_type: int = None) -> None:
             else:
                 raise ValueError(f"{name}: unsupported dtype {arr.dtype}")
             payload = None
-            if (quant_type is not None and arr.ndim == 2 and arr.dtype == np.float16 and arr.shape[1] % 32 == 0
-                    and "positional_embedding" not in name):
+            if (quant_type is not None and arr.ndim == 2 and arr.dtype == np.float16
+                    and arr.shape[1] % (QK_K if quant_type == GGML_TYPE_Q5_K else 32) == 0 and "positional_embedding" not in name):
                 ttype = quant_type
                 payload = quantize_blocks(arr.astype(np.float32), quant_type)
             nb = name.encode()
@@ -296,12 +360,12 @@ def read_ggml(path: str) -> GgmlModel:
         elif ttype == GGML_TYPE_F16:
             arr = np.frombuffer(data, dtype="<f2", count=count, offset=off)
             off += 2 * count
-        elif ttype in QUANT_BLOCK_BYTES:
-            nbytes = count // 32 * QUANT_BLOCK_BYTES[ttype]
+        elif ttype in QUANT_BLOCK_BYTES or ttype == GGML_TYPE_Q5_K:
+            nbytes = count // QK_K * Q5_K_BYTES if ttype == GGML_TYPE_Q5_K else count // 32 * QUANT_BLOCK_BYTES[ttype]
             arr = dequantize_blocks(data[off:off + nbytes], ttype, count)        # f32, like the engine's loader
             off += nbytes
         else:
-            raise ValueError(f"{name}: tensor type {ttype} (k-quants) not supported")
+            raise ValueError(f"{name}: tensor type {ttype} (k-quants other than q5_K) not supported")
         tensors[name] = arr.reshape(shape).copy()
     return GgmlModel(hp, mel, vocab, tensors)
 

@@ -152,11 +152,11 @@ def test_language_auto_detect_matches_oracle(cuda_dev, model_dir):
     eng.close()
 
 
-@pytest.mark.parametrize("qt", [3, 6])       # q4_1 (catalog: Medium), q5_0 (catalog: Large-v3)
-def test_quantised_model_file_matches_oracle(cuda_dev, model_dir, qt):
+@pytest.mark.parametrize("qt,arch", [(3, "nano"), (6, "nano"), (13, "micro")])   # q4_1 (catalog: Medium), q5_0 (Large-v3), q5_K (Breeze)
+def test_quantised_model_file_matches_oracle(cuda_dev, model_dir, qt, arch):
     """block-quantised GGML files load (dequantised on load, then stored in the engine's 16-bit
     operand type); the oracle runs on the same dequantised weights."""
-    path = synth.ensure_model_file("nano", model_dir, quant_type=qt)
+    path = synth.ensure_model_file(arch, model_dir, quant_type=qt)
     model = ggml_format.read_ggml(path)
     oracle = whisper_ref.WhisperOracle(model, act_f16=True)
     eng = capi.Engine(path, dtype=capi.SB_DTYPE_F16, max_batch=4)

@@ -150,3 +150,41 @@ def test_ggml_block_quantisation_round_trip(tmp_path):
     err = np.abs(q.tensors[name] - ref.tensors[name].astype(np.float32)).max()
     assert 0 < err < 0.1 * np.abs(ref.tensors[name].astype(np.float32)).max()
     assert np.array_equal(q.tensors["encoder.conv1.weight"], ref.tensors["encoder.conv1.weight"])
+
+
+def test_ggml_q5_k_layout_known_answer_and_round_trip(tmp_path):
+    """q5_K (the catalog's breeze-asr-q5_k.bin).  A hand-built super-block pins the bit layout
+    (get_scale_min_k4 packing, nibble / fifth-bit placement); quantise -> dequantise stays within a step."""
+    from spittle_b200 import ggml_format as g, synth
+    d, dmin = b"\x00\x38", b"\x00\x34"                  # 0.5, 0.25
+    sc = [1, 2, 3, 4, 17, 34, 51, 63]                   # 6-bit scales of the 8 sub-blocks (j >= 4 need the high-bit fields)
+    mn = [0, 1, 2, 3, 16, 33, 50, 63]
+    scales = bytearray(12)
+    for j in range(4):
+        scales[j] = sc[j]
+        scales[j + 4] = mn[j]
+    for j in range(4, 8):
+        scales[j + 4] = (sc[j] & 0xF) | ((mn[j] & 0xF) << 4)
+        scales[j - 4] |= (sc[j] >> 4) << 6
+        scales[j] |= (mn[j] >> 4) << 6
+    q = np.zeros((8, 32), np.int32)
+    for j in range(8):
+        q[j] = (np.arange(32) + 3 * j) % 32
+    qs, qh = bytearray(128), bytearray(32)
+    for grp in range(4):
+        for l in range(32):
+            lo, hi = int(q[2 * grp, l]), int(q[2 * grp + 1, l])
+            qs[32 * grp + l] = (lo & 0xF) | ((hi & 0xF) << 4)
+            qh[l] |= ((lo >> 4) & 1) << (2 * grp)
+            qh[l] |= ((hi >> 4) & 1) << (2 * grp + 1)
+    x = g.dequantize_blocks(d + dmin + bytes(scales) + bytes(qh) + bytes(qs), g.GGML_TYPE_Q5_K, 256).reshape(8, 32)
+    for j in range(8):
+        assert np.array_equal(x[j], (0.5 * sc[j]) * q[j] - 0.25 * mn[j]), j
+    rng = np.random.default_rng(2)
+    w = rng.normal(0, 0.1, (4, 512)).astype(np.float32)
+    y = g.dequantize_blocks(g.quantize_blocks(w, g.GGML_TYPE_Q5_K), g.GGML_TYPE_Q5_K, w.size).reshape(w.shape)
+    span = (w.reshape(-1, 32).max(axis=1) - np.minimum(w.reshape(-1, 32).min(axis=1), 0))
+    assert (np.abs(y - w).reshape(-1, 32).max(axis=1) <= 1.6 * span / 31 + 2e-3).all()
+    path = synth.ensure_model_file("micro", str(tmp_path), quant_type=g.GGML_TYPE_Q5_K)
+    m = g.read_ggml(path)
+    assert m.hparams.ftype == 13 and m.tensors["decoder.blocks.0.mlp.0.weight"].dtype == np.float32
