@@ -43,6 +43,16 @@ __global__ void __launch_bounds__(256) k_skinny_gemm_w32(const T* __restrict__ X
     skinny_body<T, 2, 8>(X, ldx, W, ldw, Bn, N, K, ep, blockIdx.x, blockIdx.y, smem_w32, sync);
 }
 
+// 32 weight rows x 32 sequences at <= 128 registers: half the blocks of the narrow kernel for the wide projections of the d >= 1024
+// models (Large-v3-Turbo: decode 274 -> 265 ms; Small, d = 768: 420 -> 430 ms, so it keeps the 16-row blocks)
+template <typename T>
+__global__ void __launch_bounds__(256, 2) k_skinny_gemm_w32n(const T* __restrict__ X, int ldx, const T* __restrict__ W, int ldw,
+                                                             int Bn, int N, int K, SkinnyEpilogue ep) {
+    extern __shared__ __align__(16) unsigned char smem_w32[];
+    PdlSync sync;
+    skinny_body<T, 2, 4>(X, ldx, W, ldw, Bn, N, K, ep, blockIdx.x, blockIdx.y, smem_w32, sync);
+}
+
 // decoder LayerNorm, one warp (= one block) per row so the rows spread over as many SMs:
 // optional embedding (x = tok_emb[tok] + pos_emb[pos]) first, then LN -> 16-bit h.
 template <typename T, int VPL>
@@ -445,6 +455,16 @@ int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, 
     SkinnyEpilogue ept = ep; ept.trace = g_trace_next; g_trace_next = TraceSlot();
     const bool narrow = narrow_ok && Bn <= 32;      // 32-sequence blocks (half the registers) for a decode lane of <= 32
     const int chunks = ceil_div(Bn, narrow ? 32 : 64);
+    static const int narrow_w32_env = [] { const char* e = getenv("SB_DEC_NARROW_W32"); return e ? atoi(e) : -1; }();
+    const bool narrow_w32 = narrow_w32_env >= 0 ? narrow_w32_env != 0 : K >= 1024;
+    if (N >= w32_min_n && narrow && narrow_w32) {
+        static bool attr_done2 = false;
+        if (!attr_done2) { SB_CUDA_CHECK(cudaFuncSetAttribute(k_skinny_gemm_w32n<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkinnySmem)); attr_done2 = true; }
+        launch_pdl(k_skinny_gemm_w32n<T>, dim3(ceil_div(N, 32), chunks), dim3(256), (size_t)kSkinnySmem, st, X, ldx, W, ldw, Bn, N, K, ept);
+        g_launches += 1;
+        SB_CUDA_CHECK(cudaGetLastError());
+        return SB_OK;
+    }
     if (N >= w32_min_n && !narrow) {
         static bool attr_done = false;
         if (!attr_done) {
