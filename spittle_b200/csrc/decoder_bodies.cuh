@@ -94,6 +94,18 @@ __device__ __forceinline__ void skinny_body(const T* __restrict__ X, int ldx, co
                 whi[m][i] = ldg_nc_v4(w_hi[m] + (kb0 + warp + 8 * i) * 32);
             }
         }
+    // the ring is only kWB k-blocks deep: the weight fragments of the later k-blocks of this warp are requested into L2
+    // now (one prefetch per future load address of lanes t == 0 / 2: a 64-byte k-block row is two 32-byte sectors), so
+    // that they do not pay the HBM latency one after the other inside the loop
+    if (!(t & 1)) {
+        for (int i = kWB; i < n_it; ++i) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(w_lo[m] + (kb0 + warp + 8 * i) * 32));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(w_hi[m] + (kb0 + warp + 8 * i) * 32));
+            }
+        }
+    }
     sync.wait();     // weights are immutable: only the activations depend on the previous stage
     // epilogue operands do not depend on the main loop: fetch them now so their L2 round trip is hidden
     constexpr int kTpb = 256 / (NJ * 8);            // threads per sequence in the epilogue
