@@ -96,6 +96,14 @@ __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv
             asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + (int64_t)k * d + 32));
         }
     }
+    // this thread's first key row (k = tid < pos) is an old cache row: it is loaded into registers before the wait
+    uint4 kpre[8];
+    const bool has_pre = !skip && tid < pos;
+    if (has_pre) {
+        const uint4* kr = reinterpret_cast<const uint4*>(kb + (int64_t)tid * d);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) kpre[c] = __ldcg(kr + c);
+    }
     pdl_wait();
     pdl_trigger();
     if (skip) return;
@@ -112,21 +120,40 @@ __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv
     __syncthreads();                                     // the appended row is visible to the whole block
     const int n_keys = pos + 1;
     float mx = -INFINITY;
-    for (int k = tid; k < n_keys; k += 128) {
-        const uint4* kr = reinterpret_cast<const uint4*>(kb + (int64_t)k * d);
+    auto score = [&](const uint4 (&u8)[8]) {
         float sc = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const uint4 u = __ldcg(kr + c);
+            const uint4 u = u8[c];
             float2 f;
             f = Op16<T>::unpack2(u.x); sc = fmaf(qf[c * 8 + 0], f.x, sc); sc = fmaf(qf[c * 8 + 1], f.y, sc);
             f = Op16<T>::unpack2(u.y); sc = fmaf(qf[c * 8 + 2], f.x, sc); sc = fmaf(qf[c * 8 + 3], f.y, sc);
             f = Op16<T>::unpack2(u.z); sc = fmaf(qf[c * 8 + 4], f.x, sc); sc = fmaf(qf[c * 8 + 5], f.y, sc);
             f = Op16<T>::unpack2(u.w); sc = fmaf(qf[c * 8 + 6], f.x, sc); sc = fmaf(qf[c * 8 + 7], f.y, sc);
         }
-        sc *= 0.125f;
+        return sc * 0.125f;
+    };
+    for (int k = tid; k < n_keys; k += 128) {
+        uint4 u8[8];
+        if (k == tid && has_pre) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) u8[c] = kpre[c];
+        } else {
+            const uint4* kr = reinterpret_cast<const uint4*>(kb + (int64_t)k * d);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) u8[c] = __ldcg(kr + c);
+        }
+        const float sc = score(u8);
         s_p[k] = sc;
         mx = fmaxf(mx, sc);
+    }
+    // the first batch of value rows does not depend on the softmax: request it before the block-wide reductions
+    // P V: warp w takes keys w, w + 4, ...; lane <-> 2 output dims; 16 value loads are issued before their FMAs
+    uint32_t vv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int k = min(warp + 4 * i, n_keys - 1);
+        vv[i] = __ldcg(reinterpret_cast<const uint32_t*>(vb + (int64_t)k * d) + lane);
     }
     mx = warp_max(mx);
     if (lane == 0) s_red[warp] = mx;
@@ -143,15 +170,15 @@ __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv
     if (lane == 0) s_red[warp] = sum;
     __syncthreads();
     const float inv = 1.0f / (((s_red[0] + s_red[1]) + s_red[2]) + s_red[3]);
-    // P V: warp w takes keys w, w + 4, ...; lane <-> 2 output dims; probabilities rounded to the operand type like
-    // ggml's mul_mat; 16 value loads are issued before their FMAs
+    // probabilities rounded to the operand type like ggml's mul_mat
     float o0 = 0.f, o1 = 0.f;
     for (int k0 = warp; k0 < n_keys; k0 += 64) {
-        uint32_t vv[16];
+        if (k0 != warp) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int k = min(k0 + 4 * i, n_keys - 1);
-            vv[i] = __ldcg(reinterpret_cast<const uint32_t*>(vb + (int64_t)k * d) + lane);
+            for (int i = 0; i < 16; ++i) {
+                const int k = min(k0 + 4 * i, n_keys - 1);
+                vv[i] = __ldcg(reinterpret_cast<const uint32_t*>(vb + (int64_t)k * d) + lane);
+            }
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
