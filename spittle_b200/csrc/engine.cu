@@ -169,9 +169,7 @@ struct Engine : EngineBase {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, prof_pool[i].a, prof_pool[i].b);
             if (prof_pool[i].cls == 0) { stats.gemm_ms += ms; stats.gemm_flops += prof_pool[i].work; stats.gemm_launches += 1; }
-            else if (prof_pool[i].cls == 1) { stats.attn_ms += ms; stats.attn_flops += prof_pool[i].work; stats.attn_launches += 1; }
-            else if (prof_pool[i].cls == 2) { stats.skinny_ms += ms; stats.skinny_bytes += prof_pool[i].work; stats.skinny_launches += 1; }
-            else { stats.xattn_ms += ms; stats.xattn_bytes += prof_pool[i].work; stats.xattn_launches += 1; }
+            else { stats.attn_ms += ms; stats.attn_flops += prof_pool[i].work; stats.attn_launches += 1; }
         }
         prof_used = 0;
     }
