@@ -3,6 +3,8 @@ is mounted; the GPU box only reads the committed outputs).
 
   silero_v4_16k.npz      the 16 kHz-branch tensors of the reference's own
                          src-tauri/resources/models/silero_vad_v4.onnx (weights only; MIT-licensed model)
+  capture_formats_golden.npz   outputs of oracle/capture_formats.py (the restatement of the reference's own
+                         audio/utils.rs and audio/visualizer.rs) on seeded synthetic inputs
   oracle_golden.npz      outputs of THIS repo's oracle on seeded synthetic inputs -- they pin the oracle
                          against drift; none of them comes from the reference (it has no fixtures on
                          this path)
@@ -15,13 +17,27 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-from oracle import logmel, resample, silero, vad_gate, whisper_ref      # noqa: E402
+from oracle import capture_formats, logmel, resample, silero, vad_gate, whisper_ref      # noqa: E402
 from spittle_b200 import silero_weights, synth                          # noqa: E402
 
 ONNX = "/root/reference/src-tauri/resources/models/silero_vad_v4.onnx"
 
 
+def capture_formats_fixture():
+    c = {}
+    x = synth.make_clip(41, seconds=0.3, sr=48000)[: 12 * 1024]
+    c["vis_clip41_48k_chunk1024"] = capture_formats.visualiser_levels(x, 1024, 48000)
+    x16 = synth.make_clip(42, seconds=0.5)[: 12 * 512]
+    c["vis_clip42_16k_chunk512"] = capture_formats.visualiser_levels(x16, 512, 16000)
+    c["i16_clip42_head"] = capture_formats.pcm_f32_to_i16(x16[:256] * 4.0)          # x4: exercises the saturation
+    np.savez_compressed(os.path.join(HERE, "capture_formats_golden.npz"), **c)
+    print("wrote", sorted(c))
+
+
 def main():
+    if "--capture-only" in sys.argv:
+        return capture_formats_fixture()
+    capture_formats_fixture()
     w = silero_weights.silero_v4_16k_from_onnx(ONNX)
     np.savez_compressed(os.path.join(HERE, "silero_v4_16k.npz"), **w)
     g = {}

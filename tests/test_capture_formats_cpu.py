@@ -37,3 +37,16 @@ def test_visualiser_tone_lands_in_the_right_bucket_and_silence_is_zero():
     # only the first 512 samples of a chunk are analysed: changing the tail changes nothing
     tone2 = tone.copy(); tone2[512:] = 0
     assert np.array_equal(cf.AudioVisualiser(sr).feed(tone2), lv)
+
+
+def test_oracle_reproduces_capture_format_fixtures():
+    """tests/golden/capture_formats_golden.npz (tests/golden/make_golden.py) pins the oracle against drift."""
+    import os
+    from spittle_b200 import synth
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "capture_formats_golden.npz"))
+    x = synth.make_clip(41, seconds=0.3, sr=48000)[: 12 * 1024]
+    assert np.allclose(cf.visualiser_levels(x, 1024, 48000), gold["vis_clip41_48k_chunk1024"], atol=1e-6)
+    x16 = synth.make_clip(42, seconds=0.5)[: 12 * 512]
+    assert np.allclose(cf.visualiser_levels(x16, 512, 16000), gold["vis_clip42_16k_chunk512"], atol=1e-6)
+    assert np.array_equal(cf.pcm_f32_to_i16(x16[:256] * 4.0), gold["i16_clip42_head"])
+    assert np.abs(gold["i16_clip42_head"]).max() == 32767 or np.abs(gold["i16_clip42_head"].astype(np.int32)).max() == 32768
