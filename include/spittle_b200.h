@@ -115,6 +115,8 @@ SB_API int sb_downmix_mono_dev(const void* in, int sample_format, int channels, 
  * out[i] = (in[i] * 32767) as i16 with Rust's cast semantics (truncate toward zero, saturate, NaN -> 0).
  * Device pointers, 16-byte aligned, async on `stream`. */
 SB_API int sb_pcm_f32_to_i16_dev(const float* in, int16_t* out, size_t n, void* stream);
+/* same with host pointers (what save_wav_file's caller has: a &[f32]); synchronous */
+SB_API int sb_pcm_f32_to_i16(const float* samples, int16_t* out, size_t n);
 
 /* Mic-level visualiser, batched.  Replaces AudioVisualiser::{new, feed} (audio_toolkit/audio/visualizer.rs:20-149,
  * constructed at audio/recorder.rs:276-282 with window 512, 16 buckets, 400-4000 Hz; fed once per captured chunk,
@@ -123,6 +125,9 @@ SB_API int sb_pcm_f32_to_i16_dev(const float* in, int16_t* out, size_t n, void* 
  * chunk_len >= 512; out [n_streams][n_chunks][16] f32.  Device pointers, async on `stream`. */
 SB_API int sb_visualiser_levels_dev(const float* pcm, int64_t stream_stride, int n_streams, int n_chunks, int chunk_len,
                                     int sample_rate, float* out, void* stream);
+/* one stream with host pointers: pcm[n_samples] cut into chunks of chunk_len (a trailing partial chunk is ignored);
+ * out [n_chunks][16], *n_chunks_out = n_samples / chunk_len; synchronous */
+SB_API int sb_visualiser_levels(const float* pcm, size_t n_samples, int chunk_len, int sample_rate, float* out, int* n_chunks_out);
 
 /* Silero VAD v4 (16 kHz branch).  Replaces vad_rs::Vad::{new, compute} over onnxruntime
  * (audio_toolkit/vad/silero.rs:25,41-44).  blob: the f32 tensors of the model in the order of

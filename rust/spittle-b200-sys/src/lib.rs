@@ -56,6 +56,9 @@ extern "C" {
                                count: size_t, p: *const sb_params, out: *mut sb_result) -> c_int;
     pub fn sb_result_free(r: *mut sb_result);
     // capture-side formats: history WAV payload, mic-level visualiser; device pointers
+    pub fn sb_pcm_f32_to_i16(samples: *const c_float, out: *mut i16, n: size_t) -> c_int;
+    pub fn sb_visualiser_levels(pcm: *const c_float, n_samples: size_t, chunk_len: c_int, sample_rate: c_int,
+                                out: *mut c_float, n_chunks_out: *mut c_int) -> c_int;
     pub fn sb_pcm_f32_to_i16_dev(input: *const c_float, out: *mut i16, n: size_t, stream: *mut core::ffi::c_void) -> c_int;
     pub fn sb_visualiser_levels_dev(pcm: *const c_float, stream_stride: i64, n_streams: c_int, n_chunks: c_int,
                                     chunk_len: c_int, sample_rate: c_int, out: *mut c_float,

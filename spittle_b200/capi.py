@@ -319,6 +319,8 @@ def _declare_frontend(l: C.CDLL) -> None:
     vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
     l.sb_downmix_mono_dev.argtypes = [vp, i32, i32, i64, sz, i32, vp, i64, vp]
     l.sb_pcm_f32_to_i16_dev.argtypes = [vp, vp, sz, vp]
+    l.sb_pcm_f32_to_i16.argtypes = [vp, vp, sz]
+    l.sb_visualiser_levels.argtypes = [vp, sz, i32, i32, vp, vp]
     l.sb_visualiser_levels_dev.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp]
     l.sb_resampler_create.argtypes = [i32, i32, C.POINTER(vp)]
     l.sb_resampler_destroy.argtypes = [vp]
@@ -397,6 +399,24 @@ def downmix_mono_dev(in_ptr, sample_format: int, channels: int, in_stride: int, 
 
 def pcm_f32_to_i16_dev(in_ptr, out_ptr, n: int, stream=None) -> None:
     check(lib().sb_pcm_f32_to_i16_dev(in_ptr, out_ptr, n, stream or None))
+
+
+def pcm_f32_to_i16(samples: np.ndarray) -> np.ndarray:
+    """Host arrays: (sample * 32767) as i16 (audio_toolkit/audio/utils.rs:17-20)."""
+    x = np.ascontiguousarray(samples, np.float32).reshape(-1)
+    out = np.empty(x.shape[0], np.int16)
+    check(lib().sb_pcm_f32_to_i16(x.ctypes.data, out.ctypes.data, x.shape[0]))
+    return out
+
+
+def visualiser_levels(pcm: np.ndarray, chunk_len: int, sample_rate: int) -> np.ndarray:
+    """Host arrays, one stream: [n_chunks, 16] levels (audio_toolkit/audio/visualizer.rs:84-149)."""
+    x = np.ascontiguousarray(pcm, np.float32).reshape(-1)
+    n_chunks = x.shape[0] // chunk_len
+    out = np.empty((max(n_chunks, 1), 16), np.float32)
+    n = C.c_int(0)
+    check(lib().sb_visualiser_levels(x.ctypes.data, x.shape[0], chunk_len, sample_rate, out.ctypes.data, C.addressof(n)))
+    return out[: n.value]
 
 
 def visualiser_levels_dev(pcm_ptr, stream_stride: int, n_streams: int, n_chunks: int, chunk_len: int, sample_rate: int,

@@ -151,3 +151,43 @@ extern "C" int sb_visualiser_levels_dev(const float* pcm, int64_t stream_stride,
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
 }
+
+// ---- host-pointer forms: what the reference's (CUDA-free) Rust side calls -- save_wav_file hands over a &[f32], the
+//      recorder a captured chunk; staging buffers live for the duration of the call like sb_logmel's ----------------
+extern "C" int sb_pcm_f32_to_i16(const float* samples, int16_t* out, size_t n) {
+    SB_CHECK_ARG(samples && out, "null pointer");
+    if (n == 0) return SB_OK;
+    float* d_in = nullptr; int16_t* d_out = nullptr;
+    SB_CUDA_CHECK(cudaMalloc(&d_in, n * sizeof(float)));
+    cudaError_t e = cudaMalloc(&d_out, n * sizeof(int16_t));
+    int rc = SB_OK;
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, samples, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = sb_pcm_f32_to_i16_dev(d_in, d_out, n, nullptr);
+        if (rc == SB_OK) e = cudaMemcpy(out, d_out, n * sizeof(int16_t), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) { sb::set_error(std::string("sb_pcm_f32_to_i16: ") + cudaGetErrorString(e)); return SB_ERR_CUDA; }
+    return rc;
+}
+
+extern "C" int sb_visualiser_levels(const float* pcm, size_t n_samples, int chunk_len, int sample_rate, float* out, int* n_chunks_out) {
+    SB_CHECK_ARG(pcm && out, "null pointer");
+    SB_CHECK_ARG(chunk_len >= sb::kVisN, "visualiser: a chunk must hold the 512-sample analysis window");
+    const int n_chunks = (int)(n_samples / (size_t)chunk_len);
+    if (n_chunks_out) *n_chunks_out = n_chunks;
+    if (n_chunks == 0) return SB_OK;
+    const size_t n = (size_t)n_chunks * chunk_len;
+    float *d_in = nullptr, *d_out = nullptr;
+    SB_CUDA_CHECK(cudaMalloc(&d_in, n * sizeof(float)));
+    cudaError_t e = cudaMalloc(&d_out, (size_t)n_chunks * sb::kVisBuckets * sizeof(float));
+    int rc = SB_OK;
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, pcm, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = sb_visualiser_levels_dev(d_in, (int64_t)n, 1, n_chunks, chunk_len, sample_rate, d_out, nullptr);
+        if (rc == SB_OK) e = cudaMemcpy(out, d_out, (size_t)n_chunks * sb::kVisBuckets * sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) { sb::set_error(std::string("sb_visualiser_levels: ") + cudaGetErrorString(e)); return SB_ERR_CUDA; }
+    return rc;
+}

@@ -65,3 +65,15 @@ def test_visualiser_levels_match_oracle(cuda_dev, sr, chunk):
     assert got.shape == want.shape == (n_streams, n_chunks, 16)
     assert np.abs(got - want).max() <= 2e-4, np.abs(got - want).max()
     assert (got[3] == 0).all() and got.min() >= 0.0 and got.max() <= 1.0
+
+
+def test_host_pointer_forms_match_oracle(cuda_dev):
+    """sb_pcm_f32_to_i16 / sb_visualiser_levels: what a CUDA-free host (the reference's Rust side) calls."""
+    x = synth.make_clip(43, seconds=0.6, sr=48000)
+    assert (capi.pcm_f32_to_i16(x * 4.0) == cf.pcm_f32_to_i16(x * 4.0)).all()
+    assert capi.pcm_f32_to_i16(np.zeros(0, np.float32)).shape == (0,)
+    got = capi.visualiser_levels(x, 1024, 48000)
+    want = cf.visualiser_levels(x, 1024, 48000)
+    assert got.shape == want.shape == (x.shape[0] // 1024, 16)
+    assert np.abs(got - want).max() <= 2e-4
+    assert capi.visualiser_levels(x[:700], 1024, 48000).shape == (0, 16)      # no whole chunk: nothing emitted
