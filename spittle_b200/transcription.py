@@ -14,7 +14,7 @@ from typing import Callable, Dict, List, Optional
 
 import numpy as np
 
-from . import capi, text_filters
+from . import capi, jargon, text_filters
 
 
 class TranscriptionError(RuntimeError):
@@ -30,6 +30,11 @@ class Settings:
     model_unload_timeout: str = "never"      # "never" | "immediately" | seconds as str
     custom_words: List[str] = field(default_factory=list)
     word_correction_threshold: float = 0.18      # default_settings.json / settings.rs
+    # jargon (settings.rs; all empty by default): profile ids, user terms / corrections, and the profile table itself
+    jargon_enabled_profiles: List[str] = field(default_factory=list)
+    jargon_custom_terms: List[str] = field(default_factory=list)
+    jargon_custom_corrections: List["jargon.JargonCorrection"] = field(default_factory=list)
+    jargon_profiles: Dict[str, "jargon.JargonProfile"] = field(default_factory=dict)
     device: int = 0
     max_batch: int = 64
     dtype: int = capi.SB_DTYPE_F16
@@ -108,12 +113,18 @@ class TranscriptionManager:
 
     @staticmethod
     def _post_filter(text: str, s: Settings) -> str:
-        """transcription.rs:537-549: custom-word correction (only when configured), then the filler /
-        stutter / hallucination filter.  Jargon corrections (:552-580) are settings-driven string rules
-        outside this path's scope (off in the default settings)."""
+        """transcription.rs:537-580: custom-word correction (only when configured), the filler / stutter /
+        hallucination filter, then the jargon corrections (only when profiles or custom corrections are configured)."""
         if s.custom_words:
             text = text_filters.apply_custom_words(text, s.custom_words, s.word_correction_threshold)
-        return text_filters.filter_transcription_output(text)
+        text = text_filters.filter_transcription_output(text)
+        if s.jargon_enabled_profiles or s.jargon_custom_corrections:
+            d = jargon.compute_active_dictionary(
+                jargon.JargonSettings(s.jargon_enabled_profiles, s.jargon_custom_terms, s.jargon_custom_corrections),
+                s.jargon_profiles)
+            if d.corrections:
+                text = jargon.apply_corrections(text, d.corrections)
+        return text
 
     def transcribe(self, audio) -> str:
         self._last_activity = time.time()
