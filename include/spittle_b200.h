@@ -153,6 +153,19 @@ SB_API int sb_vad_gate_dev(const float* probs, const float* pcm16k, int64_t pcm_
                            float* out, int64_t out_stride, int32_t* out_frames, void* workspace,
                            void* stream);
 
+/* The capture stages by their blueprint names, host pointers, ONE stream, synchronous: staging
+ * wrappers over the batched device forms above for a caller without CUDA code (the reference's Rust side).
+ *   sb_resample_48k_16k  FrameResampler::{push(all), finish} at 48 -> 16 kHz (audio/resampler.rs:16-98): *n_out =
+ *                        480 * frames emitted (also set when out_cap is too small, which fails with SB_ERR_INVALID)
+ *   sb_silero_v4         SileroVad scoring of n_frames 480-sample frames (vad/silero.rs:41-44); h, c: [2][64] f32,
+ *                        read and updated like vad-rs carries them from frame to frame
+ *   sb_vad_gate          SmoothedVad::push_frame over the frames + concatenation of the kept ones (vad/smoothed.rs:41-96,
+ *                        recorder.rs:284-314); *out_frames may exceed n_frames (an onset re-emits the prefill ring) */
+SB_API int sb_resample_48k_16k(const float* pcm48k, size_t n_in, float* out16k, size_t out_cap, size_t* n_out);
+SB_API int sb_silero_v4(const sb_vad* v, const float* pcm16k, int n_frames, float* h_state, float* c_state, float* probs);
+SB_API int sb_vad_gate(const float* probs, const float* pcm16k, int n_frames, float threshold, int prefill, int hangover,
+                       int onset, float* out, size_t out_cap, int* out_frames);
+
 /* ------------------------------------------------------------------------------------
  * Tensor-core GEMM stage entry (parity tests / benchmarks).  C[M,N] = epi(A[M,K] * W[N,K]^T)
  * with tcgen05.mma, TMEM accumulators, TMA-fed.  Replaces ggml's CPU mul_mat (f16 x f16 ->
@@ -293,6 +306,7 @@ SB_API int sb_encode(sb_engine* e, const float* mel_windows, int n_windows, floa
  *   logits_out  [n_windows][n_steps][n_vocab] raw f32 logits before filtering; may be NULL
  *   tokens_out  [n_windows][n_steps] sampled tokens;  margins_out same shape or NULL
  * seek = 0 and seek_end = seek_end[w] for every window. */
+/* (the blueprint's `sb_decode_step` is this entry with n_steps = 1) */
 SB_API int sb_decode_trace(sb_engine* e, const float* mel_windows, int n_windows, const int32_t* seek_end,
                            const sb_params* p, const int32_t* forced, int n_steps, float* logits_out,
                            int32_t* tokens_out, float* margins_out);

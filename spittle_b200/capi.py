@@ -320,6 +320,9 @@ def _declare_frontend(l: C.CDLL) -> None:
     l.sb_downmix_mono_dev.argtypes = [vp, i32, i32, i64, sz, i32, vp, i64, vp]
     l.sb_pcm_f32_to_i16_dev.argtypes = [vp, vp, sz, vp]
     l.sb_pcm_f32_to_i16.argtypes = [vp, vp, sz]
+    l.sb_resample_48k_16k.argtypes = [vp, sz, vp, sz, vp]
+    l.sb_silero_v4.argtypes = [vp, vp, i32, vp, vp, vp]
+    l.sb_vad_gate.argtypes = [vp, vp, i32, C.c_float, i32, i32, i32, vp, sz, vp]
     l.sb_visualiser_levels.argtypes = [vp, sz, i32, i32, vp, vp]
     l.sb_visualiser_levels_dev.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp]
     l.sb_resampler_create.argtypes = [i32, i32, C.POINTER(vp)]
@@ -399,6 +402,38 @@ def downmix_mono_dev(in_ptr, sample_format: int, channels: int, in_stride: int, 
 
 def pcm_f32_to_i16_dev(in_ptr, out_ptr, n: int, stream=None) -> None:
     check(lib().sb_pcm_f32_to_i16_dev(in_ptr, out_ptr, n, stream or None))
+
+
+def resample_48k_16k(pcm48k: np.ndarray) -> np.ndarray:
+    """Host arrays, one stream: FrameResampler push(all) + finish at 48 -> 16 kHz; returns whole 480-sample frames."""
+    x = np.ascontiguousarray(pcm48k, np.float32).reshape(-1)
+    out = np.empty(x.shape[0] // 3 + 2048, np.float32)
+    n = C.c_size_t(0)
+    check(lib().sb_resample_48k_16k(x.ctypes.data, x.shape[0], out.ctypes.data, out.shape[0], C.addressof(n)))
+    return out[: n.value].copy()
+
+
+def silero_v4(vad: "Vad", pcm16k: np.ndarray, h: np.ndarray, c: np.ndarray) -> np.ndarray:
+    """Host arrays, one stream: probabilities of the whole 480-sample frames of pcm16k; h, c [2, 64] are updated in place."""
+    x = np.ascontiguousarray(pcm16k, np.float32).reshape(-1)
+    n_frames = x.shape[0] // 480
+    probs = np.empty(n_frames, np.float32)
+    assert h.dtype == np.float32 and c.dtype == np.float32 and h.shape == (2, 64) and c.shape == (2, 64)
+    check(lib().sb_silero_v4(vad._h, x.ctypes.data, n_frames, h.ctypes.data, c.ctypes.data, probs.ctypes.data))
+    return probs
+
+
+def vad_gate(probs: np.ndarray, pcm16k: np.ndarray, threshold: float, prefill: int, hangover: int, onset: int) -> np.ndarray:
+    """Host arrays, one stream: the samples SmoothedVad keeps (concatenated Speech slices)."""
+    p = np.ascontiguousarray(probs, np.float32).reshape(-1)
+    x = np.ascontiguousarray(pcm16k, np.float32).reshape(-1)
+    n_frames = p.shape[0]
+    cap = (n_frames * (prefill + 1 + onset) // max(1, onset) + prefill + 1) * 480
+    out = np.empty(max(cap, 1), np.float32)
+    cnt = C.c_int(0)
+    check(lib().sb_vad_gate(p.ctypes.data, x.ctypes.data, n_frames, threshold, prefill, hangover, onset, out.ctypes.data, cap,
+                            C.addressof(cnt)))
+    return out[: cnt.value * 480].copy()
 
 
 def pcm_f32_to_i16(samples: np.ndarray) -> np.ndarray:

@@ -5,6 +5,8 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cstdint>
+#include <string>
+#include <vector>
 
 namespace sb {
 extern std::atomic<uint64_t> g_launches;
@@ -190,4 +192,103 @@ extern "C" int sb_visualiser_levels(const float* pcm, size_t n_samples, int chun
     cudaFree(d_in); cudaFree(d_out);
     if (e != cudaSuccess) { sb::set_error(std::string("sb_visualiser_levels: ") + cudaGetErrorString(e)); return SB_ERR_CUDA; }
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// SURVEY.md 8(b) stage entry points by their blueprint names, host pointers, one stream, synchronous: thin staging
+// wrappers over the batched device forms in frontend.cu (for a CUDA-free caller such as the reference's Rust side).
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+struct DevBufs {                       // frees whatever was allocated when the call leaves
+    std::vector<void*> p;
+    ~DevBufs() { for (void* q : p) cudaFree(q); }
+    template <typename V> cudaError_t alloc(V** out, size_t bytes) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, bytes ? bytes : 1);
+        if (e == cudaSuccess) { p.push_back(q); *out = (V*)q; }
+        return e;
+    }
+};
+int cuda_fail(const char* what, cudaError_t e) { sb::set_error(std::string(what) + ": " + cudaGetErrorString(e)); return SB_ERR_CUDA; }
+}  // namespace
+
+extern "C" int sb_resample_48k_16k(const float* pcm48k, size_t n_in, float* out16k, size_t out_cap, size_t* n_out) {
+    SB_CHECK_ARG(pcm48k && out16k && n_out, "null pointer");
+    sb_resampler* r = nullptr;
+    int rc = sb_resampler_create(48000, 16000, &r);
+    if (rc != SB_OK) return rc;
+    size_t n_fed = 0, n_res = 0, n_frames = 0;
+    rc = sb_resample_geometry(r, n_in, &n_fed, &n_res, &n_frames);
+    const size_t need = n_frames * 480;
+    *n_out = need;
+    if (rc == SB_OK && need > out_cap) { sb::set_error("sb_resample_48k_16k: output buffer too small"); rc = SB_ERR_INVALID; }
+    if (rc == SB_OK && need > 0) {
+        DevBufs b;
+        float *d_in = nullptr, *d_out = nullptr;
+        cudaError_t e = b.alloc(&d_in, n_in * sizeof(float));
+        if (e == cudaSuccess) e = b.alloc(&d_out, need * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(d_in, pcm48k, n_in * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            rc = sb_resample_dev(r, d_in, (int64_t)n_in, n_in, 1, d_out, (int64_t)need, nullptr);
+            if (rc == SB_OK) e = cudaMemcpy(out16k, d_out, need * sizeof(float), cudaMemcpyDeviceToHost);
+        }
+        if (e != cudaSuccess) rc = cuda_fail("sb_resample_48k_16k", e);
+    }
+    sb_resampler_destroy(r);
+    return rc;
+}
+
+extern "C" int sb_silero_v4(const sb_vad* v, const float* pcm16k, int n_frames, float* h_state, float* c_state, float* probs) {
+    SB_CHECK_ARG(v && pcm16k && h_state && c_state && probs, "null pointer");
+    if (n_frames <= 0) return SB_OK;
+    DevBufs b;
+    float *d_pcm = nullptr, *d_h = nullptr, *d_c = nullptr, *d_p = nullptr; void* d_ws = nullptr;
+    const size_t n = (size_t)n_frames * 480;
+    cudaError_t e = b.alloc(&d_pcm, n * sizeof(float));
+    if (e == cudaSuccess) e = b.alloc(&d_h, 2 * 64 * sizeof(float));
+    if (e == cudaSuccess) e = b.alloc(&d_c, 2 * 64 * sizeof(float));
+    if (e == cudaSuccess) e = b.alloc(&d_p, (size_t)n_frames * sizeof(float));
+    if (e == cudaSuccess) e = b.alloc(&d_ws, sb_vad_workspace_bytes(1, n_frames));
+    if (e == cudaSuccess) e = cudaMemcpy(d_pcm, pcm16k, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_h, h_state, 2 * 64 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_c, c_state, 2 * 64 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail("sb_silero_v4", e);
+    int rc = sb_vad_score_dev(v, d_pcm, (int64_t)n, 1, n_frames, d_h, d_c, d_p, d_ws, nullptr);
+    if (rc != SB_OK) return rc;
+    e = cudaMemcpy(probs, d_p, (size_t)n_frames * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_state, d_h, 2 * 64 * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(c_state, d_c, 2 * 64 * sizeof(float), cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? SB_OK : cuda_fail("sb_silero_v4", e);
+}
+
+extern "C" int sb_vad_gate(const float* probs, const float* pcm16k, int n_frames, float threshold, int prefill, int hangover,
+                           int onset, float* out, size_t out_cap, int* out_frames) {
+    SB_CHECK_ARG(probs && pcm16k && out && out_frames, "null pointer");
+    SB_CHECK_ARG(prefill >= 0 && hangover >= 0 && onset >= 1, "bad gate parameters");
+    *out_frames = 0;
+    if (n_frames <= 0) return SB_OK;
+    // every onset may re-emit the prefill ring: worst case (prefill + 1) extra frames per `onset` voiced frames
+    const size_t max_frames = (size_t)n_frames * (prefill + 1 + onset) / onset + prefill + 1;
+    DevBufs b;
+    float *d_pr = nullptr, *d_pcm = nullptr, *d_out = nullptr; int32_t* d_cnt = nullptr; void* d_ws = nullptr;
+    const size_t n = (size_t)n_frames * 480;
+    cudaError_t e = b.alloc(&d_pr, (size_t)n_frames * sizeof(float));
+    if (e == cudaSuccess) e = b.alloc(&d_pcm, n * sizeof(float));
+    if (e == cudaSuccess) e = b.alloc(&d_out, max_frames * 480 * sizeof(float));
+    if (e == cudaSuccess) e = b.alloc(&d_cnt, sizeof(int32_t));
+    if (e == cudaSuccess) e = b.alloc(&d_ws, sb_vad_gate_workspace_bytes(1, n_frames));
+    if (e == cudaSuccess) e = cudaMemcpy(d_pr, probs, (size_t)n_frames * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_pcm, pcm16k, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_cnt, 0, sizeof(int32_t));
+    if (e != cudaSuccess) return cuda_fail("sb_vad_gate", e);
+    int rc = sb_vad_gate_dev(d_pr, d_pcm, (int64_t)n, 1, n_frames, threshold, prefill, hangover, onset, d_out, (int64_t)(max_frames * 480),
+                             d_cnt, d_ws, nullptr);
+    if (rc != SB_OK) return rc;
+    int32_t cnt = 0;
+    e = cudaMemcpy(&cnt, d_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return cuda_fail("sb_vad_gate", e);
+    *out_frames = cnt;
+    if ((size_t)cnt * 480 > out_cap) { sb::set_error("sb_vad_gate: output buffer too small"); return SB_ERR_INVALID; }
+    e = cudaMemcpy(out, d_out, (size_t)cnt * 480 * sizeof(float), cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? SB_OK : cuda_fail("sb_vad_gate", e);
 }

@@ -183,3 +183,28 @@ def test_downmix_mono_bit_exact(cuda_dev, fmt, dtype, channels):
         ref = vad_gate.downmix_mono(host[s, : n_frames * channels], channels)
         assert np.array_equal(got[s, :n_frames], ref)
         assert np.all(got[s, n_frames:] == 0)
+
+
+def test_blueprint_named_host_entries_match_the_batched_forms(cuda_dev):
+    """sb_resample_48k_16k / sb_silero_v4 / sb_vad_gate (SURVEY 8(b) names; host pointers, one stream): same results as
+    the oracle / the batched device forms they wrap."""
+    x48 = synth.make_clip(6, seconds=2.0, sr=48000, kind="vowel")
+    y = capi.resample_48k_16k(x48)
+    ref = resample.resample_block_fft(x48)
+    n = min(y.shape[0], ref.shape[0])
+    assert y.shape[0] % 480 == 0 and y.shape[0] >= n > 30000
+    assert np.abs(y[:n] - ref[:n]).max() <= RESAMPLE_TOL
+    # Silero on the resampled audio, state carried across two calls
+    w = silero_weights.load_npz(SILERO)
+    vad = capi.Vad(silero_weights.to_blob(w))
+    h, c = np.zeros((2, 64), np.float32), np.zeros((2, 64), np.float32)
+    half = (y.shape[0] // 480 // 2) * 480
+    probs = np.concatenate([capi.silero_v4(vad, y[:half], h, c), capi.silero_v4(vad, y[half:], h, c)])
+    o = silero.SileroOracle(w)
+    assert np.abs(probs - o.score(y)).max() <= SILERO_TOL
+    assert np.abs(h).max() > 0                                   # the state came back
+    # gate: bit-exact against the oracle plan
+    kept = capi.vad_gate(probs, y, 0.3, 15, 15, 2)
+    want = vad_gate.gate_audio(y.reshape(-1, 480), probs, 0.3, 15, 15, 2)
+    assert kept.shape == want.shape and np.array_equal(kept, want)
+    vad.close()
