@@ -286,6 +286,10 @@ SB_API int sb_engine_destroy(sb_engine* e);
 SB_API int sb_engine_info(const sb_engine* e, sb_model_info* info);
 /* id -> token bytes (whisper_token_to_str); returns length, copies at most cap bytes */
 SB_API int sb_token_text(const sb_engine* e, int32_t id, char* buf, int cap);
+/* whisper.cpp's tokeniser (whisper_tokenize, what turns WhisperInferenceParams::initial_prompt into prompt tokens,
+ * managers/transcription.rs:461-499): regex word split, then greedy longest vocabulary match per word.  Writes at most
+ * `cap` ids and returns the number of tokens of the text (>= 0), or a negative sb_status. */
+SB_API int sb_tokenize(const sb_engine* e, const char* text, int32_t* tokens, int cap);
 
 /* One clip: 16 kHz mono f32 host samples -> text.  Empty input returns SB_OK with empty text
  * (reference: transcription.rs:412-416); < 1 s of audio returns empty text like whisper.cpp

@@ -170,6 +170,7 @@ def _declare_engine(l: C.CDLL) -> None:
     l.sb_engine_destroy.argtypes = [vp]
     l.sb_engine_info.argtypes = [vp, C.POINTER(SbModelInfo)]
     l.sb_token_text.argtypes = [vp, C.c_int32, C.c_char_p, i32]
+    l.sb_tokenize.argtypes = [vp, C.c_char_p, vp, i32]
     l.sb_engine_stream.argtypes = [vp]
     l.sb_engine_stream.restype = vp
     l.sb_engine_set_profile.argtypes = [vp, i32]
@@ -252,6 +253,16 @@ class Engine:
         st = SbStats()
         check(lib().sb_engine_stats(self._h, C.byref(st), int(reset)))
         return {n: getattr(st, n) for n, _ in SbStats._fields_}
+
+    def tokenize(self, text) -> list:
+        """whisper.cpp tokenisation of a prompt text with this model's vocabulary."""
+        b = text if isinstance(text, bytes) else text.encode("utf-8")
+        n = lib().sb_tokenize(self._h, b, None, 0)
+        if n < 0:
+            check(n)
+        out = (C.c_int32 * max(n, 1))()
+        lib().sb_tokenize(self._h, b, C.addressof(out), n)
+        return [int(out[i]) for i in range(n)]
 
     def token_text(self, tid: int) -> bytes:
         buf = C.create_string_buffer(256)

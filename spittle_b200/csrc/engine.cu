@@ -9,6 +9,9 @@
 #include "ggml_loader.h"
 #include <algorithm>
 #include <memory>
+#include <mutex>
+#include <regex>
+#include <unordered_map>
 #include <vector>
 
 struct sb_melplan;
@@ -79,6 +82,34 @@ struct EngineBase {
     virtual int decode_trace(const float* mel_windows, int n_windows, const int32_t* seek_end, const sb_params& p,
                              const int32_t* forced, int n_steps, float* logits_out, int32_t* tokens_out,
                              float* margins_out) = 0;
+    // whisper.cpp `tokenize` (whisper_tokenize; used for initial_prompt) [MEM]: GPT-2 style word split by regex over the
+    // bytes of the text, then each word is cut greedily into the LONGEST vocabulary entries; bytes no entry covers are
+    // skipped.  token_to_id keeps the last id of a duplicated entry, like the loader's `token_to_id[word] = i`.
+    mutable std::unordered_map<std::string, int> token_to_id;
+    mutable std::once_flag token_to_id_once;
+    std::vector<int> tokenize(const std::string& text) const {
+        std::call_once(token_to_id_once, [this] {
+            for (int i = 0; i < (int)vocab.size(); ++i) token_to_id[vocab[i]] = i;
+        });
+        static const std::regex re(R"('s|'t|'re|'ve|'m|'ll|'d| ?[[:alpha:]]+| ?[[:digit:]]+| ?[^\s[:alpha:][:digit:]]+|\s+(?!\S)|\s+)");
+        std::vector<int> out;
+        for (std::sregex_iterator it(text.begin(), text.end(), re), end; it != end; ++it) {
+            const std::string word = it->str();
+            const int n = (int)word.size();
+            int i = 0;
+            while (i < n) {
+                int j = n;
+                bool found = false;
+                while (j > i) {
+                    auto f = token_to_id.find(word.substr(i, j - i));
+                    if (f != token_to_id.end()) { out.push_back(f->second); i = j; found = true; break; }
+                    --j;
+                }
+                if (!found) ++i;          // whisper.cpp logs "unknown token" and moves on
+            }
+        }
+        return out;
+    }
     std::string token_text(int id) const {
         if (id >= 0 && id < (int)vocab.size()) return vocab[id];
         if (id == sp.eot) return "[_EOT_]";
@@ -1045,6 +1076,14 @@ int sb_token_text(const sb_engine* e, int32_t id, char* buf, int cap) {
     const std::string s = e->impl->token_text(id);
     if (buf && cap > 0) memcpy(buf, s.data(), std::min<size_t>(s.size(), (size_t)cap));
     return (int)s.size();
+}
+
+int sb_tokenize(const sb_engine* e, const char* text, int32_t* tokens, int cap) {
+    if (!e) { sb::set_error("Model is not loaded for transcription."); return SB_ERR_NOT_LOADED; }
+    SB_CHECK_ARG(text && (tokens || cap == 0), "null pointer");
+    const std::vector<int> t = e->impl->tokenize(text);
+    for (int i = 0; i < (int)t.size() && i < cap; ++i) tokens[i] = t[i];
+    return (int)t.size();
 }
 
 int sb_transcribe_batch(sb_engine* e, const float* const* pcm16k, const size_t* n_samples, size_t count,

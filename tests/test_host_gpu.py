@@ -114,3 +114,22 @@ def test_long_audio_many_windows_and_batch_chunking(cuda_dev, model_dir):
     for i in (0, 17, 64, 127):
         assert out[i].sampled == big.transcribe(many[i], params).sampled
     big.close()
+
+
+def test_engine_tokenizer_matches_the_mirror(cuda_dev, model_dir):
+    """sb_tokenize (C++: std::regex word split + greedy longest vocabulary match) == spittle_b200/tokenizer.py on the
+    synthetic vocabulary, for the text jargon.build_initial_prompt produces and for odd input."""
+    from spittle_b200 import ggml_format, jargon, tokenizer
+    path = synth.ensure_model_file("nano", model_dir)
+    model = ggml_format.read_ggml(path)
+    eng = capi.Engine(path, max_batch=2)
+    t2i = tokenizer.token_to_id(model.vocab)
+    prompt = jargon.build_initial_prompt(jargon.ActiveDictionary(["TypeScript", "Next.js", "kubectl", "EC2", "O'Reilly's"], []))
+    texts = [prompt, "", "   leading spaces and\ttabs\n", "it's 42 degrees, isn't it?", "café naïve — done", " " .join(
+        model.vocab[i].decode("utf-8", errors="ignore") for i in (400, 4000, 14000, 30000))]
+    for t in texts:
+        got = eng.tokenize(t)
+        want = tokenizer.tokenize(t2i, t)
+        assert got == want, (t, got[:8], want[:8])
+    assert len(eng.tokenize(prompt)) > 0
+    eng.close()
