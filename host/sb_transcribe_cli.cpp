@@ -8,6 +8,7 @@
 #include <iterator>
 #include <iostream>
 
+#include "jargon.hpp"
 #include "text_filters.hpp"
 #include "transcription_manager.hpp"
 
@@ -21,6 +22,23 @@ int main(int argc, char** argv) {
         if (argc < 3) return 2;
         std::vector<std::string> words(argv + 3, argv + argc);
         std::fputs(sb::apply_custom_words(text, words, std::atof(argv[2])).c_str(), stdout);
+        return 0;
+    }
+    //   sb_transcribe_cli --jargon-correct from1 to1 from2 to2 ..   compute_active_dictionary (custom corrections only) +
+    //                                                               apply_corrections on stdin
+    //   sb_transcribe_cli --jargon-prompt term1 term2 ..            build_initial_prompt of the custom terms
+    if (argc >= 2 && !std::strcmp(argv[1], "--jargon-correct")) {
+        std::string text((std::istreambuf_iterator<char>(std::cin)), std::istreambuf_iterator<char>());
+        sb::JargonSettings js;
+        for (int i = 2; i + 1 < argc; i += 2) js.custom_corrections.push_back({argv[i], argv[i + 1]});
+        const sb::ActiveDictionary d = sb::compute_active_dictionary(js, {});
+        std::fputs(sb::apply_corrections(text, d.corrections).c_str(), stdout);
+        return 0;
+    }
+    if (argc >= 2 && !std::strcmp(argv[1], "--jargon-prompt")) {
+        sb::JargonSettings js;
+        for (int i = 2; i < argc; ++i) js.custom_terms.push_back(argv[i]);
+        std::fputs(sb::build_initial_prompt(sb::compute_active_dictionary(js, {})).c_str(), stdout);
         return 0;
     }
     if (argc < 3) { std::fprintf(stderr, "usage: %s model.bin clip.f32 [language]\n", argv[0]); return 2; }

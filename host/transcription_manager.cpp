@@ -123,6 +123,19 @@ std::string TranscriptionManager::effective_language(const Settings& s) const {
     return s.selected_language;
 }
 
+// transcription.rs:537-580: custom-word correction (only when configured), the filler / stutter / hallucination filter,
+// then the jargon corrections (only when profiles or custom corrections are configured)
+static std::string post_filter(std::string text, const Settings& s) {
+    if (!s.custom_words.empty()) text = apply_custom_words(text, s.custom_words, s.word_correction_threshold);
+    text = filter_transcription_output(text);
+    if (!s.jargon_enabled_profiles.empty() || !s.jargon_custom_corrections.empty()) {
+        JargonSettings js{s.jargon_enabled_profiles, s.jargon_custom_terms, s.jargon_custom_corrections};
+        const ActiveDictionary d = compute_active_dictionary(js, s.jargon_profiles);
+        if (!d.corrections.empty()) text = apply_corrections(text, d.corrections);
+    }
+    return text;
+}
+
 Result<std::string> TranscriptionManager::transcribe(std::vector<float> audio) {
     last_activity_.store(now_ms());
     if (audio.empty()) {                                      // transcription.rs:412-416
@@ -149,10 +162,7 @@ Result<std::string> TranscriptionManager::transcribe(std::vector<float> audio) {
         text.assign(r.text ? r.text : "", r.text_len);
         sb_result_free(&r);
     }
-    // transcription.rs:537-549: custom-word correction (only when configured), then the filler / stutter /
-    // hallucination filter.  Jargon corrections (:552-580) are settings-driven string rules outside this path.
-    if (!s.custom_words.empty()) text = apply_custom_words(text, s.custom_words, s.word_correction_threshold);
-    text = filter_transcription_output(text);
+    text = post_filter(text, s);
     maybe_unload_immediately("transcription");
     return Result<std::string>::Ok(std::move(text));
 }
@@ -185,8 +195,7 @@ std::vector<Result<std::string>> TranscriptionManager::transcribe_batch(const st
     } else {
         for (size_t i = 0; i < clips.size(); ++i) {
             std::string text(res[i].text ? res[i].text : "", res[i].text_len);
-            if (!s.custom_words.empty()) text = apply_custom_words(text, s.custom_words, s.word_correction_threshold);
-            out[i] = Result<std::string>::Ok(filter_transcription_output(text));
+            out[i] = Result<std::string>::Ok(post_filter(text, s));
         }
     }
     for (auto& r : res) sb_result_free(&r);

@@ -18,6 +18,7 @@
 //
 // Result<T> is modelled as sb::Result<T>{ok, value, error}; the error strings are the reference's.
 #pragma once
+#include "jargon.hpp"
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -55,6 +56,10 @@ struct Settings {
     ModelUnloadTimeout model_unload_timeout = ModelUnloadTimeout::Never;
     std::vector<std::string> custom_words;            // settings.rs custom_words
     double word_correction_threshold = 0.18;          // settings.rs:446-448
+    // jargon (all empty by default): profile ids, user terms / corrections, and the profile table they index
+    std::vector<std::string> jargon_enabled_profiles, jargon_custom_terms;
+    std::vector<JargonCorrection> jargon_custom_corrections;
+    std::map<std::string, JargonProfile> jargon_profiles;
     int device = 0;
     int max_batch = 64;
     int dtype = SB_DTYPE_F16;

@@ -97,9 +97,10 @@ def build_host() -> str:
     """C++ host-side mirror of the reference TranscriptionManager + a small CLI over it."""
     root = os.path.dirname(HERE)
     out = os.path.join(root, "host", "sb_transcribe_cli")
-    srcs = [os.path.join(root, "host", f) for f in ("transcription_manager.cpp", "text_filters.cpp", "sb_transcribe_cli.cpp")]
+    srcs = [os.path.join(root, "host", f) for f in ("transcription_manager.cpp", "text_filters.cpp", "jargon.cpp", "sb_transcribe_cli.cpp")]
     newest = max(os.path.getmtime(p) for p in srcs + [os.path.join(root, "host", "transcription_manager.hpp"),
-                                                      os.path.join(root, "host", "text_filters.hpp"), LIB])
+                                                      os.path.join(root, "host", "text_filters.hpp"),
+                                                      os.path.join(root, "host", "jargon.hpp"), LIB])
     if os.path.exists(out) and os.path.getmtime(out) >= newest:
         return out
     cmd = ["g++", "-std=c++17", "-O2", "-I", INCLUDE] + srcs + ["-o", out, "-L", HERE, "-lspittle_b200",

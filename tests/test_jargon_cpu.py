@@ -83,3 +83,53 @@ def test_manager_applies_jargon_after_the_filters():
     s = Settings(jargon_custom_corrections=[C("type script", "TypeScript")])
     assert TranscriptionManager._post_filter("um I use type script", s) == "I use TypeScript"
     assert TranscriptionManager._post_filter("um I use type script", Settings()) == "I use type script"
+
+
+# ---- the same vectors through the compiled C++ host mirror (host/jargon.cpp via host/sb_transcribe_cli) ----
+import os
+
+import pytest
+
+
+@pytest.fixture(scope="module")
+def cli():
+    import subprocess
+    from spittle_b200 import build
+    if not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "spittle_b200", "libspittle_b200.so")):
+        pytest.skip("libspittle_b200.so not built")
+    exe = build.build_host()
+
+    def run(args, text=""):
+        r = subprocess.run([exe] + args, input=text.encode(), capture_output=True, timeout=30)
+        assert r.returncode == 0, r.stderr
+        return r.stdout.decode()
+    return run
+
+
+def test_cpp_apply_corrections(cli):
+    ts = ["type script", "TypeScript"]
+    for text, keep in (("Check @file.rs for type script code", "@file.rs"),
+                       ("Run `type script build` with type script", "`type script build`"),
+                       ("Visit https://type-script.org for type script docs", "https://type-script.org"),
+                       ("Open /usr/local/bin/app and type script", "/usr/local/bin/app"),
+                       ("Use --verbose and type script", "--verbose")):
+        r = cli(["--jargon-correct"] + ts, text)
+        assert keep in r and "TypeScript" in r and r == j.apply_corrections(text, TS), (text, r)
+    assert cli(["--jargon-correct"] + ts, "This script is good") == "This script is good"
+    assert cli(["--jargon-correct"] + ts, "I use Type Script and TYPE SCRIPT") == "I use TypeScript and TypeScript"
+    assert cli(["--jargon-correct"] + ts + ["next js", "Next.js"], "I use type script with next js") == "I use TypeScript with Next.js"
+    assert cli(["--jargon-correct"] + ts, "") == ""
+    # longest phrase first (jargon.rs:887-894): "E C two" must win over "E C"
+    assert cli(["--jargon-correct", "E C", "EC", "E C two", "EC2"], "launch an E C two box on E C") == "launch an EC2 box on EC"
+    assert j.apply_corrections("launch an E C two box on E C", j.compute_active_dictionary(
+        settings([], [], [("E C", "EC"), ("E C two", "EC2")]), {}).corrections) == "launch an EC2 box on EC"
+
+
+def test_cpp_build_initial_prompt(cli):
+    assert cli(["--jargon-prompt"]) == ""
+    assert cli(["--jargon-prompt", "MyCustomTerm", "TypeScript", "typescript"]) == "Technical dictation. Common terms: MyCustomTerm, typescript."
+    assert j.build_initial_prompt(j.compute_active_dictionary(settings([], ["MyCustomTerm", "TypeScript", "typescript"], []), {})) == \
+        "Technical dictation. Common terms: MyCustomTerm, typescript."
+    terms = ["VeryLongTermNumber%d" % i for i in range(200)]
+    p = cli(["--jargon-prompt"] + terms)
+    assert p == j.build_initial_prompt(j.ActiveDictionary(terms, [])) and 900 < len(p) <= 1000
