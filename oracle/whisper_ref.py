@@ -74,6 +74,13 @@ class DecodeConfig:
     max_initial_ts: float = 1.0
     single_segment: bool = False
     n_max_override: Optional[int] = None   # benches/tests may cap decode length
+    # Text conditioning [MEM, uncertain -- oracle/ASSUMPTIONS.md]: whisper.cpp keeps `prompt_past` inside one whisper_full
+    # call: the tokens of `initial_prompt` first, then after every window the window's kept tokens; a window's prompt is
+    # [prev] + the last min(n_max_text_ctx, n_text_ctx/2) tokens of it + [sot, lang, task].  The ENGINE does not do this yet,
+    # so both switches default to the engine's behaviour (no prefix); they exist so that the checker is ready.
+    initial_prompt_tokens: Optional[List[int]] = None
+    carry_context: bool = False
+    n_max_text_ctx: int = 16384
 
 
 @dataclass
@@ -279,11 +286,16 @@ class WhisperOracle:
 
     # -- one 30 s window ---------------------------------------------------------------
     def decode_window(self, enc: np.ndarray, seek: int, seek_end: int, cfg: DecodeConfig,
-                      trace: bool = False, forced: Optional[List[int]] = None) -> WindowResult:
+                      trace: bool = False, forced: Optional[List[int]] = None,
+                      prompt_past: Optional[List[int]] = None) -> WindowResult:
         hp, sp = self.hp, self.sp
         kv_cross = self.cross_kv(enc)
         kv_self = self.new_kv()
-        prompt = [sp.sot]
+        prompt = []
+        if prompt_past and cfg.n_max_text_ctx > 0:       # temperature is 0 here (< 0.5)
+            n_take = min(cfg.n_max_text_ctx, hp.n_text_ctx // 2, len(prompt_past))
+            prompt = [sp.prev] + list(prompt_past[len(prompt_past) - n_take:])
+        prompt.append(sp.sot)
         if hp.n_vocab >= 51865:
             prompt.append(sp.lang_first + cfg.language_id)
             prompt.append(sp.translate if cfg.translate else sp.transcribe)
@@ -369,6 +381,7 @@ class WhisperOracle:
         windows: List[WindowResult] = []
         kept: List[int] = []
         text = b""
+        prompt_past: List[int] = list(cfg.initial_prompt_tokens or [])
         if seek_end < seek + 100:
             return b"", kept, windows
         while len(windows) < max_windows:
@@ -379,9 +392,14 @@ class WhisperOracle:
                 lang, _ = self.detect_language(enc) if self.hp.n_vocab >= 51865 else (0, None)
                 cfg = dataclasses.replace(cfg, language_id=lang)
                 self.last_detected_language = lang
-            w = self.decode_window(enc, seek, seek_end, cfg)
+            if seek > 0 and seek + 500 >= seek_end:      # a very short tail: whisper.cpp drops the text context
+                prompt_past = []
+            w = self.decode_window(enc, seek, seek_end, cfg, prompt_past=prompt_past)
             windows.append(w)
             toks = w.tokens[: w.result_len]
+            if cfg.carry_context:                        # prompt_past = the part of it that was used + this window's kept tokens
+                n_take = min(cfg.n_max_text_ctx, self.hp.n_text_ctx // 2, len(prompt_past)) if cfg.n_max_text_ctx > 0 else 0
+                prompt_past = list(prompt_past[len(prompt_past) - n_take:]) + list(toks)
             kept.extend(toks)
             for t in toks:
                 if t < self.sp.eot:

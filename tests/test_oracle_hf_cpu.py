@@ -119,3 +119,28 @@ def test_decoder_logits_match_hf_teacher_forced_and_cached(pair):
     scale = np.abs(ref).max()
     assert np.abs(mine - ref).max() <= 3e-4 * max(1.0, scale), np.abs(mine - ref).max()
     assert (mine.argmax(-1) == ref.argmax(-1)).all()
+
+
+def test_prompt_prefix_conditioning_matches_hf_and_changes_the_decode(pair):
+    """[prev] + context tokens in front of [sot, lang, task] (whisper.cpp's prompt_past / initial_prompt): the oracle's
+    KV-cached steps over the longer prompt equal HF's one-shot decoder, and the prefix changes the greedy tokens."""
+    from oracle.whisper_ref import DecodeConfig
+    model, hf, win = pair
+    sp = model.special
+    orc = WhisperOracle(model, act_f16=False, gelu="erf")
+    enc = orc.encode(win)
+    past = [int(t) for t in np.random.default_rng(9).integers(0, sp.eot, size=20)]
+    toks = [sp.prev] + past + [sp.sot, sp.lang_first, sp.transcribe]
+    kv_self, kv_cross = orc.new_kv(), orc.cross_kv(enc)
+    mine = np.stack([orc.decode_step(t, i, kv_self, kv_cross) for i, t in enumerate(toks)])
+    with torch.no_grad():
+        ref = hf(encoder_outputs=(torch.from_numpy(enc)[None],), decoder_input_ids=torch.tensor([toks])).logits[0].numpy()
+    assert np.abs(mine - ref).max() <= 3e-4 * max(1.0, np.abs(ref).max())
+    cfg = DecodeConfig(n_max_override=10)
+    plain = orc.decode_window(enc, 0, 3000, cfg)
+    cond = orc.decode_window(enc, 0, 3000, cfg, prompt_past=past)
+    assert len(cond.tokens) > 0 and plain.tokens != cond.tokens
+    # n_take: at most n_text_ctx / 2 context tokens are used
+    long_past = list(range(300))
+    w = orc.decode_window(enc, 0, 3000, DecodeConfig(n_max_override=1), prompt_past=long_past)
+    assert len(w.tokens) == 1
