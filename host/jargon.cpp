@@ -70,6 +70,35 @@ std::string build_initial_prompt(const ActiveDictionary& d) {
     return prefix + body + suffix;
 }
 
+// Rust regex `Replacer for &str` (re.replace_all(&masked, correction.to.as_str()), jargon.rs:697): `$$` is a literal `$`;
+// `$name` / `${name}` / `$N` expand capture groups -- the correction pattern has none, so `$0` is the whole match and every
+// other reference is empty; a `$` followed by anything else stays.
+static std::string expand_replacement(const std::string& to, const std::string& matched) {
+    std::string out;
+    const size_t n = to.size();
+    for (size_t i = 0; i < n;) {
+        if (to[i] != '$') { out += to[i++]; continue; }
+        if (i + 1 < n && to[i + 1] == '$') { out += '$'; i += 2; continue; }
+        size_t j = i + 1;
+        std::string name;
+        if (j < n && to[j] == '{') {
+            const size_t k = to.find('}', j);
+            if (k == std::string::npos) { out += '$'; ++i; continue; }
+            name = to.substr(j + 1, k - j - 1); j = k + 1;
+        } else {
+            size_t k = j;
+            while (k < n && (std::isalnum((unsigned char)to[k]) || to[k] == '_')) ++k;
+            if (k == j) { out += '$'; ++i; continue; }
+            name = to.substr(j, k - j); j = k;
+        }
+        bool digits = !name.empty();
+        for (char ch : name) digits = digits && std::isdigit((unsigned char)ch);
+        if (digits && std::stol(name.substr(0, 9)) == 0 && name.find_first_not_of('0') == std::string::npos) out += matched;
+        i = j;
+    }
+    return out;
+}
+
 std::string apply_corrections(const std::string& text, const std::vector<JargonCorrection>& corrections) {
     if (corrections.empty() || text.empty()) return text;
     // protected spans: @refs, `code`, URLs, file paths, CLI flags (jargon.rs:637-644)
@@ -92,7 +121,7 @@ std::string apply_corrections(const std::string& text, const std::vector<JargonC
             size_t last = 0;
             for (auto it = begin; it != std::sregex_iterator(); ++it) {
                 out.append(masked, last, (size_t)it->position() - last);
-                out += c.to;                                       // literal replacement
+                out += expand_replacement(c.to, it->str());        // Rust's `$` expansion of the replacement
                 last = (size_t)it->position() + (size_t)it->length();
             }
             out.append(masked, last, std::string::npos);

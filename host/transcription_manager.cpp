@@ -1,5 +1,6 @@
 // C++ mirror of the reference TranscriptionManager (see transcription_manager.hpp).
 #include "transcription_manager.hpp"
+#include <algorithm>
 #include "text_filters.hpp"
 
 #include <cstring>
@@ -80,6 +81,7 @@ Result<Unit> TranscriptionManager::load_model(const std::string& model_id) {
     cfg.max_batch = s.max_batch;
     cfg.dtype = s.dtype;
     cfg.use_cuda_graph = 1;
+    if (!s.devices.empty()) { cfg.devices = s.devices.data(); cfg.n_devices = (int)s.devices.size(); }
     sb_engine* e = nullptr;
     if (sb_engine_create(&cfg, &e) != SB_OK)
         return Result<Unit>::Err(std::string("Failed to load whisper model ") + model_id + ": " + sb_last_error());
@@ -123,13 +125,38 @@ std::string TranscriptionManager::effective_language(const Settings& s) const {
     return s.selected_language;
 }
 
+// transcription.rs:65-87: the enabled profiles, replaced by (or blended with) the domain selector's pick
+static std::vector<std::string> effective_profile_ids(const Settings& s, const std::string& context_text) {
+    std::vector<std::string> ids = s.jargon_enabled_profiles;
+    if (s.profile_selector) {
+        if (auto picked = s.profile_selector(context_text)) {
+            if (s.domain_selector_blend_manual_profiles) {
+                for (const auto& p : *picked)
+                    if (std::find(ids.begin(), ids.end(), p) == ids.end()) ids.push_back(p);
+            } else {
+                ids = *picked;
+            }
+        }
+    }
+    return ids;
+}
+
+// transcription.rs:461-492: the jargon dictionary's terms as Whisper's initial_prompt ("" = none)
+static std::string jargon_initial_prompt(const Settings& s) {
+    if (s.jargon_enabled_profiles.empty() && s.jargon_custom_terms.empty() && s.jargon_packs.empty()) return "";
+    JargonSettings js{effective_profile_ids(s, ""), s.jargon_custom_terms, s.jargon_custom_corrections};
+    const ActiveDictionary d = compute_active_dictionary(js, s.jargon_profiles);
+    if (d.terms.empty()) return "";
+    return build_initial_prompt(d);
+}
+
 // transcription.rs:537-580: custom-word correction (only when configured), the filler / stutter / hallucination filter,
 // then the jargon corrections (only when profiles or custom corrections are configured)
 static std::string post_filter(std::string text, const Settings& s) {
     if (!s.custom_words.empty()) text = apply_custom_words(text, s.custom_words, s.word_correction_threshold);
     text = filter_transcription_output(text);
-    if (!s.jargon_enabled_profiles.empty() || !s.jargon_custom_corrections.empty()) {
-        JargonSettings js{s.jargon_enabled_profiles, s.jargon_custom_terms, s.jargon_custom_corrections};
+    if (!s.jargon_enabled_profiles.empty() || !s.jargon_custom_corrections.empty() || !s.jargon_packs.empty()) {
+        JargonSettings js{effective_profile_ids(s, text), s.jargon_custom_terms, s.jargon_custom_corrections};
         const ActiveDictionary d = compute_active_dictionary(js, s.jargon_profiles);
         if (!d.corrections.empty()) text = apply_corrections(text, d.corrections);
     }
@@ -156,6 +183,8 @@ Result<std::string> TranscriptionManager::transcribe(std::vector<float> audio) {
         const std::string lang = effective_language(s);
         p.language = lang == "auto" ? nullptr : lang.c_str();
         p.translate = s.translate_to_english ? 1 : 0;
+        const std::string prompt = jargon_initial_prompt(s);
+        p.initial_prompt = prompt.empty() ? nullptr : prompt.c_str();
         sb_result r;
         if (sb_transcribe(engine_, audio.data(), audio.size(), &p, &r) != SB_OK)
             return Result<std::string>::Err(std::string("Whisper transcription failed: ") + sb_last_error());
@@ -188,6 +217,8 @@ std::vector<Result<std::string>> TranscriptionManager::transcribe_batch(const st
     const std::string lang = effective_language(s);
     p.language = lang == "auto" ? nullptr : lang.c_str();
     p.translate = s.translate_to_english ? 1 : 0;
+    const std::string prompt = jargon_initial_prompt(s);
+    p.initial_prompt = prompt.empty() ? nullptr : prompt.c_str();
     std::vector<sb_result> res(clips.size());
     if (sb_transcribe_batch(engine_, ptrs.data(), ns.data(), clips.size(), &p, res.data()) != SB_OK) {
         const std::string e = std::string("Whisper transcription failed: ") + sb_last_error();

@@ -60,7 +60,14 @@ struct Settings {
     std::vector<std::string> jargon_enabled_profiles, jargon_custom_terms;
     std::vector<JargonCorrection> jargon_custom_corrections;
     std::map<std::string, JargonProfile> jargon_profiles;
+    // ids of the user's jargon packs (settings.jargon_packs; build_profiles_map, transcription.rs:50-63, merges their
+    // profiles into the table above): only their presence matters for the gates at :462-464 / :553-555
+    std::vector<std::string> jargon_packs;
+    // DomainSelectorManager stand-in (transcription.rs:65-87): (context text) -> profile ids, or nullopt
+    std::function<std::optional<std::vector<std::string>>(const std::string&)> profile_selector;
+    bool domain_selector_blend_manual_profiles = false;
     int device = 0;
+    std::vector<int> devices;              // non-empty: one model replica per listed CUDA device (transcribe_batch)
     int max_batch = 64;
     int dtype = SB_DTYPE_F16;
 };

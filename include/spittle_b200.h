@@ -203,17 +203,19 @@ SB_API int sb_skinny_gemm_dev(int dtype, const void* X, int64_t ldx, const void*
  *       initial_prompt, ..}))      managers/transcription.rs:494-503  -> sb_transcribe
  * An engine may be created / used / destroyed from different threads; calls on one engine
  * must be serialised by the caller (the reference holds its engine mutex across the whole
- * inference, transcription.rs:437).  One engine drives one CUDA device; multi-GPU hosts
- * create one engine per device (clips are independent, no collective).
+ * inference, transcription.rs:437).  An engine drives one CUDA device, or several when
+ * sb_config.devices is set (one replica per device; clips are independent, no collective).
  * ---------------------------------------------------------------------------------- */
 typedef struct sb_engine sb_engine;
 
 typedef struct sb_config {
-    const char* model_path;   /* GGML legacy ggml-*.bin (f32 / f16 tensors) */
+    const char* model_path;   /* GGML legacy ggml-*.bin (f32 / f16 / q4_0 / q4_1 / q5_0 / q5_1 / q8_0 / q5_K tensors) */
     int device;               /* CUDA device ordinal */
-    int max_batch;            /* windows decoded together (0 -> 64) */
+    int max_batch;            /* decode slots: windows decoded together (0 -> 64) */
     int dtype;                /* sb_dtype: operand type of the tensor-core GEMMs */
     int use_cuda_graph;       /* 1: capture the decoder step into a CUDA graph (default), 0: plain launches */
+    const int* devices;       /* NULL, or n_devices distinct CUDA ordinals: one replica of the model per device; then     */
+    int n_devices;            /* sb_transcribe_batch sends clip i to devices[i % n_devices], one worker thread per device  */
 } sb_config;
 
 typedef struct sb_model_info {
@@ -223,18 +225,24 @@ typedef struct sb_model_info {
 } sb_model_info;
 
 /* Decode policy.  sb_params_default() gives the configuration pinned for parity in
- * language "en", transcribe, timestamps on, suppress_blank, no_context,
- * max_initial_ts 1.0, greedy (temperature 0, no fallback), n_max = n_text_ctx/2 - 4. */
+ * language "en", transcribe, timestamps on, suppress_blank, no_context (nothing is carried
+ * from one CALL to the next; inside a call whisper_full conditions every window on the previous windows' text,
+ * n_max_text_ctx 16384), max_initial_ts 1.0, greedy (temperature 0, no fallback), n_max = n_text_ctx/2 - 4. */
 typedef struct sb_params {
-    const char* language;        /* "en", ... ; NULL = reference's "auto" (NOT implemented yet: SB_ERR_UNSUPPORTED) */
-    int translate;               /* WhisperInferenceParams.translate */
-    const char* initial_prompt;  /* must be NULL for now (needs the BPE encoder; SB_ERR_UNSUPPORTED otherwise) */
+    const char* language;        /* "en", "de", ...; NULL, "" or "auto" = the reference's default "auto": the language is
+                                    detected on the clip's first window like whisper_full (whisper_lang_auto_detect) */
+    int translate;               /* WhisperInferenceParams.translate: task token <|translate|> instead of <|transcribe|> */
+    const char* initial_prompt;  /* UTF-8 or NULL.  WhisperInferenceParams.initial_prompt (the reference sets it from the jargon
+                                    dictionary, transcription.rs:461-499): tokenised with sb_tokenize and prepended as
+                                    [prev] + tokens to the decoder prompt of every window, like whisper.cpp's prompt_past */
     int no_timestamps;
     int suppress_blank;
     int single_segment;
     float max_initial_ts;
     int n_max_tokens;            /* 0 -> n_text_ctx/2 - 4 (whisper.cpp); tests may cap it */
     int max_windows;             /* 0 -> unlimited; safety cap on the seek loop */
+    int n_max_text_ctx;          /* whisper_full_params.n_max_text_ctx (default 16384): tokens of text context carried from one
+                                    window of a clip to the next ([prev] + last min(this, n_text_ctx/2) tokens); <= 0 disables */
 } sb_params;
 
 typedef struct sb_window_info {
@@ -244,14 +252,28 @@ typedef struct sb_window_info {
     int32_t seek_delta;
     int32_t failed;
     int32_t token_offset;    /* offset of this window's sampled tokens in sb_result.sampled */
+    int32_t n_prompt;        /* decoder prompt length of this window: [prev + text context] + [sot, lang, task, ...] */
 } sb_window_info;
+
+/* One segment of the transcript (transcribe-rs TranscriptionResult.segments = whisper_full_get_segment_{t0,t1,text}):
+ * the text between two timestamp tokens. */
+typedef struct sb_segment {
+    int64_t t0, t1;          /* start / end in 10 ms units from the start of the clip */
+    const char* text;        /* UTF-8, NUL-terminated, untrimmed; points into sb_result.segment_text */
+    size_t text_len;
+    int32_t token_offset;    /* this segment's tokens inside sb_result.tokens */
+    int32_t n_tokens;
+} sb_segment;
 
 typedef struct sb_result {
     char* text;  size_t text_len;          /* UTF-8 bytes, trimmed like transcribe-rs; NUL-terminated */
     int32_t* tokens; size_t n_tokens;      /* kept tokens (incl. timestamps / EOT), all windows */
     int32_t* sampled; size_t n_sampled;    /* every sampled token, all windows */
     float* margins;                        /* [n_sampled] top1-top2 of the filtered logits */
+    int32_t* tids;                         /* [n_sampled] whisper_token_data.tid: most probable timestamp token of each step */
     sb_window_info* windows; size_t n_windows;
+    sb_segment* segments; size_t n_segments;
+    char* segment_text;                    /* storage of the segment texts */
     float ms_mel, ms_encode, ms_decode;    /* device time of the batch this clip was part of */
     int status;                            /* per-clip sb_status (batch API) */
     int lang_id;                           /* whisper language id used for the prompt (detected when params.language is NULL /
@@ -284,6 +306,8 @@ SB_API int sb_engine_stats(sb_engine* e, sb_stats* out, int reset);
 SB_API int sb_engine_create(const sb_config* cfg, sb_engine** out);
 SB_API int sb_engine_destroy(sb_engine* e);
 SB_API int sb_engine_info(const sb_engine* e, sb_model_info* info);
+/* number of devices (model replicas) this engine drives */
+SB_API int sb_engine_device_count(const sb_engine* e);
 /* id -> token bytes (whisper_token_to_str); returns length, copies at most cap bytes */
 SB_API int sb_token_text(const sb_engine* e, int32_t id, char* buf, int cap);
 /* whisper.cpp's tokeniser (whisper_tokenize, what turns WhisperInferenceParams::initial_prompt into prompt tokens,
@@ -296,7 +320,10 @@ SB_API int sb_tokenize(const sb_engine* e, const char* text, int32_t* tokens, in
  * (the reference pads such clips upstream, managers/audio.rs:466-475). */
 SB_API int sb_transcribe(sb_engine* e, const float* pcm16k, size_t n_samples, const sb_params* p,
                          sb_result* out);
-/* Independent clips batched on this engine's GPU.  out: array of `count` results. */
+/* Independent clips batched on this engine's GPU(s).  out: array of `count` results.  All clips of the call share the
+ * engine's decode slots: every clip's seek loop runs window by window, a finished window's slot is refilled with the
+ * next ready window of any clip.  With sb_config.devices the clips are split over the devices (no collective: clips do
+ * not interact) and decoded concurrently by one worker thread per device. */
 SB_API int sb_transcribe_batch(sb_engine* e, const float* const* pcm16k, const size_t* n_samples,
                                size_t count, const sb_params* p, sb_result* out);
 SB_API void sb_result_free(sb_result* r);
@@ -314,6 +341,12 @@ SB_API int sb_encode(sb_engine* e, const float* mel_windows, int n_windows, floa
 SB_API int sb_decode_trace(sb_engine* e, const float* mel_windows, int n_windows, const int32_t* seek_end,
                            const sb_params* p, const int32_t* forced, int n_steps, float* logits_out,
                            int32_t* tokens_out, float* margins_out);
+
+/* ABI self-description: one row per field of the structs above (struct name, field name, sizeof(struct),
+ * offsetof(struct, field)).  Writes at most `cap` rows, returns the number of rows.  A binding checks its own layout
+ * against this table (tests/test_abi.py does it for ctypes; rust/spittle-b200-sys asserts the same numbers). */
+typedef struct sb_abi_field { const char* struct_name; const char* field; int struct_size; int offset; } sb_abi_field;
+SB_API int sb_abi_layout(sb_abi_field* out, int cap);
 
 #ifdef __cplusplus
 }

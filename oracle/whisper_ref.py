@@ -74,12 +74,11 @@ class DecodeConfig:
     max_initial_ts: float = 1.0
     single_segment: bool = False
     n_max_override: Optional[int] = None   # benches/tests may cap decode length
-    # Text conditioning [MEM, uncertain -- oracle/ASSUMPTIONS.md]: whisper.cpp keeps `prompt_past` inside one whisper_full
-    # call: the tokens of `initial_prompt` first, then after every window the window's kept tokens; a window's prompt is
-    # [prev] + the last min(n_max_text_ctx, n_text_ctx/2) tokens of it + [sot, lang, task].  The ENGINE does not do this yet,
-    # so both switches default to the engine's behaviour (no prefix); they exist so that the checker is ready.
+    # Text conditioning [MEM -- oracle/ASSUMPTIONS.md]: whisper.cpp keeps `prompt_past` inside one whisper_full call: the
+    # tokens of `initial_prompt` first, then after every window the context that window used + its kept tokens; a window's
+    # prompt is [prev] + the last min(n_max_text_ctx, n_text_ctx/2) tokens of it + [sot, lang, task].  `no_context` (true in
+    # whisper-rs' defaults) only clears what an EARLIER call left behind.  n_max_text_ctx = 0 switches the prefix off.
     initial_prompt_tokens: Optional[List[int]] = None
-    carry_context: bool = False
     n_max_text_ctx: int = 16384
 
 
@@ -397,9 +396,9 @@ class WhisperOracle:
             w = self.decode_window(enc, seek, seek_end, cfg, prompt_past=prompt_past)
             windows.append(w)
             toks = w.tokens[: w.result_len]
-            if cfg.carry_context:                        # prompt_past = the part of it that was used + this window's kept tokens
-                n_take = min(cfg.n_max_text_ctx, self.hp.n_text_ctx // 2, len(prompt_past)) if cfg.n_max_text_ctx > 0 else 0
-                prompt_past = list(prompt_past[len(prompt_past) - n_take:]) + list(toks)
+            # prompt_past = the part of it this window used + this window's kept tokens
+            n_take = min(cfg.n_max_text_ctx, self.hp.n_text_ctx // 2, len(prompt_past)) if cfg.n_max_text_ctx > 0 else 0
+            prompt_past = list(prompt_past[len(prompt_past) - n_take:]) + list(toks)
             kept.extend(toks)
             for t in toks:
                 if t < self.sp.eot:

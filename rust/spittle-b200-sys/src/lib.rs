@@ -1,7 +1,13 @@
 //! Raw FFI bindings of include/spittle_b200.h (engine subset used by the drop-in manager).
 //! NOT COMPILED IN THIS IMAGE: there is no Rust toolchain; kept mechanical so a maintainer can
 //! `cargo build` it next to the prebuilt libspittle_b200.so.
+//!
+//! Layout guard: the `const _: () = assert!(...)` lines below pin sizeof / offsetof of every struct to the numbers the
+//! library itself reports through `sb_abi_layout()`; the same table is checked in as tests/golden/abi_layout.json and
+//! tests/test_abi.py compares it with the built library, with the ctypes mirror and with THIS FILE (it parses the
+//! asserts), so a field added to the C header without updating the bindings fails the CPU test suite.
 #![allow(non_camel_case_types)]
+use core::mem::{offset_of, size_of};
 use libc::{c_char, c_float, c_int, size_t};
 
 #[repr(C)]
@@ -14,24 +20,35 @@ pub struct sb_config {
     pub max_batch: c_int,
     pub dtype: c_int,          // 0 bf16, 1 f16
     pub use_cuda_graph: c_int,
+    pub devices: *const c_int, // NULL or n_devices CUDA ordinals: one replica per device
+    pub n_devices: c_int,
 }
 
 #[repr(C)]
 pub struct sb_params {
     pub language: *const c_char,        // NULL = "auto"
     pub translate: c_int,
-    pub initial_prompt: *const c_char,
+    pub initial_prompt: *const c_char,  // NULL or UTF-8 (jargon prompt)
     pub no_timestamps: c_int,
     pub suppress_blank: c_int,
     pub single_segment: c_int,
     pub max_initial_ts: c_float,
     pub n_max_tokens: c_int,
     pub max_windows: c_int,
+    pub n_max_text_ctx: c_int,
 }
 
 #[repr(C)]
 pub struct sb_window_info {
     pub seek: i32, pub n_tokens: i32, pub result_len: i32, pub seek_delta: i32, pub failed: i32, pub token_offset: i32,
+    pub n_prompt: i32,
+}
+
+#[repr(C)]
+pub struct sb_segment {
+    pub t0: i64, pub t1: i64,           // 10 ms units
+    pub text: *const c_char, pub text_len: size_t,
+    pub token_offset: i32, pub n_tokens: i32,
 }
 
 #[repr(C)]
@@ -40,16 +57,49 @@ pub struct sb_result {
     pub tokens: *mut i32, pub n_tokens: size_t,
     pub sampled: *mut i32, pub n_sampled: size_t,
     pub margins: *mut c_float,
+    pub tids: *mut i32,
     pub windows: *mut sb_window_info, pub n_windows: size_t,
+    pub segments: *mut sb_segment, pub n_segments: size_t,
+    pub segment_text: *mut c_char,
     pub ms_mel: c_float, pub ms_encode: c_float, pub ms_decode: c_float,
     pub status: c_int,
+    pub lang_id: c_int,
 }
+
+#[repr(C)]
+pub struct sb_abi_field { pub struct_name: *const c_char, pub field: *const c_char, pub struct_size: c_int, pub offset: c_int }
+
+// ---- layout guard (numbers = sb_abi_layout() of the library; tests/golden/abi_layout.json) ----
+const _: () = assert!(size_of::<sb_config>() == 40);
+const _: () = assert!(offset_of!(sb_config, devices) == 24);
+const _: () = assert!(offset_of!(sb_config, n_devices) == 32);
+const _: () = assert!(size_of::<sb_params>() == 56);
+const _: () = assert!(offset_of!(sb_params, initial_prompt) == 16);
+const _: () = assert!(offset_of!(sb_params, max_initial_ts) == 36);
+const _: () = assert!(offset_of!(sb_params, n_max_text_ctx) == 48);
+const _: () = assert!(size_of::<sb_window_info>() == 28);
+const _: () = assert!(offset_of!(sb_window_info, n_prompt) == 24);
+const _: () = assert!(size_of::<sb_segment>() == 40);
+const _: () = assert!(offset_of!(sb_segment, text) == 16);
+const _: () = assert!(offset_of!(sb_segment, n_tokens) == 36);
+const _: () = assert!(size_of::<sb_result>() == 128);
+const _: () = assert!(offset_of!(sb_result, margins) == 48);
+const _: () = assert!(offset_of!(sb_result, tids) == 56);
+const _: () = assert!(offset_of!(sb_result, windows) == 64);
+const _: () = assert!(offset_of!(sb_result, segments) == 80);
+const _: () = assert!(offset_of!(sb_result, segment_text) == 96);
+const _: () = assert!(offset_of!(sb_result, ms_mel) == 104);
+const _: () = assert!(offset_of!(sb_result, status) == 116);
+const _: () = assert!(offset_of!(sb_result, lang_id) == 120);
 
 extern "C" {
     pub fn sb_last_error() -> *const c_char;
+    pub fn sb_abi_layout(out: *mut sb_abi_field, cap: c_int) -> c_int;
     pub fn sb_params_default(p: *mut sb_params);
     pub fn sb_engine_create(cfg: *const sb_config, out: *mut *mut sb_engine) -> c_int;
     pub fn sb_engine_destroy(e: *mut sb_engine) -> c_int;
+    pub fn sb_engine_device_count(e: *const sb_engine) -> c_int;
+    pub fn sb_tokenize(e: *const sb_engine, text: *const c_char, tokens: *mut i32, cap: c_int) -> c_int;
     pub fn sb_transcribe(e: *mut sb_engine, pcm16k: *const c_float, n_samples: size_t, p: *const sb_params,
                          out: *mut sb_result) -> c_int;
     pub fn sb_transcribe_batch(e: *mut sb_engine, pcm16k: *const *const c_float, n_samples: *const size_t,

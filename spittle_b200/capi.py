@@ -125,7 +125,7 @@ def gemm_tn_dev(dtype: int, a_ptr: int, lda: int, w_ptr: int, ldw: int, M: int, 
 # ---------------------------------------------------------------------------------------
 class SbConfig(C.Structure):
     _fields_ = [("model_path", C.c_char_p), ("device", C.c_int), ("max_batch", C.c_int), ("dtype", C.c_int),
-                ("use_cuda_graph", C.c_int)]
+                ("use_cuda_graph", C.c_int), ("devices", C.POINTER(C.c_int)), ("n_devices", C.c_int)]
 
 
 class SbModelInfo(C.Structure):
@@ -137,7 +137,8 @@ class SbModelInfo(C.Structure):
 class SbParams(C.Structure):
     _fields_ = [("language", C.c_char_p), ("translate", C.c_int), ("initial_prompt", C.c_char_p),
                 ("no_timestamps", C.c_int), ("suppress_blank", C.c_int), ("single_segment", C.c_int),
-                ("max_initial_ts", C.c_float), ("n_max_tokens", C.c_int), ("max_windows", C.c_int)]
+                ("max_initial_ts", C.c_float), ("n_max_tokens", C.c_int), ("max_windows", C.c_int),
+                ("n_max_text_ctx", C.c_int)]
 
 
 class SbStats(C.Structure):
@@ -149,21 +150,50 @@ class SbStats(C.Structure):
 
 
 class SbWindowInfo(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("seek", "n_tokens", "result_len", "seek_delta", "failed", "token_offset")]
+    _fields_ = [(n, C.c_int32) for n in ("seek", "n_tokens", "result_len", "seek_delta", "failed", "token_offset",
+                                         "n_prompt")]
+
+
+class SbSegment(C.Structure):
+    _fields_ = [("t0", C.c_int64), ("t1", C.c_int64), ("text", C.POINTER(C.c_char)), ("text_len", C.c_size_t),
+                ("token_offset", C.c_int32), ("n_tokens", C.c_int32)]
 
 
 class SbResult(C.Structure):
     _fields_ = [("text", C.POINTER(C.c_char)), ("text_len", C.c_size_t),
                 ("tokens", C.POINTER(C.c_int32)), ("n_tokens", C.c_size_t),
                 ("sampled", C.POINTER(C.c_int32)), ("n_sampled", C.c_size_t),
-                ("margins", C.POINTER(C.c_float)),
+                ("margins", C.POINTER(C.c_float)), ("tids", C.POINTER(C.c_int32)),
                 ("windows", C.POINTER(SbWindowInfo)), ("n_windows", C.c_size_t),
+                ("segments", C.POINTER(SbSegment)), ("n_segments", C.c_size_t), ("segment_text", C.POINTER(C.c_char)),
                 ("ms_mel", C.c_float), ("ms_encode", C.c_float), ("ms_decode", C.c_float),
                 ("status", C.c_int), ("lang_id", C.c_int)]
 
 
+class SbAbiField(C.Structure):
+    _fields_ = [("struct_name", C.c_char_p), ("field", C.c_char_p), ("struct_size", C.c_int), ("offset", C.c_int)]
+
+
+def abi_layout():
+    """The library's own sizeof / offsetof table: [(struct, field, sizeof, offset)] (sb_abi_layout)."""
+    l = lib()
+    n = l.sb_abi_layout(None, 0)
+    rows = (SbAbiField * n)()
+    l.sb_abi_layout(rows, n)
+    return [(r.struct_name.decode(), r.field.decode(), r.struct_size, r.offset) for r in rows]
+
+
+ABI_STRUCTS = {}     # name -> ctypes mirror; filled below (checked against abi_layout() by tests/test_abi.py)
+
+
+ABI_STRUCTS.update(sb_config=SbConfig, sb_params=SbParams, sb_window_info=SbWindowInfo, sb_segment=SbSegment,
+                   sb_result=SbResult, sb_model_info=SbModelInfo, sb_stats=SbStats)
+
+
 def _declare_engine(l: C.CDLL) -> None:
     vp, i32 = C.c_void_p, C.c_int
+    l.sb_abi_layout.argtypes = [C.POINTER(SbAbiField), i32]
+    l.sb_engine_device_count.argtypes = [vp]
     l.sb_params_default.argtypes = [C.POINTER(SbParams)]
     l.sb_params_default.restype = None
     l.sb_engine_create.argtypes = [C.POINTER(SbConfig), C.POINTER(vp)]
@@ -196,9 +226,12 @@ class ClipResult:
         self.tokens = [r.tokens[i] for i in range(r.n_tokens)]
         self.sampled = [r.sampled[i] for i in range(r.n_sampled)]
         self.margins = [r.margins[i] for i in range(r.n_sampled)]
+        self.tids = [r.tids[i] for i in range(r.n_sampled)]
         self.windows = [dict(seek=w.seek, n_tokens=w.n_tokens, result_len=w.result_len, seek_delta=w.seek_delta,
-                             failed=w.failed, token_offset=w.token_offset)
+                             failed=w.failed, token_offset=w.token_offset, n_prompt=w.n_prompt)
                         for w in (r.windows[i] for i in range(r.n_windows))]
+        self.segments = [dict(t0=g.t0, t1=g.t1, text=C.string_at(g.text, g.text_len), token_offset=g.token_offset,
+                              n_tokens=g.n_tokens) for g in (r.segments[i] for i in range(r.n_segments))]
         self.ms_mel, self.ms_encode, self.ms_decode = r.ms_mel, r.ms_encode, r.ms_decode
         self.status = r.status
         self.lang_id = r.lang_id
@@ -219,9 +252,12 @@ class Engine:
     """sb_engine: one loaded model on one CUDA device."""
 
     def __init__(self, model_path: str, device: int = 0, max_batch: int = 64, dtype: int = SB_DTYPE_BF16,
-                 use_cuda_graph: bool = True):
+                 use_cuda_graph: bool = True, devices=None):
+        """devices: list of CUDA ordinals -> one model replica per device, clips of a batch are split over them."""
         l = lib()
-        cfg = SbConfig(model_path.encode(), device, max_batch, dtype, int(use_cuda_graph))
+        devs = (C.c_int * len(devices))(*devices) if devices else None
+        cfg = SbConfig(model_path.encode(), device, max_batch, dtype, int(use_cuda_graph),
+                       C.cast(devs, C.POINTER(C.c_int)) if devs is not None else None, len(devices) if devices else 0)
         self._h = C.c_void_p()
         check(l.sb_engine_create(C.byref(cfg), C.byref(self._h)))
         self.info = SbModelInfo()

@@ -420,13 +420,19 @@ k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 // S_{j+2} cannot overwrite buffer j%2 before PV_j has read P_j, and the softmax warps always find S_{j+1}
 // complete when they finish tile j.  Pass 1 (row maxima) rings over the three 64-column buffers below Q.
 // ==========================================================================================
-static unsigned long long* g_attn_fallback_ctr = nullptr;       // one device counter for all instantiations
+static std::atomic<unsigned long long*> g_attn_fallback_ctr[64];       // one device counter per GPU for all instantiations
 static int attn_fallback_counter(unsigned long long** out) {
-    if (!g_attn_fallback_ctr) {
-        SB_CUDA_CHECK(cudaMalloc(&g_attn_fallback_ctr, 8));
-        SB_CUDA_CHECK(cudaMemset(g_attn_fallback_ctr, 0, 8));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::atomic<unsigned long long*>& slot = g_attn_fallback_ctr[dev & 63];
+    unsigned long long* p = slot.load(std::memory_order_acquire);
+    if (!p) {
+        SB_CUDA_CHECK(cudaMalloc(&p, 8));
+        SB_CUDA_CHECK(cudaMemset(p, 0, 8));
+        unsigned long long* expected = nullptr;
+        if (!slot.compare_exchange_strong(expected, p)) { cudaFree(p); p = expected; }
     }
-    *out = g_attn_fallback_ctr;
+    *out = p;
     return SB_OK;
 }
 __device__ unsigned long long g_attn_trace[4096 * 6];     // debug (SB_ATTN_TRACE=1): per-CTA phase timestamps
@@ -770,11 +776,7 @@ static int attn_enc_ts_launch(const T* qkv, T* out, int n_windows, int n_ctx, in
     const int is_f16 = std::is_same<T, __half>::value ? 1 : 0;
     int rc = make_tmap_2d(&tkv, qkv, is_f16, (int64_t)n_windows * n_ctx, 3 * (int64_t)d_model, 3 * (int64_t)d_model, 64);
     if (rc) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SB_CUDA_CHECK(cudaFuncSetAttribute(k_attn_enc_ts<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem));
-        attr_done = true;
-    }
+    SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(k_attn_enc_ts<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem)); });
     dim3 grid(ceil_div(n_ctx, kAtBM), n_head, n_windows);
     const float scale_log2e = (1.0f / 8.0f) * 1.4426950408889634f;
     static int trace = [] { const char* e = getenv("SB_ATTN_TRACE"); return e ? atoi(e) : 0; }();
@@ -796,11 +798,7 @@ static int attn_enc_tc_launch(const T* qkv, T* out, int n_windows, int n_ctx, in
     int rc = make_tmap_2d(&tq, qkv, is_f16, (int64_t)n_windows * n_ctx, 3 * (int64_t)d_model, 3 * (int64_t)d_model, 128);
     if (rc) return rc;
     if ((rc = make_tmap_2d(&tkv, qkv, is_f16, (int64_t)n_windows * n_ctx, 3 * (int64_t)d_model, 3 * (int64_t)d_model, BN))) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SB_CUDA_CHECK(cudaFuncSetAttribute(k_attn_enc_tc<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<BN>::kSmem));
-        attr_done = true;
-    }
+    SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(k_attn_enc_tc<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<BN>::kSmem)); });
     dim3 grid(ceil_div(n_ctx, kAtBM), n_head, n_windows);
     const float scale_log2e = (1.0f / 8.0f) * 1.4426950408889634f;
     static int mma_sleep = [] { const char* e = getenv("SB_ATTN_SLEEP"); return e ? atoi(e) : 64; }();
@@ -834,8 +832,11 @@ extern "C" __attribute__((visibility("default"))) int sb_debug_attn_trace(unsign
 extern "C" __attribute__((visibility("default"))) int sb_debug_attn_fallbacks(unsigned long long* out) {
     SB_CHECK_ARG(out, "null pointer");
     *out = 0;
-    if (!sb::g_attn_fallback_ctr) return SB_OK;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    unsigned long long* p = sb::g_attn_fallback_ctr[dev & 63].load();
+    if (!p) return SB_OK;
     SB_CUDA_CHECK(cudaDeviceSynchronize());
-    SB_CUDA_CHECK(cudaMemcpy(out, sb::g_attn_fallback_ctr, 8, cudaMemcpyDeviceToHost));
+    SB_CUDA_CHECK(cudaMemcpy(out, p, 8, cudaMemcpyDeviceToHost));
     return SB_OK;
 }

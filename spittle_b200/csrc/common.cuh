@@ -115,28 +115,30 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // Device-side launch trace (sb_engine_set_profile(e, 2)): thread 0 of every block stamps %globaltimer into the slot
-// of its launch (slot = decode position x launches-per-step + index of the launch inside the step; min over the
+// of its launch (slot = lane step x launches-per-step + index of the launch inside the step; min over the
 // blocks for the start, max for the end).  The launches keep their CUDA graph and their PDL overlap, so these are the
 // durations inside the real chain, which CUDA-event brackets around single launches cannot give.
 struct TraceSlot {
     unsigned long long* t0 = nullptr;   // [max_steps * per_step] first block start (ns)
     unsigned long long* t1 = nullptr;   // [max_steps * per_step] last block end (ns)
-    const int* pos = nullptr;           // device: decode position of this step
-    int idx = 0, per_step = 0;
+    const int* tick = nullptr;          // device: step counter of the lane
+    int idx = 0, per_step = 0, max_steps = 0;
 };
 #ifdef __CUDACC__
 __device__ __forceinline__ void trace_begin(const TraceSlot& ts) {
     if (ts.t0 && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        atomicMin(ts.t0 + (size_t)__ldcg(ts.pos) * ts.per_step + ts.idx, t);
+        const int step = __ldcg(ts.tick);
+        if (step < ts.max_steps) atomicMin(ts.t0 + (size_t)step * ts.per_step + ts.idx, t);
     }
 }
 __device__ __forceinline__ void trace_end(const TraceSlot& ts) {
     if (ts.t1 && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        atomicMax(ts.t1 + (size_t)__ldcg(ts.pos) * ts.per_step + ts.idx, t);
+        const int step = __ldcg(ts.tick);
+        if (step < ts.max_steps) atomicMax(ts.t1 + (size_t)step * ts.per_step + ts.idx, t);
     }
 }
 #endif
@@ -154,6 +156,20 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
+
+// cudaFuncSetAttribute is PER DEVICE and one process may drive several GPUs (sb_config.devices): `SB_ONCE_PER_DEVICE(stmt)`
+// runs `stmt` the first time this call site is reached with each device current (set twice under a race: harmless).
+#define SB_ONCE_PER_DEVICE(...)                                                          \
+    do {                                                                                 \
+        static std::atomic<uint64_t> _sb_mask{0};                                        \
+        int _sb_dev = 0;                                                                 \
+        cudaGetDevice(&_sb_dev);                                                         \
+        const uint64_t _sb_bit = 1ull << (_sb_dev & 63);                                 \
+        if (!(_sb_mask.load(std::memory_order_acquire) & _sb_bit)) {                     \
+            __VA_ARGS__;                                                                  \
+            _sb_mask.fetch_or(_sb_bit, std::memory_order_release);                       \
+        }                                                                                \
+    } while (0)
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }

@@ -8,38 +8,48 @@ struct SpecialIds {
     int eot, sot, translate, transcribe, solm, prev, nosp, not_, beg, lang_first, num_languages, blank;
 };
 
-// per-sequence decode state, device resident (whisper_full's per-decoder bookkeeping, App. C.4)
+// longest decoder prompt: [prev] + n_text_ctx/2 = 224 context tokens + [sot, lang, task, notimestamps] (+ the extra leading
+// [sot] of a language-detect restart), rounded up to a multiple of 8
+constexpr int kMaxPrompt = 232;
+
+// per-sequence decode state, device resident (whisper_full's per-decoder bookkeeping, App. C.4).  Every sequence of a
+// batch has its OWN position: prompts differ in length (text context carried between the windows of one call,
+// initial_prompt), and a decode slot is refilled with the next window as soon as its sequence ends.
 struct __align__(16) SeqState {
-    int n_tok;        // tokens sampled so far in this window (tokens_cur.size())
+    int n_tok;        // tokens sampled so far in this window (tokens_cur.size()) = index of the token sampled next
     int last, prev;   // last / penultimate sampled token
     int has_ts;
     int seek_delta;
     int result_len;
     int failed;
-    int done;
+    int done;         // 1: finished (or an empty slot): attention kernels skip it, the sampler leaves it alone
     int seek, seek_end;
     float sum_logprob;
-    int pad_;
-};   // 48 bytes, 16-byte aligned array elements (read with three 128-bit loads)
+    int pos;          // KV-cache position of the token fed in the current step (n_past)
+    int idx;          // prompt index of the token fed in the current step; sampling starts at idx == n_prompt - 1
+    int n_prompt;
+    int lang_slot;    // prompt index of the language token (holds -1 until k_lang_detect fills it), or -1
+    int restart;      // 1: prompt[0] is an extra [sot] fed at position 0 only to detect the language (whisper_lang_auto_detect
+                      //    decodes [sot] alone); the real prompt then starts again at position 0
+};   // 64 bytes, 16-byte aligned array elements (read with four 128-bit loads)
 
 struct SamplerArgs {
     SeqState* state;          // [B]
-    const int* step_ptr;      // device: index of the token being sampled
     int* tokens_out;          // [B][n_max]
     float* margins_out;       // [B][n_max] top1 - top2 of the filtered logits, or null
+    int* tids_out;            // [B][n_max] whisper_token_data.tid: most probable timestamp token of the step (0: none)
     int* next_tokens;         // [B] input of the next decoder step
     const int* forced;        // [B][n_max] teacher-forced tokens (<0 = free) or null
-    int* n_done;              // device counter of finished sequences
+    int* tick;                // device: steps this lane has run (launch trace index), or null
     SpecialIds sp;
     int n_vocab;
     int n_max;
+    int n_text_ctx;
     int suppress_blank;
     int no_timestamps;
     int single_segment;
     int max_initial_tid;      // round(max_initial_ts / 0.02), < 0 disables the rule
-    const int* pos_ptr;       // device: position of the token just fed to the decoder
-    const int* prompt;        // device: prompt tokens [B][n_prompt] (per sequence: the language token may differ)
-    int n_prompt;
+    int* prompt;              // device: prompt tokens [B][kMaxPrompt]
 };
 
 struct SkinnyEpilogue {
@@ -90,13 +100,16 @@ bool use_tc_attention();   // env SB_ATTN=mma selects the legacy mma.sync kernel
 
 // decoder-side launchers (decoder_kernels.cu)
 template <typename T> int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, const SkinnyEpilogue& ep, cudaStream_t st);
-template <typename T> int dec_ln(float* x, const float* gamma, const float* beta, T* out16, int rows, int d, const T* tok_emb, const float* pos_emb, const int* next_tokens, const int* pos_ptr, cudaStream_t st);
-template <typename T> int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const int* pos_ptr, const SeqState* state, int Bn, int n_head, int d, int n_text_ctx, cudaStream_t st);
+template <typename T> int dec_ln(float* x, const float* gamma, const float* beta, T* out16, int rows, int d, const T* tok_emb, const float* pos_emb, const int* next_tokens, const SeqState* state, cudaStream_t st);
+// honor_done = 0: teacher-forced traces keep every sequence alive
+template <typename T> int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const SeqState* state, int honor_done, int Bn, int n_head, int d, int n_text_ctx, cudaStream_t st);
 template <typename T> int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t ld_kv, int64_t win_stride, T* out, const SeqState* state, int Bn, int n_head, int d, int n_ctx, cudaStream_t st);
 int sample_step(const float* logits, int ld, const SamplerArgs& a, int Bn, cudaStream_t st);
-// whisper_lang_auto_detect: at decode position 0 ([sot] only) pick the language token with the largest logit and
-// write it into prompt slot 1 of every sequence whose slot holds the sentinel -1 (no-op at any other position)
-int lang_detect_step(const float* logits, int ld, int* prompt, int n_prompt, const int* pos_ptr, int* lang_out, SpecialIds sp, int Bn, cudaStream_t st);
-int dec_advance(int* pos_ptr, int* step_ptr, int n_prompt, cudaStream_t st);
+// whisper_lang_auto_detect: at prompt index 0 ([sot] alone at position 0) pick the language token with the largest logit
+// and write it into the language slot of every sequence whose slot holds the sentinel -1 (no-op for every other sequence)
+int lang_detect_step(const float* logits, int ld, int* prompt, const SeqState* state, int* lang_out, SpecialIds sp, int Bn, cudaStream_t st);
+// scatter freshly assigned windows into their decode slots (state, first token, prompt); items: device copy of SlotInit[n]
+struct SlotInit { int slot; int next_token; int pad_[2]; SeqState state; int prompt[kMaxPrompt]; };
+int slot_init(const SlotInit* items, int n, SeqState* state, int* next_tokens, int* prompt, int* lang_out, cudaStream_t st);
 
 }  // namespace sb

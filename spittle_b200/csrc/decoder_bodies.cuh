@@ -211,7 +211,7 @@ template <typename T, int VPL, typename Sync>
 __device__ __forceinline__ void ln_row_dec(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                            T* __restrict__ out16, int row, int d, const T* __restrict__ tok_emb,
                                            const float* __restrict__ pos_emb, const int* __restrict__ next_tokens,
-                                           const int* __restrict__ pos_ptr, Sync& sync) {
+                                           const SeqState* __restrict__ state, Sync& sync) {
     const int lane = threadIdx.x & 31;
     const int n4 = d >> 2;
     // immutable operands first: they are in flight while the predecessor is still finishing
@@ -226,7 +226,7 @@ __device__ __forceinline__ void ln_row_dec(float* __restrict__ x, const float* _
     float4* xr = reinterpret_cast<float4*>(x + (int64_t)row * d);
     if (tok_emb) {
         const int tok = __ldcg(next_tokens + row);
-        const int pos = __ldcg(pos_ptr);
+        const int pos = __ldcg(&state[row].pos);         // every sequence has its own position
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
             const int idx = lane + 32 * i;

@@ -1,6 +1,6 @@
 // Decoder-step kernels (whisper.cpp decoder graph + sampler, SURVEY.md App. C.3 / C.4, rows
-// a7 / a8 of 8(a)).  One "step" advances every live sequence of the batch by one token; all
-// sequences share the same position (prompt is identical), finished ones are masked.
+// a7 / a8 of 8(a)).  One "step" advances every live sequence of a decode lane by one token; every
+// sequence has its own position and prompt (SeqState), finished sequences / empty slots are masked.
 //
 //   k_dec_ln              LayerNorm of the residual stream (+ token / positional embedding at layer 0)
 //   k_skinny_gemm         Y[B,N] = X[B,K] W[N,K]^T (+bias, GELU, +residual); B <= 64 per pass,
@@ -59,10 +59,10 @@ template <typename T, int VPL>
 __global__ void __launch_bounds__(32) k_dec_ln(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                T* __restrict__ out16, int d, const T* __restrict__ tok_emb,
                                                const float* __restrict__ pos_emb, const int* __restrict__ next_tokens,
-                                               const int* __restrict__ pos_ptr, TraceSlot ts) {
+                                               const SeqState* __restrict__ state, TraceSlot ts) {
     trace_begin(ts);
     struct S { __device__ __forceinline__ void wait() { pdl_wait(); pdl_trigger(); } } sync;
-    ln_row_dec<T, VPL>(x, gamma, beta, out16, blockIdx.x, d, tok_emb, pos_emb, next_tokens, pos_ptr, sync);
+    ln_row_dec<T, VPL>(x, gamma, beta, out16, blockIdx.x, d, tok_emb, pos_emb, next_tokens, state, sync);
     trace_end(ts);
 }
 
@@ -71,20 +71,19 @@ __global__ void __launch_bounds__(32) k_dec_ln(float* __restrict__ x, const floa
 // interleaved over the warps -- so the two dependent sweeps over the cache are a quarter as long as with one warp.
 template <typename T>
 __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc,
-                                                       T* __restrict__ out, const int* __restrict__ pos_ptr,
-                                                       const SeqState* __restrict__ state, int n_head, int d, int n_text_ctx,
-                                                       TraceSlot ts) {
+                                                       T* __restrict__ out, const SeqState* __restrict__ state, int honor_done,
+                                                       int n_head, int d, int n_text_ctx, TraceSlot ts) {
     trace_begin(ts);
     __shared__ float s_p[448];
     __shared__ float s_red[4];
     __shared__ float s_o[4][64];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int h = blockIdx.x, b = blockIdx.y;
-    // `done` and `pos` were written by the sampler / k_dec_advance of the previous step (many launches ago) and the cache
+    // `done` and `pos` were written by the sampler of the previous step (many launches ago) and the cache
     // rows [0, pos) by earlier steps: all of it may be touched before the dependency wait, so the rows this block is
     // about to sweep are requested into L2 while the QKV projection in front of it is still finishing
-    const bool skip = state && __ldcg(&state[b].done);   // finished sequences are skipped
-    const int pos = __ldcg(pos_ptr);                     // index of the new token; attends to [0, pos]
+    const bool skip = honor_done && __ldcg(&state[b].done);   // finished sequences / empty slots are skipped
+    const int pos = min(__ldcg(&state[b].pos), n_text_ctx - 1);   // this sequence's new token; attends to [0, pos]
     const T* q = qkv + (int64_t)b * 3 * d + h * 64;
     T* kb = kc + ((int64_t)b * n_text_ctx) * d + h * 64;
     T* vb = vc + ((int64_t)b * n_text_ctx) * d + h * 64;
@@ -302,20 +301,25 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
     const int b = blockIdx.x;
     pdl_wait();
     pdl_trigger();
+    if (b == 0 && threadIdx.x == 0 && a.tick) *a.tick = __ldcg(a.tick) + 1;      // lane step counter (launch trace only)
     SeqState st;
     {
-        static_assert(sizeof(SeqState) == 48, "SeqState is read as three int4");
+        static_assert(sizeof(SeqState) == 64, "SeqState is read as four int4");
         const int4* sp4 = reinterpret_cast<const int4*>(a.state + b);
         int4* dp4 = reinterpret_cast<int4*>(&st);
-        dp4[0] = __ldcg(sp4); dp4[1] = __ldcg(sp4 + 1); dp4[2] = __ldcg(sp4 + 2);
+        dp4[0] = __ldcg(sp4); dp4[1] = __ldcg(sp4 + 1); dp4[2] = __ldcg(sp4 + 2); dp4[3] = __ldcg(sp4 + 3);
     }
-    const int step = __ldcg(a.step_ptr);   // index of the token being sampled (i in whisper_full)
-    const int pos = __ldcg(a.pos_ptr);
-    if (pos < a.n_prompt - 1) {            // still feeding the prompt: queue its next token
-        if (threadIdx.x == 0) a.next_tokens[b] = __ldcg(a.prompt + (int64_t)b * a.n_prompt + pos + 1);
+    if (st.done) return;                   // finished sequence or empty slot
+    if (st.idx < st.n_prompt - 1) {        // still feeding the prompt: queue its next token
+        if (threadIdx.x == 0) {
+            a.next_tokens[b] = __ldcg(a.prompt + (int64_t)b * kMaxPrompt + st.idx + 1);
+            // after the language-detect [sot] the real prompt starts again at position 0
+            a.state[b].pos = (st.restart && st.idx == 0) ? 0 : st.pos + 1;
+            a.state[b].idx = st.idx + 1;
+        }
         return;
     }
-    if (st.done) return;
+    const int step = st.n_tok;             // index of the token being sampled (i in whisper_full)
     const SpecialIds sp = a.sp;
     const int V = a.n_vocab;
     // Stage the whole vocabulary row (207 KB, L2-resident: the logits GEMM just wrote it) in shared memory with one
@@ -402,7 +406,21 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
     float gv; int gi;
     red.argmax(bv, bi, gv, gi);
     const float sv = red.max_f(bi == gi ? b2 : bv);
+    // whisper_token_data.tid (whisper_sample_token): the most probable timestamp token of this step, first maximum in
+    // ascending id; probabilities that underflow to 0 never win and leave tid = 0.  Segment start times come from it.
+    float tv = -INFINITY; int ti = 0x7fffffff;
+    if (!a.no_timestamps)
+        for (int id = sp.beg + threadIdx.x; id < V; id += kSampThreads) {
+            if (mk.suppressed(id)) continue;
+            const float x = lg[id];
+            if (x > tv) { tv = x; ti = id; }
+        }
+    float gtv; int gti;
+    red.argmax(tv, ti, gtv, gti);
     if (threadIdx.x != 0) return;
+    // after the timestamp-mass rule the text tokens are gone and the distribution is renormalised over the timestamps
+    const float lse_eff = force_ts ? (logf(ts.s) + ts.m) : lse;
+    const int tid = (gtv > -INFINITY && expf(gtv - lse_eff) > 0.f) ? gti : 0;
 
     int tok = gi;
     if (a.forced) {
@@ -411,6 +429,7 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
     }
     a.tokens_out[(int64_t)b * a.n_max + step] = tok;
     if (a.margins_out) a.margins_out[(int64_t)b * a.n_max + step] = gv - sv;
+    if (a.tids_out) a.tids_out[(int64_t)b * a.n_max + step] = tid;
     a.next_tokens[b] = tok;
     st.prev = st.last; st.last = tok; st.n_tok += 1;
     st.sum_logprob += (gv - lse);
@@ -431,20 +450,23 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
     }
     if (!stop && step == a.n_max - 1 && (st.result_len == 0 || st.seek_delta < 1500)) { st.failed = 1; stop = true; }
     if (!stop && step == a.n_max - 1) stop = true;
-    if (stop) { st.done = 1; atomicAdd(a.n_done, 1); }
+    if (!stop && st.pos + 1 >= a.n_text_ctx) { if (st.result_len == 0) st.failed = 1; stop = true; }   // text context exhausted
+    if (stop) st.done = 1;
+    st.pos += 1;
     a.state[b] = st;
 }
 
 // language auto-detect (whisper.cpp whisper_lang_auto_detect_with_state): the decoder has seen [sot] only;
 // among the language tokens the one with the largest raw logit (= largest softmax probability; lowest id on
 // ties) becomes prompt token 1 of the sequence.  One warp per sequence.
-__global__ void __launch_bounds__(32) k_lang_detect(const float* __restrict__ logits, int ld, int* __restrict__ prompt, int n_prompt,
-                                                    const int* __restrict__ pos_ptr, int* __restrict__ lang_out, SpecialIds sp) {
+__global__ void __launch_bounds__(32) k_lang_detect(const float* __restrict__ logits, int ld, int* __restrict__ prompt,
+                                                    const SeqState* __restrict__ state, int* __restrict__ lang_out, SpecialIds sp) {
     pdl_wait();
     pdl_trigger();
-    if (__ldcg(pos_ptr) != 0) return;
     const int b = blockIdx.x, lane = threadIdx.x;
-    if (__ldcg(prompt + (int64_t)b * n_prompt + 1) >= 0) return;       // language given (or detected on an earlier window)
+    const int idx = __ldcg(&state[b].idx), slot = __ldcg(&state[b].lang_slot);
+    if (__ldcg(&state[b].done) || idx != 0 || slot < 0) return;
+    if (__ldcg(prompt + (int64_t)b * kMaxPrompt + slot) >= 0) return;       // language given (or detected on an earlier window)
     const float* lg = logits + (int64_t)b * ld + sp.lang_first;
     float bv = -INFINITY; int bi = 0x7fffffff;
     for (int i = lane; i < sp.num_languages; i += 32) {
@@ -458,18 +480,18 @@ __global__ void __launch_bounds__(32) k_lang_detect(const float* __restrict__ lo
         if (v2 > bv || (v2 == bv && i2 < bi)) { bv = v2; bi = i2; }
     }
     if (lane == 0) {
-        prompt[(int64_t)b * n_prompt + 1] = sp.lang_first + bi;
+        prompt[(int64_t)b * kMaxPrompt + slot] = sp.lang_first + bi;
         if (lang_out) lang_out[b] = bi;
     }
 }
 
-// advance the shared position / step counters (single thread) after a step
-__global__ void k_dec_advance(int* pos_ptr, int* step_ptr, int n_prompt) {
-    pdl_wait();
-    pdl_trigger();
-    const int p = __ldcg(pos_ptr);
-    if (p >= n_prompt - 1) *step_ptr = __ldcg(step_ptr) + 1;
-    *pos_ptr = p + 1;
+// freshly assigned windows -> their decode slots.  One block per item; runs on the lane's stream between two steps.
+__global__ void __launch_bounds__(64) k_slot_init(const SlotInit* __restrict__ items, SeqState* __restrict__ state,
+                                                  int* __restrict__ next_tokens, int* __restrict__ prompt, int* __restrict__ lang_out) {
+    const SlotInit& it = items[blockIdx.x];
+    const int slot = it.slot;
+    for (int i = threadIdx.x; i < kMaxPrompt; i += 64) prompt[(int64_t)slot * kMaxPrompt + i] = it.prompt[i];
+    if (threadIdx.x == 0) { state[slot] = it.state; next_tokens[slot] = it.next_token; if (lang_out) lang_out[slot] = -1; }
 }
 
 // ---- launchers -------------------------------------------------------------------------
@@ -485,19 +507,14 @@ int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, 
     static const int narrow_w32_env = [] { const char* e = getenv("SB_DEC_NARROW_W32"); return e ? atoi(e) : -1; }();
     const bool narrow_w32 = narrow_w32_env >= 0 ? narrow_w32_env != 0 : K >= 1024;
     if (N >= w32_min_n && narrow && narrow_w32) {
-        static bool attr_done2 = false;
-        if (!attr_done2) { SB_CUDA_CHECK(cudaFuncSetAttribute(k_skinny_gemm_w32n<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkinnySmem)); attr_done2 = true; }
+        SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(k_skinny_gemm_w32n<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkinnySmem)); });
         launch_pdl(k_skinny_gemm_w32n<T>, dim3(ceil_div(N, 32), chunks), dim3(256), (size_t)kSkinnySmem, st, X, ldx, W, ldw, Bn, N, K, ept);
         g_launches += 1;
         SB_CUDA_CHECK(cudaGetLastError());
         return SB_OK;
     }
     if (N >= w32_min_n && !narrow) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            SB_CUDA_CHECK(cudaFuncSetAttribute(k_skinny_gemm_w32<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkinnySmem));
-            attr_done = true;
-        }
+        SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(k_skinny_gemm_w32<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkinnySmem)); });
         launch_pdl(k_skinny_gemm_w32<T>, dim3(ceil_div(N, 32), chunks), dim3(256), (size_t)kSkinnySmem, st, X, ldx, W, ldw, Bn, N, K, ept);
         g_launches += 1;
         SB_CUDA_CHECK(cudaGetLastError());
@@ -512,24 +529,24 @@ int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, 
 }
 template <typename T>
 int dec_ln(float* x, const float* gamma, const float* beta, T* out16, int rows, int d, const T* tok_emb, const float* pos_emb,
-           const int* next_tokens, const int* pos_ptr, cudaStream_t st) {
+           const int* next_tokens, const SeqState* state, cudaStream_t st) {
     SB_CHECK_ARG(d % 4 == 0 && d <= 1536, "decoder layernorm: d % 4, d <= 1536");
     const TraceSlot ts = g_trace_next; g_trace_next = TraceSlot();
     if (dbg_skip() & 4) return SB_OK;
-    if (d <= 768) launch_pdl(k_dec_ln<T, 6>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr, ts);
-    else if (d <= 1280) launch_pdl(k_dec_ln<T, 10>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr, ts);
-    else launch_pdl(k_dec_ln<T, 12>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, pos_ptr, ts);
+    if (d <= 768) launch_pdl(k_dec_ln<T, 6>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, state, ts);
+    else if (d <= 1280) launch_pdl(k_dec_ln<T, 10>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, state, ts);
+    else launch_pdl(k_dec_ln<T, 12>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, state, ts);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
 }
 template <typename T>
-int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const int* pos_ptr, const SeqState* state, int Bn, int n_head, int d,
+int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const SeqState* state, int honor_done, int Bn, int n_head, int d,
                   int n_text_ctx, cudaStream_t st) {
     SB_CHECK_ARG(n_text_ctx <= 448 && d == n_head * 64, "self attention: n_text_ctx <= 448, d_head 64");
     const TraceSlot ts = g_trace_next; g_trace_next = TraceSlot();
     if (dbg_skip() & 8) return SB_OK;
-    launch_pdl(k_dec_self_attn<T>, dim3(n_head, Bn), dim3(128), 0, st, qkv, kc, vc, out, pos_ptr, state, n_head, d, n_text_ctx, ts);
+    launch_pdl(k_dec_self_attn<T>, dim3(n_head, Bn), dim3(128), 0, st, qkv, kc, vc, out, state, honor_done, n_head, d, n_text_ctx, ts);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
@@ -550,26 +567,23 @@ int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t 
 int sample_step(const float* logits, int ld, const SamplerArgs& a, int Bn, cudaStream_t st) {
     const size_t smem = (size_t)((a.n_vocab + 3) / 4) * 16;
     SB_CHECK_ARG(smem <= 226 * 1024 && ld % 4 == 0, "sampler: vocabulary row must fit shared memory (<= 57856 tokens)");
-    static bool attr_done = false;
-    if (!attr_done) {
-        SB_CUDA_CHECK(cudaFuncSetAttribute(k_logits_filter_argmax, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        attr_done = true;
-    }
+    SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(k_logits_filter_argmax, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); });
     launch_pdl(k_logits_filter_argmax, dim3(Bn), dim3(kSampThreads), smem, st, logits, ld, a);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
 }
-int lang_detect_step(const float* logits, int ld, int* prompt, int n_prompt, const int* pos_ptr, int* lang_out, SpecialIds sp, int Bn,
+int lang_detect_step(const float* logits, int ld, int* prompt, const SeqState* state, int* lang_out, SpecialIds sp, int Bn,
                      cudaStream_t st) {
-    SB_CHECK_ARG(n_prompt >= 2 && sp.num_languages > 0, "language auto-detect needs a multilingual model");
-    launch_pdl(k_lang_detect, dim3(Bn), dim3(32), 0, st, logits, ld, prompt, n_prompt, pos_ptr, lang_out, sp);
+    SB_CHECK_ARG(sp.num_languages > 0, "language auto-detect needs a multilingual model");
+    launch_pdl(k_lang_detect, dim3(Bn), dim3(32), 0, st, logits, ld, prompt, state, lang_out, sp);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
 }
-int dec_advance(int* pos_ptr, int* step_ptr, int n_prompt, cudaStream_t st) {
-    launch_pdl(k_dec_advance, dim3(1), dim3(1), 0, st, pos_ptr, step_ptr, n_prompt);
+int slot_init(const SlotInit* items, int n, SeqState* state, int* next_tokens, int* prompt, int* lang_out, cudaStream_t st) {
+    if (n <= 0) return SB_OK;
+    k_slot_init<<<n, 64, 0, st>>>(items, state, next_tokens, prompt, lang_out);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
@@ -577,8 +591,8 @@ int dec_advance(int* pos_ptr, int* step_ptr, int n_prompt, cudaStream_t st) {
 
 #define SB_INST_D(T)                                                                                              \
     template int skinny_gemm<T>(const T*, int, const T*, int, int, int, int, const SkinnyEpilogue&, cudaStream_t); \
-    template int dec_ln<T>(float*, const float*, const float*, T*, int, int, const T*, const float*, const int*, const int*, cudaStream_t); \
-    template int dec_self_attn<T>(const T*, T*, T*, T*, const int*, const SeqState*, int, int, int, int, cudaStream_t);             \
+    template int dec_ln<T>(float*, const float*, const float*, T*, int, int, const T*, const float*, const int*, const SeqState*, cudaStream_t); \
+    template int dec_self_attn<T>(const T*, T*, T*, T*, const SeqState*, int, int, int, int, int, cudaStream_t);             \
     template int dec_cross_attn<T>(const T*, int, const T*, const T*, int64_t, int64_t, T*, const SeqState*, int, int, int, int, cudaStream_t);
 SB_INST_D(__nv_bfloat16)
 SB_INST_D(__half)

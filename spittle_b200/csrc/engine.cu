@@ -11,6 +11,8 @@
 #include <memory>
 #include <mutex>
 #include <regex>
+#include <thread>
+#include <cstddef>
 #include <unordered_map>
 #include <vector>
 
@@ -50,6 +52,21 @@ struct DevBuf {
         return SB_OK;
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+struct PinBuf {        // pinned host staging
+    void* p = nullptr; size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return SB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMallocHost(&p, need);
+        if (e != cudaSuccess) { set_error(std::string("cudaMallocHost(") + std::to_string(need) + "): " + cudaGetErrorString(e)); return SB_ERR_NOMEM; }
+        bytes = need;
+        return SB_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
     template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
 };
 
@@ -129,6 +146,9 @@ struct EngineBase {
 
 static SpecialIds special_from_vocab(int n_vocab, const std::vector<std::string>& vocab) {
     SpecialIds s{50256, 50257, 50357, 50358, 50359, 50360, 50361, 50362, 50363, 0, 0, 220};
+    // whisper.cpp: num_languages = n_vocab - 51765 - (multilingual ? 1 : 0); English-only vocabularies keep the 99 language
+    // ids 50258..50356 (always suppressed by the logits filter) even though their prompt carries no language token
+    s.num_languages = std::max(0, n_vocab - 51765);
     if (n_vocab >= 51865) {
         s.num_languages = n_vocab - 51765 - 1;
         s.eot++; s.sot++;
@@ -163,8 +183,8 @@ struct Engine : EngineBase {
     DevBuf b_pcm, b_mel, b_cmax, b_floor, b_clipmeta, b_winmeta;
     DevBuf b_col1, b_c1, b_x, b_h, b_qkv, b_att, b_mlp, b_enc32;
     DevBuf b_ckv, b_kself, b_vself, b_dx, b_dh, b_dqkv, b_datt, b_dq, b_dmlp, b_logits;
-    DevBuf b_state, b_tokens, b_margins, b_next, b_forced, b_ctr, b_prompt;
-    int* h_ctr = nullptr;   // pinned: [pos, step, n_done]
+    DevBuf b_state, b_tokens, b_margins, b_tids, b_next, b_forced, b_tick, b_prompt, b_lang, b_init;
+    PinBuf h_state, h_tokens, h_margins, h_tids, h_lang, h_init, h_winmeta;   // host mirrors polled once per burst / slot-init staging
     // profile == 2: device-side launch trace of the decoder step (TraceSlot, common.cuh)
     DevBuf b_trace;
     std::vector<int> trace_cls;          // class of launch idx inside a step: 0 projection, 1 LayerNorm, 2 self-attn, 3 cross-attn
@@ -217,22 +237,29 @@ struct Engine : EngineBase {
     // different lanes overlap and the cross-attention of one lane streams while the others wait on latency.
     static constexpr int kMaxLanes = 4;
     struct GraphKey {
-        int W, w0, Wl, n_max, flags, max_init, n_prompt, has_forced, gen;
+        int S, s0, n, n_max, flags, max_init, has_forced, gen;
         bool operator==(const GraphKey& o) const {
-            return W == o.W && w0 == o.w0 && Wl == o.Wl && n_max == o.n_max && flags == o.flags && max_init == o.max_init &&
-                   n_prompt == o.n_prompt && has_forced == o.has_forced && gen == o.gen;
+            return S == o.S && s0 == o.s0 && n == o.n && n_max == o.n_max && flags == o.flags && max_init == o.max_init &&
+                   has_forced == o.has_forced && gen == o.gen;
         }
     };
+    // A decode SLOT holds one window being decoded (its cross-KV rows, self-KV cache, SeqState, prompt, token row); a
+    // LANE is a contiguous range of slots stepped together on its own stream with its own captured step graph.
     struct Lane {
         cudaStream_t st = nullptr;
         cudaEvent_t done = nullptr;
         cudaGraphExec_t gexec = nullptr;
-        GraphKey key{0, 0, 0, 0, 0, 0, 0, 0, -1};
+        GraphKey key{0, 0, 0, 0, 0, 0, 0, -1};
         int graph_nodes = 0;
+        int s0 = 0, n = 0;        // slots [s0, s0 + n)
+        int active = 0;           // slots of this lane holding a live sequence
+        int steps = 0;            // steps run in the current call
     };
     Lane lanes[kMaxLanes];
-    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_enc = nullptr;
     int n_lanes_cfg = 2;
+    int n_slots = 0, n_lanes = 0, n_max_cur = 0;
+    int refill_min_cfg = 0;       // free slots needed before a refill encode is started (0: max(1, slots / 8))
 
     ~Engine() override {
         for (auto& l : lanes) {
@@ -241,14 +268,17 @@ struct Engine : EngineBase {
             if (l.st) cudaStreamDestroy(l.st);
         }
         if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_enc) cudaEventDestroy(ev_enc);
         for (auto& r : prof_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
         for (void* p : owned) cudaFree(p);
         DevBuf* bufs[] = {&b_pcm, &b_mel, &b_cmax, &b_floor, &b_clipmeta, &b_winmeta, &b_col1, &b_c1, &b_x, &b_h, &b_qkv,
                           &b_att, &b_mlp, &b_enc32, &b_ckv, &b_kself, &b_vself, &b_dx, &b_dh, &b_dqkv, &b_datt, &b_dq,
-                          &b_dmlp, &b_logits, &b_state, &b_tokens, &b_margins, &b_next, &b_forced, &b_ctr, &b_prompt};
+                          &b_dmlp, &b_logits, &b_state, &b_tokens, &b_margins, &b_tids, &b_next, &b_forced, &b_tick, &b_prompt,
+                          &b_lang, &b_init, &b_trace};
         for (DevBuf* b : bufs) b->release();
+        PinBuf* pins[] = {&h_state, &h_tokens, &h_margins, &h_tids, &h_lang, &h_init, &h_winmeta};
+        for (PinBuf* b : pins) b->release();
         if (melplan) sb_melplan_destroy(melplan);
-        if (h_ctr) cudaFreeHost(h_ctr);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (st) cudaStreamDestroy(st);
     }
@@ -351,12 +381,13 @@ struct Engine : EngineBase {
         SB_CHECK_ARG(hp.n_text_ctx <= 448, "n_text_ctx must be <= 448");
         SB_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         for (auto& e : ev) SB_CUDA_CHECK(cudaEventCreate(&e));
-        SB_CUDA_CHECK(cudaMallocHost(&h_ctr, 16 * kMaxLanes * sizeof(int)));
         for (auto& l : lanes) {
             SB_CUDA_CHECK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
             SB_CUDA_CHECK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
         }
         SB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        SB_CUDA_CHECK(cudaEventCreate(&ev_enc));
+        if (const char* e = getenv("SB_REFILL_MIN")) refill_min_cfg = std::max(0, atoi(e));
         if (const char* e = getenv("SB_DECODE_LANES")) { n_lanes_cfg = atoi(e); if (n_lanes_cfg < 1) n_lanes_cfg = 1; if (n_lanes_cfg > kMaxLanes) n_lanes_cfg = kMaxLanes; }
         int rc = sb_melplan_create(f.mel_filters.data(), hp.n_mels, &melplan);
         if (rc) return rc;
@@ -409,8 +440,9 @@ struct Engine : EngineBase {
     }
 
     // ---- encoder over `W` windows whose im2col rows are already in b_col1 -------------------
-    // produces cross-KV rows [w0*1500 .. (w0+W)*1500) of b_ckv and (optionally) f32 encoder output
-    int encode_chunk(int W, int w0, float* enc32_out) {
+    // writes the cross-KV of window i into decode slot slots[i] (identity when slots == nullptr) and (optionally) the
+    // f32 encoder output
+    int encode_chunk(int W, const int* slots, float* enc32_out) {
         const int d = hp.n_audio_state, nctx = hp.n_audio_ctx, nfr = 2 * nctx;
         const int M2 = W * nfr, M = W * nctx;
         int rc;
@@ -428,8 +460,7 @@ struct Engine : EngineBase {
             ep = GemmEpilogue{b_qkv.p, 3 * d, 0, L.qkv.b, 0, nullptr, 0, 0};
             if ((rc = gemm_p(b_h.p, d, L.qkv.w, d, M, 3 * d, d, ep))) return rc;
             if ((rc = prof_begin(1, 4.0 * W * (double)nctx * nctx * d))) return rc;
-            if (use_tc_attention()) { if ((rc = attn_enc_tc<T>(b_qkv.as<T>(), b_att.as<T>(), W, nctx, d, hp.n_audio_head, st))) return rc; }
-            else if ((rc = attn_enc<T>(b_qkv.as<T>(), b_att.as<T>(), W, nctx, d, hp.n_audio_head, st))) return rc;
+            if ((rc = attn_enc_tc<T>(b_qkv.as<T>(), b_att.as<T>(), W, nctx, d, hp.n_audio_head, st))) return rc;
             if ((rc = prof_end())) return rc;
             ep = GemmEpilogue{b_x.p, d, 1, L.o.b, 0, b_x.as<float>(), d, 0};
             if ((rc = gemm_p(b_att.p, d, L.o.w, d, M, d, d, ep))) return rc;
@@ -440,14 +471,21 @@ struct Engine : EngineBase {
             if ((rc = gemm_p(b_mlp.p, 4 * d, L.fc2.w, 4 * d, M, d, 4 * d, ep))) return rc;
         }
         if ((rc = layernorm<T>(b_x.as<float>(), ln_post.g, ln_post.b, b_h.as<T>(), enc32_out, M, d, st))) return rc;
-        // cross-KV for every decoder layer in one GEMM: [M, Ld*2*d]
+        // cross-KV for every decoder layer in one GEMM per run of consecutive slots: [rows, Ld*2*d]
         const int nkv = hp.n_text_layer * 2 * d;
-        ep = GemmEpilogue{b_ckv.as<T>() + (int64_t)w0 * nctx * nkv, nkv, 0, cross_kv.b, 0, nullptr, 0, 0};
-        if ((rc = gemm_p(b_h.p, d, cross_kv.w, d, M, nkv, d, ep))) return rc;
+        for (int i = 0; i < W;) {
+            int j = i + 1;
+            while (slots && j < W && slots[j] == slots[j - 1] + 1) ++j;
+            if (!slots) j = W;
+            const int slot0 = slots ? slots[i] : 0;
+            ep = GemmEpilogue{b_ckv.as<T>() + (int64_t)slot0 * nctx * nkv, nkv, 0, cross_kv.b, 0, nullptr, 0, 0};
+            if ((rc = gemm_p(b_h.as<T>() + (int64_t)i * nctx * d, d, cross_kv.w, d, (j - i) * nctx, nkv, d, ep))) return rc;
+            i = j;
+        }
         return SB_OK;
     }
 
-    int ensure_encoder_ws(int Wc, int Wtot, bool want32) {
+    int ensure_encoder_ws(int Wc, bool want32) {
         const size_t d = hp.n_audio_state, nctx = hp.n_audio_ctx;
         const size_t M = (size_t)Wc * nctx, M2 = 2 * M;
         int rc;
@@ -459,39 +497,49 @@ struct Engine : EngineBase {
         if ((rc = b_att.ensure(M * d * 2))) return rc;
         if ((rc = b_mlp.ensure(M * 4 * d * 2))) return rc;
         if (want32 && (rc = b_enc32.ensure(M * d * 4))) return rc;
-        if ((rc = b_ckv.ensure((size_t)Wtot * nctx * hp.n_text_layer * 2 * d * 2))) return rc;
         return SB_OK;
     }
 
-    int ensure_decoder_ws(int W, int n_max) {
+    int ensure_decoder_ws(int S, int n_max) {
         const size_t d = hp.n_text_state;
         int rc;
-        const size_t kvb = (size_t)hp.n_text_layer * W * hp.n_text_ctx * d * 2;
+        const size_t kvb = (size_t)hp.n_text_layer * S * hp.n_text_ctx * d * 2;
+        if ((rc = b_ckv.ensure((size_t)S * hp.n_audio_ctx * hp.n_text_layer * 2 * d * 2))) return rc;
         if ((rc = b_kself.ensure(kvb))) return rc;
         if ((rc = b_vself.ensure(kvb))) return rc;
-        if ((rc = b_dx.ensure(W * d * 4))) return rc;
-        if ((rc = b_dh.ensure(W * d * 2))) return rc;
-        if ((rc = b_dqkv.ensure(W * 3 * d * 2))) return rc;
-        if ((rc = b_datt.ensure(W * d * 2))) return rc;
-        if ((rc = b_dq.ensure(W * d * 2))) return rc;
-        if ((rc = b_dmlp.ensure(W * 4 * d * 2))) return rc;
-        if ((rc = b_logits.ensure((size_t)W * round_up(hp.n_vocab, 8) * 4))) return rc;
-        if ((rc = b_state.ensure(W * sizeof(SeqState)))) return rc;
-        if ((rc = b_tokens.ensure((size_t)W * n_max * 4))) return rc;
-        if ((rc = b_margins.ensure((size_t)W * n_max * 4))) return rc;
-        if ((rc = b_forced.ensure((size_t)W * n_max * 4))) return rc;
-        if ((rc = b_next.ensure(W * 4))) return rc;
-        if ((rc = b_ctr.ensure(64 * kMaxLanes))) return rc;
-        if ((rc = b_prompt.ensure(64))) return rc;
+        if ((rc = b_dx.ensure(S * d * 4))) return rc;
+        if ((rc = b_dh.ensure(S * d * 2))) return rc;
+        if ((rc = b_dqkv.ensure(S * 3 * d * 2))) return rc;
+        if ((rc = b_datt.ensure(S * d * 2))) return rc;
+        if ((rc = b_dq.ensure(S * d * 2))) return rc;
+        if ((rc = b_dmlp.ensure(S * 4 * d * 2))) return rc;
+        if ((rc = b_logits.ensure((size_t)S * round_up(hp.n_vocab, 8) * 4))) return rc;
+        if ((rc = b_state.ensure(S * sizeof(SeqState)))) return rc;
+        if ((rc = b_tokens.ensure((size_t)S * n_max * 4))) return rc;
+        if ((rc = b_margins.ensure((size_t)S * n_max * 4))) return rc;
+        if ((rc = b_tids.ensure((size_t)S * n_max * 4))) return rc;
+        if ((rc = b_forced.ensure((size_t)S * n_max * 4))) return rc;
+        if ((rc = b_next.ensure(S * 4))) return rc;
+        if ((rc = b_lang.ensure(S * 4))) return rc;
+        if ((rc = b_tick.ensure(64 * kMaxLanes))) return rc;
+        if ((rc = b_prompt.ensure((size_t)S * kMaxPrompt * 4))) return rc;
+        if ((rc = b_init.ensure((size_t)S * sizeof(SlotInit)))) return rc;
+        if ((rc = h_state.ensure(S * sizeof(SeqState)))) return rc;
+        if ((rc = h_tokens.ensure((size_t)S * n_max * 4))) return rc;
+        if ((rc = h_margins.ensure((size_t)S * n_max * 4))) return rc;
+        if ((rc = h_tids.ensure((size_t)S * n_max * 4))) return rc;
+        if ((rc = h_lang.ensure(S * 4))) return rc;
+        if ((rc = h_init.ensure((size_t)S * sizeof(SlotInit)))) return rc;
         return SB_OK;
     }
 
-    // ---- one decoder step for sequences [w0, w0 + Wl) of a W-sequence batch, all launches on `sl` ----
-    int enqueue_step(int W, int w0, int Wl, int* ctr, cudaStream_t sl, const SamplerArgs& sa) {
+    // ---- one decoder step for the slots of lane `li`, all launches on the lane's stream ----
+    int enqueue_step(int li, const SamplerArgs& sa, bool honor_done) {
+        const Lane& Ln = lanes[li];
+        const int S = n_slots, w0 = Ln.s0, Wl = Ln.n;
+        cudaStream_t sl = Ln.st;
         const int d = hp.n_text_state, nctx = hp.n_audio_ctx;
         const int nkv = hp.n_text_layer * 2 * d;
-        int* pos_ptr = ctr;
-        int* step_ptr = ctr + 1;
         float* dx = b_dx.as<float>() + (int64_t)w0 * d;
         T* dh = b_dh.as<T>() + (int64_t)w0 * d;
         T* dqkv = b_dqkv.as<T>() + (int64_t)w0 * 3 * d;
@@ -500,14 +548,12 @@ struct Engine : EngineBase {
         T* dmlp = b_dmlp.as<T>() + (int64_t)w0 * 4 * d;
         const int vpad = (int)round_up(hp.n_vocab, 8);
         float* logits = b_logits.as<float>() + (int64_t)w0 * vpad;
-        // teacher-forced traces keep every sequence alive (their `done` flag only marks where free-running would stop)
-        const SeqState* seq_state = sa.forced ? nullptr : sa.state;
+        const SeqState* seq_state = sa.state;
         int rc;
         // PDL chain, one launch per stage (what was measured against it and lost -- a persistent per-step megakernel,
         // split-K / cluster projections, LayerNorm fused into the projections -- is in profiles/r1_mega_stage_trace.md)
         // profile == 2: every stage launch of the step gets a trace slot (class, algorithmic bytes); the step keeps its graph
         const bool tracing = profile == 2 && trace_per_step > 0;
-        const int lane_idx = (int)((ctr - b_ctr.as<int>()) / 16);
         int tidx = 0;
         auto tr = [&](int cls, double work) {
             if (!tracing) return;
@@ -515,9 +561,9 @@ struct Engine : EngineBase {
             trace_cls[tidx] = cls; trace_work[tidx] = work;
             const size_t n = (size_t)trace_max_steps * trace_per_step;
             TraceSlot ts;
-            ts.t0 = b_trace.as<unsigned long long>() + (size_t)lane_idx * 2 * n;
+            ts.t0 = b_trace.as<unsigned long long>() + (size_t)li * 2 * n;
             ts.t1 = ts.t0 + n;
-            ts.pos = pos_ptr; ts.idx = tidx; ts.per_step = trace_per_step;
+            ts.tick = sa.tick; ts.idx = tidx; ts.per_step = trace_per_step; ts.max_steps = trace_max_steps;
             g_trace_next = ts;
             ++tidx;
         };
@@ -528,109 +574,89 @@ struct Engine : EngineBase {
         const int* next_tok = b_next.as<int>() + w0;
         for (int l = 0; l < hp.n_text_layer; ++l) {
             const DecLayer<T>& L = dec[l];
-            T* kc = b_kself.as<T>() + ((int64_t)l * W + w0) * hp.n_text_ctx * d;
-            T* vc = b_vself.as<T>() + ((int64_t)l * W + w0) * hp.n_text_ctx * d;
+            T* kc = b_kself.as<T>() + ((int64_t)l * S + w0) * hp.n_text_ctx * d;
+            T* vc = b_vself.as<T>() + ((int64_t)l * S + w0) * hp.n_text_ctx * d;
             SkinnyEpilogue e{};
             // attn_ln; layer 0 forms x = token_embedding[tok] + positional_embedding[pos] first
             tr(1, 0);
-            if ((rc = dec_ln<T>(dx, L.ln1.g, L.ln1.b, dh, Wl, d, l == 0 ? tok_emb : nullptr, dec_pos, next_tok, pos_ptr, sl))) return rc;
+            if ((rc = dec_ln<T>(dx, L.ln1.g, L.ln1.b, dh, Wl, d, l == 0 ? tok_emb : nullptr, dec_pos, next_tok, seq_state, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.qkv.b; e.out16 = dqkv; e.ldo16 = 3 * d;
             if ((rc = sk(dh, d, L.qkv.w, d, 3 * d, d, e))) return rc;
             tr(2, 0);
-            if ((rc = dec_self_attn<T>(dqkv, kc, vc, datt, pos_ptr, seq_state, Wl, hp.n_text_head, d, hp.n_text_ctx, sl))) return rc;
+            if ((rc = dec_self_attn<T>(dqkv, kc, vc, datt, seq_state, honor_done ? 1 : 0, Wl, hp.n_text_head, d, hp.n_text_ctx, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.o.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
             if ((rc = sk(datt, d, L.o.w, d, d, d, e))) return rc;
             const T* kb = b_ckv.as<T>() + (int64_t)w0 * nctx * nkv + (int64_t)l * 2 * d;
             tr(1, 0);
-            if ((rc = dec_ln<T>(dx, L.ln2.g, L.ln2.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, sl))) return rc;
+            if ((rc = dec_ln<T>(dx, L.ln2.g, L.ln2.b, dh, Wl, d, nullptr, nullptr, nullptr, seq_state, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.cq.b; e.out16 = dq; e.ldo16 = d;
             if ((rc = sk(dh, d, L.cq.w, d, d, d, e))) return rc;
             tr(3, 0);
-            if ((rc = dec_cross_attn<T>(dq, d, kb, kb + d, nkv, (int64_t)nctx * nkv, datt, seq_state, Wl, hp.n_text_head, d, nctx, sl))) return rc;
+            if ((rc = dec_cross_attn<T>(dq, d, kb, kb + d, nkv, (int64_t)nctx * nkv, datt, honor_done ? seq_state : nullptr, Wl, hp.n_text_head, d, nctx, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.co.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
             if ((rc = sk(datt, d, L.co.w, d, d, d, e))) return rc;
             tr(1, 0);
-            if ((rc = dec_ln<T>(dx, L.ln3.g, L.ln3.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, sl))) return rc;
+            if ((rc = dec_ln<T>(dx, L.ln3.g, L.ln3.b, dh, Wl, d, nullptr, nullptr, nullptr, seq_state, sl))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.fc1.b; e.act = 1; e.out16 = dmlp; e.ldo16 = 4 * d;
             if ((rc = sk(dh, d, L.fc1.w, d, 4 * d, d, e))) return rc;
             e = SkinnyEpilogue{}; e.bias = L.fc2.b; e.residual = dx; e.ldr = d; e.out32 = dx; e.ldo32 = d;
             if ((rc = sk(dmlp, 4 * d, L.fc2.w, 4 * d, d, 4 * d, e))) return rc;
         }
         tr(1, 0);
-        if ((rc = dec_ln<T>(dx, ln_f.g, ln_f.b, dh, Wl, d, nullptr, nullptr, nullptr, pos_ptr, sl))) return rc;
+        if ((rc = dec_ln<T>(dx, ln_f.g, ln_f.b, dh, Wl, d, nullptr, nullptr, nullptr, seq_state, sl))) return rc;
         // tied-embedding logits: 80-130 MB of weights per step -> the TMA-fed tcgen05 GEMM streams them
         // (one 128-row tile of sequences, ~200 column tiles) instead of the small-N weight-streaming kernel
         GemmEpilogue ge{logits, vpad, 1, nullptr, 0, nullptr, 0, 0};
         if ((rc = gemm_tn(dtype, dh, d, tok_emb, d, Wl, vpad, d, ge, sl))) return rc;
-        if (detect_lang && (rc = lang_detect_step(logits, vpad, const_cast<int*>(sa.prompt), sa.n_prompt, pos_ptr, detect_out + w0, sp, Wl, sl))) return rc;
+        if (detect_lang && (rc = lang_detect_step(logits, vpad, sa.prompt, sa.state, b_lang.as<int>() + w0, sp, Wl, sl))) return rc;
         if ((rc = sample_step(logits, vpad, sa, Wl, sl))) return rc;
-        if ((rc = dec_advance(pos_ptr, step_ptr, sa.n_prompt, sl))) return rc;
         return SB_OK;
     }
 
-    struct DecodeOut { std::vector<SeqState> state; std::vector<int> tokens; std::vector<float> margins; std::vector<int> langs; int n_max = 0; };
-    bool detect_lang = false; int* detect_out = nullptr;     // set by decode() for enqueue_step
-    bool auto_mode = false;                                  // current transcribe_batch call asked for language auto-detect
+    bool detect_lang = false;       // the current call asked for language auto-detect: k_lang_detect is part of the step
 
-    // decode W windows whose cross-KV occupies rows [0, W*1500) of b_ckv
-    // langs[w]: language id of window w's prompt, or < 0: detect it at decode position 0 (reference default "auto")
-    int decode(int W, const std::vector<int>& seek, const std::vector<int>& seek_end, const sb_params& p, const std::vector<int>& langs,
-               const int32_t* forced_host, int n_steps_cap, float* logits_out, DecodeOut& out) {
+    // ---- slots / lanes of one call ----------------------------------------------------------
+    struct DecodeCfg { SamplerArgs sa0; bool has_forced = false, graph = false, honor_done = true; int flags = 0; };
+    DecodeCfg dcfg;
+
+    int setup_slots(int S, const sb_params& p, int n_steps_cap, bool single_lane, bool has_forced, bool want_graph) {
         int n_max = hp.n_text_ctx / 2 - 4;
         if (p.n_max_tokens > 0) n_max = std::min(n_max, p.n_max_tokens);
         if (n_steps_cap > 0) n_max = std::min(n_max, n_steps_cap);
-        out.n_max = n_max;
-        int rc = ensure_decoder_ws(W, n_max);
+        int rc = ensure_decoder_ws(S, n_max);
         if (rc) return rc;
-        std::vector<int> prompt = {sp.sot};
-        if (hp.n_vocab >= 51865) { prompt.push_back(sp.lang_first); prompt.push_back(p.translate ? sp.translate : sp.transcribe); }
-        if (p.no_timestamps) prompt.push_back(sp.not_);
-        const int n_prompt = (int)prompt.size();
-        bool detect = false;
-        std::vector<int> prompts((size_t)W * n_prompt);
-        for (int w = 0; w < W; ++w) {
-            for (int i = 0; i < n_prompt; ++i) prompts[(size_t)w * n_prompt + i] = prompt[i];
-            if (n_prompt >= 2) {
-                if (langs[w] < 0) { detect = true; prompts[(size_t)w * n_prompt + 1] = -1; }     // sentinel: k_lang_detect fills it
-                else prompts[(size_t)w * n_prompt + 1] = sp.lang_first + langs[w];
-            }
+        n_slots = S; n_max_cur = n_max;
+        n_lanes = single_lane ? 1 : std::min(n_lanes_cfg, std::max(1, S / 8));
+        for (int i = 0; i < n_lanes; ++i) {
+            Lane& L = lanes[i];
+            L.s0 = (int)((int64_t)S * i / n_lanes);
+            L.n = (int)((int64_t)S * (i + 1) / n_lanes) - L.s0;
+            L.active = 0; L.steps = 0;
         }
-        if ((rc = b_prompt.ensure((size_t)W * n_prompt * 4 + (size_t)W * 4))) return rc;
-        int* d_lang = b_prompt.as<int>() + (size_t)W * n_prompt;      // detected language ids [W]
-        std::vector<SeqState> hs(W);
-        for (int w = 0; w < W; ++w) {
-            SeqState s{}; s.seek_delta = 3000; s.seek = seek[w]; s.seek_end = seek_end[w];
-            hs[w] = s;
-        }
-        SB_CUDA_CHECK(cudaMemcpyAsync(b_state.p, hs.data(), W * sizeof(SeqState), cudaMemcpyHostToDevice, st));
-        SB_CUDA_CHECK(cudaMemcpyAsync(b_prompt.p, prompts.data(), prompts.size() * 4, cudaMemcpyHostToDevice, st));
-        SB_CUDA_CHECK(cudaMemsetAsync(d_lang, 0xff, (size_t)W * 4, st));
-        SB_CUDA_CHECK(cudaMemsetAsync(b_ctr.p, 0, 64 * kMaxLanes, st));
-        SB_CUDA_CHECK(cudaMemsetAsync(b_tokens.p, 0xff, (size_t)W * n_max * 4, st));
-        SB_CUDA_CHECK(cudaMemsetAsync(b_margins.p, 0, (size_t)W * n_max * 4, st));
-        k_fill_i32<<<ceil_div(W, 256), 256, 0, st>>>(b_next.as<int>(), W, prompt[0]);
+        // every slot starts empty: done = 1, and a valid token / position so that the row-wise stages stay in bounds
+        SeqState* hs = h_state.as<SeqState>();
+        for (int s_ = 0; s_ < S; ++s_) { SeqState z{}; z.done = 1; z.n_prompt = 1; z.lang_slot = -1; hs[s_] = z; }
+        SB_CUDA_CHECK(cudaMemcpyAsync(b_state.p, hs, S * sizeof(SeqState), cudaMemcpyHostToDevice, st));
+        SB_CUDA_CHECK(cudaMemsetAsync(b_tick.p, 0, 64 * kMaxLanes, st));
+        SB_CUDA_CHECK(cudaMemsetAsync(b_tokens.p, 0xff, (size_t)S * n_max * 4, st));
+        SB_CUDA_CHECK(cudaMemsetAsync(b_margins.p, 0, (size_t)S * n_max * 4, st));
+        SB_CUDA_CHECK(cudaMemsetAsync(b_tids.p, 0, (size_t)S * n_max * 4, st));
+        SB_CUDA_CHECK(cudaMemsetAsync(b_lang.p, 0xff, (size_t)S * 4, st));
+        k_fill_i32<<<ceil_div(S, 256), 256, 0, st>>>(b_next.as<int>(), S, sp.sot);
         g_launches += 1;
-        if (forced_host) SB_CUDA_CHECK(cudaMemcpyAsync(b_forced.p, forced_host, (size_t)W * n_max * 4, cudaMemcpyHostToDevice, st));
+        SB_CUDA_CHECK(cudaStreamSynchronize(st));        // h_state is reused as the polling mirror
         SamplerArgs sa0{};
-        sa0.forced = nullptr;
-        sa0.sp = sp; sa0.n_vocab = hp.n_vocab; sa0.n_max = n_max;
+        sa0.sp = sp; sa0.n_vocab = hp.n_vocab; sa0.n_max = n_max; sa0.n_text_ctx = hp.n_text_ctx;
         sa0.suppress_blank = p.suppress_blank; sa0.no_timestamps = p.no_timestamps; sa0.single_segment = p.single_segment;
         sa0.max_initial_tid = p.max_initial_ts > 0.f ? (int)lroundf(p.max_initial_ts / (30.0f / hp.n_audio_ctx)) : -1;
-        sa0.prompt = b_prompt.as<int>(); sa0.n_prompt = n_prompt;
-        // the detect launch stays in the step graph for the whole call once auto-detect was requested (it is a no-op for
-        // sequences whose language is known), so later seek-loop rounds reuse the captured graph
-        if (detect) auto_mode = true;
-        detect = auto_mode && n_prompt >= 2;
-        detect_lang = detect; detect_out = d_lang;
-
-        const int total_steps = n_prompt - 1 + n_max;
-        const bool tracing = profile == 2 && !logits_out;
-        const bool graph = use_graph && !logits_out;
-        // launch trace: [lane][start | end][step][launch] globaltimer stamps, reset per decode() call
+        dcfg.sa0 = sa0; dcfg.has_forced = has_forced; dcfg.graph = want_graph; dcfg.honor_done = !has_forced;
+        const bool tracing = profile == 2 && want_graph;
+        dcfg.flags = (p.suppress_blank ? 1 : 0) | (p.no_timestamps ? 2 : 0) | (p.single_segment ? 4 : 0) | (detect_lang ? 8 : 0) | (tracing ? 16 : 0);
+        // launch trace: [lane][start | end][step][launch] globaltimer stamps, reset per call
         trace_per_step = 0;
         if (tracing) {
             trace_per_step = 11 * hp.n_text_layer + 1;
-            trace_max_steps = total_steps;
+            trace_max_steps = 4096;
             const size_t n = (size_t)trace_max_steps * trace_per_step;
             if ((rc = b_trace.ensure((size_t)kMaxLanes * 2 * n * 8))) return rc;
             for (int i = 0; i < kMaxLanes; ++i) {
@@ -638,151 +664,202 @@ struct Engine : EngineBase {
                 SB_CUDA_CHECK(cudaMemsetAsync(b_trace.as<unsigned long long>() + (size_t)i * 2 * n + n, 0, n * 8, st));
             }
         }
-        // lanes: independent sub-batches on their own streams (one lane when tracing logits)
-        int n_lanes = logits_out ? 1 : std::min(n_lanes_cfg, std::max(1, W / 8));
-        struct LaneRun { int w0, Wl; bool finished; int steps; };
-        std::vector<LaneRun> lr(n_lanes);
-        for (int i = 0; i < n_lanes; ++i) {
-            const int w0 = (int)((int64_t)W * i / n_lanes), w1 = (int)((int64_t)W * (i + 1) / n_lanes);
-            lr[i] = LaneRun{w0, w1 - w0, false, 0};
-        }
-        auto lane_args = [&](int i) {
-            SamplerArgs sa = sa0;
-            const int w0 = lr[i].w0;
-            int* ctr = b_ctr.as<int>() + 16 * i;
-            sa.state = b_state.as<SeqState>() + w0;
-            sa.step_ptr = ctr + 1;
-            sa.tokens_out = b_tokens.as<int>() + (size_t)w0 * n_max;
-            sa.margins_out = b_margins.as<float>() + (size_t)w0 * n_max;
-            sa.next_tokens = b_next.as<int>() + w0;
-            sa.forced = forced_host ? b_forced.as<int>() + (size_t)w0 * n_max : nullptr;
-            sa.n_done = ctr + 2;
-            sa.pos_ptr = ctr;
-            sa.prompt = b_prompt.as<int>() + (size_t)w0 * n_prompt;
-            return sa;
-        };
         // fork: every lane stream waits for the setup work queued on the main stream
         SB_CUDA_CHECK(cudaEventRecord(ev_fork, st));
         for (int i = 0; i < n_lanes; ++i) SB_CUDA_CHECK(cudaStreamWaitEvent(lanes[i].st, ev_fork, 0));
-        if (graph) {
-            for (int i = 0; i < n_lanes; ++i) {
-                Lane& L = lanes[i];
-                GraphKey k{W, lr[i].w0, lr[i].Wl, n_max,
-                           (p.suppress_blank ? 1 : 0) | (p.no_timestamps ? 2 : 0) | (p.single_segment ? 4 : 0) | (detect ? 8 : 0) | (tracing ? 16 : 0),
-                           sa0.max_initial_tid, n_prompt, forced_host ? 1 : 0, g_ws_gen.load()};
-                if (L.gexec && k == L.key) continue;
-                if (L.gexec) { cudaGraphExecDestroy(L.gexec); L.gexec = nullptr; }
-                cudaGraph_t g = nullptr;
-                const uint64_t l0 = g_launches.load();
-                SB_CUDA_CHECK(cudaStreamBeginCapture(L.st, cudaStreamCaptureModeThreadLocal));
-                rc = enqueue_step(W, lr[i].w0, lr[i].Wl, b_ctr.as<int>() + 16 * i, L.st, lane_args(i));
-                cudaError_t ce = cudaStreamEndCapture(L.st, &g);
-                L.graph_nodes = (int)(g_launches.load() - l0);
-                g_launches -= (uint64_t)L.graph_nodes;      // captured, not executed
-                if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-                if (ce != cudaSuccess) { set_error(std::string("graph capture: ") + cudaGetErrorString(ce)); return SB_ERR_CUDA; }
-                ce = cudaGraphInstantiate(&L.gexec, g, 0);
-                cudaGraphDestroy(g);
-                if (ce != cudaSuccess) { L.gexec = nullptr; set_error(std::string("graph instantiate: ") + cudaGetErrorString(ce)); return SB_ERR_CUDA; }
-                L.key = k;
-            }
+        if (want_graph)
+            for (int i = 0; i < n_lanes; ++i) if ((rc = ensure_graph(i))) return rc;
+        return SB_OK;
+    }
+
+    SamplerArgs lane_args(int li) const {
+        SamplerArgs sa = dcfg.sa0;
+        const int w0 = lanes[li].s0;
+        sa.state = b_state.as<SeqState>() + w0;
+        sa.tokens_out = b_tokens.as<int>() + (size_t)w0 * n_max_cur;
+        sa.margins_out = b_margins.as<float>() + (size_t)w0 * n_max_cur;
+        sa.tids_out = b_tids.as<int>() + (size_t)w0 * n_max_cur;
+        sa.next_tokens = b_next.as<int>() + w0;
+        sa.forced = dcfg.has_forced ? b_forced.as<int>() + (size_t)w0 * n_max_cur : nullptr;
+        sa.tick = b_tick.as<int>() + 16 * li;
+        sa.prompt = b_prompt.as<int>() + (size_t)w0 * kMaxPrompt;
+        return sa;
+    }
+
+    int ensure_graph(int li) {
+        Lane& L = lanes[li];
+        GraphKey k{n_slots, L.s0, L.n, n_max_cur, dcfg.flags, dcfg.sa0.max_initial_tid, dcfg.has_forced ? 1 : 0, g_ws_gen.load()};
+        if (L.gexec && k == L.key) return SB_OK;
+        if (L.gexec) { cudaGraphExecDestroy(L.gexec); L.gexec = nullptr; }
+        cudaGraph_t g = nullptr;
+        const uint64_t l0 = g_launches.load();
+        SB_CUDA_CHECK(cudaStreamBeginCapture(L.st, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_step(li, lane_args(li), dcfg.honor_done);
+        cudaError_t ce = cudaStreamEndCapture(L.st, &g);
+        L.graph_nodes = (int)(g_launches.load() - l0);
+        g_launches -= (uint64_t)L.graph_nodes;      // captured, not executed
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (ce != cudaSuccess) { set_error(std::string("graph capture: ") + cudaGetErrorString(ce)); return SB_ERR_CUDA; }
+        ce = cudaGraphInstantiate(&L.gexec, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) { L.gexec = nullptr; set_error(std::string("graph instantiate: ") + cudaGetErrorString(ce)); return SB_ERR_CUDA; }
+        L.key = k;
+        return SB_OK;
+    }
+
+    int run_steps(int li, int k) {
+        Lane& L = lanes[li];
+        int rc;
+        for (int b = 0; b < k; ++b) {
+            if (dcfg.graph) { SB_CUDA_CHECK(cudaGraphLaunch(L.gexec, L.st)); g_launches += (uint64_t)L.graph_nodes; }
+            else if ((rc = enqueue_step(li, lane_args(li), dcfg.honor_done))) return rc;
         }
-        int active = n_lanes;
-        while (active > 0) {
-            for (int i = 0; i < n_lanes; ++i) {
-                if (lr[i].finished) continue;
-                Lane& L = lanes[i];
-                const int burst = logits_out ? 1 : std::min(8, total_steps - lr[i].steps);
-                for (int b = 0; b < burst; ++b) {
-                    if (graph) { SB_CUDA_CHECK(cudaGraphLaunch(L.gexec, L.st)); g_launches += (uint64_t)L.graph_nodes; }
-                    else if ((rc = enqueue_step(W, lr[i].w0, lr[i].Wl, b_ctr.as<int>() + 16 * i, L.st, lane_args(i)))) return rc;
-                }
-                if (logits_out && lr[i].steps >= n_prompt - 1) {
-                    const int sidx = lr[i].steps - (n_prompt - 1);
-                    for (int w = 0; w < W; ++w)
-                        SB_CUDA_CHECK(cudaMemcpyAsync(logits_out + ((size_t)w * n_max + sidx) * hp.n_vocab,
-                                                      b_logits.as<float>() + (size_t)w * round_up(hp.n_vocab, 8), (size_t)hp.n_vocab * 4,
-                                                      cudaMemcpyDeviceToHost, L.st));
-                }
-                lr[i].steps += burst;
-                stats.decoder_steps += (double)burst * lr[i].Wl / W; stats.d2h_bytes += 16;
-                SB_CUDA_CHECK(cudaMemcpyAsync(h_ctr + 16 * i, b_ctr.as<int>() + 16 * i, 16, cudaMemcpyDeviceToHost, L.st));
-            }
-            for (int i = 0; i < n_lanes; ++i) {
-                if (lr[i].finished) continue;
-                SB_CUDA_CHECK(cudaStreamSynchronize(lanes[i].st));
-                if (h_ctr[16 * i + 2] >= lr[i].Wl || lr[i].steps >= total_steps) { lr[i].finished = true; --active; }
-            }
+        L.steps += k;
+        stats.decoder_steps += (double)k * L.n / n_slots;
+        return SB_OK;
+    }
+
+    // D2H of the lane's state / token rows into the pinned mirrors (async on the lane's stream)
+    int poll_lane(int li) {
+        const Lane& L = lanes[li];
+        const size_t o = (size_t)L.s0 * n_max_cur, nb = (size_t)L.n * n_max_cur * 4;
+        SB_CUDA_CHECK(cudaMemcpyAsync(h_state.as<SeqState>() + L.s0, b_state.as<SeqState>() + L.s0, L.n * sizeof(SeqState), cudaMemcpyDeviceToHost, L.st));
+        SB_CUDA_CHECK(cudaMemcpyAsync(h_tokens.as<int>() + o, b_tokens.as<int>() + o, nb, cudaMemcpyDeviceToHost, L.st));
+        SB_CUDA_CHECK(cudaMemcpyAsync(h_margins.as<float>() + o, b_margins.as<float>() + o, nb, cudaMemcpyDeviceToHost, L.st));
+        SB_CUDA_CHECK(cudaMemcpyAsync(h_tids.as<int>() + o, b_tids.as<int>() + o, nb, cudaMemcpyDeviceToHost, L.st));
+        SB_CUDA_CHECK(cudaMemcpyAsync(h_lang.as<int>() + L.s0, b_lang.as<int>() + L.s0, L.n * 4, cudaMemcpyDeviceToHost, L.st));
+        stats.d2h_bytes += (double)L.n * (sizeof(SeqState) + 4) + 3.0 * nb;
+        return SB_OK;
+    }
+
+    // one window assigned to a decode slot
+    struct WinJob {
+        int clip = 0, slot = 0, seek = 0, seek_end = 0;
+        std::vector<int> prompt;      // full decoder prompt (language slot = -1 when it is to be detected)
+        int lang_slot = -1, restart = 0;
+    };
+
+    // whisper_full's prompt of one window: [prev] + the last <= n_text_ctx/2 tokens of prompt_past (text context of this
+    // call: initial_prompt tokens, then the kept tokens of the previous windows) + [sot, lang, task] (+ [notimestamps])
+    void build_prompt(WinJob& j, const std::vector<int>& prompt_past, int lang, const sb_params& p) const {
+        j.prompt.clear();
+        const int n_ctx_max = p.n_max_text_ctx;
+        if (!prompt_past.empty() && n_ctx_max > 0) {       // (temperature is 0 here: whisper.cpp requires t_cur < 0.5)
+            const int n_take = std::min(std::min(n_ctx_max, hp.n_text_ctx / 2), (int)prompt_past.size());
+            j.prompt.push_back(sp.prev);
+            j.prompt.insert(j.prompt.end(), prompt_past.end() - n_take, prompt_past.end());
         }
-        // join: the main stream continues after every lane
+        const bool multilingual = hp.n_vocab >= 51865;
+        const bool prefixed = !j.prompt.empty();
+        j.prompt.push_back(sp.sot);
+        j.lang_slot = -1; j.restart = 0;
+        if (multilingual) {
+            j.lang_slot = (int)j.prompt.size();
+            j.prompt.push_back(lang >= 0 ? sp.lang_first + lang : -1);
+            j.prompt.push_back(p.translate ? sp.translate : sp.transcribe);
+        }
+        if (p.no_timestamps) j.prompt.push_back(sp.not_);
+        if (multilingual && lang < 0 && prefixed) {        // detect on [sot] alone, then restart at position 0
+            j.prompt.insert(j.prompt.begin(), sp.sot);
+            j.lang_slot += 1; j.restart = 1;
+        }
+    }
+
+    // scatter the jobs into their slots: staged per lane in pinned memory, copied and applied on the lane's own stream
+    // (in order with the lane's steps, after the encoder's cross-KV for these slots is complete: ev_enc)
+    int init_slots(const std::vector<WinJob>& jobs) {
+        SlotInit* hi = h_init.as<SlotInit>();
+        int rc;
+        for (int li = 0; li < n_lanes; ++li) {
+            Lane& L = lanes[li];
+            int cnt = 0;
+            for (const WinJob& j : jobs) {
+                if (j.slot < L.s0 || j.slot >= L.s0 + L.n) continue;
+                SlotInit& it = hi[L.s0 + cnt];
+                memset(&it, 0, sizeof(it));
+                it.slot = j.slot;
+                it.next_token = j.prompt[0];
+                SeqState s{};
+                s.seek_delta = 3000; s.seek = j.seek; s.seek_end = j.seek_end;
+                s.n_prompt = (int)j.prompt.size(); s.lang_slot = j.lang_slot; s.restart = j.restart;
+                it.state = s;
+                for (size_t k = 0; k < j.prompt.size(); ++k) it.prompt[k] = j.prompt[k];
+                ++cnt;
+            }
+            if (!cnt) continue;
+            SB_CUDA_CHECK(cudaStreamWaitEvent(L.st, ev_enc, 0));
+            SB_CUDA_CHECK(cudaMemcpyAsync(b_init.as<SlotInit>() + L.s0, hi + L.s0, cnt * sizeof(SlotInit), cudaMemcpyHostToDevice, L.st));
+            if ((rc = slot_init(b_init.as<SlotInit>() + L.s0, cnt, b_state.as<SeqState>(), b_next.as<int>(), b_prompt.as<int>(),
+                                b_lang.as<int>(), L.st))) return rc;
+            L.active += cnt;
+            stats.h2d_bytes += (double)cnt * sizeof(SlotInit);
+        }
+        return SB_OK;
+    }
+
+    // join: the main stream continues after every lane
+    int join_lanes() {
         for (int i = 0; i < n_lanes; ++i) {
             SB_CUDA_CHECK(cudaEventRecord(lanes[i].done, lanes[i].st));
             SB_CUDA_CHECK(cudaStreamWaitEvent(st, lanes[i].done, 0));
         }
-        out.state.resize(W); out.tokens.resize((size_t)W * n_max); out.margins.resize((size_t)W * n_max);
-        out.langs.assign(W, -1);
-        if (detect) SB_CUDA_CHECK(cudaMemcpyAsync(out.langs.data(), d_lang, (size_t)W * 4, cudaMemcpyDeviceToHost, st));     // -1 where nothing was detected
-        SB_CUDA_CHECK(cudaMemcpyAsync(out.state.data(), b_state.p, W * sizeof(SeqState), cudaMemcpyDeviceToHost, st));
-        SB_CUDA_CHECK(cudaMemcpyAsync(out.tokens.data(), b_tokens.p, (size_t)W * n_max * 4, cudaMemcpyDeviceToHost, st));
-        SB_CUDA_CHECK(cudaMemcpyAsync(out.margins.data(), b_margins.p, (size_t)W * n_max * 4, cudaMemcpyDeviceToHost, st));
-        SB_CUDA_CHECK(cudaStreamSynchronize(st));
-        if (tracing) {
-            const size_t n = (size_t)trace_max_steps * trace_per_step;
-            std::vector<unsigned long long> ht((size_t)n_lanes * 2 * n);
-            SB_CUDA_CHECK(cudaMemcpy(ht.data(), b_trace.p, ht.size() * 8, cudaMemcpyDeviceToHost));
-            for (int i = 0; i < n_lanes; ++i) {
-                const unsigned long long* t0 = ht.data() + (size_t)i * 2 * n;
-                const unsigned long long* t1 = t0 + n;
-                for (int sI = 0; sI < lr[i].steps && sI < trace_max_steps; ++sI) {
-                    unsigned long long first = ~0ull, last = 0;
-                    for (int k = 0; k < trace_per_step && k < (int)trace_cls.size(); ++k) {
-                        const unsigned long long a = t0[(size_t)sI * trace_per_step + k], b = t1[(size_t)sI * trace_per_step + k];
-                        if (a == ~0ull || b <= a) continue;          // never ran (every block skipped) or clock wrap
-                        const double ms = (double)(b - a) * 1e-6;
-                        first = std::min(first, a); last = std::max(last, b);
-                        switch (trace_cls[k]) {
-                            case 0: stats.skinny_ms += ms; stats.skinny_bytes += trace_work[k]; stats.skinny_launches += 1; break;
-                            case 1: stats.dln_ms += ms; stats.dln_launches += 1; break;
-                            case 2: stats.dself_ms += ms; stats.dself_launches += 1; break;
-                            default: stats.xattn_ms += ms; stats.xattn_launches += 1; break;
-                        }
-                    }
-                    if (last > first) { stats.dstep_ms += (double)(last - first) * 1e-6; stats.dstep_count += 1; }
-                    if (last > first && getenv("SB_TRACE_DUMP")) {    // per-index timeline relative to the lane-step's first start
-                        if ((int)trace_cnt.size() < trace_per_step) {
-                            trace_sum_dur.assign(trace_per_step, 0.0); trace_sum_t0.assign(trace_per_step, 0.0);
-                            trace_sum_t1.assign(trace_per_step, 0.0); trace_cnt.assign(trace_per_step, 0.0);
-                        }
-                        for (int k = 0; k < trace_per_step && k < (int)trace_cls.size(); ++k) {
-                            const unsigned long long a = t0[(size_t)sI * trace_per_step + k], b = t1[(size_t)sI * trace_per_step + k];
-                            if (a == ~0ull || b <= a) continue;
-                            trace_sum_dur[k] += (double)(b - a); trace_sum_t0[k] += (double)(a - first);
-                            trace_sum_t1[k] += (double)(b - first); trace_cnt[k] += 1;
-                        }
-                    }
-                }
-            }
-            if (const char* dump = getenv("SB_TRACE_DUMP")) {
-                if (FILE* f = fopen(dump, "w")) {
-                    fprintf(f, "idx,class,work_bytes,count,avg_us,avg_start_us,avg_end_us\n");
-                    for (int k = 0; k < (int)trace_cnt.size() && k < (int)trace_cls.size(); ++k)
-                        if (trace_cnt[k] > 0)
-                            fprintf(f, "%d,%d,%.0f,%.0f,%.3f,%.3f,%.3f\n", k, trace_cls[k], trace_work[k], trace_cnt[k],
-                                    trace_sum_dur[k] / trace_cnt[k] * 1e-3, trace_sum_t0[k] / trace_cnt[k] * 1e-3, trace_sum_t1[k] / trace_cnt[k] * 1e-3);
-                    fclose(f);
-                }
-            }
-            // cross-attention bytes: a sequence with n_tok sampled tokens was live for n_prompt + n_tok - 1 steps
-            for (int w = 0; w < W; ++w)
-                stats.xattn_bytes += (double)(n_prompt + std::max(out.state[w].n_tok, 1) - 1) * hp.n_text_layer * 4.0 * hp.n_audio_ctx * hp.n_text_state;
-        }
-        stats.d2h_bytes += (double)W * (sizeof(SeqState) + 8.0 * n_max);
-        stats.h2d_bytes += (double)W * sizeof(SeqState) + 4.0 * n_prompt;
         return SB_OK;
     }
 
+    // profile == 2: fold the device-side launch trace of this call into the stats (stream idle)
+    int collect_trace() {
+        if (!(profile == 2 && trace_per_step > 0)) return SB_OK;
+        const size_t n = (size_t)trace_max_steps * trace_per_step;
+        std::vector<unsigned long long> ht((size_t)n_lanes * 2 * n);
+        SB_CUDA_CHECK(cudaMemcpy(ht.data(), b_trace.p, ht.size() * 8, cudaMemcpyDeviceToHost));
+        const bool dump = getenv("SB_TRACE_DUMP") != nullptr;
+        for (int i = 0; i < n_lanes; ++i) {
+            const unsigned long long* t0 = ht.data() + (size_t)i * 2 * n;
+            const unsigned long long* t1 = t0 + n;
+            for (int sI = 0; sI < lanes[i].steps && sI < trace_max_steps; ++sI) {
+                unsigned long long first = ~0ull, last = 0;
+                for (int k = 0; k < trace_per_step && k < (int)trace_cls.size(); ++k) {
+                    const unsigned long long a = t0[(size_t)sI * trace_per_step + k], b = t1[(size_t)sI * trace_per_step + k];
+                    if (a == ~0ull || b <= a) continue;          // never ran (every block skipped) or clock wrap
+                    const double ms = (double)(b - a) * 1e-6;
+                    first = std::min(first, a); last = std::max(last, b);
+                    switch (trace_cls[k]) {
+                        case 0: stats.skinny_ms += ms; stats.skinny_bytes += trace_work[k]; stats.skinny_launches += 1; break;
+                        case 1: stats.dln_ms += ms; stats.dln_launches += 1; break;
+                        case 2: stats.dself_ms += ms; stats.dself_launches += 1; break;
+                        default: stats.xattn_ms += ms; stats.xattn_launches += 1; break;
+                    }
+                }
+                if (last > first) { stats.dstep_ms += (double)(last - first) * 1e-6; stats.dstep_count += 1; }
+                if (last > first && dump) {    // per-index timeline relative to the lane-step's first start
+                    if ((int)trace_cnt.size() < trace_per_step) {
+                        trace_sum_dur.assign(trace_per_step, 0.0); trace_sum_t0.assign(trace_per_step, 0.0);
+                        trace_sum_t1.assign(trace_per_step, 0.0); trace_cnt.assign(trace_per_step, 0.0);
+                    }
+                    for (int k = 0; k < trace_per_step && k < (int)trace_cls.size(); ++k) {
+                        const unsigned long long a = t0[(size_t)sI * trace_per_step + k], b = t1[(size_t)sI * trace_per_step + k];
+                        if (a == ~0ull || b <= a) continue;
+                        trace_sum_dur[k] += (double)(b - a); trace_sum_t0[k] += (double)(a - first);
+                        trace_sum_t1[k] += (double)(b - first); trace_cnt[k] += 1;
+                    }
+                }
+            }
+        }
+        if (const char* path = getenv("SB_TRACE_DUMP")) {
+            if (FILE* f = fopen(path, "w")) {
+                fprintf(f, "idx,class,work_bytes,count,avg_us,avg_start_us,avg_end_us\n");
+                for (int k = 0; k < (int)trace_cnt.size() && k < (int)trace_cls.size(); ++k)
+                    if (trace_cnt[k] > 0)
+                        fprintf(f, "%d,%d,%.0f,%.0f,%.3f,%.3f,%.3f\n", k, trace_cls[k], trace_work[k], trace_cnt[k],
+                                trace_sum_dur[k] / trace_cnt[k] * 1e-3, trace_sum_t0[k] / trace_cnt[k] * 1e-3, trace_sum_t1[k] / trace_cnt[k] * 1e-3);
+                fclose(f);
+            }
+        }
+        return SB_OK;
+    }
+
+    // language / initial prompt of a call.  *lang = -1: detect (reference default "auto")
     int resolve_language(const sb_params& p, int* lang) {
-        if (p.initial_prompt && p.initial_prompt[0]) { set_error("initial_prompt is not implemented yet (needs the BPE encoder)"); return SB_ERR_UNSUPPORTED; }
         // NULL / "" / "auto": whisper_full detects the language on the first window (multilingual models);
         // English-only models have no language token at all
         if (!p.language || !p.language[0] || std::string(p.language) == "auto") { *lang = hp.n_vocab >= 51865 ? -1 : 0; return SB_OK; }
@@ -790,8 +867,14 @@ struct Engine : EngineBase {
         if (l == "zh-Hans" || l == "zh-Hant") l = "zh";   // reference: transcription.rs:448-459
         const int id = lang_id(l.c_str());
         if (id < 0 || (hp.n_vocab >= 51865 && id >= sp.num_languages)) { set_error("unknown language code: " + l); return SB_ERR_INVALID; }
+        if (hp.n_vocab < 51865 && id != 0) { set_error("English-only model: language must be \"en\" or auto, got " + l); return SB_ERR_INVALID; }
         *lang = id;
         return SB_OK;
+    }
+    // WhisperInferenceParams::initial_prompt (transcription.rs:461-499) -> whisper.cpp tokenises it into prompt_past
+    std::vector<int> initial_prompt_tokens(const sb_params& p) const {
+        if (!p.initial_prompt || !p.initial_prompt[0]) return {};
+        return tokenize(p.initial_prompt);
     }
 
     // im2col of the mel windows given as a host array [W][n_mel][3000] (parity hooks)
@@ -817,11 +900,12 @@ struct Engine : EngineBase {
     int encode_host(const float* mel_windows, int W, float* enc_out) override {
         SB_CHECK_ARG(mel_windows && enc_out && W > 0 && W <= max_batch, "sb_encode: bad arguments (n_windows <= max_batch)");
         SB_CUDA_CHECK(cudaSetDevice(device));
-        int rc = ensure_encoder_ws(W, W, true);
+        int rc = ensure_encoder_ws(W, true);
         if (rc) return rc;
+        if ((rc = b_ckv.ensure((size_t)W * hp.n_audio_ctx * hp.n_text_layer * 2 * hp.n_text_state * 2))) return rc;
         if ((rc = stage_mel_windows(mel_windows, W))) return rc;
         SB_CUDA_CHECK(cudaEventRecord(ev[0], st));
-        if ((rc = encode_chunk(W, 0, b_enc32.as<float>()))) return rc;
+        if ((rc = encode_chunk(W, nullptr, b_enc32.as<float>()))) return rc;
         SB_CUDA_CHECK(cudaEventRecord(ev[1], st));
         SB_CUDA_CHECK(cudaMemcpyAsync(enc_out, b_enc32.p, (size_t)W * hp.n_audio_ctx * hp.n_audio_state * 4, cudaMemcpyDeviceToHost, st));
         SB_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -830,52 +914,134 @@ struct Engine : EngineBase {
         return SB_OK;
     }
 
+    // parity hook: encode W windows, then n_steps decoder steps from the window prompt, optionally teacher-forced, with
+    // the raw logits of every sampling step copied out
     int decode_trace(const float* mel_windows, int W, const int32_t* seek_end, const sb_params& p, const int32_t* forced,
                      int n_steps, float* logits_out, int32_t* tokens_out, float* margins_out) override {
         SB_CHECK_ARG(mel_windows && seek_end && tokens_out && W > 0 && W <= max_batch && n_steps > 0, "sb_decode_trace: bad arguments");
+        SB_CHECK_ARG(n_steps <= hp.n_text_ctx / 2 - 4 && (p.n_max_tokens <= 0 || p.n_max_tokens >= n_steps), "n_steps exceeds n_text_ctx/2 - 4");
         SB_CUDA_CHECK(cudaSetDevice(device));
         int lang = 0;
         int rc = resolve_language(p, &lang);
         if (rc) return rc;
-        auto_mode = lang < 0;
-        if ((rc = ensure_encoder_ws(W, W, false))) return rc;
+        detect_lang = lang < 0;
+        const std::vector<int> past = initial_prompt_tokens(p);
+        if ((rc = ensure_encoder_ws(W, false))) return rc;
+        if ((rc = setup_slots(W, p, n_steps, logits_out != nullptr, forced != nullptr, use_graph && !logits_out))) return rc;
         if ((rc = stage_mel_windows(mel_windows, W))) return rc;
-        if ((rc = encode_chunk(W, 0, nullptr))) return rc;
-        std::vector<int> seek(W, 0), se(seek_end, seek_end + W);
-        DecodeOut out;
-        if ((rc = decode(W, seek, se, p, std::vector<int>(W, lang), forced, n_steps, logits_out, out))) return rc;
+        if ((rc = encode_chunk(W, nullptr, nullptr))) return rc;
+        if (forced) SB_CUDA_CHECK(cudaMemcpyAsync(b_forced.p, forced, (size_t)W * n_steps * 4, cudaMemcpyHostToDevice, st));
+        SB_CUDA_CHECK(cudaEventRecord(ev_enc, st));
+        std::vector<WinJob> jobs(W);
+        for (int w = 0; w < W; ++w) {
+            jobs[w].clip = w; jobs[w].slot = w; jobs[w].seek = 0; jobs[w].seek_end = seek_end[w];
+            build_prompt(jobs[w], past, lang, p);
+        }
+        if ((rc = init_slots(jobs))) return rc;
+        const int feed = (int)jobs[0].prompt.size() - 1;         // the prompt is the same for every window here
+        const int total_steps = feed + n_steps;
+        const int vpad = (int)round_up(hp.n_vocab, 8);
+        if (logits_out) {
+            for (int s_ = 0; s_ < total_steps; ++s_) {
+                if ((rc = run_steps(0, 1))) return rc;
+                if (s_ >= feed)
+                    for (int w = 0; w < W; ++w)
+                        SB_CUDA_CHECK(cudaMemcpyAsync(logits_out + ((size_t)w * n_steps + (s_ - feed)) * hp.n_vocab,
+                                                      b_logits.as<float>() + (size_t)w * vpad, (size_t)hp.n_vocab * 4,
+                                                      cudaMemcpyDeviceToHost, lanes[0].st));
+            }
+        } else {
+            for (int li = 0; li < n_lanes; ++li) if ((rc = run_steps(li, total_steps))) return rc;
+        }
+        for (int li = 0; li < n_lanes; ++li) if ((rc = poll_lane(li))) return rc;
+        if ((rc = join_lanes())) return rc;
+        SB_CUDA_CHECK(cudaStreamSynchronize(st));
         prof_collect();
-        if (out.n_max != n_steps) { set_error("n_steps exceeds n_text_ctx/2 - 4"); return SB_ERR_INVALID; }
-        memcpy(tokens_out, out.tokens.data(), (size_t)W * n_steps * 4);
-        if (margins_out) memcpy(margins_out, out.margins.data(), (size_t)W * n_steps * 4);
+        memcpy(tokens_out, h_tokens.p, (size_t)W * n_steps * 4);
+        if (margins_out) memcpy(margins_out, h_margins.p, (size_t)W * n_steps * 4);
         return SB_OK;
     }
 
-    // ---- whisper_full over a group of <= max_batch clips -------------------------------------
+    // ---- whisper_full over a group of clips ---------------------------------------------------
+    struct Segment { int64_t t0, t1; std::string text; int tok_off, n_tok; };
     struct ClipRun {
         size_t n = 0; int n_len = 0, n_len_org = 0, n_calc = 0;
-        int seek = 0; bool active = false; int lang = 0;
-        std::vector<int32_t> kept, sampled; std::vector<float> margins; std::vector<sb_window_info> windows;
+        int seek = 0; bool active = false, running = false; int lang = 0;
+        std::vector<int> prompt_past;         // whisper_full's prompt_past of this call
+        std::vector<int32_t> kept, sampled, tids; std::vector<float> margins; std::vector<sb_window_info> windows;
+        std::vector<Segment> segments;
         std::string text;
     };
+
+    // one finished window: whisper_full's per-window epilogue (tokens_cur.resize(result_len), segments at timestamp
+    // tokens, prompt_past update, seek += seek_delta)
+    void finish_window(ClipRun& r, const WinJob& j, const SeqState& s, const int* toks, const float* margs, const int* tids,
+                       const sb_params& p) {
+        sb_window_info wi{};
+        wi.seek = r.seek; wi.n_tokens = s.n_tok; wi.result_len = s.result_len; wi.seek_delta = s.seek_delta;
+        wi.failed = s.failed; wi.token_offset = (int)r.sampled.size();
+        wi.n_prompt = (int)j.prompt.size() - j.restart;
+        const int kept0 = (int)r.kept.size();
+        for (int i = 0; i < s.n_tok; ++i) {
+            r.sampled.push_back(toks[i]); r.margins.push_back(margs[i]); r.tids.push_back(tids[i]);
+            if (i < s.result_len) { r.kept.push_back(toks[i]); if (toks[i] < sp.eot) r.text += token_text(toks[i]); }
+        }
+        r.windows.push_back(wi);
+        // segments (whisper_full_with_state): text between timestamp tokens; the first segment starts at the most
+        // probable timestamp of the first token (tid), an unterminated tail ends at seek + seek_delta
+        const int n = std::min(s.result_len, s.n_tok);
+        if (n > 0) {
+            int i0 = 0;
+            int64_t t0 = r.seek + 2 * (int64_t)(tids[0] - sp.beg);
+            std::string text;
+            for (int i = 0; i < n; ++i) {
+                if (toks[i] < sp.eot) text += token_text(toks[i]);
+                if (toks[i] > sp.beg && !p.single_segment) {
+                    const int64_t t1 = r.seek + 2 * (int64_t)(tids[i] - sp.beg);
+                    if (!text.empty()) r.segments.push_back(Segment{t0, t1, text, kept0 + i0, i - i0 + 1});
+                    text.clear();
+                    while (i < n && toks[i] > sp.beg) ++i;
+                    --i;
+                    t0 = t1; i0 = i + 1;
+                }
+            }
+            if (!text.empty()) r.segments.push_back(Segment{t0, (int64_t)r.seek + s.seek_delta, text, kept0 + i0, n - i0});
+        }
+        // prompt_past = the context this window actually used + its kept tokens
+        std::vector<int> np;
+        const int lead = j.restart;
+        if ((int)j.prompt.size() > lead && j.prompt[lead] == sp.prev) {
+            const int n_init = 1 + (hp.n_vocab >= 51865 ? 2 : 0) + (p.no_timestamps ? 1 : 0);
+            np.assign(j.prompt.begin() + lead + 1, j.prompt.end() - n_init);
+        }
+        for (int i = 0; i < n; ++i) np.push_back(toks[i]);
+        r.prompt_past.swap(np);
+        r.seek += s.seek_delta;
+        stats.tokens_sampled += (double)s.n_tok;
+        if (profile == 2)   // cross-attention bytes: the sequence was live for every fed prompt token and every sampled token
+            stats.xattn_bytes += (double)((int)j.prompt.size() + std::max(s.n_tok, 1) - 1) * hp.n_text_layer * 4.0 * hp.n_audio_ctx * hp.n_text_state;
+    }
 
     int run_group(const float* const* pcm, const size_t* ns, int G, const sb_params& p, int lang, sb_result* out) {
         const int n_mel = hp.n_mels;
         std::vector<ClipRun> clips(G);
-        size_t max_n = 0; int max_calc = 0; bool uniform = true;
+        const std::vector<int> init_past = initial_prompt_tokens(p);
+        size_t max_n = 0; int max_calc = 0; bool uniform = true; int n_active = 0;
         for (int c = 0; c < G; ++c) {
             ClipRun& r = clips[c];
             r.n = ns[c];
             r.lang = lang;
+            r.prompt_past = init_past;
             if (r.n == 0) continue;
             sb_logmel_geometry(r.n, &r.n_len, &r.n_len_org, &r.n_calc);
             // whisper.cpp: "input is too short" below 1 s -> no segments
             r.active = r.n >= 201 && r.n_len_org >= 100;
             if (!r.active) continue;
+            ++n_active;
             max_n = std::max(max_n, r.n); max_calc = std::max(max_calc, r.n_calc);
         }
         for (int c = 0; c < G; ++c) if (clips[c].active && clips[c].n != max_n) uniform = false;
-        float ms_mel = 0.f, ms_enc = 0.f, ms_dec = 0.f;
+        float ms_mel = 0.f, ms_enc = 0.f, ms_total = 0.f;
         int rc;
         if (max_n > 0) {
             const int stride = (int)round_up(max_calc, 32);
@@ -884,7 +1050,10 @@ struct Engine : EngineBase {
             if ((rc = b_cmax.ensure(G * 4))) return rc;
             if ((rc = b_floor.ensure(G * 4))) return rc;
             if ((rc = b_clipmeta.ensure(G * 2 * 4))) return rc;
-            if ((rc = b_winmeta.ensure(G * 2 * 4))) return rc;
+            const int S = std::min(max_batch, n_active);
+            if ((rc = b_winmeta.ensure(std::max(G, S) * 2 * 4))) return rc;
+            if ((rc = h_winmeta.ensure(S * 2 * 4))) return rc;
+            if ((rc = ensure_encoder_ws(S, false))) return rc;
             SB_CUDA_CHECK(cudaEventRecord(ev[0], st));
             std::vector<int> meta(2 * G, 0);
             for (int c = 0; c < G; ++c) {
@@ -912,53 +1081,118 @@ struct Engine : EngineBase {
             SB_CUDA_CHECK(cudaStreamSynchronize(st));   // meta vector lifetime + mel timing
             { float t; cudaEventElapsedTime(&t, ev[0], ev[1]); ms_mel += t; }
 
-            // seek loop: every round encodes + decodes one window of every clip that still has audio
+            // ---- the seek loop of every clip, scheduled over S decode slots -------------------------------------
+            // A clip's next window becomes READY when its previous one ends (seek and text context depend on it).  Ready
+            // windows are encoded in batches on the main stream while the lanes keep stepping the live slots; a batch
+            // is started once `refill_min` slots are free (or nothing is running), and its windows enter their slots
+            // as soon as the encoder is done.  Sequences are independent, so the schedule does not change any result.
+            if ((rc = setup_slots(S, p, 0, false, false, use_graph != 0))) return rc;
+            const int refill_min = refill_min_cfg > 0 ? refill_min_cfg : std::max(1, S / 8);
             const int max_windows = p.max_windows > 0 ? p.max_windows : 1 << 20;
-            for (;;) {
-                std::vector<int> wclip, wseek, wend, wlang;
-                for (int c = 0; c < G; ++c) {
-                    ClipRun& r = clips[c];
-                    if (!r.active) continue;
-                    if (r.seek + 100 >= r.n_len_org || (int)r.windows.size() >= max_windows) { r.active = false; continue; }
-                    wclip.push_back(c); wseek.push_back(r.seek); wend.push_back(r.n_len_org); wlang.push_back(r.lang);
+            std::vector<int> slot_job(S, -1);             // index into `live` jobs, or -1
+            std::vector<WinJob> live(S);
+            std::vector<WinJob> pending;                  // encoded (or encoding) on the main stream, not yet in their slots
+            bool pend_active = false;
+            int running = 0;
+            SB_CUDA_CHECK(cudaEventRecord(ev[2], st));     // (ev[1] / ev_enc bracket one encoder batch at a time)
+            for (long iter = 0; iter < (1L << 24); ++iter) {
+                // (1) windows whose encoder pass is complete enter their slots
+                if (pend_active && (running == 0 || cudaEventQuery(ev_enc) == cudaSuccess)) {
+                    if (running == 0) SB_CUDA_CHECK(cudaEventSynchronize(ev_enc));      // nothing to step meanwhile
+                    { float t = 0.f; if (cudaEventElapsedTime(&t, ev[1], ev_enc) == cudaSuccess) ms_enc += t; }
+                    if ((rc = init_slots(pending))) return rc;
+                    for (const WinJob& j : pending) { live[j.slot] = j; slot_job[j.slot] = 1; }
+                    running += (int)pending.size();
+                    pending.clear(); pend_active = false;
                 }
-                const int W = (int)wclip.size();
-                if (W == 0) break;
-                if ((rc = ensure_encoder_ws(W, W, false))) return rc;
-                std::vector<int> wm(2 * W);
-                for (int w = 0; w < W; ++w) { wm[w] = wclip[w]; wm[W + w] = wseek[w]; }
-                SB_CUDA_CHECK(cudaMemcpyAsync(b_winmeta.p, wm.data(), 2 * W * 4, cudaMemcpyHostToDevice, st));
-                SB_CUDA_CHECK(cudaEventRecord(ev[0], st));
-                Im2col1Args a{b_mel.as<float>(), b_floor.as<float>(), b_winmeta.as<int>(), b_winmeta.as<int>() + W,
-                              b_clipmeta.as<int>(), b_clipmeta.as<int>() + G, (int64_t)n_mel * stride, stride, n_mel,
-                              2 * hp.n_audio_ctx};
-                if ((rc = im2col_conv1<T>(a, b_col1.as<T>(), W, st))) return rc;
-                if ((rc = encode_chunk(W, 0, nullptr))) return rc;
-                SB_CUDA_CHECK(cudaEventRecord(ev[1], st));
-                DecodeOut d;
-                if ((rc = decode(W, wseek, wend, p, wlang, nullptr, 0, nullptr, d))) return rc;
-                SB_CUDA_CHECK(cudaEventRecord(ev[2], st));
-                SB_CUDA_CHECK(cudaStreamSynchronize(st));
-                { float t; cudaEventElapsedTime(&t, ev[0], ev[1]); ms_enc += t; cudaEventElapsedTime(&t, ev[1], ev[2]); ms_dec += t; }
-                prof_collect();
-                stats.windows += W; stats.rounds += 1;
-                for (int w = 0; w < W; ++w) {
-                    ClipRun& r = clips[wclip[w]];
-                    if (r.lang < 0) r.lang = d.langs[w] >= 0 ? d.langs[w] : 0;     // detected on the clip's first window
-                    const SeqState& s = d.state[w];
-                    sb_window_info wi{};
-                    wi.seek = r.seek; wi.n_tokens = s.n_tok; wi.result_len = s.result_len; wi.seek_delta = s.seek_delta;
-                    wi.failed = s.failed; wi.token_offset = (int)r.sampled.size();
-                    for (int i = 0; i < s.n_tok; ++i) {
-                        const int t = d.tokens[(size_t)w * d.n_max + i];
-                        r.sampled.push_back(t); r.margins.push_back(d.margins[(size_t)w * d.n_max + i]);
-                        if (i < s.result_len) { r.kept.push_back(t); if (t < sp.eot) r.text += token_text(t); }
+                // (2) start encoding the next batch of ready windows
+                if (!pend_active) {
+                    std::vector<int> ready, freeslots;
+                    for (int c = 0; c < G; ++c) {
+                        ClipRun& r = clips[c];
+                        if (!r.active || r.running) continue;
+                        if (r.seek + 100 >= r.n_len_org || (int)r.windows.size() >= max_windows) { r.active = false; continue; }
+                        ready.push_back(c);
                     }
-                    r.windows.push_back(wi);
-                    r.seek += s.seek_delta;
+                    for (int s_ = 0; s_ < S; ++s_) if (slot_job[s_] < 0) freeslots.push_back(s_);
+                    const int k = (int)std::min(ready.size(), freeslots.size());
+                    if (k > 0 && (running == 0 || k >= refill_min)) {
+                        // spread the new windows over the lanes with the fewest live sequences
+                        std::vector<int> lane_load(n_lanes);
+                        for (int li = 0; li < n_lanes; ++li) lane_load[li] = lanes[li].active;
+                        std::vector<int> chosen;
+                        std::vector<char> used(S, 0);
+                        for (int i = 0; i < k; ++i) {
+                            int best = -1, best_lane = -1;
+                            for (int s_ : freeslots) {
+                                if (used[s_]) continue;
+                                int li = 0;
+                                while (s_ >= lanes[li].s0 + lanes[li].n) ++li;
+                                if (best < 0 || lane_load[li] < lane_load[best_lane]) { best = s_; best_lane = li; }
+                            }
+                            used[best] = 1; lane_load[best_lane] += 1; chosen.push_back(best);
+                        }
+                        std::sort(chosen.begin(), chosen.end());
+                        // pinned: the previous batch (the only other user) has left the encoder before a new one is staged
+                        int* wm = h_winmeta.as<int>();
+                        std::vector<int> slots(k);
+                        for (int i = 0; i < k; ++i) {
+                            ClipRun& r = clips[ready[i]];
+                            // whisper.cpp: a very short tail drops the text context ("it tends to confuse the decoder")
+                            if (r.seek > 0 && r.seek + 500 >= r.n_len_org) r.prompt_past.clear();
+                            WinJob j;
+                            j.clip = ready[i]; j.slot = chosen[i]; j.seek = r.seek; j.seek_end = r.n_len_org;
+                            build_prompt(j, r.prompt_past, r.lang, p);
+                            r.running = true;
+                            pending.push_back(std::move(j));
+                            wm[i] = ready[i]; wm[k + i] = r.seek; slots[i] = chosen[i];
+                        }
+                        SB_CUDA_CHECK(cudaEventRecord(ev[1], st));
+                        SB_CUDA_CHECK(cudaMemcpyAsync(b_winmeta.p, wm, 2 * k * 4, cudaMemcpyHostToDevice, st));
+                        Im2col1Args a{b_mel.as<float>(), b_floor.as<float>(), b_winmeta.as<int>(), b_winmeta.as<int>() + k,
+                                      b_clipmeta.as<int>(), b_clipmeta.as<int>() + G, (int64_t)n_mel * stride, stride, n_mel,
+                                      2 * hp.n_audio_ctx};
+                        if ((rc = im2col_conv1<T>(a, b_col1.as<T>(), k, st))) return rc;
+                        if ((rc = encode_chunk(k, slots.data(), nullptr))) return rc;
+                        SB_CUDA_CHECK(cudaEventRecord(ev_enc, st));
+                        pend_active = true;
+                        stats.windows += k; stats.rounds += 1;
+                        if (running == 0) continue;            // nothing to step meanwhile: enter the slots right away
+                    }
+                }
+                if (running == 0 && !pend_active) break;
+                if (running == 0) continue;
+                // (3) a burst of steps on every lane with live sequences, then poll
+                for (int li = 0; li < n_lanes; ++li) {
+                    if (lanes[li].active == 0) continue;
+                    if ((rc = run_steps(li, 8))) return rc;
+                    if ((rc = poll_lane(li))) return rc;
+                }
+                for (int li = 0; li < n_lanes; ++li) {
+                    Lane& L = lanes[li];
+                    if (L.active == 0) continue;
+                    SB_CUDA_CHECK(cudaStreamSynchronize(L.st));
+                    const SeqState* hs = h_state.as<SeqState>();
+                    for (int s_ = L.s0; s_ < L.s0 + L.n; ++s_) {
+                        if (slot_job[s_] < 0 || !hs[s_].done) continue;
+                        const WinJob& j = live[s_];
+                        ClipRun& r = clips[j.clip];
+                        if (r.lang < 0) { const int dl = h_lang.as<int>()[s_]; r.lang = dl >= 0 ? dl : 0; }     // detected on the clip's first window
+                        finish_window(r, j, hs[s_], h_tokens.as<int>() + (size_t)s_ * n_max_cur,
+                                      h_margins.as<float>() + (size_t)s_ * n_max_cur, h_tids.as<int>() + (size_t)s_ * n_max_cur, p);
+                        r.running = false;
+                        slot_job[s_] = -1; L.active -= 1; running -= 1;
+                    }
                 }
             }
+            if ((rc = join_lanes())) return rc;
+            SB_CUDA_CHECK(cudaEventRecord(ev[0], st));
+            SB_CUDA_CHECK(cudaStreamSynchronize(st));
+            { float t; cudaEventElapsedTime(&t, ev[2], ev[0]); ms_total = t; }
+            prof_collect();
+            if ((rc = collect_trace())) return rc;
         }
+        const float ms_dec = std::max(0.f, ms_total - ms_enc);
         for (int c = 0; c < G; ++c) {
             ClipRun& r = clips[c];
             sb_result& o = out[c];
@@ -971,14 +1205,28 @@ struct Engine : EngineBase {
             o.text_len = e - b;
             o.text = (char*)malloc(o.text_len + 1);
             memcpy(o.text, r.text.data() + b, o.text_len); o.text[o.text_len] = 0;
-            auto dup = [](const void* src, size_t bytes) -> void* { void* p = malloc(bytes ? bytes : 1); if (bytes) memcpy(p, src, bytes); return p; };
+            auto dup = [](const void* src, size_t bytes) -> void* { void* q = malloc(bytes ? bytes : 1); if (bytes) memcpy(q, src, bytes); return q; };
             o.n_tokens = r.kept.size(); o.tokens = (int32_t*)dup(r.kept.data(), r.kept.size() * 4);
             o.n_sampled = r.sampled.size(); o.sampled = (int32_t*)dup(r.sampled.data(), r.sampled.size() * 4);
             o.margins = (float*)dup(r.margins.data(), r.margins.size() * 4);
+            o.tids = (int32_t*)dup(r.tids.data(), r.tids.size() * 4);
             o.n_windows = r.windows.size(); o.windows = (sb_window_info*)dup(r.windows.data(), r.windows.size() * sizeof(sb_window_info));
+            // segments: one blob holds every segment text (NUL-terminated), the records point into it
+            size_t blob = 0;
+            for (const Segment& sg : r.segments) blob += sg.text.size() + 1;
+            o.n_segments = r.segments.size();
+            o.segments = (sb_segment*)malloc(std::max<size_t>(1, r.segments.size()) * sizeof(sb_segment));
+            o.segment_text = (char*)malloc(std::max<size_t>(1, blob));
+            size_t off = 0;
+            for (size_t i = 0; i < r.segments.size(); ++i) {
+                const Segment& sg = r.segments[i];
+                memcpy(o.segment_text + off, sg.text.data(), sg.text.size());
+                o.segment_text[off + sg.text.size()] = 0;
+                o.segments[i] = sb_segment{sg.t0, sg.t1, o.segment_text + off, sg.text.size(), sg.tok_off, sg.n_tok};
+                off += sg.text.size() + 1;
+            }
             o.ms_mel = ms_mel; o.ms_encode = ms_enc; o.ms_decode = ms_dec; o.status = SB_OK;
             o.lang_id = hp.n_vocab >= 51865 ? r.lang : -1;
-            stats.tokens_sampled += (double)r.sampled.size();
         }
         stats.mel_ms += ms_mel; stats.encode_ms += ms_enc; stats.decode_ms += ms_dec; stats.clips += G;
         return SB_OK;
@@ -989,18 +1237,31 @@ struct Engine : EngineBase {
         int lang = 0;
         int rc = resolve_language(p, &lang);
         if (rc) return rc;
-        auto_mode = lang < 0;
-        for (size_t c0 = 0; c0 < count; c0 += max_batch) {
-            const int G = (int)std::min<size_t>(max_batch, count - c0);
-            if ((rc = run_group(pcm + c0, ns + c0, G, p, lang, out + c0))) return rc;
-        }
-        return SB_OK;
+        detect_lang = lang < 0;
+        // all clips of the call share the decode slots: a finished clip's slot goes to the next waiting clip
+        return run_group(pcm, ns, (int)count, p, lang, out);
     }
 };
 
 }  // namespace sb
 
-struct sb_engine { std::unique_ptr<sb::EngineBase> impl; };
+// One replica per CUDA device.  replicas[0] answers the single-device queries (info, stream, stats, tokenize).
+struct sb_engine {
+    std::vector<std::unique_ptr<sb::EngineBase>> replicas;
+    sb::EngineBase* impl() const { return replicas[0].get(); }
+};
+
+// nothing may throw across the C ABI (the reference's release profile is panic = "abort"): host-side allocation
+// failures and library exceptions (vector, string, regex) become an sb_status
+template <typename F>
+static int sb_guarded(F&& f) noexcept {
+    try { return f(); }
+    catch (const std::bad_alloc&) { sb::set_error("out of host memory"); return SB_ERR_NOMEM; }
+    catch (const std::exception& e) { sb::set_error(std::string("internal error: ") + e.what()); return SB_ERR_INVALID; }
+    catch (...) { sb::set_error("internal error"); return SB_ERR_INVALID; }
+}
+
+static const char* kNotLoaded = "Model is not loaded for transcription.";   // transcription.rs:427-429
 
 extern "C" {
 
@@ -1010,91 +1271,146 @@ void sb_params_default(sb_params* p) {
     p->language = "en";
     p->suppress_blank = 1;
     p->max_initial_ts = 1.0f;
+    p->n_max_text_ctx = 16384;
 }
 
 int sb_engine_create(const sb_config* cfg, sb_engine** out) {
-    SB_CHECK_ARG(cfg && out && cfg->model_path, "cfg/out/model_path is null");
-    SB_CHECK_ARG(cfg->dtype == SB_DTYPE_BF16 || cfg->dtype == SB_DTYPE_F16, "cfg.dtype");
-    int ndev = 0;
-    SB_CUDA_CHECK(cudaGetDeviceCount(&ndev));
-    SB_CHECK_ARG(cfg->device >= 0 && cfg->device < ndev, "cfg.device out of range");
-    SB_CUDA_CHECK(cudaSetDevice(cfg->device));
-    sb::GgmlFile file;
-    int rc = sb::load_ggml_file(cfg->model_path, file);
-    if (rc) return rc;
-    std::unique_ptr<sb::EngineBase> e;
-    if (cfg->dtype == SB_DTYPE_F16) e.reset(new sb::Engine<__half>());
-    else e.reset(new sb::Engine<__nv_bfloat16>());
-    e->device = cfg->device;
-    e->max_batch = cfg->max_batch > 0 ? cfg->max_batch : 64;
-    e->dtype = cfg->dtype;
-    e->use_graph = cfg->use_cuda_graph;
-    if (cfg->dtype == SB_DTYPE_F16) rc = static_cast<sb::Engine<__half>*>(e.get())->load(file);
-    else rc = static_cast<sb::Engine<__nv_bfloat16>*>(e.get())->load(file);
-    if (rc) return rc;
-    SB_CUDA_CHECK(cudaDeviceSynchronize());
-    sb_engine* h = new sb_engine();
-    h->impl = std::move(e);
-    *out = h;
-    return SB_OK;
+    return sb_guarded([&]() -> int {
+        SB_CHECK_ARG(cfg && out && cfg->model_path, "cfg/out/model_path is null");
+        SB_CHECK_ARG(cfg->dtype == SB_DTYPE_BF16 || cfg->dtype == SB_DTYPE_F16, "cfg.dtype");
+        int ndev = 0;
+        SB_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+        std::vector<int> devs;
+        if (cfg->devices && cfg->n_devices > 0) devs.assign(cfg->devices, cfg->devices + cfg->n_devices);
+        else devs.push_back(cfg->device);
+        SB_CHECK_ARG(devs.size() <= 64, "at most 64 devices");
+        for (size_t i = 0; i < devs.size(); ++i) {
+            SB_CHECK_ARG(devs[i] >= 0 && devs[i] < ndev, "cfg.device / cfg.devices[] out of range");
+            for (size_t j = 0; j < i; ++j) SB_CHECK_ARG(devs[j] != devs[i], "cfg.devices[] lists a device twice");
+        }
+        sb::GgmlFile file;
+        int rc = sb::load_ggml_file(cfg->model_path, file);
+        if (rc) return rc;
+        std::unique_ptr<sb_engine> h(new sb_engine());
+        for (int dev : devs) {
+            SB_CUDA_CHECK(cudaSetDevice(dev));
+            std::unique_ptr<sb::EngineBase> e;
+            if (cfg->dtype == SB_DTYPE_F16) e.reset(new sb::Engine<__half>());
+            else e.reset(new sb::Engine<__nv_bfloat16>());
+            e->device = dev;
+            e->max_batch = cfg->max_batch > 0 ? cfg->max_batch : 64;
+            e->dtype = cfg->dtype;
+            e->use_graph = cfg->use_cuda_graph;
+            if (cfg->dtype == SB_DTYPE_F16) rc = static_cast<sb::Engine<__half>*>(e.get())->load(file);
+            else rc = static_cast<sb::Engine<__nv_bfloat16>*>(e.get())->load(file);
+            if (rc) return rc;
+            SB_CUDA_CHECK(cudaDeviceSynchronize());
+            h->replicas.push_back(std::move(e));
+        }
+        *out = h.release();
+        return SB_OK;
+    });
 }
 
 int sb_engine_destroy(sb_engine* e) {
     if (!e) return SB_OK;
-    cudaSetDevice(e->impl->device);
-    cudaDeviceSynchronize();
-    delete e;
-    return SB_OK;
+    return sb_guarded([&]() -> int {
+        for (auto& r : e->replicas) {
+            cudaSetDevice(r->device);
+            cudaDeviceSynchronize();
+            r.reset();
+        }
+        delete e;
+        return SB_OK;
+    });
 }
 
 int sb_engine_info(const sb_engine* e, sb_model_info* info) {
     SB_CHECK_ARG(e && info, "null pointer");
-    const sb::WhisperHParams& h = e->impl->hp;
+    const sb::WhisperHParams& h = e->impl()->hp;
     *info = sb_model_info{h.n_vocab, h.n_audio_ctx, h.n_audio_state, h.n_audio_head, h.n_audio_layer, h.n_text_ctx,
                           h.n_text_state, h.n_text_head, h.n_text_layer, h.n_mels, h.ftype,
-                          e->impl->sp.eot, e->impl->sp.sot, e->impl->sp.beg, e->impl->sp.blank};
+                          e->impl()->sp.eot, e->impl()->sp.sot, e->impl()->sp.beg, e->impl()->sp.blank};
     return SB_OK;
 }
 
-void* sb_engine_stream(sb_engine* e) { return e ? e->impl->stream_handle() : nullptr; }
+int sb_engine_device_count(const sb_engine* e) { return e ? (int)e->replicas.size() : 0; }
+
+void* sb_engine_stream(sb_engine* e) { return e ? e->impl()->stream_handle() : nullptr; }
 
 int sb_engine_set_profile(sb_engine* e, int enable) {
     SB_CHECK_ARG(e, "null engine");
-    e->impl->profile = enable;
+    for (auto& r : e->replicas) r->profile = enable;
     return SB_OK;
 }
 
 int sb_engine_stats(sb_engine* e, sb_stats* out, int reset) {
     SB_CHECK_ARG(e && out, "null pointer");
-    *out = e->impl->stats;
-    if (reset) memset(&e->impl->stats, 0, sizeof(sb_stats));
+    *out = e->impl()->stats;
+    if (reset) for (auto& r : e->replicas) memset(&r->stats, 0, sizeof(sb_stats));
     return SB_OK;
 }
 
 int sb_token_text(const sb_engine* e, int32_t id, char* buf, int cap) {
     if (!e) return 0;
-    const std::string s = e->impl->token_text(id);
-    if (buf && cap > 0) memcpy(buf, s.data(), std::min<size_t>(s.size(), (size_t)cap));
-    return (int)s.size();
+    int n = 0;
+    sb_guarded([&]() -> int {
+        const std::string s = e->impl()->token_text(id);
+        if (buf && cap > 0) memcpy(buf, s.data(), std::min<size_t>(s.size(), (size_t)cap));
+        n = (int)s.size();
+        return SB_OK;
+    });
+    return n;
 }
 
 int sb_tokenize(const sb_engine* e, const char* text, int32_t* tokens, int cap) {
-    if (!e) { sb::set_error("Model is not loaded for transcription."); return SB_ERR_NOT_LOADED; }
-    SB_CHECK_ARG(text && (tokens || cap == 0), "null pointer");
-    const std::vector<int> t = e->impl->tokenize(text);
-    for (int i = 0; i < (int)t.size() && i < cap; ++i) tokens[i] = t[i];
-    return (int)t.size();
+    if (!e) { sb::set_error(kNotLoaded); return SB_ERR_NOT_LOADED; }
+    return sb_guarded([&]() -> int {
+        SB_CHECK_ARG(text && (tokens || cap == 0), "null pointer");
+        const std::vector<int> t = e->impl()->tokenize(text);
+        for (int i = 0; i < (int)t.size() && i < cap; ++i) tokens[i] = t[i];
+        return (int)t.size();
+    });
 }
 
 int sb_transcribe_batch(sb_engine* e, const float* const* pcm16k, const size_t* n_samples, size_t count,
                         const sb_params* p, sb_result* out) {
-    if (!e) { sb::set_error("Model is not loaded for transcription."); return SB_ERR_NOT_LOADED; }
-    SB_CHECK_ARG(out && (count == 0 || (pcm16k && n_samples)), "null pointer");
-    memset(out, 0, count * sizeof(sb_result));
-    sb_params dp;
-    if (!p) { sb_params_default(&dp); p = &dp; }
-    for (size_t i = 0; i < count; ++i) SB_CHECK_ARG(n_samples[i] == 0 || pcm16k[i], "null clip pointer");
-    return e->impl->transcribe_batch(pcm16k, n_samples, count, *p, out);
+    if (!e) { sb::set_error(kNotLoaded); return SB_ERR_NOT_LOADED; }
+    return sb_guarded([&]() -> int {
+        SB_CHECK_ARG(out && (count == 0 || (pcm16k && n_samples)), "null pointer");
+        memset(out, 0, count * sizeof(sb_result));
+        sb_params dp;
+        if (!p) { sb_params_default(&dp); p = &dp; }
+        for (size_t i = 0; i < count; ++i) SB_CHECK_ARG(n_samples[i] == 0 || pcm16k[i], "null clip pointer");
+        const size_t R = e->replicas.size();
+        if (R == 1 || count <= 1) return e->impl()->transcribe_batch(pcm16k, n_samples, count, *p, out);
+        // clips are independent: clip i goes to device i mod R, one worker thread per device, no collective
+        std::vector<std::vector<const float*>> ptrs(R);
+        std::vector<std::vector<size_t>> ns(R), idx(R);
+        for (size_t i = 0; i < count; ++i) { ptrs[i % R].push_back(pcm16k[i]); ns[i % R].push_back(n_samples[i]); idx[i % R].push_back(i); }
+        std::vector<std::vector<sb_result>> res(R);
+        std::vector<int> rcs(R, SB_OK);
+        std::vector<std::string> errs(R);
+        std::vector<std::thread> workers;
+        for (size_t r = 0; r < R; ++r) {
+            if (idx[r].empty()) continue;
+            res[r].resize(idx[r].size());
+            workers.emplace_back([&, r] {
+                rcs[r] = sb_guarded([&]() -> int {
+                    return e->replicas[r]->transcribe_batch(ptrs[r].data(), ns[r].data(), idx[r].size(), *p, res[r].data());
+                });
+                if (rcs[r]) errs[r] = sb::get_error();       // the message is thread-local: hand it to the caller
+            });
+        }
+        for (auto& w : workers) w.join();
+        int rc = SB_OK;
+        for (size_t r = 0; r < R; ++r) {
+            for (size_t k = 0; k < idx[r].size(); ++k) out[idx[r][k]] = res[r][k];
+            if (rcs[r] && !rc) { rc = rcs[r]; sb::set_error("device " + std::to_string(e->replicas[r]->device) + ": " + errs[r]); }
+        }
+        if (rc) for (size_t i = 0; i < count; ++i) sb_result_free(out + i);
+        return rc;
+    });
 }
 
 int sb_transcribe(sb_engine* e, const float* pcm16k, size_t n_samples, const sb_params* p, sb_result* out) {
@@ -1105,21 +1421,53 @@ int sb_transcribe(sb_engine* e, const float* pcm16k, size_t n_samples, const sb_
 
 void sb_result_free(sb_result* r) {
     if (!r) return;
-    free(r->text); free(r->tokens); free(r->sampled); free(r->margins); free(r->windows);
+    free(r->text); free(r->tokens); free(r->sampled); free(r->margins); free(r->tids); free(r->windows);
+    free(r->segments); free(r->segment_text);
     memset(r, 0, sizeof(*r));
 }
 
 int sb_encode(sb_engine* e, const float* mel_windows, int n_windows, float* enc_out) {
-    if (!e) { sb::set_error("Model is not loaded for transcription."); return SB_ERR_NOT_LOADED; }
-    return e->impl->encode_host(mel_windows, n_windows, enc_out);
+    if (!e) { sb::set_error(kNotLoaded); return SB_ERR_NOT_LOADED; }
+    return sb_guarded([&]() -> int { return e->impl()->encode_host(mel_windows, n_windows, enc_out); });
 }
 
 int sb_decode_trace(sb_engine* e, const float* mel_windows, int n_windows, const int32_t* seek_end, const sb_params* p,
                     const int32_t* forced, int n_steps, float* logits_out, int32_t* tokens_out, float* margins_out) {
-    if (!e) { sb::set_error("Model is not loaded for transcription."); return SB_ERR_NOT_LOADED; }
-    sb_params dp;
-    if (!p) { sb_params_default(&dp); p = &dp; }
-    return e->impl->decode_trace(mel_windows, n_windows, seek_end, *p, forced, n_steps, logits_out, tokens_out, margins_out);
+    if (!e) { sb::set_error(kNotLoaded); return SB_ERR_NOT_LOADED; }
+    return sb_guarded([&]() -> int {
+        sb_params dp;
+        if (!p) { sb_params_default(&dp); p = &dp; }
+        return e->impl()->decode_trace(mel_windows, n_windows, seek_end, *p, forced, n_steps, logits_out, tokens_out, margins_out);
+    });
+}
+
+/* ABI layout table: sizeof / offsetof of every struct that crosses the boundary, so that a binding in another language
+ * (ctypes here, the Rust crate in rust/spittle-b200-sys) can be checked against the library it loads. */
+#define SB_LAYOUT_ROWS(X)                                                                                               \
+    X(sb_config, model_path) X(sb_config, device) X(sb_config, max_batch) X(sb_config, dtype) X(sb_config, use_cuda_graph) \
+    X(sb_config, devices) X(sb_config, n_devices)                                                                       \
+    X(sb_params, language) X(sb_params, translate) X(sb_params, initial_prompt) X(sb_params, no_timestamps)             \
+    X(sb_params, suppress_blank) X(sb_params, single_segment) X(sb_params, max_initial_ts) X(sb_params, n_max_tokens)   \
+    X(sb_params, max_windows) X(sb_params, n_max_text_ctx)                                                              \
+    X(sb_window_info, seek) X(sb_window_info, n_tokens) X(sb_window_info, result_len) X(sb_window_info, seek_delta)     \
+    X(sb_window_info, failed) X(sb_window_info, token_offset) X(sb_window_info, n_prompt)                               \
+    X(sb_segment, t0) X(sb_segment, t1) X(sb_segment, text) X(sb_segment, text_len) X(sb_segment, token_offset)         \
+    X(sb_segment, n_tokens)                                                                                             \
+    X(sb_result, text) X(sb_result, text_len) X(sb_result, tokens) X(sb_result, n_tokens) X(sb_result, sampled)         \
+    X(sb_result, n_sampled) X(sb_result, margins) X(sb_result, tids) X(sb_result, windows) X(sb_result, n_windows)      \
+    X(sb_result, segments) X(sb_result, n_segments) X(sb_result, segment_text) X(sb_result, ms_mel)                     \
+    X(sb_result, ms_encode) X(sb_result, ms_decode) X(sb_result, status) X(sb_result, lang_id)                          \
+    X(sb_model_info, n_vocab) X(sb_model_info, token_blank) X(sb_stats, clips) X(sb_stats, dstep_count)
+
+int sb_abi_layout(sb_abi_field* out, int cap) {
+    static const sb_abi_field rows[] = {
+#define X(S, F) {#S, #F, (int)sizeof(S), (int)offsetof(S, F)},
+        SB_LAYOUT_ROWS(X)
+#undef X
+    };
+    const int n = (int)(sizeof(rows) / sizeof(rows[0]));
+    for (int i = 0; i < n && i < cap && out; ++i) out[i] = rows[i];
+    return n;
 }
 
 }  // extern "C"

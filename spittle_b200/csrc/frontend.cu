@@ -724,11 +724,7 @@ int sb_vad_score_dev(const sb_vad* v, const float* pcm16k, int64_t pcm_stride, i
     cudaStream_t st = (cudaStream_t)stream;
     float* feat = (float*)workspace;
     float* h1 = feat + (size_t)n_streams * n_frames * 64;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_silero_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sb::SileroSmem)));
-        attr_done = true;
-    }
+    SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_silero_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sb::SileroSmem))); });
     dim3 grid((n_frames + sb::kSfFrames - 1) / sb::kSfFrames, n_streams);
     sb::k_silero_features<<<grid, sb::kSfThreads, sizeof(sb::SileroSmem), st>>>(pcm16k, pcm_stride, n_frames, feat, v->dev);
     const int nb = (n_streams + sb::kLsStreams - 1) / sb::kLsStreams;

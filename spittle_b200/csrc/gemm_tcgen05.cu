@@ -405,16 +405,18 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int is_f16, int64_t rows, in
     return SB_OK;
 }
 
-static int g_num_sms = 0;
-
+// SM count of the CURRENT device (one process may drive several GPUs)
 int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int n = cache[dev & 63].load(std::memory_order_relaxed);
+    if (n == 0) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+        cache[dev & 63].store(n, std::memory_order_relaxed);
     }
-    return g_num_sms;
+    return n;
 }
 
 // A [M,K] (row stride lda), W [N,K] (row stride ldw); dtype 0 bf16 / 1 f16.
@@ -431,14 +433,10 @@ int gemm_tn(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, i
     if (rc != SB_OK) return rc;
     rc = make_tmap_2d(&tb, W, dtype, N, K, ldw, pair ? GemmCfg<2>::kRowsB : GemmCfg<1>::kRowsB);
     if (rc != SB_OK) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::kSmem));
+    SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::kSmem));
         SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__half, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::kSmem));
         SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__nv_bfloat16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::kSmem));
-        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__half, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::kSmem));
-        attr_done = true;
-    }
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__half, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::kSmem)); });
     if (pair) {
         const int num_tiles = ceil_div(M, 2 * kBM) * ceil_div(N, kBN);
         const int clusters = std::min(num_tiles, num_sms() / 2);

@@ -89,13 +89,13 @@ struct Reader {
     const uint8_t* p; size_t n; size_t off = 0; bool ok = true;
     template <typename V> V get() {
         V v{};
-        if (off + sizeof(V) > n) { ok = false; return v; }
+        if (sizeof(V) > n - off) { ok = false; return v; }
         memcpy(&v, p + off, sizeof(V));
         off += sizeof(V);
         return v;
     }
     const uint8_t* take(size_t k) {
-        if (off + k > n) { ok = false; return nullptr; }
+        if (k > n - off) { ok = false; return nullptr; }      // (off <= n always: no wrap-around)
         const uint8_t* r = p + off;
         off += k;
         return r;
@@ -155,6 +155,15 @@ int load_ggml_file(const char* path, GgmlFile& out) {
         for (int i = 0; i < n_dims; ++i) ne[i] = r.get<int32_t>();
         const uint8_t* nm = r.take(name_len);
         if (!r.ok) { set_error("corrupt tensor header"); return SB_ERR_FORMAT; }
+        // a corrupt file must end in SB_ERR_FORMAT, never in a wrapped size, a backwards cursor or std::bad_alloc
+        int64_t numel = 1;
+        bool dims_ok = true;
+        for (int i = 0; i < n_dims; ++i) {
+            if (ne[i] <= 0 || ne[i] > (int64_t)1 << 31) { dims_ok = false; break; }
+            numel *= ne[i];
+            if (numel > 2 * (int64_t)r.n) { dims_ok = false; break; }    // every supported type stores > 0.5 byte per element
+        }
+        if (!dims_ok) { set_error("corrupt tensor header: bad dimensions"); return SB_ERR_FORMAT; }
         std::string name(reinterpret_cast<const char*>(nm), name_len);
         HostTensor t;
         t.ttype = ttype;

@@ -331,12 +331,8 @@ int logmel_launch(const sb_melplan* plan, const float* pcm, int n_clips, size_t 
     SB_CHECK_ARG(n_samples >= 201, "log-mel needs more than 200 samples (whisper.cpp reflect pad)");
     SB_CHECK_ARG(mel_stride >= n_calc && mel_stride % 4 == 0, "mel_stride must be >= n_calc and a multiple of 4");
     SB_CHECK_ARG(n_clips > 0 && n_clips <= 65535, "n_clips out of range");
-    static bool attr_done = false;
-    if (!attr_done) {
-        SB_CUDA_CHECK(cudaFuncSetAttribute(k_logmel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(LogmelSmem)));
-        attr_done = true;
-    }
+    SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(k_logmel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(LogmelSmem))); });
     LogmelArgs a;
     a.pcm = pcm; a.mel = mel; a.clip_max = clip_max;
     a.pcm_clip_stride = pcm_clip_stride; a.n_samples = (int)n_samples; a.n_calc = n_calc;

@@ -202,6 +202,9 @@ ARCHS: Dict[str, WhisperHParams] = {
     # fast CPU/GPU test shape: same structure, d_head = 64
     "nano": WhisperHParams(n_audio_state=128, n_audio_head=2, n_audio_layer=2,
                            n_text_state=128, n_text_head=2, n_text_layer=2, n_mels=80),
+    # English-only vocabulary (ggml-*.en.bin): no language / task tokens in the prompt, ids shifted down (App. C.5)
+    "nano.en": WhisperHParams(n_vocab=51864, n_audio_state=128, n_audio_head=2, n_audio_layer=2,
+                              n_text_state=128, n_text_head=2, n_text_layer=2, n_mels=80),
     "micro": WhisperHParams(n_audio_state=256, n_audio_head=4, n_audio_layer=3,
                             n_text_state=256, n_text_head=4, n_text_layer=3, n_mels=128,
                             n_vocab=51866),
@@ -235,7 +238,9 @@ class SpecialTokens:
     def from_n_vocab(n_vocab: int, blank: int = 220) -> "SpecialTokens":
         eot, sot, translate, transcribe, solm, prev, nosp, not_, beg = (
             50256, 50257, 50357, 50358, 50359, 50360, 50361, 50362, 50363)
-        num_languages = 0
+        # whisper.cpp: num_languages = n_vocab - 51765 - (multilingual ? 1 : 0): English-only vocabularies keep the 99
+        # language ids 50258..50356, which the logits filter always suppresses
+        num_languages = max(0, n_vocab - 51765)
         if n_vocab >= 51865:  # multilingual
             num_languages = n_vocab - 51765 - 1
             eot += 1

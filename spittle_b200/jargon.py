@@ -125,6 +125,40 @@ def restore_protected_spans(text: str, spans: List[Tuple[str, str]]) -> str:
     return text
 
 
+def expand_replacement(to: str, matched: str) -> str:
+    """Rust regex `Replacer for &str` (what `re.replace_all(&masked, correction.to.as_str())` does, jargon.rs:697): `$$` is a
+    literal `$`; `$name` / `${name}` / `$N` expand capture groups -- the correction pattern has none, so `$0` is the whole
+    match and every other reference is the empty string; a `$` followed by anything else stays."""
+    out, i, n = [], 0, len(to)
+    while i < n:
+        ch = to[i]
+        if ch != "$":
+            out.append(ch); i += 1
+            continue
+        if i + 1 < n and to[i + 1] == "$":
+            out.append("$"); i += 2
+            continue
+        j = i + 1
+        if j < n and to[j] == "{":
+            k = to.find("}", j)
+            if k < 0:
+                out.append("$"); i += 1
+                continue
+            name, j = to[j + 1:k], k + 1
+        else:
+            k = j
+            while k < n and (to[k].isascii() and (to[k].isalnum() or to[k] == "_")):
+                k += 1
+            if k == j:
+                out.append("$"); i += 1
+                continue
+            name, j = to[j:k], k
+        if name.isdigit() and int(name) == 0:
+            out.append(matched)
+        i = j
+    return "".join(out)
+
+
 def apply_corrections(text: str, corrections: List[JargonCorrection]) -> str:
     if not corrections or not text:
         return text
@@ -134,7 +168,7 @@ def apply_corrections(text: str, corrections: List[JargonCorrection]) -> str:
             pat = re.compile(r"(?i)\b" + re.escape(c.from_) + r"\b")
         except re.error:
             continue
-        masked = pat.sub(lambda _m, to=c.to: to, masked)
+        masked = pat.sub(lambda m, to=c.to: expand_replacement(to, m.group(0)), masked)
     restored = restore_protected_spans(masked, spans)
     if any(ph in restored for ph, _ in spans):
         return text

@@ -270,7 +270,7 @@ def make_synthetic_model(arch: str, seed: int = 42, recipe: str = "sharp",
         # random decoder otherwise locks onto repeating its own input token (E_t . E_t term)
         T["decoder.ln.weight"] = rng.choice(np.array([-1.0, 1.0], np.float32), size=dt).astype(np.float32)
 
-    return GgmlModel(hparams=hp, mel_filters=mel_filterbank(hp.n_mels), vocab=synthetic_vocab(),
+    return GgmlModel(hparams=hp, mel_filters=mel_filterbank(hp.n_mels), vocab=synthetic_vocab(50257 if hp.n_vocab >= 51865 else 50256),
                      tensors=T)
 
 

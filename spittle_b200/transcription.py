@@ -35,6 +35,12 @@ class Settings:
     jargon_custom_terms: List[str] = field(default_factory=list)
     jargon_custom_corrections: List["jargon.JargonCorrection"] = field(default_factory=list)
     jargon_profiles: Dict[str, "jargon.JargonProfile"] = field(default_factory=dict)
+    # ids of user jargon packs (settings.jargon_packs; their profiles are part of jargon_profiles, like build_profiles_map
+    # transcription.rs:50-63 merges them): only their presence matters for the gates at :462-464 / :553-555
+    jargon_packs: List[str] = field(default_factory=list)
+    # DomainSelectorManager stand-in (transcription.rs:65-87): (settings, context_text) -> profile ids or None
+    profile_selector: Optional[Callable[["Settings", str], Optional[List[str]]]] = None
+    domain_selector_blend_manual_profiles: bool = False
     device: int = 0
     max_batch: int = 64
     dtype: int = capi.SB_DTYPE_F16
@@ -102,6 +108,30 @@ class TranscriptionManager:
     def get_current_model(self) -> Optional[str]:
         return self._current_model_id
 
+    @staticmethod
+    def _effective_profile_ids(s: Settings, context_text: str) -> List[str]:
+        """transcription.rs:65-87: the enabled profiles, replaced by (or blended with) the domain selector's pick."""
+        ids = list(s.jargon_enabled_profiles)
+        auto = s.profile_selector(s, context_text) if s.profile_selector else None
+        if auto is not None:
+            if s.domain_selector_blend_manual_profiles:
+                ids += [p for p in auto if p not in ids]
+            else:
+                ids = list(auto)
+        return ids
+
+    @classmethod
+    def _initial_prompt(cls, s: Settings) -> Optional[str]:
+        """transcription.rs:461-492: the jargon dictionary's terms as Whisper's initial_prompt."""
+        if not (s.jargon_enabled_profiles or s.jargon_custom_terms or s.jargon_packs):
+            return None
+        d = jargon.compute_active_dictionary(
+            jargon.JargonSettings(cls._effective_profile_ids(s, ""), s.jargon_custom_terms, s.jargon_custom_corrections),
+            s.jargon_profiles)
+        if not d.terms:
+            return None
+        return jargon.build_initial_prompt(d) or None
+
     def _params(self, s: Settings):
         lang = s.selected_language
         if lang in ("zh-Hans", "zh-Hant"):
@@ -109,18 +139,20 @@ class TranscriptionManager:
         kw = dict(translate=int(s.translate_to_english))
         p = capi.default_params(**kw)
         p.language = None if lang == "auto" else lang.encode()
+        prompt = self._initial_prompt(s)
+        p.initial_prompt = prompt.encode("utf-8") if prompt else None
         return p
 
-    @staticmethod
-    def _post_filter(text: str, s: Settings) -> str:
+    @classmethod
+    def _post_filter(cls, text: str, s: Settings) -> str:
         """transcription.rs:537-580: custom-word correction (only when configured), the filler / stutter /
         hallucination filter, then the jargon corrections (only when profiles or custom corrections are configured)."""
         if s.custom_words:
             text = text_filters.apply_custom_words(text, s.custom_words, s.word_correction_threshold)
         text = text_filters.filter_transcription_output(text)
-        if s.jargon_enabled_profiles or s.jargon_custom_corrections:
+        if s.jargon_enabled_profiles or s.jargon_custom_corrections or s.jargon_packs:
             d = jargon.compute_active_dictionary(
-                jargon.JargonSettings(s.jargon_enabled_profiles, s.jargon_custom_terms, s.jargon_custom_corrections),
+                jargon.JargonSettings(cls._effective_profile_ids(s, text), s.jargon_custom_terms, s.jargon_custom_corrections),
                 s.jargon_profiles)
             if d.corrections:
                 text = jargon.apply_corrections(text, d.corrections)

@@ -40,3 +40,51 @@ def test_no_device_fails_loudly(lib_built):
         pytest.skip("has a GPU")
     with pytest.raises(capi.SbError):
         capi.MelPlan(synth.mel_filterbank(80))
+
+
+# ---- struct layout: library == checked-in table == ctypes mirror == Rust bindings ------------------------------
+def _golden_layout():
+    import json
+    root = os.path.dirname(os.path.abspath(__file__))
+    return [tuple(r) for r in json.load(open(os.path.join(root, "golden", "abi_layout.json")))]
+
+
+def test_abi_layout_matches_checked_in_table_and_ctypes(lib_built):
+    """sizeof / offsetof of every ABI struct as the LIBRARY reports them (sb_abi_layout) against the checked-in
+    table and against the ctypes mirror the tests call through (round 1 shipped a Rust sb_result 8 bytes short)."""
+    import ctypes as C
+    from spittle_b200 import capi
+    rows = capi.abi_layout()
+    assert rows == _golden_layout(), "include/spittle_b200.h changed: regenerate tests/golden/abi_layout.json AND the bindings"
+    for sname, field, size, off in rows:
+        st = capi.ABI_STRUCTS[sname]
+        assert C.sizeof(st) == size, (sname, C.sizeof(st), size)
+        assert getattr(st, field).offset == off, (sname, field)
+    # every field of the mirrored structs that carry results / parameters is covered by the table
+    for sname in ("sb_config", "sb_params", "sb_window_info", "sb_segment", "sb_result"):
+        covered = {f for s_, f, _, _ in rows if s_ == sname}
+        assert covered == {n for n, _ in capi.ABI_STRUCTS[sname]._fields_}, sname
+
+
+def test_rust_bindings_assert_the_same_layout():
+    """rust/spittle-b200-sys cannot be compiled here (no cargo): its const layout asserts are parsed and compared
+    with the table, and its struct field lists with the header's."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "rust", "spittle-b200-sys", "src", "lib.rs")).read()
+    table = {(s_, f): (size, off) for s_, f, size, off in _golden_layout()}
+    sizes = {s_: size for s_, _, size, _ in _golden_layout()}
+    n = 0
+    for s_, size in re.findall(r"assert!\(size_of::<(\w+)>\(\) == (\d+)\)", src):
+        assert sizes[s_] == int(size), s_
+        n += 1
+    for s_, f, off in re.findall(r"assert!\(offset_of!\((\w+), (\w+)\) == (\d+)\)", src):
+        assert table[(s_, f)][1] == int(off), (s_, f)
+        n += 1
+    assert n >= 15
+    # field order / names of the Rust structs equal the table's (fields are declared `pub name: type`)
+    for sname in ("sb_config", "sb_params", "sb_window_info", "sb_segment", "sb_result"):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % sname, src, re.S).group(1)
+        body = re.sub(r"//[^\n]*", "", body)
+        rust_fields = re.findall(r"pub (\w+):", body)
+        want = [f for s_, f, _, _ in _golden_layout() if s_ == sname]
+        assert rust_fields == want, (sname, rust_fields, want)
