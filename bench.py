@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the Whisper transcription hot path on B200.
 
-Metric (BASELINE.json): RTFx = audio-seconds per wall-second.  Workload at N=1:
-BASELINE.json configs[1] "Whisper Small batch of 64 synthetic 30 s clips on 1xB200".
+Metric (BASELINE.json): RTFx = audio-seconds per wall-second.  Workload: BASELINE.json configs[2] "Whisper
+Large-v3 Turbo (128-mel, 4-layer decoder) batched clips sharded across 1/2/4/8 B200" -- the model north_star names --
+with 64 synthetic 30 s clips per GPU; SB_BENCH_ARCH=small runs configs[1] (Whisper Small, 64 clips), and at N = 1 the
+default run carries that configuration as the secondary `config.small_64` entry.
 A step = one pass of the whole hot path (log-mel -> encoder -> cross-KV -> greedy decode with
 the whisper.cpp seek loop -> text) over one batch of 64 clips through the C ABI
 (sb_transcribe_batch).  N > 1: one process per GPU (torchrun), every rank transcribes its own
@@ -37,7 +39,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np
 
-ARCH = os.environ.get("SB_BENCH_ARCH", "small")
+ARCH = os.environ.get("SB_BENCH_ARCH", "large-v3-turbo")
 CLIPS_PER_GPU = int(os.environ.get("SB_BENCH_CLIPS", "64"))
 CLIP_SECONDS = 30.0
 
@@ -97,91 +99,136 @@ def model_path(arch: str) -> str:
     return synth.ensure_model_file(arch, d)
 
 
-def cpu_port_rtfx(arch: str, n_clips: int, threads_note: bool = True):
-    """Oracle (numpy port of the whisper.cpp path) timed on the host cores: bounded sample."""
-    from oracle import whisper_ref
-    from spittle_b200 import ggml_format
-    model = ggml_format.read_ggml(model_path(arch))
-    oracle = whisper_ref.WhisperOracle(model, act_f16=True)
-    clips = make_clips(0, n_clips)
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_ref_run(arch: str, clip_ids, n_threads: int):
+    """oracle/cpu_ref (C++ restatement of the whisper.cpp CPU path, std::thread) over the given clips of the bench batch.
+    Returns (rtfx, seconds, per-clip results)."""
+    from oracle import cpu_ref
+    ref = cpu_ref.CpuRef(model_path(arch), n_threads=n_threads)
+    from spittle_b200 import synth
+    out = []
     t0 = time.perf_counter()
-    n_tok = 0
-    n_win = 0
-    for x in clips:
-        _, kept, wins = oracle.full(x, whisper_ref.DecodeConfig())
-        n_tok += sum(len(w.tokens) for w in wins)
-        n_win += len(wins)
+    for i in clip_ids:
+        out.append(ref.full(synth.make_clip(i, seconds=CLIP_SECONDS)))
     dt = time.perf_counter() - t0
-    return (n_clips * CLIP_SECONDS) / dt, dt, n_tok, n_win
+    isa = ref.isa
+    ref.close()
+    return (len(clip_ids) * CLIP_SECONDS) / dt, dt, out, isa
+
+
+def cpu_baseline_block(arch: str, budget_s: float = 20.0):
+    """Bounded CPU sample: clips 0, 1, ... of the bench batch with all host threads until ~budget_s of CPU wall time,
+    then clip 0 again at 4 threads (whisper.cpp's default n_threads = min(4, hardware_concurrency))."""
+    cores = host_threads()
+    results, secs, n = [], 0.0, 0
+    isa = 0
+    while secs < budget_s and n < 8:
+        v, dt, out, isa = cpu_ref_run(arch, [n], cores)
+        results += out
+        secs += dt
+        n += 1
+    v_all = n * CLIP_SECONDS / secs
+    v4, dt4, _, _ = cpu_ref_run(arch, [0], min(4, cores))
+    n_tok = sum(len(w["tokens"]) for r in results for w in r["windows"])
+    n_win = sum(len(r["windows"]) for r in results)
+    block = {"value": v_all, "unit": "x real-time", "cores": cores, "kind": "port",
+             "threads4_value": v4,
+             "sample": f"clips 0..{n - 1} of the same batch ({n} x 30 s, {n_win} windows, {n_tok} decoded tokens, {secs:.1f} s CPU wall "
+                       f"at {cores} threads; clip 0 again at {min(4, cores)} threads = whisper.cpp's default: {dt4:.1f} s); oracle/cpu_ref = C++ "
+                       f"restatement of the whisper.cpp CPU path (f16 weights, f16-rounded activations, AVX{isa}), validated against "
+                       "the numpy oracle; the reference itself cannot be built here (no cargo/rustc, crates not vendored)"}
+    return block, results
+
+
+def parity_block(gpu_results, cpu_results):
+    """GPU tokens of clips 0..n-1 (through sb_transcribe_batch) against the CPU restatement's tokens, window by window."""
+    n_win = n_exact = n_tok = 0
+    first_div = None
+    for ci, (g, c) in enumerate(zip(gpu_results, cpu_results)):
+        for wi, cw in enumerate(c["windows"]):
+            n_win += 1
+            if wi >= len(g.windows):
+                first_div = first_div or {"clip": ci, "window": wi, "step": 0, "cpu_margin": None, "note": "GPU produced fewer windows"}
+                break
+            gw = g.windows[wi]
+            got = g.sampled[gw["token_offset"]: gw["token_offset"] + gw["n_tokens"]]
+            if got == cw["tokens"]:
+                n_exact += 1
+                n_tok += len(got)
+                continue
+            k = next((i for i in range(min(len(got), len(cw["tokens"]))) if got[i] != cw["tokens"][i]), min(len(got), len(cw["tokens"])))
+            n_tok += k
+            if first_div is None:
+                first_div = {"clip": ci, "window": wi, "step": k,
+                             "cpu_margin": cw["margins"][k] if k < len(cw["margins"]) else None,
+                             "gpu_margin": g.margins[gw["token_offset"] + k] if gw["token_offset"] + k < len(g.margins) else None}
+            break          # later windows of this clip depend on the diverged text context
+    return {"checker": "oracle/cpu_ref", "clips": len(cpu_results), "windows": n_win, "exact_windows": n_exact,
+            "tokens_identical": n_tok, "first_divergence": first_div,
+            "note": "a divergence is only legitimate at a top-1/top-2 margin below the logit tolerance (tests/test_parity_sizes_gpu.py)"}
 
 
 def run_reference(args):
-    """--impl reference: the CPU port of the reference path, all host threads numpy/BLAS will use."""
+    """--impl reference: the reference's CPU path (oracle/cpu_ref, the C++ restatement of whisper.cpp's CPU implementation;
+    the reference itself cannot be built here) on all host threads, each step = clip 0 of the bench batch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
+    cores = host_threads()
+    # one probe step sizes the run: the whole --steps / --warmup run must end within a few minutes
+    v, dt, out, isa = cpu_ref_run(ARCH, [0], cores)
+    budget = 150.0
+    warm = 0 if dt > 20 else min(max(args.warmup, 0), 2)
+    steps = max(1, min(args.steps, int(max(1.0, (budget - dt * (1 + warm)) / max(dt, 1e-3)))))
+    for _ in range(max(0, warm - 1)):
+        cpu_ref_run(ARCH, [0], cores)
     vals = []
-    for i in range(args.warmup if args.warmup < 1 else 0):
-        pass
-    steps = max(1, min(args.steps, 3))
     for _ in range(steps):
-        v, dt, n_tok, n_win = cpu_port_rtfx(ARCH, 1)
+        v, dt, out, isa = cpu_ref_run(ARCH, [0], cores)
         vals.append((v, dt))
-    value = float(np.mean([v for v, _ in vals]))
-    ms = float(np.mean([dt for _, dt in vals])) * 1e3
+    value = CLIP_SECONDS * len(vals) / sum(d for _, d in vals)
+    ms = float(np.mean([d for _, d in vals])) * 1e3
+    n_tok = sum(len(w["tokens"]) for w in out[0]["windows"])
     line = {
         "impl": "reference", "metric": "RTFx (audio-s per wall-s)", "value": value, "unit": "x real-time",
-        "n_gpus": args.gpus, "steps": steps, "warmup": 0, "ms_per_step": ms, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16 (ggml rounding points) / f32 accumulate", "data": "synthetic",
-        "config": {"workload": f"Whisper {ARCH} greedy decode, batch of {CLIPS_PER_GPU} synthetic 30 s 16 kHz clips per GPU "
-                               "(BASELINE.json configs[1]), random-init 'sharp' recipe seed 42, language en, timestamps on, "
-                               "no fallback", "arch": ARCH, "clips_per_gpu": CLIPS_PER_GPU,
-                   "sample": "each step = clip 0 of that batch (1 x 30 s), CPU only"},
+        "config": workload_config(ARCH, extra={"sample": "each step = clip 0 of that batch (1 x 30 s), CPU only, "
+                                                         f"{len(out[0]['windows'])} windows, {n_tok} decoded tokens",
+                                               "threads": cores, "isa": f"AVX{isa}"}),
         "cpu_baseline": {"value": value, "unit": "x real-time", "cores": cores, "kind": "port",
-                         "sample": "1 clip x 30 s per step, numpy/OpenBLAS oracle restating whisper.cpp "
-                                   "(reference not buildable here: no cargo/rustc, crates not vendored)"},
+                         "sample": f"1 clip x 30 s per step, {cores} std::threads; oracle/cpu_ref = C++ restatement of the whisper.cpp CPU "
+                                   "path, validated against the numpy oracle (reference not buildable here: no cargo/rustc, crates not vendored)"},
         "e2e": {"value": value, "unit": "x real-time", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
     return 0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--dtype", default=os.environ.get("SB_BENCH_DTYPE", "f16"), choices=["f16", "bf16"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
+def workload_config(arch: str, extra=None):
+    which = {"large-v3-turbo": "configs[2]", "small": "configs[1]", "large-v3": "configs[3] model"}.get(arch, "test architecture")
+    cfg = {"workload": f"Whisper {arch} greedy decode, batch of {CLIPS_PER_GPU} synthetic 30 s 16 kHz clips per GPU (BASELINE.json {which}), "
+                       "random-init 'sharp' recipe seed 42, language en, timestamps on, text context carried between the windows of a "
+                       "clip like whisper_full, no temperature fallback",
+           "arch": arch, "clips_per_gpu": CLIPS_PER_GPU}
+    if extra:
+        cfg.update(extra)
+    return cfg
 
-    import torch
-    from spittle_b200 import capi
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: spittle_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    warmup = max(3, args.warmup)
-    peaks, peak_src = load_peaks()
-
-    # rank 0 writes the synthetic model file once; other ranks wait for it
+def measure(arch, args, torch, capi, dist, rank, local_rank, world, steps, warmup, trace=True):
+    """Load `arch`, run warm-up + the two timed regions (device-resident PCM, pinned host PCM) + one traced batch."""
     if rank == 0:
-        path = model_path(ARCH)
+        model_path(arch)                  # rank 0 writes the synthetic model file once; other ranks wait for it
     if dist:
         dist.barrier()
-    path = model_path(ARCH)
+    path = model_path(arch)
     dtype = capi.SB_DTYPE_F16 if args.dtype == "f16" else capi.SB_DTYPE_BF16
     eng = capi.Engine(path, device=local_rank, max_batch=CLIPS_PER_GPU, dtype=dtype)
     clips = make_clips(rank, CLIPS_PER_GPU)
@@ -192,8 +239,6 @@ def main():
     host_ptrs = [host.data_ptr() + i * n * 4 for i in range(CLIPS_PER_GPU)]
     dev_ptrs = [devbuf.data_ptr() + i * n * 4 for i in range(CLIPS_PER_GPU)]
     sizes = [n] * CLIPS_PER_GPU
-    audio_s = CLIPS_PER_GPU * CLIP_SECONDS
-
     eng_stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
 
     def sync_all():
@@ -218,32 +263,87 @@ def main():
         torch.cuda.synchronize()
         ms_dev = e0.elapsed_time(e1)
         wall = (time.perf_counter() - t0) * 1e3
-        ms = max(ms_dev, wall)    # the call is synchronous: wall additionally covers host bookkeeping
+        ms_rank = max(ms_dev, wall)    # the call is synchronous: wall additionally covers host bookkeeping
+        ms = ms_rank
         if dist:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, res, eng.stats(reset=True), capi.launch_count() - l0
+        return ms, ms_rank, res, eng.stats(reset=True), capi.launch_count() - l0
 
     for _ in range(warmup):
         eng.transcribe_batch_ptrs(dev_ptrs, sizes, params)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_dev, res, st_dev, launches = timed(dev_ptrs, args.steps, profile=True)
-    ms_e2e, res2, st_e2e, _ = timed(host_ptrs, args.steps, profile=False)
+    ms_dev, ms_rank, res, st_dev, launches = timed(dev_ptrs, steps, profile=True)
+    ms_e2e, ms_e2e_rank, res2, st_e2e, _ = timed(host_ptrs, steps, profile=False)
     sampler.stop_flag.set()
     sampler.join(timeout=2)
+    st_dec = None
+    if trace:
+        # one more (untimed) batch with the device-side launch trace on (sb_engine_set_profile(e, 2)): every decoder-stage
+        # launch stamps %globaltimer at its first block's start and its last block's end.  The step keeps its CUDA graph,
+        # its lanes and its PDL overlap, so these are the durations inside the real chain.
+        eng.set_profile(2)
+        eng.stats(reset=True)
+        eng.transcribe_batch_ptrs(dev_ptrs, sizes, params)
+        st_dec = eng.stats(reset=True)
+        eng.set_profile(0)
+    n_mels = eng.info.n_mels
+    eng.close()
+    del devbuf
+    torch.cuda.empty_cache()
+    return dict(ms_dev=ms_dev, ms_rank=ms_rank, ms_e2e=ms_e2e, ms_e2e_rank=ms_e2e_rank, res=res, st_dev=st_dev, st_e2e=st_e2e,
+                st_dec=st_dec, launches=launches, clocks=sampler.summary(), n_mels=n_mels)
 
-    # one more (untimed) batch with the device-side launch trace on (sb_engine_set_profile(e, 2)): every decoder-stage
-    # launch stamps %globaltimer at its first block's start and its last block's end.  The step keeps its CUDA graph, its
-    # lanes and its PDL overlap, so these are the durations inside the real chain.
-    eng.set_profile(2)
-    eng.stats(reset=True)
-    eng.transcribe_batch_ptrs(dev_ptrs, sizes, params)
-    st_dec = eng.stats(reset=True)
-    eng.set_profile(0)
-    value = world * audio_s * args.steps / (ms_dev / 1e3)
-    e2e = world * audio_s * args.steps / (ms_e2e / 1e3)
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default=os.environ.get("SB_BENCH_DTYPE", "f16"), choices=["f16", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the Whisper Small (configs[1]) secondary entry")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from spittle_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: spittle_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    warmup = max(3, args.warmup)
+    steps = args.steps
+    peaks, peak_src = load_peaks()
+    audio_s = CLIPS_PER_GPU * CLIP_SECONDS
+
+    m = measure(ARCH, args, torch, capi, dist, rank, local_rank, world, steps, warmup)
+    ms_dev, ms_e2e, st_dev, st_e2e, st_dec, launches = m["ms_dev"], m["ms_e2e"], m["st_dev"], m["st_e2e"], m["st_dec"], m["launches"]
+
+    # per-rank breakdown (where does the N > 1 loss come from: device phases or the host side of a rank?)
+    mine = [m["ms_rank"] / steps, m["ms_e2e_rank"] / steps, st_dev["mel_ms"] / steps, st_dev["encode_ms"] / steps,
+            st_dev["decode_ms"] / steps, st_dev["decoder_steps"] / steps]
+    per_rank = [mine]
+    if dist:
+        t = torch.tensor(mine, device="cuda", dtype=torch.float64)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [[float(v) for v in x.tolist()] for x in allt]
+
+    value = world * audio_s * steps / (ms_dev / 1e3)
+    e2e = world * audio_s * steps / (ms_e2e / 1e3)
     gemm_tflops = st_dev["gemm_flops"] / max(st_dev["gemm_ms"], 1e-9) / 1e9
     attn_tflops = st_dev["attn_flops"] / max(st_dev["attn_ms"], 1e-9) / 1e9
     peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
@@ -251,39 +351,47 @@ def main():
     skinny_gbps = st_dec["skinny_bytes"] / max(st_dec["skinny_ms"], 1e-9) / 1e6
     xattn_gbps = st_dec["xattn_bytes"] / max(st_dec["xattn_ms"], 1e-9) / 1e6
     # log-mel: algorithmic bytes (PCM in + n_mel x 3000 f32 out per 30 s clip) over the engine's mel time
-    mel_bytes = CLIPS_PER_GPU * (480000 * 4 + eng.info.n_mels * 3000 * 4)
-    mel_gbps = mel_bytes * args.steps / max(st_dev["mel_ms"], 1e-9) / 1e6
+    mel_bytes = CLIPS_PER_GPU * (480000 * 4 + m["n_mels"] * 3000 * 4)
+    mel_gbps = mel_bytes * steps / max(st_dev["mel_ms"], 1e-9) / 1e6
+
+    secondary = None
+    if world == 1 and ARCH != "small" and not args.no_secondary:
+        # BASELINE.json configs[1] (Whisper Small, 64 clips, 1 GPU) carried as a secondary entry of the default run
+        m2 = measure("small", args, torch, capi, None, rank, local_rank, 1, min(steps, 5), 3, trace=False)
+        k2 = min(steps, 5)
+        secondary = {"workload": workload_config("small")["workload"], "value": audio_s * k2 / (m2["ms_dev"] / 1e3),
+                     "e2e": audio_s * k2 / (m2["ms_e2e"] / 1e3), "unit": "x real-time", "steps": k2, "ms_per_step": m2["ms_dev"] / k2,
+                     "ms_encode": m2["st_dev"]["encode_ms"] / k2, "ms_decode": m2["st_dev"]["decode_ms"] / k2,
+                     "decoder_steps_per_step": m2["st_dev"]["decoder_steps"] / k2}
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return 0
 
-    cpu_base = None
+    cpu_base = parity = None
     if world == 1 and not args.no_cpu_baseline:
-        v, dt, n_tok, n_win = cpu_port_rtfx(ARCH, 1)
-        cpu_base = {"value": v, "unit": "x real-time", "cores": os.cpu_count() or 1, "kind": "port",
-                    "sample": f"1 clip x 30 s of the same batch (clip 0), {n_win} window(s), {n_tok} decoded tokens, "
-                              f"{dt:.1f} s CPU wall; numpy/OpenBLAS oracle"}
-    steps = args.steps
+        cpu_base, cpu_results = cpu_baseline_block(ARCH)
+        parity = parity_block(m["res"], cpu_results)
     line = {
         "metric": "RTFx (audio-s per wall-s)", "value": value, "unit": "x real-time", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"Whisper {ARCH} greedy decode, batch of {CLIPS_PER_GPU} synthetic 30 s 16 kHz clips per GPU "
-                               "(BASELINE.json configs[1]), random-init 'sharp' recipe seed 42, language en, timestamps on, "
-                               "no fallback", "arch": ARCH, "clips_per_gpu": CLIPS_PER_GPU,
-                   "l2": "inputs+activations per step >> 126 MB L2; no explicit flush",
-                   "windows_per_step": st_dev["windows"] / steps, "decoder_steps_per_step": st_dev["decoder_steps"] / steps,
-                   "tokens_per_step": st_dev["tokens_sampled"] / steps,
-                   "ms_mel": st_dev["mel_ms"] / steps, "ms_encode": st_dev["encode_ms"] / steps,
-                   "ms_decode": st_dev["decode_ms"] / steps},
+        "config": workload_config(ARCH, extra={
+            "l2": "inputs+activations per step >> 126 MB L2; no explicit flush",
+            "windows_per_step": st_dev["windows"] / steps, "decoder_steps_per_step": st_dev["decoder_steps"] / steps,
+            "tokens_per_step": st_dev["tokens_sampled"] / steps, "encoder_batches_per_step": st_dev["rounds"] / steps,
+            "ms_mel": st_dev["mel_ms"] / steps, "ms_encode": st_dev["encode_ms"] / steps,
+            "ms_decode": st_dev["decode_ms"] / steps,
+            "phase_note": "ms_encode = sum of the encoder batches (refill batches overlap the decode lanes); ms_decode = the rest of the call",
+            "small_64": secondary}),
         "e2e": {"value": e2e, "unit": "x real-time", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": (st_e2e["pcm_bytes"] + st_e2e["h2d_bytes"]) / steps,
                 "d2h_bytes_per_step": st_e2e["d2h_bytes"] / steps},
         "gpu_launches": int(launches),
+        "per_rank": [dict(zip(("ms_per_step", "ms_per_step_e2e", "ms_mel", "ms_encode", "ms_decode", "decoder_steps"), r)) for r in per_rank],
         "roofline": None,
         "roofline_extra": None,
-        "clocks": sampler.summary(),
+        "clocks": m["clocks"],
     }
     # ---- rooflines: per-kernel entries, the one with the largest share of the timed step first ----
     skinny_avg_us = 1e3 * st_dec["skinny_ms"] / max(st_dec["skinny_launches"], 1)
@@ -342,6 +450,7 @@ def main():
     line["roofline_extra"] = entries[1:]
     if cpu_base:
         line["cpu_baseline"] = cpu_base
+        line["parity"] = parity
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
