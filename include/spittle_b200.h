@@ -296,6 +296,7 @@ typedef struct sb_stats {
     double skinny_ms, skinny_bytes, skinny_launches;
     double xattn_ms, xattn_bytes, xattn_launches;
     double dln_ms, dln_launches, dself_ms, dself_launches, dstep_ms, dstep_count;
+    double prefill_rows;              /* prompt tokens that went through the batched prefill pass */
 } sb_stats;
 
 SB_API void sb_params_default(sb_params* p);

@@ -146,7 +146,7 @@ class SbStats(C.Structure):
         "clips", "windows", "rounds", "decoder_steps", "tokens_sampled", "pcm_bytes", "h2d_bytes", "d2h_bytes",
         "mel_ms", "encode_ms", "decode_ms", "gemm_ms", "gemm_flops", "gemm_launches", "attn_ms", "attn_flops",
         "attn_launches", "skinny_ms", "skinny_bytes", "skinny_launches", "xattn_ms", "xattn_bytes", "xattn_launches",
-        "dln_ms", "dln_launches", "dself_ms", "dself_launches", "dstep_ms", "dstep_count")]
+        "dln_ms", "dln_launches", "dself_ms", "dself_launches", "dstep_ms", "dstep_count", "prefill_rows")]
 
 
 class SbWindowInfo(C.Structure):

@@ -102,8 +102,12 @@ bool use_tc_attention();   // env SB_ATTN=mma selects the legacy mma.sync kernel
 template <typename T> int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, const SkinnyEpilogue& ep, cudaStream_t st);
 template <typename T> int dec_ln(float* x, const float* gamma, const float* beta, T* out16, int rows, int d, const T* tok_emb, const float* pos_emb, const int* next_tokens, const SeqState* state, cudaStream_t st);
 // honor_done = 0: teacher-forced traces keep every sequence alive
-template <typename T> int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const SeqState* state, int honor_done, int Bn, int n_head, int d, int n_text_ctx, cudaStream_t st);
-template <typename T> int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t ld_kv, int64_t win_stride, T* out, const SeqState* state, int Bn, int n_head, int d, int n_ctx, cudaStream_t st);
+// row_slot / row_pos != null: prompt-prefill mode -- "sequence" b is prompt row b = (decode slot row_slot[b], position
+// row_pos[b]); plain launches (no PDL), nothing appended to the cache, `state` unused
+template <typename T> int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const SeqState* state, int honor_done, int Bn, int n_head, int d, int n_text_ctx, cudaStream_t st, const int* row_slot = nullptr, const int* row_pos = nullptr);
+template <typename T> int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t ld_kv, int64_t win_stride, T* out, const SeqState* state, int Bn, int n_head, int d, int n_ctx, cudaStream_t st, const int* row_slot = nullptr);
+template <typename T> int prefill_embed(const T* tok_emb, const float* pos_emb, const int* row_tok, const int* row_pos, float* x, int rows, int d, cudaStream_t st);
+template <typename T> int prefill_kv_scatter(const T* qkv, const int* row_slot, const int* row_pos, T* kc, T* vc, int rows, int d, int n_text_ctx, cudaStream_t st);
 int sample_step(const float* logits, int ld, const SamplerArgs& a, int Bn, cudaStream_t st);
 // whisper_lang_auto_detect: at prompt index 0 ([sot] alone at position 0) pick the language token with the largest logit
 // and write it into the language slot of every sequence whose slot holds the sentinel -1 (no-op for every other sequence)

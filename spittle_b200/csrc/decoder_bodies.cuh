@@ -288,7 +288,7 @@ constexpr int kCrossSmem = 1504 * 4 + 8 * 4 + 8 * 64 * 4;
 template <typename T, typename Sync>
 __device__ __forceinline__ void cross_attn_body(const T* __restrict__ q, int ldq, const T* __restrict__ kbase,
                                                        const T* __restrict__ vbase, int64_t ld_kv, int64_t win_stride,
-                                                       T* __restrict__ out, int d, int n_ctx, int h, int b,
+                                                       T* __restrict__ out, int d, int n_ctx, int h, int b, int bkv,
                                                        unsigned char* smem, Sync& sync, const TraceSlot& ts) {
     trace_begin(ts);
     float* s_sc = reinterpret_cast<float*>(smem);        // scores / probabilities
@@ -298,7 +298,7 @@ __device__ __forceinline__ void cross_attn_body(const T* __restrict__ q, int ldq
     const int sub = lane >> 3, ch = lane & 7;
     // this lane's keys: key(it, u) = it * 256 + u * 32 + warp * 4 + sub
     const int key_l = warp * 4 + sub;
-    const T* vp = vbase + (int64_t)b * win_stride + h * 64 + ch * 8 + (int64_t)key_l * ld_kv;
+    const T* vp = vbase + (int64_t)bkv * win_stride + h * 64 + ch * 8 + (int64_t)key_l * ld_kv;      // bkv: whose cross-KV (b: query / output row)
     const int64_t u_stride = 32 * ld_kv;
     // ---- pass 1: scores on the tensor cores.  A 16-key x 64-dim slab is the A operand of four m16n8k16 MMAs whose
     // B operand carries q in column 0 (the other seven columns are zero): lane (g = lane / 4, t = lane % 4) loads
@@ -310,7 +310,7 @@ __device__ __forceinline__ void cross_attn_body(const T* __restrict__ q, int ldq
     const int n_slab = (n_ctx + 15) >> 4;
     // load cursor: rows g / g + 8 of the next slab to request; slabs are requested in the order they are consumed
     // (warp, warp + 8, warp + 16, ...), so the cursor only ever advances by 128 rows
-    const T* kcur = kbase + (int64_t)b * win_stride + h * 64 + t * 8 + (int64_t)(warp * 16 + g) * ld_kv;
+    const T* kcur = kbase + (int64_t)bkv * win_stride + h * 64 + t * 8 + (int64_t)(warp * 16 + g) * ld_kv;
     const int64_t row8 = 8 * ld_kv, slab_step = 128 * ld_kv;
     int krow = warp * 16 + g;
     auto slab_load = [&](uint4 (&dst)[4]) {

@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(32) k_dec_ln(float* __restrict__ x, const floa
 template <typename T>
 __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc,
                                                        T* __restrict__ out, const SeqState* __restrict__ state, int honor_done,
-                                                       int n_head, int d, int n_text_ctx, TraceSlot ts) {
+                                                       int n_head, int d, int n_text_ctx, TraceSlot ts,
+                                                       const int* __restrict__ row_slot, const int* __restrict__ row_pos) {
     trace_begin(ts);
     __shared__ float s_p[448];
     __shared__ float s_red[4];
@@ -82,12 +83,17 @@ __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv
     // `done` and `pos` were written by the sampler of the previous step (many launches ago) and the cache
     // rows [0, pos) by earlier steps: all of it may be touched before the dependency wait, so the rows this block is
     // about to sweep are requested into L2 while the QKV projection in front of it is still finishing
-    const bool skip = honor_done && __ldcg(&state[b].done);   // finished sequences / empty slots are skipped
-    const int pos = min(__ldcg(&state[b].pos), n_text_ctx - 1);   // this sequence's new token; attends to [0, pos]
+    // prompt-prefill mode (row_slot != null): block row b is prompt token row_pos[b] of decode slot row_slot[b]; every row's
+    // K / V was scattered into the cache by the launch in front of this one (a plain launch, no PDL overlap), nothing is
+    // appended and nothing may be touched early
+    const bool rows = row_slot != nullptr;
+    const int sl = rows ? __ldg(row_slot + b) : b;
+    const bool skip = !rows && honor_done && __ldcg(&state[b].done);   // finished sequences / empty slots are skipped
+    const int pos = rows ? __ldg(row_pos + b) : min(__ldcg(&state[b].pos), n_text_ctx - 1);   // this sequence's new token; attends to [0, pos]
     const T* q = qkv + (int64_t)b * 3 * d + h * 64;
-    T* kb = kc + ((int64_t)b * n_text_ctx) * d + h * 64;
-    T* vb = vc + ((int64_t)b * n_text_ctx) * d + h * 64;
-    if (!skip) {
+    T* kb = kc + ((int64_t)sl * n_text_ctx) * d + h * 64;
+    T* vb = vc + ((int64_t)sl * n_text_ctx) * d + h * 64;
+    if (!skip && !rows) {
         for (int k = tid; k < pos; k += 128) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + (int64_t)k * d));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + (int64_t)k * d + 32));
@@ -97,7 +103,7 @@ __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv
     }
     // this thread's first key row (k = tid < pos) is an old cache row: it is loaded into registers before the wait
     uint4 kpre[8];
-    const bool has_pre = !skip && tid < pos;
+    const bool has_pre = !skip && !rows && tid < pos;
     if (has_pre) {
         const uint4* kr = reinterpret_cast<const uint4*>(kb + (int64_t)tid * d);
 #pragma unroll
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(128) k_dec_self_attn(const T* __restrict__ qkv
     pdl_wait();
     pdl_trigger();
     if (skip) return;
-    if (warp == 0) {                                     // append this step's K, V (each lane moves 2 elements)
+    if (warp == 0 && !rows) {                            // append this step's K, V (each lane moves 2 elements)
         reinterpret_cast<uint32_t*>(kb + (int64_t)pos * d)[lane] = __ldcg(reinterpret_cast<const uint32_t*>(q + d) + lane);
         reinterpret_cast<uint32_t*>(vb + (int64_t)pos * d)[lane] = __ldcg(reinterpret_cast<const uint32_t*>(q + 2 * d) + lane);
     }
@@ -204,13 +210,15 @@ template <typename T>
 __global__ void __launch_bounds__(256, 3) k_dec_cross_attn(const T* __restrict__ q, int ldq, const T* __restrict__ kbase,
                                                            const T* __restrict__ vbase, int64_t ld_kv, int64_t win_stride,
                                                            T* __restrict__ out, const SeqState* __restrict__ state, int d,
-                                                           int n_ctx, TraceSlot ts) {
+                                                           int n_ctx, TraceSlot ts, const int* __restrict__ row_slot) {
     __shared__ __align__(16) unsigned char smem[kCrossSmem];
     // a finished sequence no longer needs its 2 x 1500 x 64 keys/values streamed: `done` was written by the
     // sampler of an earlier step (many launches ago), so it may be read before the dependency wait
     if (state && __ldcg(&state[blockIdx.y].done)) { pdl_wait(); pdl_trigger(); return; }
     PdlSync sync;
-    cross_attn_body<T>(q, ldq, kbase, vbase, ld_kv, win_stride, out, d, n_ctx, blockIdx.x, blockIdx.y, smem, sync, ts);
+    // prompt-prefill mode: query row blockIdx.y attends over the cross-KV of decode slot row_slot[blockIdx.y]
+    const int kv = row_slot ? __ldg(row_slot + blockIdx.y) : blockIdx.y;
+    cross_attn_body<T>(q, ldq, kbase, vbase, ld_kv, win_stride, out, d, n_ctx, blockIdx.x, blockIdx.y, kv, smem, sync, ts);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -494,7 +502,51 @@ __global__ void __launch_bounds__(64) k_slot_init(const SlotInit* __restrict__ i
     if (threadIdx.x == 0) { state[slot] = it.state; next_tokens[slot] = it.next_token; if (lang_out) lang_out[slot] = -1; }
 }
 
+// ---- prompt prefill: all prompt tokens of the freshly assigned windows in one pass ------------------------------
+// x[r] = token_embedding[tok[r]] + positional_embedding[pos[r]]   (f32 rows for the tcgen05 GEMM chain)
+template <typename T>
+__global__ void __launch_bounds__(128) k_prefill_embed(const T* __restrict__ tok_emb, const float* __restrict__ pos_emb,
+                                                       const int* __restrict__ row_tok, const int* __restrict__ row_pos,
+                                                       float* __restrict__ x, int d) {
+    const int r = blockIdx.x;
+    const int tok = __ldg(row_tok + r), pos = __ldg(row_pos + r);
+    for (int i = threadIdx.x; i < d / 4; i += 128) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(tok_emb + (int64_t)tok * d) + i);
+        const float4 p = __ldg(reinterpret_cast<const float4*>(pos_emb + (int64_t)pos * d) + i);
+        const float2 a = Op16<T>::unpack2(u.x), b = Op16<T>::unpack2(u.y);
+        reinterpret_cast<float4*>(x + (int64_t)r * d)[i] = make_float4(a.x + p.x, a.y + p.y, b.x + p.z, b.y + p.w);
+    }
+}
+// K, V columns of qkv[r] -> self-KV cache row (slot[r], pos[r]) of one layer
+template <typename T>
+__global__ void __launch_bounds__(128) k_prefill_kv_scatter(const T* __restrict__ qkv, const int* __restrict__ row_slot,
+                                                            const int* __restrict__ row_pos, T* __restrict__ kc, T* __restrict__ vc,
+                                                            int d, int n_text_ctx) {
+    const int r = blockIdx.x;
+    const int64_t dst = ((int64_t)__ldg(row_slot + r) * n_text_ctx + __ldg(row_pos + r)) * d;
+    const uint4* src = reinterpret_cast<const uint4*>(qkv + (int64_t)r * 3 * d);
+    const int n16 = d / 8;
+    for (int i = threadIdx.x; i < n16; i += 128) {
+        reinterpret_cast<uint4*>(kc + dst)[i] = src[n16 + i];
+        reinterpret_cast<uint4*>(vc + dst)[i] = src[2 * n16 + i];
+    }
+}
+
 // ---- launchers -------------------------------------------------------------------------
+template <typename T>
+int prefill_embed(const T* tok_emb, const float* pos_emb, const int* row_tok, const int* row_pos, float* x, int rows, int d, cudaStream_t st) {
+    k_prefill_embed<T><<<rows, 128, 0, st>>>(tok_emb, pos_emb, row_tok, row_pos, x, d);
+    g_launches += 1;
+    SB_CUDA_CHECK(cudaGetLastError());
+    return SB_OK;
+}
+template <typename T>
+int prefill_kv_scatter(const T* qkv, const int* row_slot, const int* row_pos, T* kc, T* vc, int rows, int d, int n_text_ctx, cudaStream_t st) {
+    k_prefill_kv_scatter<T><<<rows, 128, 0, st>>>(qkv, row_slot, row_pos, kc, vc, d, n_text_ctx);
+    g_launches += 1;
+    SB_CUDA_CHECK(cudaGetLastError());
+    return SB_OK;
+}
 template <typename T>
 int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, const SkinnyEpilogue& ep, cudaStream_t st) {
     SB_CHECK_ARG(K % 32 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "skinny gemm: K % 32 and 16-byte row alignment required");
@@ -542,24 +594,26 @@ int dec_ln(float* x, const float* gamma, const float* beta, T* out16, int rows, 
 }
 template <typename T>
 int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const SeqState* state, int honor_done, int Bn, int n_head, int d,
-                  int n_text_ctx, cudaStream_t st) {
+                  int n_text_ctx, cudaStream_t st, const int* row_slot, const int* row_pos) {
     SB_CHECK_ARG(n_text_ctx <= 448 && d == n_head * 64, "self attention: n_text_ctx <= 448, d_head 64");
     const TraceSlot ts = g_trace_next; g_trace_next = TraceSlot();
     if (dbg_skip() & 8) return SB_OK;
-    launch_pdl(k_dec_self_attn<T>, dim3(n_head, Bn), dim3(128), 0, st, qkv, kc, vc, out, state, honor_done, n_head, d, n_text_ctx, ts);
+    if (row_slot) k_dec_self_attn<T><<<dim3(n_head, Bn), dim3(128), 0, st>>>(qkv, kc, vc, out, state, honor_done, n_head, d, n_text_ctx, ts, row_slot, row_pos);
+    else launch_pdl(k_dec_self_attn<T>, dim3(n_head, Bn), dim3(128), 0, st, qkv, kc, vc, out, state, honor_done, n_head, d, n_text_ctx, ts, row_slot, row_pos);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
 }
 template <typename T>
 int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t ld_kv, int64_t win_stride, T* out,
-                   const SeqState* state, int Bn, int n_head, int d, int n_ctx, cudaStream_t st) {
+                   const SeqState* state, int Bn, int n_head, int d, int n_ctx, cudaStream_t st, const int* row_slot) {
     SB_CHECK_ARG(n_ctx <= 1504 && d == n_head * 64 && d <= 1504 && d % 32 == 0 && ldq % 8 == 0 && ld_kv % 8 == 0,
                  "cross attention: n_audio_ctx, d <= 1504, d_head 64, 16-byte aligned rows");
     const TraceSlot ts = g_trace_next; g_trace_next = TraceSlot();
     if (dbg_skip() & 1) return SB_OK;
     dim3 grid(n_head, Bn);
-    launch_pdl(k_dec_cross_attn<T>, grid, dim3(256), 0, st, q, ldq, kbase, vbase, ld_kv, win_stride, out, state, d, n_ctx, ts);
+    if (row_slot) k_dec_cross_attn<T><<<grid, dim3(256), 0, st>>>(q, ldq, kbase, vbase, ld_kv, win_stride, out, state, d, n_ctx, ts, row_slot);
+    else launch_pdl(k_dec_cross_attn<T>, grid, dim3(256), 0, st, q, ldq, kbase, vbase, ld_kv, win_stride, out, state, d, n_ctx, ts, row_slot);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
@@ -592,8 +646,10 @@ int slot_init(const SlotInit* items, int n, SeqState* state, int* next_tokens, i
 #define SB_INST_D(T)                                                                                              \
     template int skinny_gemm<T>(const T*, int, const T*, int, int, int, int, const SkinnyEpilogue&, cudaStream_t); \
     template int dec_ln<T>(float*, const float*, const float*, T*, int, int, const T*, const float*, const int*, const SeqState*, cudaStream_t); \
-    template int dec_self_attn<T>(const T*, T*, T*, T*, const SeqState*, int, int, int, int, int, cudaStream_t);             \
-    template int dec_cross_attn<T>(const T*, int, const T*, const T*, int64_t, int64_t, T*, const SeqState*, int, int, int, int, cudaStream_t);
+    template int dec_self_attn<T>(const T*, T*, T*, T*, const SeqState*, int, int, int, int, int, cudaStream_t, const int*, const int*); \
+    template int dec_cross_attn<T>(const T*, int, const T*, const T*, int64_t, int64_t, T*, const SeqState*, int, int, int, int, cudaStream_t, const int*); \
+    template int prefill_embed<T>(const T*, const float*, const int*, const int*, float*, int, int, cudaStream_t);       \
+    template int prefill_kv_scatter<T>(const T*, const int*, const int*, T*, T*, int, int, int, cudaStream_t);
 SB_INST_D(__nv_bfloat16)
 SB_INST_D(__half)
 

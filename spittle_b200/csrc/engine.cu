@@ -183,8 +183,8 @@ struct Engine : EngineBase {
     DevBuf b_pcm, b_mel, b_cmax, b_floor, b_clipmeta, b_winmeta;
     DevBuf b_col1, b_c1, b_x, b_h, b_qkv, b_att, b_mlp, b_enc32;
     DevBuf b_ckv, b_kself, b_vself, b_dx, b_dh, b_dqkv, b_datt, b_dq, b_dmlp, b_logits;
-    DevBuf b_state, b_tokens, b_margins, b_tids, b_next, b_forced, b_tick, b_prompt, b_lang, b_init;
-    PinBuf h_state, h_tokens, h_margins, h_tids, h_lang, h_init, h_winmeta;   // host mirrors polled once per burst / slot-init staging
+    DevBuf b_state, b_tokens, b_margins, b_tids, b_next, b_forced, b_tick, b_prompt, b_lang, b_init, b_prow;
+    PinBuf h_state, h_tokens, h_margins, h_tids, h_lang, h_init, h_winmeta, h_prow;   // host mirrors polled once per burst / slot-init staging
     // profile == 2: device-side launch trace of the decoder step (TraceSlot, common.cuh)
     DevBuf b_trace;
     std::vector<int> trace_cls;          // class of launch idx inside a step: 0 projection, 1 LayerNorm, 2 self-attn, 3 cross-attn
@@ -260,6 +260,7 @@ struct Engine : EngineBase {
     int n_lanes_cfg = 2;
     int n_slots = 0, n_lanes = 0, n_max_cur = 0;
     int refill_min_cfg = 0;       // free slots needed before a refill encode is started (0: max(1, slots / 8))
+    int prefill_min = 8;          // prompts of at least this many tokens are prefilled in one pass (0: token-by-token feed)
 
     ~Engine() override {
         for (auto& l : lanes) {
@@ -274,9 +275,9 @@ struct Engine : EngineBase {
         DevBuf* bufs[] = {&b_pcm, &b_mel, &b_cmax, &b_floor, &b_clipmeta, &b_winmeta, &b_col1, &b_c1, &b_x, &b_h, &b_qkv,
                           &b_att, &b_mlp, &b_enc32, &b_ckv, &b_kself, &b_vself, &b_dx, &b_dh, &b_dqkv, &b_datt, &b_dq,
                           &b_dmlp, &b_logits, &b_state, &b_tokens, &b_margins, &b_tids, &b_next, &b_forced, &b_tick, &b_prompt,
-                          &b_lang, &b_init, &b_trace};
+                          &b_lang, &b_init, &b_trace, &b_prow};
         for (DevBuf* b : bufs) b->release();
-        PinBuf* pins[] = {&h_state, &h_tokens, &h_margins, &h_tids, &h_lang, &h_init, &h_winmeta};
+        PinBuf* pins[] = {&h_state, &h_tokens, &h_margins, &h_tids, &h_lang, &h_init, &h_winmeta, &h_prow};
         for (PinBuf* b : pins) b->release();
         if (melplan) sb_melplan_destroy(melplan);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -388,6 +389,7 @@ struct Engine : EngineBase {
         SB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         SB_CUDA_CHECK(cudaEventCreate(&ev_enc));
         if (const char* e = getenv("SB_REFILL_MIN")) refill_min_cfg = std::max(0, atoi(e));
+        if (const char* e = getenv("SB_PREFILL_MIN")) prefill_min = std::max(0, atoi(e));
         if (const char* e = getenv("SB_DECODE_LANES")) { n_lanes_cfg = atoi(e); if (n_lanes_cfg < 1) n_lanes_cfg = 1; if (n_lanes_cfg > kMaxLanes) n_lanes_cfg = kMaxLanes; }
         int rc = sb_melplan_create(f.mel_filters.data(), hp.n_mels, &melplan);
         if (rc) return rc;
@@ -737,6 +739,7 @@ struct Engine : EngineBase {
         int clip = 0, slot = 0, seek = 0, seek_end = 0;
         std::vector<int> prompt;      // full decoder prompt (language slot = -1 when it is to be detected)
         int lang_slot = -1, restart = 0;
+        int prefilled = 0;            // prompt tokens [0, prefilled) went through the batched prefill pass
     };
 
     // whisper_full's prompt of one window: [prev] + the last <= n_text_ctx/2 tokens of prompt_past (text context of this
@@ -765,6 +768,65 @@ struct Engine : EngineBase {
         }
     }
 
+    // Prompt prefill.  A window that carries text context has a prompt of up to 229 tokens; fed one token per decoder step
+    // it would hold its slot for as many steps before the first token is sampled.  Instead, all prompt tokens but the last
+    // of every job of a batch go through the decoder ONCE as rows of the encoder's tcgen05 GEMMs (M = total prompt tokens),
+    // with the decoder-step attention kernels in row mode (row -> (slot, position)); their K / V land in the slot's self-KV
+    // cache and the step loop starts at the last prompt token.  Runs on the main stream right after the encoder batch.
+    int prefill(std::vector<WinJob>& jobs) {
+        if (prefill_min <= 0) return SB_OK;
+        int R = 0;
+        for (const WinJob& j : jobs)
+            if (!j.restart && (int)j.prompt.size() - 1 >= prefill_min) R += (int)j.prompt.size() - 1;
+        if (R == 0) return SB_OK;
+        int rc;
+        if ((rc = b_prow.ensure((size_t)3 * R * 4))) return rc;
+        if ((rc = h_prow.ensure((size_t)3 * n_slots * kMaxPrompt * 4))) return rc;
+        int* hr = h_prow.as<int>();
+        int r = 0;
+        for (WinJob& j : jobs) {
+            if (j.restart || (int)j.prompt.size() - 1 < prefill_min) continue;
+            j.prefilled = (int)j.prompt.size() - 1;
+            for (int p_ = 0; p_ < j.prefilled; ++p_, ++r) { hr[r] = j.slot; hr[R + r] = p_; hr[2 * R + r] = j.prompt[p_]; }
+        }
+        SB_CUDA_CHECK(cudaMemcpyAsync(b_prow.p, hr, (size_t)3 * R * 4, cudaMemcpyHostToDevice, st));
+        stats.h2d_bytes += 12.0 * R;
+        const int* row_slot = b_prow.as<int>();
+        const int* row_pos = row_slot + R;
+        const int* row_tok = row_slot + 2 * R;
+        const int d = hp.n_text_state, nctx = hp.n_audio_ctx, S = n_slots;
+        const int nkv = hp.n_text_layer * 2 * d;
+        float* x = b_x.as<float>();
+        T* h = b_h.as<T>(); T* qkv = b_qkv.as<T>(); T* att = b_att.as<T>(); T* mlp = b_mlp.as<T>();
+        if ((rc = prefill_embed<T>(tok_emb, dec_pos, row_tok, row_pos, x, R, d, st))) return rc;
+        for (int l = 0; l < hp.n_text_layer; ++l) {
+            const DecLayer<T>& L = dec[l];
+            T* kc = b_kself.as<T>() + (int64_t)l * S * hp.n_text_ctx * d;
+            T* vc = b_vself.as<T>() + (int64_t)l * S * hp.n_text_ctx * d;
+            if ((rc = layernorm<T>(x, L.ln1.g, L.ln1.b, h, nullptr, R, d, st))) return rc;
+            GemmEpilogue ep{qkv, 3 * d, 0, L.qkv.b, 0, nullptr, 0, 0};
+            if ((rc = gemm_tn(dtype, h, d, L.qkv.w, d, R, 3 * d, d, ep, st))) return rc;
+            if ((rc = prefill_kv_scatter<T>(qkv, row_slot, row_pos, kc, vc, R, d, hp.n_text_ctx, st))) return rc;
+            if ((rc = dec_self_attn<T>(qkv, kc, vc, att, nullptr, 0, R, hp.n_text_head, d, hp.n_text_ctx, st, row_slot, row_pos))) return rc;
+            ep = GemmEpilogue{x, d, 1, L.o.b, 0, x, d, 0};
+            if ((rc = gemm_tn(dtype, att, d, L.o.w, d, R, d, d, ep, st))) return rc;
+            if ((rc = layernorm<T>(x, L.ln2.g, L.ln2.b, h, nullptr, R, d, st))) return rc;
+            ep = GemmEpilogue{qkv, d, 0, L.cq.b, 0, nullptr, 0, 0};
+            if ((rc = gemm_tn(dtype, h, d, L.cq.w, d, R, d, d, ep, st))) return rc;
+            const T* kb = b_ckv.as<T>() + (int64_t)l * 2 * d;
+            if ((rc = dec_cross_attn<T>(qkv, d, kb, kb + d, nkv, (int64_t)nctx * nkv, att, nullptr, R, hp.n_text_head, d, nctx, st, row_slot))) return rc;
+            ep = GemmEpilogue{x, d, 1, L.co.b, 0, x, d, 0};
+            if ((rc = gemm_tn(dtype, att, d, L.co.w, d, R, d, d, ep, st))) return rc;
+            if ((rc = layernorm<T>(x, L.ln3.g, L.ln3.b, h, nullptr, R, d, st))) return rc;
+            ep = GemmEpilogue{mlp, 4 * d, 0, L.fc1.b, 1, nullptr, 0, 0};
+            if ((rc = gemm_tn(dtype, h, d, L.fc1.w, d, R, 4 * d, d, ep, st))) return rc;
+            ep = GemmEpilogue{x, d, 1, L.fc2.b, 0, x, d, 0};
+            if ((rc = gemm_tn(dtype, mlp, 4 * d, L.fc2.w, 4 * d, R, d, 4 * d, ep, st))) return rc;
+        }
+        stats.prefill_rows += R;
+        return SB_OK;
+    }
+
     // scatter the jobs into their slots: staged per lane in pinned memory, copied and applied on the lane's own stream
     // (in order with the lane's steps, after the encoder's cross-KV for these slots is complete: ev_enc)
     int init_slots(const std::vector<WinJob>& jobs) {
@@ -782,6 +844,8 @@ struct Engine : EngineBase {
                 SeqState s{};
                 s.seek_delta = 3000; s.seek = j.seek; s.seek_end = j.seek_end;
                 s.n_prompt = (int)j.prompt.size(); s.lang_slot = j.lang_slot; s.restart = j.restart;
+                s.idx = s.pos = j.prefilled;           // the step loop continues after the prefilled part of the prompt
+                it.next_token = j.prompt[j.prefilled];
                 it.state = s;
                 for (size_t k = 0; k < j.prompt.size(); ++k) it.prompt[k] = j.prompt[k];
                 ++cnt;
@@ -931,14 +995,15 @@ struct Engine : EngineBase {
         if ((rc = stage_mel_windows(mel_windows, W))) return rc;
         if ((rc = encode_chunk(W, nullptr, nullptr))) return rc;
         if (forced) SB_CUDA_CHECK(cudaMemcpyAsync(b_forced.p, forced, (size_t)W * n_steps * 4, cudaMemcpyHostToDevice, st));
-        SB_CUDA_CHECK(cudaEventRecord(ev_enc, st));
         std::vector<WinJob> jobs(W);
         for (int w = 0; w < W; ++w) {
             jobs[w].clip = w; jobs[w].slot = w; jobs[w].seek = 0; jobs[w].seek_end = seek_end[w];
             build_prompt(jobs[w], past, lang, p);
         }
+        if ((rc = prefill(jobs))) return rc;
+        SB_CUDA_CHECK(cudaEventRecord(ev_enc, st));
         if ((rc = init_slots(jobs))) return rc;
-        const int feed = (int)jobs[0].prompt.size() - 1;         // the prompt is the same for every window here
+        const int feed = (int)jobs[0].prompt.size() - 1 - jobs[0].prefilled;         // the prompt is the same for every window here
         const int total_steps = feed + n_steps;
         const int vpad = (int)round_up(hp.n_vocab, 8);
         if (logits_out) {
@@ -1154,6 +1219,7 @@ struct Engine : EngineBase {
                                       2 * hp.n_audio_ctx};
                         if ((rc = im2col_conv1<T>(a, b_col1.as<T>(), k, st))) return rc;
                         if ((rc = encode_chunk(k, slots.data(), nullptr))) return rc;
+                        if ((rc = prefill(pending))) return rc;
                         SB_CUDA_CHECK(cudaEventRecord(ev_enc, st));
                         pend_active = true;
                         stats.windows += k; stats.rounds += 1;
@@ -1457,7 +1523,7 @@ int sb_decode_trace(sb_engine* e, const float* mel_windows, int n_windows, const
     X(sb_result, n_sampled) X(sb_result, margins) X(sb_result, tids) X(sb_result, windows) X(sb_result, n_windows)      \
     X(sb_result, segments) X(sb_result, n_segments) X(sb_result, segment_text) X(sb_result, ms_mel)                     \
     X(sb_result, ms_encode) X(sb_result, ms_decode) X(sb_result, status) X(sb_result, lang_id)                          \
-    X(sb_model_info, n_vocab) X(sb_model_info, token_blank) X(sb_stats, clips) X(sb_stats, dstep_count)
+    X(sb_model_info, n_vocab) X(sb_model_info, token_blank) X(sb_stats, clips) X(sb_stats, dstep_count) X(sb_stats, prefill_rows)
 
 int sb_abi_layout(sb_abi_field* out, int cap) {
     static const sb_abi_field rows[] = {

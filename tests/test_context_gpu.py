@@ -293,3 +293,45 @@ def test_engine_over_two_devices(nano):
     assert dev1.transcribe(clips[3], params).sampled == want[3].sampled
     dev1.close()
     two.close()
+
+
+def test_prompt_prefill_equals_token_by_token_feed(nano):
+    """Prompts of >= 8 tokens go through the decoder in ONE batched pass (tcgen05 GEMMs over all prompt rows, attention
+    kernels in row mode) instead of one token per step; SB_PREFILL_MIN=0 keeps the token-by-token feed.  Same tokens --
+    up to a step where the engine's own top-1 / top-2 margin is indecisive (different f32 summation order)."""
+    import os
+    path, model, oracle = nano
+    prompt = " ".join(model.vocab[i].decode().strip() for i in range(2000, 2000 + 2 * 90, 2))
+    clips = [np.concatenate([synth.make_clip(1, 30.0), synth.make_clip(2, 30.0), synth.make_clip(4, 9.0)]), synth.make_clip(5, 16.0)]
+    params = capi.default_params(n_max_tokens=24, max_windows=3, initial_prompt=prompt)
+    eng = capi.Engine(path, dtype=capi.SB_DTYPE_F16, max_batch=4)
+    eng.stats(reset=True)
+    fast = eng.transcribe_batch(clips, params)
+    rows = eng.stats()["prefill_rows"]
+    eng.close()
+    assert rows >= sum(w["n_prompt"] - 1 for r in fast for w in r.windows if w["n_prompt"] - 1 >= 8) > 200
+    os.environ["SB_PREFILL_MIN"] = "0"
+    try:
+        slow_eng = capi.Engine(path, dtype=capi.SB_DTYPE_F16, max_batch=4)
+        slow_eng.stats(reset=True)
+        slow = slow_eng.transcribe_batch(clips, params)
+        assert slow_eng.stats()["prefill_rows"] == 0
+        slow_eng.close()
+    finally:
+        os.environ.pop("SB_PREFILL_MIN", None)
+    n_same = 0
+    for a, b in zip(fast, slow):
+        for wa, wb in zip(a.windows, b.windows):
+            ta = a.sampled[wa["token_offset"]: wa["token_offset"] + wa["n_tokens"]]
+            tb = b.sampled[wb["token_offset"]: wb["token_offset"] + wb["n_tokens"]]
+            assert wa["n_prompt"] == wb["n_prompt"]
+            if ta != tb:
+                k = next(i for i in range(min(len(ta), len(tb))) if ta[i] != tb[i])
+                assert min(a.margins[wa["token_offset"] + k], b.margins[wb["token_offset"] + k]) < MARGIN_TOL
+                break
+            n_same += 1
+    assert n_same >= 2
+    # and against the oracle
+    toks = capi.Engine(path, max_batch=1).tokenize(prompt)
+    _, _, wins = oracle.full(clips[1], whisper_ref.DecodeConfig(n_max_override=24, initial_prompt_tokens=toks), max_windows=3)
+    _compare_windows(fast[1], wins, "prefill vs oracle")
