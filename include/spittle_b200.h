@@ -243,6 +243,16 @@ typedef struct sb_params {
     int max_windows;             /* 0 -> unlimited; safety cap on the seek loop */
     int n_max_text_ctx;          /* whisper_full_params.n_max_text_ctx (default 16384): tokens of text context carried from one
                                     window of a clip to the next ([prev] + last min(this, n_text_ctx/2) tokens); <= 0 disables */
+    /* Temperature fallback (whisper_full): a window is decoded at `temperature`; when the result fails (timestamps went
+     * backwards, no timestamp before n_max, token entropy of the last 32 tokens < entropy_thold) or its mean token
+     * log-probability is below logprob_thold, it is decoded again at temperature + temperature_inc, ... up to 1.0.  At a
+     * temperature > 0 tokens are DRAWN (best_of = 1) with a per-clip std::mt19937(0) stream like whisper.cpp; from 0.5 up the
+     * text context is dropped from the prompt.  temperature_inc = 0 (the pinned parity configuration, sb_params_default)
+     * disables the fallback; whisper.cpp's own defaults are 0.0 / 0.2 / -1.0 / 2.4. */
+    float temperature;
+    float temperature_inc;
+    float logprob_thold;
+    float entropy_thold;
 } sb_params;
 
 typedef struct sb_window_info {
@@ -253,6 +263,9 @@ typedef struct sb_window_info {
     int32_t failed;
     int32_t token_offset;    /* offset of this window's sampled tokens in sb_result.sampled */
     int32_t n_prompt;        /* decoder prompt length of this window: [prev + text context] + [sot, lang, task, ...] */
+    float temperature;       /* temperature of the accepted decode of this window */
+    int32_t n_attempts;      /* decodes of this window (1 + temperature fallbacks) */
+    float avg_logprob;       /* mean log-probability of the kept tokens (whisper_sequence_score) */
 } sb_window_info;
 
 /* One segment of the transcript (transcribe-rs TranscriptionResult.segments = whisper_full_get_segment_{t0,t1,text}):
@@ -271,6 +284,7 @@ typedef struct sb_result {
     int32_t* sampled; size_t n_sampled;    /* every sampled token, all windows */
     float* margins;                        /* [n_sampled] top1-top2 of the filtered logits */
     int32_t* tids;                         /* [n_sampled] whisper_token_data.tid: most probable timestamp token of each step */
+    float* logprobs;                       /* [n_sampled] whisper_token_data.plog: log-probability of each sampled token */
     sb_window_info* windows; size_t n_windows;
     sb_segment* segments; size_t n_segments;
     char* segment_text;                    /* storage of the segment texts */
@@ -297,6 +311,7 @@ typedef struct sb_stats {
     double xattn_ms, xattn_bytes, xattn_launches;
     double dln_ms, dln_launches, dself_ms, dself_launches, dstep_ms, dstep_count;
     double prefill_rows;              /* prompt tokens that went through the batched prefill pass */
+    double fallbacks;                 /* windows decoded again at a higher temperature */
 } sb_stats;
 
 SB_API void sb_params_default(sb_params* p);

@@ -80,6 +80,15 @@ class DecodeConfig:
     # whisper-rs' defaults) only clears what an EARLIER call left behind.  n_max_text_ctx = 0 switches the prefix off.
     initial_prompt_tokens: Optional[List[int]] = None
     n_max_text_ctx: int = 16384
+    # Temperature fallback [MEM]: whisper_full decodes a window at `temperature`; if the decode failed, or the mean
+    # log-probability of its kept tokens is below logprob_thold, or (more than 32 kept tokens) the entropy of the last 32
+    # is below entropy_thold, it decodes it again at temperature + temperature_inc, ... up to 1.0.  At temperature > 0 the
+    # token is drawn with std::discrete_distribution over the decoder's std::mt19937(0) (best_of = 1); from 0.5 up the text
+    # context is dropped from the prompt.  temperature_inc = 0 is the pinned parity configuration (no fallback).
+    temperature: float = 0.0
+    temperature_inc: float = 0.0
+    logprob_thold: float = -1.0
+    entropy_thold: float = 2.4
 
 
 @dataclass
@@ -90,6 +99,14 @@ class WindowResult:
     failed: bool
     logits_trace: Optional[List[np.ndarray]] = None  # raw logits at each sampling step
     margins: List[float] = field(default_factory=list)  # top1-top2 of filtered logits
+    plogs: List[float] = field(default_factory=list)    # log-probability of every sampled token
+    temperature: float = 0.0
+    attempts: int = 1
+    avg_logprob: float = float("nan")
+    # temperature > 0: distance (in probability mass) of the uniform number from the nearer edge of the drawn token's
+    # interval of the cumulative distribution -- a draw with a small margin may legitimately differ between two
+    # implementations whose logits differ by rounding
+    draw_margins: List[float] = field(default_factory=list)
 
 
 class WhisperOracle:
@@ -223,10 +240,12 @@ class WhisperOracle:
 
     # -- logits filter + sampler (App. C.4) -------------------------------------------
     def process_logits(self, logits: np.ndarray, tokens_cur: List[int], has_ts: bool,
-                       seek_delta: int, cfg: DecodeConfig):
+                       seek_delta: int, cfg: DecodeConfig, temperature: float = 0.0):
         sp = self.sp
         n = logits.shape[0]
         lg = logits.astype(F32).copy()
+        if temperature > 0.0:
+            lg = (lg / F32(temperature)).astype(F32)
         NEG = F32(-np.inf)
         is_initial = len(tokens_cur) == 0
         if cfg.suppress_blank and is_initial:
@@ -286,12 +305,12 @@ class WhisperOracle:
     # -- one 30 s window ---------------------------------------------------------------
     def decode_window(self, enc: np.ndarray, seek: int, seek_end: int, cfg: DecodeConfig,
                       trace: bool = False, forced: Optional[List[int]] = None,
-                      prompt_past: Optional[List[int]] = None) -> WindowResult:
+                      prompt_past: Optional[List[int]] = None, temperature: float = 0.0, rng=None) -> WindowResult:
         hp, sp = self.hp, self.sp
         kv_cross = self.cross_kv(enc)
         kv_self = self.new_kv()
         prompt = []
-        if prompt_past and cfg.n_max_text_ctx > 0:       # temperature is 0 here (< 0.5)
+        if prompt_past and cfg.n_max_text_ctx > 0 and temperature < 0.5:
             n_take = min(cfg.n_max_text_ctx, hp.n_text_ctx // 2, len(prompt_past))
             prompt = [sp.prev] + list(prompt_past[len(prompt_past) - n_take:])
         prompt.append(sp.sot)
@@ -315,16 +334,29 @@ class WhisperOracle:
         failed = False
         tr: List[np.ndarray] = []
         margins: List[float] = []
+        plogs: List[float] = []
+        draw_margins: List[float] = []
         for i in range(n_max):
-            lg, logprobs, probs = self.process_logits(logits, tokens, has_ts, seek_delta, cfg)
+            lg, logprobs, probs = self.process_logits(logits, tokens, has_ts, seek_delta, cfg, temperature)
             if trace:
                 tr.append(logits.copy())
             top2 = np.partition(lg, -2)[-2:]
             margins.append(float(top2[1] - top2[0]))
-            tid = self.sample_best(probs)
+            if temperature > 0.0 and rng is not None:
+                # whisper_sample_token(best = false): std::discrete_distribution over probs -- normalised in double,
+                # cumulative sums with the last one pinned to 1.0, first index whose cumulative probability is >= u
+                p64 = probs.astype(np.float64)
+                cp = np.cumsum(p64 / p64.sum())
+                cp[-1] = 1.0
+                u = rng.uniform()
+                tid = int(np.searchsorted(cp, u, side="left"))
+                draw_margins.append(float(min(cp[tid] - u, u - (cp[tid - 1] if tid > 0 else 0.0))))
+            else:
+                tid = self.sample_best(probs)
             if forced is not None and i < len(forced):
                 tid = forced[i]
             tokens.append(tid)
+            plogs.append(float(logprobs[tid]))
             # bookkeeping
             completed = False
             if tid > sp.beg:
@@ -353,7 +385,10 @@ class WhisperOracle:
                 break
             logits = self.decode_step(tid, n_past, kv_self, kv_cross)
             n_past += 1
-        return WindowResult(tokens, result_len, seek_delta, failed, tr if trace else None, margins)
+        n = min(result_len, len(tokens))
+        avg = float(np.sum(np.asarray(plogs[:n], np.float64)) / n) if n > 0 else float("nan")
+        return WindowResult(tokens, result_len, seek_delta, failed, tr if trace else None, margins, plogs, temperature, 1, avg,
+                            draw_margins)
 
     def detect_language(self, enc: np.ndarray):
         """whisper.cpp whisper_lang_auto_detect_with_state (App. C.4 / reference default selected_language
@@ -381,6 +416,8 @@ class WhisperOracle:
         kept: List[int] = []
         text = b""
         prompt_past: List[int] = list(cfg.initial_prompt_tokens or [])
+        from .mt19937 import Mt19937
+        rng = Mt19937(0)
         if seek_end < seek + 100:
             return b"", kept, windows
         while len(windows) < max_windows:
@@ -393,11 +430,29 @@ class WhisperOracle:
                 self.last_detected_language = lang
             if seek > 0 and seek + 500 >= seek_end:      # a very short tail: whisper.cpp drops the text context
                 prompt_past = []
-            w = self.decode_window(enc, seek, seek_end, cfg, prompt_past=prompt_past)
+            # temperature schedule of whisper_full (one decoder, best_of = 1)
+            t_cur, attempts = max(0.0, cfg.temperature), 0
+            while True:
+                w = self.decode_window(enc, seek, seek_end, cfg, prompt_past=prompt_past, temperature=t_cur, rng=rng)
+                attempts += 1
+                n = min(w.result_len, len(w.tokens))
+                failed = w.failed
+                if n > 32:
+                    _, counts = np.unique(np.asarray(w.tokens[n - 32:n]), return_counts=True)
+                    pr = counts / 32.0
+                    if float(-(pr * np.log(pr)).sum()) < cfg.entropy_thold:
+                        failed = True
+                success = not (failed or w.avg_logprob < cfg.logprob_thold)
+                t_next = np.float32(t_cur) + np.float32(cfg.temperature_inc)
+                if success or cfg.temperature_inc <= 0.0 or not (t_next < 1.0 + 1e-6):
+                    break
+                t_cur = float(t_next)
+            w.attempts = attempts
             windows.append(w)
             toks = w.tokens[: w.result_len]
             # prompt_past = the part of it this window used + this window's kept tokens
-            n_take = min(cfg.n_max_text_ctx, self.hp.n_text_ctx // 2, len(prompt_past)) if cfg.n_max_text_ctx > 0 else 0
+            n_take = min(cfg.n_max_text_ctx, self.hp.n_text_ctx // 2, len(prompt_past)) \
+                if (cfg.n_max_text_ctx > 0 and w.temperature < 0.5) else 0
             prompt_past = list(prompt_past[len(prompt_past) - n_take:]) + list(toks)
             kept.extend(toks)
             for t in toks:

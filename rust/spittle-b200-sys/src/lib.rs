@@ -36,12 +36,17 @@ pub struct sb_params {
     pub n_max_tokens: c_int,
     pub max_windows: c_int,
     pub n_max_text_ctx: c_int,
+    pub temperature: c_float,
+    pub temperature_inc: c_float,       // 0 = no temperature fallback (sb_params_default)
+    pub logprob_thold: c_float,
+    pub entropy_thold: c_float,
 }
 
 #[repr(C)]
 pub struct sb_window_info {
     pub seek: i32, pub n_tokens: i32, pub result_len: i32, pub seek_delta: i32, pub failed: i32, pub token_offset: i32,
     pub n_prompt: i32,
+    pub temperature: c_float, pub n_attempts: i32, pub avg_logprob: c_float,
 }
 
 #[repr(C)]
@@ -58,6 +63,7 @@ pub struct sb_result {
     pub sampled: *mut i32, pub n_sampled: size_t,
     pub margins: *mut c_float,
     pub tids: *mut i32,
+    pub logprobs: *mut c_float,
     pub windows: *mut sb_window_info, pub n_windows: size_t,
     pub segments: *mut sb_segment, pub n_segments: size_t,
     pub segment_text: *mut c_char,
@@ -73,24 +79,24 @@ pub struct sb_abi_field { pub struct_name: *const c_char, pub field: *const c_ch
 const _: () = assert!(size_of::<sb_config>() == 40);
 const _: () = assert!(offset_of!(sb_config, devices) == 24);
 const _: () = assert!(offset_of!(sb_config, n_devices) == 32);
-const _: () = assert!(size_of::<sb_params>() == 56);
+const _: () = assert!(size_of::<sb_params>() == 72);
 const _: () = assert!(offset_of!(sb_params, initial_prompt) == 16);
 const _: () = assert!(offset_of!(sb_params, max_initial_ts) == 36);
 const _: () = assert!(offset_of!(sb_params, n_max_text_ctx) == 48);
-const _: () = assert!(size_of::<sb_window_info>() == 28);
+const _: () = assert!(size_of::<sb_window_info>() == 40);
 const _: () = assert!(offset_of!(sb_window_info, n_prompt) == 24);
 const _: () = assert!(size_of::<sb_segment>() == 40);
 const _: () = assert!(offset_of!(sb_segment, text) == 16);
 const _: () = assert!(offset_of!(sb_segment, n_tokens) == 36);
-const _: () = assert!(size_of::<sb_result>() == 128);
+const _: () = assert!(size_of::<sb_result>() == 136);
 const _: () = assert!(offset_of!(sb_result, margins) == 48);
 const _: () = assert!(offset_of!(sb_result, tids) == 56);
-const _: () = assert!(offset_of!(sb_result, windows) == 64);
-const _: () = assert!(offset_of!(sb_result, segments) == 80);
-const _: () = assert!(offset_of!(sb_result, segment_text) == 96);
-const _: () = assert!(offset_of!(sb_result, ms_mel) == 104);
-const _: () = assert!(offset_of!(sb_result, status) == 116);
-const _: () = assert!(offset_of!(sb_result, lang_id) == 120);
+const _: () = assert!(offset_of!(sb_result, windows) == 72);
+const _: () = assert!(offset_of!(sb_result, segments) == 88);
+const _: () = assert!(offset_of!(sb_result, segment_text) == 104);
+const _: () = assert!(offset_of!(sb_result, ms_mel) == 112);
+const _: () = assert!(offset_of!(sb_result, status) == 124);
+const _: () = assert!(offset_of!(sb_result, lang_id) == 128);
 
 extern "C" {
     pub fn sb_last_error() -> *const c_char;

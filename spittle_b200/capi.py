@@ -138,7 +138,8 @@ class SbParams(C.Structure):
     _fields_ = [("language", C.c_char_p), ("translate", C.c_int), ("initial_prompt", C.c_char_p),
                 ("no_timestamps", C.c_int), ("suppress_blank", C.c_int), ("single_segment", C.c_int),
                 ("max_initial_ts", C.c_float), ("n_max_tokens", C.c_int), ("max_windows", C.c_int),
-                ("n_max_text_ctx", C.c_int)]
+                ("n_max_text_ctx", C.c_int), ("temperature", C.c_float), ("temperature_inc", C.c_float),
+                ("logprob_thold", C.c_float), ("entropy_thold", C.c_float)]
 
 
 class SbStats(C.Structure):
@@ -146,12 +147,13 @@ class SbStats(C.Structure):
         "clips", "windows", "rounds", "decoder_steps", "tokens_sampled", "pcm_bytes", "h2d_bytes", "d2h_bytes",
         "mel_ms", "encode_ms", "decode_ms", "gemm_ms", "gemm_flops", "gemm_launches", "attn_ms", "attn_flops",
         "attn_launches", "skinny_ms", "skinny_bytes", "skinny_launches", "xattn_ms", "xattn_bytes", "xattn_launches",
-        "dln_ms", "dln_launches", "dself_ms", "dself_launches", "dstep_ms", "dstep_count", "prefill_rows")]
+        "dln_ms", "dln_launches", "dself_ms", "dself_launches", "dstep_ms", "dstep_count", "prefill_rows", "fallbacks")]
 
 
 class SbWindowInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("seek", "n_tokens", "result_len", "seek_delta", "failed", "token_offset",
-                                         "n_prompt")]
+                                         "n_prompt")] + [("temperature", C.c_float), ("n_attempts", C.c_int32),
+                                                         ("avg_logprob", C.c_float)]
 
 
 class SbSegment(C.Structure):
@@ -163,7 +165,7 @@ class SbResult(C.Structure):
     _fields_ = [("text", C.POINTER(C.c_char)), ("text_len", C.c_size_t),
                 ("tokens", C.POINTER(C.c_int32)), ("n_tokens", C.c_size_t),
                 ("sampled", C.POINTER(C.c_int32)), ("n_sampled", C.c_size_t),
-                ("margins", C.POINTER(C.c_float)), ("tids", C.POINTER(C.c_int32)),
+                ("margins", C.POINTER(C.c_float)), ("tids", C.POINTER(C.c_int32)), ("logprobs", C.POINTER(C.c_float)),
                 ("windows", C.POINTER(SbWindowInfo)), ("n_windows", C.c_size_t),
                 ("segments", C.POINTER(SbSegment)), ("n_segments", C.c_size_t), ("segment_text", C.POINTER(C.c_char)),
                 ("ms_mel", C.c_float), ("ms_encode", C.c_float), ("ms_decode", C.c_float),
@@ -227,8 +229,10 @@ class ClipResult:
         self.sampled = [r.sampled[i] for i in range(r.n_sampled)]
         self.margins = [r.margins[i] for i in range(r.n_sampled)]
         self.tids = [r.tids[i] for i in range(r.n_sampled)]
+        self.logprobs = [r.logprobs[i] for i in range(r.n_sampled)]
         self.windows = [dict(seek=w.seek, n_tokens=w.n_tokens, result_len=w.result_len, seek_delta=w.seek_delta,
-                             failed=w.failed, token_offset=w.token_offset, n_prompt=w.n_prompt)
+                             failed=w.failed, token_offset=w.token_offset, n_prompt=w.n_prompt, temperature=w.temperature,
+                             n_attempts=w.n_attempts, avg_logprob=w.avg_logprob)
                         for w in (r.windows[i] for i in range(r.n_windows))]
         self.segments = [dict(t0=g.t0, t1=g.t1, text=C.string_at(g.text, g.text_len), token_offset=g.token_offset,
                               n_tokens=g.n_tokens) for g in (r.segments[i] for i in range(r.n_segments))]

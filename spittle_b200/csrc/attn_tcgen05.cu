@@ -1,4 +1,4 @@
-// k_attn_enc_tc: encoder self-attention (non-causal, d_head 64, T = 1500) on tcgen05 / TMEM.
+// k_attn_enc_ts: encoder self-attention (non-causal, d_head 64, T = 1500) on tcgen05 / TMEM.
 //
 // Replaces the KQ / softmax / KQV part of the whisper.cpp encoder graph.
 // One CTA = one (window, head, 128-query tile).  S = Q K^T and O = P V are tcgen05.mma with the
@@ -32,16 +32,6 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int is_f16, int64_t rows, in
 
 constexpr int kAtBM = 128;            // queries per CTA
 constexpr int kAtD = 64;
-constexpr int kAtKvStages = 4;
-constexpr int kAtQBytes = 128 * 64 * 2;
-// BN = keys per tile: 128 (512 TMEM columns, 1 CTA/SM) or 64 (256 columns, 2 CTAs/SM so one CTA's
-// pipeline bubbles -- prologue, pass switch, epilogue -- are covered by the other's work)
-template <int BN> struct AtCfg {
-    static constexpr int kTileBytes = BN * 64 * 2;            // K or V tile
-    static constexpr int kPBytes = 128 * BN * 2;              // P tile: BN/64 swizzle atoms of 16 KB
-    static constexpr int kSmem = 1024 + kAtQBytes + kAtKvStages * kTileBytes + 2 * kPBytes + 256 + 2 * 128 * 4;
-    static constexpr int kTmemCols = BN == 128 ? 512 : 256;   // 2 x BN (S double buffer) + 64 (O), power of two
-};
 constexpr int kAtThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two per TMEM lane quarter)
 
 __device__ __forceinline__ uint32_t at_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -130,282 +120,11 @@ __device__ __forceinline__ uint64_t at_desc(uint32_t saddr) {
     return d;
 }
 
-template <typename T, int BN>
-__global__ void __launch_bounds__(kAtThreads, BN == 128 ? 1 : 2)
-k_attn_enc_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, T* __restrict__ out,
-              int n_ctx, int d_model, float scale_log2e, int mma_sleep) {
-    constexpr int kAtBN = BN;
-    constexpr int kAtTileBytes = AtCfg<BN>::kTileBytes;
-    constexpr int kAtPBytes = AtCfg<BN>::kPBytes;
-    extern __shared__ unsigned char at_smem_raw[];
-    const uint32_t raw = at_smem_u32(at_smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
-    unsigned char* base_ptr = at_smem_raw + (base - raw);
-    const uint32_t sQ = base;
-    const uint32_t sKV = base + kAtQBytes;
-    const uint32_t sP = sKV + kAtKvStages * kAtTileBytes;
-    const uint32_t bar0 = sP + 2 * kAtPBytes;
-    unsigned char* p_ptr = base_ptr + kAtQBytes + kAtKvStages * kAtTileBytes;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + kAtQBytes + kAtKvStages * kAtTileBytes + 2 * kAtPBytes + 192);
-    // barriers (8 B each)
-    const uint32_t q_full = bar0;
-    auto kv_full = [&](int s) { return bar0 + 8u * (1 + s); };
-    auto kv_empty = [&](int s) { return bar0 + 8u * (1 + kAtKvStages + s); };
-    auto s_full = [&](int b) { return bar0 + 8u * (1 + 2 * kAtKvStages + b); };
-    auto s_empty = [&](int b) { return bar0 + 8u * (3 + 2 * kAtKvStages + b); };
-    auto p_full = [&](int b) { return bar0 + 8u * (5 + 2 * kAtKvStages + b); };
-    auto p_empty = [&](int b) { return bar0 + 8u * (7 + 2 * kAtKvStages + b); };
-    const uint32_t o_full = bar0 + 8u * (9 + 2 * kAtKvStages);
-    // pass 1 has no O accumulator yet: its S ring uses the whole TMEM allocation (4 buffers), so the MMAs run ahead
-    // of the row-maximum sweep instead of ping-ponging with it
-    constexpr int kS1 = AtCfg<BN>::kTmemCols / BN;
-    auto s1_full = [&](int b) { return bar0 + 8u * (10 + 2 * kAtKvStages + b); };
-    auto s1_empty = [&](int b) { return bar0 + 8u * (10 + 2 * kAtKvStages + kS1 + b); };
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = blockIdx.x, head = blockIdx.y, win = blockIdx.z;
-    const int n_kt = (n_ctx + kAtBN - 1) / kAtBN;
-    const int row_q0 = win * n_ctx + qt * kAtBM;         // first query row in the flattened [W*n_ctx] matrix
-    const int col_q = head * kAtD, col_k = d_model + head * kAtD, col_v = 2 * d_model + head * kAtD;
-
-    if (threadIdx.x == 0) {
-        at_mbar_init(q_full, 1);
-        for (int s = 0; s < kAtKvStages; ++s) { at_mbar_init(kv_full(s), 1); at_mbar_init(kv_empty(s), 1); }
-        for (int b = 0; b < 2; ++b) {
-            at_mbar_init(s_full(b), 1); at_mbar_init(s_empty(b), 8);
-            at_mbar_init(p_full(b), 8); at_mbar_init(p_empty(b), 1);
-        }
-        at_mbar_init(o_full, 1);
-        for (int b = 0; b < kS1; ++b) { at_mbar_init(s1_full(b), 1); at_mbar_init(s1_empty(b), 8); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_kv) : "memory");
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(at_smem_u32(tmem_slot)), "r"(AtCfg<BN>::kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    at_fence_before();
-    __syncthreads();
-    at_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t tS0 = tmem, tO = tmem + 2 * BN;         // S buffers at columns [0,BN) and [BN,2BN); O in the next 64
-
-    if (warp == 0) {
-        if (lane == 0) {
-            at_mbar_expect_tx(q_full, kAtQBytes);
-            at_tma_2d(sQ, &tm_q, col_q, row_q0, q_full);
-            int stage = 0; uint32_t phase = 0;
-            // pass 1: K tiles only; pass 2: K then V per tile
-            for (int pass = 0; pass < 2; ++pass)
-                for (int j = 0; j < n_kt; ++j)
-                    for (int which = 0; which <= pass; ++which) {
-                        at_mbar_wait_relaxed(kv_empty(stage), phase ^ 1);
-                        at_mbar_expect_tx(kv_full(stage), kAtTileBytes);
-                        at_tma_2d(sKV + stage * kAtTileBytes, &tm_kv, which == 0 ? col_k : col_v, win * n_ctx + j * kAtBN,
-                                  kv_full(stage));
-                        if (++stage == kAtKvStages) { stage = 0; phase ^= 1; }
-                    }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t fmt = (uint32_t)Op16<T>::kUmmaFormat;
-            // S: D f32, A/B K-major, M 128, N 128.   PV: M 128, N 64, B (= V) MN-major
-            const uint32_t idesc_s = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kAtBN >> 3) << 17) | ((uint32_t)(kAtBM >> 4) << 24);
-            const uint32_t idesc_o = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) | ((uint32_t)(kAtD >> 3) << 17) | ((uint32_t)(kAtBM >> 4) << 24);
-            const uint64_t qdesc = at_desc(sQ);
-            int stage = 0; uint32_t phase = 0;
-            int sb = 0; uint32_t sphase = 0;      // S buffer ring (shared by both passes)
-            at_mbar_wait(q_full, 0);
-            at_fence_after();
-            auto issue_s = [&]() {
-                at_mbar_wait_relaxed(s_empty(sb), sphase ^ 1, (unsigned)mma_sleep);
-                at_mbar_wait_relaxed(kv_full(stage), phase, (unsigned)mma_sleep);
-                at_fence_after();
-                const uint64_t kdesc = at_desc(sKV + stage * kAtTileBytes);
-#pragma unroll
-                for (int k = 0; k < kAtD / 16; ++k) at_mma(tS0 + sb * BN, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-                at_commit(kv_empty(stage));
-                at_commit(s_full(sb));
-                if (++stage == kAtKvStages) { stage = 0; phase ^= 1; }
-                if (++sb == 2) { sb = 0; sphase ^= 1; }
-            };
-            // pass 1: S_j into ring buffer j % kS1
-            for (int j = 0; j < n_kt; ++j) {
-                const int b1 = j % kS1; const uint32_t ph1 = (uint32_t)(j / kS1) & 1u;
-                at_mbar_wait_relaxed(s1_empty(b1), ph1 ^ 1, (unsigned)mma_sleep);
-                at_mbar_wait_relaxed(kv_full(stage), phase, (unsigned)mma_sleep);
-                at_fence_after();
-                const uint64_t kdesc = at_desc(sKV + stage * kAtTileBytes);
-#pragma unroll
-                for (int k = 0; k < kAtD / 16; ++k) at_mma(tS0 + b1 * BN, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-                at_commit(kv_empty(stage));
-                at_commit(s1_full(b1));
-                if (++stage == kAtKvStages) { stage = 0; phase ^= 1; }
-            }
-            // pass 2 reuses the TMEM columns: every pass-1 buffer must have been read out
-            for (int b1 = 0; b1 < kS1; ++b1) {
-                const int uses = b1 < n_kt ? (n_kt - b1 + kS1 - 1) / kS1 : 0;
-                if (uses > 0) at_mbar_wait_relaxed(s1_empty(b1), (uint32_t)(uses - 1) & 1u);
-            }
-            at_fence_after();
-            // pass 2: S_0, then for each tile: S_{j+1} before PV_j so the tensor pipe always has work queued
-            int pb = 0; uint32_t pphase = 0;
-            issue_s();
-            for (int j = 0; j < n_kt; ++j) {
-                // V_j sits in the stage after K_j; K_{j+1} (if any) after that
-                const int v_stage = stage; const uint32_t v_phase = phase;
-                if (++stage == kAtKvStages) { stage = 0; phase ^= 1; }
-                if (j + 1 < n_kt) issue_s();
-                at_mbar_wait_relaxed(p_full(pb), pphase, (unsigned)mma_sleep);
-                at_mbar_wait_relaxed(kv_full(v_stage), v_phase, (unsigned)mma_sleep);
-                at_fence_after();
-                const uint64_t vdesc = at_desc(sKV + v_stage * kAtTileBytes);
-#pragma unroll
-                for (int k = 0; k < kAtBN / 16; ++k) {
-                    // P: BN/64 atoms of 16 KB, 32 B per k16 step inside an atom; V: 16 keys = 16 rows x 128 B
-                    const uint64_t pdesc = at_desc(sP + pb * kAtPBytes + (k >> 2) * 16384) + 2 * (k & 3);
-                    at_mma(tO, pdesc, vdesc + (uint64_t)(k * 2048 >> 4), idesc_o, (j | k) != 0);
-                }
-                at_commit(kv_empty(v_stage));
-                at_commit(p_empty(pb));
-                if (++pb == 2) { pb = 0; pphase ^= 1; }
-            }
-            at_commit(o_full);
-        }
-    } else {
-        // softmax warps: thread <-> (query row = TMEM lane, half of the key columns)
-        const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const int row = q * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        float* xch = reinterpret_cast<float*>(base_ptr + kAtQBytes + kAtKvStages * kAtTileBytes + 2 * kAtPBytes + 256);
-        constexpr int HC = BN / 2;            // key columns per softmax warp (32 or 64)
-        int sb = 0; uint32_t sphase = 0;
-        float m = -INFINITY;
-        // ---- pass 1: row maxima over this warp's 64 columns of every tile ----
-        for (int j = 0; j < n_kt; ++j) {
-            const int b1 = j % kS1;
-            at_mbar_wait(s1_full(b1), (uint32_t)(j / kS1) & 1u);
-            at_fence_after();
-            uint32_t v0[32], v1[32];
-            at_ld32(tS0 + lane_addr + b1 * BN + half * HC, v0);
-            if (HC == 64) at_ld32(tS0 + lane_addr + b1 * BN + half * HC + 32, v1);
-            at_wait_ld();
-            at_fence_before();
-            __syncwarp();
-            if (lane == 0) at_mbar_arrive(s1_empty(b1));     // values are in registers: release the buffer early
-            const int k0 = j * kAtBN + half * HC;
-            if (k0 + HC <= n_ctx) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v0[i]));
-                if (HC == 64) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v1[i]));
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (k0 + i < n_ctx) m = fmaxf(m, __uint_as_float(v0[i]));
-                    if (HC == 64 && k0 + 32 + i < n_ctx) m = fmaxf(m, __uint_as_float(v1[i]));
-                }
-            }
-        }
-        xch[half * 128 + row] = m;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        m = fmaxf(xch[row], xch[128 + row]);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        // ---- pass 2: probabilities with the final maximum ----
-        const float ms = m * scale_log2e;
-        float l = 0.f;
-        int pb = 0; uint32_t pphase = 0;
-        for (int j = 0; j < n_kt; ++j) {
-            at_mbar_wait(s_full(sb), sphase);
-            at_fence_after();
-            uint32_t v0[32], v1[32];
-            at_ld32(tS0 + lane_addr + sb * BN + half * HC, v0);
-            if (HC == 64) at_ld32(tS0 + lane_addr + sb * BN + half * HC + 32, v1);
-            at_wait_ld();
-            at_fence_before();
-            __syncwarp();
-            if (lane == 0) at_mbar_arrive(s_empty(sb));
-            at_mbar_wait(p_empty(pb), pphase ^ 1);
-            // BN 128: this warp's 64 keys are swizzle atom `half`; BN 64: its 32 keys are chunks half*4.. of the only atom
-            unsigned char* prow = p_ptr + pb * kAtPBytes + (HC == 64 ? half * 16384 : 0) + row * 128;
-            const int cb = HC == 64 ? 0 : half * 4;
-            const int k0 = j * kAtBN + half * HC;
-            const bool tail = k0 + HC > n_ctx;
-            auto do_chunk = [&](const uint32_t (&v)[32], int cbase, int kk, auto tail_tag) {
-                constexpr bool kTail = decltype(tail_tag)::value;
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float p0 = at_ex2(fmaf(__uint_as_float(v[2 * i]), scale_log2e, -ms));
-                    float p1 = at_ex2(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -ms));
-                    if (kTail) {
-                        if (kk + 2 * i >= n_ctx) p0 = 0.f;
-                        if (kk + 2 * i + 1 >= n_ctx) p1 = 0.f;
-                    }
-                    l += p0 + p1;
-                    pk[i] = Op16<T>::pack2(p0, p1);
-                }
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch)
-                    *reinterpret_cast<uint4*>(prow + (((cbase + ch) ^ (row & 7)) << 4)) =
-                        make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
-            };
-            if (tail) {
-                do_chunk(v0, cb, k0, std::true_type{});
-                if (HC == 64) do_chunk(v1, 4, k0 + 32, std::true_type{});
-            } else {
-                do_chunk(v0, cb, k0, std::false_type{});
-                if (HC == 64) do_chunk(v1, 4, k0 + 32, std::false_type{});
-            }
-            // P half-tile written through the generic proxy -> make it visible to the tensor core (async proxy)
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) at_mbar_arrive(p_full(pb));
-            if (++sb == 2) { sb = 0; sphase ^= 1; }
-            if (++pb == 2) { pb = 0; pphase ^= 1; }
-        }
-        xch[half * 128 + row] = l;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        l = xch[row] + xch[128 + row];
-        // ---- epilogue: O / l, each warp stores 32 of the 64 head dims ----
-        at_mbar_wait(o_full, 0);
-        at_fence_after();
-        const float inv = 1.0f / l;
-        const int t = qt * kAtBM + row;
-        T* orow = out + ((int64_t)win * n_ctx + t) * d_model + head * kAtD + half * 32;
-        {
-            uint32_t v[32];
-            at_ld32(tO + lane_addr + half * 32, v);
-            at_wait_ld();
-            if (t < n_ctx) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 u;
-                    u.x = Op16<T>::pack2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
-                    u.y = Op16<T>::pack2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
-                    u.z = Op16<T>::pack2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
-                    u.w = Op16<T>::pack2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
-                    *reinterpret_cast<uint4*>(orow + i) = u;
-                }
-            }
-        }
-        at_fence_before();
-    }
-    __syncthreads();
-    if (warp == 2) {
-        at_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(AtCfg<BN>::kTmemCols));
-    }
-}
-
 // ==========================================================================================
-// k_attn_enc_ts: same algorithm, but Q and P are tcgen05.mma A operands read from TMEM.
+// k_attn_enc_ts: Q and P are tcgen05.mma A operands read from TMEM.
 //
-// ncu on k_attn_enc_tc (profiles/r1_full_attn_enc_tc_bn64.md): XU 43 %, tensor 33 %, issue 49 % -- nothing
+// The first tcgen05 version (round 1, `k_attn_enc_tc`, removed) moved Q, K, V and P through shared memory;
+// ncu on it (profiles/r1_full_attn_enc_tc_bn64.md): XU 43 %, tensor 33 %, issue 49 % -- nothing
 // saturated, yet no pipeline change moved the time.  What is saturated is shared-memory bandwidth: an
 // M128 x N64 x K16 UMMA reads 4 KB of A and 2 KB of B for 32 tensor-clocks of math (192 B/clk against the
 // SM's 128 B/clk), and per 64-key tile the CTA moved Q (16 KB, re-read for every tile), P (16 KB written by
@@ -465,6 +184,11 @@ __device__ __forceinline__ void at_wait_st() { asm volatile("tcgen05.wait::st.sy
 // result O / l is mathematically independent of m.  Only if some row's scores climb more than 2^14 above its
 // first-tile maximum (flagged per CTA) is the q-tile recomputed by the exact two-pass algorithm (attempt 1) --
 // measured per-CTA time of the two-pass kernel: pass 1 9.6 us of 25 us (profiles/r1_attn_phase_trace.md).
+//
+// Measured and rejected (round 2, tools/kbench.py attn): `ex2.approx.f16x2` on packed exponent arguments with the row sums taken
+// from the tensor pipe (P x ones).  ptxas lowers the packed ex2 to TWO MUFU.EX2.F16, so the MUFU count does not drop: 530 vs
+// 641 TFLOP/s (Large-v3 shape) and twice the error (5.3e-4 vs 2.9e-4 rel-RMS); mixing an f16 P with a bf16 V in one kind::f16
+// MMA is an illegal instruction.  The sweep stays one MUFU.EX2 per score: 128 x 64 per tile against 256 tensor clocks.
 template <typename T>
 __global__ void __launch_bounds__(kAtThreads, 2)
 k_attn_enc_ts(const __grid_constant__ CUtensorMap tm_kv, const T* __restrict__ qkv, T* __restrict__ out, int n_ctx, int d_model,
@@ -486,10 +210,11 @@ k_attn_enc_ts(const __grid_constant__ CUtensorMap tm_kv, const T* __restrict__ q
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* base_ptr = at_smem_raw + (base - raw);
     const uint32_t sKV = base;
-    const uint32_t bar0 = sKV + kTsKvStages * kTsTileBytes;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + kTsKvStages * kTsTileBytes + 192);
-    int* redo_flag = reinterpret_cast<int*>(base_ptr + kTsKvStages * kTsTileBytes + 196);
-    float* xch = reinterpret_cast<float*>(base_ptr + kTsKvStages * kTsTileBytes + 256);
+    constexpr int kCtl = kTsKvStages * kTsTileBytes;      // barriers / flags / exchange follow
+    const uint32_t bar0 = sKV + kCtl;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + kCtl + 192);
+    int* redo_flag = reinterpret_cast<int*>(base_ptr + kCtl + 196);
+    float* xch = reinterpret_cast<float*>(base_ptr + kCtl + 256);
     auto kv_full = [&](int s) { return bar0 + 8u * s; };
     auto kv_empty = [&](int s) { return bar0 + 8u * (kTsKvStages + s); };
     auto s_full = [&](int b) { return bar0 + 8u * (2 * kTsKvStages + b); };           // exp sweep, 2 buffers
@@ -789,32 +514,10 @@ static int attn_enc_ts_launch(const T* qkv, T* out, int n_windows, int n_ctx, in
     return SB_OK;
 }
 
-static int attn_bn() { const char* e = getenv("SB_ATTN_BN"); return (e && atoi(e) == 128) ? 128 : 64; }
-
-template <typename T, int BN>
-static int attn_enc_tc_launch(const T* qkv, T* out, int n_windows, int n_ctx, int d_model, int n_head, cudaStream_t st) {
-    CUtensorMap tq, tkv;
-    const int is_f16 = std::is_same<T, __half>::value ? 1 : 0;
-    int rc = make_tmap_2d(&tq, qkv, is_f16, (int64_t)n_windows * n_ctx, 3 * (int64_t)d_model, 3 * (int64_t)d_model, 128);
-    if (rc) return rc;
-    if ((rc = make_tmap_2d(&tkv, qkv, is_f16, (int64_t)n_windows * n_ctx, 3 * (int64_t)d_model, 3 * (int64_t)d_model, BN))) return rc;
-    SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(k_attn_enc_tc<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<BN>::kSmem)); });
-    dim3 grid(ceil_div(n_ctx, kAtBM), n_head, n_windows);
-    const float scale_log2e = (1.0f / 8.0f) * 1.4426950408889634f;
-    static int mma_sleep = [] { const char* e = getenv("SB_ATTN_SLEEP"); return e ? atoi(e) : 64; }();
-    k_attn_enc_tc<T, BN><<<grid, kAtThreads, AtCfg<BN>::kSmem, st>>>(tq, tkv, out, n_ctx, d_model, scale_log2e, mma_sleep);
-    g_launches += 1;
-    SB_CUDA_CHECK(cudaGetLastError());
-    return SB_OK;
-}
-
 template <typename T>
 int attn_enc_tc(const T* qkv, T* out, int n_windows, int n_ctx, int d_model, int n_head, cudaStream_t st) {
     SB_CHECK_ARG(d_model == n_head * kAtD, "attention: d_head must be 64");
-    static const bool ts = [] { const char* e = getenv("SB_ATTN_TS"); return !(e && e[0] == '0'); }();    // SB_ATTN_TS=0: P/Q through shared memory
-    if (ts) return attn_enc_ts_launch<T>(qkv, out, n_windows, n_ctx, d_model, n_head, st);
-    if (attn_bn() == 128) return attn_enc_tc_launch<T, 128>(qkv, out, n_windows, n_ctx, d_model, n_head, st);
-    return attn_enc_tc_launch<T, 64>(qkv, out, n_windows, n_ctx, d_model, n_head, st);
+    return attn_enc_ts_launch<T>(qkv, out, n_windows, n_ctx, d_model, n_head, st);
 }
 template int attn_enc_tc<__half>(const __half*, __half*, int, int, int, int, cudaStream_t);
 template int attn_enc_tc<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, cudaStream_t);

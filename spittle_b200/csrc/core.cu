@@ -10,7 +10,6 @@ std::atomic<uint64_t> g_launches{0};
 static bool pdl_from_env() { const char* e = getenv("SB_PDL"); return !(e && e[0] == '0'); }
 bool g_pdl = pdl_from_env();
 thread_local TraceSlot g_trace_next;
-bool use_tc_attention() { const char* e = getenv("SB_ATTN"); return !(e && strcmp(e, "mma") == 0); }
 
 void set_error(const std::string& msg) { t_last_error = msg; }
 const char* get_error() { return t_last_error.c_str(); }

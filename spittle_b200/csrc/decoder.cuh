@@ -50,6 +50,12 @@ struct SamplerArgs {
     int single_segment;
     int max_initial_tid;      // round(max_initial_ts / 0.02), < 0 disables the rule
     int* prompt;              // device: prompt tokens [B][kMaxPrompt]
+    float* plogs_out;         // [B][n_max] log-probability of every sampled token (whisper_token_data.plog)
+    // temperature fallback (whisper_full's temperature schedule): temperature[b] > 0 -> the logits are divided by it and the
+    // token is DRAWN from the filtered distribution with the uniform number rng_u[b][step] (inverse CDF, like
+    // std::discrete_distribution over std::mt19937); null / 0 -> greedy
+    const float* temperature; // [B] or null
+    const double* rng_u;      // [B][n_max] or null
 };
 
 struct SkinnyEpilogue {
@@ -94,9 +100,7 @@ int num_sms();
 template <typename T> int im2col_conv1(const Im2col1Args& a, T* out, int n_windows, cudaStream_t st);
 template <typename T> int im2col_conv2(const T* in, T* out, int n_windows, int n_in, int n_out, int d, cudaStream_t st);
 template <typename T> int layernorm(const float* x, const float* g, const float* b, T* out16, float* out32, int rows, int d, cudaStream_t st);
-template <typename T> int attn_enc(const T* qkv, T* out, int n_windows, int n_ctx, int d_model, int n_head, cudaStream_t st);   // mma.sync version
-template <typename T> int attn_enc_tc(const T* qkv, T* out, int n_windows, int n_ctx, int d_model, int n_head, cudaStream_t st);  // tcgen05 version
-bool use_tc_attention();   // env SB_ATTN=mma selects the legacy mma.sync kernel
+template <typename T> int attn_enc_tc(const T* qkv, T* out, int n_windows, int n_ctx, int d_model, int n_head, cudaStream_t st);   // tcgen05 (k_attn_enc_ts)
 
 // decoder-side launchers (decoder_kernels.cu)
 template <typename T> int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, const SkinnyEpilogue& ep, cudaStream_t st);
@@ -113,7 +117,7 @@ int sample_step(const float* logits, int ld, const SamplerArgs& a, int Bn, cudaS
 // and write it into the language slot of every sequence whose slot holds the sentinel -1 (no-op for every other sequence)
 int lang_detect_step(const float* logits, int ld, int* prompt, const SeqState* state, int* lang_out, SpecialIds sp, int Bn, cudaStream_t st);
 // scatter freshly assigned windows into their decode slots (state, first token, prompt); items: device copy of SlotInit[n]
-struct SlotInit { int slot; int next_token; int pad_[2]; SeqState state; int prompt[kMaxPrompt]; };
-int slot_init(const SlotInit* items, int n, SeqState* state, int* next_tokens, int* prompt, int* lang_out, cudaStream_t st);
+struct SlotInit { int slot; int next_token; float temperature; int pad_; SeqState state; int prompt[kMaxPrompt]; };
+int slot_init(const SlotInit* items, int n, SeqState* state, int* next_tokens, int* prompt, int* lang_out, float* temperature, cudaStream_t st);
 
 }  // namespace sb

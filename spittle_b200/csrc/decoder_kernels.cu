@@ -343,6 +343,11 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
         asm volatile("cp.async.wait_group 0;");
         __syncthreads();
     }
+    const float temp = a.temperature ? __ldcg(a.temperature + b) : 0.f;
+    if (temp > 0.f) {                  // whisper_process_logits: logits[i] /= temperature, before every rule
+        for (int i = threadIdx.x; i < V; i += kSampThreads) s_row[i] = s_row[i] / temp;
+        __syncthreads();
+    }
     const float* lg = s_row;
     LogitMask mk;
     mk.sp = sp;
@@ -425,12 +430,62 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
         }
     float gtv; int gti;
     red.argmax(tv, ti, gtv, gti);
+    // ---- temperature > 0: draw the token (whisper_sample_token(best = false)) ----
+    // probs[i] = expf(logprobs[i]) in f32 for the allowed ids, 0 otherwise; std::discrete_distribution normalises them in
+    // double, forms the cumulative sums and returns the first index whose cumulative probability is >= u.  Each thread
+    // owns a contiguous run of ids, the runs are combined with a block scan in double.
+    __shared__ double sd[kSampThreads / 32];
+    __shared__ int s_pick;
+    int drawn = -1;
+    if (temp > 0.f && a.rng_u) {
+        const int C = (V + kSampThreads - 1) / kSampThreads;
+        const int i0 = threadIdx.x * C, i1 = min(V, i0 + C);
+        auto weight = [&](int id) -> float {
+            if (id < sp.eot) { if (text_off || force_ts || id == blank_off) return 0.f; }
+            else if (mk.suppressed(id) || (force_ts && id < sp.beg)) return 0.f;
+            return expf(lg[id] - lse);
+        };
+        double part = 0.0;
+        for (int id = i0; id < i1; ++id) part += (double)weight(id);
+        auto block_sum_d = [&](double v) -> double {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) sd[threadIdx.x >> 5] = v;
+            __syncthreads();
+            double r = 0.0;
+            for (int i = 0; i < kSampThreads / 32; ++i) r += sd[i];
+            return r;
+        };
+        const double S = block_sum_d(part);
+        double q = 0.0;
+        for (int id = i0; id < i1; ++id) q += (double)weight(id) / S;
+        // exclusive scan of q over the block
+        double incl = q;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double n = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += n; }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 31) sd[threadIdx.x >> 5] = incl;
+        if (threadIdx.x == 0) s_pick = V - 1;            // libstdc++ pins the last cumulative value to 1.0
+        __syncthreads();
+        double base = incl - q;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) base += sd[w];
+        const double u = __ldcg(a.rng_u + (int64_t)b * a.n_max + step);
+        if (base < u && u <= base + q) {
+            double c = base;
+            int pick = i1 - 1;
+            for (int id = i0; id < i1; ++id) { c += (double)weight(id) / S; if (c >= u) { pick = id; break; } }
+            atomicMin(&s_pick, pick);
+        }
+        __syncthreads();
+        drawn = s_pick;
+    }
     if (threadIdx.x != 0) return;
     // after the timestamp-mass rule the text tokens are gone and the distribution is renormalised over the timestamps
     const float lse_eff = force_ts ? (logf(ts.s) + ts.m) : lse;
     const int tid = (gtv > -INFINITY && expf(gtv - lse_eff) > 0.f) ? gti : 0;
 
-    int tok = gi;
+    int tok = drawn >= 0 ? drawn : gi;
     if (a.forced) {
         const int f = __ldcg(a.forced + (int64_t)b * a.n_max + step);
         if (f >= 0) tok = f;
@@ -438,9 +493,11 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
     a.tokens_out[(int64_t)b * a.n_max + step] = tok;
     if (a.margins_out) a.margins_out[(int64_t)b * a.n_max + step] = gv - sv;
     if (a.tids_out) a.tids_out[(int64_t)b * a.n_max + step] = tid;
+    const float plog = lg[tok] - lse;                 // logprobs[id] of the token that was taken
+    if (a.plogs_out) a.plogs_out[(int64_t)b * a.n_max + step] = plog;
     a.next_tokens[b] = tok;
     st.prev = st.last; st.last = tok; st.n_tok += 1;
-    st.sum_logprob += (gv - lse);
+    st.sum_logprob += plog;
     // ---- whisper_full bookkeeping (App. C.4) ----
     bool stop = false;
     if (tok > sp.beg) {
@@ -495,11 +552,16 @@ __global__ void __launch_bounds__(32) k_lang_detect(const float* __restrict__ lo
 
 // freshly assigned windows -> their decode slots.  One block per item; runs on the lane's stream between two steps.
 __global__ void __launch_bounds__(64) k_slot_init(const SlotInit* __restrict__ items, SeqState* __restrict__ state,
-                                                  int* __restrict__ next_tokens, int* __restrict__ prompt, int* __restrict__ lang_out) {
+                                                  int* __restrict__ next_tokens, int* __restrict__ prompt, int* __restrict__ lang_out,
+                                                  float* __restrict__ temperature) {
     const SlotInit& it = items[blockIdx.x];
     const int slot = it.slot;
     for (int i = threadIdx.x; i < kMaxPrompt; i += 64) prompt[(int64_t)slot * kMaxPrompt + i] = it.prompt[i];
-    if (threadIdx.x == 0) { state[slot] = it.state; next_tokens[slot] = it.next_token; if (lang_out) lang_out[slot] = -1; }
+    if (threadIdx.x == 0) {
+        state[slot] = it.state; next_tokens[slot] = it.next_token;
+        if (lang_out) lang_out[slot] = -1;
+        if (temperature) temperature[slot] = it.temperature;
+    }
 }
 
 // ---- prompt prefill: all prompt tokens of the freshly assigned windows in one pass ------------------------------
@@ -635,9 +697,10 @@ int lang_detect_step(const float* logits, int ld, int* prompt, const SeqState* s
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
 }
-int slot_init(const SlotInit* items, int n, SeqState* state, int* next_tokens, int* prompt, int* lang_out, cudaStream_t st) {
+int slot_init(const SlotInit* items, int n, SeqState* state, int* next_tokens, int* prompt, int* lang_out, float* temperature,
+              cudaStream_t st) {
     if (n <= 0) return SB_OK;
-    k_slot_init<<<n, 64, 0, st>>>(items, state, next_tokens, prompt, lang_out);
+    k_slot_init<<<n, 64, 0, st>>>(items, state, next_tokens, prompt, lang_out, temperature);
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;

@@ -120,186 +120,6 @@ __global__ void __launch_bounds__(256) k_layernorm(const float* x, const float* 
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Encoder attention (non-causal), d_head = 64.
-// qkv: [n_win * n_ctx, 3*d_model] rows = (window, t), columns [Q | K | V] each [head][64].
-// out: [n_win * n_ctx, d_model].
-// grid (ceil(n_ctx/64), n_head, n_win), 128 threads: each warp owns 16 query rows.
-// ------------------------------------------------------------------------------------------
-template <typename T> struct MmaOp;
-template <> struct MmaOp<__nv_bfloat16> {
-    __device__ __forceinline__ static void mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-    }
-};
-template <> struct MmaOp<__half> {
-    __device__ __forceinline__ static void mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-    }
-};
-
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-    const int sz = valid ? 16 : 0;   // src-size 0 -> zero fill
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
-
-constexpr int kAttnBQ = 64, kAttnBK = 64, kAttnD = 64, kAttnPad = 8;
-constexpr int kAttnLd = kAttnD + kAttnPad;   // 72 elements = 144 B rows
-
-template <typename T>
-__global__ void __launch_bounds__(128) k_attn_enc(const T* __restrict__ qkv, T* __restrict__ out, int n_ctx,
-                                                  int d_model, float scale_log2e) {
-    __shared__ __align__(16) T sQ[kAttnBQ * kAttnLd];
-    __shared__ __align__(16) T sK[2][kAttnBK * kAttnLd];
-    __shared__ __align__(16) T sV[2][kAttnBK * kAttnLd];
-    const int qt = blockIdx.x, head = blockIdx.y, win = blockIdx.z;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t ld = 3 * (int64_t)d_model;
-    const T* base = qkv + (int64_t)win * n_ctx * ld + head * kAttnD;
-    const int q0 = qt * kAttnBQ;
-
-    auto load_tile = [&](T* dst, const T* src_col, int row0) {
-        // 64 rows x 8 chunks of 16 B
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int idx = tid + 128 * i;
-            const int r = idx >> 3, c = idx & 7;
-            const int row = row0 + r;
-            const bool ok = row < n_ctx;
-            const T* src = src_col + (int64_t)(ok ? row : 0) * ld + c * 8;
-            cp_async16((uint32_t)__cvta_generic_to_shared(dst + r * kAttnLd + c * 8), src, ok);
-        }
-    };
-    load_tile(sQ, base, q0);
-    load_tile(sK[0], base + d_model, 0);
-    load_tile(sV[0], base + 2 * d_model, 0);
-    cp_async_commit();
-
-    const int n_kt = (n_ctx + kAttnBK - 1) / kAttnBK;
-    uint32_t qf[4][4];
-    float o[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-
-    for (int kt = 0; kt < n_kt; ++kt) {
-        const int buf = kt & 1;
-        if (kt + 1 < n_kt) {
-            load_tile(sK[buf ^ 1], base + d_model, (kt + 1) * kAttnBK);
-            load_tile(sV[buf ^ 1], base + 2 * d_model, (kt + 1) * kAttnBK);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-        if (kt == 0) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t addr = (uint32_t)__cvta_generic_to_shared(
-                    sQ + (warp * 16 + (lane & 15)) * kAttnLd + ks * 16 + (lane >> 4) * 8);
-                ldsm_x4(addr, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
-            }
-        }
-        // S = Q K^T  (16 x 64 per warp)
-        float s[8][4];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-            for (int jp = 0; jp < 4; ++jp) {   // pairs of key n-tiles
-                uint32_t b0, b1, b2, b3;
-                const uint32_t addr = (uint32_t)__cvta_generic_to_shared(
-                    sK[buf] + (jp * 16 + (lane & 7) + (lane >> 4) * 8) * kAttnLd + ks * 16 + ((lane >> 3) & 1) * 8);
-                ldsm_x4(addr, b0, b1, b2, b3);
-                MmaOp<T>::mma(s[2 * jp], qf[ks], b0, b1);
-                MmaOp<T>::mma(s[2 * jp + 1], qf[ks], b2, b3);
-            }
-        }
-        // mask keys beyond n_ctx (last tile only)
-        const int kbase = kt * kAttnBK;
-        if (kbase + kAttnBK > n_ctx) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int key = kbase + j * 8 + (lane & 3) * 2;
-                if (key >= n_ctx) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
-                if (key + 1 >= n_ctx) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
-            }
-        }
-        // online softmax (rows g = lane/4 and g + 8)
-        float mx0 = m0, mx1 = m1;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
-            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
-        }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float c0 = exp2f((m0 - mx0) * scale_log2e), c1 = exp2f((m1 - mx1) * scale_log2e);
-        m0 = mx0; m1 = mx1;
-        const float ms0 = mx0 * scale_log2e, ms1 = mx1 * scale_log2e;
-        float rs0 = 0.f, rs1 = 0.f;
-        uint32_t pf[4][4];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float p0 = exp2f(fmaf(s[j][0], scale_log2e, -ms0));
-            const float p1 = exp2f(fmaf(s[j][1], scale_log2e, -ms0));
-            const float p2 = exp2f(fmaf(s[j][2], scale_log2e, -ms1));
-            const float p3 = exp2f(fmaf(s[j][3], scale_log2e, -ms1));
-            // round to the operand type first so the row sum matches what the PV mma consumes
-            const uint32_t u01 = Op16<T>::pack2(p0, p1), u23 = Op16<T>::pack2(p2, p3);
-            const float2 f01 = Op16<T>::unpack2(u01), f23 = Op16<T>::unpack2(u23);
-            rs0 += f01.x + f01.y; rs1 += f23.x + f23.y;
-            pf[j >> 1][(j & 1) * 2 + 0] = u01;
-            pf[j >> 1][(j & 1) * 2 + 1] = u23;
-        }
-        l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
-        // O += P V
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {       // 16 keys per step
-#pragma unroll
-            for (int jp = 0; jp < 4; ++jp) {   // pairs of d n-tiles
-                uint32_t b0, b1, b2, b3;
-                const uint32_t addr = (uint32_t)__cvta_generic_to_shared(
-                    sV[buf] + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kAttnLd + jp * 16 + (lane >> 4) * 8);
-                ldsm_x4_t(addr, b0, b1, b2, b3);
-                MmaOp<T>::mma(o[2 * jp], pf[ks], b0, b1);
-                MmaOp<T>::mma(o[2 * jp + 1], pf[ks], b2, b3);
-            }
-        }
-        __syncthreads();
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-    const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
-    T* obase = out + (int64_t)win * n_ctx * d_model + head * kAttnD + (lane & 3) * 2;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if (r0 < n_ctx) *reinterpret_cast<uint32_t*>(obase + (int64_t)r0 * d_model + j * 8) = Op16<T>::pack2(o[j][0] * inv0, o[j][1] * inv0);
-        if (r1 < n_ctx) *reinterpret_cast<uint32_t*>(obase + (int64_t)r1 * d_model + j * 8) = Op16<T>::pack2(o[j][2] * inv1, o[j][3] * inv1);
-    }
-}
-
 // ---- launchers -------------------------------------------------------------------------
 template <typename T>
 int im2col_conv1(const Im2col1Args& a, T* out, int n_windows, cudaStream_t st) {
@@ -331,22 +151,12 @@ int layernorm(const float* x, const float* g, const float* b, T* out16, float* o
     SB_CUDA_CHECK(cudaGetLastError());
     return SB_OK;
 }
-template <typename T>
-int attn_enc(const T* qkv, T* out, int n_windows, int n_ctx, int d_model, int n_head, cudaStream_t st) {
-    SB_CHECK_ARG(d_model == n_head * kAttnD, "attention: d_head must be 64");
-    dim3 grid(ceil_div(n_ctx, kAttnBQ), n_head, n_windows);
-    const float scale_log2e = (1.0f / 8.0f) * 1.4426950408889634f;
-    k_attn_enc<T><<<grid, 128, 0, st>>>(qkv, out, n_ctx, d_model, scale_log2e);
-    g_launches += 1;
-    SB_CUDA_CHECK(cudaGetLastError());
-    return SB_OK;
-}
 
 #define SB_INST(T)                                                                                          \
     template int im2col_conv1<T>(const Im2col1Args&, T*, int, cudaStream_t);                                \
     template int im2col_conv2<T>(const T*, T*, int, int, int, int, cudaStream_t);                           \
-    template int layernorm<T>(const float*, const float*, const float*, T*, float*, int, int, cudaStream_t); \
-    template int attn_enc<T>(const T*, T*, int, int, int, int, cudaStream_t);
+    template int layernorm<T>(const float*, const float*, const float*, T*, float*, int, int, cudaStream_t);
+
 SB_INST(__nv_bfloat16)
 SB_INST(__half)
 
@@ -364,14 +174,8 @@ extern "C" int sb_layernorm_dev(int dtype, const float* x, const float* gamma, c
 extern "C" int sb_attn_enc_dev(int dtype, const void* qkv, void* out, int n_windows, int n_ctx, int d_model,
                                int n_head, void* stream) {
     SB_CHECK_ARG(qkv && out, "null pointer");
-    if (sb::use_tc_attention()) {
-        if (dtype == SB_DTYPE_F16)
-            return sb::attn_enc_tc<__half>((const __half*)qkv, (__half*)out, n_windows, n_ctx, d_model, n_head, (cudaStream_t)stream);
-        return sb::attn_enc_tc<__nv_bfloat16>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n_windows, n_ctx, d_model, n_head,
-                                              (cudaStream_t)stream);
-    }
     if (dtype == SB_DTYPE_F16)
-        return sb::attn_enc<__half>((const __half*)qkv, (__half*)out, n_windows, n_ctx, d_model, n_head, (cudaStream_t)stream);
-    return sb::attn_enc<__nv_bfloat16>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n_windows, n_ctx, d_model, n_head,
-                                       (cudaStream_t)stream);
+        return sb::attn_enc_tc<__half>((const __half*)qkv, (__half*)out, n_windows, n_ctx, d_model, n_head, (cudaStream_t)stream);
+    return sb::attn_enc_tc<__nv_bfloat16>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n_windows, n_ctx, d_model, n_head,
+                                          (cudaStream_t)stream);
 }

@@ -11,6 +11,7 @@
 #include <memory>
 #include <mutex>
 #include <regex>
+#include <cmath>
 #include <thread>
 #include <cstddef>
 #include <unordered_map>
@@ -68,6 +69,34 @@ struct PinBuf {        // pinned host staging
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
     template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+// std::mt19937 restated (whisper.cpp gives every decoder a std::mt19937(0)); uniform() is libstdc++'s
+// std::generate_canonical<double, 53>: two 32-bit draws, (x1 + x2 * 2^32) / 2^64 -- what std::discrete_distribution consumes
+struct Mt19937 {
+    uint32_t mt[624]; int idx = 624;
+    explicit Mt19937(uint32_t seed = 0) {
+        mt[0] = seed;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    }
+    uint32_t next() {
+        if (idx >= 624) {
+            for (int i = 0; i < 624; ++i) {
+                const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+                mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+        return y;
+    }
+    double uniform() {
+        const double x1 = (double)next(), x2 = (double)next();
+        double u = (x1 + x2 * 4294967296.0) / 18446744073709551616.0;
+        if (u >= 1.0) u = std::nextafter(1.0, 0.0);
+        return u;
+    }
 };
 
 __global__ void k_fill_i32(int* p, int n, int v) {
@@ -183,8 +212,8 @@ struct Engine : EngineBase {
     DevBuf b_pcm, b_mel, b_cmax, b_floor, b_clipmeta, b_winmeta;
     DevBuf b_col1, b_c1, b_x, b_h, b_qkv, b_att, b_mlp, b_enc32;
     DevBuf b_ckv, b_kself, b_vself, b_dx, b_dh, b_dqkv, b_datt, b_dq, b_dmlp, b_logits;
-    DevBuf b_state, b_tokens, b_margins, b_tids, b_next, b_forced, b_tick, b_prompt, b_lang, b_init, b_prow;
-    PinBuf h_state, h_tokens, h_margins, h_tids, h_lang, h_init, h_winmeta, h_prow;   // host mirrors polled once per burst / slot-init staging
+    DevBuf b_state, b_tokens, b_margins, b_tids, b_plogs, b_next, b_forced, b_tick, b_prompt, b_lang, b_init, b_prow, b_temp, b_rng;
+    PinBuf h_state, h_tokens, h_margins, h_tids, h_plogs, h_lang, h_init, h_winmeta, h_prow, h_rng;   // host mirrors polled once per burst / slot-init staging
     // profile == 2: device-side launch trace of the decoder step (TraceSlot, common.cuh)
     DevBuf b_trace;
     std::vector<int> trace_cls;          // class of launch idx inside a step: 0 projection, 1 LayerNorm, 2 self-attn, 3 cross-attn
@@ -275,9 +304,9 @@ struct Engine : EngineBase {
         DevBuf* bufs[] = {&b_pcm, &b_mel, &b_cmax, &b_floor, &b_clipmeta, &b_winmeta, &b_col1, &b_c1, &b_x, &b_h, &b_qkv,
                           &b_att, &b_mlp, &b_enc32, &b_ckv, &b_kself, &b_vself, &b_dx, &b_dh, &b_dqkv, &b_datt, &b_dq,
                           &b_dmlp, &b_logits, &b_state, &b_tokens, &b_margins, &b_tids, &b_next, &b_forced, &b_tick, &b_prompt,
-                          &b_lang, &b_init, &b_trace, &b_prow};
+                          &b_lang, &b_init, &b_trace, &b_prow, &b_plogs, &b_temp, &b_rng};
         for (DevBuf* b : bufs) b->release();
-        PinBuf* pins[] = {&h_state, &h_tokens, &h_margins, &h_tids, &h_lang, &h_init, &h_winmeta, &h_prow};
+        PinBuf* pins[] = {&h_state, &h_tokens, &h_margins, &h_tids, &h_lang, &h_init, &h_winmeta, &h_prow, &h_plogs, &h_rng};
         for (PinBuf* b : pins) b->release();
         if (melplan) sb_melplan_destroy(melplan);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -520,6 +549,11 @@ struct Engine : EngineBase {
         if ((rc = b_tokens.ensure((size_t)S * n_max * 4))) return rc;
         if ((rc = b_margins.ensure((size_t)S * n_max * 4))) return rc;
         if ((rc = b_tids.ensure((size_t)S * n_max * 4))) return rc;
+        if ((rc = b_plogs.ensure((size_t)S * n_max * 4))) return rc;
+        if ((rc = b_temp.ensure((size_t)S * 4))) return rc;
+        if ((rc = b_rng.ensure((size_t)S * n_max * 8))) return rc;
+        if ((rc = h_plogs.ensure((size_t)S * n_max * 4))) return rc;
+        if ((rc = h_rng.ensure((size_t)S * n_max * 8))) return rc;
         if ((rc = b_forced.ensure((size_t)S * n_max * 4))) return rc;
         if ((rc = b_next.ensure(S * 4))) return rc;
         if ((rc = b_lang.ensure(S * 4))) return rc;
@@ -643,6 +677,8 @@ struct Engine : EngineBase {
         SB_CUDA_CHECK(cudaMemsetAsync(b_tokens.p, 0xff, (size_t)S * n_max * 4, st));
         SB_CUDA_CHECK(cudaMemsetAsync(b_margins.p, 0, (size_t)S * n_max * 4, st));
         SB_CUDA_CHECK(cudaMemsetAsync(b_tids.p, 0, (size_t)S * n_max * 4, st));
+        SB_CUDA_CHECK(cudaMemsetAsync(b_plogs.p, 0, (size_t)S * n_max * 4, st));
+        SB_CUDA_CHECK(cudaMemsetAsync(b_temp.p, 0, (size_t)S * 4, st));
         SB_CUDA_CHECK(cudaMemsetAsync(b_lang.p, 0xff, (size_t)S * 4, st));
         k_fill_i32<<<ceil_div(S, 256), 256, 0, st>>>(b_next.as<int>(), S, sp.sot);
         g_launches += 1;
@@ -681,6 +717,9 @@ struct Engine : EngineBase {
         sa.tokens_out = b_tokens.as<int>() + (size_t)w0 * n_max_cur;
         sa.margins_out = b_margins.as<float>() + (size_t)w0 * n_max_cur;
         sa.tids_out = b_tids.as<int>() + (size_t)w0 * n_max_cur;
+        sa.plogs_out = b_plogs.as<float>() + (size_t)w0 * n_max_cur;
+        sa.temperature = b_temp.as<float>() + w0;
+        sa.rng_u = b_rng.as<double>() + (size_t)w0 * n_max_cur;
         sa.next_tokens = b_next.as<int>() + w0;
         sa.forced = dcfg.has_forced ? b_forced.as<int>() + (size_t)w0 * n_max_cur : nullptr;
         sa.tick = b_tick.as<int>() + 16 * li;
@@ -729,8 +768,9 @@ struct Engine : EngineBase {
         SB_CUDA_CHECK(cudaMemcpyAsync(h_tokens.as<int>() + o, b_tokens.as<int>() + o, nb, cudaMemcpyDeviceToHost, L.st));
         SB_CUDA_CHECK(cudaMemcpyAsync(h_margins.as<float>() + o, b_margins.as<float>() + o, nb, cudaMemcpyDeviceToHost, L.st));
         SB_CUDA_CHECK(cudaMemcpyAsync(h_tids.as<int>() + o, b_tids.as<int>() + o, nb, cudaMemcpyDeviceToHost, L.st));
+        SB_CUDA_CHECK(cudaMemcpyAsync(h_plogs.as<float>() + o, b_plogs.as<float>() + o, nb, cudaMemcpyDeviceToHost, L.st));
         SB_CUDA_CHECK(cudaMemcpyAsync(h_lang.as<int>() + L.s0, b_lang.as<int>() + L.s0, L.n * 4, cudaMemcpyDeviceToHost, L.st));
-        stats.d2h_bytes += (double)L.n * (sizeof(SeqState) + 4) + 3.0 * nb;
+        stats.d2h_bytes += (double)L.n * (sizeof(SeqState) + 4) + 4.0 * nb;
         return SB_OK;
     }
 
@@ -740,6 +780,9 @@ struct Engine : EngineBase {
         std::vector<int> prompt;      // full decoder prompt (language slot = -1 when it is to be detected)
         int lang_slot = -1, restart = 0;
         int prefilled = 0;            // prompt tokens [0, prefilled) went through the batched prefill pass
+        float temperature = 0.f;      // > 0: tokens are drawn with `rng_u` (n_max uniform numbers of the clip's stream)
+        int attempt = 0;
+        std::vector<double> rng_u;
     };
 
     // whisper_full's prompt of one window: [prev] + the last <= n_text_ctx/2 tokens of prompt_past (text context of this
@@ -747,7 +790,7 @@ struct Engine : EngineBase {
     void build_prompt(WinJob& j, const std::vector<int>& prompt_past, int lang, const sb_params& p) const {
         j.prompt.clear();
         const int n_ctx_max = p.n_max_text_ctx;
-        if (!prompt_past.empty() && n_ctx_max > 0) {       // (temperature is 0 here: whisper.cpp requires t_cur < 0.5)
+        if (!prompt_past.empty() && n_ctx_max > 0 && j.temperature < 0.5f) {       // whisper.cpp: t_cur < 0.5
             const int n_take = std::min(std::min(n_ctx_max, hp.n_text_ctx / 2), (int)prompt_past.size());
             j.prompt.push_back(sp.prev);
             j.prompt.insert(j.prompt.end(), prompt_past.end() - n_take, prompt_past.end());
@@ -829,7 +872,7 @@ struct Engine : EngineBase {
 
     // scatter the jobs into their slots: staged per lane in pinned memory, copied and applied on the lane's own stream
     // (in order with the lane's steps, after the encoder's cross-KV for these slots is complete: ev_enc)
-    int init_slots(const std::vector<WinJob>& jobs) {
+    int init_slots(const std::vector<WinJob>& jobs, cudaEvent_t wait_ev) {
         SlotInit* hi = h_init.as<SlotInit>();
         int rc;
         for (int li = 0; li < n_lanes; ++li) {
@@ -840,6 +883,13 @@ struct Engine : EngineBase {
                 SlotInit& it = hi[L.s0 + cnt];
                 memset(&it, 0, sizeof(it));
                 it.slot = j.slot;
+                it.temperature = j.temperature;
+                if (j.temperature > 0.f) {          // this slot's uniform numbers: staged and copied on the lane's stream
+                    double* hr = h_rng.as<double>() + (size_t)j.slot * n_max_cur;
+                    for (int k = 0; k < n_max_cur; ++k) hr[k] = k < (int)j.rng_u.size() ? j.rng_u[k] : 0.5;
+                    SB_CUDA_CHECK(cudaMemcpyAsync(b_rng.as<double>() + (size_t)j.slot * n_max_cur, hr, (size_t)n_max_cur * 8,
+                                                  cudaMemcpyHostToDevice, L.st));
+                }
                 it.next_token = j.prompt[0];
                 SeqState s{};
                 s.seek_delta = 3000; s.seek = j.seek; s.seek_end = j.seek_end;
@@ -851,10 +901,10 @@ struct Engine : EngineBase {
                 ++cnt;
             }
             if (!cnt) continue;
-            SB_CUDA_CHECK(cudaStreamWaitEvent(L.st, ev_enc, 0));
+            if (wait_ev) SB_CUDA_CHECK(cudaStreamWaitEvent(L.st, wait_ev, 0));
             SB_CUDA_CHECK(cudaMemcpyAsync(b_init.as<SlotInit>() + L.s0, hi + L.s0, cnt * sizeof(SlotInit), cudaMemcpyHostToDevice, L.st));
             if ((rc = slot_init(b_init.as<SlotInit>() + L.s0, cnt, b_state.as<SeqState>(), b_next.as<int>(), b_prompt.as<int>(),
-                                b_lang.as<int>(), L.st))) return rc;
+                                b_lang.as<int>(), b_temp.as<float>(), L.st))) return rc;
             L.active += cnt;
             stats.h2d_bytes += (double)cnt * sizeof(SlotInit);
         }
@@ -1002,7 +1052,7 @@ struct Engine : EngineBase {
         }
         if ((rc = prefill(jobs))) return rc;
         SB_CUDA_CHECK(cudaEventRecord(ev_enc, st));
-        if ((rc = init_slots(jobs))) return rc;
+        if ((rc = init_slots(jobs, ev_enc))) return rc;
         const int feed = (int)jobs[0].prompt.size() - 1 - jobs[0].prefilled;         // the prompt is the same for every window here
         const int total_steps = feed + n_steps;
         const int vpad = (int)round_up(hp.n_vocab, 8);
@@ -1033,7 +1083,8 @@ struct Engine : EngineBase {
         size_t n = 0; int n_len = 0, n_len_org = 0, n_calc = 0;
         int seek = 0; bool active = false, running = false; int lang = 0;
         std::vector<int> prompt_past;         // whisper_full's prompt_past of this call
-        std::vector<int32_t> kept, sampled, tids; std::vector<float> margins; std::vector<sb_window_info> windows;
+        Mt19937 rng{0};                       // the decoder's std::mt19937(0): consumed by the draws at temperature > 0
+        std::vector<int32_t> kept, sampled, tids; std::vector<float> margins, plogs; std::vector<sb_window_info> windows;
         std::vector<Segment> segments;
         std::string text;
     };
@@ -1041,14 +1092,15 @@ struct Engine : EngineBase {
     // one finished window: whisper_full's per-window epilogue (tokens_cur.resize(result_len), segments at timestamp
     // tokens, prompt_past update, seek += seek_delta)
     void finish_window(ClipRun& r, const WinJob& j, const SeqState& s, const int* toks, const float* margs, const int* tids,
-                       const sb_params& p) {
+                       const float* plogs, float avg_logprob, const sb_params& p) {
         sb_window_info wi{};
+        wi.temperature = j.temperature; wi.n_attempts = j.attempt + 1; wi.avg_logprob = avg_logprob;
         wi.seek = r.seek; wi.n_tokens = s.n_tok; wi.result_len = s.result_len; wi.seek_delta = s.seek_delta;
         wi.failed = s.failed; wi.token_offset = (int)r.sampled.size();
         wi.n_prompt = (int)j.prompt.size() - j.restart;
         const int kept0 = (int)r.kept.size();
         for (int i = 0; i < s.n_tok; ++i) {
-            r.sampled.push_back(toks[i]); r.margins.push_back(margs[i]); r.tids.push_back(tids[i]);
+            r.sampled.push_back(toks[i]); r.margins.push_back(margs[i]); r.tids.push_back(tids[i]); r.plogs.push_back(plogs[i]);
             if (i < s.result_len) { r.kept.push_back(toks[i]); if (toks[i] < sp.eot) r.text += token_text(toks[i]); }
         }
         r.windows.push_back(wi);
@@ -1165,7 +1217,7 @@ struct Engine : EngineBase {
                 if (pend_active && (running == 0 || cudaEventQuery(ev_enc) == cudaSuccess)) {
                     if (running == 0) SB_CUDA_CHECK(cudaEventSynchronize(ev_enc));      // nothing to step meanwhile
                     { float t = 0.f; if (cudaEventElapsedTime(&t, ev[1], ev_enc) == cudaSuccess) ms_enc += t; }
-                    if ((rc = init_slots(pending))) return rc;
+                    if ((rc = init_slots(pending, ev_enc))) return rc;
                     for (const WinJob& j : pending) { live[j.slot] = j; slot_job[j.slot] = 1; }
                     running += (int)pending.size();
                     pending.clear(); pend_active = false;
@@ -1207,6 +1259,12 @@ struct Engine : EngineBase {
                             if (r.seek > 0 && r.seek + 500 >= r.n_len_org) r.prompt_past.clear();
                             WinJob j;
                             j.clip = ready[i]; j.slot = chosen[i]; j.seek = r.seek; j.seek_end = r.n_len_org;
+                            j.temperature = std::max(0.f, p.temperature);
+                            if (j.temperature > 0.f) {
+                                Mt19937 peek = r.rng;
+                                j.rng_u.resize(n_max_cur);
+                                for (double& u : j.rng_u) u = peek.uniform();
+                            }
                             build_prompt(j, r.prompt_past, r.lang, p);
                             r.running = true;
                             pending.push_back(std::move(j));
@@ -1239,15 +1297,59 @@ struct Engine : EngineBase {
                     if (L.active == 0) continue;
                     SB_CUDA_CHECK(cudaStreamSynchronize(L.st));
                     const SeqState* hs = h_state.as<SeqState>();
+                    std::vector<WinJob> retries;
                     for (int s_ = L.s0; s_ < L.s0 + L.n; ++s_) {
                         if (slot_job[s_] < 0 || !hs[s_].done) continue;
                         const WinJob& j = live[s_];
                         ClipRun& r = clips[j.clip];
                         if (r.lang < 0) { const int dl = h_lang.as<int>()[s_]; r.lang = dl >= 0 ? dl : 0; }     // detected on the clip's first window
-                        finish_window(r, j, hs[s_], h_tokens.as<int>() + (size_t)s_ * n_max_cur,
-                                      h_margins.as<float>() + (size_t)s_ * n_max_cur, h_tids.as<int>() + (size_t)s_ * n_max_cur, p);
+                        const SeqState& fs = hs[s_];
+                        const int* toks = h_tokens.as<int>() + (size_t)s_ * n_max_cur;
+                        const float* plogs = h_plogs.as<float>() + (size_t)s_ * n_max_cur;
+                        // whisper_sequence_score + the fallback test of whisper_full: mean log-probability of the kept tokens,
+                        // entropy of the last 32 of them
+                        const int n = std::min(fs.result_len, fs.n_tok);
+                        double sum = 0.0;
+                        for (int i = 0; i < n; ++i) sum += plogs[i];
+                        const float avg = n > 0 ? (float)(sum / n) : NAN;
+                        bool failed = fs.failed != 0;
+                        if (n > 32) {
+                            std::unordered_map<int, int> cnt;
+                            for (int i = n - 32; i < n; ++i) cnt[toks[i]]++;
+                            double ent = 0.0;
+                            for (auto& kv : cnt) { const double pr = kv.second / 32.0; ent -= pr * std::log(pr); }
+                            if (ent < p.entropy_thold) failed = true;
+                        }
+                        if (j.temperature > 0.f) for (int i = 0; i < fs.n_tok; ++i) r.rng.uniform();      // the draws this attempt consumed
+                        const bool success = !(failed || avg < p.logprob_thold);
+                        const float t_next = j.temperature + p.temperature_inc;
+                        L.active -= 1; running -= 1;
+                        if (!success && p.temperature_inc > 0.f && t_next < 1.0f + 1e-6f) {
+                            // decode the same window again, one temperature up, in the same slot (its cross-KV is still there)
+                            WinJob nj;
+                            nj.clip = j.clip; nj.slot = s_; nj.seek = j.seek; nj.seek_end = j.seek_end;
+                            nj.temperature = t_next; nj.attempt = j.attempt + 1;
+                            build_prompt(nj, r.prompt_past, r.lang, p);
+                            Mt19937 peek = r.rng;
+                            nj.rng_u.resize(n_max_cur);
+                            for (double& u : nj.rng_u) u = peek.uniform();
+                            retries.push_back(std::move(nj));
+                            stats.fallbacks += 1;
+                            continue;
+                        }
+                        finish_window(r, j, fs, toks, h_margins.as<float>() + (size_t)s_ * n_max_cur, h_tids.as<int>() + (size_t)s_ * n_max_cur,
+                                      plogs, avg, p);
                         r.running = false;
-                        slot_job[s_] = -1; L.active -= 1; running -= 1;
+                        slot_job[s_] = -1;
+                    }
+                    if (!retries.empty()) {
+                        cudaEvent_t wait_ev = nullptr;
+                        size_t rows0 = (size_t)stats.prefill_rows;
+                        if ((rc = prefill(retries))) return rc;
+                        if ((size_t)stats.prefill_rows != rows0) { SB_CUDA_CHECK(cudaEventRecord(ev_fork, st)); wait_ev = ev_fork; }
+                        if ((rc = init_slots(retries, wait_ev))) return rc;
+                        for (WinJob& nj : retries) live[nj.slot] = std::move(nj);
+                        running += (int)retries.size();
                     }
                 }
             }
@@ -1276,6 +1378,7 @@ struct Engine : EngineBase {
             o.n_sampled = r.sampled.size(); o.sampled = (int32_t*)dup(r.sampled.data(), r.sampled.size() * 4);
             o.margins = (float*)dup(r.margins.data(), r.margins.size() * 4);
             o.tids = (int32_t*)dup(r.tids.data(), r.tids.size() * 4);
+            o.logprobs = (float*)dup(r.plogs.data(), r.plogs.size() * 4);
             o.n_windows = r.windows.size(); o.windows = (sb_window_info*)dup(r.windows.data(), r.windows.size() * sizeof(sb_window_info));
             // segments: one blob holds every segment text (NUL-terminated), the records point into it
             size_t blob = 0;
@@ -1338,6 +1441,10 @@ void sb_params_default(sb_params* p) {
     p->suppress_blank = 1;
     p->max_initial_ts = 1.0f;
     p->n_max_text_ctx = 16384;
+    p->temperature = 0.0f;
+    p->temperature_inc = 0.0f;          // pinned parity configuration: no fallback (whisper.cpp's default is 0.2)
+    p->logprob_thold = -1.0f;
+    p->entropy_thold = 2.4f;
 }
 
 int sb_engine_create(const sb_config* cfg, sb_engine** out) {
@@ -1487,7 +1594,7 @@ int sb_transcribe(sb_engine* e, const float* pcm16k, size_t n_samples, const sb_
 
 void sb_result_free(sb_result* r) {
     if (!r) return;
-    free(r->text); free(r->tokens); free(r->sampled); free(r->margins); free(r->tids); free(r->windows);
+    free(r->text); free(r->tokens); free(r->sampled); free(r->margins); free(r->tids); free(r->logprobs); free(r->windows);
     free(r->segments); free(r->segment_text);
     memset(r, 0, sizeof(*r));
 }
@@ -1514,16 +1621,18 @@ int sb_decode_trace(sb_engine* e, const float* mel_windows, int n_windows, const
     X(sb_config, devices) X(sb_config, n_devices)                                                                       \
     X(sb_params, language) X(sb_params, translate) X(sb_params, initial_prompt) X(sb_params, no_timestamps)             \
     X(sb_params, suppress_blank) X(sb_params, single_segment) X(sb_params, max_initial_ts) X(sb_params, n_max_tokens)   \
-    X(sb_params, max_windows) X(sb_params, n_max_text_ctx)                                                              \
+    X(sb_params, max_windows) X(sb_params, n_max_text_ctx) X(sb_params, temperature) X(sb_params, temperature_inc)            \
+    X(sb_params, logprob_thold) X(sb_params, entropy_thold)                                                              \
     X(sb_window_info, seek) X(sb_window_info, n_tokens) X(sb_window_info, result_len) X(sb_window_info, seek_delta)     \
-    X(sb_window_info, failed) X(sb_window_info, token_offset) X(sb_window_info, n_prompt)                               \
+    X(sb_window_info, failed) X(sb_window_info, token_offset) X(sb_window_info, n_prompt) X(sb_window_info, temperature)  \
+    X(sb_window_info, n_attempts) X(sb_window_info, avg_logprob)                               \
     X(sb_segment, t0) X(sb_segment, t1) X(sb_segment, text) X(sb_segment, text_len) X(sb_segment, token_offset)         \
     X(sb_segment, n_tokens)                                                                                             \
     X(sb_result, text) X(sb_result, text_len) X(sb_result, tokens) X(sb_result, n_tokens) X(sb_result, sampled)         \
-    X(sb_result, n_sampled) X(sb_result, margins) X(sb_result, tids) X(sb_result, windows) X(sb_result, n_windows)      \
+    X(sb_result, n_sampled) X(sb_result, margins) X(sb_result, tids) X(sb_result, logprobs) X(sb_result, windows) X(sb_result, n_windows)      \
     X(sb_result, segments) X(sb_result, n_segments) X(sb_result, segment_text) X(sb_result, ms_mel)                     \
     X(sb_result, ms_encode) X(sb_result, ms_decode) X(sb_result, status) X(sb_result, lang_id)                          \
-    X(sb_model_info, n_vocab) X(sb_model_info, token_blank) X(sb_stats, clips) X(sb_stats, dstep_count) X(sb_stats, prefill_rows)
+    X(sb_model_info, n_vocab) X(sb_model_info, token_blank) X(sb_stats, clips) X(sb_stats, dstep_count) X(sb_stats, prefill_rows) X(sb_stats, fallbacks)
 
 int sb_abi_layout(sb_abi_field* out, int cap) {
     static const sb_abi_field rows[] = {

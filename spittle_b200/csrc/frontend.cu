@@ -1,7 +1,8 @@
 // Capture front-end on sm_100a (rows a9-a13 of SURVEY.md 8(a)):
-//   k_resample_fir     rubato FftFixedIn (48 -> 16 kHz) as a polyphase decimating FIR with the same
-//                      1026 Blackman-Harris^2 sinc taps (reference: audio_toolkit/audio/resampler.rs:24,
-//                      51-56; equivalence of the two forms: SURVEY.md App. B, ~1e-9)
+//   k_resample_mma     rubato FftFixedIn (48 -> 16 kHz) as a decimating FIR with the same 1026
+//                      Blackman-Harris^2 sinc taps, run as a Toeplitz GEMM on the tensor cores (3xTF32)
+//                      (reference: audio_toolkit/audio/resampler.rs:24, 51-56; equivalence of the FFT and
+//                      FIR forms: SURVEY.md App. B, ~1e-9; the CUDA-core form of round 1 was removed)
 //   k_silero_features  Silero v4 per-frame front: reflect pad, STFT conv, magnitude, log, adaptive
 //                      normalisation, 4 separable conv blocks (reference: vad/silero.rs:41-44 ->
 //                      vad-rs -> onnxruntime; graph first-hand from silero_vad_v4.onnx, App. A)
@@ -44,66 +45,6 @@ __global__ void __launch_bounds__(256) k_downmix_mono(const S* __restrict__ in, 
         for (int c = 0; c < channels; ++c) a += to_sample_f32<S>(__ldg(fr + c));
         dst[f] = a / (float)channels;
         (void)inv;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// polyphase decimating FIR:  y[m] = sum_k h[k] x[D m - k],  x = 0 outside [0, n_in)
-// ------------------------------------------------------------------------------------------
-constexpr int kFirTile = 1024;     // outputs per CTA
-constexpr int kFirR = 8;           // outputs per thread
-constexpr int kFirThreads = kFirTile / kFirR;
-
-__device__ __forceinline__ int fir_pad(int i) { return i + (i >> 3); }   // bank-conflict-free for stride-8 lanes
-
-template <int D>
-__global__ void __launch_bounds__(kFirThreads) k_resample_fir(const float* __restrict__ x, int64_t x_stride, int n_in,
-                                                              float* __restrict__ y, int64_t y_stride, int n_out,
-                                                              const float* __restrict__ h, int n_taps) {
-    extern __shared__ float s_fir[];
-    const int taps_p = n_taps / D;                        // taps per phase (342)
-    const int win = kFirTile + taps_p - 1;                // x_p samples needed per phase
-    const int win_pad = fir_pad(win) + 1;
-    float* hs = s_fir;                                    // [D][taps_p]
-    float* xs = s_fir + D * taps_p;                       // [D][win_pad]
-    const int stream = blockIdx.y;
-    const int m0 = blockIdx.x * kFirTile;
-    const float* xin = x + (int64_t)stream * x_stride;
-    for (int i = threadIdx.x; i < n_taps; i += blockDim.x) { const int p = i % D, j = i / D; hs[p * taps_p + j] = h[i]; }
-    // x_p[i] = x[D i - p],  i in [m0 - (taps_p - 1), m0 + kFirTile)
-    for (int i = threadIdx.x; i < D * win; i += blockDim.x) {
-        const int p = i / win, l = i - p * win;
-        const int64_t src = (int64_t)D * (m0 - (taps_p - 1) + l) - p;
-        xs[p * win_pad + fir_pad(l)] = (src >= 0 && src < n_in) ? __ldg(xin + src) : 0.0f;
-    }
-    __syncthreads();
-    float acc[kFirR];
-#pragma unroll
-    for (int r = 0; r < kFirR; ++r) acc[r] = 0.f;
-    const int base = threadIdx.x * kFirR + (taps_p - 1);  // local index of x_p[m] for r = 0, j = 0
-#pragma unroll 1
-    for (int p = 0; p < D; ++p) {
-        const float* xp = xs + p * win_pad;
-        const float* hp = hs + p * taps_p;
-        float w[kFirR];
-#pragma unroll
-        for (int r = 0; r < kFirR; ++r) w[r] = xp[fir_pad(base + r)];
-        for (int j = 0; j < taps_p; ++j) {
-            const float hv = hp[j];
-#pragma unroll
-            for (int r = 0; r < kFirR; ++r) acc[r] = fmaf(hv, w[r], acc[r]);
-            // slide the window one sample towards the past
-#pragma unroll
-            for (int r = kFirR - 1; r > 0; --r) w[r] = w[r - 1];
-            const int nxt = base - j - 1;
-            w[0] = nxt >= 0 ? xp[fir_pad(nxt)] : 0.0f;
-        }
-    }
-    float* yo = y + (int64_t)stream * y_stride;
-#pragma unroll
-    for (int r = 0; r < kFirR; ++r) {
-        const int m = m0 + threadIdx.x * kFirR + r;
-        if (m < n_out) yo[m] = acc[r];
     }
 }
 
@@ -639,34 +580,20 @@ int sb_resample_dev(const sb_resampler* r, const float* in, int64_t in_stride, s
         return SB_OK;
     }
     if (n_out == 0) return SB_OK;
-    const int D = r->decim, taps_p = r->n_taps / D;
-    static const bool use_mma = [] { const char* e = getenv("SB_RESAMPLE_MMA"); return !(e && e[0] == '0'); }();
-    if (use_mma) {
+    const int D = r->decim;
+    {
         // tensor-core Toeplitz form (k_resample_mma)
         const int T = r->n_taps;
         const int Kp = (T + 15 * D + 7) & ~7;
         const size_t smem = (size_t)(((T + 15 * D + Kp + 8 + 3) & ~3) + Kp + 16 * D * (sb::kRmBlocks - 1)) * sizeof(float);
         SB_CHECK_ARG(smem <= 200 * 1024, "resampler: filter too long for the shared-memory segment");
-        SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_resample_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_resample_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); });
         dim3 grid((unsigned)((n_out + sb::kRmTile - 1) / sb::kRmTile), n_streams);
         sb::k_resample_mma<<<grid, 256, smem, st>>>(in, in_stride, (int)n_in, out, out_stride, (int)n_out, r->d_h, T, D, Kp);
         sb::g_launches += 1;
         SB_CUDA_CHECK(cudaGetLastError());
         return SB_OK;
     }
-    const int win = sb::kFirTile + taps_p - 1;
-    const size_t smem = (size_t)(D * taps_p + D * (win + (win >> 3) + 2)) * sizeof(float);
-    dim3 grid((unsigned)((n_out + sb::kFirTile - 1) / sb::kFirTile), n_streams);
-#define SB_FIR(DD)                                                                                                   \
-    case DD:                                                                                                         \
-        SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_resample_fir<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        sb::k_resample_fir<DD><<<grid, sb::kFirThreads, smem, st>>>(in, in_stride, (int)n_in, out, out_stride, (int)n_out, r->d_h, r->n_taps); \
-        break;
-    switch (D) { SB_FIR(2) SB_FIR(3) SB_FIR(4) SB_FIR(6) default: sb::set_error("unsupported decimation"); return SB_ERR_UNSUPPORTED; }
-#undef SB_FIR
-    sb::g_launches += 1;
-    SB_CUDA_CHECK(cudaGetLastError());
-    return SB_OK;
 }
 
 // blob layout: spittle_b200/silero_weights.py BLOB_LAYOUT

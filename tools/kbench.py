@@ -58,6 +58,59 @@ def bench_gemm():
             del A, W, out
 
 
+def bench_gemm_epilogue():
+    """the three epilogue kinds of the encoder GEMMs on the Large-v3 / Turbo shapes (64 windows): 16-bit out, f32 out,
+    f32 out + f32 residual read (what the O-projection and FC2 do: x += W a + b in the f32 residual stream)"""
+    st = torch.cuda.current_stream().cuda_stream
+    dtype, tdt = capi.SB_DTYPE_F16, torch.float16
+    for (M, N, K, tag) in [(96000, 1280, 1280, "turbo out-proj B64"), (96000, 1280, 5120, "turbo fc2 B64"),
+                           (96000, 768, 768, "small out-proj B64"), (96000, 768, 3072, "small fc2 B64")]:
+        A = (torch.randn(M, K, device=dev) * 0.5).to(tdt)
+        W = (torch.randn(N, K, device=dev) * 0.05).to(tdt)
+        o16 = torch.empty(M, N, dtype=tdt, device=dev)
+        o32 = torch.zeros(M, N, dtype=torch.float32, device=dev)
+        bias = torch.randn(N, device=dev)
+        fl = 2.0 * M * N * K
+        cases = {
+            "out16": lambda: capi.gemm_tn_dev(dtype, A.data_ptr(), K, W.data_ptr(), K, M, N, K, o16.data_ptr(), N, False, bias.data_ptr(), 0, 0, 0, 0, st),
+            "out32": lambda: capi.gemm_tn_dev(dtype, A.data_ptr(), K, W.data_ptr(), K, M, N, K, o32.data_ptr(), N, True, bias.data_ptr(), 0, 0, 0, 0, st),
+            "out32+res": lambda: capi.gemm_tn_dev(dtype, A.data_ptr(), K, W.data_ptr(), K, M, N, K, o32.data_ptr(), N, True, bias.data_ptr(), 0, o32.data_ptr(), N, 0, st),
+        }
+        row = {"kernel": "gemm_tcgen05 epilogues", "case": tag, "M": M, "N": N, "K": K}
+        for name, f in cases.items():
+            med, mn = timeit(f, flush=False)
+            row[name + "_ms"] = med
+            row[name + "_tflops"] = fl / med / 1e9
+        print(json.dumps(row), flush=True)
+        del A, W, o16, o32
+
+
+def bench_attn():
+    """encoder attention, exact f32 sweep or packed (env SB_ATTN_PACKED, read once per process), with the error against
+    an f32 torch reference on the same 16-bit inputs"""
+    st = torch.cuda.current_stream().cuda_stream
+    l = capi.lib()
+    for dtype, tdt in ((capi.SB_DTYPE_F16, torch.float16), (capi.SB_DTYPE_BF16, torch.bfloat16)):
+        for (Wn, H, tag) in [(16, 20, "turbo 16 windows"), (16, 12, "small 16 windows")]:
+            d = 64 * H
+            T = 1500
+            torch.manual_seed(1)
+            qkv = (torch.randn(Wn * T, 3 * d, device=dev) * 1.5).to(tdt)
+            out = torch.empty(Wn * T, d, dtype=tdt, device=dev)
+            f = lambda: capi.check(l.sb_attn_enc_dev(dtype, qkv.data_ptr(), out.data_ptr(), Wn, T, d, H, st))
+            med, mn = timeit(f, flush=False)
+            # reference on window 0, f32
+            q, k, v = [x.float().reshape(T, H, 64).transpose(0, 1) for x in qkv[:T].split(d, dim=1)]
+            ref = torch.softmax(q @ k.transpose(1, 2) / 8.0, dim=-1) @ v
+            ref = ref.transpose(0, 1).reshape(T, d)
+            got = out[:T].float()
+            err = (got - ref)
+            fl = 4.0 * Wn * H * T * T * 64
+            print(json.dumps({"kernel": "k_attn_enc_ts", "packed": os.environ.get("SB_ATTN_PACKED", "0"), "dtype": str(tdt), "case": tag,
+                              "ms": med, "tflops": fl / med / 1e9, "rel_rms": (err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item(),
+                              "max_abs": err.abs().max().item()}), flush=True)
+
+
 def bench_logmel():
     st = torch.cuda.current_stream().cuda_stream
     for n_mel in (80, 128):
@@ -114,3 +167,7 @@ if __name__ == "__main__":
         bench_logmel()
     if "skinny" in what:
         bench_skinny()
+    if "epilogue" in what:
+        bench_gemm_epilogue()
+    if "attn" in what:
+        bench_attn()
