@@ -26,8 +26,9 @@ std::optional<uint64_t> TranscriptionManager::unload_limit_seconds(ModelUnloadTi
     return std::nullopt;
 }
 
-TranscriptionManager::TranscriptionManager(ModelResolver resolver, SettingsFn get_settings)
-    : resolver_(std::move(resolver)), get_settings_(std::move(get_settings)), last_activity_(now_ms()) {
+TranscriptionManager::TranscriptionManager(ModelResolver resolver, SettingsFn get_settings, EventFn on_model_state)
+    : resolver_(std::move(resolver)), get_settings_(std::move(get_settings)), on_model_state_(std::move(on_model_state)),
+      last_activity_(now_ms()) {
     // idle watcher: checks every 10 s, unloads after the configured idle time (transcription.rs:112-163)
     watcher_ = std::thread([this] {
         while (!shutdown_.load()) {
@@ -36,7 +37,8 @@ TranscriptionManager::TranscriptionManager(ModelResolver resolver, SettingsFn ge
             const Settings s = get_settings_();
             const auto limit = unload_limit_seconds(s.model_unload_timeout);
             if (!limit || s.model_unload_timeout == ModelUnloadTimeout::Immediately) continue;
-            if (now_ms() - last_activity_.load() > *limit * 1000 && is_model_loaded()) unload_model();
+            if (now_ms() - last_activity_.load() > *limit * 1000 && is_model_loaded() && unload_model().ok)
+                emit("unloaded");          // (the reference emits from unload_model AND from the watcher, :139-147)
         }
     });
 }
@@ -63,6 +65,7 @@ Result<Unit> TranscriptionManager::unload_model() {
         std::lock_guard<std::mutex> g(model_mu_);
         current_model_id_.reset();
     }
+    emit("unloaded");
     return Result<Unit>::Ok({});
 }
 
@@ -72,6 +75,7 @@ void TranscriptionManager::maybe_unload_immediately(const std::string&) {
 }
 
 Result<Unit> TranscriptionManager::load_model(const std::string& model_id) {
+    emit("loading_started", model_id);
     const auto path = resolver_(model_id);
     if (!path) return Result<Unit>::Err("Model not found: " + model_id);
     const Settings s = get_settings_();
@@ -83,8 +87,11 @@ Result<Unit> TranscriptionManager::load_model(const std::string& model_id) {
     cfg.use_cuda_graph = 1;
     if (!s.devices.empty()) { cfg.devices = s.devices.data(); cfg.n_devices = (int)s.devices.size(); }
     sb_engine* e = nullptr;
-    if (sb_engine_create(&cfg, &e) != SB_OK)
-        return Result<Unit>::Err(std::string("Failed to load whisper model ") + model_id + ": " + sb_last_error());
+    if (sb_engine_create(&cfg, &e) != SB_OK) {
+        const std::string msg = std::string("Failed to load whisper model ") + model_id + ": " + sb_last_error();
+        emit("loading_failed", model_id, msg);
+        return Result<Unit>::Err(msg);
+    }
     {
         std::lock_guard<std::mutex> g(engine_mu_);
         if (engine_) sb_engine_destroy(engine_);
@@ -94,6 +101,7 @@ Result<Unit> TranscriptionManager::load_model(const std::string& model_id) {
         std::lock_guard<std::mutex> g(model_mu_);
         current_model_id_ = model_id;
     }
+    emit("loaded", model_id);
     return Result<Unit>::Ok({});
 }
 

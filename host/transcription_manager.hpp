@@ -77,8 +77,12 @@ class TranscriptionManager {
     // model_id -> path of a GGML .bin (ModelManager::get_model_path, model.rs:804-847)
     using ModelResolver = std::function<std::optional<std::string>(const std::string& model_id)>;
     using SettingsFn = std::function<Settings()>;
+    // app_handle.emit("model-state-changed", ModelStateEvent{event_type, model_id, model_name, error}) stand-in
+    // (domain/events.rs:3-43; emitted at transcription.rs:139-147, 195-199, 227-236, 263-275, 357-366):
+    // event_type is "loading_started" | "loading_failed" | "loaded" | "unloaded"
+    using EventFn = std::function<void(const std::string& event_type, const std::string& model_id, const std::string& error)>;
 
-    TranscriptionManager(ModelResolver resolver, SettingsFn get_settings);
+    TranscriptionManager(ModelResolver resolver, SettingsFn get_settings, EventFn on_model_state = nullptr);
     ~TranscriptionManager();
     TranscriptionManager(const TranscriptionManager&) = delete;
     TranscriptionManager& operator=(const TranscriptionManager&) = delete;
@@ -98,8 +102,12 @@ class TranscriptionManager {
     static std::optional<uint64_t> unload_limit_seconds(ModelUnloadTimeout t);
     std::string effective_language(const Settings& s) const;
 
+    void emit(const char* event_type, const std::string& model_id = "", const std::string& error = "") {
+        if (on_model_state_) on_model_state_(event_type, model_id, error);
+    }
     ModelResolver resolver_;
     SettingsFn get_settings_;
+    EventFn on_model_state_;
     std::mutex engine_mu_;                 // engine: Arc<Mutex<Option<LoadedEngine>>>
     sb_engine* engine_ = nullptr;
     std::mutex model_mu_;

@@ -47,9 +47,13 @@ class Settings:
 
 
 class TranscriptionManager:
-    def __init__(self, model_paths: Dict[str, str], get_settings: Callable[[], Settings]):
+    def __init__(self, model_paths: Dict[str, str], get_settings: Callable[[], Settings],
+                 on_model_state: Optional[Callable[[str, Optional[str], Optional[str]], None]] = None):
+        """on_model_state(event_type, model_id, error): stand-in for app_handle.emit("model-state-changed", ModelStateEvent)
+        (domain/events.rs:3-43): "loading_started" | "loading_failed" | "loaded" | "unloaded"."""
         self._paths = model_paths                  # ModelManager::get_model_path stand-in
         self._get_settings = get_settings
+        self._emit = on_model_state or (lambda *a: None)
         self._engine: Optional[capi.Engine] = None
         self._engine_lock = threading.Lock()
         self._current_model_id: Optional[str] = None
@@ -67,12 +71,14 @@ class TranscriptionManager:
                 self._engine.close()
             self._engine = None
         self._current_model_id = None
+        self._emit("unloaded", None, None)
 
     def maybe_unload_immediately(self, context: str) -> None:
         if self._get_settings().model_unload_timeout == "immediately" and self.is_model_loaded():
             self.unload_model()
 
     def load_model(self, model_id: str) -> None:
+        self._emit("loading_started", model_id, None)
         path = self._paths.get(model_id)
         if path is None:
             raise TranscriptionError(f"Model not found: {model_id}")
@@ -80,12 +86,15 @@ class TranscriptionManager:
         try:
             eng = capi.Engine(path, device=s.device, max_batch=s.max_batch, dtype=s.dtype)
         except capi.SbError as e:
-            raise TranscriptionError(f"Failed to load whisper model {model_id}: {e}") from e
+            msg = f"Failed to load whisper model {model_id}: {e}"
+            self._emit("loading_failed", model_id, msg)
+            raise TranscriptionError(msg) from e
         with self._engine_lock:
             if self._engine is not None:
                 self._engine.close()
             self._engine = eng
         self._current_model_id = model_id
+        self._emit("loaded", model_id, None)
 
     def initiate_model_load(self) -> None:
         with self._loading_cv:

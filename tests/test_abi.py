@@ -88,3 +88,27 @@ def test_rust_bindings_assert_the_same_layout():
         rust_fields = re.findall(r"pub (\w+):", body)
         want = [f for s_, f, _, _ in _golden_layout() if s_ == sname]
         assert rust_fields == want, (sname, rust_fields, want)
+
+
+def test_rust_drop_in_declares_the_reference_surface():
+    """rust/transcription_b200.rs must offer what every caller of managers::transcription uses (reference
+    transcription.rs:89-624 / transcription_mock.rs:25-55) -- it cannot be compiled here, so the surface is checked textually."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "rust", "transcription_b200.rs")).read()
+    for sig in ("pub fn new(app_handle: &AppHandle, model_manager: Arc<ModelManager>) -> Result<Self>",
+                "pub fn is_model_loaded(&self) -> bool", "pub fn unload_model(&self) -> Result<()>",
+                "pub fn maybe_unload_immediately(&self, context: &str)", "pub fn load_model(&self, model_id: &str) -> Result<()>",
+                "pub fn initiate_model_load(&self)", "pub fn get_current_model(&self) -> Option<String>",
+                "pub fn transcribe(&self, audio: Vec<f32>) -> Result<String>", "impl Drop for TranscriptionManager",
+                "#[derive(Clone)]\npub struct TranscriptionManager"):
+        assert sig in src, sig
+    # the pieces round 1 lacked: idle watcher, model-state events, last_activity, jargon prompt + corrections
+    for needle in ("fn spawn_idle_watcher", "\"model-state-changed\"", "ModelStateKind::LoadingFailed", "last_activity.store",
+                   "build_initial_prompt", "apply_corrections", "p.initial_prompt =", "handle.join()"):
+        assert needle in src, needle
+    # every sb_* symbol the drop-in calls is declared by the sys crate, and every one of those by the header
+    sys_src = open(os.path.join(root, "rust", "spittle-b200-sys", "src", "lib.rs")).read()
+    used = set(re.findall(r"sys::(sb_\w+)\(", src))
+    declared = set(re.findall(r"pub fn (sb_\w+)\(", sys_src))
+    assert used and used <= declared, used - declared
+    assert declared <= set(declared_symbols()), declared - set(declared_symbols())

@@ -7,10 +7,12 @@ from spittle_b200 import capi, synth, ggml_format
 
 pytestmark = pytest.mark.gpu
 
-# Stated logit tolerances (raw logits have std ~ 5 with the "sharp" recipe):
-LOGIT_TOL = {capi.SB_DTYPE_F16: 2e-1, capi.SB_DTYPE_BF16: 1.0}
-# A token mismatch is only acceptable where the oracle's own top-1/top-2 margin is below this:
-MARGIN_TOL = {capi.SB_DTYPE_F16: 4e-1, capi.SB_DTYPE_BF16: 2.0}
+# Stated logit tolerances (raw logits have std ~ 5 with the "sharp" recipe) = 1.5 x the error measured on B200 in round 2
+# (nano: f16 8.5e-2, bf16 6.1e-1 over 3 windows x 20 teacher-forced steps; Small / Turbo f16: 2.0e-2, test_parity_sizes_gpu.py)
+LOGIT_TOL = {capi.SB_DTYPE_F16: 0.13, capi.SB_DTYPE_BF16: 0.92}
+# A token mismatch is only acceptable where the oracle's own top-1/top-2 margin is below this (two logits move against
+# each other: 1.5 x the logit tolerance would be the worst case; the largest margin at a measured divergence was 0.060 / f16):
+MARGIN_TOL = {capi.SB_DTYPE_F16: 0.15, capi.SB_DTYPE_BF16: 1.4}
 
 
 def _setup(model_dir, arch, dtype, clip_ids, n_steps):
@@ -43,7 +45,7 @@ def test_teacher_forced_logits_match_oracle(cuda_dev, model_dir, dtype):
             err = float(np.abs(logits[w, s] - ref).max())
             assert err <= LOGIT_TOL[dtype], (w, s, err)
             # argmax of the *filtered* logits must agree wherever the oracle margin is decisive
-            if tr.margins[s] > 2 * LOGIT_TOL[dtype]:
+            if tr.margins[s] > 1.5 * LOGIT_TOL[dtype]:
                 assert toks[w, s] == tr.tokens[s]
         print(f"dtype={dtype} window {w}: {len(tr.tokens)} steps, max logit err "
               f"{max(float(np.abs(logits[w, s] - tr.logits_trace[s]).max()) for s in range(len(tr.tokens))):.3e}")
@@ -68,8 +70,9 @@ def test_free_running_tokens_match_oracle(cuda_dev, model_dir, dtype, graph):
         print(f"dtype={dtype} window {w}: first divergence at step {first}, oracle margin {tr.margins[first]:.4f}")
         assert tr.margins[first] < MARGIN_TOL[dtype], (w, first, tr.margins[first])
     print(f"dtype={dtype} graph={graph}: {exact}/{len(traces)} windows token-exact over {n_steps} steps")
+    # every divergence above was checked against MARGIN_TOL; on top of that most windows must be identical
     if dtype == capi.SB_DTYPE_F16:
-        assert exact >= len(traces) // 2
+        assert exact >= (3 * len(traces)) // 4
     eng.close()
 
 

@@ -33,7 +33,8 @@ def test_cpp_transcription_manager_cli(cuda_dev, model_dir, tmp_path):
 def test_python_transcription_manager(cuda_dev, model_dir):
     path = synth.ensure_model_file("nano", model_dir)
     st = transcription.Settings(selected_model="nano", selected_language="en")
-    tm = transcription.TranscriptionManager({"nano": path}, lambda: st)
+    events = []
+    tm = transcription.TranscriptionManager({"nano": path}, lambda: st, on_model_state=lambda *a: events.append(a))
     assert tm.transcribe(np.zeros(0, np.float32)) == ""
     with pytest.raises(transcription.TranscriptionError, match="Model is not loaded for transcription."):
         tm.transcribe(synth.make_clip(1, 2.0))
@@ -53,6 +54,19 @@ def test_python_transcription_manager(cuda_dev, model_dir):
     assert not tm.is_model_loaded()
     with pytest.raises(transcription.TranscriptionError, match="Model not found"):
         tm.load_model("missing")
+    # model-state-changed events (domain/events.rs): background load, then the immediate unload after the last call
+    kinds = [e[0] for e in events]
+    assert kinds[:2] == ["loading_started", "loaded"] and events[1][1] == "nano" and kinds.count("unloaded") == 1
+    # jargon: the dictionary's terms become Whisper's initial_prompt (transcription.rs:461-492) and steer the decoder
+    from spittle_b200 import jargon
+    st.model_unload_timeout = "never"
+    tm.load_model("nano")
+    plain = tm.transcribe(clip)
+    st.jargon_custom_terms = ["kubectl", "TypeScript", "Next.js"]
+    assert tm._initial_prompt(st) == jargon.build_initial_prompt(jargon.ActiveDictionary(st.jargon_custom_terms, []))
+    with_prompt = tm.transcribe(clip)
+    assert with_prompt != plain
+    tm.unload_model()
 
 
 def test_full_size_batch_invariance_and_determinism(cuda_dev, model_dir):

@@ -11,11 +11,12 @@ from spittle_b200 import capi, ggml_format, synth
 
 pytestmark = pytest.mark.gpu
 
-# Stated tolerances, f16 engine vs the ggml-faithful oracle (act_f16): 1.5 x the error measured on B200 (printed by
-# the tests; profiles/r2_parity_sizes.md holds the measured values)
-ENC_REL_RMS = {"small": 1.5e-3, "large-v3-turbo": 1.5e-3}
-LOGIT_TOL = {"small": 0.12, "large-v3-turbo": 0.12}       # raw logits have std ~ 5 (sharp recipe)
-MARGIN_TOL = 0.15                                         # a token may only differ where the oracle margin is below this
+# Stated tolerances, f16 engine vs the ggml-faithful oracle (act_f16): 1.5 x the error measured on B200 in round 2
+# (profiles/r2_parity_sizes.md: encoder rel-RMS 4.70e-4 / 4.76e-4, teacher-forced logits 1.84e-2 / 2.00e-2 over 16 steps).
+# For scale: two CPU restatements of the same rounding points (numpy oracle vs oracle/cpu_ref) differ by 3.7e-4 / 1.5e-2.
+ENC_REL_RMS = {"small": 7.1e-4, "large-v3-turbo": 7.2e-4}
+LOGIT_TOL = {"small": 2.8e-2, "large-v3-turbo": 3.0e-2}   # raw logits have std ~ 5 (sharp recipe)
+MARGIN_TOL = 0.06                                         # a token may only differ where the oracle margin is below 2 x LOGIT_TOL
 
 
 @pytest.fixture(scope="module", params=["small", "large-v3-turbo"])
