@@ -70,7 +70,7 @@ struct SkinnyEpilogue {
 // conv1 im2col: window w reads clip clip_of[w] starting at mel frame seek[w]
 struct Im2col1Args {
     const float* mel;          // [n_clips][n_mel][mel_stride]
-    const float* floor_val;    // [n_clips]
+    const float* floor_val;    // [n_clips]; used when clip_max == null (mel already normalised)
     const int* clip_of;        // [n_windows]
     const int* seek;           // [n_windows]
     const int* n_calc;         // [n_clips]
@@ -79,6 +79,8 @@ struct Im2col1Args {
     int mel_stride;
     int n_mel;
     int n_frames;              // 3000
+    const int32_t* clip_max = nullptr;   // [n_clips] or null.  Not null: `mel` holds RAW log10 values and the kernel applies whisper.cpp's
+                               // normalisation itself: max(v, clip maximum - 8), then (v + 4) / 4; the floor follows from it
 };
 
 struct GemmEpilogue {
@@ -90,6 +92,8 @@ struct GemmEpilogue {
     const float* residual;  // f32 [*, ldr] or null; added after activation
     int ldr;
     int res_row_mod;      // 0: residual row = row; >0: row % res_row_mod (positional embedding)
+    int direct = -1;      // epilogue store path: 1 = registers -> global (lane = row, 16-byte stores), 0 = transposed through
+                          // shared memory (whole 128-byte lines per warp instruction), -1 = the launcher's choice
 };
 
 int gemm_tn(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,

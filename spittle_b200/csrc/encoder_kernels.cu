@@ -26,7 +26,10 @@ __global__ void __launch_bounds__(256) k_im2col_conv1(Im2col1Args a, T* out) {
     const int clip = a.clip_of[w];
     const int seek = a.seek[w];
     const int ncalc = a.n_calc[clip], nlen = a.n_len[clip];
-    const float floor_v = a.floor_val[clip];
+    // raw mel (engine path): global max - 8 clamp and (x + 4) / 4 applied here, the same two operations k_logmel_norm performs
+    const bool raw = a.clip_max != nullptr;
+    const float mmax = raw ? key_float(__ldg(a.clip_max + clip)) - 8.0f : 0.f;
+    const float floor_v = raw ? (fmaxf(-10.0f, mmax) + 4.0f) * 0.25f : a.floor_val[clip];
     const float* mel = a.mel + (int64_t)clip * a.mel_clip_stride;
     for (int i = threadIdx.x; i < a.n_mel * 34; i += blockDim.x) {
         const int c = i / 34, j = i - c * 34;
@@ -34,7 +37,7 @@ __global__ void __launch_bounds__(256) k_im2col_conv1(Im2col1Args a, T* out) {
         float v = 0.0f;
         if (t >= 0 && t < a.n_frames) {
             const int f = seek + t;
-            if (f < ncalc) v = __ldg(mel + (int64_t)c * a.mel_stride + f);
+            if (f < ncalc) { v = __ldg(mel + (int64_t)c * a.mel_stride + f); if (raw) v = (fmaxf(v, mmax) + 4.0f) * 0.25f; }
             else if (f < nlen) v = floor_v;
         }
         s_tile[c * 35 + j] = v;

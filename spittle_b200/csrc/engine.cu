@@ -20,9 +20,9 @@
 struct sb_melplan;
 namespace sb {
 extern std::atomic<uint64_t> g_launches;
-int logmel_launch(const sb_melplan* plan, const float* pcm, int n_clips, size_t n_samples, int64_t pcm_clip_stride,
-                  float* mel, int64_t mel_clip_stride, int mel_stride, int32_t* clip_max, float* floor_val,
-                  cudaStream_t st);
+int logmel_launch_ragged(const sb_melplan* plan, const float* const* pcm_ptrs, const int* n_samples_v, const int* n_calc_v,
+                         int n_clips, int max_n_calc, float* mel, int64_t mel_clip_stride, int mel_stride, int32_t* clip_max,
+                         cudaStream_t st);
 
 static const char* kLangs[] = {
     "en", "zh", "de", "es", "ru", "ko", "fr", "ja", "pt", "tr", "pl", "ca", "nl", "ar", "sv", "it", "id", "hi", "fi",
@@ -209,7 +209,7 @@ struct Engine : EngineBase {
     LnW ln_f;
 
     // workspaces
-    DevBuf b_pcm, b_mel, b_cmax, b_floor, b_clipmeta, b_winmeta;
+    DevBuf b_pcm, b_mel, b_cmax, b_floor, b_clipmeta, b_winmeta, b_pcmptr;
     DevBuf b_col1, b_c1, b_x, b_h, b_qkv, b_att, b_mlp, b_enc32;
     DevBuf b_ckv, b_kself, b_vself, b_dx, b_dh, b_dqkv, b_datt, b_dq, b_dmlp, b_logits;
     DevBuf b_state, b_tokens, b_margins, b_tids, b_plogs, b_next, b_forced, b_tick, b_prompt, b_lang, b_init, b_prow, b_temp, b_rng;
@@ -304,7 +304,7 @@ struct Engine : EngineBase {
         DevBuf* bufs[] = {&b_pcm, &b_mel, &b_cmax, &b_floor, &b_clipmeta, &b_winmeta, &b_col1, &b_c1, &b_x, &b_h, &b_qkv,
                           &b_att, &b_mlp, &b_enc32, &b_ckv, &b_kself, &b_vself, &b_dx, &b_dh, &b_dqkv, &b_datt, &b_dq,
                           &b_dmlp, &b_logits, &b_state, &b_tokens, &b_margins, &b_tids, &b_next, &b_forced, &b_tick, &b_prompt,
-                          &b_lang, &b_init, &b_trace, &b_prow, &b_plogs, &b_temp, &b_rng};
+                          &b_lang, &b_init, &b_trace, &b_prow, &b_plogs, &b_temp, &b_rng, &b_pcmptr};
         for (DevBuf* b : bufs) b->release();
         PinBuf* pins[] = {&h_state, &h_tokens, &h_margins, &h_tids, &h_lang, &h_init, &h_winmeta, &h_prow, &h_plogs, &h_rng};
         for (PinBuf* b : pins) b->release();
@@ -1143,7 +1143,7 @@ struct Engine : EngineBase {
         const int n_mel = hp.n_mels;
         std::vector<ClipRun> clips(G);
         const std::vector<int> init_past = initial_prompt_tokens(p);
-        size_t max_n = 0; int max_calc = 0; bool uniform = true; int n_active = 0;
+        size_t max_n = 0; int max_calc = 0; int n_active = 0;
         for (int c = 0; c < G; ++c) {
             ClipRun& r = clips[c];
             r.n = ns[c];
@@ -1157,43 +1157,49 @@ struct Engine : EngineBase {
             ++n_active;
             max_n = std::max(max_n, r.n); max_calc = std::max(max_calc, r.n_calc);
         }
-        for (int c = 0; c < G; ++c) if (clips[c].active && clips[c].n != max_n) uniform = false;
         float ms_mel = 0.f, ms_enc = 0.f, ms_total = 0.f;
         int rc;
         if (max_n > 0) {
             const int stride = (int)round_up(max_calc, 32);
-            if ((rc = b_pcm.ensure((size_t)G * max_n * 4))) return rc;
             if ((rc = b_mel.ensure((size_t)G * n_mel * stride * 4))) return rc;
             if ((rc = b_cmax.ensure(G * 4))) return rc;
             if ((rc = b_floor.ensure(G * 4))) return rc;
-            if ((rc = b_clipmeta.ensure(G * 2 * 4))) return rc;
+            if ((rc = b_clipmeta.ensure(G * 3 * 4))) return rc;
+            if ((rc = b_pcmptr.ensure(G * sizeof(float*)))) return rc;
             const int S = std::min(max_batch, n_active);
             if ((rc = b_winmeta.ensure(std::max(G, S) * 2 * 4))) return rc;
             if ((rc = h_winmeta.ensure(S * 2 * 4))) return rc;
             if ((rc = ensure_encoder_ws(S, false))) return rc;
-            SB_CUDA_CHECK(cudaEventRecord(ev[0], st));
-            std::vector<int> meta(2 * G, 0);
+            // clips that already live in this device's memory are read in place; host clips are staged (H2D)
+            std::vector<char> on_device(G, 0);
+            bool any_host = false;
             for (int c = 0; c < G; ++c) {
                 if (!clips[c].active) continue;
-                // cudaMemcpyDefault: the clip may live in host (pinned or pageable) or device memory
-                SB_CUDA_CHECK(cudaMemcpyAsync(b_pcm.as<float>() + (size_t)c * max_n, pcm[c], clips[c].n * 4, cudaMemcpyDefault, st));
-                stats.pcm_bytes += clips[c].n * 4.0;
-                meta[c] = clips[c].n_calc; meta[G + c] = clips[c].n_len;
+                cudaPointerAttributes attr{};
+                if (cudaPointerGetAttributes(&attr, pcm[c]) == cudaSuccess)
+                    on_device[c] = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) && attr.device == device;
+                else cudaGetLastError();
+                any_host = any_host || !on_device[c];
             }
-            SB_CUDA_CHECK(cudaMemcpyAsync(b_clipmeta.p, meta.data(), 2 * G * 4, cudaMemcpyHostToDevice, st));
-            bool all_active = true;
-            for (int c = 0; c < G; ++c) all_active = all_active && clips[c].active;
-            if (uniform && all_active) {
-                if ((rc = logmel_launch(melplan, b_pcm.as<float>(), G, max_n, (int64_t)max_n, b_mel.as<float>(),
-                                        (int64_t)n_mel * stride, stride, b_cmax.as<int32_t>(), b_floor.as<float>(), st))) return rc;
-            } else {
-                for (int c = 0; c < G; ++c) {
-                    if (!clips[c].active) continue;
-                    if ((rc = logmel_launch(melplan, b_pcm.as<float>() + (size_t)c * max_n, 1, clips[c].n, (int64_t)max_n,
-                                            b_mel.as<float>() + (size_t)c * n_mel * stride, (int64_t)n_mel * stride, stride,
-                                            b_cmax.as<int32_t>() + c, b_floor.as<float>() + c, st))) return rc;
+            if (any_host && (rc = b_pcm.ensure((size_t)G * max_n * 4))) return rc;
+            SB_CUDA_CHECK(cudaEventRecord(ev[0], st));
+            std::vector<int> meta(3 * G, 0);             // n_calc | n_len | n_samples
+            std::vector<const float*> ptrs(G, nullptr);
+            for (int c = 0; c < G; ++c) {
+                if (!clips[c].active) continue;
+                if (on_device[c]) ptrs[c] = pcm[c];
+                else {
+                    ptrs[c] = b_pcm.as<float>() + (size_t)c * max_n;
+                    SB_CUDA_CHECK(cudaMemcpyAsync(b_pcm.as<float>() + (size_t)c * max_n, pcm[c], clips[c].n * 4, cudaMemcpyHostToDevice, st));
                 }
+                stats.pcm_bytes += clips[c].n * 4.0;
+                meta[c] = clips[c].n_calc; meta[G + c] = clips[c].n_len; meta[2 * G + c] = (int)clips[c].n;
             }
+            SB_CUDA_CHECK(cudaMemcpyAsync(b_clipmeta.p, meta.data(), 3 * G * 4, cudaMemcpyHostToDevice, st));
+            SB_CUDA_CHECK(cudaMemcpyAsync(b_pcmptr.p, ptrs.data(), G * sizeof(float*), cudaMemcpyHostToDevice, st));
+            // ONE log-mel launch for the whole (ragged) group; raw log10 values, normalised by the conv1 im2col
+            if ((rc = logmel_launch_ragged(melplan, b_pcmptr.as<const float*>(), b_clipmeta.as<int>() + 2 * G, b_clipmeta.as<int>(), G,
+                                           max_calc, b_mel.as<float>(), (int64_t)n_mel * stride, stride, b_cmax.as<int32_t>(), st))) return rc;
             SB_CUDA_CHECK(cudaEventRecord(ev[1], st));
             SB_CUDA_CHECK(cudaStreamSynchronize(st));   // meta vector lifetime + mel timing
             { float t; cudaEventElapsedTime(&t, ev[0], ev[1]); ms_mel += t; }
@@ -1274,7 +1280,7 @@ struct Engine : EngineBase {
                         SB_CUDA_CHECK(cudaMemcpyAsync(b_winmeta.p, wm, 2 * k * 4, cudaMemcpyHostToDevice, st));
                         Im2col1Args a{b_mel.as<float>(), b_floor.as<float>(), b_winmeta.as<int>(), b_winmeta.as<int>() + k,
                                       b_clipmeta.as<int>(), b_clipmeta.as<int>() + G, (int64_t)n_mel * stride, stride, n_mel,
-                                      2 * hp.n_audio_ctx};
+                                      2 * hp.n_audio_ctx, b_cmax.as<int32_t>()};        // raw mel: normalised on the fly
                         if ((rc = im2col_conv1<T>(a, b_col1.as<T>(), k, st))) return rc;
                         if ((rc = encode_chunk(k, slots.data(), nullptr))) return rc;
                         if ((rc = prefill(pending))) return rc;

@@ -56,6 +56,11 @@ struct LogmelArgs {
     int n_calc;
     int64_t mel_clip_stride;   // floats between clips
     int mel_stride;            // floats between mel rows
+    // ragged batch in one launch (engine path): per-clip sample pointers / lengths / frame counts (device arrays); the
+    // grid is sized for the longest clip, blocks past a clip's last frame exit.  null -> the uniform geometry above
+    const float* const* pcm_ptrs;
+    const int* n_samples_v;
+    const int* n_calc_v;
 };
 
 __constant__ float c_cos20[20];
@@ -145,9 +150,10 @@ k_logmel(LogmelArgs a, MelPlanDev plan) {
     const int tid = threadIdx.x;
     const int clip = blockIdx.y;
     const int frame0 = blockIdx.x * kFpb;
-    if (frame0 >= a.n_calc) return;
-    const float* pcm = a.pcm + (int64_t)clip * a.pcm_clip_stride;
-    const int n = a.n_samples;
+    const int n_calc_c = a.n_calc_v ? __ldg(a.n_calc_v + clip) : a.n_calc;
+    if (frame0 >= n_calc_c) return;
+    const float* pcm = a.pcm_ptrs ? a.pcm_ptrs[clip] : a.pcm + (int64_t)clip * a.pcm_clip_stride;
+    const int n = a.n_samples_v ? __ldg(a.n_samples_v + clip) : a.n_samples;
 
     // ---- stage samples (padded coordinates p = frame*160 + j ; original index = p - 200) ----
     // p0 - 200 is a multiple of 8, so the interior of the tile is read with aligned 128-bit loads
@@ -237,7 +243,7 @@ k_logmel(LogmelArgs a, MelPlanDev plan) {
     // ---- mel bands: lane = frame, warp strides over mel rows ----
     const int lane = tid & 31, warp = tid >> 5;
     const int frame = frame0 + lane;
-    const bool valid = frame < a.n_calc;
+    const bool valid = frame < n_calc_c;
     float* out = a.mel + (int64_t)clip * a.mel_clip_stride;
     const float* prow = s.p + lane * kPStride;
     float vmax = -10.0f;
@@ -323,6 +329,29 @@ static int upload_twiddles() {
     return SB_OK;
 }
 
+// Ragged batch, one launch, RAW output (engine path): clip c = pcm_ptrs[c][0 .. n_samples_v[c]) (device pointers: the
+// caller's own buffers when they already live in device memory), frames [0, n_calc_v[c]) of mel row-block c receive
+// log10(max(mel energy, 1e-10)) and clip_max[c] the monotone key of the clip's maximum.  The global-max clamp and the
+// (x + 4) / 4 of whisper.cpp are applied by the consumer (k_im2col_conv1) from clip_max: no second pass over the mel.
+int logmel_launch_ragged(const sb_melplan* plan, const float* const* pcm_ptrs, const int* n_samples_v, const int* n_calc_v,
+                         int n_clips, int max_n_calc, float* mel, int64_t mel_clip_stride, int mel_stride, int32_t* clip_max,
+                         cudaStream_t st) {
+    SB_CHECK_ARG(mel_stride >= max_n_calc && mel_stride % 4 == 0, "mel_stride must be >= n_calc and a multiple of 4");
+    SB_CHECK_ARG(n_clips > 0 && n_clips <= 65535, "n_clips out of range");
+    SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(k_logmel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(LogmelSmem))); });
+    LogmelArgs a{};
+    a.mel = mel; a.clip_max = clip_max; a.mel_clip_stride = mel_clip_stride; a.mel_stride = mel_stride;
+    a.pcm_ptrs = pcm_ptrs; a.n_samples_v = n_samples_v; a.n_calc_v = n_calc_v; a.n_calc = max_n_calc;
+    MelPlanDev pd{plan->d_tab, plan->n_mel, plan->n_w, plan->d_start, plan->d_len, plan->d_off, plan->d_w};
+    k_logmel_init<<<ceil_div(n_clips, 256), 256, 0, st>>>(clip_max, n_clips);
+    dim3 grid(ceil_div(max_n_calc, kFpb), n_clips);
+    k_logmel<<<grid, kThreads, sizeof(LogmelSmem), st>>>(a, pd);
+    g_launches += 2;
+    SB_CUDA_CHECK(cudaGetLastError());
+    return SB_OK;
+}
+
 int logmel_launch(const sb_melplan* plan, const float* pcm, int n_clips, size_t n_samples,
                   int64_t pcm_clip_stride, float* mel, int64_t mel_clip_stride, int mel_stride,
                   int32_t* clip_max, float* floor_val, cudaStream_t st) {
@@ -333,7 +362,7 @@ int logmel_launch(const sb_melplan* plan, const float* pcm, int n_clips, size_t 
     SB_CHECK_ARG(n_clips > 0 && n_clips <= 65535, "n_clips out of range");
     SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(k_logmel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)sizeof(LogmelSmem))); });
-    LogmelArgs a;
+    LogmelArgs a{};
     a.pcm = pcm; a.mel = mel; a.clip_max = clip_max;
     a.pcm_clip_stride = pcm_clip_stride; a.n_samples = (int)n_samples; a.n_calc = n_calc;
     a.mel_clip_stride = mel_clip_stride; a.mel_stride = mel_stride;
