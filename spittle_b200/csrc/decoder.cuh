@@ -92,8 +92,6 @@ struct GemmEpilogue {
     const float* residual;  // f32 [*, ldr] or null; added after activation
     int ldr;
     int res_row_mod;      // 0: residual row = row; >0: row % res_row_mod (positional embedding)
-    int direct = -1;      // epilogue store path: 1 = registers -> global (lane = row, 16-byte stores), 0 = transposed through
-                          // shared memory (whole 128-byte lines per warp instruction), -1 = the launcher's choice
 };
 
 int gemm_tn(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,

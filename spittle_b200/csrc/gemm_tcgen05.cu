@@ -291,7 +291,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                     }
                 }
             };
-            if (has_res && ep.direct != 1) load_res(0, rnext);
+            if (has_res) load_res(0, rnext);
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
 #pragma unroll
@@ -303,51 +303,12 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                 float4 rcur[8];
 #pragma unroll
                 for (int it = 0; it < 8; ++it) rcur[it] = rnext[it];
-                if (has_res && ep.direct != 1 && cc + 1 < 4) load_res(cc + 1, rnext);
+                if (has_res && cc + 1 < 4) load_res(cc + 1, rnext);
                 tc_wait_ld();
                 const int col0 = n_blk * kBN + c * 32;
                 if (col0 >= N || row_base >= M) continue;       // warp-uniform
-                if (ep.direct == 1) {
-                    // registers -> global: lane = row, its 32 consecutive columns leave as 16-byte stores.  No shared-memory
-                    // round trip (the staging traffic competes with TMA writes and UMMA operand reads for the SM's 128 B/clk).
-                    const int row = row_base + lane;
-                    if (row < M) {
-                        const int rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : row;
-#pragma unroll
-                        for (int j = 0; j < 8; j += 2) {
-                            const int col = col0 + 4 * j;
-                            if (col >= N) break;                 // N % 8 == 0: an 8-column group is all in or all out
-                            float o[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[4 * j + e]);
-                            if (ep.bias) {
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 4));
-                                o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-                            }
-                            if (ep.act == 1) {
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) o[e] = gelu_tanh(o[e]);
-                            }
-                            if (has_res) {
-                                const float4 r0 = *reinterpret_cast<const float4*>(ep.residual + (int64_t)rrow * ep.ldr + col);
-                                const float4 r1 = *reinterpret_cast<const float4*>(ep.residual + (int64_t)rrow * ep.ldr + col + 4);
-                                o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w; o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
-                            }
-                            if (ep.out_f32) {
-                                float* dst = reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldo + col;
-                                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-                                *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
-                            } else {
-                                uint4 u;
-                                u.x = Op16<T>::pack2(o[0], o[1]); u.y = Op16<T>::pack2(o[2], o[3]);
-                                u.z = Op16<T>::pack2(o[4], o[5]); u.w = Op16<T>::pack2(o[6], o[7]);
-                                *reinterpret_cast<uint4*>(reinterpret_cast<T*>(ep.out) + (int64_t)row * ep.ldo + col) = u;
-                            }
-                        }
-                    }
-                    continue;
-                }
+                // (measured and rejected, round 2: storing straight from the registers -- lane = row, 16-byte stores, no
+                // shared-memory round trip -- is 15-45 % SLOWER on every K <= 1280 shape: profiles/r2_gemm_epilogue_ab.md)
                 // transpose through smem: lane = row writes its 32 values as 8 float4, chunk index XOR (row & 7)
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -469,11 +430,6 @@ int gemm_tn(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, i
     // CTA pairs (cta_group::2, 256x256 tiles) when there are enough rows to fill the machine with them
     static const int pair_min_m = [] { const char* e = getenv("SB_GEMM_PAIR_MIN_M"); return e ? atoi(e) : 4096; }();
     const bool pair = M >= pair_min_m;
-    GemmEpilogue epv = ep;
-    if (epv.direct < 0) {
-        static const int env = [] { const char* e = getenv("SB_GEMM_DIRECT_EPI"); return e ? atoi(e) : 0; }();
-        epv.direct = env;
-    }
     CUtensorMap ta, tb;
     int rc = make_tmap_2d(&ta, A, dtype, M, K, lda, kBM);
     if (rc != SB_OK) return rc;
@@ -492,15 +448,15 @@ int gemm_tn(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, i
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        if (dtype == SB_DTYPE_F16) SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tn<__half, 2>, ta, tb, epv, M, N, K));
-        else SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tn<__nv_bfloat16, 2>, ta, tb, epv, M, N, K));
+        if (dtype == SB_DTYPE_F16) SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tn<__half, 2>, ta, tb, ep, M, N, K));
+        else SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tn<__nv_bfloat16, 2>, ta, tb, ep, M, N, K));
     } else {
         const int num_tiles = ceil_div(M, kBM) * ceil_div(N, kBN);
         const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
         if (dtype == SB_DTYPE_F16)
-            k_gemm_tn<__half, 1><<<grid, kGemmThreads, GemmCfg<1>::kSmem, st>>>(ta, tb, epv, M, N, K);
+            k_gemm_tn<__half, 1><<<grid, kGemmThreads, GemmCfg<1>::kSmem, st>>>(ta, tb, ep, M, N, K);
         else
-            k_gemm_tn<__nv_bfloat16, 1><<<grid, kGemmThreads, GemmCfg<1>::kSmem, st>>>(ta, tb, epv, M, N, K);
+            k_gemm_tn<__nv_bfloat16, 1><<<grid, kGemmThreads, GemmCfg<1>::kSmem, st>>>(ta, tb, ep, M, N, K);
     }
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
