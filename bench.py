@@ -3,12 +3,12 @@
 
 Metric (BASELINE.json): RTFx = audio-seconds per wall-second.  Workload: BASELINE.json configs[2] "Whisper
 Large-v3 Turbo (128-mel, 4-layer decoder) batched clips sharded across 1/2/4/8 B200" -- the model north_star names --
-with 64 synthetic 30 s clips per GPU; SB_BENCH_ARCH=small runs configs[1] (Whisper Small, 64 clips), and at N = 1 the
+with 128 synthetic 30 s clips per GPU; SB_BENCH_ARCH=small runs configs[1] (Whisper Small, 64 clips), and at N = 1 the
 default run carries that configuration as the secondary `config.small_64` entry.
 A step = one pass of the whole hot path (log-mel -> encoder -> cross-KV -> greedy decode with
-the whisper.cpp seek loop -> text) over one batch of 64 clips through the C ABI
+the whisper.cpp seek loop -> text) over one batch of clips through the C ABI
 (sb_transcribe_batch).  N > 1: one process per GPU (torchrun), every rank transcribes its own
-64 clips (weak scaling, no collective on the data path -- clips do not interact).
+batch (weak scaling, no collective on the data path -- clips do not interact).
 
   value  RTFx with the PCM already resident in HBM (device pointers handed to the C ABI)
   e2e    RTFx with pinned HOST buffers: H2D of the PCM and D2H of tokens inside the timed region
@@ -40,7 +40,9 @@ sys.path.insert(0, ROOT)
 import numpy as np
 
 ARCH = os.environ.get("SB_BENCH_ARCH", "large-v3-turbo")
-CLIPS_PER_GPU = int(os.environ.get("SB_BENCH_CLIPS", "64"))
+# clips per GPU: configs[1] fixes 64 for Whisper Small; configs[2] (Turbo) leaves it open -- 128 clips on 128 decode slots is
+# where one B200 saturates (profiles/r2_batch_sweep.md: 64 -> 3217, 128 -> 3555 RTFx)
+CLIPS_PER_GPU = int(os.environ.get("SB_BENCH_CLIPS", "64" if ARCH == "small" else "128"))
 CLIP_SECONDS = 30.0
 
 
@@ -211,18 +213,19 @@ def run_reference(args):
     return 0
 
 
-def workload_config(arch: str, extra=None):
+def workload_config(arch: str, extra=None, n_clips=None):
     which = {"large-v3-turbo": "configs[2]", "small": "configs[1]", "large-v3": "configs[3] model"}.get(arch, "test architecture")
-    cfg = {"workload": f"Whisper {arch} greedy decode, batch of {CLIPS_PER_GPU} synthetic 30 s 16 kHz clips per GPU (BASELINE.json {which}), "
+    n_clips = n_clips or CLIPS_PER_GPU
+    cfg = {"workload": f"Whisper {arch} greedy decode, batch of {n_clips} synthetic 30 s 16 kHz clips per GPU (BASELINE.json {which}), "
                        "random-init 'sharp' recipe seed 42, language en, timestamps on, text context carried between the windows of a "
                        "clip like whisper_full, no temperature fallback",
-           "arch": arch, "clips_per_gpu": CLIPS_PER_GPU}
+           "arch": arch, "clips_per_gpu": n_clips}
     if extra:
         cfg.update(extra)
     return cfg
 
 
-def measure(arch, args, torch, capi, dist, rank, local_rank, world, steps, warmup, trace=True):
+def measure(arch, args, torch, capi, dist, rank, local_rank, world, steps, warmup, trace=True, n_clips=None):
     """Load `arch`, run warm-up + the two timed regions (device-resident PCM, pinned host PCM) + one traced batch."""
     if rank == 0:
         model_path(arch)                  # rank 0 writes the synthetic model file once; other ranks wait for it
@@ -230,15 +233,16 @@ def measure(arch, args, torch, capi, dist, rank, local_rank, world, steps, warmu
         dist.barrier()
     path = model_path(arch)
     dtype = capi.SB_DTYPE_F16 if args.dtype == "f16" else capi.SB_DTYPE_BF16
-    eng = capi.Engine(path, device=local_rank, max_batch=CLIPS_PER_GPU, dtype=dtype)
-    clips = make_clips(rank, CLIPS_PER_GPU)
+    n_clips = n_clips or CLIPS_PER_GPU
+    eng = capi.Engine(path, device=local_rank, max_batch=n_clips, dtype=dtype)
+    clips = make_clips(rank, n_clips)
     n = clips[0].shape[0]
     host = torch.from_numpy(np.stack(clips)).pin_memory()
     devbuf = host.to(torch.device("cuda", local_rank))
     params = capi.default_params()
-    host_ptrs = [host.data_ptr() + i * n * 4 for i in range(CLIPS_PER_GPU)]
-    dev_ptrs = [devbuf.data_ptr() + i * n * 4 for i in range(CLIPS_PER_GPU)]
-    sizes = [n] * CLIPS_PER_GPU
+    host_ptrs = [host.data_ptr() + i * n * 4 for i in range(n_clips)]
+    dev_ptrs = [devbuf.data_ptr() + i * n * 4 for i in range(n_clips)]
+    sizes = [n] * n_clips
     eng_stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
 
     def sync_all():
@@ -357,10 +361,10 @@ def main():
     secondary = None
     if world == 1 and ARCH != "small" and not args.no_secondary:
         # BASELINE.json configs[1] (Whisper Small, 64 clips, 1 GPU) carried as a secondary entry of the default run
-        m2 = measure("small", args, torch, capi, None, rank, local_rank, 1, min(steps, 5), 3, trace=False)
+        m2 = measure("small", args, torch, capi, None, rank, local_rank, 1, min(steps, 5), 3, trace=False, n_clips=64)
         k2 = min(steps, 5)
-        secondary = {"workload": workload_config("small")["workload"], "value": audio_s * k2 / (m2["ms_dev"] / 1e3),
-                     "e2e": audio_s * k2 / (m2["ms_e2e"] / 1e3), "unit": "x real-time", "steps": k2, "ms_per_step": m2["ms_dev"] / k2,
+        secondary = {"workload": workload_config("small", n_clips=64)["workload"], "value": 64 * CLIP_SECONDS * k2 / (m2["ms_dev"] / 1e3),
+                     "e2e": 64 * CLIP_SECONDS * k2 / (m2["ms_e2e"] / 1e3), "unit": "x real-time", "steps": k2, "ms_per_step": m2["ms_dev"] / k2,
                      "ms_encode": m2["st_dev"]["encode_ms"] / k2, "ms_decode": m2["st_dev"]["decode_ms"] / k2,
                      "decoder_steps_per_step": m2["st_dev"]["decoder_steps"] / k2}
     if rank != 0:

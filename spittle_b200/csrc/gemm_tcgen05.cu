@@ -42,16 +42,23 @@ constexpr int kBM = 128;
 constexpr int kBN = 256;
 constexpr int kBK = 64;          // 64 x 2 B = 128 B = swizzle span
 constexpr int kUmmaK = 16;
-constexpr int kEpiWarps = 8;           // two per TMEM lane quarter, each takes half of the 256 columns
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kStagingBytes = 32 * 32 * 4;          // per epilogue warp: one 32x32 f32 chunk, XOR-swizzled
 constexpr int kStageBytesA = kBM * kBK * 2;
-template <int kCtas> struct GemmCfg {
-    static constexpr int kStages = kCtas == 1 ? 4 : 6;
+// kEW epilogue warps (warps 2 .. 2 + kEW): kEW / 4 per TMEM lane quarter, each owning 256 / (kEW / 4) accumulator columns.
+// ncu on the 8-warp epilogue (profiles/r2_full_gemm_tn.md): FC1 + GELU tensor pipe 53 % active with XU 21 %, FMA 15 %, issue 30 %
+// -- nothing saturated: two warps per scheduler cannot hide the tcgen05.ld / shared-memory / MUFU latencies of the chunk
+// loop, and for K <= 1280 the epilogue of a tile is as long as its mainloop.  16 warps (four per scheduler, <= 113 registers)
+// on the CTA-pair tiles (5-stage ring instead of 6 to make room for the staging buffers); the residual rows of a chunk are
+// requested while its TMEM load is in flight.
+template <int kCtas, int kEW> struct GemmCfg {
+    static_assert(kEW == 8 || (kEW == 16 && kCtas == 2), "16 epilogue warps only with the CTA-pair tile (shared-memory budget)");
+    static constexpr int kStages = kCtas == 1 ? 4 : (kEW == 16 ? 5 : 6);
+    static constexpr int kThreads = 64 + 32 * kEW;                  // warp 0 TMA, warp 1 MMA, the rest epilogue
     static constexpr int kRowsB = kBN / kCtas;                      // W rows (output columns) staged by one CTA
     static constexpr int kStageBytesB = kRowsB * kBK * 2;
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-    static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * kStagingBytes;
+    static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEW * kStagingBytes;
+    static_assert(kSmem <= 227 * 1024, "shared memory");
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------
@@ -157,11 +164,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return d;
 }
 
-template <typename T, int kCtas>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <typename T, int kCtas, int kEW, bool kRes>
+__global__ void __launch_bounds__(GemmCfg<kCtas, kEW>::kThreads, 1)
 k_gemm_tn(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
           GemmEpilogue ep, int M, int N, int K) {
-    using Cfg = GemmCfg<kCtas>;
+    using Cfg = GemmCfg<kCtas, kEW>;
+    constexpr int kEpiWarps = kEW;
     constexpr int kStages = Cfg::kStages;
     constexpr int kStageBytes = Cfg::kStageBytes;
     constexpr int kTileM = kBM * kCtas;                    // rows of one output tile (of the CTA pair)
@@ -264,9 +272,10 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
             }
         }
     } else {
-        const int ew = warp - 2;              // 0..7
+        const int ew = warp - 2;              // 0 .. kEW - 1
         const int q = warp & 3;               // TMEM lane quarter this warp may access
-        const int half = ew >> 2;             // which 128 columns of the 256-wide accumulator
+        constexpr int kChunks = 8 / (kEW / 4);     // 32-column chunks per warp: 4 (8 warps) or 2 (16 warps)
+        const int part = ew >> 2;             // which kChunks x 32 columns of the 256-wide accumulator
         float4* stg = reinterpret_cast<float4*>(base_ptr + kStages * kStageBytes + 256 + ew * kStagingBytes);
         const int rsub = lane >> 3;           // read-back: 4 rows per instruction, 8 lanes x float4 per row
         const int c4 = lane & 7;
@@ -274,36 +283,31 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             const int n_blk = tile % num_n, m_blk = tile / num_n;
             const int row_base = m_blk * kTileM + (int)cta_rank * kBM + q * 32;
-            // residual rows of this warp's 4 chunks are independent of the MMA: they are fetched one chunk
-            // ahead (the first one before waiting for the accumulator) so their HBM latency is not exposed
             const int col_l = c4 * 4;
-            const bool has_res = ep.residual != nullptr;
-            float4 rnext[8];
-            auto load_res = [&](int cc, float4 (&dst)[8]) {
-                const int col = n_blk * kBN + (half * 4 + cc) * 32 + col_l;
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int row = row_base + it * 4 + rsub;
-                    dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (has_res && row < M && col < N) {
-                        const int rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : row;
-                        dst[it] = *reinterpret_cast<const float4*>(ep.residual + (int64_t)rrow * ep.ldr + col);
-                    }
-                }
-            };
-            if (has_res) load_res(0, rnext);
+            const bool has_res = kRes && ep.residual != nullptr;
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const int c = half * 4 + cc;
+            for (int cc = 0; cc < kChunks; ++cc) {
+                const int c = part * kChunks + cc;
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kBN + c * 32);
                 tc_ld32(taddr, v);
-                float4 rcur[8];
+                // the residual rows of this chunk are requested while the TMEM load is in flight (four warps per scheduler
+                // cover the rest of the HBM latency)
+                float4 rcur[kRes ? 8 : 1];
+                if constexpr (kRes) {
+                    const int colr = n_blk * kBN + c * 32 + col_l;
 #pragma unroll
-                for (int it = 0; it < 8; ++it) rcur[it] = rnext[it];
-                if (has_res && cc + 1 < 4) load_res(cc + 1, rnext);
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = row_base + it * 4 + rsub;
+                        rcur[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (has_res && row < M && colr < N) {
+                            const int rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : row;
+                            rcur[it] = *reinterpret_cast<const float4*>(ep.residual + (int64_t)rrow * ep.ldr + colr);
+                        }
+                    }
+                }
                 tc_wait_ld();
                 const int col0 = n_blk * kBN + c * 32;
                 if (col0 >= N || row_base >= M) continue;       // warp-uniform
@@ -338,7 +342,9 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                     const int row = row_base + it * 4 + rsub;
                     if (row < M && col_ok) {
                         float4 o = f[it];
-                        if (has_res) { o.x += rcur[it].x; o.y += rcur[it].y; o.z += rcur[it].z; o.w += rcur[it].w; }
+                        if constexpr (kRes) {
+                            if (has_res) { o.x += rcur[it].x; o.y += rcur[it].y; o.z += rcur[it].z; o.w += rcur[it].w; }
+                        }
                         if (ep.out_f32) {
                             *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldo + col) = o;
                         } else {
@@ -433,30 +439,41 @@ int gemm_tn(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, i
     CUtensorMap ta, tb;
     int rc = make_tmap_2d(&ta, A, dtype, M, K, lda, kBM);
     if (rc != SB_OK) return rc;
-    rc = make_tmap_2d(&tb, W, dtype, N, K, ldw, pair ? GemmCfg<2>::kRowsB : GemmCfg<1>::kRowsB);
+    rc = make_tmap_2d(&tb, W, dtype, N, K, ldw, pair ? GemmCfg<2, 8>::kRowsB : GemmCfg<1, 8>::kRowsB);
     if (rc != SB_OK) return rc;
-    SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::kSmem));
-        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__half, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::kSmem));
-        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__nv_bfloat16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::kSmem));
-        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__half, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::kSmem)); });
+    using C1 = GemmCfg<1, 8>; using C2 = GemmCfg<2, 16>;
+    SB_ONCE_PER_DEVICE({
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__nv_bfloat16, 1, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1::kSmem));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__half, 1, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1::kSmem));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__nv_bfloat16, 2, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::kSmem));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__half, 2, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::kSmem));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__nv_bfloat16, 2, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::kSmem));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tn<__half, 2, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::kSmem)); });
     if (pair) {
+        const bool res = ep.residual != nullptr;
         const int num_tiles = ceil_div(M, 2 * kBM) * ceil_div(N, kBN);
         const int clusters = std::min(num_tiles, num_sms() / 2);
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = GemmCfg<2>::kSmem; cfg.stream = st;
+        cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(C2::kThreads);
+        cfg.dynamicSmemBytes = C2::kSmem; cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        if (dtype == SB_DTYPE_F16) SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tn<__half, 2>, ta, tb, ep, M, N, K));
-        else SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tn<__nv_bfloat16, 2>, ta, tb, ep, M, N, K));
+        if (dtype == SB_DTYPE_F16) {
+            if (res) SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tn<__half, 2, 16, true>, ta, tb, ep, M, N, K));
+            else SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tn<__half, 2, 16, false>, ta, tb, ep, M, N, K));
+        } else {
+            if (res) SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tn<__nv_bfloat16, 2, 16, true>, ta, tb, ep, M, N, K));
+            else SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tn<__nv_bfloat16, 2, 16, false>, ta, tb, ep, M, N, K));
+        }
     } else {
         const int num_tiles = ceil_div(M, kBM) * ceil_div(N, kBN);
         const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
         if (dtype == SB_DTYPE_F16)
-            k_gemm_tn<__half, 1><<<grid, kGemmThreads, GemmCfg<1>::kSmem, st>>>(ta, tb, ep, M, N, K);
+            k_gemm_tn<__half, 1, 8, true><<<grid, C1::kThreads, C1::kSmem, st>>>(ta, tb, ep, M, N, K);
         else
-            k_gemm_tn<__nv_bfloat16, 1><<<grid, kGemmThreads, GemmCfg<1>::kSmem, st>>>(ta, tb, ep, M, N, K);
+            k_gemm_tn<__nv_bfloat16, 1, 8, true><<<grid, C1::kThreads, C1::kSmem, st>>>(ta, tb, ep, M, N, K);
     }
     g_launches += 1;
     SB_CUDA_CHECK(cudaGetLastError());
