@@ -12,15 +12,16 @@ batch (weak scaling, no collective on the data path -- clips do not interact).
 
   value  RTFx with the PCM already resident in HBM (device pointers handed to the C ABI)
   e2e    RTFx with pinned HOST buffers: H2D of the PCM and D2H of tokens inside the timed region
-  roofline      the kernel with the largest share of the step (decoder-step projections on Small, the tcgen05
-                GEMM on Large-v3 / Turbo): algorithmic bytes or FLOPs per launch / its CUDA-event duration, measured
+  roofline      the kernel with the largest share of the step (the tcgen05 GEMM on Large-v3-Turbo, the decoder-step
+                projections on Small): algorithmic bytes or FLOPs per launch / its CUDA-event duration, measured
                 live; the other hot kernels follow in roofline_extra
-  cpu_baseline  the numpy oracle ("port" of whisper.cpp) on the host cores,
-                bounded sample
-  --impl reference   times that same CPU port as the reference arm (the reference itself cannot be
+  cpu_baseline  oracle/cpu_ref (C++ restatement of the whisper.cpp CPU path, std::thread, AVX2 / AVX-512) on the host cores,
+                all threads and whisper.cpp's default 4, bounded sample
+  parity        tokens of the timed GPU run against that CPU restatement on the first clips of the batch
+  --impl reference   times the same CPU restatement as the reference arm (the reference itself cannot be
                      built here: no Rust toolchain, crates not vendored -- DESIGN.md)
 
-Timing: W >= 3 warm-up steps; inputs (64 x 1.92 MB PCM plus ~4 GB of activations and 3.5 GB of
+Timing: W >= 3 warm-up steps; inputs (128 x 1.92 MB PCM plus ~6 GB of activations and 3.9 GB of
 cross-KV per step) are far larger than the 126 MB L2, so no explicit flush is needed; device
 timing with CUDA events bracketed by barrier + synchronize, max over ranks.
 """
@@ -415,8 +416,9 @@ def main():
          "alg_bytes_per_launch": st_dec["skinny_bytes"] / max(st_dec["skinny_launches"], 1),
          "avg_launch_us": skinny_avg_us, "launches_per_step": st_dec["skinny_launches"],
          "share_of_step": dec_share * st_dec["skinny_ms"] / t_all,
-         "note": "latency-bound: 1-5 MB of weights per launch inside a ~140-launch dependent chain per lane-step "
-                 f"(traced lane-step {lane_step_us:.0f} us); duration = first block start -> last block end (device trace); "
+         "note": "latency-bound launch (1-13 MB of weights) inside the dependent chain of a lane-step "
+                 f"(traced lane-step {lane_step_us:.0f} us) that overlaps the other lanes' cross-attention streams; duration = first block "
+                 "start -> last block end (device trace); the decode PHASE runs within ~1.5x of its HBM floor (DESIGN.md 4.3); "
                  "ncu (profiles/r1_full_skinny_gemm.md, 768x768 launch): 1.31 MB DRAM read for 1.18 MB of weights",
          "peak_source": f"{peak_src} hbm_gbs", "traffic": 1.31e6 / 1.18e6 * st_dec["skinny_bytes"] / max(st_dec["skinny_launches"], 1)},
         {"kernel": "k_dec_cross_attn (decoder cross-attention over the cached 1500 encoder keys, register streaming, "
@@ -435,17 +437,24 @@ def main():
          "launches_per_step": st_dec["dln_launches"] + st_dec["dself_launches"],
          "share_of_step": dec_share * (st_dec["dln_ms"] + st_dec["dself_ms"]) / t_all,
          "note": "latency-bound stages of the chain", "traffic": None},
-        {"kernel": "k_gemm_tn (tcgen05 / TMEM / TMA, encoder + cross-KV projections)", "bound": "tensor",
+        {"kernel": "k_gemm_tn (tcgen05 / TMEM / TMA, CTA pairs, 16 epilogue warps: encoder + cross-KV projections)", "bound": "tensor",
          "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
+         "alg_flops_per_launch": st_dev["gemm_flops"] / max(st_dev["gemm_launches"], 1),
+         "avg_launch_us": 1e3 * st_dev["gemm_ms"] / max(st_dev["gemm_launches"], 1),
          "launches_per_step": st_dev["gemm_launches"] / steps, "share_of_step": st_dev["gemm_ms"] / steps / ms_step,
-         "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)", "traffic": None},
+         "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step); {gemm_tflops / peaks['bf16_tflops']:.3f} of the burst figure",
+         "note": "2 M N K FLOP per launch / CUDA-event time of every launch on the engine's stream, summed over the timed steps",
+         # DRAM bytes per launch from ncu --set full of one Turbo encoder layer (profiles/r2_full_gemm_tn.md: 1307 MB for 944 GFLOP over
+         # the QKV / out / FC1 / FC2 launches), scaled by this run's FLOPs per launch
+         "traffic": 1307e6 / 944e9 * st_dev["gemm_flops"] / max(st_dev["gemm_launches"], 1)},
         {"kernel": "k_attn_enc_ts (tcgen05 encoder attention, Q/P as TMEM operands, single exp sweep)", "bound": "tensor",
          "achieved": attn_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": attn_tflops / peak_tf,
          "launches_per_step": st_dev["attn_launches"] / steps, "share_of_step": st_dev["attn_ms"] / steps / ms_step,
          "note": "algorithmic 4 T^2 d FLOP; the kernel is bound by MUFU.EX2 (d_head 64), see profiles/", "traffic": None},
         {"kernel": "k_logmel + k_logmel_norm", "bound": "hbm", "achieved": mel_gbps, "peak": peak_hbm, "unit": "GB/s",
          "frac": mel_gbps / peak_hbm, "share_of_step": st_dev["mel_ms"] / steps / ms_step,
-         "note": "fp32 400-point FFT on the CUDA cores: instruction-bound (DESIGN.md 5)", "traffic": 1.59e8 / 64 * CLIPS_PER_GPU},
+         "note": "fp32 400-point FFT on the CUDA cores: instruction-bound (DESIGN.md 4.2); one ragged launch, device clips read in place, "
+                 "normalisation folded into the conv1 im2col", "traffic": None},
     ]
     entries.sort(key=lambda e: -e["share_of_step"])
     if entries[0]["frac"] is None:      # the dominant entry must carry a roofline fraction
