@@ -3,21 +3,23 @@
 //                      Blackman-Harris^2 sinc taps, run as a Toeplitz GEMM on the tensor cores (3xTF32)
 //                      (reference: audio_toolkit/audio/resampler.rs:24, 51-56; equivalence of the FFT and
 //                      FIR forms: SURVEY.md App. B, ~1e-9; the CUDA-core form of round 1 was removed)
-//   k_silero_features  Silero v4 per-frame front: reflect pad, STFT conv, magnitude, log, adaptive
+//   k_silero_features_fft / _direct   Silero v4 per-frame front: reflect pad, STFT conv, magnitude, log, adaptive
 //                      normalisation, 4 separable conv blocks (reference: vad/silero.rs:41-44 ->
-//                      vad-rs -> onnxruntime; graph first-hand from silero_vad_v4.onnx, App. A)
+//                      vad-rs -> onnxruntime; graph first-hand from silero_vad_v4.onnx, App. A).  The shipped
+//                      model's 258 x 256 STFT basis is a periodic-Hann-windowed DFT (checked at sb_vad_create to
+//                      4e-7), so the convolution runs as 256-point FFTs in registers (25x fewer FLOPs); any other
+//                      basis takes the direct-convolution kernel
 //   k_silero_lstm      the two LSTM(64) layers + decoder + sigmoid, state carried across frames,
 //                      gate weights resident in registers for the whole sequence
 //   k_vad_plan / k_vad_compact   SmoothedVad onset / hangover / prefill FSM and the capture consumer's
 //                      concatenation of kept frames (reference: vad/smoothed.rs:41-96,
 //                      audio/recorder.rs:284-314)
-// All fp32 (Silero decisions are thresholded: SURVEY 7.3 item 6); first, correctness-oriented
-// version on the CUDA cores -- the tensor-core (split-precision) formulation of the FIR and of the
-// STFT convolution is the next step.
+// All fp32 (Silero decisions are thresholded: SURVEY 7.3 item 6).
 #include "common.cuh"
 #include <vector>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 namespace sb {
 extern std::atomic<uint64_t> g_launches;
@@ -154,6 +156,15 @@ struct SileroDev {
     const float *b4_dw_w, *b4_dw_b, *b4_pw_w, *b4_pw_b, *b4_proj_w, *b4_proj_b, *b4_down_w, *b4_down_b;
     const float *lstm_w[2], *lstm_r[2], *lstm_b[2];
     const float *dec_w, *dec_b;
+    // FFT form (sb_vad_create): analysis window = basis row 0, W128^{n2 k1} laid out [k1][n2] and e^{-2 pi i k / 256} in f64, the
+    // residual of the stored basis against the exact windowed DFT (x 2^24, bf16, mma A-fragment order), block-1 pointwise
+    // weights transposed to [ci][16]
+    const float* win;
+    const double2 *tw, *tw2;
+    const uint4* delta_frag;
+    const float *b1_pw_t, *b1_proj_t;
+    // [ci][co] transposes of the k1 convolutions of blocks 1-4 (mix_relu)
+    const float *b1_down_t, *b2_pw_t, *b2_proj_t, *b2_down_t, *b3_pw_t, *b3_down_t, *b4_pw_t, *b4_proj_t, *b4_down_t;
 };
 
 constexpr int kSfFrames = 4;                 // frames per CTA (72 KB of shared memory: three CTAs per SM)
@@ -232,8 +243,8 @@ struct SileroSmem {
 static_assert(sizeof(SileroSmem) * 3 <= 227 * 1024 - 3 * 1024, "three CTAs per SM");
 
 // pcm: [n_streams][n_frames*480]; out: [n_streams][n_frames][64]
-__global__ void __launch_bounds__(kSfThreads, 3) k_silero_features(const float* __restrict__ pcm, int64_t pcm_stride, int n_frames,
-                                                                float* __restrict__ out, SileroDev wts) {
+__global__ void __launch_bounds__(kSfThreads, 3) k_silero_features_direct(const float* __restrict__ pcm, int64_t pcm_stride, int n_frames,
+                                                                       float* __restrict__ out, SileroDev wts) {
     extern __shared__ __align__(16) unsigned char smem_raw_s[];
     SileroSmem& s = *reinterpret_cast<SileroSmem*>(smem_raw_s);
     const int stream = blockIdx.y;
@@ -361,6 +372,441 @@ __global__ void __launch_bounds__(kSfThreads, 3) k_silero_features(const float* 
         float a = __ldg(wts.b4_down_b + co);
         for (int ci = 0; ci < 64; ++ci) a = fmaf(__ldg(wts.b4_down_w + co * 64 + ci), s.v1[ci * kSfFrames + f], a);
         out[((int64_t)stream * n_frames + f0 + f) * 64 + co] = fmaxf(a, 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FFT form of the same front.  The STFT basis of the shipped model is row c: win[n] cos(2 pi c n / 256), row 129 + c:
+// -win[n] sin(2 pi c n / 256) (win = periodic Hann) ROUNDED TO f32: B = fl32(W D).  The kernel evaluates the reference's
+// operator exactly as  B x = D (W x) + delta x,  delta = B - W D  (|delta| <= 7.7e-8, known to f64 on the host):
+//   * D (W x): one 128-point complex FFT per real column, z[n] = x[2n] + i x[2n+1], then the real-input split
+//     X[k] = E[k] + e^{-2 pi i k / 256} O[k], E = (Z[k] + conj Z[128-k]) / 2, O = (Z[k] - conj Z[128-k]) / 2i -- in f64:
+//     log(1 + 2^20 |X|) magnifies the round-off that loud bins leave on quiet ones, and an f32 FFT alone moved the
+//     probabilities by up to 3.5e-4 (the direct f32 convolution needs blocked summation for the same reason).  One FFT =
+//     8 lanes: radix-16 over n1 (n = 8 n1 + n2) in registers, twiddle W128^{n2 k1}, 16 x 8 exchange through shared memory
+//     (row stride 9 double2: conflict-free both ways, __syncwarp only), two radix-8 over n2 per lane, partner bins by
+//     shuffle.  25x fewer FLOPs than the convolution.
+//   * delta x: needs 1 % relative accuracy only (it is a 2e-4 effect on the probabilities) -> one bf16 mma.sync pass
+//     on the tensor cores: delta * 2^24 in bf16, pre-arranged on the host in m16n8k16 A-fragment order (256 rows: 129
+//     cosine + the 127 non-zero sine rows), the columns read as overlapping windows of a bf16 copy of the frames.
+// Without the delta term the FFT differs from the reference's stored operator by 2.4e-4 on the probabilities.
+// 4 frames = 28 columns = 28 FFTs = 224 threads per CTA, 107 KB of shared memory (two CTAs per SM).
+// ------------------------------------------------------------------------------------------
+// out[co][p] = relu(b1[co] + sum_ci w1t[ci][co] in1[ci][off(p)] (+ b2[co] + sum_ci w2t[ci][co] in2[ci][off(p)]) (+ res[co][p])):
+// the pointwise and the strided k1 convolutions of blocks 1-4 on [C][frames x T] tiles.  Weights are transposed to
+// [ci][co] (sb_vad_create) and co is the fastest thread index, so one warp-wide weight load is one contiguous row; the
+// activation is a shared-memory broadcast; PPT outputs per thread share the weight.  Every stage is a single round.
+template <int CIN, int COUT, int P, int PPT, bool TWO, bool RES, typename Off>
+__device__ __forceinline__ void mix_relu(const float* __restrict__ in1, const float* __restrict__ w1t, const float* __restrict__ b1,
+                                         const float* __restrict__ in2, const float* __restrict__ w2t, const float* __restrict__ b2,
+                                         const float* __restrict__ res, float* __restrict__ out, int in_stride, Off off) {
+    constexpr int PG = P / PPT;
+    static_assert(P % PPT == 0, "P must be a multiple of PPT");
+    for (int item = threadIdx.x; item < COUT * PG; item += blockDim.x) {
+        const int co = item % COUT, pg = item / COUT;
+        int o[PPT];
+        float a[PPT];
+        const float bias = TWO ? __ldg(b1 + co) + __ldg(b2 + co) : __ldg(b1 + co);
+#pragma unroll
+        for (int e = 0; e < PPT; ++e) { o[e] = off(pg + PG * e); a[e] = bias; }
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float w = __ldg(w1t + ci * COUT + co);
+#pragma unroll
+            for (int e = 0; e < PPT; ++e) a[e] = fmaf(w, in1[ci * in_stride + o[e]], a[e]);
+            if (TWO) {
+                const float w2 = __ldg(w2t + ci * COUT + co);
+#pragma unroll
+                for (int e = 0; e < PPT; ++e) a[e] = fmaf(w2, in2[ci * in_stride + o[e]], a[e]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < PPT; ++e) {
+            const int pp = pg + PG * e;
+            float v = a[e];
+            if (RES) v += res[co * P + pp];
+            out[co * P + pp] = fmaxf(v, 0.f);
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void dft4r(T& r0, T& i0, T& r1, T& i1, T& r2, T& i2, T& r3, T& i3) {
+    const T t0r = r0 + r2, t0i = i0 + i2, t1r = r0 - r2, t1i = i0 - i2;
+    const T t2r = r1 + r3, t2i = i1 + i3, t3r = r1 - r3, t3i = i1 - i3;
+    r0 = t0r + t2r; i0 = t0i + t2i;
+    r2 = t0r - t2r; i2 = t0i - t2i;
+    r1 = t1r + t3i; i1 = t1i - t3r;   // t1 - i t3
+    r3 = t1r - t3i; i3 = t1i + t3r;   // t1 + i t3
+}
+// 16-point forward DFT in registers: in x[n], out X[k] (natural order, in place)
+template <typename T>
+__device__ __forceinline__ void dft16(T (&xr)[16], T (&xi)[16]) {
+    constexpr double c1 = 0.92387953251128673848, c2 = 0.70710678118654752440, c3 = 0.38268343236508977173;
+    constexpr double kC[10] = {1.0, c1, c2, c3, 0.0, -c3, -c2, -c1, -1.0, -c1};
+    constexpr double kS[10] = {0.0, c3, c2, c1, 1.0, c1, c2, c3, 0.0, -c3};
+    // n = 4 n1 + n2: radix-4 over n1 for each n2 -> element 4 k1 + n2
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2)
+        dft4r(xr[n2], xi[n2], xr[4 + n2], xi[4 + n2], xr[8 + n2], xi[8 + n2], xr[12 + n2], xi[12 + n2]);
+#pragma unroll
+    for (int k1 = 1; k1 < 4; ++k1)
+#pragma unroll
+        for (int n2 = 1; n2 < 4; ++n2) {          // W16^{n2 k1} = c - i s
+            const T c = (T)kC[n2 * k1], sn = (T)kS[n2 * k1];
+            const T r = xr[4 * k1 + n2], im = xi[4 * k1 + n2];
+            xr[4 * k1 + n2] = r * c + im * sn;
+            xi[4 * k1 + n2] = im * c - r * sn;
+        }
+    // radix-4 over n2 for each k1: element 4 k1 + k2 = X[k1 + 4 k2]
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1)
+        dft4r(xr[4 * k1], xi[4 * k1], xr[4 * k1 + 1], xi[4 * k1 + 1], xr[4 * k1 + 2], xi[4 * k1 + 2], xr[4 * k1 + 3], xi[4 * k1 + 3]);
+    T tr[16], ti[16];
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) { tr[k1 + 4 * k2] = xr[4 * k1 + k2]; ti[k1 + 4 * k2] = xi[4 * k1 + k2]; }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { xr[k] = tr[k]; xi[k] = ti[k]; }
+}
+// 8-point forward DFT in registers (natural order, in place)
+template <typename T>
+__device__ __forceinline__ void dft8(T (&xr)[8], T (&xi)[8]) {
+    constexpr T h = (T)0.70710678118654752440;
+    dft4r(xr[0], xi[0], xr[2], xi[2], xr[4], xi[4], xr[6], xi[6]);   // E[k] at 2k
+    dft4r(xr[1], xi[1], xr[3], xi[3], xr[5], xi[5], xr[7], xi[7]);   // O[k] at 2k + 1
+    const T o0r = xr[1], o0i = xi[1];
+    const T o1r = h * (xr[3] + xi[3]), o1i = h * (xi[3] - xr[3]);     // W8^1 = h (1 - i)
+    const T o2r = xi[5], o2i = -xr[5];                                // W8^2 = -i
+    const T o3r = h * (xi[7] - xr[7]), o3i = -h * (xr[7] + xi[7]);    // W8^3 = -h (1 + i)
+    const T e0r = xr[0], e0i = xi[0], e1r = xr[2], e1i = xi[2], e2r = xr[4], e2i = xi[4], e3r = xr[6], e3i = xi[6];
+    xr[0] = e0r + o0r; xi[0] = e0i + o0i; xr[4] = e0r - o0r; xi[4] = e0i - o0i;
+    xr[1] = e1r + o1r; xi[1] = e1i + o1i; xr[5] = e1r - o1r; xi[5] = e1i - o1i;
+    xr[2] = e2r + o2r; xi[2] = e2i + o2i; xr[6] = e2r - o2r; xi[6] = e2i - o2i;
+    xr[3] = e3r + o3r; xi[3] = e3i + o3i; xr[7] = e3r - o3r; xi[7] = e3i - o3i;
+}
+
+constexpr int kFfFfts = kSfCols;             // one 128-point complex FFT per real column
+constexpr int kFfThreads = kFfFfts * 8;      // 224
+constexpr int kFfZRow = 9;                   // double2 row stride of the 16 x 8 exchange
+constexpr int kFfZFft = 16 * kFfZRow;        // double2 per FFT
+
+constexpr int kFfXbFrame = kSfPadLen + 8;     // bf16 frame stride: 340 words = 20 mod 32
+constexpr int kFfXbCopy = kSfFrames * kFfXbFrame;   // second copy starts 1360 words = 16 mod 32 further: see the delta term
+
+struct SileroFftSmem {
+    union {
+        float xs[kSfFrames * kSfPadLen];  // reflect-padded frames: dead once the FFTs are done ...
+        struct {                          // ... so the small late-stage buffers live in the same bytes
+            float y2[16 * kSfFrames * 4];
+            float r2[16 * kSfFrames * 4];
+            float z1[32 * kSfFrames * 4];
+            float z2[32 * kSfFrames * 2];
+            float r3[32 * kSfFrames * 2];
+            float u1[32 * kSfFrames * 2];
+            float u2[32 * kSfFrames];
+            float r4[32 * kSfFrames];
+            float v1[64 * kSfFrames];
+        };
+    };
+    union {
+        __nv_bfloat16 xb[2 * kFfXbCopy];       // two bf16 copies of the frames (B operand of the delta term), then ...
+        double2 z[kFfFfts * kFfZFft];          // ... the FFT exchange, then ...
+        float r1[258 * kSfCols];               // ... the depthwise output of block 1
+    };
+    float x1[258 * kSfCols];              // [258][frames][7]: re | im, then magnitude | log spectrum, then magnitude | norm
+    float y1[16 * kSfCols];
+    float part[8 * kSfCols];
+    float mm[kSfFrames];
+};
+static_assert(sizeof(SileroFftSmem) * 2 <= 227 * 1024 - 2 * 1024, "two CTAs per SM");
+static_assert(kSfPadLen == 3 * kFfThreads, "the frame load assumes three samples per thread");
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const float* __restrict__ pcm, int64_t pcm_stride, int n_frames,
+                                                                    float* __restrict__ out, SileroDev wts) {
+    extern __shared__ __align__(16) unsigned char smem_raw_f[];
+    SileroFftSmem& s = *reinterpret_cast<SileroFftSmem*>(smem_raw_f);
+    const int tid = threadIdx.x;
+    const int stream = blockIdx.y;
+    const int f0 = blockIdx.x * kSfFrames;
+    const float* src = pcm + (int64_t)stream * pcm_stride;
+    // reflect pad 96 on both sides of every 480-sample frame; two bf16 copies for the delta term
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int j = tid + r * kFfThreads;
+        int k = j - 96;
+        if (k < 0) k = -k;
+        if (k >= 480) k = 2 * 479 - k;
+#pragma unroll
+        for (int f = 0; f < kSfFrames; ++f) {
+            const float v = (f0 + f < n_frames) ? __ldg(src + (int64_t)(f0 + f) * 480 + k) : 0.0f;
+            s.xs[f * kSfPadLen + j] = v;
+            const __nv_bfloat16 vb = __float2bfloat16_rn(v);
+            s.xb[f * kFfXbFrame + j] = vb;
+            s.xb[kFfXbCopy + f * kFfXbFrame + j] = vb;
+        }
+    }
+    __syncthreads();
+    {
+        // delta term on the tensor cores: C[256 rows][28 columns] = (2^24 delta)[256][256] . x[256][28].  Warp w takes the
+        // row tiles w, w + 7, w + 14; per k-step one coalesced 16-byte load of the pre-arranged A fragment and, per column
+        // tile, the B fragment straight from the bf16 frames.  MMA column (tile nt, g) = STFT column t = 2 nt + (g >> 2) of
+        // frame g & 3, read from copy g >> 2: the eight windows of one B load then start in eight different 4-bank groups
+        // (frame stride 20, copy offset 16 banks), where consecutive windows of ONE frame would all share one (64 samples
+        // = 32 words apart).  Tile 3 has t = 6 only; its upper half repeats it and is dropped.
+        const int wq = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+        int boff[4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int t = min(2 * nt + (g >> 2), 6);
+            boff[nt] = (g >> 2) * kFfXbCopy + (g & 3) * kFfXbFrame + 64 * t + 2 * t4;
+        }
+        for (int mt = wq; mt < 16; mt += 7) {
+            float acc[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+            const uint4* ap = wts.delta_frag + (size_t)mt * 16 * 32 + lane;
+#pragma unroll 4
+            for (int ks = 0; ks < 16; ++ks) {
+                const uint4 a = __ldg(ap + ks * 32);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(s.xb + boff[nt] + ks * 16);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(s.xb + boff[nt] + ks * 16 + 8);
+                    mma_bf16_16816(acc[nt], a, b0, b1);
+                }
+            }
+            const int r0 = mt * 16 + g, r1 = r0 + 8;
+            const int R0 = r0 < 129 ? r0 : r0 + 1, R1 = r1 < 129 ? r1 : r1 + 1;   // sine rows 1..127 live at 130..256
+            constexpr float kScale = 1.0f / 16777216.0f;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int gc = 2 * t4 + e, t = 2 * nt + (gc >> 2);           // C fragment: MMA columns 2 t4, 2 t4 + 1
+                    if (t < 7) {
+                        const int c = (gc & 3) * 7 + t;
+                        s.x1[R0 * kSfCols + c] = kScale * acc[nt][e];
+                        s.x1[R1 * kSfCols + c] = kScale * acc[nt][2 + e];
+                    }
+                }
+        }
+    }
+    __syncthreads();
+    {
+        const int j = tid >> 3, l = tid & 7;             // column j = frame * 7 + t
+        const int f = j / 7, t = j - f * 7;
+        const float2* xa = reinterpret_cast<const float2*>(s.xs + f * kSfPadLen + 64 * t);
+        const float2* wn = reinterpret_cast<const float2*>(wts.win);
+        double xr[16], xi[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {                // z[8 n1 + l] = (x[2n], x[2n + 1]) win  (exact in f64)
+            const float2 v = xa[8 * n1 + l], w = __ldg(wn + 8 * n1 + l);
+            xr[n1] = (double)v.x * (double)w.x;
+            xi[n1] = (double)v.y * (double)w.y;
+        }
+        dft16(xr, xi);                                   // Y[k1] of column n2 = l
+        double2* zj = s.z + j * kFfZFft;
+        zj[l] = make_double2(xr[0], xi[0]);
+#pragma unroll
+        for (int k1 = 1; k1 < 16; ++k1) {
+            const double2 w = __ldg(wts.tw + k1 * 8 + l);   // W128^{l k1}
+            zj[k1 * kFfZRow + l] = make_double2(xr[k1] * w.x - xi[k1] * w.y, xr[k1] * w.y + xi[k1] * w.x);
+        }
+        __syncwarp();
+        {
+            // rows k1 = l and l + 8: Z[k1 + 16 k2] = Z[l + 8 m], m = 2 k2 (+ 1 for the second row)
+            double ar[8], ai[8];
+#pragma unroll
+            for (int n2 = 0; n2 < 8; ++n2) { const double2 v = zj[l * kFfZRow + n2]; ar[n2] = v.x; ai[n2] = v.y; }
+            dft8(ar, ai);
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) { xr[2 * k2] = ar[k2]; xi[2 * k2] = ai[k2]; }
+#pragma unroll
+            for (int n2 = 0; n2 < 8; ++n2) { const double2 v = zj[(l + 8) * kFfZRow + n2]; ar[n2] = v.x; ai[n2] = v.y; }
+            dft8(ar, ai);
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) { xr[2 * k2 + 1] = ar[k2]; xi[2 * k2 + 1] = ai[k2]; }
+        }
+        // bin k = l + 8 m needs Z[128 - k]: lane (8 - l) & 7 holds it at index 15 - m (l > 0), lane 0 its own at (16 - m) & 15
+        const int srcl = (tid & 24) | ((8 - l) & 7);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            double pr = __shfl_sync(0xffffffffu, xr[15 - m], srcl);
+            double pi = __shfl_sync(0xffffffffu, xi[15 - m], srcl);
+            if (l == 0) { pr = xr[(16 - m) & 15]; pi = xi[(16 - m) & 15]; }
+            const int k = l + 8 * m;
+            const double er = 0.5 * (xr[m] + pr), ei = 0.5 * (xi[m] - pi);
+            const double qr = 0.5 * (xi[m] + pi), qi = 0.5 * (pr - xr[m]);       // O[k]
+            const double2 w = __ldg(wts.tw2 + k);                                 // e^{-2 pi i k / 256}
+            const float re = (float)(er + (qr * w.x - qi * w.y)), im = (float)(ei + (qr * w.y + qi * w.x));
+            s.x1[k * kSfCols + j] += re;                 // on top of the delta term
+            if (k == 0) s.x1[129 * kSfCols + j] = 0.0f;  // sine row of bin 0: exactly zero, no delta row
+            else s.x1[(129 + k) * kSfCols + j] += im;
+        }
+        if (l == 0) {                                    // X[128] = E[0] - O[0] = Re Z[0] - Im Z[0]
+            s.x1[128 * kSfCols + j] += (float)(xr[0] - xi[0]);
+            s.x1[257 * kSfCols + j] = 0.0f;
+        }
+    }
+    __syncthreads();
+    // magnitude | log(1 + 2^20 magnitude), in place
+    for (int i = tid; i < 129 * kSfCols; i += kFfThreads) {
+        const float re = s.x1[i], im = s.x1[129 * kSfCols + i];
+        const float mag = sqrtf(re * re + im * im);
+        s.x1[i] = mag;
+        s.x1[129 * kSfCols + i] = log1pf(1048576.0f * mag);
+    }
+    __syncthreads();
+    // adaptive normalisation: mean over the 129 bins, reflect pad 3, 7-tap filter, mean over T
+    {
+        const int p = tid / kSfCols, col = tid - p * kSfCols;     // 8 partial sums per column
+        float a = 0.f;
+        for (int i = p; i < 129; i += 8) a += s.x1[(129 + i) * kSfCols + col];
+        s.part[p * kSfCols + col] = a;
+    }
+    __syncthreads();
+    if (tid < kSfFrames) {
+        float m[7];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            float a = 0.f;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) a += s.part[p * kSfCols + tid * 7 + t];
+            m[t] = a / 129.0f;
+        }
+        float p[13];
+        p[0] = m[3]; p[1] = m[2]; p[2] = m[1];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) p[3 + t] = m[t];
+        p[10] = m[5]; p[11] = m[4]; p[12] = m[3];
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) a = fmaf(__ldg(wts.norm_filter + k), p[t + k], a);
+            acc += a;
+        }
+        s.mm[tid] = acc / 7.0f;
+    }
+    __syncthreads();
+    // block 1 (258 -> 16, T 7 -> 4).  Depthwise k5: one (channel, frame) row of 7 per item; the normalisation
+    // (norm = log spectrum - mm[frame]) is applied on the way through and written back for the projection.
+    for (int item = tid; item < 258 * kSfFrames; item += kFfThreads) {
+        const int c = item >> 2, f = item & 3;
+        float* row = s.x1 + item * 7;
+        float v[11];
+        v[0] = v[1] = v[9] = v[10] = 0.f;
+        const float sub = c >= 129 ? s.mm[f] : 0.f;
+#pragma unroll
+        for (int t = 0; t < 7; ++t) { v[2 + t] = row[t] - sub; }
+        if (c >= 129) {
+#pragma unroll
+            for (int t = 0; t < 7; ++t) row[t] = v[2 + t];
+        }
+        float w[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) w[k] = __ldg(wts.b1_dw_w + c * 5 + k);
+        const float b = __ldg(wts.b1_dw_b + c);
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            float a = b;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) a = fmaf(w[k], v[t + k], a);
+            s.r1[item * 7 + t] = fmaxf(a, 0.f);
+        }
+    }
+    __syncthreads();
+    {
+        // pointwise 2 x (258 -> 16) on 28 columns: warp = 4 columns, lane = slice of the 258 input channels
+        // (ci = lane + 32 i), 8 output channels per pass; the 32 partial sums per lane are folded over the 32 lanes
+        // with a halving butterfly (lane ends up with flat output `lane` = column-in-quad * 8 + channel)
+        const int wq = tid >> 5, lane = tid & 31;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+#pragma unroll 1
+            for (int ci = lane; ci < 258; ci += 32) {
+                const float4 a = *reinterpret_cast<const float4*>(s.r1 + ci * kSfCols + 4 * wq);
+                const float4 b = *reinterpret_cast<const float4*>(s.x1 + ci * kSfCols + 4 * wq);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float4 wp = __ldg(reinterpret_cast<const float4*>(wts.b1_pw_t + ci * 16 + 8 * half) + q);
+                    const float4 wj = __ldg(reinterpret_cast<const float4*>(wts.b1_proj_t + ci * 16 + 8 * half) + q);
+                    const float wpv[4] = {wp.x, wp.y, wp.z, wp.w}, wjv[4] = {wj.x, wj.y, wj.z, wj.w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            acc[c * 8 + 4 * q + e] = fmaf(wpv[e], av[c], fmaf(wjv[e], bv[c], acc[c * 8 + 4 * q + e]));
+                }
+            }
+#pragma unroll
+            for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < n / 2; ++i) {
+                    const float send = up ? acc[i] : acc[i + n / 2];
+                    const float keep = up ? acc[i + n / 2] : acc[i];
+                    acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            const int c = lane >> 3, co = 8 * half + (lane & 7);
+            s.y1[co * kSfCols + 4 * wq + c] = fmaxf(acc[0] + __ldg(wts.b1_pw_b + co) + __ldg(wts.b1_proj_b + co), 0.f);
+        }
+    }
+    __syncthreads();
+    constexpr int F = kSfFrames;
+    auto ident = [](int p) { return p; };
+    mix_relu<16, 16, F * 4, 2, false, false>(s.y1, wts.b1_down_t, wts.b1_down_b, nullptr, nullptr, nullptr, nullptr, s.y2, F * 7,
+                                             [](int p) { return (p >> 2) * 7 + (p & 3) * 2; });              // T 7 -> 4
+    __syncthreads();
+    // block 2 (16 -> 32, T 4 -> 2)
+    dw5_relu(s.y2, s.r2, wts.b2_dw_w, wts.b2_dw_b, 16, 4);
+    __syncthreads();
+    mix_relu<16, 32, F * 4, 4, true, false>(s.r2, wts.b2_pw_t, wts.b2_pw_b, s.y2, wts.b2_proj_t, wts.b2_proj_b, nullptr, s.z1, F * 4, ident);
+    __syncthreads();
+    mix_relu<32, 32, F * 2, 2, false, false>(s.z1, wts.b2_down_t, wts.b2_down_b, nullptr, nullptr, nullptr, nullptr, s.z2, F * 4,
+                                             [](int p) { return (p >> 1) * 4 + (p & 1) * 2; });              // T 4 -> 2
+    __syncthreads();
+    // block 3 (32 -> 32 with identity residual, T 2 -> 1)
+    dw5_relu(s.z2, s.r3, wts.b3_dw_w, wts.b3_dw_b, 32, 2);
+    __syncthreads();
+    mix_relu<32, 32, F * 2, 2, false, true>(s.r3, wts.b3_pw_t, wts.b3_pw_b, nullptr, nullptr, nullptr, s.z2, s.u1, F * 2, ident);
+    __syncthreads();
+    mix_relu<32, 32, F, 2, false, false>(s.u1, wts.b3_down_t, wts.b3_down_b, nullptr, nullptr, nullptr, nullptr, s.u2, F * 2,
+                                         [](int p) { return p * 2; });                                       // T 2 -> 1
+    __syncthreads();
+    // block 4 (32 -> 64, T 1)
+    dw5_relu(s.u2, s.r4, wts.b4_dw_w, wts.b4_dw_b, 32, 1);
+    __syncthreads();
+    mix_relu<32, 64, F, 2, true, false>(s.r4, wts.b4_pw_t, wts.b4_pw_b, s.u2, wts.b4_proj_t, wts.b4_proj_b, nullptr, s.v1, F, ident);
+    __syncthreads();
+    // final 64 -> 64, ReLU, write [frame][64]: two frames per thread
+    if (tid < 128) {
+        const int co = tid & 63, fp = tid >> 6;          // frames fp and fp + 2
+        float a0 = __ldg(wts.b4_down_b + co), a1 = a0;
+#pragma unroll
+        for (int ci = 0; ci < 64; ++ci) {
+            const float w = __ldg(wts.b4_down_t + ci * 64 + co);
+            a0 = fmaf(w, s.v1[ci * F + fp], a0);
+            a1 = fmaf(w, s.v1[ci * F + fp + 2], a1);
+        }
+        if (f0 + fp < n_frames) out[((int64_t)stream * n_frames + f0 + fp) * 64 + co] = fmaxf(a0, 0.f);
+        if (f0 + fp + 2 < n_frames) out[((int64_t)stream * n_frames + f0 + fp + 2) * 64 + co] = fmaxf(a1, 0.f);
     }
 }
 
@@ -500,6 +946,8 @@ struct sb_resampler {
 struct sb_vad {
     float* d_blob = nullptr;
     float* d_basis_t = nullptr;
+    void* d_aux = nullptr;         // FFT-form tables, see sb_vad_create
+    bool basis_is_dft = false;     // the STFT basis is a windowed 256-point DFT: k_silero_features_fft applies
     sb::SileroDev dev{};
 };
 
@@ -629,13 +1077,115 @@ int sb_vad_create(const float* blob, size_t n_floats, sb_vad** out) {
     d.lstm_w[0] = ptr[32]; d.lstm_r[0] = ptr[33]; d.lstm_b[0] = ptr[34];
     d.lstm_w[1] = ptr[35]; d.lstm_r[1] = ptr[36]; d.lstm_b[1] = ptr[37];
     d.dec_w = ptr[38]; d.dec_b = ptr[39];
+    // is the basis row c = win[n] cos(2 pi c n / 256), row 129 + c = -win[n] sin(...), win = row 0?  (the shipped model:
+    // yes, to f32 rounding = 7.7e-8)
+    {
+        double worst = 0.0;
+        for (int c = 0; c < 129; ++c)
+            for (int n = 0; n < 256; ++n) {
+                const double w = blob[n], th = 2.0 * M_PI * (double)((c * n) & 255) / 256.0;
+                worst = std::max(worst, std::fabs((double)blob[c * 256 + n] - w * cos(th)));
+                worst = std::max(worst, std::fabs((double)blob[(129 + c) * 256 + n] + w * sin(th)));
+            }
+        const char* force = getenv("SB_SILERO_DIRECT");
+        v->basis_is_dft = worst <= 4e-7 && !(force && force[0] == '1');
+    }
+    // FFT-form tables (one device buffer): win f32[256] | W128^{n2 k1} double2[16][8] | e^{-2 pi i k / 256} double2[128] |
+    // delta fragments uint4[16][16][32] | b1_pw_t f32[258][16] | b1_proj_t f32[258][16] | the nine [ci][co] transposes of the
+    // later k1 convolutions
+    constexpr size_t kOffTw = 1024, kOffTw2 = kOffTw + 2048, kOffDelta = kOffTw2 + 2048, kOffPw = kOffDelta + 16 * 16 * 32 * 16,
+                     kOffProj = kOffPw + 258 * 16 * 4, kOffLate = kOffProj + 258 * 16 * 4, kAuxBytes = kOffLate + 12544 * 4;
+    std::vector<unsigned char> aux(kAuxBytes);
+    float* a_win = reinterpret_cast<float*>(aux.data());
+    double* a_tw = reinterpret_cast<double*>(aux.data() + kOffTw);
+    double* a_tw2 = reinterpret_cast<double*>(aux.data() + kOffTw2);
+    uint32_t* a_delta = reinterpret_cast<uint32_t*>(aux.data() + kOffDelta);
+    float* a_pw = reinterpret_cast<float*>(aux.data() + kOffPw);
+    float* a_proj = reinterpret_cast<float*>(aux.data() + kOffProj);
+    for (int n = 0; n < 256; ++n) a_win[n] = blob[n];
+    for (int k1 = 0; k1 < 16; ++k1)
+        for (int n2 = 0; n2 < 8; ++n2) {
+            const double th = 2.0 * M_PI * (double)(k1 * n2) / 128.0;
+            a_tw[2 * (k1 * 8 + n2)] = cos(th);
+            a_tw[2 * (k1 * 8 + n2) + 1] = -sin(th);
+        }
+    for (int k = 0; k < 128; ++k) {
+        const double th = 2.0 * M_PI * (double)k / 256.0;
+        a_tw2[2 * k] = cos(th);
+        a_tw2[2 * k + 1] = -sin(th);
+    }
+    {
+        // residual of the stored basis against the exact windowed DFT, x 2^24, bf16 (round to nearest even), arranged as
+        // mma.m16n8k16 A fragments.  MMA row r: cosine bin r (r <= 128) or sine bin r - 128 (r >= 129) = basis row r + 1;
+        // the sine rows of bins 0 and 128 are (numerically) zero and are not corrected.
+        auto delta_bf16 = [&](int r, int n) -> uint32_t {
+            const int R = r < 129 ? r : r + 1, k = r < 129 ? r : r - 128;
+            const double th = 2.0 * M_PI * (double)((k * n) & 255) / 256.0;
+            const double exact = (double)blob[n] * (r < 129 ? cos(th) : -sin(th));
+            const float d = (float)(((double)blob[R * 256 + n] - exact) * 16777216.0);
+            uint32_t u;
+            memcpy(&u, &d, 4);
+            u += 0x7FFFu + ((u >> 16) & 1u);
+            return u >> 16;
+        };
+        for (int mt = 0; mt < 16; ++mt)
+            for (int ks = 0; ks < 16; ++ks)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int g = lane >> 2, t = lane & 3, r = mt * 16 + g, c = ks * 16 + 2 * t;
+                    uint32_t* o = a_delta + ((size_t)(mt * 16 + ks) * 32 + lane) * 4;
+                    o[0] = delta_bf16(r, c) | (delta_bf16(r, c + 1) << 16);
+                    o[1] = delta_bf16(r + 8, c) | (delta_bf16(r + 8, c + 1) << 16);
+                    o[2] = delta_bf16(r, c + 8) | (delta_bf16(r, c + 9) << 16);
+                    o[3] = delta_bf16(r + 8, c + 8) | (delta_bf16(r + 8, c + 9) << 16);
+                }
+    }
+    {
+        size_t o = 0;
+        for (int i = 0; i < 4; ++i) o += sizes[i];
+        const float* pw = blob + o;                         // b1_pw_w [16][258]
+        const float* pj = blob + o + sizes[4] + sizes[5];   // b1_proj_w [16][258]
+        for (int ci = 0; ci < 258; ++ci)
+            for (int co = 0; co < 16; ++co) {
+                a_pw[ci * 16 + co] = pw[co * 258 + ci];
+                a_proj[ci * 16 + co] = pj[co * 258 + ci];
+            }
+    }
+    size_t late_off[9];
+    {
+        static const struct { int idx, cout, cin; } kLate[9] = {{8, 16, 16}, {12, 32, 16}, {14, 32, 16}, {16, 32, 32}, {20, 32, 32},
+                                                                {22, 32, 32}, {26, 64, 32}, {28, 64, 32}, {30, 64, 64}};
+        float* dst = reinterpret_cast<float*>(aux.data() + kOffLate);
+        size_t used = 0;
+        for (int i = 0; i < 9; ++i) {
+            size_t o = 0;
+            for (int j = 0; j < kLate[i].idx; ++j) o += sizes[j];
+            const float* w = blob + o;
+            for (int ci = 0; ci < kLate[i].cin; ++ci)
+                for (int co = 0; co < kLate[i].cout; ++co) dst[used + (size_t)ci * kLate[i].cout + co] = w[(size_t)co * kLate[i].cin + ci];
+            late_off[i] = kOffLate + used * 4;
+            used += (size_t)kLate[i].cout * kLate[i].cin;
+        }
+    }
+    SB_CUDA_CHECK(cudaMalloc(&v->d_aux, kAuxBytes));
+    SB_CUDA_CHECK(cudaMemcpy(v->d_aux, aux.data(), kAuxBytes, cudaMemcpyHostToDevice));
+    {
+        const unsigned char* base = reinterpret_cast<const unsigned char*>(v->d_aux);
+        d.win = reinterpret_cast<const float*>(base);
+        d.tw = reinterpret_cast<const double2*>(base + kOffTw);
+        d.tw2 = reinterpret_cast<const double2*>(base + kOffTw2);
+        d.delta_frag = reinterpret_cast<const uint4*>(base + kOffDelta);
+        d.b1_pw_t = reinterpret_cast<const float*>(base + kOffPw);
+        d.b1_proj_t = reinterpret_cast<const float*>(base + kOffProj);
+        const float** slots[9] = {&d.b1_down_t, &d.b2_pw_t, &d.b2_proj_t, &d.b2_down_t, &d.b3_pw_t, &d.b3_down_t, &d.b4_pw_t, &d.b4_proj_t, &d.b4_down_t};
+        for (int i = 0; i < 9; ++i) *slots[i] = reinterpret_cast<const float*>(base + late_off[i]);
+    }
     *out = v;
     return SB_OK;
 }
 
 int sb_vad_destroy(sb_vad* v) {
     if (!v) return SB_OK;
-    cudaFree(v->d_blob); cudaFree(v->d_basis_t);
+    cudaFree(v->d_blob); cudaFree(v->d_basis_t); cudaFree(v->d_aux);
     delete v;
     return SB_OK;
 }
@@ -651,9 +1201,15 @@ int sb_vad_score_dev(const sb_vad* v, const float* pcm16k, int64_t pcm_stride, i
     cudaStream_t st = (cudaStream_t)stream;
     float* feat = (float*)workspace;
     float* h1 = feat + (size_t)n_streams * n_frames * 64;
-    SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_silero_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sb::SileroSmem))); });
+    SB_ONCE_PER_DEVICE({
+        SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_silero_features_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sb::SileroSmem)));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_silero_features_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sb::SileroFftSmem)));
+    });
     dim3 grid((n_frames + sb::kSfFrames - 1) / sb::kSfFrames, n_streams);
-    sb::k_silero_features<<<grid, sb::kSfThreads, sizeof(sb::SileroSmem), st>>>(pcm16k, pcm_stride, n_frames, feat, v->dev);
+    if (v->basis_is_dft)
+        sb::k_silero_features_fft<<<grid, sb::kFfThreads, sizeof(sb::SileroFftSmem), st>>>(pcm16k, pcm_stride, n_frames, feat, v->dev);
+    else
+        sb::k_silero_features_direct<<<grid, sb::kSfThreads, sizeof(sb::SileroSmem), st>>>(pcm16k, pcm_stride, n_frames, feat, v->dev);
     const int nb = (n_streams + sb::kLsStreams - 1) / sb::kLsStreams;
     // state layout [2][n_streams][64]: layer-major like vad-rs' h,c [2,1,64] per stream
     sb::k_silero_lstm<false><<<nb, 256, 0, st>>>(feat, n_streams, n_frames, v->dev.lstm_w[0], v->dev.lstm_r[0], v->dev.lstm_b[0],

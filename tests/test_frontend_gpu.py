@@ -71,6 +71,7 @@ def test_silero_probs_and_decisions_match_oracle(cuda_dev):
         o = silero.SileroOracle(w)
         ref = o.score(clips[s])
         err = np.abs(probs[s] - ref).max()
+        print(f"silero {kinds[s]}: max |dp| {err:.2e}")
         assert err <= SILERO_TOL, (kinds[s], err)
         near = np.abs(ref - 0.3) < SILERO_TOL
         borderline += int(near.sum())
@@ -87,6 +88,38 @@ def test_silero_probs_and_decisions_match_oracle(cuda_dev):
     xg = synth.make_clip(4, seconds=3.0, kind="vowel")
     pg = vad.score(torch.from_numpy(xg[: 100 * 480]).cuda().view(1, 100, 480)).cpu().numpy()[0]
     assert np.abs(pg - gold["silero_vowel_probs"]).max() <= SILERO_TOL
+
+
+def test_silero_direct_convolution_path(cuda_dev, monkeypatch):
+    """sb_vad_create picks the FFT form of the STFT when the basis is a windowed DFT (the shipped model) and the
+    direct-convolution kernel otherwise: both against the oracle, (a) forced through SB_SILERO_DIRECT, (b) on a basis
+    that is NOT a DFT (every row scaled by a different gain -- |X| changes, so a wrongly taken FFT path would show)."""
+    import torch
+    w = silero_weights.load_npz(SILERO)
+    clips = np.stack([synth.make_clip(40 + i, seconds=2.4, kind=k) for i, k in enumerate(["vowel", "mix", "tone"])])
+    n_frames = clips.shape[1] // 480
+    frames = torch.from_numpy(clips[:, : n_frames * 480]).cuda().view(3, n_frames, 480)
+
+    monkeypatch.setenv("SB_SILERO_DIRECT", "1")
+    sv = audio_toolkit.SileroVad(SILERO, 0.3)
+    direct = sv.score(frames).cpu().numpy()
+    monkeypatch.delenv("SB_SILERO_DIRECT")
+    sv2 = audio_toolkit.SileroVad(SILERO, 0.3)
+    fft = sv2.score(frames).cpu().numpy()
+    for s_ in range(3):
+        ref = silero.SileroOracle(w).score(clips[s_])
+        assert np.abs(direct[s_] - ref).max() <= SILERO_TOL
+        assert np.abs(fft[s_] - ref).max() <= SILERO_TOL
+    print("FFT vs direct STFT path, max |dp|:", float(np.abs(fft - direct).max()))
+    # (b) a non-DFT basis
+    w2 = dict(w)
+    gains = (1.0 + 0.25 * np.cos(np.arange(258))).astype(np.float32)
+    w2["stft_basis"] = (w["stft_basis"] * gains[:, None]).astype(np.float32)
+    sv3 = audio_toolkit.SileroVad(w2, 0.3)
+    got = sv3.score(frames).cpu().numpy()
+    for s_ in range(3):
+        ref = silero.SileroOracle(w2).score(clips[s_])
+        assert np.abs(got[s_] - ref).max() <= SILERO_TOL
 
 
 def test_gate_is_bit_exact(cuda_dev):
