@@ -16,6 +16,7 @@
 //                      audio/recorder.rs:284-314)
 // All fp32 (Silero decisions are thresholded: SURVEY 7.3 item 6).
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <vector>
 #include <cmath>
 #include <cstdlib>
@@ -68,6 +69,13 @@ __device__ __forceinline__ uint32_t tf32_hi(float x) { uint32_t r; asm("cvt.rna.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     hi = tf32_hi(x);
     lo = tf32_hi(x - __uint_as_float(hi));
+}
+// cheap split for operands whose partner is split exactly: hi = the top 10 mantissa bits (truncated), lo = the exact
+// remainder, of which the tensor core reads the top 10 bits again: 2^-21 relative, two instructions (cvt.rna.tf32 is
+// emulated with four on sm_100)
+__device__ __forceinline__ void split_tf32_trunc(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -145,6 +153,100 @@ __global__ void __launch_bounds__(256) k_resample_mma(const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// The decimating FIR as D polyphase branches on the f16 tensor cores (the shipped path; k_resample_mma above is kept as the
+// TF32 reference form and for filters whose taps do not fit f16 after scaling).
+//   y[m] = sum_u h[u] x[D m - u] = sum_p sum_q h[D q + p] x_p[m - q],   x_p[r] = x[D r - p],  q < Q = ceil(T / D)
+// Each branch is a stride-1 convolution, i.e. a Toeplitz GEMM whose B operand is a sliding window with a column pitch
+// of 16 samples (not 16 D): A_p[i][j] = h_p[Q - 1 + i - j] (16 x (Q + 15), constant), B_p[j][n] = x_p[m0 + 16 n - (Q-1) + j].
+// mma.sync.m16n8k16 f16 with the 3-pass split a_hi b_hi + a_hi b_lo + a_lo b_hi (hi = f16(v), lo = f16(v - hi); the taps
+// are scaled by 2^12 first so that their lo parts stay normal): products carry 22 bits, accumulation is f32 -- measured
+// 6e-8 against the f64 rubato restatement, like the 3xTF32 form, at twice the MACs per instruction and with
+//   * A fragments (hi | lo) pre-arranged on the host: two coalesced 16-byte loads per k-step, shared by 4 column tiles;
+//   * B fragments by ldmatrix.x4 (hi k 0-7, hi k 8-15, lo k 0-7, lo k 8-15) from f16 copies of the branch signals: the
+//     eight windows of a tile start 16 halves = 8 words apart, so columns 4-7 read a second copy stored 4 words further
+//     and the eight 16-byte rows of every 8 x 8 matrix fall into eight different bank groups;
+//   * no operand splitting in the loop (the TF32 form spent 16 emulated cvt.rna per 6 MMAs: it was issue-bound).
+// CTA = 128 threads = 4 warps x 4 column tiles = 2048 outputs of one stream.
+// ------------------------------------------------------------------------------------------
+constexpr int kRpTile = 2048;
+constexpr int kRpThreads = 128;
+constexpr int kRpScaleLog2 = 12;
+
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+// smem: f16 arrays [part hi|lo][copy 0|1][branch p][L], L = kRpTile + 16 SP + 8; copy 1 is stored 8 halves further
+__global__ void __launch_bounds__(kRpThreads) k_resample_poly(const float* __restrict__ x, int64_t x_stride, int n_in,
+                                                             float* __restrict__ y, int64_t y_stride, int n_out,
+                                                             const uint4* __restrict__ afrag, int D, int Q, int SP) {
+    extern __shared__ __align__(16) unsigned char s_rp[];
+    __half* xh = reinterpret_cast<__half*>(s_rp);
+    const int L = kRpTile + 16 * SP + 8;
+    const int tid = threadIdx.x;
+    const int stream = blockIdx.y;
+    const int m0 = blockIdx.x * kRpTile;
+    const float* xin = x + (int64_t)stream * x_stride;
+    const int64_t rbase = (int64_t)m0 - (Q - 1);
+    const int npair = (kRpTile + 16 * SP) / 2;
+    for (int i = tid; i < D * npair; i += kRpThreads) {
+        const int p = i / npair, r2 = (i - p * npair) * 2;
+        const int64_t s0 = (int64_t)D * (rbase + r2) - p, s1 = s0 + D;
+        const float v0 = (s0 >= 0 && s0 < n_in) ? __ldg(xin + s0) : 0.0f;
+        const float v1 = (s1 >= 0 && s1 < n_in) ? __ldg(xin + s1) : 0.0f;
+        const __half2 hi = __floats2half2_rn(v0, v1);
+        const float2 hf = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+        __half* a = xh + p * L + r2;
+        *reinterpret_cast<__half2*>(a) = hi;
+        *reinterpret_cast<__half2*>(a + D * L + 8) = hi;
+        *reinterpret_cast<__half2*>(a + 2 * D * L) = lo;
+        *reinterpret_cast<__half2*>(a + 3 * D * L + 8) = lo;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    // ldmatrix row of this lane: matrix lane >> 3 = (part, k half), row lane & 7 = column of the tile
+    const int part = lane >> 4, khalf = (lane >> 3) & 1, r = lane & 7, copy = r >> 2;
+    const uint32_t rowbase = (uint32_t)__cvta_generic_to_shared(xh + ((part * 2 + copy) * D) * L + 8 * copy + 16 * (32 * warp + r) + 8 * khalf);
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+    for (int p = 0; p < D; ++p) {
+        const uint4* ap = afrag + ((size_t)p * SP * 32 + lane) * 2;
+        const uint32_t bp = rowbase + (uint32_t)(p * L * 2);
+#pragma unroll 2
+        for (int sI = 0; sI < SP; ++sI) {
+            const uint4 ah = __ldg(ap + sI * 64), al = __ldg(ap + sI * 64 + 1);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                uint32_t b[4];
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(bp + nt * 256 + sI * 32));
+                mma_f16_16816(acc[nt], ah, b[0], b[1]);
+                mma_f16_16816(acc[nt], ah, b[2], b[3]);
+                mma_f16_16816(acc[nt], al, b[0], b[1]);
+            }
+        }
+    }
+    // C[i][n]: c0 (g, 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)  ->  output m0 + 16 n + i
+    float* yo = y + (int64_t)stream * y_stride;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr float kInv = 1.0f / (float)(1 << kRpScaleLog2);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int n = 8 * (4 * warp + nt) + 2 * t + (e & 1);
+            const int m = m0 + 16 * n + g + ((e >> 1) << 3);
+            if (m < n_out) yo[m] = acc[nt][e] * kInv;
+        }
+}
+
+// ------------------------------------------------------------------------------------------
 // Silero v4 (16 kHz) weights, device resident
 // ------------------------------------------------------------------------------------------
 struct SileroDev {
@@ -163,6 +265,7 @@ struct SileroDev {
     const double2 *tw, *tw2;
     const uint4* delta_frag;
     const float *b1_pw_t, *b1_proj_t;
+    const uint4* b1_frag;   // block-1 pointwise weights as TF32 hi | lo mma A fragments: [66 k-steps][32 lanes][2]
     // [ci][co] transposes of the k1 convolutions of blocks 1-4 (mix_relu)
     const float *b1_down_t, *b2_pw_t, *b2_proj_t, *b2_down_t, *b3_pw_t, *b3_down_t, *b4_pw_t, *b4_proj_t, *b4_down_t;
 };
@@ -513,7 +616,10 @@ struct SileroFftSmem {
     union {
         __nv_bfloat16 xb[2 * kFfXbCopy];       // two bf16 copies of the frames (B operand of the delta term), then ...
         double2 z[kFfFfts * kFfZFft];          // ... the FFT exchange, then ...
-        float r1[258 * kSfCols];               // ... the depthwise output of block 1
+        struct {
+            float r1[258 * kSfCols + 8];       // ... the depthwise output of block 1 (+ 8: tile 3 reads past the last row)
+            float part1[7 * 512];              //     and the seven partial tiles of its pointwise product
+        };
     };
     float x1[258 * kSfCols];              // [258][frames][7]: re | im, then magnitude | log spectrum, then magnitude | norm
     float y1[16 * kSfCols];
@@ -562,11 +668,16 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
         // (frame stride 20, copy offset 16 banks), where consecutive windows of ONE frame would all share one (64 samples
         // = 32 words apart).  Tile 3 has t = 6 only; its upper half repeats it and is dropped.
         const int wq = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-        int boff[4];
+        // ldmatrix.x4 = the B fragments of two column tiles at one k-step: lanes 8 i .. 8 i + 7 address the eight rows
+        // (= windows) of matrix i = (tile pair's tile i >> 1, k half i & 1)
+        uint32_t brow[2];
+        {
+            const int i = lane >> 3, r = lane & 7;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            const int t = min(2 * nt + (g >> 2), 6);
-            boff[nt] = (g >> 2) * kFfXbCopy + (g & 3) * kFfXbFrame + 64 * t + 2 * t4;
+            for (int pr = 0; pr < 2; ++pr) {
+                const int t = min(2 * (2 * pr + (i >> 1)) + (r >> 2), 6);
+                brow[pr] = (uint32_t)__cvta_generic_to_shared(s.xb + (r >> 2) * kFfXbCopy + (r & 3) * kFfXbFrame + 64 * t + 8 * (i & 1));
+            }
         }
         for (int mt = wq; mt < 16; mt += 7) {
             float acc[4][4];
@@ -579,10 +690,12 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
             for (int ks = 0; ks < 16; ++ks) {
                 const uint4 a = __ldg(ap + ks * 32);
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(s.xb + boff[nt] + ks * 16);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(s.xb + boff[nt] + ks * 16 + 8);
-                    mma_bf16_16816(acc[nt], a, b0, b1);
+                for (int pr = 0; pr < 2; ++pr) {
+                    uint32_t b[4];
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(brow[pr] + ks * 32));
+                    mma_bf16_16816(acc[2 * pr], a, b[0], b[1]);
+                    mma_bf16_16816(acc[2 * pr + 1], a, b[2], b[3]);
                 }
             }
             const int r0 = mt * 16 + g, r1 = r0 + 8;
@@ -664,7 +777,7 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
         const float re = s.x1[i], im = s.x1[129 * kSfCols + i];
         const float mag = sqrtf(re * re + im * im);
         s.x1[i] = mag;
-        s.x1[129 * kSfCols + i] = log1pf(1048576.0f * mag);
+        s.x1[129 * kSfCols + i] = __logf(fmaf(1048576.0f, mag, 1.0f));   // abs error < 5e-6 on values up to 18: see the parity test
     }
     __syncthreads();
     // adaptive normalisation: mean over the 129 bins, reflect pad 3, 7-tap filter, mean over T
@@ -728,45 +841,51 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
     }
     __syncthreads();
     {
-        // pointwise 2 x (258 -> 16) on 28 columns: warp = 4 columns, lane = slice of the 258 input channels
-        // (ci = lane + 32 i), 8 output channels per pass; the 32 partial sums per lane are folded over the 32 lanes
-        // with a halving butterfly (lane ends up with flat output `lane` = column-in-quad * 8 + channel)
-        const int wq = tid >> 5, lane = tid & 31;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            float acc[32];
+        // pointwise 2 x (258 -> 16) on 28 columns = one [16 x 528] x [528 x 32] product on the tensor cores: K = the 258
+        // depthwise outputs (padded to 264) | the 258 block inputs (padded to 264), 66 k-steps of mma.m16n8k8 TF32 with the
+        // 3-pass split (weights pre-split and pre-arranged as A fragments on the host, activations split here): f32-level
+        // products, f32 accumulation.  Warp w takes the k-steps w, w + 7, ...; the seven partial tiles are summed through
+        // the free tail of the exchange buffer in a fixed order.
+        const int wq = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+        float acc[4][4];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-#pragma unroll 1
-            for (int ci = lane; ci < 258; ci += 32) {
-                const float4 a = *reinterpret_cast<const float4*>(s.r1 + ci * kSfCols + 4 * wq);
-                const float4 b = *reinterpret_cast<const float4*>(s.x1 + ci * kSfCols + 4 * wq);
-                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+        for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const float4 wp = __ldg(reinterpret_cast<const float4*>(wts.b1_pw_t + ci * 16 + 8 * half) + q);
-                    const float4 wj = __ldg(reinterpret_cast<const float4*>(wts.b1_proj_t + ci * 16 + 8 * half) + q);
-                    const float wpv[4] = {wp.x, wp.y, wp.z, wp.w}, wjv[4] = {wj.x, wj.y, wj.z, wj.w};
+            for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+#pragma unroll 2
+        for (int ks = wq; ks < 66; ks += 7) {
+            const uint4 ahv = __ldg(wts.b1_frag + (ks * 32 + lane) * 2), alv = __ldg(wts.b1_frag + (ks * 32 + lane) * 2 + 1);
+            const uint32_t ah[4] = {ahv.x, ahv.y, ahv.z, ahv.w}, al[4] = {alv.x, alv.y, alv.z, alv.w};
+            const bool second = ks >= 33;
+            const float* srcp = second ? s.x1 : s.r1;
+            const int c0 = (second ? ks - 33 : ks) * 8 + t4;           // input channel of b0; b1 is c0 + 4
+            const bool ok0 = c0 < 258, ok1 = c0 + 4 < 258;              // the padding rows: zero weights, but the operand must be finite
+            const float* p0 = srcp + c0 * kSfCols + g;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            acc[c * 8 + 4 * q + e] = fmaf(wpv[e], av[c], fmaf(wjv[e], bv[c], acc[c * 8 + 4 * q + e]));
-                }
+            for (int nt = 0; nt < 4; ++nt) {                           // columns 28..31 of tile 3 read the next row: finite, dropped
+                const float b0 = ok0 ? p0[nt * 8] : 0.f, b1 = ok1 ? p0[4 * kSfCols + nt * 8] : 0.f;
+                uint32_t h0, l0, h1, l1;
+                split_tf32_trunc(b0, h0, l0);
+                split_tf32_trunc(b1, h1, l1);
+                mma_tf32(acc[nt], ah, h0, h1);
+                mma_tf32(acc[nt], ah, l0, l1);
+                mma_tf32(acc[nt], al, h0, h1);
             }
-#pragma unroll
-            for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
-                const bool up = (lane & off) != 0;
-#pragma unroll
-                for (int i = 0; i < n / 2; ++i) {
-                    const float send = up ? acc[i] : acc[i + n / 2];
-                    const float keep = up ? acc[i + n / 2] : acc[i];
-                    acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
-            }
-            const int c = lane >> 3, co = 8 * half + (lane & 7);
-            s.y1[co * kSfCols + 4 * wq + c] = fmaxf(acc[0] + __ldg(wts.b1_pw_b + co) + __ldg(wts.b1_proj_b + co), 0.f);
         }
+        float* part = s.part1 + wq * 512;                   // [16 co][32 columns] per warp
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            *reinterpret_cast<float2*>(part + g * 32 + nt * 8 + 2 * t4) = make_float2(acc[nt][0], acc[nt][1]);
+            *reinterpret_cast<float2*>(part + (g + 8) * 32 + nt * 8 + 2 * t4) = make_float2(acc[nt][2], acc[nt][3]);
+        }
+    }
+    __syncthreads();
+    for (int o = tid; o < 16 * kSfCols; o += kFfThreads) {
+        const int co = o / kSfCols, col = o - co * kSfCols;
+        float a = __ldg(wts.b1_pw_b + co) + __ldg(wts.b1_proj_b + co);
+#pragma unroll
+        for (int w = 0; w < 7; ++w) a += s.part1[w * 512 + co * 32 + col];
+        s.y1[o] = fmaxf(a, 0.f);
     }
     __syncthreads();
     constexpr int F = kSfFrames;
@@ -817,6 +936,7 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
 //   h, c [n_streams][64] in/out state of this layer
 // ------------------------------------------------------------------------------------------
 constexpr int kLsStreams = 8;
+static_assert(kLsStreams % 4 == 0, "the gate loop takes four streams per pass");
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -848,17 +968,27 @@ __global__ void __launch_bounds__(256, 1) k_silero_lstm(const float* __restrict_
             xh[s][j] = (s0 + s < n_streams) ? __ldg(xin + ((int64_t)(s0 + s) * n_frames + t) * 64 + j) : 0.f;
         }
         __syncthreads();
+        // four streams per pass: four independent FMA chains (one accumulator per stream, so the summation order -- and
+        // the result -- is that of the one-stream loop; a single chain ran at the FMA latency, not the FMA rate)
 #pragma unroll 1
-        for (int s = 0; s < kLsStreams; ++s) {
-            float a = bias;
-            const float4* v = reinterpret_cast<const float4*>(xh[s]);
+        for (int s = 0; s < kLsStreams; s += 4) {
+            float a[4] = {bias, bias, bias, bias};
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float4 q = v[j];
-                a = fmaf(w[4 * j], q.x, a); a = fmaf(w[4 * j + 1], q.y, a);
-                a = fmaf(w[4 * j + 2], q.z, a); a = fmaf(w[4 * j + 3], q.w, a);
+                float4 q[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) q[e] = reinterpret_cast<const float4*>(xh[s + e])[j];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a[e] = fmaf(w[4 * j], q[e].x, a[e]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a[e] = fmaf(w[4 * j + 1], q[e].y, a[e]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a[e] = fmaf(w[4 * j + 2], q[e].z, a[e]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a[e] = fmaf(w[4 * j + 3], q[e].w, a[e]);
             }
-            gates[s][g] = a;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) gates[s + e][g] = a[e];
         }
         __syncthreads();
         for (int i = threadIdx.x; i < kLsStreams * 64; i += 256) {
@@ -941,6 +1071,9 @@ __global__ void __launch_bounds__(128) k_vad_compact(const float* __restrict__ p
 struct sb_resampler {
     int fs_in = 0, fs_out = 0, decim = 1, n_taps = 0, fft_in = 0, fft_out = 0;
     float* d_h = nullptr;
+    uint4* d_afrag = nullptr;      // polyphase A fragments, f16 hi | lo: [D][SP][32 lanes][2]
+    int Q = 0, SP = 0;             // taps per branch, k-steps per branch
+    bool tf32_form = false;        // SB_RESAMPLE_TF32=1: the 3xTF32 Toeplitz kernel instead of the f16 polyphase one
 };
 
 struct sb_vad {
@@ -989,6 +1122,38 @@ int sb_resampler_create(int fs_in, int fs_out, sb_resampler** out) {
         for (int x = 0; x < N; ++x) hf[x] = (float)(h[x] / sum);
         SB_CUDA_CHECK(cudaMalloc(&r->d_h, N * sizeof(float)));
         SB_CUDA_CHECK(cudaMemcpy(r->d_h, hf.data(), N * sizeof(float), cudaMemcpyHostToDevice));
+        // polyphase A fragments: A_p[i][j] = 2^12 h[D (Q - 1 + i - j) + p], m16n8k16 layout (a0a1: row g, k 2t..; a2a3: row g + 8;
+        // a4a5: row g, k 2t + 8..; a6a7: row g + 8), split hi = f16(v) | lo = f16(v - hi)
+        const int D = a, Q = (N + D - 1) / D, SP = (Q + 15 + 15) / 16;
+        r->Q = Q; r->SP = SP;
+        auto tap = [&](int p, int i, int j) -> float {
+            const int q = Q - 1 + i - j;
+            if (q < 0 || q >= Q || D * q + p >= N) return 0.0f;
+            return hf[D * q + p] * (float)(1 << sb::kRpScaleLog2);
+        };
+        std::vector<uint32_t> fr((size_t)D * SP * 32 * 8);
+        for (int p = 0; p < D; ++p)
+            for (int sI = 0; sI < SP; ++sI)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int g = lane >> 2, t = lane & 3;
+                    const int rows[4] = {g, g + 8, g, g + 8}, cols[4] = {2 * t, 2 * t, 2 * t + 8, 2 * t + 8};
+                    uint32_t* o = fr.data() + (((size_t)p * SP + sI) * 32 + lane) * 8;
+                    for (int e = 0; e < 4; ++e) {
+                        uint32_t hi2 = 0, lo2 = 0;
+                        for (int w = 0; w < 2; ++w) {
+                            const float v = tap(p, rows[e], 16 * sI + cols[e] + w);
+                            const __half hi = __float2half_rn(v);
+                            const __half lo = __float2half_rn(v - __half2float(hi));
+                            hi2 |= (uint32_t)__half_as_ushort(hi) << (16 * w);
+                            lo2 |= (uint32_t)__half_as_ushort(lo) << (16 * w);
+                        }
+                        o[e] = hi2; o[4 + e] = lo2;
+                    }
+                }
+        SB_CUDA_CHECK(cudaMalloc(&r->d_afrag, fr.size() * sizeof(uint32_t)));
+        SB_CUDA_CHECK(cudaMemcpy(r->d_afrag, fr.data(), fr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        const char* force = getenv("SB_RESAMPLE_TF32");
+        r->tf32_form = force && force[0] == '1';
     }
     *out = r;
     return SB_OK;
@@ -996,7 +1161,7 @@ int sb_resampler_create(int fs_in, int fs_out, sb_resampler** out) {
 
 int sb_resampler_destroy(sb_resampler* r) {
     if (!r) return SB_OK;
-    cudaFree(r->d_h);
+    cudaFree(r->d_h); cudaFree(r->d_afrag);
     delete r;
     return SB_OK;
 }
@@ -1029,8 +1194,18 @@ int sb_resample_dev(const sb_resampler* r, const float* in, int64_t in_stride, s
     }
     if (n_out == 0) return SB_OK;
     const int D = r->decim;
+    if (!r->tf32_form) {
+        const size_t smem = (size_t)4 * D * (sb::kRpTile + 16 * r->SP + 8) * sizeof(__half);
+        SB_CHECK_ARG(smem <= 200 * 1024, "resampler: filter too long for the shared-memory segment");
+        SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_resample_poly, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); });
+        dim3 grid((unsigned)((n_out + sb::kRpTile - 1) / sb::kRpTile), n_streams);
+        sb::k_resample_poly<<<grid, sb::kRpThreads, smem, st>>>(in, in_stride, (int)n_in, out, out_stride, (int)n_out, r->d_afrag, D, r->Q, r->SP);
+        sb::g_launches += 1;
+        SB_CUDA_CHECK(cudaGetLastError());
+        return SB_OK;
+    }
     {
-        // tensor-core Toeplitz form (k_resample_mma)
+        // 3xTF32 Toeplitz form (k_resample_mma)
         const int T = r->n_taps;
         const int Kp = (T + 15 * D + 7) & ~7;
         const size_t smem = (size_t)(((T + 15 * D + Kp + 8 + 3) & ~3) + Kp + 16 * D * (sb::kRmBlocks - 1)) * sizeof(float);
@@ -1094,7 +1269,8 @@ int sb_vad_create(const float* blob, size_t n_floats, sb_vad** out) {
     // delta fragments uint4[16][16][32] | b1_pw_t f32[258][16] | b1_proj_t f32[258][16] | the nine [ci][co] transposes of the
     // later k1 convolutions
     constexpr size_t kOffTw = 1024, kOffTw2 = kOffTw + 2048, kOffDelta = kOffTw2 + 2048, kOffPw = kOffDelta + 16 * 16 * 32 * 16,
-                     kOffProj = kOffPw + 258 * 16 * 4, kOffLate = kOffProj + 258 * 16 * 4, kAuxBytes = kOffLate + 12544 * 4;
+                     kOffProj = kOffPw + 258 * 16 * 4, kOffLate = kOffProj + 258 * 16 * 4, kOffB1Frag = kOffLate + 12544 * 4,
+                     kAuxBytes = kOffB1Frag + 66 * 32 * 32;
     std::vector<unsigned char> aux(kAuxBytes);
     float* a_win = reinterpret_cast<float*>(aux.data());
     double* a_tw = reinterpret_cast<double*>(aux.data() + kOffTw);
@@ -1150,6 +1326,34 @@ int sb_vad_create(const float* blob, size_t n_floats, sb_vad** out) {
                 a_proj[ci * 16 + co] = pj[co * 258 + ci];
             }
     }
+    {
+        // block-1 pointwise weights [16][264 | 264] as m16n8k8 TF32 A fragments, split hi (round to nearest, 10-bit
+        // mantissa) | lo (the remainder, rounded the same way)
+        auto tf32 = [](float x) -> float {
+            uint32_t u;
+            memcpy(&u, &x, 4);
+            u = (u + 0xFFFu + ((u >> 13) & 1u)) & ~0x1FFFu;
+            float r;
+            memcpy(&r, &u, 4);
+            return r;
+        };
+        auto wsrc = [&](int co, int k) -> float {
+            const int ci = k < 264 ? k : k - 264;
+            if (ci >= 258) return 0.f;
+            return k < 264 ? a_pw[ci * 16 + co] : a_proj[ci * 16 + co];
+        };
+        float* fr = reinterpret_cast<float*>(aux.data() + kOffB1Frag);
+        for (int ks = 0; ks < 66; ++ks)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, t = lane & 3;
+                const float w[4] = {wsrc(g, ks * 8 + t), wsrc(g + 8, ks * 8 + t), wsrc(g, ks * 8 + t + 4), wsrc(g + 8, ks * 8 + t + 4)};
+                for (int e = 0; e < 4; ++e) {
+                    const float hi = tf32(w[e]);
+                    fr[(size_t)(ks * 32 + lane) * 8 + e] = hi;
+                    fr[(size_t)(ks * 32 + lane) * 8 + 4 + e] = tf32(w[e] - hi);
+                }
+            }
+    }
     size_t late_off[9];
     {
         static const struct { int idx, cout, cin; } kLate[9] = {{8, 16, 16}, {12, 32, 16}, {14, 32, 16}, {16, 32, 32}, {20, 32, 32},
@@ -1176,6 +1380,7 @@ int sb_vad_create(const float* blob, size_t n_floats, sb_vad** out) {
         d.delta_frag = reinterpret_cast<const uint4*>(base + kOffDelta);
         d.b1_pw_t = reinterpret_cast<const float*>(base + kOffPw);
         d.b1_proj_t = reinterpret_cast<const float*>(base + kOffProj);
+        d.b1_frag = reinterpret_cast<const uint4*>(base + kOffB1Frag);
         const float** slots[9] = {&d.b1_down_t, &d.b2_pw_t, &d.b2_proj_t, &d.b2_down_t, &d.b3_pw_t, &d.b3_down_t, &d.b4_pw_t, &d.b4_proj_t, &d.b4_down_t};
         for (int i = 0; i < 9; ++i) *slots[i] = reinterpret_cast<const float*>(base + late_off[i]);
     }

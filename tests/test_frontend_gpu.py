@@ -42,6 +42,27 @@ def test_resampler_matches_rubato_oracle(cuda_dev):
         audio_toolkit.FrameResampler(44100, 16000)
 
 
+def test_resampler_other_ratios_and_tf32_form(cuda_dev, monkeypatch):
+    """The polyphase f16 kernel at decimation 2, 4 and 6 (32 / 64 / 96 kHz capture devices), and the 3xTF32 Toeplitz
+    form (SB_RESAMPLE_TF32=1) that it replaced, both against the f64 rubato restatement."""
+    for fs in (32000, 64000, 96000):
+        x = np.stack([synth.make_clip(30 + i, seconds=1.5, sr=fs, kind=k) for i, k in enumerate(["vowel", "noise"])])
+        got = audio_toolkit.FrameResampler(fs, 16000).process(x).cpu().numpy()
+        for s_ in range(2):
+            ref = resample.frame_resampler(x[s_], fs, 16000)
+            assert got[s_].shape == ref.shape
+            err = np.abs(got[s_] - ref).max()
+            print(f"resample {fs} -> 16000: max err {err:.2e}")
+            assert err <= RESAMPLE_TOL, (fs, err)
+    x = np.stack([synth.make_clip(33, seconds=2.0, sr=48000, kind="mix")])
+    ref = resample.frame_resampler(x[0])
+    poly = audio_toolkit.FrameResampler(48000, 16000).process(x).cpu().numpy()[0]
+    monkeypatch.setenv("SB_RESAMPLE_TF32", "1")
+    tf32 = audio_toolkit.FrameResampler(48000, 16000).process(x).cpu().numpy()[0]
+    print(f"48000 -> 16000: polyphase f16 {np.abs(poly - ref).max():.2e}, 3xTF32 {np.abs(tf32 - ref).max():.2e}")
+    assert np.abs(poly - ref).max() <= RESAMPLE_TOL and np.abs(tf32 - ref).max() <= RESAMPLE_TOL
+
+
 def test_resampler_properties_full_size(cuda_dev):
     """Size-independent properties at the C5 stream length (30 s @ 48 kHz): linearity, unity DC gain,
     group delay of 171 output samples."""
