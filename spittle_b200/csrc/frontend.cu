@@ -154,23 +154,27 @@ __global__ void __launch_bounds__(256) k_resample_mma(const float* __restrict__ 
 
 // ------------------------------------------------------------------------------------------
 // The decimating FIR as D polyphase branches on the f16 tensor cores (the shipped path; k_resample_mma above is kept as the
-// TF32 reference form and for filters whose taps do not fit f16 after scaling).
+// TF32 reference form, SB_RESAMPLE_TF32=1).
 //   y[m] = sum_u h[u] x[D m - u] = sum_p sum_q h[D q + p] x_p[m - q],   x_p[r] = x[D r - p],  q < Q = ceil(T / D)
 // Each branch is a stride-1 convolution, i.e. a Toeplitz GEMM whose B operand is a sliding window with a column pitch
 // of 16 samples (not 16 D): A_p[i][j] = h_p[Q - 1 + i - j] (16 x (Q + 15), constant), B_p[j][n] = x_p[m0 + 16 n - (Q-1) + j].
 // mma.sync.m16n8k16 f16 with the 3-pass split a_hi b_hi + a_hi b_lo + a_lo b_hi (hi = f16(v), lo = f16(v - hi); the taps
-// are scaled by 2^12 first so that their lo parts stay normal): products carry 22 bits, accumulation is f32 -- measured
-// 6e-8 against the f64 rubato restatement, like the 3xTF32 form, at twice the MACs per instruction and with
-//   * A fragments (hi | lo) pre-arranged on the host: two coalesced 16-byte loads per k-step, shared by 4 column tiles;
-//   * B fragments by ldmatrix.x4 (hi k 0-7, hi k 8-15, lo k 0-7, lo k 8-15) from f16 copies of the branch signals: the
-//     eight windows of a tile start 16 halves = 8 words apart, so columns 4-7 read a second copy stored 4 words further
-//     and the eight 16-byte rows of every 8 x 8 matrix fall into eight different bank groups;
+// are scaled by 2^12 first so that their lo parts stay normal): products carry 22 bits, accumulation is f32 -- 1.7e-6
+// against the f64 rubato restatement (3xTF32 form: 3.1e-6), at twice the MACs per instruction and with
+//   * A fragments (hi | lo) pre-arranged on the host; every lane streams its own 32 bytes per k-step through a private
+//     4-deep cp.async ring (ld.global prefetches four steps ahead did not work: ptxas put them on one scoreboard, so
+//     every step waited for the load issued one step earlier);
+//   * B fragments by ldmatrix.x4 (hi k 0-7, hi k 8-15, lo k 0-7, lo k 8-15) from f16 copies of the branch signals.  The
+//     eight windows of a tile start 16 halves = two 16-byte chunks apart, so rows g and g + 4 would share a bank group;
+//     chunk c is stored at c ^ ((c >> 3) & 1), which moves exactly one of the two by a chunk: conflict-free, one copy;
 //   * no operand splitting in the loop (the TF32 form spent 16 emulated cvt.rna per 6 MMAs: it was issue-bound).
-// CTA = 128 threads = 4 warps x 4 column tiles = 2048 outputs of one stream.
+// CTA = 128 threads = 4 warps x 8 column tiles = 4096 outputs of one stream.
 // ------------------------------------------------------------------------------------------
-constexpr int kRpTile = 2048;
+constexpr int kRpTile = 4096;
 constexpr int kRpThreads = 128;
+constexpr int kRpNT = 8;                 // column tiles per warp
 constexpr int kRpScaleLog2 = 12;
+constexpr int kRpRingBytes = 4 * 4 * 2 * 32 * 16;   // [warp][stage][hi|lo][lane] uint4
 
 __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -178,69 +182,98 @@ __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint4& a, uin
                  : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
 
-// smem: f16 arrays [part hi|lo][copy 0|1][branch p][L], L = kRpTile + 16 SP + 8; copy 1 is stored 8 halves further
+// smem: A ring | f16 arrays [part hi|lo][branch p][L], L a multiple of 64 halves (every array starts on bank 0)
+__host__ __device__ constexpr int rp_array_len(int SP) { return (kRpTile + 16 * SP + 63) & ~63; }
+__device__ __forceinline__ int rp_swz(int chunk) { return chunk ^ ((chunk >> 3) & 1); }
+
+template <int D>
 __global__ void __launch_bounds__(kRpThreads) k_resample_poly(const float* __restrict__ x, int64_t x_stride, int n_in,
                                                              float* __restrict__ y, int64_t y_stride, int n_out,
-                                                             const uint4* __restrict__ afrag, int D, int Q, int SP) {
-    extern __shared__ __align__(16) unsigned char s_rp[];
-    __half* xh = reinterpret_cast<__half*>(s_rp);
-    const int L = kRpTile + 16 * SP + 8;
+                                                             const uint4* __restrict__ afrag, int Q, int SP) {
+    extern __shared__ __align__(128) unsigned char s_rp[];
+    __half* xh = reinterpret_cast<__half*>(s_rp + kRpRingBytes);
+    const int L = rp_array_len(SP);
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const int stream = blockIdx.y;
     const int m0 = blockIdx.x * kRpTile;
     const float* xin = x + (int64_t)stream * x_stride;
-    const int64_t rbase = (int64_t)m0 - (Q - 1);
-    const int npair = (kRpTile + 16 * SP) / 2;
-    for (int i = tid; i < D * npair; i += kRpThreads) {
-        const int p = i / npair, r2 = (i - p * npair) * 2;
-        const int64_t s0 = (int64_t)D * (rbase + r2) - p, s1 = s0 + D;
-        const float v0 = (s0 >= 0 && s0 < n_in) ? __ldg(xin + s0) : 0.0f;
-        const float v1 = (s1 >= 0 && s1 < n_in) ? __ldg(xin + s1) : 0.0f;
-        const __half2 hi = __floats2half2_rn(v0, v1);
-        const float2 hf = __half22float2(hi);
-        const __half2 lo = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-        __half* a = xh + p * L + r2;
-        *reinterpret_cast<__half2*>(a) = hi;
-        *reinterpret_cast<__half2*>(a + D * L + 8) = hi;
-        *reinterpret_cast<__half2*>(a + 2 * D * L) = lo;
-        *reinterpret_cast<__half2*>(a + 3 * D * L + 8) = lo;
-    }
-    __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-    // ldmatrix row of this lane: matrix lane >> 3 = (part, k half), row lane & 7 = column of the tile
-    const int part = lane >> 4, khalf = (lane >> 3) & 1, r = lane & 7, copy = r >> 2;
-    const uint32_t rowbase = (uint32_t)__cvta_generic_to_shared(xh + ((part * 2 + copy) * D) * L + 8 * copy + 16 * (32 * warp + r) + 8 * khalf);
-    float acc[4][4];
+    // A ring: start the first four k-steps before anything else
+    const int n_steps = D * SP;
+    const uint4* ap = afrag + lane * 2;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_rp) + (uint32_t)(warp * 4 * 1024 + lane * 16);
+    auto issue = [&](int step, int slot) {
+        const uint4* src = ap + (size_t)step * 64;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring + slot * 1024), "l"(src));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring + slot * 1024 + 512), "l"(src + 1));
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int u = 0; u < 4; ++u) issue(min(u, n_steps - 1), u);
+    const int rbase = m0 - (Q - 1);
+    const int nload = kRpTile + 16 * SP;
+    // branch signals x_p[r] = x[D r - p]: the 2 D consecutive samples x[D r - D + 1 .. D r + D] give the pair (r, r + 1) of
+    // every branch
+    for (int r2 = 2 * tid; r2 < nload; r2 += 2 * kRpThreads) {
+        const int s0 = D * (rbase + r2);                                   // D n_out < 2^31: sb_resample_dev checks
+        float v[2 * D];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
-    for (int p = 0; p < D; ++p) {
-        const uint4* ap = afrag + ((size_t)p * SP * 32 + lane) * 2;
-        const uint32_t bp = rowbase + (uint32_t)(p * L * 2);
-#pragma unroll 2
-        for (int sI = 0; sI < SP; ++sI) {
-            const uint4 ah = __ldg(ap + sI * 64), al = __ldg(ap + sI * 64 + 1);
+        for (int e = 0; e < 2 * D; ++e) {
+            const int si = s0 - (D - 1) + e;
+            v[e] = (unsigned)si < (unsigned)n_in ? __ldg(xin + si) : 0.0f;
+        }
+        const int off = (rp_swz(r2 >> 3) << 3) | (r2 & 7);
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                uint32_t b[4];
-                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(bp + nt * 256 + sI * 32));
-                mma_f16_16816(acc[nt], ah, b[0], b[1]);
-                mma_f16_16816(acc[nt], ah, b[2], b[3]);
-                mma_f16_16816(acc[nt], al, b[0], b[1]);
-            }
+        for (int p = 0; p < D; ++p) {
+            const float v0 = v[D - 1 - p], v1 = v[2 * D - 1 - p];          // x[D r - p], x[D (r + 1) - p]
+            const __half2 hi = __floats2half2_rn(v0, v1);
+            const float2 hf = __half22float2(hi);
+            const __half2 lo = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+            *reinterpret_cast<__half2*>(xh + p * L + off) = hi;
+            *reinterpret_cast<__half2*>(xh + (D + p) * L + off) = lo;
         }
     }
+    __syncthreads();
+    // ldmatrix row of this lane: matrix lane >> 3 = (part, k half), row lane & 7 = column of the tile.  Chunk (16 bytes)
+    // of the row at k-step s, tile nt: cb + 2 s + 16 nt, swizzled (the swizzle bit does not depend on nt)
+    const int part = lane >> 4, khalf = (lane >> 3) & 1, r = lane & 7;
+    const int cb = 2 * (8 * kRpNT * warp + r) + khalf;
+    uint32_t bbase = (uint32_t)__cvta_generic_to_shared(xh + (part * D) * L);
+    float acc[kRpNT][4];
+#pragma unroll
+    for (int nt = 0; nt < kRpNT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+    int sI = 0;
+    for (int it = 0; it < n_steps; ++it) {
+        asm volatile("cp.async.wait_group 3;" ::: "memory");
+        const int slot = it & 3;
+        uint4 ah, al;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ah.x), "=r"(ah.y), "=r"(ah.z), "=r"(ah.w) : "r"(ring + slot * 1024));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(al.x), "=r"(al.y), "=r"(al.z), "=r"(al.w) : "r"(ring + slot * 1024 + 512));
+        const uint32_t baddr = bbase + ((uint32_t)rp_swz(cb + 2 * sI) << 4);
+#pragma unroll
+        for (int nt = 0; nt < kRpNT; ++nt) {
+            uint32_t bq[4];
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(bq[0]), "=r"(bq[1]), "=r"(bq[2]), "=r"(bq[3]) : "r"(baddr + nt * 256));
+            mma_f16_16816(acc[nt], ah, bq[0], bq[1]);
+            mma_f16_16816(acc[nt], ah, bq[2], bq[3]);
+            mma_f16_16816(acc[nt], al, bq[0], bq[1]);
+        }
+        issue(min(it + 4, n_steps - 1), slot);           // the slot's fragments are in registers (and consumed)
+        if (++sI == SP) { sI = 0; bbase += (uint32_t)(L * 2); }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // C[i][n]: c0 (g, 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)  ->  output m0 + 16 n + i
     float* yo = y + (int64_t)stream * y_stride;
     const int g = lane >> 2, t = lane & 3;
     constexpr float kInv = 1.0f / (float)(1 << kRpScaleLog2);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < kRpNT; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const int n = 8 * (4 * warp + nt) + 2 * t + (e & 1);
+            const int n = 8 * (kRpNT * warp + nt) + 2 * t + (e & 1);
             const int m = m0 + 16 * n + g + ((e >> 1) << 3);
             if (m < n_out) yo[m] = acc[nt][e] * kInv;
         }
@@ -1195,11 +1228,24 @@ int sb_resample_dev(const sb_resampler* r, const float* in, int64_t in_stride, s
     if (n_out == 0) return SB_OK;
     const int D = r->decim;
     if (!r->tf32_form) {
-        const size_t smem = (size_t)4 * D * (sb::kRpTile + 16 * r->SP + 8) * sizeof(__half);
+        const size_t smem = sb::kRpRingBytes + (size_t)2 * D * sb::rp_array_len(r->SP) * sizeof(__half);
+        SB_CHECK_ARG((uint64_t)D * (n_out + sb::kRpTile + 16 * r->SP) < (1ull << 31), "resampler: stream too long for 32-bit sample indices");
         SB_CHECK_ARG(smem <= 200 * 1024, "resampler: filter too long for the shared-memory segment");
-        SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_resample_poly, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); });
+        SB_ONCE_PER_DEVICE({
+            SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_resample_poly<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_resample_poly<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_resample_poly<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_resample_poly<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        });
         dim3 grid((unsigned)((n_out + sb::kRpTile - 1) / sb::kRpTile), n_streams);
-        sb::k_resample_poly<<<grid, sb::kRpThreads, smem, st>>>(in, in_stride, (int)n_in, out, out_stride, (int)n_out, r->d_afrag, D, r->Q, r->SP);
+#define SB_RP_LAUNCH(DD) sb::k_resample_poly<DD><<<grid, sb::kRpThreads, smem, st>>>(in, in_stride, (int)n_in, out, out_stride, (int)n_out, r->d_afrag, r->Q, r->SP)
+        switch (D) {
+            case 2: SB_RP_LAUNCH(2); break;
+            case 3: SB_RP_LAUNCH(3); break;
+            case 4: SB_RP_LAUNCH(4); break;
+            default: SB_RP_LAUNCH(6); break;     // sb_resampler_create admits 2, 3, 4, 6 only
+        }
+#undef SB_RP_LAUNCH
         sb::g_launches += 1;
         SB_CUDA_CHECK(cudaGetLastError());
         return SB_OK;
