@@ -963,15 +963,24 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
 }
 
 // ------------------------------------------------------------------------------------------
-// LSTM layer (ONNX gate order i, o, f, c).  CTA = 256 threads (one gate row each, its 128 weights
-// in registers for the whole sequence) x kLsStreams streams processed in lock step.
+// LSTM layer (ONNX gate order i, o, f, c) on the f16 tensor cores.  Per time step the 256 gate pre-activations of the
+// CTA's 8 streams are one [256 x 128] x [128 x 8] product: A = [W | R] (constant: each warp keeps its two 16-row tiles
+// as m16n8k16 fragments in registers for the whole sequence, split hi = f16(256 w) | lo = f16(256 w - hi)), B = [x_t ;
+// h_{t-1}] of the 8 streams, kept in shared memory as f16 hi | lo (22 bits) and read with ldmatrix; three MMAs per
+// product (hi hi + hi lo + lo hi), f32 accumulation.  The CUDA-core form spent 1024 FMAs per thread and step on this.
 //   xin  [n_streams][n_frames][64]   hout [n_streams][n_frames][64] (layer 1) or probs (layer 2)
 //   h, c [n_streams][64] in/out state of this layer
 // ------------------------------------------------------------------------------------------
 constexpr int kLsStreams = 8;
-static_assert(kLsStreams % 4 == 0, "the gate loop takes four streams per pass");
+constexpr int kLsPitch = 136;            // halves per stream row of [x ; h]: 17 16-byte chunks, conflict-free for ldmatrix
+constexpr int kLsGPitch = 260;           // floats per stream row of the gate buffer (4 mod 32: conflict-free fragment stores)
+constexpr float kLsWScale = 256.0f;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
 
 template <bool LAST>
 __global__ void __launch_bounds__(256, 1) k_silero_lstm(const float* __restrict__ xin, int n_streams, int n_frames,
@@ -980,72 +989,123 @@ __global__ void __launch_bounds__(256, 1) k_silero_lstm(const float* __restrict_
                                                         float* __restrict__ c_state, float* __restrict__ hout,
                                                         const float* __restrict__ dec_w, const float* __restrict__ dec_b,
                                                         float* __restrict__ probs) {
-    __shared__ __align__(16) float xh[kLsStreams][128];
-    __shared__ float gates[kLsStreams][256];
+    __shared__ __align__(16) __half xh[2][kLsStreams][kLsPitch];   // [hi | lo][stream][x_t (64) ; h_{t-1} (64)]
+    __shared__ float gates[kLsStreams][kLsGPitch];
     __shared__ float cst[kLsStreams][64];
-    const int g = threadIdx.x;
+    __shared__ float hf[kLsStreams][64];                           // h_t in f32 (state out, decoder)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int s0 = blockIdx.x * kLsStreams;
-    float w[128];
+    // A fragments of the warp's row tiles 2 warp, 2 warp + 1: a0a1 (row g, k 2t..), a2a3 (row g + 8), a4a5 (row g, k 2t + 8..),
+    // a6a7 (row g + 8, k 2t + 8..)
+    uint4 ah[2][8], al[2][8];
+    float bias[2][2];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) { w[j] = __ldg(W + g * 64 + j); w[64 + j] = __ldg(R + g * 64 + j); }
-    const float bias = __ldg(B + g) + __ldg(B + 256 + g);
-    for (int i = threadIdx.x; i < kLsStreams * 64; i += 256) {
-        const int s = i >> 6, j = i & 63;
-        const bool ok = s0 + s < n_streams;
-        xh[s][64 + j] = ok ? h_state[(int64_t)(s0 + s) * 64 + j] : 0.f;
-        cst[s][j] = ok ? c_state[(int64_t)(s0 + s) * 64 + j] : 0.f;
-    }
-    for (int t = 0; t < n_frames; ++t) {
-        for (int i = threadIdx.x; i < kLsStreams * 64; i += 256) {
-            const int s = i >> 6, j = i & 63;
-            xh[s][j] = (s0 + s < n_streams) ? __ldg(xin + ((int64_t)(s0 + s) * n_frames + t) * 64 + j) : 0.f;
-        }
-        __syncthreads();
-        // four streams per pass: four independent FMA chains (one accumulator per stream, so the summation order -- and
-        // the result -- is that of the one-stream loop; a single chain ran at the FMA latency, not the FMA rate)
-#pragma unroll 1
-        for (int s = 0; s < kLsStreams; s += 4) {
-            float a[4] = {bias, bias, bias, bias};
+    for (int mt = 0; mt < 2; ++mt) {
+        const int row0 = 32 * warp + 16 * mt + g;
+        bias[mt][0] = __ldg(B + row0) + __ldg(B + 256 + row0);
+        bias[mt][1] = __ldg(B + row0 + 8) + __ldg(B + 256 + row0 + 8);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float4 q[4];
+        for (int ks = 0; ks < 8; ++ks) {
+            uint32_t h4[4], l4[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) q[e] = reinterpret_cast<const float4*>(xh[s + e])[j];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) a[e] = fmaf(w[4 * j], q[e].x, a[e]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) a[e] = fmaf(w[4 * j + 1], q[e].y, a[e]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) a[e] = fmaf(w[4 * j + 2], q[e].z, a[e]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) a[e] = fmaf(w[4 * j + 3], q[e].w, a[e]);
+            for (int e = 0; e < 4; ++e) {
+                const int row = row0 + 8 * (e & 1), k = 16 * ks + 2 * t4 + 8 * (e >> 1);
+                const float* src = k < 64 ? W + row * 64 + k : R + row * 64 + (k - 64);
+                __half h0, l0, h1, l1;
+                split_f16(__ldg(src) * kLsWScale, h0, l0);
+                split_f16(__ldg(src + 1) * kLsWScale, h1, l1);
+                h4[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                l4[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
             }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) gates[s + e][g] = a[e];
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < kLsStreams * 64; i += 256) {
-            const int s = i >> 6, j = i & 63;
-            const float ig = sigmoidf_(gates[s][j]), og = sigmoidf_(gates[s][64 + j]);
-            const float fg = sigmoidf_(gates[s][128 + j]), cg = tanhf(gates[s][192 + j]);
-            const float c = fg * cst[s][j] + ig * cg;
-            const float h = og * tanhf(c);
-            cst[s][j] = c;
-            xh[s][64 + j] = h;
-            if (!LAST && s0 + s < n_streams) hout[((int64_t)(s0 + s) * n_frames + t) * 64 + j] = h;
-        }
-        __syncthreads();
-        if (LAST && threadIdx.x < kLsStreams && s0 + threadIdx.x < n_streams) {
-            const int s = threadIdx.x;
-            float a = __ldg(dec_b);
-            for (int j = 0; j < 64; ++j) a = fmaf(__ldg(dec_w + j), fmaxf(xh[s][64 + j], 0.f), a);
-            probs[(int64_t)(s0 + s) * n_frames + t] = sigmoidf_(a);
+            ah[mt][ks] = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+            al[mt][ks] = make_uint4(l4[0], l4[1], l4[2], l4[3]);
         }
     }
+    // element pairs (stream, 2 j): 256 threads x one pair of the 8 x 64 tile
+    const int es = tid >> 5, ej = (tid & 31) * 2;
+    const bool s_ok = s0 + es < n_streams;
+    auto put = [&](int col, float v0, float v1) {
+        const __half2 hi = __floats2half2_rn(v0, v1);
+        const float2 f = __half22float2(hi);
+        *reinterpret_cast<__half2*>(&xh[0][es][col]) = hi;
+        *reinterpret_cast<__half2*>(&xh[1][es][col]) = __floats2half2_rn(v0 - f.x, v1 - f.y);
+    };
+    {
+        float2 h0 = make_float2(0.f, 0.f), c0 = h0;
+        if (s_ok) {
+            h0 = *reinterpret_cast<const float2*>(h_state + (int64_t)(s0 + es) * 64 + ej);
+            c0 = *reinterpret_cast<const float2*>(c_state + (int64_t)(s0 + es) * 64 + ej);
+        }
+        put(64 + ej, h0.x, h0.y);
+        hf[es][ej] = h0.x; hf[es][ej + 1] = h0.y;
+        cst[es][ej] = c0.x; cst[es][ej + 1] = c0.y;
+    }
+    const float* xrow = xin + (int64_t)(s0 + es) * n_frames * 64 + ej;
+    float2 xn = s_ok ? __ldg(reinterpret_cast<const float2*>(xrow)) : make_float2(0.f, 0.f);
+    put(ej, xn.x, xn.y);
+    // ldmatrix row of this lane: matrix lane >> 3 = (hi | lo, k half), row lane & 7 = stream
+    const uint32_t brow = (uint32_t)__cvta_generic_to_shared(&xh[lane >> 4][lane & 7][8 * ((lane >> 3) & 1)]);
+    const float db = LAST ? __ldg(dec_b) : 0.f;
+    const float dw0 = LAST ? __ldg(dec_w + ej) : 0.f, dw1 = LAST ? __ldg(dec_w + ej + 1) : 0.f;
     __syncthreads();
-    for (int i = threadIdx.x; i < kLsStreams * 64; i += 256) {
-        const int s = i >> 6, j = i & 63;
-        if (s0 + s < n_streams) { h_state[(int64_t)(s0 + s) * 64 + j] = xh[s][64 + j]; c_state[(int64_t)(s0 + s) * 64 + j] = cst[s][j]; }
+    for (int t = 0; t < n_frames; ++t) {
+        // next step's input: in flight during this step's product
+        if (t + 1 < n_frames && s_ok) xn = __ldg(reinterpret_cast<const float2*>(xrow + (int64_t)(t + 1) * 64));
+        float acc[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) { acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            uint32_t b[4];
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(brow + ks * 32));
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                mma_f16_16816(acc[mt], ah[mt][ks], b[0], b[1]);
+                mma_f16_16816(acc[mt], ah[mt][ks], b[2], b[3]);
+                mma_f16_16816(acc[mt], al[mt][ks], b[0], b[1]);
+            }
+        }
+        // C fragment: c0 c1 (row g, streams 2 t4, 2 t4 + 1), c2 c3 (row g + 8)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int row = 32 * warp + 16 * mt + g;
+            gates[2 * t4][row] = fmaf(acc[mt][0], 1.0f / kLsWScale, bias[mt][0]);
+            gates[2 * t4 + 1][row] = fmaf(acc[mt][1], 1.0f / kLsWScale, bias[mt][0]);
+            gates[2 * t4][row + 8] = fmaf(acc[mt][2], 1.0f / kLsWScale, bias[mt][1]);
+            gates[2 * t4 + 1][row + 8] = fmaf(acc[mt][3], 1.0f / kLsWScale, bias[mt][1]);
+        }
+        __syncthreads();
+        {
+            float hv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = ej + e;
+                const float ig = sigmoidf_(gates[es][j]), og = sigmoidf_(gates[es][64 + j]);
+                const float fg = sigmoidf_(gates[es][128 + j]), cg = tanhf(gates[es][192 + j]);
+                const float c = fg * cst[es][j] + ig * cg;
+                cst[es][j] = c;
+                hv[e] = og * tanhf(c);
+            }
+            put(64 + ej, hv[0], hv[1]);
+            put(ej, xn.x, xn.y);
+            if (!LAST) {
+                if (s_ok) *reinterpret_cast<float2*>(hout + ((int64_t)(s0 + es) * n_frames + t) * 64 + ej) = make_float2(hv[0], hv[1]);
+                if (t + 1 == n_frames) { hf[es][ej] = hv[0]; hf[es][ej + 1] = hv[1]; }
+            } else {
+                hf[es][ej] = hv[0]; hf[es][ej + 1] = hv[1];
+                // decoder: warp = stream (es == warp), lane = the two units it just produced
+                float a = fmaf(dw0, fmaxf(hv[0], 0.f), dw1 * fmaxf(hv[1], 0.f));
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0 && s_ok) probs[(int64_t)(s0 + es) * n_frames + t] = sigmoidf_(a + db);
+            }
+        }
+        __syncthreads();
+    }
+    if (s_ok) {
+        *reinterpret_cast<float2*>(h_state + (int64_t)(s0 + es) * 64 + ej) = make_float2(hf[es][ej], hf[es][ej + 1]);
+        *reinterpret_cast<float2*>(c_state + (int64_t)(s0 + es) * 64 + ej) = make_float2(cst[es][ej], cst[es][ej + 1]);
     }
 }
 
