@@ -325,6 +325,22 @@ __device__ void dw5_relu(const float* in, float* out, const float* w, const floa
         out[i] = fmaxf(a, 0.f);
     }
 }
+// the same for tiles of F frames
+template <int F>
+__device__ __forceinline__ void dw5_relu_f(const float* in, float* out, const float* __restrict__ w, const float* __restrict__ b, int C, int T) {
+    const int total = C * F * T;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int c = i / (F * T), rem = i - c * F * T;
+        const int t = rem % T;
+        float a = __ldg(b + c);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int tt = t + k - 2;
+            if (tt >= 0 && tt < T) a = fmaf(__ldg(w + c * 5 + k), in[i + k - 2], a);
+        }
+        out[i] = fmaxf(a, 0.f);
+    }
+}
 // pointwise: out[co][f][t] = relu( W1[co,:] . in1[:,f,t] + b1 (+ W2[co,:] . in2[:,f,t] + b2) (+ res[co][f][t]) )
 __device__ void pw_relu(const float* in1, const float* w1, const float* b1, const float* in2, const float* w2,
                         const float* b2, const float* res, float* out, int Cin, int Cout, int T) {
@@ -531,7 +547,7 @@ __global__ void __launch_bounds__(kSfThreads, 3) k_silero_features_direct(const 
 // out[co][p] = relu(b1[co] + sum_ci w1t[ci][co] in1[ci][off(p)] (+ b2[co] + sum_ci w2t[ci][co] in2[ci][off(p)]) (+ res[co][p])):
 // the pointwise and the strided k1 convolutions of blocks 1-4 on [C][frames x T] tiles.  Weights are transposed to
 // [ci][co] (sb_vad_create) and co is the fastest thread index, so one warp-wide weight load is one contiguous row; the
-// activation is a shared-memory broadcast; PPT outputs per thread share the weight.  Every stage is a single round.
+// activation is a shared-memory broadcast; PPT outputs per thread share the weight.
 template <int CIN, int COUT, int P, int PPT, bool TWO, bool RES, typename Off>
 __device__ __forceinline__ void mix_relu(const float* __restrict__ in1, const float* __restrict__ w1t, const float* __restrict__ b1,
                                          const float* __restrict__ in2, const float* __restrict__ w2t, const float* __restrict__ b2,
@@ -542,16 +558,16 @@ __device__ __forceinline__ void mix_relu(const float* __restrict__ in1, const fl
         const int co = item % COUT, pg = item / COUT;
         int o[PPT];
         float a[PPT];
-        const float bias = TWO ? __ldg(b1 + co) + __ldg(b2 + co) : __ldg(b1 + co);
+        const float bias = TWO ? b1[co] + b2[co] : b1[co];
 #pragma unroll
         for (int e = 0; e < PPT; ++e) { o[e] = off(pg + PG * e); a[e] = bias; }
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
-            const float w = __ldg(w1t + ci * COUT + co);
+            const float w = w1t[ci * COUT + co];
 #pragma unroll
             for (int e = 0; e < PPT; ++e) a[e] = fmaf(w, in1[ci * in_stride + o[e]], a[e]);
             if (TWO) {
-                const float w2 = __ldg(w2t + ci * COUT + co);
+                const float w2 = w2t[ci * COUT + co];
 #pragma unroll
                 for (int e = 0; e < PPT; ++e) a[e] = fmaf(w2, in2[ci * in_stride + o[e]], a[e]);
             }
@@ -562,6 +578,50 @@ __device__ __forceinline__ void mix_relu(const float* __restrict__ in1, const fl
             float v = a[e];
             if (RES) v += res[co * P + pp];
             out[co * P + pp] = fmaxf(v, 0.f);
+        }
+    }
+}
+
+// the same with the identity position map: PPT consecutive positions per thread, read as float4 broadcasts
+template <int CIN, int COUT, int P, int PPT, bool TWO, bool RES>
+__device__ __forceinline__ void mix4_relu(const float* __restrict__ in1, const float* __restrict__ w1t, const float* __restrict__ b1,
+                                          const float* __restrict__ in2, const float* __restrict__ w2t, const float* __restrict__ b2,
+                                          const float* __restrict__ res, float* __restrict__ out) {
+    static_assert(PPT % 4 == 0 && P % PPT == 0, "PPT a multiple of 4 dividing P");
+    for (int item = threadIdx.x; item < COUT * (P / PPT); item += blockDim.x) {
+        const int co = item % COUT, p0 = (item / COUT) * PPT;
+        float a[PPT];
+        const float bias = TWO ? b1[co] + b2[co] : b1[co];
+#pragma unroll
+        for (int e = 0; e < PPT; ++e) a[e] = bias;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float w = w1t[ci * COUT + co];
+#pragma unroll
+            for (int q = 0; q < PPT / 4; ++q) {
+                const float4 v = *reinterpret_cast<const float4*>(in1 + ci * P + p0 + 4 * q);
+                a[4 * q] = fmaf(w, v.x, a[4 * q]); a[4 * q + 1] = fmaf(w, v.y, a[4 * q + 1]);
+                a[4 * q + 2] = fmaf(w, v.z, a[4 * q + 2]); a[4 * q + 3] = fmaf(w, v.w, a[4 * q + 3]);
+            }
+            if (TWO) {
+                const float w2 = w2t[ci * COUT + co];
+#pragma unroll
+                for (int q = 0; q < PPT / 4; ++q) {
+                    const float4 v = *reinterpret_cast<const float4*>(in2 + ci * P + p0 + 4 * q);
+                    a[4 * q] = fmaf(w2, v.x, a[4 * q]); a[4 * q + 1] = fmaf(w2, v.y, a[4 * q + 1]);
+                    a[4 * q + 2] = fmaf(w2, v.z, a[4 * q + 2]); a[4 * q + 3] = fmaf(w2, v.w, a[4 * q + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < PPT / 4; ++q) {
+            float4 v = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+            if (RES) {
+                const float4 r = *reinterpret_cast<const float4*>(res + co * P + p0 + 4 * q);
+                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            }
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            *reinterpret_cast<float4*>(out + co * P + p0 + 4 * q) = v;
         }
     }
 }
@@ -628,6 +688,7 @@ constexpr int kFfThreads = kFfFfts * 8;      // 224
 constexpr int kFfZRow = 9;                   // double2 row stride of the 16 x 8 exchange
 constexpr int kFfZFft = 16 * kFfZRow;        // double2 per FFT
 
+constexpr int kFfR1Pitch = 24;
 constexpr int kFfXbFrame = kSfPadLen + 8;     // bf16 frame stride: 340 words = 20 mod 32
 constexpr int kFfXbCopy = kSfFrames * kFfXbFrame;   // second copy starts 1360 words = 16 mod 32 further: see the delta term
 
@@ -650,12 +711,13 @@ struct SileroFftSmem {
         __nv_bfloat16 xb[2 * kFfXbCopy];       // two bf16 copies of the frames (B operand of the delta term), then ...
         double2 z[kFfFfts * kFfZFft];          // ... the FFT exchange, then ...
         struct {
-            float r1[258 * kSfCols + 8];       // ... the depthwise output of block 1 (+ 8: tile 3 reads past the last row)
-            float part1[7 * 512];              //     and the seven partial tiles of its pointwise product
+            float r1[258 * kFfR1Pitch];        // ... the depthwise output of block 1 at the even STFT columns (the only ones
+                                               //     the stride-2 convolution behind it reads), row pitch 24: conflict-free B loads
+            float part1[7 * 256];              //     and the seven partial tiles of its pointwise product
         };
     };
     float x1[258 * kSfCols];              // [258][frames][7]: re | im, then magnitude | log spectrum, then magnitude | norm
-    float y1[16 * kSfCols];
+    float y1[16 * kSfFrames * 4];
     float part[8 * kSfCols];
     float mm[kSfFrames];
 };
@@ -669,7 +731,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint4& a, ui
 }
 
 __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const float* __restrict__ pcm, int64_t pcm_stride, int n_frames,
-                                                                    float* __restrict__ out, SileroDev wts) {
+                                                                    float* __restrict__ y2g, SileroDev wts) {
     extern __shared__ __align__(16) unsigned char smem_raw_f[];
     SileroFftSmem& s = *reinterpret_cast<SileroFftSmem*>(smem_raw_f);
     const int tid = threadIdx.x;
@@ -864,39 +926,45 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
 #pragma unroll
         for (int k = 0; k < 5; ++k) w[k] = __ldg(wts.b1_dw_w + c * 5 + k);
         const float b = __ldg(wts.b1_dw_b + c);
+        float o[4];
 #pragma unroll
-        for (int t = 0; t < 7; ++t) {
+        for (int j = 0; j < 4; ++j) {                    // t = 2 j: the stride-2 k1 convolution after the pointwise one reads no other
             float a = b;
 #pragma unroll
-            for (int k = 0; k < 5; ++k) a = fmaf(w[k], v[t + k], a);
-            s.r1[item * 7 + t] = fmaxf(a, 0.f);
+            for (int k = 0; k < 5; ++k) a = fmaf(w[k], v[2 * j + k], a);
+            o[j] = fmaxf(a, 0.f);
         }
+        *reinterpret_cast<float4*>(s.r1 + c * kFfR1Pitch + f * 4) = make_float4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();
     {
-        // pointwise 2 x (258 -> 16) on 28 columns = one [16 x 528] x [528 x 32] product on the tensor cores: K = the 258
-        // depthwise outputs (padded to 264) | the 258 block inputs (padded to 264), 66 k-steps of mma.m16n8k8 TF32 with the
-        // 3-pass split (weights pre-split and pre-arranged as A fragments on the host, activations split here): f32-level
-        // products, f32 accumulation.  Warp w takes the k-steps w, w + 7, ...; the seven partial tiles are summed through
-        // the free tail of the exchange buffer in a fixed order.
+        // pointwise 2 x (258 -> 16) at the 16 even STFT columns (4 frames x t = 0, 2, 4, 6; the stride-2 convolution that
+        // follows reads no others) = one [16 x 528] x [528 x 16] product on the tensor cores: K = the 258 depthwise outputs
+        // (padded to 264) | the 258 block inputs (padded to 264), 66 k-steps of mma.m16n8k8 TF32 with the 3-pass split
+        // (weights pre-split and pre-arranged as A fragments on the host, activations split here): f32-level products, f32
+        // accumulation.  Warp w takes the k-steps w, w + 7, ...; the seven partial tiles are summed in a fixed order.
         const int wq = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-        float acc[4][4];
+        float acc[2][4];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+        // MMA column n = frame * 4 + j: r1 holds it at n, x1 at frame * 7 + 2 j
+        int xcol[2];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) { const int n = nt * 8 + g; xcol[nt] = (n >> 2) * 7 + (n & 3) * 2; }
 #pragma unroll 2
         for (int ks = wq; ks < 66; ks += 7) {
             const uint4 ahv = __ldg(wts.b1_frag + (ks * 32 + lane) * 2), alv = __ldg(wts.b1_frag + (ks * 32 + lane) * 2 + 1);
             const uint32_t ah[4] = {ahv.x, ahv.y, ahv.z, ahv.w}, al[4] = {alv.x, alv.y, alv.z, alv.w};
             const bool second = ks >= 33;
-            const float* srcp = second ? s.x1 : s.r1;
             const int c0 = (second ? ks - 33 : ks) * 8 + t4;           // input channel of b0; b1 is c0 + 4
             const bool ok0 = c0 < 258, ok1 = c0 + 4 < 258;              // the padding rows: zero weights, but the operand must be finite
-            const float* p0 = srcp + c0 * kSfCols + g;
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {                           // columns 28..31 of tile 3 read the next row: finite, dropped
-                const float b0 = ok0 ? p0[nt * 8] : 0.f, b1 = ok1 ? p0[4 * kSfCols + nt * 8] : 0.f;
+            for (int nt = 0; nt < 2; ++nt) {
+                const float* p0 = second ? s.x1 + c0 * kSfCols + xcol[nt] : s.r1 + c0 * kFfR1Pitch + nt * 8 + g;
+                const int rs = second ? 4 * kSfCols : 4 * kFfR1Pitch;
+                const float b0 = ok0 ? p0[0] : 0.f, b1 = ok1 ? p0[rs] : 0.f;
                 uint32_t h0, l0, h1, l1;
                 split_tf32_trunc(b0, h0, l0);
                 split_tf32_trunc(b1, h1, l1);
@@ -905,60 +973,140 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
                 mma_tf32(acc[nt], al, h0, h1);
             }
         }
-        float* part = s.part1 + wq * 512;                   // [16 co][32 columns] per warp
+        float* part = s.part1 + wq * 256;                              // [16 co][16 columns] per warp
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            *reinterpret_cast<float2*>(part + g * 32 + nt * 8 + 2 * t4) = make_float2(acc[nt][0], acc[nt][1]);
-            *reinterpret_cast<float2*>(part + (g + 8) * 32 + nt * 8 + 2 * t4) = make_float2(acc[nt][2], acc[nt][3]);
+        for (int nt = 0; nt < 2; ++nt) {
+            *reinterpret_cast<float2*>(part + g * 16 + nt * 8 + 2 * t4) = make_float2(acc[nt][0], acc[nt][1]);
+            *reinterpret_cast<float2*>(part + (g + 8) * 16 + nt * 8 + 2 * t4) = make_float2(acc[nt][2], acc[nt][3]);
         }
     }
     __syncthreads();
-    for (int o = tid; o < 16 * kSfCols; o += kFfThreads) {
-        const int co = o / kSfCols, col = o - co * kSfCols;
+    for (int o = tid; o < 16 * 16; o += kFfThreads) {
+        const int co = o >> 4;
         float a = __ldg(wts.b1_pw_b + co) + __ldg(wts.b1_proj_b + co);
 #pragma unroll
-        for (int w = 0; w < 7; ++w) a += s.part1[w * 512 + co * 32 + col];
+        for (int w = 0; w < 7; ++w) a += s.part1[w * 256 + o];
         s.y1[o] = fmaxf(a, 0.f);
     }
     __syncthreads();
     constexpr int F = kSfFrames;
-    auto ident = [](int p) { return p; };
-    mix_relu<16, 16, F * 4, 2, false, false>(s.y1, wts.b1_down_t, wts.b1_down_b, nullptr, nullptr, nullptr, nullptr, s.y2, F * 7,
-                                             [](int p) { return (p >> 2) * 7 + (p & 3) * 2; });              // T 7 -> 4
+    mix_relu<16, 16, F * 4, 2, false, false>(s.y1, wts.b1_down_t, wts.b1_down_b, nullptr, nullptr, nullptr, nullptr, s.y2, F * 4,
+                                             [](int p) { return p; });                                       // T 7 -> 4, already decimated
     __syncthreads();
-    // block 2 (16 -> 32, T 4 -> 2)
-    dw5_relu(s.y2, s.r2, wts.b2_dw_w, wts.b2_dw_b, 16, 4);
-    __syncthreads();
-    mix_relu<16, 32, F * 4, 4, true, false>(s.r2, wts.b2_pw_t, wts.b2_pw_b, s.y2, wts.b2_proj_t, wts.b2_proj_b, nullptr, s.z1, F * 4, ident);
-    __syncthreads();
-    mix_relu<32, 32, F * 2, 2, false, false>(s.z1, wts.b2_down_t, wts.b2_down_b, nullptr, nullptr, nullptr, nullptr, s.z2, F * 4,
-                                             [](int p) { return (p >> 1) * 4 + (p & 1) * 2; });              // T 4 -> 2
-    __syncthreads();
-    // block 3 (32 -> 32 with identity residual, T 2 -> 1)
-    dw5_relu(s.z2, s.r3, wts.b3_dw_w, wts.b3_dw_b, 32, 2);
-    __syncthreads();
-    mix_relu<32, 32, F * 2, 2, false, true>(s.r3, wts.b3_pw_t, wts.b3_pw_b, nullptr, nullptr, nullptr, s.z2, s.u1, F * 2, ident);
-    __syncthreads();
-    mix_relu<32, 32, F, 2, false, false>(s.u1, wts.b3_down_t, wts.b3_down_b, nullptr, nullptr, nullptr, nullptr, s.u2, F * 2,
-                                         [](int p) { return p * 2; });                                       // T 2 -> 1
-    __syncthreads();
-    // block 4 (32 -> 64, T 1)
-    dw5_relu(s.u2, s.r4, wts.b4_dw_w, wts.b4_dw_b, 32, 1);
-    __syncthreads();
-    mix_relu<32, 64, F, 2, true, false>(s.r4, wts.b4_pw_t, wts.b4_pw_b, s.u2, wts.b4_proj_t, wts.b4_proj_b, nullptr, s.v1, F, ident);
-    __syncthreads();
-    // final 64 -> 64, ReLU, write [frame][64]: two frames per thread
-    if (tid < 128) {
-        const int co = tid & 63, fp = tid >> 6;          // frames fp and fp + 2
-        float a0 = __ldg(wts.b4_down_b + co), a1 = a0;
-#pragma unroll
-        for (int ci = 0; ci < 64; ++ci) {
-            const float w = __ldg(wts.b4_down_t + ci * 64 + co);
-            a0 = fmaf(w, s.v1[ci * F + fp], a0);
-            a1 = fmaf(w, s.v1[ci * F + fp + 2], a1);
+    // block-1 output [frame][16][4] for k_silero_blocks
+    for (int i = tid; i < F * 64; i += kFfThreads) {
+        const int f = i >> 6, ch = (i >> 2) & 15, t = i & 3;
+        if (f0 + f < n_frames) y2g[((int64_t)stream * n_frames + f0 + f) * 64 + (i & 63)] = s.y2[ch * (F * 4) + f * 4 + t];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Blocks 2-4 of the Silero front for 32 frames per CTA: the k1 convolutions' weights (48 KB, [ci][co]) are staged in shared
+// memory once per CTA, so the nine small stages run at shared-memory latency instead of one L2 round trip each (inside the
+// per-4-frame kernel they were 27 % of its time).  in: block-1 output [frame][16][4]; out: [frame][64].
+// ------------------------------------------------------------------------------------------
+constexpr int kS2Frames = 32;
+constexpr int kS2Weights = 2 * 512 + 1024 + 1024 + 1024 + 2 * 2048 + 4096;   // b2_pw_t .. b4_down_t, contiguous in the table
+
+struct Silero2Smem {
+    float w[kS2Weights];
+    float a[4096];                       // y2 | y2e | r2, then z2 | r3 | z2e, then v1
+    float b[4096];                       // z1, then u1 | u2 | r4
+};
+static_assert(kS2Frames == 32, "the buffer offsets in k_silero_blocks assume 32 frames");
+static_assert(sizeof(Silero2Smem) * 2 <= 227 * 1024 - 2 * 1024, "two CTAs per SM");
+
+__global__ void __launch_bounds__(256, 2) k_silero_blocks(const float* __restrict__ y2g, int n_frames, float* __restrict__ out, SileroDev wts) {
+    extern __shared__ __align__(16) unsigned char smem_raw_2[];
+    Silero2Smem& s = *reinterpret_cast<Silero2Smem*>(smem_raw_2);
+    constexpr int F = kS2Frames;
+    const int tid = threadIdx.x;
+    const int stream = blockIdx.y;
+    const int f0 = blockIdx.x * F;
+    {
+        const float4* src = reinterpret_cast<const float4*>(wts.b2_pw_t);
+        float4* dst = reinterpret_cast<float4*>(s.w);
+        for (int i = tid; i < kS2Weights / 4; i += 256) dst[i] = __ldg(src + i);
+        // [frame][16][4] -> [16][frame * 4 + t]
+        const float4* yin = reinterpret_cast<const float4*>(y2g + ((int64_t)stream * n_frames + f0) * 64);
+        for (int i = tid; i < F * 16; i += 256) {
+            const int f = i >> 4, ch = i & 15;
+            const float4 v = f0 + f < n_frames ? __ldg(yin + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(s.a + ch * (F * 4) + f * 4) = v;
         }
-        if (f0 + fp < n_frames) out[((int64_t)stream * n_frames + f0 + fp) * 64 + co] = fmaxf(a0, 0.f);
-        if (f0 + fp + 2 < n_frames) out[((int64_t)stream * n_frames + f0 + fp + 2) * 64 + co] = fmaxf(a1, 0.f);
+    }
+    __syncthreads();
+    const float* w_b2_pw = s.w, *w_b2_proj = s.w + 512, *w_b2_down = s.w + 1024, *w_b3_pw = s.w + 2048, *w_b3_down = s.w + 3072;
+    const float* w_b4_pw = s.w + 4096, *w_b4_proj = s.w + 6144, *w_b4_down = s.w + 8192;
+    // Every block ends in a k1 convolution of stride 2, which reads the even positions only: the depthwise and pointwise
+    // convolutions in front of it are evaluated at those positions and stored compactly ([C][frame][T / 2]).
+    float* y2 = s.a;                   // [16][F][4]
+    float* y2e = s.a + 2048;           // [16][F][2]  (t = 0, 2)
+    float* r2 = s.a + 3072;            // [16][F][2]
+    float* z1 = s.b;                   // [32][F][2]
+    float* z2 = s.a;                   // [32][F][2]
+    float* r3 = s.a + 2048;            // [32][F]     (t = 0)
+    float* z2e = s.a + 3072;           // [32][F]
+    float* u1 = s.b;                   // [32][F]
+    float* u2 = s.b + 1024;            // [32][F]
+    float* r4 = s.b + 2048;            // [32][F]
+    float* v1 = s.a;                   // [64][F]
+    // block 2 (16 -> 32, T 4 -> 2): depthwise k5 (zero pad inside the frame) at t = 0, 2
+    for (int i = tid; i < 16 * F; i += 256) {
+        const int c = i / F;
+        const float4 v = *reinterpret_cast<const float4*>(y2 + i * 4);
+        float w[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) w[k] = __ldg(wts.b2_dw_w + c * 5 + k);
+        const float b = __ldg(wts.b2_dw_b + c);
+        const float o0 = fmaf(w[4], v.z, fmaf(w[3], v.y, fmaf(w[2], v.x, b)));                       // t = 0: taps 2..4
+        const float o2 = fmaf(w[3], v.w, fmaf(w[2], v.z, fmaf(w[1], v.y, fmaf(w[0], v.x, b))));      // t = 2: taps 0..3
+        *reinterpret_cast<float2*>(r2 + i * 2) = make_float2(fmaxf(o0, 0.f), fmaxf(o2, 0.f));
+        *reinterpret_cast<float2*>(y2e + i * 2) = make_float2(v.x, v.z);
+    }
+    __syncthreads();
+    mix4_relu<16, 32, F * 2, 8, true, false>(r2, w_b2_pw, wts.b2_pw_b, y2e, w_b2_proj, wts.b2_proj_b, nullptr, z1);
+    __syncthreads();
+    mix4_relu<32, 32, F * 2, 8, false, false>(z1, w_b2_down, wts.b2_down_b, nullptr, nullptr, nullptr, nullptr, z2);
+    __syncthreads();
+    // block 3 (32 -> 32 with identity residual, T 2 -> 1): depthwise at t = 0
+    for (int i = tid; i < 32 * F; i += 256) {
+        const int c = i / F;
+        const float2 v = *reinterpret_cast<const float2*>(z2 + i * 2);
+        r3[i] = fmaxf(fmaf(__ldg(wts.b3_dw_w + c * 5 + 3), v.y, fmaf(__ldg(wts.b3_dw_w + c * 5 + 2), v.x, __ldg(wts.b3_dw_b + c))), 0.f);
+        z2e[i] = v.x;
+    }
+    __syncthreads();
+    mix4_relu<32, 32, F, 4, false, true>(r3, w_b3_pw, wts.b3_pw_b, nullptr, nullptr, nullptr, z2e, u1);
+    __syncthreads();
+    mix4_relu<32, 32, F, 4, false, false>(u1, w_b3_down, wts.b3_down_b, nullptr, nullptr, nullptr, nullptr, u2);
+    __syncthreads();
+    // block 4 (32 -> 64, T 1): the depthwise convolution sees its centre tap only
+    for (int i = tid; i < 32 * F; i += 256) {
+        const int c = i / F;
+        r4[i] = fmaxf(fmaf(__ldg(wts.b4_dw_w + c * 5 + 2), u2[i], __ldg(wts.b4_dw_b + c)), 0.f);
+    }
+    __syncthreads();
+    mix4_relu<32, 64, F, 8, true, false>(r4, w_b4_pw, wts.b4_pw_b, u2, w_b4_proj, wts.b4_proj_b, nullptr, v1);
+    __syncthreads();
+    // final 64 -> 64, ReLU, write [frame][64]: eight frames per thread
+    {
+        const int co = tid & 63, fq = tid >> 6;          // frames fq + 4 e
+        float acc[8];
+        const float bias = __ldg(wts.b4_down_b + co);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = bias;
+#pragma unroll 8
+        for (int ci = 0; ci < 64; ++ci) {
+            const float w = w_b4_down[ci * 64 + co];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, v1[ci * F + fq + 4 * e], acc[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int f = f0 + fq + 4 * e;
+            if (f < n_frames) out[((int64_t)stream * n_frames + f) * 64 + co] = fmaxf(acc[e], 0.f);
+        }
     }
 }
 
@@ -1515,11 +1663,16 @@ int sb_vad_score_dev(const sb_vad* v, const float* pcm16k, int64_t pcm_stride, i
     SB_ONCE_PER_DEVICE({
         SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_silero_features_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sb::SileroSmem)));
         SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_silero_features_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sb::SileroFftSmem)));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_silero_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sb::Silero2Smem)));
     });
     dim3 grid((n_frames + sb::kSfFrames - 1) / sb::kSfFrames, n_streams);
-    if (v->basis_is_dft)
-        sb::k_silero_features_fft<<<grid, sb::kFfThreads, sizeof(sb::SileroFftSmem), st>>>(pcm16k, pcm_stride, n_frames, feat, v->dev);
-    else
+    if (v->basis_is_dft) {
+        // blocks 2-4 run in a second kernel on 32 frames per CTA; its input aliases h1 (written only later, by LSTM layer 1)
+        sb::k_silero_features_fft<<<grid, sb::kFfThreads, sizeof(sb::SileroFftSmem), st>>>(pcm16k, pcm_stride, n_frames, h1, v->dev);
+        dim3 grid2((n_frames + sb::kS2Frames - 1) / sb::kS2Frames, n_streams);
+        sb::k_silero_blocks<<<grid2, 256, sizeof(sb::Silero2Smem), st>>>(h1, n_frames, feat, v->dev);
+        sb::g_launches += 1;
+    } else
         sb::k_silero_features_direct<<<grid, sb::kSfThreads, sizeof(sb::SileroSmem), st>>>(pcm16k, pcm_stride, n_frames, feat, v->dev);
     const int nb = (n_streams + sb::kLsStreams - 1) / sb::kLsStreams;
     // state layout [2][n_streams][64]: layer-major like vad-rs' h,c [2,1,64] per stream
