@@ -711,12 +711,13 @@ struct SileroFftSmem {
         __nv_bfloat16 xb[2 * kFfXbCopy];       // two bf16 copies of the frames (B operand of the delta term), then ...
         double2 z[kFfFfts * kFfZFft];          // ... the FFT exchange, then ...
         struct {
-            float r1[258 * kFfR1Pitch];        // ... the depthwise output of block 1 at the even STFT columns (the only ones
+            float r1[264 * kFfR1Pitch];        // ... the depthwise output of block 1 at the even STFT columns (the only ones
                                                //     the stride-2 convolution behind it reads), row pitch 24: conflict-free B loads
             float part1[7 * 256];              //     and the seven partial tiles of its pointwise product
         };
     };
-    float x1[258 * kSfCols];              // [258][frames][7]: re | im, then magnitude | log spectrum, then magnitude | norm
+    float x1[264 * kSfCols];              // [258][frames][7]: re | im, then magnitude | log spectrum, then magnitude | norm;
+                                          // rows 258..263 stay zero (K padding of the block-1 product)
     float y1[16 * kSfFrames * 4];
     float part[8 * kSfCols];
     float mm[kSfFrames];
@@ -738,6 +739,7 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
     const int stream = blockIdx.y;
     const int f0 = blockIdx.x * kSfFrames;
     const float* src = pcm + (int64_t)stream * pcm_stride;
+    if (tid < 6 * kSfCols) s.x1[258 * kSfCols + tid] = 0.0f;          // K padding rows of the block-1 product
     // reflect pad 96 on both sides of every 480-sample frame; two bf16 copies for the delta term
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -856,23 +858,19 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
             const double er = 0.5 * (xr[m] + pr), ei = 0.5 * (xi[m] - pi);
             const double qr = 0.5 * (xi[m] + pi), qi = 0.5 * (pr - xr[m]);       // O[k]
             const double2 w = __ldg(wts.tw2 + k);                                 // e^{-2 pi i k / 256}
-            const float re = (float)(er + (qr * w.x - qi * w.y)), im = (float)(ei + (qr * w.y + qi * w.x));
-            s.x1[k * kSfCols + j] += re;                 // on top of the delta term
-            if (k == 0) s.x1[129 * kSfCols + j] = 0.0f;  // sine row of bin 0: exactly zero, no delta row
-            else s.x1[(129 + k) * kSfCols + j] += im;
+            // + the delta term already in x1, then magnitude | log(1 + 2^20 magnitude) in place (the sine rows of bins 0 and
+            // 128 have no delta row: their slots hold nothing yet)
+            const float re = (float)(er + (qr * w.x - qi * w.y)) + s.x1[k * kSfCols + j];
+            const float im = k == 0 ? 0.0f : (float)(ei + (qr * w.y + qi * w.x)) + s.x1[(129 + k) * kSfCols + j];
+            const float mag = sqrtf(re * re + im * im);
+            s.x1[k * kSfCols + j] = mag;
+            s.x1[(129 + k) * kSfCols + j] = __logf(fmaf(1048576.0f, mag, 1.0f));   // abs error < 5e-6 on values up to 18: see the parity test
         }
-        if (l == 0) {                                    // X[128] = E[0] - O[0] = Re Z[0] - Im Z[0]
-            s.x1[128 * kSfCols + j] += (float)(xr[0] - xi[0]);
-            s.x1[257 * kSfCols + j] = 0.0f;
+        if (l == 0) {                                    // X[128] = E[0] - O[0] = Re Z[0] - Im Z[0], real
+            const float mag = fabsf((float)(xr[0] - xi[0]) + s.x1[128 * kSfCols + j]);
+            s.x1[128 * kSfCols + j] = mag;
+            s.x1[257 * kSfCols + j] = __logf(fmaf(1048576.0f, mag, 1.0f));
         }
-    }
-    __syncthreads();
-    // magnitude | log(1 + 2^20 magnitude), in place
-    for (int i = tid; i < 129 * kSfCols; i += kFfThreads) {
-        const float re = s.x1[i], im = s.x1[129 * kSfCols + i];
-        const float mag = sqrtf(re * re + im * im);
-        s.x1[i] = mag;
-        s.x1[129 * kSfCols + i] = __logf(fmaf(1048576.0f, mag, 1.0f));   // abs error < 5e-6 on values up to 18: see the parity test
     }
     __syncthreads();
     // adaptive normalisation: mean over the 129 bins, reflect pad 3, 7-tap filter, mean over T
@@ -908,6 +906,7 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
         s.mm[tid] = acc / 7.0f;
     }
     __syncthreads();
+    if (tid < 6 * kFfR1Pitch) s.r1[258 * kFfR1Pitch + tid] = 0.0f;    // K padding rows (the exchange buffer is dead by now)
     // block 1 (258 -> 16, T 7 -> 4).  Depthwise k5: one (channel, frame) row of 7 per item; the normalisation
     // (norm = log spectrum - mm[frame]) is applied on the way through and written back for the projection.
     for (int item = tid; item < 258 * kSfFrames; item += kFfThreads) {
@@ -953,25 +952,30 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
         int xcol[2];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) { const int n = nt * 8 + g; xcol[nt] = (n >> 2) * 7 + (n & 3) * 2; }
-#pragma unroll 2
-        for (int ks = wq; ks < 66; ks += 7) {
+        // rows 258..263 of both operands are zero (K padding): no predicates in the loops
+        auto kstep = [&](int ks, const float* p0, const float* p1, int rs) {
             const uint4 ahv = __ldg(wts.b1_frag + (ks * 32 + lane) * 2), alv = __ldg(wts.b1_frag + (ks * 32 + lane) * 2 + 1);
             const uint32_t ah[4] = {ahv.x, ahv.y, ahv.z, ahv.w}, al[4] = {alv.x, alv.y, alv.z, alv.w};
-            const bool second = ks >= 33;
-            const int c0 = (second ? ks - 33 : ks) * 8 + t4;           // input channel of b0; b1 is c0 + 4
-            const bool ok0 = c0 < 258, ok1 = c0 + 4 < 258;              // the padding rows: zero weights, but the operand must be finite
+            const float* pp[2] = {p0, p1};
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-                const float* p0 = second ? s.x1 + c0 * kSfCols + xcol[nt] : s.r1 + c0 * kFfR1Pitch + nt * 8 + g;
-                const int rs = second ? 4 * kSfCols : 4 * kFfR1Pitch;
-                const float b0 = ok0 ? p0[0] : 0.f, b1 = ok1 ? p0[rs] : 0.f;
                 uint32_t h0, l0, h1, l1;
-                split_tf32_trunc(b0, h0, l0);
-                split_tf32_trunc(b1, h1, l1);
+                split_tf32_trunc(pp[nt][0], h0, l0);
+                split_tf32_trunc(pp[nt][rs], h1, l1);
                 mma_tf32(acc[nt], ah, h0, h1);
                 mma_tf32(acc[nt], ah, l0, l1);
                 mma_tf32(acc[nt], al, h0, h1);
             }
+        };
+#pragma unroll 2
+        for (int ks = wq; ks < 33; ks += 7) {                          // depthwise outputs: channel 8 ks + t4 (+ 4)
+            const float* p = s.r1 + (ks * 8 + t4) * kFfR1Pitch + g;
+            kstep(ks, p, p + 8, 4 * kFfR1Pitch);
+        }
+#pragma unroll 2
+        for (int ks = wq; ks < 33; ks += 7) {                          // block inputs
+            const float* p = s.x1 + (ks * 8 + t4) * kSfCols;
+            kstep(33 + ks, p + xcol[0], p + xcol[1], 4 * kSfCols);
         }
         float* part = s.part1 + wq * 256;                              // [16 co][16 columns] per warp
 #pragma unroll
@@ -1427,7 +1431,9 @@ int sb_resample_dev(const sb_resampler* r, const float* in, int64_t in_stride, s
     SB_CHECK_ARG((size_t)out_stride >= n_frames * 480, "out_stride must hold n_frames * 480 samples");
     cudaStream_t st = (cudaStream_t)stream;
     // the last frame is zero padded by FrameResampler::finish
-    SB_CUDA_CHECK(cudaMemset2DAsync(out, out_stride * sizeof(float), 0, n_frames * 480 * sizeof(float), n_streams, st));
+    // the kernels write [0, n_out); only the tail of the last frame needs zeroing
+    if (n_frames * 480 > n_out)
+        SB_CUDA_CHECK(cudaMemset2DAsync(out + n_out, out_stride * sizeof(float), 0, (n_frames * 480 - n_out) * sizeof(float), n_streams, st));
     if (r->decim == 1) {
         SB_CUDA_CHECK(cudaMemcpy2DAsync(out, out_stride * sizeof(float), in, in_stride * sizeof(float), n_in * sizeof(float),
                                         n_streams, cudaMemcpyDeviceToDevice, st));
