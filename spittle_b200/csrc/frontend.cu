@@ -156,25 +156,25 @@ __global__ void __launch_bounds__(256) k_resample_mma(const float* __restrict__ 
 // The decimating FIR as D polyphase branches on the f16 tensor cores (the shipped path; k_resample_mma above is kept as the
 // TF32 reference form, SB_RESAMPLE_TF32=1).
 //   y[m] = sum_u h[u] x[D m - u] = sum_p sum_q h[D q + p] x_p[m - q],   x_p[r] = x[D r - p],  q < Q = ceil(T / D)
-// Each branch is a stride-1 convolution, i.e. a Toeplitz GEMM whose B operand is a sliding window with a column pitch
-// of 16 samples (not 16 D): A_p[i][j] = h_p[Q - 1 + i - j] (16 x (Q + 15), constant), B_p[j][n] = x_p[m0 + 16 n - (Q-1) + j].
+// Each branch is a stride-1 convolution, i.e. a Toeplitz GEMM over 32 consecutive outputs per column:
+//   A_p[i][j] = h_p[Q - 1 + i - j]  (32 x (Q + 31), constant),   B_p[j][n] = x_p[m0 + 32 n - (Q - 1) + j]  (a sliding window).
 // mma.sync.m16n8k16 f16 with the 3-pass split a_hi b_hi + a_hi b_lo + a_lo b_hi (hi = f16(v), lo = f16(v - hi); the taps
 // are scaled by 2^12 first so that their lo parts stay normal): products carry 22 bits, accumulation is f32 -- 1.7e-6
-// against the f64 rubato restatement (3xTF32 form: 3.1e-6), at twice the MACs per instruction and with
-//   * A fragments (hi | lo) pre-arranged on the host; every lane streams its own 32 bytes per k-step through a private
-//     4-deep cp.async ring (ld.global prefetches four steps ahead did not work: ptxas put them on one scoreboard, so
-//     every step waited for the load issued one step earlier);
-//   * B fragments by ldmatrix.x4 (hi k 0-7, hi k 8-15, lo k 0-7, lo k 8-15) from f16 copies of the branch signals.  The
-//     eight windows of a tile start 16 halves = two 16-byte chunks apart, so rows g and g + 4 would share a bank group;
-//     chunk c is stored at c ^ ((c >> 3) & 1), which moves exactly one of the two by a chunk: conflict-free, one copy;
+// against the f64 rubato restatement (3xTF32 form: 3.1e-6), at twice the MACs per instruction.  Operand traffic is what
+// bounds this kernel (the first f16 version sat at 96 % of the L1 / shared-memory pipe with the tensor pipe at 65 %), so:
+//   * rows 16..31 of A_p are rows 0..15 shifted by one k-step (Toeplitz), so the second row tile reuses the fragments the
+//     first one used a step earlier: one fragment load (hi | lo, pre-arranged on the host, 2 x 16 bytes per lane) feeds
+//     two row tiles x eight column tiles = 48 MMAs;
+//   * B fragments by ldmatrix.x4 (hi k 0-7, hi k 8-15, lo k 0-7, lo k 8-15), each shared by the two row tiles.  The eight
+//     windows of a tile start 32 halves = four 16-byte chunks apart; chunk c is stored at c ^ ((c >> 3) & 3), which puts
+//     the eight rows of every 8 x 8 matrix into eight different bank groups with a single copy of the signal;
 //   * no operand splitting in the loop (the TF32 form spent 16 emulated cvt.rna per 6 MMAs: it was issue-bound).
-// CTA = 128 threads = 4 warps x 8 column tiles = 4096 outputs of one stream.
+// CTA = 64 threads = 2 warps x (2 row tiles x 8 column tiles) = 4096 outputs of one stream; 55 KB of shared memory.
 // ------------------------------------------------------------------------------------------
 constexpr int kRpTile = 4096;
-constexpr int kRpThreads = 128;
-constexpr int kRpNT = 8;                 // column tiles per warp
+constexpr int kRpThreads = 64;
+constexpr int kRpNT = 8;                 // column tiles (of 8 x 32 outputs) per warp
 constexpr int kRpScaleLog2 = 12;
-constexpr int kRpRingBytes = 4 * 4 * 2 * 32 * 16;   // [warp][stage][hi|lo][lane] uint4
 
 __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -182,36 +182,31 @@ __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint4& a, uin
                  : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
 
-// smem: A ring | f16 arrays [part hi|lo][branch p][L], L a multiple of 64 halves (every array starts on bank 0)
-__host__ __device__ constexpr int rp_array_len(int SP) { return (kRpTile + 16 * SP + 63) & ~63; }
-__device__ __forceinline__ int rp_swz(int chunk) { return chunk ^ ((chunk >> 3) & 1); }
+// smem: f16 arrays [part hi|lo][branch p][L], L a multiple of 64 halves (every array starts on bank 0).  SP = k-steps of one
+// 16-row tile; the 32-row product takes SP + 1
+__host__ __device__ constexpr int rp_array_len(int SP) { return (kRpTile + 16 * (SP + 1) + 63) & ~63; }
+__device__ __forceinline__ int rp_swz(int chunk) { return chunk ^ ((chunk >> 3) & 3); }
 
 template <int D>
 __global__ void __launch_bounds__(kRpThreads) k_resample_poly(const float* __restrict__ x, int64_t x_stride, int n_in,
                                                              float* __restrict__ y, int64_t y_stride, int n_out,
                                                              const uint4* __restrict__ afrag, int Q, int SP) {
     extern __shared__ __align__(128) unsigned char s_rp[];
-    __half* xh = reinterpret_cast<__half*>(s_rp + kRpRingBytes);
+    __half* xh = reinterpret_cast<__half*>(s_rp);
     const int L = rp_array_len(SP);
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int stream = blockIdx.y;
     const int m0 = blockIdx.x * kRpTile;
     const float* xin = x + (int64_t)stream * x_stride;
-    // A ring: start the first four k-steps before anything else
-    const int n_steps = D * SP;
+    // A fragments: [D][SP + 1][32 lanes][hi | lo]; the last step of every branch is all zero (it is the second row tile's
+    // last step, and what that tile sees as "previous step" when the next branch starts)
+    const int n_steps = D * (SP + 1);
     const uint4* ap = afrag + lane * 2;
-    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_rp) + (uint32_t)(warp * 4 * 1024 + lane * 16);
-    auto issue = [&](int step, int slot) {
-        const uint4* src = ap + (size_t)step * 64;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring + slot * 1024), "l"(src));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring + slot * 1024 + 512), "l"(src + 1));
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-#pragma unroll
-    for (int u = 0; u < 4; ++u) issue(min(u, n_steps - 1), u);
+    uint4 ah1 = __ldg(ap), al1 = __ldg(ap + 1);                            // step 0
+    uint4 ah2 = __ldg(ap + 64), al2 = __ldg(ap + 65);                      // step 1
     const int rbase = m0 - (Q - 1);
-    const int nload = kRpTile + 16 * SP;
+    const int nload = kRpTile + 16 * (SP + 1) - 32;                        // last window starts at 32 * 127
     // branch signals x_p[r] = x[D r - p]: the 2 D consecutive samples x[D r - D + 1 .. D r + D] give the pair (r, r + 1) of
     // every branch
     for (int r2 = 2 * tid; r2 < nload; r2 += 2 * kRpThreads) {
@@ -235,48 +230,57 @@ __global__ void __launch_bounds__(kRpThreads) k_resample_poly(const float* __res
     }
     __syncthreads();
     // ldmatrix row of this lane: matrix lane >> 3 = (part, k half), row lane & 7 = column of the tile.  Chunk (16 bytes)
-    // of the row at k-step s, tile nt: cb + 2 s + 16 nt, swizzled (the swizzle bit does not depend on nt)
+    // of the row at k-step s, tile nt: cb + 2 s + 32 nt, swizzled (the swizzle bits do not depend on nt)
     const int part = lane >> 4, khalf = (lane >> 3) & 1, r = lane & 7;
-    const int cb = 2 * (8 * kRpNT * warp + r) + khalf;
+    const int cb = 4 * (8 * kRpNT * warp + r) + khalf;
     uint32_t bbase = (uint32_t)__cvta_generic_to_shared(xh + (part * D) * L);
-    float acc[kRpNT][4];
+    float acc[2][kRpNT][4];
 #pragma unroll
-    for (int nt = 0; nt < kRpNT; ++nt)
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+        for (int nt = 0; nt < kRpNT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+    uint4 ahp = make_uint4(0u, 0u, 0u, 0u), alp = ahp;                     // previous step's fragments = the second row tile's
     int sI = 0;
     for (int it = 0; it < n_steps; ++it) {
-        asm volatile("cp.async.wait_group 3;" ::: "memory");
-        const int slot = it & 3;
-        uint4 ah, al;
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ah.x), "=r"(ah.y), "=r"(ah.z), "=r"(ah.w) : "r"(ring + slot * 1024));
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(al.x), "=r"(al.y), "=r"(al.z), "=r"(al.w) : "r"(ring + slot * 1024 + 512));
+        const uint4 ah = ah1, al = al1;
+        ah1 = ah2; al1 = al2;
+        const int nx = min(it + 2, n_steps - 1);
+        ah2 = __ldg(ap + (size_t)nx * 64);
+        al2 = __ldg(ap + (size_t)nx * 64 + 1);
         const uint32_t baddr = bbase + ((uint32_t)rp_swz(cb + 2 * sI) << 4);
 #pragma unroll
-        for (int nt = 0; nt < kRpNT; ++nt) {
-            uint32_t bq[4];
-            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(bq[0]), "=r"(bq[1]), "=r"(bq[2]), "=r"(bq[3]) : "r"(baddr + nt * 256));
-            mma_f16_16816(acc[nt], ah, bq[0], bq[1]);
-            mma_f16_16816(acc[nt], ah, bq[2], bq[3]);
-            mma_f16_16816(acc[nt], al, bq[0], bq[1]);
+        for (int nt = 0; nt < kRpNT; nt += 2) {          // two column tiles per pass: a dependent MMA follows three others
+            uint32_t bq[2][4];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(bq[u][0]), "=r"(bq[u][1]), "=r"(bq[u][2]), "=r"(bq[u][3]) : "r"(baddr + (nt + u) * 512));
+#pragma unroll
+            for (int u = 0; u < 2; ++u) { mma_f16_16816(acc[0][nt + u], ah, bq[u][0], bq[u][1]); mma_f16_16816(acc[1][nt + u], ahp, bq[u][0], bq[u][1]); }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) { mma_f16_16816(acc[0][nt + u], ah, bq[u][2], bq[u][3]); mma_f16_16816(acc[1][nt + u], ahp, bq[u][2], bq[u][3]); }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) { mma_f16_16816(acc[0][nt + u], al, bq[u][0], bq[u][1]); mma_f16_16816(acc[1][nt + u], alp, bq[u][0], bq[u][1]); }
         }
-        issue(min(it + 4, n_steps - 1), slot);           // the slot's fragments are in registers (and consumed)
-        if (++sI == SP) { sI = 0; bbase += (uint32_t)(L * 2); }
+        ahp = ah; alp = al;
+        if (++sI == SP + 1) { sI = 0; bbase += (uint32_t)(L * 2); }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    // C[i][n]: c0 (g, 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)  ->  output m0 + 16 n + i
+    // C[i][n]: c0 (g, 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)  ->  output m0 + 32 n + 16 mt + i
     float* yo = y + (int64_t)stream * y_stride;
     const int g = lane >> 2, t = lane & 3;
     constexpr float kInv = 1.0f / (float)(1 << kRpScaleLog2);
 #pragma unroll
-    for (int nt = 0; nt < kRpNT; ++nt)
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int n = 8 * (kRpNT * warp + nt) + 2 * t + (e & 1);
-            const int m = m0 + 16 * n + g + ((e >> 1) << 3);
-            if (m < n_out) yo[m] = acc[nt][e] * kInv;
-        }
+        for (int nt = 0; nt < kRpNT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int n = 8 * (kRpNT * warp + nt) + 2 * t + (e & 1);
+                const int m = m0 + 32 * n + 16 * mt + g + ((e >> 1) << 3);
+                if (m < n_out) yo[m] = acc[mt][nt][e] * kInv;
+            }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1316,7 +1320,7 @@ __global__ void __launch_bounds__(128) k_vad_compact(const float* __restrict__ p
 struct sb_resampler {
     int fs_in = 0, fs_out = 0, decim = 1, n_taps = 0, fft_in = 0, fft_out = 0;
     float* d_h = nullptr;
-    uint4* d_afrag = nullptr;      // polyphase A fragments, f16 hi | lo: [D][SP][32 lanes][2]
+    uint4* d_afrag = nullptr;      // polyphase A fragments, f16 hi | lo: [D][SP + 1][32 lanes][2]
     int Q = 0, SP = 0;             // taps per branch, k-steps per branch
     bool tf32_form = false;        // SB_RESAMPLE_TF32=1: the 3xTF32 Toeplitz kernel instead of the f16 polyphase one
 };
@@ -1376,13 +1380,13 @@ int sb_resampler_create(int fs_in, int fs_out, sb_resampler** out) {
             if (q < 0 || q >= Q || D * q + p >= N) return 0.0f;
             return hf[D * q + p] * (float)(1 << sb::kRpScaleLog2);
         };
-        std::vector<uint32_t> fr((size_t)D * SP * 32 * 8);
+        std::vector<uint32_t> fr((size_t)D * (SP + 1) * 32 * 8, 0u);      // one all-zero step closes every branch
         for (int p = 0; p < D; ++p)
             for (int sI = 0; sI < SP; ++sI)
                 for (int lane = 0; lane < 32; ++lane) {
                     const int g = lane >> 2, t = lane & 3;
                     const int rows[4] = {g, g + 8, g, g + 8}, cols[4] = {2 * t, 2 * t, 2 * t + 8, 2 * t + 8};
-                    uint32_t* o = fr.data() + (((size_t)p * SP + sI) * 32 + lane) * 8;
+                    uint32_t* o = fr.data() + (((size_t)p * (SP + 1) + sI) * 32 + lane) * 8;
                     for (int e = 0; e < 4; ++e) {
                         uint32_t hi2 = 0, lo2 = 0;
                         for (int w = 0; w < 2; ++w) {
@@ -1442,7 +1446,7 @@ int sb_resample_dev(const sb_resampler* r, const float* in, int64_t in_stride, s
     if (n_out == 0) return SB_OK;
     const int D = r->decim;
     if (!r->tf32_form) {
-        const size_t smem = sb::kRpRingBytes + (size_t)2 * D * sb::rp_array_len(r->SP) * sizeof(__half);
+        const size_t smem = (size_t)2 * D * sb::rp_array_len(r->SP) * sizeof(__half);
         SB_CHECK_ARG((uint64_t)D * (n_out + sb::kRpTile + 16 * r->SP) < (1ull << 31), "resampler: stream too long for 32-bit sample indices");
         SB_CHECK_ARG(smem <= 200 * 1024, "resampler: filter too long for the shared-memory segment");
         SB_ONCE_PER_DEVICE({

@@ -11,12 +11,17 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SILERO = os.path.join(GOLD, "silero_v4_16k.npz")
 
-RESAMPLE_TOL = 1e-5      # max abs error vs the f64 rubato restatement
-# max abs error on the speech probability vs the f64 oracle on identical input.  SURVEY 8(d) proposed
-# 1e-4; an fp32 evaluation of this graph (ours, and equally onnxruntime's in the reference) sits at
-# ~1.1e-4 because log(1 + 2^20 |X|) magnifies the round-off of the 256-term fp32 STFT dot products on
-# quiet bins, so the stated tolerance is 3e-4.  Decisions (prob > 0.3) must be identical outside it.
-SILERO_TOL = 3e-4
+# max abs error vs the f64 rubato restatement.  SURVEY 8(d) proposed 1e-5; measured on B200 in round 2: 1.7e-6 for the shipped
+# polyphase f16 (3-pass) kernel, 3.1e-6 for the 3xTF32 Toeplitz form it replaced -- the stated tolerance is 3x the former.
+RESAMPLE_TOL = 5e-6
+RESAMPLE_TF32_TOL = 1e-5
+# max abs error on the speech probability vs the f64 oracle on identical input; decisions (prob > 0.3) must be identical
+# outside it.  The shipped path evaluates the STFT as f64 FFTs plus the exact residual of the stored basis (frontend.cu):
+# measured 1.9e-6 (round 1's f32 convolution: ~1.1e-4, tolerance 3e-4, because log(1 + 2^20 |X|) magnifies the round-off
+# of a 256-term f32 dot product on quiet bins).  Stated tolerance: 1e-5.  The direct-convolution kernel kept for a basis
+# that is not a windowed DFT still has the f32 behaviour and keeps the old bound.
+SILERO_TOL = 1e-5
+SILERO_DIRECT_TOL = 3e-4
 
 
 def test_resampler_matches_rubato_oracle(cuda_dev):
@@ -60,7 +65,7 @@ def test_resampler_other_ratios_and_tf32_form(cuda_dev, monkeypatch):
     monkeypatch.setenv("SB_RESAMPLE_TF32", "1")
     tf32 = audio_toolkit.FrameResampler(48000, 16000).process(x).cpu().numpy()[0]
     print(f"48000 -> 16000: polyphase f16 {np.abs(poly - ref).max():.2e}, 3xTF32 {np.abs(tf32 - ref).max():.2e}")
-    assert np.abs(poly - ref).max() <= RESAMPLE_TOL and np.abs(tf32 - ref).max() <= RESAMPLE_TOL
+    assert np.abs(poly - ref).max() <= RESAMPLE_TOL and np.abs(tf32 - ref).max() <= RESAMPLE_TF32_TOL
 
 
 def test_resampler_properties_full_size(cuda_dev):
@@ -129,7 +134,7 @@ def test_silero_direct_convolution_path(cuda_dev, monkeypatch):
     fft = sv2.score(frames).cpu().numpy()
     for s_ in range(3):
         ref = silero.SileroOracle(w).score(clips[s_])
-        assert np.abs(direct[s_] - ref).max() <= SILERO_TOL
+        assert np.abs(direct[s_] - ref).max() <= SILERO_DIRECT_TOL
         assert np.abs(fft[s_] - ref).max() <= SILERO_TOL
     print("FFT vs direct STFT path, max |dp|:", float(np.abs(fft - direct).max()))
     # (b) a non-DFT basis
@@ -140,7 +145,7 @@ def test_silero_direct_convolution_path(cuda_dev, monkeypatch):
     got = sv3.score(frames).cpu().numpy()
     for s_ in range(3):
         ref = silero.SileroOracle(w2).score(clips[s_])
-        assert np.abs(got[s_] - ref).max() <= SILERO_TOL
+        assert np.abs(got[s_] - ref).max() <= SILERO_DIRECT_TOL
 
 
 def test_gate_is_bit_exact(cuda_dev):
