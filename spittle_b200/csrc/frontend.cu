@@ -787,9 +787,12 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
             const uint4* ap = wts.delta_frag + (size_t)mt * 16 * 32 + lane;
-#pragma unroll 4
+            uint4 af[16];                                // all 16 fragments of the row tile in flight together (they come from L2)
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks) af[ks] = __ldg(ap + ks * 32);
+#pragma unroll
             for (int ks = 0; ks < 16; ++ks) {
-                const uint4 a = __ldg(ap + ks * 32);
+                const uint4 a = af[ks];
 #pragma unroll
                 for (int pr = 0; pr < 2; ++pr) {
                     uint32_t b[4];
@@ -913,7 +916,10 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
     if (tid < 6 * kFfR1Pitch) s.r1[258 * kFfR1Pitch + tid] = 0.0f;    // K padding rows (the exchange buffer is dead by now)
     // block 1 (258 -> 16, T 7 -> 4).  Depthwise k5: one (channel, frame) row of 7 per item; the normalisation
     // (norm = log spectrum - mm[frame]) is applied on the way through and written back for the projection.
-    for (int item = tid; item < 258 * kSfFrames; item += kFfThreads) {
+#pragma unroll
+    for (int pass = 0; pass < (258 * kSfFrames + kFfThreads - 1) / kFfThreads; ++pass) {   // fixed trip count: the weight loads of all passes overlap
+        const int item = tid + pass * kFfThreads;
+        if (item >= 258 * kSfFrames) break;
         const int c = item >> 2, f = item & 3;
         float* row = s.x1 + item * 7;
         float v[11];
@@ -957,8 +963,17 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) { const int n = nt * 8 + g; xcol[nt] = (n >> 2) * 7 + (n & 3) * 2; }
         // rows 258..263 of both operands are zero (K padding): no predicates in the loops
-        auto kstep = [&](int ks, const float* p0, const float* p1, int rs) {
-            const uint4 ahv = __ldg(wts.b1_frag + (ks * 32 + lane) * 2), alv = __ldg(wts.b1_frag + (ks * 32 + lane) * 2 + 1);
+        // A fragments (hi | lo) of this warp's k-steps, all in flight together (they come from L2): steps wq + 7 i of each half
+        uint4 fa[2][5][2];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int ks = min(wq + 7 * i, 32) + 33 * hf;
+                fa[hf][i][0] = __ldg(wts.b1_frag + (ks * 32 + lane) * 2);
+                fa[hf][i][1] = __ldg(wts.b1_frag + (ks * 32 + lane) * 2 + 1);
+            }
+        auto kstep = [&](const uint4& ahv, const uint4& alv, const float* p0, const float* p1, int rs) {
             const uint32_t ah[4] = {ahv.x, ahv.y, ahv.z, ahv.w}, al[4] = {alv.x, alv.y, alv.z, alv.w};
             const float* pp[2] = {p0, p1};
 #pragma unroll
@@ -971,15 +986,21 @@ __global__ void __launch_bounds__(kFfThreads, 2) k_silero_features_fft(const flo
                 mma_tf32(acc[nt], al, h0, h1);
             }
         };
-#pragma unroll 2
-        for (int ks = wq; ks < 33; ks += 7) {                          // depthwise outputs: channel 8 ks + t4 (+ 4)
-            const float* p = s.r1 + (ks * 8 + t4) * kFfR1Pitch + g;
-            kstep(ks, p, p + 8, 4 * kFfR1Pitch);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {                                  // depthwise outputs: channel 8 ks + t4 (+ 4)
+            const int ks = wq + 7 * i;
+            if (ks < 33) {
+                const float* p = s.r1 + (ks * 8 + t4) * kFfR1Pitch + g;
+                kstep(fa[0][i][0], fa[0][i][1], p, p + 8, 4 * kFfR1Pitch);
+            }
         }
-#pragma unroll 2
-        for (int ks = wq; ks < 33; ks += 7) {                          // block inputs
-            const float* p = s.x1 + (ks * 8 + t4) * kSfCols;
-            kstep(33 + ks, p + xcol[0], p + xcol[1], 4 * kSfCols);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {                                  // block inputs
+            const int ks = wq + 7 * i;
+            if (ks < 33) {
+                const float* p = s.x1 + (ks * 8 + t4) * kSfCols;
+                kstep(fa[1][i][0], fa[1][i][1], p + xcol[0], p + xcol[1], 4 * kSfCols);
+            }
         }
         float* part = s.part1 + wq * 256;                              // [16 co][16 columns] per warp
 #pragma unroll
