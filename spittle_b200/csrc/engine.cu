@@ -289,6 +289,8 @@ struct Engine : EngineBase {
     int n_lanes_cfg = 2;
     int n_slots = 0, n_lanes = 0, n_max_cur = 0;
     int refill_min_cfg = 0;       // free slots needed before a refill encode is started (0: max(1, slots / 8))
+    int enc_batch_max = 0;        // windows per encoder batch (0: as many as there are free slots): smaller first batches let the
+                                  // decode lanes start while the rest of the group is still being encoded
     int prefill_min = 8;          // prompts of at least this many tokens are prefilled in one pass (0: token-by-token feed)
 
     ~Engine() override {
@@ -419,6 +421,7 @@ struct Engine : EngineBase {
         SB_CUDA_CHECK(cudaEventCreate(&ev_enc));
         if (const char* e = getenv("SB_REFILL_MIN")) refill_min_cfg = std::max(0, atoi(e));
         if (const char* e = getenv("SB_PREFILL_MIN")) prefill_min = std::max(0, atoi(e));
+        if (const char* e = getenv("SB_ENC_BATCH_MAX")) enc_batch_max = std::max(0, atoi(e));
         if (const char* e = getenv("SB_DECODE_LANES")) { n_lanes_cfg = atoi(e); if (n_lanes_cfg < 1) n_lanes_cfg = 1; if (n_lanes_cfg > kMaxLanes) n_lanes_cfg = kMaxLanes; }
         int rc = sb_melplan_create(f.mel_filters.data(), hp.n_mels, &melplan);
         if (rc) return rc;
@@ -1238,8 +1241,9 @@ struct Engine : EngineBase {
                         ready.push_back(c);
                     }
                     for (int s_ = 0; s_ < S; ++s_) if (slot_job[s_] < 0) freeslots.push_back(s_);
-                    const int k = (int)std::min(ready.size(), freeslots.size());
-                    if (k > 0 && (running == 0 || k >= refill_min)) {
+                    int k = (int)std::min(ready.size(), freeslots.size());
+                    if (enc_batch_max > 0) k = std::min(k, enc_batch_max);
+                    if (k > 0 && (running == 0 || k >= std::min(refill_min, enc_batch_max > 0 ? enc_batch_max : refill_min))) {
                         // spread the new windows over the lanes with the fewest live sequences
                         std::vector<int> lane_load(n_lanes);
                         for (int li = 0; li < n_lanes; ++li) lane_load[li] = lanes[li].active;
