@@ -4,7 +4,9 @@
 Metric (BASELINE.json): RTFx = audio-seconds per wall-second.  Workload: BASELINE.json configs[2] "Whisper
 Large-v3 Turbo (128-mel, 4-layer decoder) batched clips sharded across 1/2/4/8 B200" -- the model north_star names --
 with 128 synthetic 30 s clips per GPU; SB_BENCH_ARCH=small runs configs[1] (Whisper Small, 64 clips), and at N = 1 the
-default run carries that configuration as the secondary `config.small_64` entry.
+default run carries that configuration as the secondary `config.small_64` entry, plus `config.c4_encoder` (configs[3] in small:
+the encoder + cross-KV GEMM on 128 windows) and `config.c5_frontend` (configs[4] in small: the 48 kHz capture front-end over
+1000 streams) so that the driver's BENCH line carries all five configurations' figures.
 A step = one pass of the whole hot path (log-mel -> encoder -> cross-KV -> greedy decode with
 the whisper.cpp seek loop -> text) over one batch of clips through the C ABI
 (sb_transcribe_batch).  N > 1: one process per GPU (torchrun), every rank transcribes its own
@@ -302,6 +304,46 @@ def measure(arch, args, torch, capi, dist, rank, local_rank, world, steps, warmu
                 st_dec=st_dec, launches=launches, clocks=sampler.summary(), n_mels=n_mels)
 
 
+def c4_encoder_block(capi, arch, dtype_name, B=128):
+    """BASELINE.json configs[3] in small: the encoder (+ cross-KV GEMM) of `arch` on B windows in one sb_encode call, device time
+    from the engine's events, as TFLOP/s and as a fraction of the measured sustained bf16 peak.  (Large-v3-Turbo has Large-v3's
+    encoder; tools/c4_encoder_sweep.py is the full B = 32 ... 512 sweep on Large-v3 itself.)"""
+    try:
+        peaks, _src = load_peaks()
+        dtype = capi.SB_DTYPE_F16 if dtype_name == "f16" else capi.SB_DTYPE_BF16
+        eng = capi.Engine(model_path(arch), max_batch=B, dtype=dtype)
+        d, L, Ld, nm = eng.info.n_audio_state, eng.info.n_audio_layer, eng.info.n_text_layer, eng.info.n_mels
+        mel = np.random.default_rng(0).uniform(-1, 1, (B, nm, 3000)).astype(np.float32)
+        flops = B * (2 * 3000 * d * nm * 3 + 2 * 1500 * d * d * 3 + L * (24 * 1500 * d * d + 4 * 1500 * 1500 * d)) + B * Ld * 4 * 1500 * d * d
+        eng.set_profile(True)
+        best = None
+        for rep in range(3):
+            eng.stats(reset=True)
+            eng.encode(mel)
+            st = eng.stats(reset=True)
+            if rep and (best is None or st["encode_ms"] < best):
+                best = st["encode_ms"]
+        eng.close()
+        tf = flops / best / 1e9
+        return {"workload": f"C4: {arch} encoder + cross-KV GEMM, {B} windows (30 s each) in one batch, {dtype_name}", "encode_ms": best,
+                "tflops": tf, "frac_sustained_bf16_peak": tf / peaks["bf16_tflops_sustained"], "encoder_only_rtfx": B * 30.0 / best * 1e3}
+    except Exception as e:          # a secondary entry must never cost the line
+        return {"error": repr(e)}
+
+
+def c5_frontend_block(n_streams=1000):
+    """BASELINE.json configs[4] in small: resample -> Silero -> log-mel over `n_streams` synthetic 48 kHz streams
+    (tools/frontend_bench.py is the same code at the stated 10 000 streams)."""
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("frontend_bench", os.path.join(ROOT, "tools", "frontend_bench.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod.run(n_streams, n_streams)
+    except Exception as e:
+        return {"error": repr(e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -310,7 +352,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default=os.environ.get("SB_BENCH_DTYPE", "f16"), choices=["f16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the Whisper Small (configs[1]) secondary entry")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary entries (Whisper Small configs[1], C4 encoder, C5 front-end)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -359,7 +401,7 @@ def main():
     mel_bytes = CLIPS_PER_GPU * (480000 * 4 + m["n_mels"] * 3000 * 4)
     mel_gbps = mel_bytes * steps / max(st_dev["mel_ms"], 1e-9) / 1e6
 
-    secondary = None
+    secondary = c4 = c5 = None
     if world == 1 and ARCH != "small" and not args.no_secondary:
         # BASELINE.json configs[1] (Whisper Small, 64 clips, 1 GPU) carried as a secondary entry of the default run
         m2 = measure("small", args, torch, capi, None, rank, local_rank, 1, min(steps, 5), 3, trace=False, n_clips=64)
@@ -368,6 +410,8 @@ def main():
                      "e2e": 64 * CLIP_SECONDS * k2 / (m2["ms_e2e"] / 1e3), "unit": "x real-time", "steps": k2, "ms_per_step": m2["ms_dev"] / k2,
                      "ms_encode": m2["st_dev"]["encode_ms"] / k2, "ms_decode": m2["st_dev"]["decode_ms"] / k2,
                      "decoder_steps_per_step": m2["st_dev"]["decoder_steps"] / k2}
+        c4 = c4_encoder_block(capi, ARCH, args.dtype)
+        c5 = c5_frontend_block(1000)
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -388,7 +432,7 @@ def main():
             "ms_mel": st_dev["mel_ms"] / steps, "ms_encode": st_dev["encode_ms"] / steps,
             "ms_decode": st_dev["decode_ms"] / steps,
             "phase_note": "ms_encode = sum of the encoder batches (refill batches overlap the decode lanes); ms_decode = the rest of the call",
-            "small_64": secondary}),
+            "small_64": secondary, "c4_encoder": c4, "c5_frontend": c5}),
         "e2e": {"value": e2e, "unit": "x real-time", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": (st_e2e["pcm_bytes"] + st_e2e["h2d_bytes"]) / steps,
                 "d2h_bytes_per_step": st_e2e["d2h_bytes"] / steps},
