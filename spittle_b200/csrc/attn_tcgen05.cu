@@ -189,6 +189,9 @@ __device__ __forceinline__ void at_wait_st() { asm volatile("tcgen05.wait::st.sy
 // from the tensor pipe (P x ones).  ptxas lowers the packed ex2 to TWO MUFU.EX2.F16, so the MUFU count does not drop: 530 vs
 // 641 TFLOP/s (Large-v3 shape) and twice the error (5.3e-4 vs 2.9e-4 rel-RMS); mixing an f16 P with a bf16 V in one kind::f16
 // MMA is an illegal instruction.  The sweep stays one MUFU.EX2 per score: 128 x 64 per tile against 256 tensor clocks.
+// Also measured and rejected (end of round 2): every fourth exp2 on the FMA / ALU pipes instead (round-to-nearest split, degree-4
+// polynomial, exponent patched in: 10 instructions, 4e-5 relative, parity unchanged) -- 631 -> 559 TFLOP/s on the Turbo shape, 579 -> 517
+// on Small: the sweep's issue slots are as loaded as its MUFU, so moving work from one to the other loses.
 template <typename T>
 __global__ void __launch_bounds__(kAtThreads, 2)
 k_attn_enc_ts(const __grid_constant__ CUtensorMap tm_kv, const T* __restrict__ qkv, T* __restrict__ out, int n_ctx, int d_model,
