@@ -89,7 +89,8 @@ SB_API int sb_logmel_batch_dev(const sb_melplan* plan, const float* pcm, int n_c
  * wrapped by FrameResampler (audio_toolkit/audio/resampler.rs:16-98).  Output semantics are those
  * of push(everything) + finish(): the input is zero-padded to whole 1024-sample chunks, only whole
  * rubato blocks (1026 -> 342 at 48 -> 16 kHz) are produced, the last 480-sample frame is zero padded.
- * Only integer decimation ratios are implemented (48 kHz, 32 kHz, 16 kHz inputs).
+ * Integer decimation ratios (96 / 64 / 48 / 32 kHz) run the polyphase tensor-core kernel, 16 kHz passes through, every other
+ * rate (44.1 / 22.05 / 11.025 / 8 kHz ...) applies rubato's block operator as a dense split-precision GEMM.
  * ---------------------------------------------------------------------------------- */
 typedef struct sb_resampler sb_resampler;
 SB_API int sb_resampler_create(int fs_in, int fs_out, sb_resampler** out);

@@ -284,6 +284,78 @@ __global__ void __launch_bounds__(kRpThreads) k_resample_poly(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------
+// Rational ratios (44.1 kHz, 22.05 kHz, 8 kHz ... -> 16 kHz): rubato's FftFixedIn as the dense linear operator it is.
+// One rubato block maps N1 = fft_size_in input samples to N2 = fft_size_out output samples through rfft(2 N1) -> spectrum
+// x filter, truncated to L bins -> irfft(2 N2) -> overlap-add of the two output halves.  Every step is linear, so
+//   out_b[m] = sum_j A[m][j] x_b[j] + sum_j A[N2 + m][j] x_{b-1}[j],
+//   A[m][j]  = filt[0] + 2 sum_{k=1}^{L-1} Re(filt[k] e^{2 pi i k (m / 2 N2 - j / 2 N1)}),   m < 2 N2, j < N1
+// i.e. C[block][m] = X[block][.] W[m][.]^T with X[block] = the 2 N1 consecutive samples x_{b-1} | x_b (materialised as f16
+// hi | lo rows, K padded to a multiple of 32) and W = [A_bottom | A_top] (built once per resampler, on the device, in f64).
+// The product runs on the tcgen05 GEMM of the encoder (sb_gemm_tn_dev) in three passes hi hi + hi lo + lo hi with the f32
+// running sum as the residual input: 22-bit products like the polyphase kernel.  (The integer ratios keep that kernel: a
+// Toeplitz operator needs K = 1026 + 45 per output there, the dense block operator 2 N1 = 2646.)
+// ------------------------------------------------------------------------------------------
+constexpr float kRdScale = 1024.0f;
+
+// W[m][kk], m < N2, kk < Kp: kk < N1 pairs with x_{b-1}[kk] (A row N2 + m), N1 <= kk < 2 N1 with x_b[kk - N1] (A row m)
+__global__ void k_resample_dense_matrix(const double2* __restrict__ filt, int N1, int N2, int L, int Kp,
+                                        __half* __restrict__ whi, __half* __restrict__ wlo) {
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+    if (kk >= Kp) return;
+    double a = 0.0;
+    if (kk < 2 * N1) {
+        const int row = kk < N1 ? N2 + m : m, j = kk < N1 ? kk : kk - N1;
+        // phase of bin k: 2 pi k (row N1 - j N2) / (2 N1 N2), reduced exactly in integers
+        const long long P = 2LL * N1 * N2;
+        long long t = ((long long)row * N1 - (long long)j * N2) % P;
+        if (t < 0) t += P;
+        a = filt[0].x;
+        // e^{i k theta} by recurrence, re-seeded exactly every 64 bins (the error of the recurrence grows like k x 1e-16)
+        double wr, wi;
+        sincospi(2.0 * (double)t / (double)P, &wi, &wr);
+        double zr = 1.0, zi = 0.0;
+        for (int k = 1; k < L; ++k) {
+            if ((k & 63) == 0) {
+                const long long u = ((long long)k * t) % P;
+                sincospi(2.0 * (double)u / (double)P, &zi, &zr);
+            } else {
+                const double nr = zr * wr - zi * wi;
+                zi = zr * wi + zi * wr; zr = nr;
+            }
+            a += 2.0 * (filt[k].x * zr - filt[k].y * zi);
+        }
+    }
+    const float v = (float)(a * (double)kRdScale);
+    const __half hi = __float2half_rn(v);
+    whi[(size_t)m * Kp + kk] = hi;
+    wlo[(size_t)m * Kp + kk] = __float2half_rn((float)(a * (double)kRdScale - (double)__half2float(hi)));
+}
+
+// X rows: row (stream, b) = samples [(b - 1) N1, (b + 1) N1) of the stream (zero outside [0, n_in)), f16 hi | lo
+__global__ void k_resample_dense_rows(const float* __restrict__ x, int64_t x_stride, int n_in, int n_blocks, int N1, int Kp,
+                                      __half* __restrict__ xhi, __half* __restrict__ xlo) {
+    const int row = blockIdx.x;                       // stream * n_blocks + b
+    const int stream = row / n_blocks, b = row - stream * n_blocks;
+    const float* src = x + (int64_t)stream * x_stride;
+    const int64_t base = (int64_t)(b - 1) * N1;
+    for (int kk = threadIdx.x; kk < Kp; kk += blockDim.x) {
+        const int64_t si = base + kk;
+        const float v = (kk < 2 * N1 && si >= 0 && si < n_in) ? __ldg(src + si) : 0.0f;
+        const __half hi = __float2half_rn(v);
+        xhi[(size_t)row * Kp + kk] = hi;
+        xlo[(size_t)row * Kp + kk] = __float2half_rn(v - __half2float(hi));
+    }
+}
+
+// out[stream][b N2 + m] = C[(stream, b)][m] / scale
+__global__ void k_resample_dense_store(const float* __restrict__ c, int n_blocks, int N2, float* __restrict__ out, int64_t out_stride) {
+    const int row = blockIdx.x;
+    const int stream = row / n_blocks, b = row - stream * n_blocks;
+    float* dst = out + (int64_t)stream * out_stride + (int64_t)b * N2;
+    for (int m = threadIdx.x; m < N2; m += blockDim.x) dst[m] = c[(size_t)row * N2 + m] * (1.0f / kRdScale);
+}
+
+// ------------------------------------------------------------------------------------------
 // Silero v4 (16 kHz) weights, device resident
 // ------------------------------------------------------------------------------------------
 struct SileroDev {
@@ -1344,6 +1416,12 @@ struct sb_resampler {
     uint4* d_afrag = nullptr;      // polyphase A fragments, f16 hi | lo: [D][SP + 1][32 lanes][2]
     int Q = 0, SP = 0;             // taps per branch, k-steps per branch
     bool tf32_form = false;        // SB_RESAMPLE_TF32=1: the 3xTF32 Toeplitz kernel instead of the f16 polyphase one
+    // rational ratios: the block operator as a dense GEMM (k_resample_dense_*)
+    bool dense = false;
+    int N1 = 0, N2 = 0, Kp = 0;
+    __half *d_whi = nullptr, *d_wlo = nullptr;
+    mutable void* d_ws = nullptr;  // X hi | X lo | C of one chunk of streams, grown on demand
+    mutable size_t ws_bytes = 0;
 };
 
 struct sb_vad {
@@ -1364,15 +1442,55 @@ int sb_resampler_create(int fs_in, int fs_out, sb_resampler** out) {
     SB_CHECK_ARG(out && fs_in > 0 && fs_out > 0, "bad arguments");
     const int g = gcd_i(fs_in, fs_out);
     const int a = fs_in / g, b = fs_out / g;
-    if (b != 1 || (a != 1 && a != 2 && a != 3 && a != 4 && a != 6)) {
-        sb::set_error("resampler: only integer decimation ratios (in/out in {1,2,3,4,6}) are implemented; "
-                      "rubato's rational ratios (e.g. 44100 -> 16000) are not yet");
-        return SB_ERR_UNSUPPORTED;
-    }
+    const bool integer_ratio = b == 1 && (a == 1 || a == 2 || a == 3 || a == 4 || a == 6);
     sb_resampler* r = new sb_resampler();
-    r->fs_in = fs_in; r->fs_out = fs_out; r->decim = a;
+    r->fs_in = fs_in; r->fs_out = fs_out; r->decim = integer_ratio ? a : 0; r->dense = !integer_ratio;
     const int fft_chunks = (1024 + a - 1) / a;               // rubato: ceil(chunk_size_in / (fs_in / gcd))
     r->fft_in = fft_chunks * a; r->fft_out = fft_chunks * b; r->n_taps = r->fft_in;
+    if (r->dense) {
+        // any other ratio (44.1 / 22.05 / 11.025 / 8 kHz ...): the block operator as a dense matrix, see k_resample_dense_matrix
+        const int N1 = r->fft_in, N2 = r->fft_out, L = N1 < N2 ? N1 + 1 : N2;
+        if (N2 % 8 != 0 || (size_t)N2 * 2 * N1 > (size_t)64 << 20) {
+            delete r;
+            sb::set_error("resampler: this ratio gives a block operator the dense path does not take (fft_size_out must be a multiple of 8)");
+            return SB_ERR_UNSUPPORTED;
+        }
+        const float cutoff_f = N1 > N2 ? powf(0.4f, 16.0f / (float)N2) * (float)N2 / (float)N1 : powf(0.4f, 16.0f / (float)N1);
+        const double cutoff = (double)cutoff_f;
+        std::vector<double> h(N1);
+        double sum = 0.0;
+        for (int x = 0; x < N1; ++x) {
+            const double ph = (double)x / N1;
+            double w = 0.35875 - 0.48829 * cos(2 * M_PI * ph) + 0.14128 * cos(4 * M_PI * ph) - 0.01168 * cos(6 * M_PI * ph);
+            w *= w;
+            const double t = ((double)x - (double)(N1 / 2)) * cutoff;
+            h[x] = w * (t == 0.0 ? 1.0 : sin(M_PI * t) / (M_PI * t));
+            sum += h[x];
+        }
+        // filter spectrum: rfft([h / sum / (2 N1), zeros(N1)]), bins 0 .. L-1 (exact phase reduction in integers)
+        std::vector<double> filt(2 * (size_t)L);
+        for (int k = 0; k < L; ++k) {
+            double re = 0.0, im = 0.0;
+            for (int x = 0; x < N1; ++x) {
+                const double th = -2.0 * M_PI * (double)(((long long)k * x) % (2 * N1)) / (double)(2 * N1);
+                re += h[x] * cos(th); im += h[x] * sin(th);
+            }
+            filt[2 * k] = re / sum / (2.0 * N1); filt[2 * k + 1] = im / sum / (2.0 * N1);
+        }
+        r->N1 = N1; r->N2 = N2; r->Kp = (2 * N1 + 31) & ~31;
+        double2* d_filt = nullptr;
+        SB_CUDA_CHECK(cudaMalloc(&d_filt, filt.size() * sizeof(double)));
+        SB_CUDA_CHECK(cudaMemcpy(d_filt, filt.data(), filt.size() * sizeof(double), cudaMemcpyHostToDevice));
+        SB_CUDA_CHECK(cudaMalloc(&r->d_whi, (size_t)N2 * r->Kp * sizeof(__half)));
+        SB_CUDA_CHECK(cudaMalloc(&r->d_wlo, (size_t)N2 * r->Kp * sizeof(__half)));
+        dim3 grid((r->Kp + 127) / 128, N2);
+        sb::k_resample_dense_matrix<<<grid, 128>>>(d_filt, N1, N2, L, r->Kp, r->d_whi, r->d_wlo);
+        SB_CUDA_CHECK(cudaGetLastError());
+        SB_CUDA_CHECK(cudaDeviceSynchronize());
+        cudaFree(d_filt);
+        *out = r;
+        return SB_OK;
+    }
     if (a > 1) {
         // make_sincs(npoints = fft_in, factor 1, cutoff, BlackmanHarris2) -- SURVEY App. B; f32 cutoff like rubato
         const float cutoff_f = powf(0.4f, 16.0f / (float)r->fft_out) * (float)r->fft_out / (float)r->fft_in;
@@ -1431,7 +1549,7 @@ int sb_resampler_create(int fs_in, int fs_out, sb_resampler** out) {
 
 int sb_resampler_destroy(sb_resampler* r) {
     if (!r) return SB_OK;
-    cudaFree(r->d_h); cudaFree(r->d_afrag);
+    cudaFree(r->d_h); cudaFree(r->d_afrag); cudaFree(r->d_whi); cudaFree(r->d_wlo); cudaFree(r->d_ws);
     delete r;
     return SB_OK;
 }
@@ -1440,7 +1558,7 @@ int sb_resample_geometry(const sb_resampler* r, size_t n_in, size_t* n_fed, size
     SB_CHECK_ARG(r, "null resampler");
     const size_t fed = (n_in + 1023) / 1024 * 1024;          // push() chunks + finish() zero pad
     size_t out = fed;
-    if (r->decim > 1) out = fed / (size_t)r->fft_in * (size_t)r->fft_out;   // whole rubato blocks only
+    if (r->decim > 1 || r->dense) out = fed / (size_t)r->fft_in * (size_t)r->fft_out;   // whole rubato blocks only
     else out = n_in;                                          // pass-through (resampler.rs:38-41)
     if (n_fed) *n_fed = fed;
     if (n_out) *n_out = out;
@@ -1465,6 +1583,36 @@ int sb_resample_dev(const sb_resampler* r, const float* in, int64_t in_stride, s
         return SB_OK;
     }
     if (n_out == 0) return SB_OK;
+    if (r->dense) {
+        const int N1 = r->N1, N2 = r->N2, Kp = r->Kp;
+        const int n_blocks = (int)(n_out / (size_t)N2);
+        // chunks of streams sized for <= ~1.5 GB of workspace: X hi | X lo (rows x Kp f16 each) | C (rows x N2 f32)
+        const size_t row_bytes = (size_t)Kp * 2 * sizeof(__half) + (size_t)N2 * sizeof(float);
+        int per_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_streams, ((size_t)1536 << 20) / (row_bytes * (size_t)n_blocks)));
+        const size_t need = row_bytes * (size_t)n_blocks * per_chunk;
+        if (need > r->ws_bytes) {
+            SB_CUDA_CHECK(cudaStreamSynchronize(st));
+            cudaFree(r->d_ws); r->d_ws = nullptr; r->ws_bytes = 0;
+            SB_CUDA_CHECK(cudaMalloc(&r->d_ws, need));
+            r->ws_bytes = need;
+        }
+        for (int s0 = 0; s0 < n_streams; s0 += per_chunk) {
+            const int ns = std::min(per_chunk, n_streams - s0);
+            const int rows = ns * n_blocks;
+            __half* xhi = (__half*)r->d_ws;
+            __half* xlo = xhi + (size_t)rows * Kp;
+            float* c = (float*)(xlo + (size_t)rows * Kp);
+            sb::k_resample_dense_rows<<<rows, 256, 0, st>>>(in + (int64_t)s0 * in_stride, in_stride, (int)n_in, n_blocks, N1, Kp, xhi, xlo);
+            int rc;
+            if ((rc = sb_gemm_tn_dev(SB_DTYPE_F16, xhi, Kp, r->d_whi, Kp, rows, N2, Kp, c, N2, 1, nullptr, 0, nullptr, 0, 0, st))) return rc;
+            if ((rc = sb_gemm_tn_dev(SB_DTYPE_F16, xhi, Kp, r->d_wlo, Kp, rows, N2, Kp, c, N2, 1, nullptr, 0, c, N2, 0, st))) return rc;
+            if ((rc = sb_gemm_tn_dev(SB_DTYPE_F16, xlo, Kp, r->d_whi, Kp, rows, N2, Kp, c, N2, 1, nullptr, 0, c, N2, 0, st))) return rc;
+            sb::k_resample_dense_store<<<rows, 256, 0, st>>>(c, n_blocks, N2, out + (int64_t)s0 * out_stride, out_stride);
+            sb::g_launches += 2;
+        }
+        SB_CUDA_CHECK(cudaGetLastError());
+        return SB_OK;
+    }
     const int D = r->decim;
     if (!r->tf32_form) {
         const size_t smem = (size_t)2 * D * sb::rp_array_len(r->SP) * sizeof(__half);

@@ -43,8 +43,26 @@ def test_resampler_matches_rubato_oracle(cuda_dev):
     x16 = synth.make_clip(2, seconds=1.0)
     fr = audio_toolkit.FrameResampler(16000, 16000).process(x16[None]).cpu().numpy().reshape(-1)
     assert np.array_equal(fr[:16000], x16) and np.all(fr[16000:] == 0) and fr.shape[0] == 34 * 480
-    with pytest.raises(capi.SbError):
-        audio_toolkit.FrameResampler(44100, 16000)
+
+
+def test_resampler_rational_ratios(cuda_dev):
+    """44.1 / 22.05 / 11.025 / 8 kHz capture devices: rubato's FftFixedIn block operator (1323 -> 480 samples at 44.1 kHz) as a dense
+    split-precision GEMM, against the f64 restatement of the block FFT algorithm (reference: resampler.rs:16-27 accepts any rate)."""
+    for fs in (44100, 22050, 11025, 8000):
+        x = np.stack([synth.make_clip(50 + i, seconds=2.0, sr=fs, kind=k) for i, k in enumerate(["vowel", "noise", "mix"])])
+        got = audio_toolkit.FrameResampler(fs, 16000).process(x).cpu().numpy()
+        for s_ in range(3):
+            ref = resample.frame_resampler(x[s_], fs, 16000)
+            assert got[s_].shape == ref.shape, (fs, got[s_].shape, ref.shape)
+            err = np.abs(got[s_] - ref).max()
+            print(f"resample {fs} -> 16000: max err {err:.2e} (max |y| {np.abs(ref).max():.2f})")
+            assert err <= RESAMPLE_TOL, (fs, err)
+    # 30 s at 44.1 kHz, several streams: the chunked workspace path and the zero tail of the last frame
+    x = np.stack([synth.make_clip(60 + i, seconds=30.0, sr=44100) for i in range(3)])
+    got = audio_toolkit.FrameResampler(44100, 16000).process(x).cpu().numpy()
+    for s_ in range(3):
+        ref = resample.frame_resampler(x[s_], 44100, 16000)
+        assert got[s_].shape == ref.shape and np.abs(got[s_] - ref).max() <= RESAMPLE_TOL
 
 
 def test_resampler_other_ratios_and_tf32_form(cuda_dev, monkeypatch):
