@@ -21,6 +21,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace sb {
 extern std::atomic<uint64_t> g_launches;
@@ -1422,6 +1423,7 @@ struct sb_resampler {
     __half *d_whi = nullptr, *d_wlo = nullptr;
     mutable void* d_ws = nullptr;  // X hi | X lo | C of one chunk of streams, grown on demand
     mutable size_t ws_bytes = 0;
+    mutable std::mutex ws_mu;      // the workspace is shared by the calls on this object: they enqueue one at a time
 };
 
 struct sb_vad {
@@ -1584,6 +1586,7 @@ int sb_resample_dev(const sb_resampler* r, const float* in, int64_t in_stride, s
     }
     if (n_out == 0) return SB_OK;
     if (r->dense) {
+        std::lock_guard<std::mutex> lock(r->ws_mu);
         const int N1 = r->N1, N2 = r->N2, Kp = r->Kp;
         const int n_blocks = (int)(n_out / (size_t)N2);
         // chunks of streams sized for <= ~1.5 GB of workspace: X hi | X lo (rows x Kp f16 each) | C (rows x N2 f32)
