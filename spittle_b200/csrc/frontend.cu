@@ -659,47 +659,63 @@ __device__ __forceinline__ void mix_relu(const float* __restrict__ in1, const fl
     }
 }
 
-// the same with the identity position map: PPT consecutive positions per thread, read as float4 broadcasts
-template <int CIN, int COUT, int P, int PPT, bool TWO, bool RES>
+// the same with the identity position map: PPT consecutive positions x NCO output channels (co, co + COUT / NCO, ...) per thread;
+// the activations are read as float4 broadcasts and shared by the NCO channels (the stage is bound by these loads)
+template <int CIN, int COUT, int P, int PPT, int NCO, bool TWO, bool RES>
 __device__ __forceinline__ void mix4_relu(const float* __restrict__ in1, const float* __restrict__ w1t, const float* __restrict__ b1,
                                           const float* __restrict__ in2, const float* __restrict__ w2t, const float* __restrict__ b2,
                                           const float* __restrict__ res, float* __restrict__ out) {
-    static_assert(PPT % 4 == 0 && P % PPT == 0, "PPT a multiple of 4 dividing P");
-    for (int item = threadIdx.x; item < COUT * (P / PPT); item += blockDim.x) {
-        const int co = item % COUT, p0 = (item / COUT) * PPT;
-        float a[PPT];
-        const float bias = TWO ? b1[co] + b2[co] : b1[co];
+    static_assert(PPT % 4 == 0 && P % PPT == 0 && COUT % NCO == 0, "PPT a multiple of 4 dividing P, NCO dividing COUT");
+    constexpr int CG = COUT / NCO;
+    for (int item = threadIdx.x; item < CG * (P / PPT); item += blockDim.x) {
+        const int co = item % CG, p0 = (item / CG) * PPT;
+        float a[NCO][PPT];
 #pragma unroll
-        for (int e = 0; e < PPT; ++e) a[e] = bias;
+        for (int c = 0; c < NCO; ++c) {
+            const float bias = TWO ? b1[co + c * CG] + b2[co + c * CG] : b1[co + c * CG];
+#pragma unroll
+            for (int e = 0; e < PPT; ++e) a[c][e] = bias;
+        }
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
-            const float w = w1t[ci * COUT + co];
+            float w[NCO];
+#pragma unroll
+            for (int c = 0; c < NCO; ++c) w[c] = w1t[ci * COUT + co + c * CG];
 #pragma unroll
             for (int q = 0; q < PPT / 4; ++q) {
                 const float4 v = *reinterpret_cast<const float4*>(in1 + ci * P + p0 + 4 * q);
-                a[4 * q] = fmaf(w, v.x, a[4 * q]); a[4 * q + 1] = fmaf(w, v.y, a[4 * q + 1]);
-                a[4 * q + 2] = fmaf(w, v.z, a[4 * q + 2]); a[4 * q + 3] = fmaf(w, v.w, a[4 * q + 3]);
+#pragma unroll
+                for (int c = 0; c < NCO; ++c) {
+                    a[c][4 * q] = fmaf(w[c], v.x, a[c][4 * q]); a[c][4 * q + 1] = fmaf(w[c], v.y, a[c][4 * q + 1]);
+                    a[c][4 * q + 2] = fmaf(w[c], v.z, a[c][4 * q + 2]); a[c][4 * q + 3] = fmaf(w[c], v.w, a[c][4 * q + 3]);
+                }
             }
             if (TWO) {
-                const float w2 = w2t[ci * COUT + co];
+#pragma unroll
+                for (int c = 0; c < NCO; ++c) w[c] = w2t[ci * COUT + co + c * CG];
 #pragma unroll
                 for (int q = 0; q < PPT / 4; ++q) {
                     const float4 v = *reinterpret_cast<const float4*>(in2 + ci * P + p0 + 4 * q);
-                    a[4 * q] = fmaf(w2, v.x, a[4 * q]); a[4 * q + 1] = fmaf(w2, v.y, a[4 * q + 1]);
-                    a[4 * q + 2] = fmaf(w2, v.z, a[4 * q + 2]); a[4 * q + 3] = fmaf(w2, v.w, a[4 * q + 3]);
+#pragma unroll
+                    for (int c = 0; c < NCO; ++c) {
+                        a[c][4 * q] = fmaf(w[c], v.x, a[c][4 * q]); a[c][4 * q + 1] = fmaf(w[c], v.y, a[c][4 * q + 1]);
+                        a[c][4 * q + 2] = fmaf(w[c], v.z, a[c][4 * q + 2]); a[c][4 * q + 3] = fmaf(w[c], v.w, a[c][4 * q + 3]);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int q = 0; q < PPT / 4; ++q) {
-            float4 v = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
-            if (RES) {
-                const float4 r = *reinterpret_cast<const float4*>(res + co * P + p0 + 4 * q);
-                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        for (int c = 0; c < NCO; ++c)
+#pragma unroll
+            for (int q = 0; q < PPT / 4; ++q) {
+                float4 v = make_float4(a[c][4 * q], a[c][4 * q + 1], a[c][4 * q + 2], a[c][4 * q + 3]);
+                if (RES) {
+                    const float4 r = *reinterpret_cast<const float4*>(res + (co + c * CG) * P + p0 + 4 * q);
+                    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+                }
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                *reinterpret_cast<float4*>(out + (co + c * CG) * P + p0 + 4 * q) = v;
             }
-            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-            *reinterpret_cast<float4*>(out + co * P + p0 + 4 * q) = v;
-        }
     }
 }
 
@@ -1167,9 +1183,9 @@ __global__ void __launch_bounds__(256, 2) k_silero_blocks(const float* __restric
         *reinterpret_cast<float2*>(y2e + i * 2) = make_float2(v.x, v.z);
     }
     __syncthreads();
-    mix4_relu<16, 32, F * 2, 8, true, false>(r2, w_b2_pw, wts.b2_pw_b, y2e, w_b2_proj, wts.b2_proj_b, nullptr, z1);
+    mix4_relu<16, 32, F * 2, 8, 2, true, false>(r2, w_b2_pw, wts.b2_pw_b, y2e, w_b2_proj, wts.b2_proj_b, nullptr, z1);
     __syncthreads();
-    mix4_relu<32, 32, F * 2, 8, false, false>(z1, w_b2_down, wts.b2_down_b, nullptr, nullptr, nullptr, nullptr, z2);
+    mix4_relu<32, 32, F * 2, 8, 2, false, false>(z1, w_b2_down, wts.b2_down_b, nullptr, nullptr, nullptr, nullptr, z2);
     __syncthreads();
     // block 3 (32 -> 32 with identity residual, T 2 -> 1): depthwise at t = 0
     for (int i = tid; i < 32 * F; i += 256) {
@@ -1179,9 +1195,9 @@ __global__ void __launch_bounds__(256, 2) k_silero_blocks(const float* __restric
         z2e[i] = v.x;
     }
     __syncthreads();
-    mix4_relu<32, 32, F, 4, false, true>(r3, w_b3_pw, wts.b3_pw_b, nullptr, nullptr, nullptr, z2e, u1);
+    mix4_relu<32, 32, F, 4, 2, false, true>(r3, w_b3_pw, wts.b3_pw_b, nullptr, nullptr, nullptr, z2e, u1);
     __syncthreads();
-    mix4_relu<32, 32, F, 4, false, false>(u1, w_b3_down, wts.b3_down_b, nullptr, nullptr, nullptr, nullptr, u2);
+    mix4_relu<32, 32, F, 4, 2, false, false>(u1, w_b3_down, wts.b3_down_b, nullptr, nullptr, nullptr, nullptr, u2);
     __syncthreads();
     // block 4 (32 -> 64, T 1): the depthwise convolution sees its centre tap only
     for (int i = tid; i < 32 * F; i += 256) {
@@ -1189,25 +1205,33 @@ __global__ void __launch_bounds__(256, 2) k_silero_blocks(const float* __restric
         r4[i] = fmaxf(fmaf(__ldg(wts.b4_dw_w + c * 5 + 2), u2[i], __ldg(wts.b4_dw_b + c)), 0.f);
     }
     __syncthreads();
-    mix4_relu<32, 64, F, 8, true, false>(r4, w_b4_pw, wts.b4_pw_b, u2, w_b4_proj, wts.b4_proj_b, nullptr, v1);
+    mix4_relu<32, 64, F, 8, 2, true, false>(r4, w_b4_pw, wts.b4_pw_b, u2, w_b4_proj, wts.b4_proj_b, nullptr, v1);
     __syncthreads();
-    // final 64 -> 64, ReLU, write [frame][64]: eight frames per thread
-    {
-        const int co = tid & 63, fq = tid >> 6;          // frames fq + 4 e
-        float acc[8];
-        const float bias = __ldg(wts.b4_down_b + co);
+    // final 64 -> 64, ReLU, write [frame][64]: two output channels x eight consecutive frames per thread (128 threads)
+    if (tid < 128) {
+        const int co = tid & 31, f8 = (tid >> 5) * 8;
+        float acc[2][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = bias;
+        for (int c = 0; c < 2; ++c) {
+            const float bias = __ldg(wts.b4_down_b + co + 32 * c);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[c][e] = bias;
+        }
 #pragma unroll 8
         for (int ci = 0; ci < 64; ++ci) {
-            const float w = w_b4_down[ci * 64 + co];
+            const float w0 = w_b4_down[ci * 64 + co], w1 = w_b4_down[ci * 64 + co + 32];
+            const float4 va = *reinterpret_cast<const float4*>(v1 + ci * F + f8), vb = *reinterpret_cast<const float4*>(v1 + ci * F + f8 + 4);
+            const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, v1[ci * F + fq + 4 * e], acc[e]);
+            for (int e = 0; e < 8; ++e) { acc[0][e] = fmaf(w0, v[e], acc[0][e]); acc[1][e] = fmaf(w1, v[e], acc[1][e]); }
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int f = f0 + fq + 4 * e;
-            if (f < n_frames) out[((int64_t)stream * n_frames + f) * 64 + co] = fmaxf(acc[e], 0.f);
+            const int f = f0 + f8 + e;
+            if (f < n_frames) {
+                out[((int64_t)stream * n_frames + f) * 64 + co] = fmaxf(acc[0][e], 0.f);
+                out[((int64_t)stream * n_frames + f) * 64 + co + 32] = fmaxf(acc[1][e], 0.f);
+            }
         }
     }
 }
