@@ -1,8 +1,9 @@
 // Capture front-end on sm_100a (rows a9-a13 of SURVEY.md 8(a)):
-//   k_resample_mma     rubato FftFixedIn (48 -> 16 kHz) as a decimating FIR with the same 1026
-//                      Blackman-Harris^2 sinc taps, run as a Toeplitz GEMM on the tensor cores (3xTF32)
+//   k_resample_poly<D> rubato FftFixedIn (96 / 64 / 48 / 32 -> 16 kHz) as a decimating FIR with the same 1026
+//                      Blackman-Harris^2 sinc taps: D polyphase Toeplitz GEMMs on the f16 tensor cores (3-pass split)
 //                      (reference: audio_toolkit/audio/resampler.rs:24, 51-56; equivalence of the FFT and
-//                      FIR forms: SURVEY.md App. B, ~1e-9; the CUDA-core form of round 1 was removed)
+//                      FIR forms: SURVEY.md App. B, ~1e-9; the CUDA-core and 3xTF32 forms were removed)
+//   k_resample_dense_* every other rate: rubato's block operator as a dense split-precision GEMM (tcgen05)
 //   k_silero_features_fft / _direct   Silero v4 per-frame front: reflect pad, STFT conv, magnitude, log, adaptive
 //                      normalisation, 4 separable conv blocks (reference: vad/silero.rs:41-44 ->
 //                      vad-rs -> onnxruntime; graph first-hand from silero_vad_v4.onnx, App. A).  The shipped
@@ -53,24 +54,8 @@ __global__ void __launch_bounds__(256) k_downmix_mono(const S* __restrict__ in, 
 }
 
 // ------------------------------------------------------------------------------------------
-// The same FIR on the tensor cores.  16 consecutive outputs m0+16n .. m0+16n+15 are one GEMM column block:
-//   y[m0 + 16 n + i] = sum_j A[i][j] * B[j][n],   A[i][j] = h[(T-1) + D i - j]  (0 outside [0, T)),
-//                                                B[j][n] = x[D (m0 + 16 n) - (T-1) + j],   j in [0, T + 15 D)
-// A is a constant 16 x (T + 15 D) Toeplitz expansion of the taps (4 % more MACs than the direct form at D = 3), B is a
-// sliding window over ONE contiguous input segment (column n starts 16 D samples after column n-1), so both operands
-// are built from shared memory with index arithmetic only.  mma.sync.m16n8k8 TF32 with the 3-pass split
-// (a_hi b_hi + a_hi b_lo + a_lo b_hi, hi = cvt.rna.tf32, lo = the exact f32 remainder): products are exact to ~2^-21,
-// accumulation is f32 -- the result stays within the 1e-5 parity bound of the f64 rubato restatement.
-// CTA = 256 threads, 2048 outputs (128 column blocks = 16 n-tiles, two per warp) of one stream.
+// TF32 mma.sync helpers (block-1 pointwise product of the Silero front)
 // ------------------------------------------------------------------------------------------
-constexpr int kRmBlocks = 128;                    // 16-output column blocks per CTA
-constexpr int kRmTile = 16 * kRmBlocks;           // outputs per CTA
-
-__device__ __forceinline__ uint32_t tf32_hi(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = tf32_hi(x);
-    lo = tf32_hi(x - __uint_as_float(hi));
-}
 // cheap split for operands whose partner is split exactly: hi = the top 10 mantissa bits (truncated), lo = the exact
 // remainder, of which the tensor core reads the top 10 bits again: 2^-21 relative, two instructions (cvt.rna.tf32 is
 // emulated with four on sm_100)
@@ -84,78 +69,8 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(256) k_resample_mma(const float* __restrict__ x, int64_t x_stride, int n_in,
-                                                      float* __restrict__ y, int64_t y_stride, int n_out,
-                                                      const float* __restrict__ h, int T, int D, int Kp) {
-    extern __shared__ float s_rm[];
-    const int hp_pad = Kp;                                  // hp[idx + hp_pad] = h[idx], zero outside [0, T)
-    const int hp_len = T + 15 * D + Kp + 8;
-    float* hp = s_rm;
-    float* xs = s_rm + ((hp_len + 3) & ~3);                 // input segment: Kp + 16 D (kRmBlocks - 1) samples
-    const int seg = Kp + 16 * D * (kRmBlocks - 1);
-    const int stream = blockIdx.y;
-    const int m0 = blockIdx.x * kRmTile;
-    const float* xin = x + (int64_t)stream * x_stride;
-    for (int i = threadIdx.x; i < hp_len; i += 256) {
-        const int idx = i - hp_pad;
-        hp[i] = (idx >= 0 && idx < T) ? __ldg(h + idx) : 0.0f;
-    }
-    const int64_t base0 = (int64_t)D * m0 - (T - 1);
-    for (int i = threadIdx.x; i < seg; i += 256) {
-        const int64_t src = base0 + i;
-        xs[i] = (src >= 0 && src < n_in) ? __ldg(xin + src) : 0.0f;
-    }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, t = lane & 3;
-    float acc[2][4];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) { acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f; }
-    // A[i][j] = hp[hp_pad + (T-1) + D i - j]; rows g and g + 8, columns 8 s + t and 8 s + t + 4
-    const float* ha = hp + hp_pad + (T - 1) + D * g - t;
-    const float* hb = ha + 8 * D;
-    // B[j][n] = xs[j + 16 D n]; this warp's n-tiles: 2 warp and 2 warp + 1 (columns 8 nt + g)
-    const float* xb0 = xs + 16 * D * (8 * (2 * warp) + g) + t;
-    const float* xb1 = xb0 + 16 * D * 8;
-    const int n_steps = Kp >> 3;
-#pragma unroll 2
-    for (int sI = 0; sI < n_steps; ++sI) {
-        const int j = 8 * sI;
-        uint32_t ah[4], al[4];
-        split_tf32(ha[-j], ah[0], al[0]);
-        split_tf32(hb[-j], ah[1], al[1]);
-        split_tf32(ha[-j - 4], ah[2], al[2]);
-        split_tf32(hb[-j - 4], ah[3], al[3]);
-        uint32_t bh0, bl0, bh1, bl1;
-        split_tf32(xb0[j], bh0, bl0);
-        split_tf32(xb0[j + 4], bh1, bl1);
-        mma_tf32(acc[0], ah, bh0, bh1);
-        mma_tf32(acc[0], ah, bl0, bl1);
-        mma_tf32(acc[0], al, bh0, bh1);
-        split_tf32(xb1[j], bh0, bl0);
-        split_tf32(xb1[j + 4], bh1, bl1);
-        mma_tf32(acc[1], ah, bh0, bh1);
-        mma_tf32(acc[1], ah, bl0, bl1);
-        mma_tf32(acc[1], al, bh0, bh1);
-    }
-    // C[i][n]: c0 (g, 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)  ->  output m0 + 16 n + i
-    float* yo = y + (int64_t)stream * y_stride;
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int nt = 2 * warp + u;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int n = 8 * nt + 2 * t + (e & 1);
-            const int i = g + ((e >> 1) << 3);
-            const int m = m0 + 16 * n + i;
-            if (m < n_out) yo[m] = acc[u][e];
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------
-// The decimating FIR as D polyphase branches on the f16 tensor cores (the shipped path; k_resample_mma above is kept as the
-// TF32 reference form, SB_RESAMPLE_TF32=1).
+// The decimating FIR as D polyphase branches on the f16 tensor cores (the 3xTF32 Toeplitz form it replaced was removed: 26.1 ms per 1000 streams, 3.1e-6).
 //   y[m] = sum_u h[u] x[D m - u] = sum_p sum_q h[D q + p] x_p[m - q],   x_p[r] = x[D r - p],  q < Q = ceil(T / D)
 // Each branch is a stride-1 convolution, i.e. a Toeplitz GEMM over 32 consecutive outputs per column:
 //   A_p[i][j] = h_p[Q - 1 + i - j]  (32 x (Q + 31), constant),   B_p[j][n] = x_p[m0 + 32 n - (Q - 1) + j]  (a sliding window).
@@ -1437,10 +1352,8 @@ __global__ void __launch_bounds__(128) k_vad_compact(const float* __restrict__ p
 // ------------------------------------------------------------------------------------------
 struct sb_resampler {
     int fs_in = 0, fs_out = 0, decim = 1, n_taps = 0, fft_in = 0, fft_out = 0;
-    float* d_h = nullptr;
     uint4* d_afrag = nullptr;      // polyphase A fragments, f16 hi | lo: [D][SP + 1][32 lanes][2]
     int Q = 0, SP = 0;             // taps per branch, k-steps per branch
-    bool tf32_form = false;        // SB_RESAMPLE_TF32=1: the 3xTF32 Toeplitz kernel instead of the f16 polyphase one
     // rational ratios: the block operator as a dense GEMM (k_resample_dense_*)
     bool dense = false;
     int N1 = 0, N2 = 0, Kp = 0;
@@ -1534,8 +1447,6 @@ int sb_resampler_create(int fs_in, int fs_out, sb_resampler** out) {
         }
         std::vector<float> hf(N);
         for (int x = 0; x < N; ++x) hf[x] = (float)(h[x] / sum);
-        SB_CUDA_CHECK(cudaMalloc(&r->d_h, N * sizeof(float)));
-        SB_CUDA_CHECK(cudaMemcpy(r->d_h, hf.data(), N * sizeof(float), cudaMemcpyHostToDevice));
         // polyphase A fragments: A_p[i][j] = 2^12 h[D (Q - 1 + i - j) + p], m16n8k16 layout (a0a1: row g, k 2t..; a2a3: row g + 8;
         // a4a5: row g, k 2t + 8..; a6a7: row g + 8), split hi = f16(v) | lo = f16(v - hi)
         const int D = a, Q = (N + D - 1) / D, SP = (Q + 15 + 15) / 16;
@@ -1566,8 +1477,6 @@ int sb_resampler_create(int fs_in, int fs_out, sb_resampler** out) {
                 }
         SB_CUDA_CHECK(cudaMalloc(&r->d_afrag, fr.size() * sizeof(uint32_t)));
         SB_CUDA_CHECK(cudaMemcpy(r->d_afrag, fr.data(), fr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        const char* force = getenv("SB_RESAMPLE_TF32");
-        r->tf32_form = force && force[0] == '1';
     }
     *out = r;
     return SB_OK;
@@ -1575,7 +1484,7 @@ int sb_resampler_create(int fs_in, int fs_out, sb_resampler** out) {
 
 int sb_resampler_destroy(sb_resampler* r) {
     if (!r) return SB_OK;
-    cudaFree(r->d_h); cudaFree(r->d_afrag); cudaFree(r->d_whi); cudaFree(r->d_wlo); cudaFree(r->d_ws);
+    cudaFree(r->d_afrag); cudaFree(r->d_whi); cudaFree(r->d_wlo); cudaFree(r->d_ws);
     delete r;
     return SB_OK;
 }
@@ -1641,7 +1550,7 @@ int sb_resample_dev(const sb_resampler* r, const float* in, int64_t in_stride, s
         return SB_OK;
     }
     const int D = r->decim;
-    if (!r->tf32_form) {
+    {
         const size_t smem = (size_t)2 * D * sb::rp_array_len(r->SP) * sizeof(__half);
         SB_CHECK_ARG((uint64_t)D * (n_out + sb::kRpTile + 16 * r->SP) < (1ull << 31), "resampler: stream too long for 32-bit sample indices");
         SB_CHECK_ARG(smem <= 200 * 1024, "resampler: filter too long for the shared-memory segment");
@@ -1660,19 +1569,6 @@ int sb_resample_dev(const sb_resampler* r, const float* in, int64_t in_stride, s
             default: SB_RP_LAUNCH(6); break;     // sb_resampler_create admits 2, 3, 4, 6 only
         }
 #undef SB_RP_LAUNCH
-        sb::g_launches += 1;
-        SB_CUDA_CHECK(cudaGetLastError());
-        return SB_OK;
-    }
-    {
-        // 3xTF32 Toeplitz form (k_resample_mma)
-        const int T = r->n_taps;
-        const int Kp = (T + 15 * D + 7) & ~7;
-        const size_t smem = (size_t)(((T + 15 * D + Kp + 8 + 3) & ~3) + Kp + 16 * D * (sb::kRmBlocks - 1)) * sizeof(float);
-        SB_CHECK_ARG(smem <= 200 * 1024, "resampler: filter too long for the shared-memory segment");
-        SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(sb::k_resample_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); });
-        dim3 grid((unsigned)((n_out + sb::kRmTile - 1) / sb::kRmTile), n_streams);
-        sb::k_resample_mma<<<grid, 256, smem, st>>>(in, in_stride, (int)n_in, out, out_stride, (int)n_out, r->d_h, T, D, Kp);
         sb::g_launches += 1;
         SB_CUDA_CHECK(cudaGetLastError());
         return SB_OK;

@@ -12,9 +12,9 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SILERO = os.path.join(GOLD, "silero_v4_16k.npz")
 
 # max abs error vs the f64 rubato restatement.  SURVEY 8(d) proposed 1e-5; measured on B200 in round 2: 1.7e-6 for the shipped
-# polyphase f16 (3-pass) kernel, 3.1e-6 for the 3xTF32 Toeplitz form it replaced -- the stated tolerance is 3x the former.
+# polyphase f16 (3-pass) kernel (3.1e-6 for the 3xTF32 Toeplitz form it replaced), 1.2e-6 for the dense block operator of the
+# non-integer ratios -- the stated tolerance is 3x the largest.
 RESAMPLE_TOL = 5e-6
-RESAMPLE_TF32_TOL = 1e-5
 # max abs error on the speech probability vs the f64 oracle on identical input; decisions (prob > 0.3) must be identical
 # outside it.  The shipped path evaluates the STFT as f64 FFTs plus the exact residual of the stored basis (frontend.cu):
 # measured 1.9e-6 (round 1's f32 convolution: ~1.1e-4, tolerance 3e-4, because log(1 + 2^20 |X|) magnifies the round-off
@@ -65,9 +65,8 @@ def test_resampler_rational_ratios(cuda_dev):
         assert got[s_].shape == ref.shape and np.abs(got[s_] - ref).max() <= RESAMPLE_TOL
 
 
-def test_resampler_other_ratios_and_tf32_form(cuda_dev, monkeypatch):
-    """The polyphase f16 kernel at decimation 2, 4 and 6 (32 / 64 / 96 kHz capture devices), and the 3xTF32 Toeplitz
-    form (SB_RESAMPLE_TF32=1) that it replaced, both against the f64 rubato restatement."""
+def test_resampler_other_integer_ratios(cuda_dev):
+    """The polyphase f16 kernel at decimation 2, 4 and 6 (32 / 64 / 96 kHz capture devices) against the f64 rubato restatement."""
     for fs in (32000, 64000, 96000):
         x = np.stack([synth.make_clip(30 + i, seconds=1.5, sr=fs, kind=k) for i, k in enumerate(["vowel", "noise"])])
         got = audio_toolkit.FrameResampler(fs, 16000).process(x).cpu().numpy()
@@ -77,13 +76,6 @@ def test_resampler_other_ratios_and_tf32_form(cuda_dev, monkeypatch):
             err = np.abs(got[s_] - ref).max()
             print(f"resample {fs} -> 16000: max err {err:.2e}")
             assert err <= RESAMPLE_TOL, (fs, err)
-    x = np.stack([synth.make_clip(33, seconds=2.0, sr=48000, kind="mix")])
-    ref = resample.frame_resampler(x[0])
-    poly = audio_toolkit.FrameResampler(48000, 16000).process(x).cpu().numpy()[0]
-    monkeypatch.setenv("SB_RESAMPLE_TF32", "1")
-    tf32 = audio_toolkit.FrameResampler(48000, 16000).process(x).cpu().numpy()[0]
-    print(f"48000 -> 16000: polyphase f16 {np.abs(poly - ref).max():.2e}, 3xTF32 {np.abs(tf32 - ref).max():.2e}")
-    assert np.abs(poly - ref).max() <= RESAMPLE_TOL and np.abs(tf32 - ref).max() <= RESAMPLE_TF32_TOL
 
 
 def test_resampler_properties_full_size(cuda_dev):
