@@ -317,22 +317,6 @@ __device__ void dw5_relu(const float* in, float* out, const float* w, const floa
         out[i] = fmaxf(a, 0.f);
     }
 }
-// the same for tiles of F frames
-template <int F>
-__device__ __forceinline__ void dw5_relu_f(const float* in, float* out, const float* __restrict__ w, const float* __restrict__ b, int C, int T) {
-    const int total = C * F * T;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int c = i / (F * T), rem = i - c * F * T;
-        const int t = rem % T;
-        float a = __ldg(b + c);
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const int tt = t + k - 2;
-            if (tt >= 0 && tt < T) a = fmaf(__ldg(w + c * 5 + k), in[i + k - 2], a);
-        }
-        out[i] = fmaxf(a, 0.f);
-    }
-}
 // pointwise: out[co][f][t] = relu( W1[co,:] . in1[:,f,t] + b1 (+ W2[co,:] . in2[:,f,t] + b2) (+ res[co][f][t]) )
 __device__ void pw_relu(const float* in1, const float* w1, const float* b1, const float* in2, const float* w2,
                         const float* b2, const float* res, float* out, int Cin, int Cout, int T) {
