@@ -158,6 +158,24 @@ def test_silero_direct_convolution_path(cuda_dev, monkeypatch):
         assert np.abs(got[s_] - ref).max() <= SILERO_DIRECT_TOL
 
 
+def test_frontend_is_deterministic(cuda_dev):
+    """Same input, same bits: the tensor-core resampler (48 k polyphase, 44.1 k dense), the Silero front (f64 FFT exchange, partial
+    tiles summed in a fixed order) and the tensor-core LSTM are run three times each -- a shared-memory race or an order-dependent
+    reduction would show as differing bits (compute-sanitizer is not available on the GPU pool)."""
+    import torch
+    x48 = np.stack([synth.make_clip(70 + i, seconds=3.0, sr=48000, kind=k) for i, k in enumerate(["vowel", "noise", "mix", "tone", "chirp"])])
+    x44 = np.stack([synth.make_clip(75 + i, seconds=3.0, sr=44100, kind=k) for i, k in enumerate(["vowel", "noise", "mix"])])
+    rs48, rs44 = audio_toolkit.FrameResampler(48000), audio_toolkit.FrameResampler(44100)
+    f0 = rs48.process(x48)
+    g0 = rs44.process(x44)
+    sv = audio_toolkit.SileroVad(SILERO, 0.3)
+    p0 = sv.score(f0)
+    for _ in range(2):
+        assert torch.equal(rs48.process(x48), f0) and torch.equal(rs44.process(x44), g0)
+        sv.reset()
+        assert torch.equal(sv.score(f0), p0)
+
+
 def test_gate_is_bit_exact(cuda_dev):
     import torch
     vad = audio_toolkit.SileroVad(SILERO, 0.3)
