@@ -5,6 +5,7 @@
   LDTM/STTM tcgen05.ld / tcgen05.st (TMEM)        UTCBAR   tcgen05.commit -> mbarrier
   SYNCS     mbarrier arrive / try_wait            HMMA     legacy mma.sync (decoder-step kernels)
   UTCATOMSWS tcgen05.alloc / dealloc              UCGABAR  cluster barrier (cta_group::2 pairs)
+  LDSM      ldmatrix (B operands of the front-end)  DFMA   fp64 FMA (Silero f64 FFT, resampler operator build)
 
 Usage: python tools/sass_census.py > profiles/r2_sass_census.md   (needs cuobjdump; no GPU)
 """
@@ -16,7 +17,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "spittle_b200", "libspittle_b200.so")
-COLS = ["UTCHMMA", "UTMALDG", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "SYNCS", "UCGABAR", "HMMA", "MUFU", "LDGSTS", "total"]
+COLS = ["UTCHMMA", "UTMALDG", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "SYNCS", "UCGABAR", "HMMA", "LDSM", "DFMA", "MUFU", "LDGSTS", "total"]
 
 
 def demangle(names):
@@ -62,7 +63,9 @@ def main():
     print("\n`wgmma` (sm_90a) does not exist in this binary; the tensor-core work of the encoder (`k_gemm_tn`, `k_attn_enc_ts`) is")
     print("UTCHMMA = `tcgen05.mma` with TMEM accumulators (LDTM / STTM) fed by TMA (UTMALDG); the HMMA counts belong to the")
     print("decoder-step weight-streaming kernels (`k_skinny_gemm*`, `k_dec_cross_attn`: M = 16-row weight tiles against <= 64")
-    print("sequences, HBM-bound) and to the 3xTF32 resampler.")
+    print("sequences, HBM-bound) and to the capture front-end (`k_resample_poly`: f16 3-pass polyphase Toeplitz GEMM; `k_silero_features_fft`:")
+    print("bf16 residual of the STFT basis + 3xTF32 block-1 product next to its f64 FFT (DFMA); `k_silero_lstm`: f16 3-pass recurrent product),")
+    print("with LDSM = `ldmatrix` feeding their B operands.")
 
 
 if __name__ == "__main__":
