@@ -255,6 +255,9 @@ typedef struct sb_params {
     float temperature_inc;
     float logprob_thold;
     float entropy_thold;
+    int suppress_nst;            /* whisper_full_params.suppress_nst (transcribe-rs: suppress_non_speech_tokens): the non-speech symbol
+                                    tokens of whisper.cpp's list (quotes, brackets, music notes ..., with and without a leading
+                                    space, plus " -" and " '") get -inf in whisper_process_logits.  whisper.cpp's default is off */
 } sb_params;
 
 typedef struct sb_window_info {

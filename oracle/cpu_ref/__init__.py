@@ -33,7 +33,8 @@ def build(force: bool = False) -> str:
 class _Cfg(C.Structure):
     _fields_ = [("language_id", C.c_int), ("translate", C.c_int), ("no_timestamps", C.c_int), ("suppress_blank", C.c_int),
                 ("single_segment", C.c_int), ("max_initial_ts", C.c_float), ("n_max_override", C.c_int),
-                ("n_max_text_ctx", C.c_int), ("initial_prompt", C.POINTER(C.c_int32)), ("n_initial_prompt", C.c_int)]
+                ("n_max_text_ctx", C.c_int), ("initial_prompt", C.POINTER(C.c_int32)), ("n_initial_prompt", C.c_int),
+                ("suppress_nst", C.c_int)]
 
 
 class _Window(C.Structure):
@@ -68,10 +69,11 @@ def lib():
 
 
 def _cfg(language_id=0, translate=False, no_timestamps=False, suppress_blank=True, single_segment=False, max_initial_ts=1.0,
-         n_max_override=None, n_max_text_ctx=16384, initial_prompt_tokens: Optional[Sequence[int]] = None):
+         n_max_override=None, n_max_text_ctx=16384, initial_prompt_tokens: Optional[Sequence[int]] = None, suppress_nst=False):
     ip = np.ascontiguousarray(initial_prompt_tokens if initial_prompt_tokens is not None else [], np.int32)
     c = _Cfg(language_id, int(translate), int(no_timestamps), int(suppress_blank), int(single_segment), max_initial_ts,
-             n_max_override or 0, n_max_text_ctx, ip.ctypes.data_as(C.POINTER(C.c_int32)) if ip.size else None, int(ip.size))
+             n_max_override or 0, n_max_text_ctx, ip.ctypes.data_as(C.POINTER(C.c_int32)) if ip.size else None, int(ip.size),
+             int(suppress_nst))
     return c, ip          # keep ip alive
 
 

@@ -34,6 +34,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <unordered_map>
 
 // ------------------------------------------------------------------------------------------------------------
 // SIMD kernels, two instruction sets
@@ -225,6 +226,7 @@ struct wcr_model {
     Special sp{};
     std::vector<float> mel_filters;       // [n_mel][201]
     std::vector<std::string> vocab;
+    std::vector<int> nst_ids;             // whisper.cpp's non_speech_tokens present in this vocabulary (suppress_nst)
     Lin conv1, conv2;                     // [d][3*n_mel], [d][3*d] (tap-major columns)
     std::vector<float> enc_pos, dec_pos;
     std::vector<EncLayer> enc;
@@ -575,6 +577,7 @@ struct wcr_cfg {
     int n_max_override;       // <= 0: n_text_ctx/2 - 4
     int n_max_text_ctx;       // whisper_full_params.n_max_text_ctx (16384); <= 0: no text context
     const int32_t* initial_prompt; int n_initial_prompt;
+    int suppress_nst;         // whisper_full_params.suppress_nst: the non-speech tokens get -inf
 };
 struct wcr_window { int32_t seek, n_tokens, result_len, seek_delta, failed, token_offset, n_prompt; };
 
@@ -634,6 +637,20 @@ int wcr_load(const char* path, wcr_model** out) {
     }
     s.lang_first = s.sot + 1;
     for (size_t i = 0; i < m->vocab.size(); ++i) if (m->vocab[i] == " ") { s.blank = (int)i; break; }
+    {
+        // whisper.cpp non_speech_tokens (= OpenAI tokenizer.non_speech_tokens), with and without a leading space, plus " -" and " '"
+        static const char* const kList[] = {
+            "\"", "#", "(", ")", "*", "+", "/", ":", ";", "<", "=", ">", "@", "[", "\\", "]", "^", "_", "`", "{", "|", "}", "~",
+            "\xe3\x80\x8c", "\xe3\x80\x8d", "\xe3\x80\x8e", "\xe3\x80\x8f",
+            "<<", ">>", "<<<", ">>>", "--", "---", "-(", "-[", "('", "(\"", "((", "))", "(((", ")))", "[[", "]]", "{{", "}}",
+            "\xe2\x99\xaa\xe2\x99\xaa", "\xe2\x99\xaa\xe2\x99\xaa\xe2\x99\xaa",
+            "\xe2\x99\xa9", "\xe2\x99\xaa", "\xe2\x99\xab", "\xe2\x99\xac", "\xe2\x99\xad", "\xe2\x99\xae", "\xe2\x99\xaf"};
+        std::unordered_map<std::string, int> t2i;
+        for (int i = 0; i < (int)m->vocab.size(); ++i) t2i[m->vocab[i]] = i;
+        auto add = [&](const std::string& w) { auto f = t2i.find(w); if (f != t2i.end()) m->nst_ids.push_back(f->second); };
+        for (const char* t : kList) { add(t); add(std::string(" ") + t); }
+        add(" -"); add(" '");
+    }
     m->sp = s;
     bool ok = load_conv(T, "encoder.conv1", d, h.n_mels, m->conv1, err) && load_conv(T, "encoder.conv2", d, d, m->conv2, err);
     if (ok) { auto it = T.find("encoder.positional_embedding"); ok = it != T.end() && to_f32(it->second, m->enc_pos); if (!ok) err = "encoder.positional_embedding"; }
@@ -780,6 +797,7 @@ static int process_and_sample(const wcr_model& m, const wcr_cfg& cfg, std::vecto
     const float NEG = -INFINITY;
     const bool is_initial = tokens_cur.empty();
     if (cfg.suppress_blank && is_initial) { lg[sp.eot] = NEG; lg[sp.blank] = NEG; }
+    if (cfg.suppress_nst) for (int id : m.nst_ids) lg[id] = NEG;
     lg[sp.not_] = NEG;
     if (cfg.no_timestamps) for (int i = sp.beg; i < n; ++i) lg[i] = NEG;
     lg[sp.sot] = NEG; lg[sp.nosp] = NEG; lg[sp.solm] = NEG; lg[sp.translate] = NEG; lg[sp.transcribe] = NEG; lg[sp.prev] = NEG;

@@ -89,6 +89,30 @@ class DecodeConfig:
     temperature_inc: float = 0.0
     logprob_thold: float = -1.0
     entropy_thold: float = 2.4
+    # whisper_full_params.suppress_nst [MEM]: whisper_process_logits sets the tokens of `non_speech_tokens` (with and without a
+    # leading space) and " -", " '" to -inf.  whisper.cpp's default is false; transcribe-rs exposes it as suppress_non_speech_tokens.
+    suppress_nst: bool = False
+
+
+# whisper.cpp `non_speech_tokens` = OpenAI tokenizer.non_speech_tokens: symbols, bracket / dash runs, music notes
+NON_SPEECH_TOKENS = (list('"#()*+/:;<=>@[\\]^_`{|}~\u300c\u300d\u300e\u300f')
+                     + "<< >> <<< >>> -- --- -( -[ (' (\" (( )) ((( ))) [[ ]] {{ }} \u266a\u266a \u266a\u266a\u266a".split()
+                     + list("\u2669\u266a\u266b\u266c\u266d\u266e\u266f"))
+
+
+def non_speech_token_ids(vocab) -> List[int]:
+    """ids of the listed strings in this vocabulary (id -> bytes; the last id of a duplicate wins, like the loader's map)."""
+    t2i = {bytes(w): i for i, w in enumerate(vocab)}
+    ids = set()
+    for t in NON_SPEECH_TOKENS:
+        for cand in (t, " " + t):
+            i = t2i.get(cand.encode("utf-8"))
+            if i is not None:
+                ids.add(i)
+    for cand in (b" -", b" '"):
+        if cand in t2i:
+            ids.add(t2i[cand])
+    return sorted(ids)
 
 
 @dataclass
@@ -119,6 +143,7 @@ class WhisperOracle:
         self.act_f16 = act_f16
         self.t = {k: v.astype(F32) for k, v in model.tensors.items()}
         self._r = _h if act_f16 else (lambda x: x.astype(F32))
+        self.nst_ids = np.asarray(non_speech_token_ids(model.vocab), np.int64)
 
     # -- building blocks ---------------------------------------------------------------
     def _mm(self, x: np.ndarray, wname: str, bname: Optional[str] = None) -> np.ndarray:
@@ -251,6 +276,8 @@ class WhisperOracle:
         if cfg.suppress_blank and is_initial:
             lg[sp.eot] = NEG
             lg[sp.blank] = NEG
+        if cfg.suppress_nst and self.nst_ids.size:
+            lg[self.nst_ids] = NEG
         lg[sp.not_] = NEG
         if cfg.no_timestamps:
             lg[sp.beg:] = NEG

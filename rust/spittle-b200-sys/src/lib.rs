@@ -40,6 +40,7 @@ pub struct sb_params {
     pub temperature_inc: c_float,       // 0 = no temperature fallback (sb_params_default)
     pub logprob_thold: c_float,
     pub entropy_thold: c_float,
+    pub suppress_nst: c_int,            // whisper_full_params.suppress_nst (transcribe-rs: suppress_non_speech_tokens); default 0
 }
 
 #[repr(C)]
@@ -83,6 +84,7 @@ const _: () = assert!(size_of::<sb_params>() == 72);
 const _: () = assert!(offset_of!(sb_params, initial_prompt) == 16);
 const _: () = assert!(offset_of!(sb_params, max_initial_ts) == 36);
 const _: () = assert!(offset_of!(sb_params, n_max_text_ctx) == 48);
+const _: () = assert!(offset_of!(sb_params, suppress_nst) == 68);
 const _: () = assert!(size_of::<sb_window_info>() == 40);
 const _: () = assert!(offset_of!(sb_window_info, n_prompt) == 24);
 const _: () = assert!(size_of::<sb_segment>() == 40);

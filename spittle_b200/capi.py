@@ -139,7 +139,7 @@ class SbParams(C.Structure):
                 ("no_timestamps", C.c_int), ("suppress_blank", C.c_int), ("single_segment", C.c_int),
                 ("max_initial_ts", C.c_float), ("n_max_tokens", C.c_int), ("max_windows", C.c_int),
                 ("n_max_text_ctx", C.c_int), ("temperature", C.c_float), ("temperature_inc", C.c_float),
-                ("logprob_thold", C.c_float), ("entropy_thold", C.c_float)]
+                ("logprob_thold", C.c_float), ("entropy_thold", C.c_float), ("suppress_nst", C.c_int)]
 
 
 class SbStats(C.Structure):

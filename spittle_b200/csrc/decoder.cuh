@@ -56,6 +56,9 @@ struct SamplerArgs {
     // std::discrete_distribution over std::mt19937); null / 0 -> greedy
     const float* temperature; // [B] or null
     const double* rng_u;      // [B][n_max] or null
+    // suppress_nst: ids of the non-speech tokens (device) that get -inf before every other rule, or null
+    const int* nst_ids;
+    int n_nst;
 };
 
 struct SkinnyEpilogue {

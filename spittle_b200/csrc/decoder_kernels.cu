@@ -289,6 +289,7 @@ struct LogitMask {
 struct Lse {
     float m, s;
     __device__ __forceinline__ void add(float x) {
+        if (x == -INFINITY) return;                       // a suppressed (non-speech) text token
         if (x > m) { s = s * __expf(m - x) + 1.0f; m = x; }
         else s += __expf(x - m);
     }
@@ -346,6 +347,10 @@ __global__ void __launch_bounds__(kSampThreads) k_logits_filter_argmax(const flo
     const float temp = a.temperature ? __ldcg(a.temperature + b) : 0.f;
     if (temp > 0.f) {                  // whisper_process_logits: logits[i] /= temperature, before every rule
         for (int i = threadIdx.x; i < V; i += kSampThreads) s_row[i] = s_row[i] / temp;
+        __syncthreads();
+    }
+    if (a.nst_ids) {                   // whisper_process_logits, suppress_nst: logits[id] = -INFINITY
+        for (int i = threadIdx.x; i < a.n_nst; i += kSampThreads) s_row[__ldg(a.nst_ids + i)] = -INFINITY;
         __syncthreads();
     }
     const float* lg = s_row;

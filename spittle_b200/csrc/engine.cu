@@ -173,6 +173,27 @@ struct EngineBase {
     }
 };
 
+// whisper.cpp's `non_speech_tokens` (the list of OpenAI's tokenizer.non_speech_tokens) as ids of THIS vocabulary: every listed
+// string with and without a leading space, plus " -" and " '" ("allow hyphens and single quotes between words, but not at the
+// beginning of a word"); whisper_process_logits sets them to -inf when params.suppress_nst is on.  Ascending, unique.
+static std::vector<int> non_speech_token_ids(const std::vector<std::string>& vocab) {
+    static const char* const kList[] = {
+        "\"", "#", "(", ")", "*", "+", "/", ":", ";", "<", "=", ">", "@", "[", "\\", "]", "^", "_", "`", "{", "|", "}", "~",
+        "\xe3\x80\x8c", "\xe3\x80\x8d", "\xe3\x80\x8e", "\xe3\x80\x8f",                       // corner brackets
+        "<<", ">>", "<<<", ">>>", "--", "---", "-(", "-[", "('", "(\"", "((", "))", "(((", ")))", "[[", "]]", "{{", "}}",
+        "\xe2\x99\xaa\xe2\x99\xaa", "\xe2\x99\xaa\xe2\x99\xaa\xe2\x99\xaa",                 // two / three eighth notes
+        "\xe2\x99\xa9", "\xe2\x99\xaa", "\xe2\x99\xab", "\xe2\x99\xac", "\xe2\x99\xad", "\xe2\x99\xae", "\xe2\x99\xaf"};
+    std::unordered_map<std::string, int> t2i;
+    for (int i = 0; i < (int)vocab.size(); ++i) t2i[vocab[i]] = i;        // last id of a duplicate, like the loader
+    std::vector<int> ids;
+    auto add = [&](const std::string& s) { auto f = t2i.find(s); if (f != t2i.end()) ids.push_back(f->second); };
+    for (const char* t : kList) { add(t); add(std::string(" ") + t); }
+    add(" -"); add(" '");
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    return ids;
+}
+
 static SpecialIds special_from_vocab(int n_vocab, const std::vector<std::string>& vocab) {
     SpecialIds s{50256, 50257, 50357, 50358, 50359, 50360, 50361, 50362, 50363, 0, 0, 220};
     // whisper.cpp: num_languages = n_vocab - 51765 - (multilingual ? 1 : 0); English-only vocabularies keep the 99 language
@@ -213,6 +234,8 @@ struct Engine : EngineBase {
     DevBuf b_col1, b_c1, b_x, b_h, b_qkv, b_att, b_mlp, b_enc32;
     DevBuf b_ckv, b_kself, b_vself, b_dx, b_dh, b_dqkv, b_datt, b_dq, b_dmlp, b_logits;
     DevBuf b_state, b_tokens, b_margins, b_tids, b_plogs, b_next, b_forced, b_tick, b_prompt, b_lang, b_init, b_prow, b_temp, b_rng;
+    DevBuf b_nst;                 // ids of whisper.cpp's non-speech tokens present in this vocabulary (suppress_nst)
+    int n_nst = 0;
     PinBuf h_state, h_tokens, h_margins, h_tids, h_plogs, h_lang, h_init, h_winmeta, h_prow, h_rng;   // host mirrors polled once per burst / slot-init staging
     // profile == 2: device-side launch trace of the decoder step (TraceSlot, common.cuh)
     DevBuf b_trace;
@@ -306,7 +329,7 @@ struct Engine : EngineBase {
         DevBuf* bufs[] = {&b_pcm, &b_mel, &b_cmax, &b_floor, &b_clipmeta, &b_winmeta, &b_col1, &b_c1, &b_x, &b_h, &b_qkv,
                           &b_att, &b_mlp, &b_enc32, &b_ckv, &b_kself, &b_vself, &b_dx, &b_dh, &b_dqkv, &b_datt, &b_dq,
                           &b_dmlp, &b_logits, &b_state, &b_tokens, &b_margins, &b_tids, &b_next, &b_forced, &b_tick, &b_prompt,
-                          &b_lang, &b_init, &b_trace, &b_prow, &b_plogs, &b_temp, &b_rng, &b_pcmptr};
+                          &b_lang, &b_init, &b_trace, &b_prow, &b_plogs, &b_temp, &b_rng, &b_pcmptr, &b_nst};
         for (DevBuf* b : bufs) b->release();
         PinBuf* pins[] = {&h_state, &h_tokens, &h_margins, &h_tids, &h_lang, &h_init, &h_winmeta, &h_prow, &h_plogs, &h_rng};
         for (PinBuf* b : pins) b->release();
@@ -412,6 +435,15 @@ struct Engine : EngineBase {
         SB_CHECK_ARG(hp.n_audio_ctx == 1500, "n_audio_ctx must be 1500");
         SB_CHECK_ARG(hp.n_text_ctx <= 448, "n_text_ctx must be <= 448");
         SB_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        {
+            const std::vector<int> ids = non_speech_token_ids(vocab);
+            n_nst = (int)ids.size();
+            if (n_nst) {
+                int rc = b_nst.ensure(ids.size() * sizeof(int));
+                if (rc) return rc;
+                SB_CUDA_CHECK(cudaMemcpy(b_nst.p, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice));
+            }
+        }
         for (auto& e : ev) SB_CUDA_CHECK(cudaEventCreate(&e));
         for (auto& l : lanes) {
             SB_CUDA_CHECK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
@@ -690,9 +722,12 @@ struct Engine : EngineBase {
         sa0.sp = sp; sa0.n_vocab = hp.n_vocab; sa0.n_max = n_max; sa0.n_text_ctx = hp.n_text_ctx;
         sa0.suppress_blank = p.suppress_blank; sa0.no_timestamps = p.no_timestamps; sa0.single_segment = p.single_segment;
         sa0.max_initial_tid = p.max_initial_ts > 0.f ? (int)lroundf(p.max_initial_ts / (30.0f / hp.n_audio_ctx)) : -1;
+        sa0.nst_ids = (p.suppress_nst && n_nst > 0) ? b_nst.as<int>() : nullptr;
+        sa0.n_nst = n_nst;
         dcfg.sa0 = sa0; dcfg.has_forced = has_forced; dcfg.graph = want_graph; dcfg.honor_done = !has_forced;
         const bool tracing = profile == 2 && want_graph;
-        dcfg.flags = (p.suppress_blank ? 1 : 0) | (p.no_timestamps ? 2 : 0) | (p.single_segment ? 4 : 0) | (detect_lang ? 8 : 0) | (tracing ? 16 : 0);
+        dcfg.flags = (p.suppress_blank ? 1 : 0) | (p.no_timestamps ? 2 : 0) | (p.single_segment ? 4 : 0) | (detect_lang ? 8 : 0) | (tracing ? 16 : 0) |
+                     (p.suppress_nst ? 32 : 0);
         // launch trace: [lane][start | end][step][launch] globaltimer stamps, reset per call
         trace_per_step = 0;
         if (tracing) {
@@ -1632,7 +1667,7 @@ int sb_decode_trace(sb_engine* e, const float* mel_windows, int n_windows, const
     X(sb_params, language) X(sb_params, translate) X(sb_params, initial_prompt) X(sb_params, no_timestamps)             \
     X(sb_params, suppress_blank) X(sb_params, single_segment) X(sb_params, max_initial_ts) X(sb_params, n_max_tokens)   \
     X(sb_params, max_windows) X(sb_params, n_max_text_ctx) X(sb_params, temperature) X(sb_params, temperature_inc)            \
-    X(sb_params, logprob_thold) X(sb_params, entropy_thold)                                                              \
+    X(sb_params, logprob_thold) X(sb_params, entropy_thold) X(sb_params, suppress_nst)                                   \
     X(sb_window_info, seek) X(sb_window_info, n_tokens) X(sb_window_info, result_len) X(sb_window_info, seek_delta)     \
     X(sb_window_info, failed) X(sb_window_info, token_offset) X(sb_window_info, n_prompt) X(sb_window_info, temperature)  \
     X(sb_window_info, n_attempts) X(sb_window_info, avg_logprob)                               \

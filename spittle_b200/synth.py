@@ -287,6 +287,22 @@ def ensure_model_file(arch: str, directory: str, seed: int = 42, recipe: str = "
     return path
 
 
+def with_non_speech_vocab(model, ids):
+    """A copy of `model` whose vocabulary entries at `ids` are whisper.cpp's non-speech strings ('(', ' (', the music notes, ...,
+    ' -', " '"): the synthetic vocabulary is plain ASCII words, so suppress_nst would have nothing to suppress.  `ids` are
+    usually the tokens a decode emits WITHOUT the rule, so that switching it on has to change the result."""
+    import dataclasses
+    from oracle.whisper_ref import NON_SPEECH_TOKENS          # test helper only: the product never imports the oracle
+    words = []
+    for t in NON_SPEECH_TOKENS:
+        words += [t.encode("utf-8"), (" " + t).encode("utf-8")]
+    words += [b" -", b" '"]
+    vocab = list(model.vocab)
+    for i, w in zip(ids, words):
+        vocab[i] = w
+    return dataclasses.replace(model, vocab=vocab)
+
+
 __all__ = ["make_clip", "mel_filterbank", "make_synthetic_model", "ensure_model_file",
            "synthetic_vocab", "sinusoids", "tone", "chirp", "noise_burst", "vowel_like",
            "read_ggml", "SAMPLE_RATE"]

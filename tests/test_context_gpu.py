@@ -335,3 +335,36 @@ def test_prompt_prefill_equals_token_by_token_feed(nano):
     toks = capi.Engine(path, max_batch=1).tokenize(prompt)
     _, _, wins = oracle.full(clips[1], whisper_ref.DecodeConfig(n_max_override=24, initial_prompt_tokens=toks), max_windows=3)
     _compare_windows(fast[1], wins, "prefill vs oracle")
+
+
+def test_suppress_nst_matches_oracle(nano, model_dir):
+    """whisper_full_params.suppress_nst (transcribe-rs: suppress_non_speech_tokens): non-speech strings planted on the tokens the
+    unconstrained decode emits; with the rule on the engine must avoid them and follow the oracle."""
+    import os
+    path, model, oracle = nano
+    x = synth.make_clip(3, 30.0)
+    mel, n_len_org = logmel.logmel_f64(x, model.mel_filters)
+    enc = oracle.encode(logmel.mel_window(mel, 0))
+    n = 48
+    base = oracle.decode_window(enc, 0, n_len_org, whisper_ref.DecodeConfig(n_max_override=n))
+    planted = sorted({t for t in base.tokens if t < model.special.eot})
+    m2 = synth.with_non_speech_vocab(model, planted)
+    p2 = os.path.join(model_dir, "ggml-synth-nano-nst-test.bin")
+    ggml_format.write_ggml(p2, m2)
+    o2 = whisper_ref.WhisperOracle(m2, act_f16=True)
+    eng = capi.Engine(p2, dtype=capi.SB_DTYPE_F16, max_batch=2)
+    try:
+        n_exact = 0
+        for flag in (0, 1):
+            r = eng.transcribe(x, capi.default_params(n_max_tokens=n, max_windows=1, suppress_nst=flag))
+            w = o2.decode_window(enc, 0, n_len_org, whisper_ref.DecodeConfig(n_max_override=n, suppress_nst=bool(flag)))
+            # identical tokens, or a first divergence at an indecisive oracle margin (f16 engine): _compare_windows asserts that
+            n_exact += _compare_windows(r, [w], f"suppress_nst={flag}")
+            got = r.sampled[: r.windows[0]["n_tokens"]]
+            if flag:
+                assert not (set(got) & set(planted)) and not (set(w.tokens) & set(planted)) and got != base.tokens
+            else:
+                assert w.tokens == base.tokens and set(got) & set(planted)
+        print(f"suppress_nst: {n_exact} of 2 decodes token-exact against the oracle")
+    finally:
+        eng.close()

@@ -108,3 +108,38 @@ def test_english_only_model(built, model_dir):
     if got["windows"][0]["tokens"] != wins[0].tokens:
         first = next(i for i in range(len(wins[0].tokens)) if got["windows"][0]["tokens"][i] != wins[0].tokens[i])
         assert wins[0].margins[first] < 6e-2
+
+
+def test_suppress_nst_numpy_oracle_and_cpu_ref(built, model_dir, tmp_path):
+    """whisper_full_params.suppress_nst: the ids of whisper.cpp's non-speech strings get -inf in whisper_process_logits.  The
+    synthetic vocabulary has none of them, so they are planted on the tokens an unconstrained decode emits; with the rule on
+    the decode must avoid them, and the two restatements must agree."""
+    path, model, oracle, ref = _load("nano", model_dir)
+    assert whisper_ref.non_speech_token_ids(model.vocab) == []
+    toy = [b"a", b"(", b" (", b" -", b"-", b" '", "\u266a".encode(), b" \xe2\x99\xaa", b"))", b"x))"]
+    assert whisper_ref.non_speech_token_ids(toy) == [1, 2, 3, 5, 6, 7, 8]
+    x = synth.make_clip(1, 30.0)
+    mel, n_len_org = logmel.logmel_f32_faithful(x, model.mel_filters)
+    enc = oracle.encode(logmel.mel_window(mel, 0))
+    n = 24
+    base = oracle.decode_window(enc, 0, n_len_org, whisper_ref.DecodeConfig(n_max_override=n))
+    sp = model.special
+    planted = sorted({t for t in base.tokens if t < sp.eot})
+    assert len(planted) >= 8
+    m2 = synth.with_non_speech_vocab(model, planted)
+    p2 = str(tmp_path / "nano-nst.bin")
+    ggml_format.write_ggml(p2, m2)
+    o2 = whisper_ref.WhisperOracle(m2, act_f16=True)
+    assert set(o2.nst_ids.tolist()) == set(planted[:110])
+    off = o2.decode_window(enc, 0, n_len_org, whisper_ref.DecodeConfig(n_max_override=n))
+    on = o2.decode_window(enc, 0, n_len_org, whisper_ref.DecodeConfig(n_max_override=n, suppress_nst=True))
+    assert off.tokens == base.tokens                         # the vocabulary strings alone change nothing
+    assert on.tokens != off.tokens and not (set(on.tokens) & set(planted))
+    r2 = cpu_ref.CpuRef(p2, n_threads=4)
+    c_on = r2.decode_window(enc, 0, n_len_org, n_max_override=n, suppress_nst=True)
+    c_off = r2.decode_window(enc, 0, n_len_org, n_max_override=n)
+    assert c_off["tokens"] == off.tokens or min(off.margins) < 6e-2
+    if c_on["tokens"] != on.tokens:
+        first = next(i for i in range(min(len(c_on["tokens"]), len(on.tokens))) if c_on["tokens"][i] != on.tokens[i])
+        assert on.margins[first] < 6e-2
+    assert not (set(c_on["tokens"]) & set(planted))
