@@ -18,9 +18,6 @@
 
 namespace sb {
 extern std::atomic<uint64_t> g_launches;
-// profiling knob (tools/ab_decode.sh): SB_DBG_SKIP bit mask drops whole stage classes from the step (1 cross-attention,
-// 2 projections, 4 LayerNorm, 8 self-attention) -- results are garbage, the point is the time of what is left
-static int dbg_skip() { static int v = getenv("SB_DBG_SKIP") ? atoi(getenv("SB_DBG_SKIP")) : 0; return v; }
 
 // ------------------------------------------------------------------------------------------
 // stand-alone launches of the shared stage bodies (decoder_bodies.cuh), chained with PDL
@@ -617,14 +614,11 @@ int prefill_kv_scatter(const T* qkv, const int* row_slot, const int* row_pos, T*
 template <typename T>
 int skinny_gemm(const T* X, int ldx, const T* W, int ldw, int Bn, int N, int K, const SkinnyEpilogue& ep, cudaStream_t st) {
     SB_CHECK_ARG(K % 32 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "skinny gemm: K % 32 and 16-byte row alignment required");
-    if (dbg_skip() & 2) return SB_OK;
-    static const int w32_min_n = [] { const char* e = getenv("SB_DEC_W32_MIN_N"); return e ? atoi(e) : 2048; }();
-    static const bool narrow_ok = [] { const char* e = getenv("SB_DEC_NARROW"); return e ? atoi(e) != 0 : true; }();
+    constexpr int w32_min_n = 2048;                 // 32-row weight tiles for the wide projections (QKV, FC1, logits)
     SkinnyEpilogue ept = ep; ept.trace = g_trace_next; g_trace_next = TraceSlot();
-    const bool narrow = narrow_ok && Bn <= 32;      // 32-sequence blocks (half the registers) for a decode lane of <= 32
+    const bool narrow = Bn <= 32;      // 32-sequence blocks (half the registers) for a decode lane of <= 32
     const int chunks = ceil_div(Bn, narrow ? 32 : 64);
-    static const int narrow_w32_env = [] { const char* e = getenv("SB_DEC_NARROW_W32"); return e ? atoi(e) : -1; }();
-    const bool narrow_w32 = narrow_w32_env >= 0 ? narrow_w32_env != 0 : K >= 1024;
+    const bool narrow_w32 = K >= 1024;
     if (N >= w32_min_n && narrow && narrow_w32) {
         SB_ONCE_PER_DEVICE({ SB_CUDA_CHECK(cudaFuncSetAttribute(k_skinny_gemm_w32n<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkinnySmem)); });
         launch_pdl(k_skinny_gemm_w32n<T>, dim3(ceil_div(N, 32), chunks), dim3(256), (size_t)kSkinnySmem, st, X, ldx, W, ldw, Bn, N, K, ept);
@@ -651,7 +645,6 @@ int dec_ln(float* x, const float* gamma, const float* beta, T* out16, int rows, 
            const int* next_tokens, const SeqState* state, cudaStream_t st) {
     SB_CHECK_ARG(d % 4 == 0 && d <= 1536, "decoder layernorm: d % 4, d <= 1536");
     const TraceSlot ts = g_trace_next; g_trace_next = TraceSlot();
-    if (dbg_skip() & 4) return SB_OK;
     if (d <= 768) launch_pdl(k_dec_ln<T, 6>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, state, ts);
     else if (d <= 1280) launch_pdl(k_dec_ln<T, 10>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, state, ts);
     else launch_pdl(k_dec_ln<T, 12>, dim3(rows), dim3(32), 0, st, x, gamma, beta, out16, d, tok_emb, pos_emb, next_tokens, state, ts);
@@ -664,7 +657,6 @@ int dec_self_attn(const T* qkv, T* kc, T* vc, T* out, const SeqState* state, int
                   int n_text_ctx, cudaStream_t st, const int* row_slot, const int* row_pos) {
     SB_CHECK_ARG(n_text_ctx <= 448 && d == n_head * 64, "self attention: n_text_ctx <= 448, d_head 64");
     const TraceSlot ts = g_trace_next; g_trace_next = TraceSlot();
-    if (dbg_skip() & 8) return SB_OK;
     if (row_slot) k_dec_self_attn<T><<<dim3(n_head, Bn), dim3(128), 0, st>>>(qkv, kc, vc, out, state, honor_done, n_head, d, n_text_ctx, ts, row_slot, row_pos);
     else launch_pdl(k_dec_self_attn<T>, dim3(n_head, Bn), dim3(128), 0, st, qkv, kc, vc, out, state, honor_done, n_head, d, n_text_ctx, ts, row_slot, row_pos);
     g_launches += 1;
@@ -677,7 +669,6 @@ int dec_cross_attn(const T* q, int ldq, const T* kbase, const T* vbase, int64_t 
     SB_CHECK_ARG(n_ctx <= 1504 && d == n_head * 64 && d <= 1504 && d % 32 == 0 && ldq % 8 == 0 && ld_kv % 8 == 0,
                  "cross attention: n_audio_ctx, d <= 1504, d_head 64, 16-byte aligned rows");
     const TraceSlot ts = g_trace_next; g_trace_next = TraceSlot();
-    if (dbg_skip() & 1) return SB_OK;
     dim3 grid(n_head, Bn);
     if (row_slot) k_dec_cross_attn<T><<<grid, dim3(256), 0, st>>>(q, ldq, kbase, vbase, ld_kv, win_stride, out, state, d, n_ctx, ts, row_slot);
     else launch_pdl(k_dec_cross_attn<T>, grid, dim3(256), 0, st, q, ldq, kbase, vbase, ld_kv, win_stride, out, state, d, n_ctx, ts, row_slot);

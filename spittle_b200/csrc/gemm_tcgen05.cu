@@ -434,7 +434,7 @@ int gemm_tn(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, i
     SB_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm: K and N must be multiples of 8");
     SB_CHECK_ARG(ep.out_f32 ? (ep.ldo % 4 == 0) : (ep.ldo % 8 == 0), "gemm: output row stride alignment");
     // CTA pairs (cta_group::2, 256x256 tiles) when there are enough rows to fill the machine with them
-    static const int pair_min_m = [] { const char* e = getenv("SB_GEMM_PAIR_MIN_M"); return e ? atoi(e) : 4096; }();
+    constexpr int pair_min_m = 4096;
     const bool pair = M >= pair_min_m;
     CUtensorMap ta, tb;
     int rc = make_tmap_2d(&ta, A, dtype, M, K, lda, kBM);
