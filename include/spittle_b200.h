@@ -92,6 +92,7 @@ SB_API int sb_logmel_batch_dev(const sb_melplan* plan, const float* pcm, int n_c
  * Integer decimation ratios (96 / 64 / 48 / 32 kHz) run the polyphase tensor-core kernel, 16 kHz passes through, every other
  * rate (44.1 / 22.05 / 11.025 / 8 kHz ...) applies rubato's block operator as a dense split-precision GEMM; that path keeps a
  * device workspace inside the resampler object, so concurrent calls on ONE object must be issued on one stream.
+ * Samples are audio in [-1, 1]; the tensor-core paths split them into two f16 halves, so |x| must stay below 65504.
  * ---------------------------------------------------------------------------------- */
 typedef struct sb_resampler sb_resampler;
 SB_API int sb_resampler_create(int fs_in, int fs_out, sb_resampler** out);
