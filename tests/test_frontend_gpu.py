@@ -176,6 +176,22 @@ def test_frontend_is_deterministic(cuda_dev):
         assert torch.equal(sv.score(f0), p0)
 
 
+@pytest.mark.parametrize("n_streams,n_frames", [(1, 1), (1, 5), (9, 3), (3, 33)])
+def test_silero_ragged_shapes(cuda_dev, n_streams, n_frames):
+    """Frame counts that are not multiples of the kernels' tiles (4 frames per CTA in the front, 32 in the conv blocks) and stream
+    counts that are not multiples of the LSTM's 8 streams per CTA."""
+    import torch
+    w = silero_weights.load_npz(SILERO)
+    clips = np.stack([synth.make_clip(80 + i, seconds=(n_frames * 480 + 7) / 16000.0, kind=["vowel", "noise", "mix"][i % 3])
+                      for i in range(n_streams)])
+    frames = torch.from_numpy(clips[:, : n_frames * 480].copy()).cuda().view(n_streams, n_frames, 480)
+    probs = audio_toolkit.SileroVad(SILERO, 0.3).score(frames).cpu().numpy()
+    assert probs.shape == (n_streams, n_frames)
+    for s_ in range(n_streams):
+        ref = silero.SileroOracle(w).score(clips[s_, : n_frames * 480])
+        assert np.abs(probs[s_] - ref).max() <= SILERO_TOL, (s_, np.abs(probs[s_] - ref).max())
+
+
 def test_gate_is_bit_exact(cuda_dev):
     import torch
     vad = audio_toolkit.SileroVad(SILERO, 0.3)
