@@ -192,6 +192,31 @@ def test_silero_ragged_shapes(cuda_dev, n_streams, n_frames):
         assert np.abs(probs[s_] - ref).max() <= SILERO_TOL, (s_, np.abs(probs[s_] - ref).max())
 
 
+def test_silero_full_size_properties(cuda_dev):
+    """Size-independent properties at the C5 stream length (30 s = 1000 frames): a stream's probabilities do not depend on which
+    other streams share the batch (bit-identical alone and inside a batch of 11), and two calls over the halves of the stream
+    equal one call over the whole (the LSTM state is carried like vad-rs does between compute() calls)."""
+    import torch
+    kinds = ["vowel", "noise", "mix", "tone", "chirp"]
+    clips = np.stack([synth.make_clip(90 + i, seconds=30.0, kind=kinds[i % 5]) for i in range(11)])
+    frames = torch.from_numpy(clips).cuda().view(11, 1000, 480)
+    sv = audio_toolkit.SileroVad(SILERO, 0.3)
+    whole = sv.score(frames)
+    assert whole.shape == (11, 1000) and bool(torch.isfinite(whole).all()) and float(whole.min()) >= 0.0 and float(whole.max()) <= 1.0
+    for s_ in (0, 4, 10):
+        sv.reset()
+        alone = sv.score(frames[s_: s_ + 1].contiguous())
+        assert torch.equal(alone[0], whole[s_]), s_
+    sv.reset()
+    a = sv.score(frames[:, :517].contiguous())
+    b = sv.score(frames[:, 517:].contiguous())
+    assert float((torch.cat([a, b], dim=1) - whole).abs().max()) < 1e-6
+    # one stream against the f64 oracle over the full 30 s
+    w = silero_weights.load_npz(SILERO)
+    ref = silero.SileroOracle(w).score(clips[2])
+    assert np.abs(whole[2].cpu().numpy() - ref).max() <= SILERO_TOL
+
+
 def test_gate_is_bit_exact(cuda_dev):
     import torch
     vad = audio_toolkit.SileroVad(SILERO, 0.3)
