@@ -90,7 +90,8 @@ SB_API int sb_logmel_batch_dev(const sb_melplan* plan, const float* pcm, int n_c
  * of push(everything) + finish(): the input is zero-padded to whole 1024-sample chunks, only whole
  * rubato blocks (1026 -> 342 at 48 -> 16 kHz) are produced, the last 480-sample frame is zero padded.
  * Integer decimation ratios (96 / 64 / 48 / 32 kHz) run the polyphase tensor-core kernel, 16 kHz passes through, every other
- * rate (44.1 / 22.05 / 11.025 / 8 kHz ...) applies rubato's block operator as a dense split-precision GEMM; that path keeps a
+ * rate (44.1 / 24 / 22.05 / 12 / 11.025 / 8 kHz ...) applies rubato's block operator as a dense split-precision GEMM (rates whose
+ * operator would exceed 64 M entries, e.g. a prime input rate, return SB_ERR_UNSUPPORTED); that path keeps a
  * device workspace inside the resampler object, so concurrent calls on ONE object must be issued on one stream.
  * Samples are audio in [-1, 1]; the tensor-core paths split them into two f16 halves, so |x| must stay below 65504.
  * ---------------------------------------------------------------------------------- */

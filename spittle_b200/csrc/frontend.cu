@@ -219,7 +219,7 @@ __global__ void k_resample_dense_matrix(const double2* __restrict__ filt, int N1
     const int kk = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
     if (kk >= Kp) return;
     double a = 0.0;
-    if (kk < 2 * N1) {
+    if (kk < 2 * N1 && m < N2) {                      // rows N2 .. N2p-1 pad the GEMM's N to a multiple of 8
         const int row = kk < N1 ? N2 + m : m, j = kk < N1 ? kk : kk - N1;
         // phase of bin k: 2 pi k (row N1 - j N2) / (2 N1 N2), reduced exactly in integers
         const long long P = 2LL * N1 * N2;
@@ -264,11 +264,11 @@ __global__ void k_resample_dense_rows(const float* __restrict__ x, int64_t x_str
 }
 
 // out[stream][b N2 + m] = C[(stream, b)][m] / scale
-__global__ void k_resample_dense_store(const float* __restrict__ c, int n_blocks, int N2, float* __restrict__ out, int64_t out_stride) {
+__global__ void k_resample_dense_store(const float* __restrict__ c, int n_blocks, int N2, int N2p, float* __restrict__ out, int64_t out_stride) {
     const int row = blockIdx.x;
     const int stream = row / n_blocks, b = row - stream * n_blocks;
     float* dst = out + (int64_t)stream * out_stride + (int64_t)b * N2;
-    for (int m = threadIdx.x; m < N2; m += blockDim.x) dst[m] = c[(size_t)row * N2 + m] * (1.0f / kRdScale);
+    for (int m = threadIdx.x; m < N2; m += blockDim.x) dst[m] = c[(size_t)row * N2p + m] * (1.0f / kRdScale);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1340,7 +1340,7 @@ struct sb_resampler {
     int Q = 0, SP = 0;             // taps per branch, k-steps per branch
     // rational ratios: the block operator as a dense GEMM (k_resample_dense_*)
     bool dense = false;
-    int N1 = 0, N2 = 0, Kp = 0;
+    int N1 = 0, N2 = 0, N2p = 0, Kp = 0;   // N2p: N2 rounded up to a multiple of 8 (GEMM N)
     __half *d_whi = nullptr, *d_wlo = nullptr;
     mutable void* d_ws = nullptr;  // X hi | X lo | C of one chunk of streams, grown on demand
     mutable size_t ws_bytes = 0;
@@ -1373,9 +1373,9 @@ int sb_resampler_create(int fs_in, int fs_out, sb_resampler** out) {
     if (r->dense) {
         // any other ratio (44.1 / 22.05 / 11.025 / 8 kHz ...): the block operator as a dense matrix, see k_resample_dense_matrix
         const int N1 = r->fft_in, N2 = r->fft_out, L = N1 < N2 ? N1 + 1 : N2;
-        if (N2 % 8 != 0 || (size_t)N2 * 2 * N1 > (size_t)64 << 20) {
+        if ((size_t)N2 * 2 * N1 > (size_t)64 << 20) {
             delete r;
-            sb::set_error("resampler: this ratio gives a block operator the dense path does not take (fft_size_out must be a multiple of 8)");
+            sb::set_error("resampler: this ratio gives a block operator of more than 64 M entries (fft_size_in x fft_size_out); not taken");
             return SB_ERR_UNSUPPORTED;
         }
         const float cutoff_f = N1 > N2 ? powf(0.4f, 16.0f / (float)N2) * (float)N2 / (float)N1 : powf(0.4f, 16.0f / (float)N1);
@@ -1400,13 +1400,13 @@ int sb_resampler_create(int fs_in, int fs_out, sb_resampler** out) {
             }
             filt[2 * k] = re / sum / (2.0 * N1); filt[2 * k + 1] = im / sum / (2.0 * N1);
         }
-        r->N1 = N1; r->N2 = N2; r->Kp = (2 * N1 + 31) & ~31;
+        r->N1 = N1; r->N2 = N2; r->N2p = (N2 + 7) & ~7; r->Kp = (2 * N1 + 31) & ~31;
         double2* d_filt = nullptr;
         SB_CUDA_CHECK(cudaMalloc(&d_filt, filt.size() * sizeof(double)));
         SB_CUDA_CHECK(cudaMemcpy(d_filt, filt.data(), filt.size() * sizeof(double), cudaMemcpyHostToDevice));
-        SB_CUDA_CHECK(cudaMalloc(&r->d_whi, (size_t)N2 * r->Kp * sizeof(__half)));
-        SB_CUDA_CHECK(cudaMalloc(&r->d_wlo, (size_t)N2 * r->Kp * sizeof(__half)));
-        dim3 grid((r->Kp + 127) / 128, N2);
+        SB_CUDA_CHECK(cudaMalloc(&r->d_whi, (size_t)r->N2p * r->Kp * sizeof(__half)));
+        SB_CUDA_CHECK(cudaMalloc(&r->d_wlo, (size_t)r->N2p * r->Kp * sizeof(__half)));
+        dim3 grid((r->Kp + 127) / 128, r->N2p);
         sb::k_resample_dense_matrix<<<grid, 128>>>(d_filt, N1, N2, L, r->Kp, r->d_whi, r->d_wlo);
         SB_CUDA_CHECK(cudaGetLastError());
         SB_CUDA_CHECK(cudaDeviceSynchronize());
@@ -1504,10 +1504,10 @@ int sb_resample_dev(const sb_resampler* r, const float* in, int64_t in_stride, s
     if (n_out == 0) return SB_OK;
     if (r->dense) {
         std::lock_guard<std::mutex> lock(r->ws_mu);
-        const int N1 = r->N1, N2 = r->N2, Kp = r->Kp;
+        const int N1 = r->N1, N2 = r->N2, N2p = r->N2p, Kp = r->Kp;
         const int n_blocks = (int)(n_out / (size_t)N2);
         // chunks of streams sized for <= ~1.5 GB of workspace: X hi | X lo (rows x Kp f16 each) | C (rows x N2 f32)
-        const size_t row_bytes = (size_t)Kp * 2 * sizeof(__half) + (size_t)N2 * sizeof(float);
+        const size_t row_bytes = (size_t)Kp * 2 * sizeof(__half) + (size_t)N2p * sizeof(float);
         int per_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_streams, ((size_t)1536 << 20) / (row_bytes * (size_t)n_blocks)));
         const size_t need = row_bytes * (size_t)n_blocks * per_chunk;
         if (need > r->ws_bytes) {
@@ -1524,10 +1524,10 @@ int sb_resample_dev(const sb_resampler* r, const float* in, int64_t in_stride, s
             float* c = (float*)(xlo + (size_t)rows * Kp);
             sb::k_resample_dense_rows<<<rows, 256, 0, st>>>(in + (int64_t)s0 * in_stride, in_stride, (int)n_in, n_blocks, N1, Kp, xhi, xlo);
             int rc;
-            if ((rc = sb_gemm_tn_dev(SB_DTYPE_F16, xhi, Kp, r->d_whi, Kp, rows, N2, Kp, c, N2, 1, nullptr, 0, nullptr, 0, 0, st))) return rc;
-            if ((rc = sb_gemm_tn_dev(SB_DTYPE_F16, xhi, Kp, r->d_wlo, Kp, rows, N2, Kp, c, N2, 1, nullptr, 0, c, N2, 0, st))) return rc;
-            if ((rc = sb_gemm_tn_dev(SB_DTYPE_F16, xlo, Kp, r->d_whi, Kp, rows, N2, Kp, c, N2, 1, nullptr, 0, c, N2, 0, st))) return rc;
-            sb::k_resample_dense_store<<<rows, 256, 0, st>>>(c, n_blocks, N2, out + (int64_t)s0 * out_stride, out_stride);
+            if ((rc = sb_gemm_tn_dev(SB_DTYPE_F16, xhi, Kp, r->d_whi, Kp, rows, N2p, Kp, c, N2p, 1, nullptr, 0, nullptr, 0, 0, st))) return rc;
+            if ((rc = sb_gemm_tn_dev(SB_DTYPE_F16, xhi, Kp, r->d_wlo, Kp, rows, N2p, Kp, c, N2p, 1, nullptr, 0, c, N2p, 0, st))) return rc;
+            if ((rc = sb_gemm_tn_dev(SB_DTYPE_F16, xlo, Kp, r->d_whi, Kp, rows, N2p, Kp, c, N2p, 1, nullptr, 0, c, N2p, 0, st))) return rc;
+            sb::k_resample_dense_store<<<rows, 256, 0, st>>>(c, n_blocks, N2, N2p, out + (int64_t)s0 * out_stride, out_stride);
             sb::g_launches += 2;
         }
         SB_CUDA_CHECK(cudaGetLastError());

@@ -48,7 +48,7 @@ def test_resampler_matches_rubato_oracle(cuda_dev):
 def test_resampler_rational_ratios(cuda_dev):
     """44.1 / 22.05 / 11.025 / 8 kHz capture devices: rubato's FftFixedIn block operator (1323 -> 480 samples at 44.1 kHz) as a dense
     split-precision GEMM, against the f64 restatement of the block FFT algorithm (reference: resampler.rs:16-27 accepts any rate)."""
-    for fs in (44100, 22050, 11025, 8000):
+    for fs in (44100, 22050, 11025, 8000, 24000, 12000):     # 24 kHz: fft_size_out = 684 is not a multiple of 8 (padded GEMM)
         x = np.stack([synth.make_clip(50 + i, seconds=2.0, sr=fs, kind=k) for i, k in enumerate(["vowel", "noise", "mix"])])
         got = audio_toolkit.FrameResampler(fs, 16000).process(x).cpu().numpy()
         for s_ in range(3):
@@ -63,6 +63,9 @@ def test_resampler_rational_ratios(cuda_dev):
     for s_ in range(3):
         ref = resample.frame_resampler(x[s_], 44100, 16000)
         assert got[s_].shape == ref.shape and np.abs(got[s_] - ref).max() <= RESAMPLE_TOL
+    # a ratio whose block operator would not fit (47 999 Hz: 47 999 x 16 000 samples per block) fails loudly
+    with pytest.raises(capi.SbError):
+        audio_toolkit.FrameResampler(47999, 16000)
 
 
 def test_resampler_other_integer_ratios(cuda_dev):
